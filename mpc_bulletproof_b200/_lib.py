@@ -1,0 +1,74 @@
+"""ctypes binding of libbpgpu.so (include/bpgpu.h).
+
+The library is built in-tree by `__graft_entry__.build()`; if it is missing or no
+CUDA device is present every call fails loudly — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbpgpu.so")
+
+BPG_OK = 0
+BPG_ERR_ARG, BPG_ERR_LEN, BPG_ERR_POW2, BPG_ERR_CAPACITY = -1, -2, -3, -4
+BPG_ERR_DECODE, BPG_ERR_VERIFY, BPG_ERR_CUDA, BPG_ERR_NOMEM = -5, -6, -7, -8
+
+
+class BpgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libbpgpu error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+_P = ctypes.c_void_p
+_SZ = ctypes.c_size_t
+_I = ctypes.c_int
+
+_SIGNATURES = {
+    "bpg_init": (_I, [_I, ctypes.POINTER(_P)]),
+    "bpg_free": (None, [_P]),
+    "bpg_set_stream": (_I, [_P, _P]),
+    "bpg_sync": (_I, [_P]),
+    "bpg_strerror": (ctypes.c_char_p, [_I]),
+    "bpg_last_cuda_error": (_I, [_P]),
+    "bpg_launch_count": (ctypes.c_uint64, [_P]),
+    "bpg_set_window": (_I, [_P, _I]),
+    "bpg_table_upload": (_I, [_P, _P, _SZ, ctypes.POINTER(_P)]),
+    "bpg_table_upload_dev": (_I, [_P, _P, _SZ, ctypes.POINTER(_P)]),
+    "bpg_table_len": (_SZ, [_P]),
+    "bpg_table_free": (None, [_P]),
+    "bpg_msm": (_I, [_P, _P, _P, _SZ, _P]),
+    "bpg_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),
+    "bpg_dev_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),
+    "bpg_dev_sum_encode": (_I, [_P, _P, _I, _I, _P, _P]),
+}
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no fallback implementation."
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code: int):
+    if code != BPG_OK:
+        raise BpgError(code, lib().bpg_strerror(code).decode())

@@ -1,0 +1,107 @@
+"""Host-side mirror of the group-level seam of the reference:
+`StarkPoint::msm_iter(scalars, points)` (reference src/inner_product_proof.rs:90,
+src/r1cs/verifier.rs:516) becomes `msm(ctx, scalars, points)`; generator tables
+(`BulletproofGens`, reference src/generators.rs:158-235) become `Table`.
+Arguments are bytes (32-byte little-endian scalars, 32-byte compressed points).
+"""
+from __future__ import annotations
+
+import ctypes
+
+from . import _lib
+from ._lib import check, lib
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self._h = ctypes.c_void_p()
+        check(lib().bpg_init(device, ctypes.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().bpg_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None):
+        check(lib().bpg_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+
+    def sync(self):
+        check(lib().bpg_sync(self._h))
+
+    def set_window(self, c: int):
+        check(lib().bpg_set_window(self._h, c))
+
+    @property
+    def launches(self) -> int:
+        return int(lib().bpg_launch_count(self._h))
+
+
+class Table:
+    """Points resident in HBM in affine-Niels form."""
+
+    def __init__(self, ctx: Context, points: bytes | None = None, *, dev_ptr: int | None = None, n: int | None = None):
+        self.ctx = ctx
+        self._h = ctypes.c_void_p()
+        if points is not None:
+            assert len(points) % 32 == 0
+            check(lib().bpg_table_upload(ctx._h, points, len(points) // 32, ctypes.byref(self._h)))
+        else:
+            check(lib().bpg_table_upload_dev(ctx._h, ctypes.c_void_p(dev_ptr), n, ctypes.byref(self._h)))
+
+    def __len__(self):
+        return int(lib().bpg_table_len(self._h))
+
+    def close(self):
+        if self._h:
+            lib().bpg_table_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def msm(self, scalars: bytes, n_sets: int = 1, offset: int = 0, n: int | None = None) -> list[bytes]:
+        """out[s] = sum_i scalars[s*n+i] * table[offset+i]; host buffers."""
+        if n is None:
+            n = len(self) - offset
+        if len(scalars) != 32 * n * n_sets:
+            raise _lib.BpgError(_lib.BPG_ERR_LEN, "scalar buffer length does not match n * n_sets")
+        out = ctypes.create_string_buffer(32 * n_sets)
+        check(lib().bpg_msm_table(self.ctx._h, self._h, offset, n, scalars, n_sets, out))
+        return [out.raw[32 * i : 32 * i + 32] for i in range(n_sets)]
+
+    def dev_msm(self, d_scalars: int, n_sets: int, d_out_ext: int, offset: int = 0, n: int | None = None):
+        """Device-resident form; enqueues on the context's stream."""
+        if n is None:
+            n = len(self) - offset
+        check(
+            lib().bpg_dev_msm_table(
+                self.ctx._h, self._h, offset, n, ctypes.c_void_p(d_scalars), n_sets, ctypes.c_void_p(d_out_ext)
+            )
+        )
+
+
+def msm(ctx: Context, scalars: bytes, points: bytes) -> bytes:
+    """sum_i scalars[i] * points[i] -> 32-byte compressed point."""
+    if len(scalars) != len(points) or len(scalars) % 32:
+        raise _lib.BpgError(_lib.BPG_ERR_LEN, "scalars and points differ in length")
+    out = ctypes.create_string_buffer(32)
+    check(lib().bpg_msm(ctx._h, scalars, points, len(scalars) // 32, out))
+    return out.raw
+
+
+def dev_sum_encode(ctx: Context, d_parts: int, n_parts: int, n_sets: int, d_out_bytes: int | None, d_out_ext: int | None = None):
+    check(
+        lib().bpg_dev_sum_encode(
+            ctx._h, ctypes.c_void_p(d_parts), n_parts, n_sets, ctypes.c_void_p(d_out_bytes or 0), ctypes.c_void_p(d_out_ext or 0)
+        )
+    )

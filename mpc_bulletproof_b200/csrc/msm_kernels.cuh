@@ -1,0 +1,389 @@
+// Signed-digit windowed Pippenger multiscalar multiplication, sm_100a.
+//
+// Replaces `StarkPoint::msm_iter(scalars, points)` / `StarkPoint::msm(..)`
+// (reference call sites: src/inner_product_proof.rs:90-114,159-172,353;
+// src/r1cs/prover.rs:465-494,532-565; src/r1cs/verifier.rs:516-547) for the
+// ristretto255 instantiation.
+//
+// Pipeline for one launch (T terms, `nsets` independent output sums that share
+// one point table; term t belongs to set t / n_points unless set_ids is given):
+//   k_hist      digits of every scalar -> per-bucket counts (atomics)
+//   scan        exclusive prefix over the nsets*W*2^(c-1) buckets
+//   k_scatter   counting-sort of (bucket -> point index | sign) entries
+//   k_accum     one thread per bucket: 7-mul mixed additions from the Niels table
+//   k_accum_big block-cooperative path for over-long buckets (structured scalars)
+//   k_reduce    chunked running sums: sum_j j*B_j per (window, chunk)
+//   k_combine   tree over chunks -> one point per window
+//   k_horner    sum_w 2^(c w) S_w per set -> extended point (the partial sum a rank owns)
+// All arithmetic is exact modular integer work; results are group elements, so
+// any evaluation order gives the same canonical encoding.
+#pragma once
+#include "ge.cuh"
+#include "sc.cuh"
+
+namespace bpg {
+
+struct MsmCfg {
+  int c;              // window width in bits
+  int W;              // windows per scalar = ceil(254 / c)
+  uint32_t nb;        // buckets per window = 2^(c-1)
+  int nsets;          // independent sums in this launch
+  uint32_t n_terms;   // scalars in this launch
+  uint32_t n_points;  // implicit indexing: term t -> point t % n_points, set t / n_points
+  uint32_t nwin;      // nsets * W
+  uint32_t B;         // nwin * nb
+  uint32_t chunk;     // buckets per reduce chunk (power of two, <= nb)
+  uint32_t nchunks;   // nb / chunk
+  uint32_t big_thresh;  // buckets longer than this go to k_accum_big
+  uint32_t big_cap;     // capacity of the big-bucket list
+  sc_bias bias;
+};
+
+constexpr uint32_t ENTRY_NEG = 0x80000000u;
+
+// ---------------------------------------------------------------------------
+// digits -> histogram
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_hist(const uint32_t* __restrict__ scalars,
+                                              const uint8_t* __restrict__ set_ids, MsmCfg cfg,
+                                              uint32_t* __restrict__ counts) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cfg.n_terms) return;
+  sc k;
+  sc_load(k, scalars + (size_t)t * 8);
+  sc_recoded r = sc_recode(k.v, cfg.bias);
+  uint32_t set = set_ids ? set_ids[t] : t / cfg.n_points;
+  uint32_t base = set * cfg.W * cfg.nb;
+  for (int w = 0; w < cfg.W; w++) {
+    int d = sc_digit(r, w, cfg.c);
+    if (d != 0) {
+      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+      atomicAdd(&counts[base + (uint32_t)w * cfg.nb + mag - 1], 1u);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// exclusive scan of counts[B] -> offsets[B+1]; zeroes counts for reuse as cursors
+// ---------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;  // per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* smem /*[32+1]*/) {
+  // returns exclusive prefix of v across the block; *total = block sum
+  uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (uint32_t)o) x += y;
+  }
+  if (lane == 31) smem[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t nw = blockDim.x >> 5;
+    uint32_t s = lane < nw ? smem[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= (uint32_t)o) s += y;
+    }
+    if (lane < nw) smem[lane] = s;  // inclusive warp totals
+    if (lane == nw - 1) smem[32] = s;
+  }
+  __syncthreads();
+  uint32_t warp_base = wid ? smem[wid - 1] : 0;
+  *total = smem[32];
+  return warp_base + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* __restrict__ counts, uint32_t B,
+                                                             uint32_t* __restrict__ tile_sums) {
+  __shared__ uint32_t smem[33];
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    uint32_t idx = base + i;
+    s += idx < B ? counts[idx] : 0;
+  }
+  uint32_t total;
+  block_exclusive_scan(s, &total, smem);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of tile_sums[ntiles] in place; writes grand total to offsets[B]
+__global__ void __launch_bounds__(1024) k_scan_spine(uint32_t* __restrict__ tile_sums, uint32_t ntiles,
+                                                     uint32_t* __restrict__ offsets, uint32_t B) {
+  __shared__ uint32_t smem[33];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t start = 0; start < ntiles; start += blockDim.x) {
+    uint32_t i = start + threadIdx.x;
+    uint32_t v = i < ntiles ? tile_sums[i] : 0;
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(v, &total, smem);
+    uint32_t carry = carry_s;
+    if (i < ntiles) tile_sums[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[B] = carry_s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t* __restrict__ counts, uint32_t B,
+                                                             const uint32_t* __restrict__ tile_sums,
+                                                             uint32_t* __restrict__ offsets) {
+  __shared__ uint32_t smem[33];
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    uint32_t idx = base + i;
+    v[i] = idx < B ? counts[idx] : 0;
+    s += v[i];
+  }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(s, &total, smem) + tile_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    uint32_t idx = base + i;
+    if (idx < B) {
+      offsets[idx] = ex;
+      counts[idx] = 0;
+    }
+    ex += v[i];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// scatter entries into bucket order (order inside a bucket is irrelevant)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ scalars,
+                                                 const uint8_t* __restrict__ set_ids,
+                                                 const uint32_t* __restrict__ point_ids, MsmCfg cfg,
+                                                 const uint32_t* __restrict__ offsets,
+                                                 uint32_t* __restrict__ cursors, uint32_t* __restrict__ entries) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cfg.n_terms) return;
+  sc k;
+  sc_load(k, scalars + (size_t)t * 8);
+  sc_recoded r = sc_recode(k.v, cfg.bias);
+  uint32_t set = set_ids ? set_ids[t] : t / cfg.n_points;
+  uint32_t pid = point_ids ? point_ids[t] : t % cfg.n_points;
+  uint32_t base = set * cfg.W * cfg.nb;
+  for (int w = 0; w < cfg.W; w++) {
+    int d = sc_digit(r, w, cfg.c);
+    if (d != 0) {
+      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+      uint32_t b = base + (uint32_t)w * cfg.nb + mag - 1;
+      uint32_t pos = offsets[b] + atomicAdd(&cursors[b], 1u);
+      entries[pos] = pid | (d < 0 ? ENTRY_NEG : 0u);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// bucket accumulation: one thread per bucket
+// ---------------------------------------------------------------------------
+constexpr int ACC_THREADS = 128;
+
+__global__ void __launch_bounds__(ACC_THREADS) k_accum(const uint32_t* __restrict__ table,
+                                                        const uint32_t* __restrict__ offsets,
+                                                        const uint32_t* __restrict__ entries, MsmCfg cfg,
+                                                        uint32_t* __restrict__ bucket_sums,
+                                                        uint32_t* __restrict__ big_count,
+                                                        uint32_t* __restrict__ big_list) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= cfg.B) return;
+  uint32_t beg = offsets[b], end = offsets[b + 1];
+  if (end - beg > cfg.big_thresh) {
+    uint32_t slot = atomicAdd(big_count, 1u);
+    if (slot < cfg.big_cap) big_list[slot] = b;
+    return;
+  }
+  ge_ext acc = ge_identity();
+  for (uint32_t i = beg; i < end; i++) {
+    uint32_t e = __ldg(entries + i);
+    ge_niels q;
+    ge_load_niels(q, table + (size_t)(e & ~ENTRY_NEG) * 24);
+    acc = ge_madd(acc, q, (e & ENTRY_NEG) != 0);
+  }
+  ge_store_ext(bucket_sums + (size_t)b * 32, acc);
+}
+
+// over-long buckets: one block per bucket, strided accumulation + shared-memory tree
+constexpr int BIG_THREADS = 256;
+__global__ void __launch_bounds__(BIG_THREADS) k_accum_big(const uint32_t* __restrict__ table,
+                                                            const uint32_t* __restrict__ offsets,
+                                                            const uint32_t* __restrict__ entries, MsmCfg cfg,
+                                                            uint32_t* __restrict__ bucket_sums,
+                                                            const uint32_t* __restrict__ big_count,
+                                                            const uint32_t* __restrict__ big_list) {
+  __shared__ uint32_t sm[BIG_THREADS / 2][32];
+  uint32_t nbig = min(*big_count, cfg.big_cap);
+  for (uint32_t k = blockIdx.x; k < nbig; k += gridDim.x) {
+    uint32_t b = big_list[k];
+    uint32_t beg = offsets[b], end = offsets[b + 1];
+    ge_ext acc = ge_identity();
+    for (uint32_t i = beg + threadIdx.x; i < end; i += BIG_THREADS) {
+      uint32_t e = __ldg(entries + i);
+      ge_niels q;
+      ge_load_niels(q, table + (size_t)(e & ~ENTRY_NEG) * 24);
+      acc = ge_madd(acc, q, (e & ENTRY_NEG) != 0);
+    }
+    for (int half = BIG_THREADS / 2; half >= 1; half >>= 1) {
+      if (threadIdx.x >= (uint32_t)half && threadIdx.x < (uint32_t)(2 * half))
+        ge_store_ext(sm[threadIdx.x - half], acc);
+      __syncthreads();
+      if (threadIdx.x < (uint32_t)half) {
+        ge_ext o;
+        ge_load_ext(o, sm[threadIdx.x]);
+        acc = ge_add(acc, o);
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) ge_store_ext(bucket_sums + (size_t)b * 32, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// bucket reduction: per (window, chunk) compute sum_j (q*chunk + j + 1) * B_j
+// ---------------------------------------------------------------------------
+constexpr int RED_THREADS = 64;
+__global__ void __launch_bounds__(RED_THREADS) k_reduce(const uint32_t* __restrict__ bucket_sums, MsmCfg cfg,
+                                                         uint32_t* __restrict__ chunk_sums) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= cfg.nwin * cfg.nchunks) return;
+  uint32_t win = g / cfg.nchunks, q = g % cfg.nchunks;
+  const uint32_t* src = bucket_sums + ((size_t)win * cfg.nb + (size_t)q * cfg.chunk) * 32;
+  ge_ext run = ge_identity(), acc = ge_identity();
+  for (int j = (int)cfg.chunk - 1; j >= 0; j--) {
+    ge_ext bj;
+    ge_load_ext(bj, src + (size_t)j * 32);
+    run = ge_add(run, bj);
+    acc = ge_add(acc, run);
+  }
+  // + (q*chunk) * run, MSB-first double-and-add
+  uint32_t m = q * cfg.chunk;
+  if (m) {
+    ge_ext t = run;
+    int top = 31 - __clz(m);
+    for (int bit = top - 1; bit >= 0; bit--) {
+      t = ge_dbl(t);
+      if ((m >> bit) & 1u) t = ge_add(t, run);
+    }
+    acc = ge_add(acc, t);
+  }
+  ge_store_ext(chunk_sums + (size_t)g * 32, acc);
+}
+
+// one block per window: sum of its chunk sums
+constexpr int COMB_THREADS = 128;
+__global__ void __launch_bounds__(COMB_THREADS) k_combine(const uint32_t* __restrict__ chunk_sums, MsmCfg cfg,
+                                                           uint32_t* __restrict__ window_sums) {
+  __shared__ uint32_t sm[COMB_THREADS / 2][32];
+  uint32_t win = blockIdx.x;
+  const uint32_t* src = chunk_sums + (size_t)win * cfg.nchunks * 32;
+  ge_ext acc = ge_identity();
+  for (uint32_t i = threadIdx.x; i < cfg.nchunks; i += COMB_THREADS) {
+    ge_ext o;
+    ge_load_ext(o, src + (size_t)i * 32);
+    acc = ge_add(acc, o);
+  }
+  for (int half = COMB_THREADS / 2; half >= 1; half >>= 1) {
+    if (threadIdx.x >= (uint32_t)half && threadIdx.x < (uint32_t)(2 * half))
+      ge_store_ext(sm[threadIdx.x - half], acc);
+    __syncthreads();
+    if (threadIdx.x < (uint32_t)half) {
+      ge_ext o;
+      ge_load_ext(o, sm[threadIdx.x]);
+      acc = ge_add(acc, o);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ge_store_ext(window_sums + (size_t)win * 32, acc);
+}
+
+// one thread per set: Horner over windows, top window first
+__global__ void k_horner(const uint32_t* __restrict__ window_sums, MsmCfg cfg, uint32_t* __restrict__ out_ext) {
+  uint32_t set = blockIdx.x * blockDim.x + threadIdx.x;
+  if (set >= (uint32_t)cfg.nsets) return;
+  const uint32_t* src = window_sums + (size_t)set * cfg.W * 32;
+  ge_ext acc;
+  ge_load_ext(acc, src + (size_t)(cfg.W - 1) * 32);
+  for (int w = cfg.W - 2; w >= 0; w--) {
+    for (int i = 0; i < cfg.c; i++) acc = ge_dbl(acc);
+    ge_ext s;
+    ge_load_ext(s, src + (size_t)w * 32);
+    acc = ge_add(acc, s);
+  }
+  ge_store_ext(out_ext + (size_t)set * 32, acc);
+}
+
+// ---------------------------------------------------------------------------
+// finishing: sum `nparts` partial sums per set (one per rank), encode
+// ---------------------------------------------------------------------------
+// parts layout: [part][set][32 words]
+__global__ void k_sum_encode(const uint32_t* __restrict__ parts, int nparts, int nsets,
+                             uint8_t* __restrict__ out_bytes /*nsets*32*/,
+                             uint32_t* __restrict__ out_ext /*nsets*32 words, may be null*/) {
+  int set = blockIdx.x * blockDim.x + threadIdx.x;
+  if (set >= nsets) return;
+  ge_ext acc;
+  ge_load_ext(acc, parts + (size_t)set * 32);
+  for (int p = 1; p < nparts; p++) {
+    ge_ext o;
+    ge_load_ext(o, parts + ((size_t)p * nsets + set) * 32);
+    acc = ge_add(acc, o);
+  }
+  if (out_ext) ge_store_ext(out_ext + (size_t)set * 32, acc);
+  if (out_bytes) ge_encode(out_bytes + (size_t)set * 32, acc);
+}
+
+// ---------------------------------------------------------------------------
+// table construction: compressed ristretto -> affine Niels
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_decode_to_niels(const uint8_t* __restrict__ comp, uint32_t n,
+                                                          uint32_t* __restrict__ table,
+                                                          uint32_t* __restrict__ bad_count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t buf[32];
+  const uint4* src = reinterpret_cast<const uint4*>(comp + (size_t)i * 32);
+  uint4 a = src[0], b = src[1];
+  uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    buf[4 * k] = (uint8_t)w[k];
+    buf[4 * k + 1] = (uint8_t)(w[k] >> 8);
+    buf[4 * k + 2] = (uint8_t)(w[k] >> 16);
+    buf[4 * k + 3] = (uint8_t)(w[k] >> 24);
+  }
+  ge_ext p;
+  bool ok = ge_decode(p, buf);
+  ge_niels q;
+  if (ok) {
+    q = ge_affine_to_niels(p.X, p.Y);
+  } else {
+    q = ge_niels_identity();
+    atomicAdd(bad_count, 1u);
+  }
+  ge_store_niels(table + (size_t)i * 24, q);
+}
+
+// extended -> compressed, one thread per point
+__global__ void __launch_bounds__(128) k_encode(const uint32_t* __restrict__ ext, uint32_t n,
+                                                 uint8_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ge_ext p;
+  ge_load_ext(p, ext + (size_t)i * 32);
+  ge_encode(out + (size_t)i * 32, p);
+}
+
+}  // namespace bpg

@@ -1,0 +1,96 @@
+// TEST INFRASTRUCTURE — host build of the __host__ __device__ arithmetic in
+// mpc_bulletproof_b200/csrc/{fe,sc,ge}.cuh so that the limb schedules and the
+// Pippenger bookkeeping can be checked against oracle/ on a machine without a GPU.
+// Nothing in the product loads this library.
+#include <vector>
+#include <cstring>
+#include "../../mpc_bulletproof_b200/csrc/ge.cuh"
+#include "../../mpc_bulletproof_b200/csrc/sc.cuh"
+using namespace bpg;
+
+static fe ld(const uint32_t* p) { fe a; for (int i = 0; i < 8; i++) a.v[i] = p[i]; return a; }
+static void st(uint32_t* p, const fe& a) { for (int i = 0; i < 8; i++) p[i] = a.v[i]; }
+static ge_ext lde(const uint32_t* p) { ge_ext e; e.X = ld(p); e.Y = ld(p + 8); e.Z = ld(p + 16); e.T = ld(p + 24); return e; }
+static void ste(uint32_t* p, const ge_ext& e) { st(p, e.X); st(p + 8, e.Y); st(p + 16, e.Z); st(p + 24, e.T); }
+static ge_niels ldn(const uint32_t* p) { ge_niels e; e.ypx = ld(p); e.ymx = ld(p + 8); e.t2d = ld(p + 16); return e; }
+static void stn(uint32_t* p, const ge_niels& e) { st(p, e.ypx); st(p + 8, e.ymx); st(p + 16, e.t2d); }
+
+extern "C" {
+void hs_fe_mul(const uint32_t* a, const uint32_t* b, uint32_t* o) { st(o, fe_mul(ld(a), ld(b))); }
+void hs_fe_sq(const uint32_t* a, uint32_t* o) { st(o, fe_sq(ld(a))); }
+void hs_fe_add(const uint32_t* a, const uint32_t* b, uint32_t* o) { st(o, fe_add(ld(a), ld(b))); }
+void hs_fe_sub(const uint32_t* a, const uint32_t* b, uint32_t* o) { st(o, fe_sub(ld(a), ld(b))); }
+void hs_fe_canon(const uint32_t* a, uint32_t* o) { st(o, fe_canon(ld(a))); }
+void hs_fe_invert(const uint32_t* a, uint32_t* o) { st(o, fe_invert(ld(a))); }
+int hs_decode(const uint8_t* b, uint32_t* ext) { ge_ext e; bool ok = ge_decode(e, b); ste(ext, e); return ok; }
+void hs_encode(const uint32_t* ext, uint8_t* b) { ge_encode(b, lde(ext)); }
+void hs_to_niels(const uint32_t* ext, uint32_t* n) { stn(n, ge_to_niels(lde(ext))); }
+void hs_madd(const uint32_t* ext, const uint32_t* n, int neg, uint32_t* o) { ste(o, ge_madd(lde(ext), ldn(n), neg)); }
+void hs_add(const uint32_t* a, const uint32_t* b, uint32_t* o) { ste(o, ge_add(lde(a), lde(b))); }
+void hs_dbl(const uint32_t* a, uint32_t* o) { ste(o, ge_dbl(lde(a))); }
+void hs_neg(const uint32_t* a, uint32_t* o) { ste(o, ge_neg(lde(a))); }
+void hs_sc_montmul(const uint32_t* a, const uint32_t* b, uint32_t* o) {
+  sc x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); sc r = sc_montmul(x, y); memcpy(o, r.v, 32);
+}
+void hs_sc_mul(const uint32_t* a, const uint32_t* b, uint32_t* o) {
+  sc x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); sc r = sc_mul(x, y); memcpy(o, r.v, 32);
+}
+void hs_sc_add(const uint32_t* a, const uint32_t* b, uint32_t* o) {
+  sc x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); sc r = sc_add(x, y); memcpy(o, r.v, 32);
+}
+void hs_sc_sub(const uint32_t* a, const uint32_t* b, uint32_t* o) {
+  sc x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); sc r = sc_sub(x, y); memcpy(o, r.v, 32);
+}
+static sc_bias mk_bias(int c, int W) {
+  sc_bias b; memset(&b, 0, sizeof b);
+  for (int w = 0; w < W; w++) { int bit = c * w + c - 1; b.v[bit >> 5] |= 1u << (bit & 31); }
+  return b;
+}
+// digits[W] for scalar k with window c
+int hs_digits(const uint32_t* k, int c, int* digits) {
+  int W = (254 + c - 1) / c;
+  sc_recoded r = sc_recode(k, mk_bias(c, W));
+  for (int w = 0; w < W; w++) digits[w] = sc_digit(r, w, c);
+  return W;
+}
+// Serial walk through the same stages as msm_kernels.cuh (buckets -> chunked
+// running sums -> window combine -> Horner), with the same device functions.
+int hs_msm(const uint8_t* scalars, const uint8_t* points, int n, int c, int chunk, uint8_t* out) {
+  int W = (254 + c - 1) / c;
+  uint32_t nb = 1u << (c - 1);
+  if ((uint32_t)chunk > nb) chunk = nb;
+  sc_bias bias = mk_bias(c, W);
+  std::vector<ge_niels> tab(n);
+  for (int i = 0; i < n; i++) {
+    ge_ext e;
+    if (!ge_decode(e, points + 32 * i)) return -1;
+    tab[i] = ge_affine_to_niels(e.X, e.Y);
+  }
+  std::vector<ge_ext> wins(W);
+  for (int w = 0; w < W; w++) {
+    std::vector<ge_ext> B(nb, ge_identity());
+    for (int i = 0; i < n; i++) {
+      uint32_t k[8]; memcpy(k, scalars + 32 * i, 32);
+      int d = sc_digit(sc_recode(k, bias), w, c);
+      if (d) { uint32_t m = d < 0 ? -d : d; B[m - 1] = ge_madd(B[m - 1], tab[i], d < 0); }
+    }
+    ge_ext wsum = ge_identity();
+    for (uint32_t q = 0; q < nb / chunk; q++) {
+      ge_ext run = ge_identity(), acc = ge_identity();
+      for (int j = chunk - 1; j >= 0; j--) { run = ge_add(run, B[q * chunk + j]); acc = ge_add(acc, run); }
+      uint32_t m = q * chunk;
+      if (m) {
+        ge_ext t = run; int top = 31 - __builtin_clz(m);
+        for (int bit = top - 1; bit >= 0; bit--) { t = ge_dbl(t); if ((m >> bit) & 1) t = ge_add(t, run); }
+        acc = ge_add(acc, t);
+      }
+      wsum = ge_add(wsum, acc);
+    }
+    wins[w] = wsum;
+  }
+  ge_ext acc = wins[W - 1];
+  for (int w = W - 2; w >= 0; w--) { for (int i = 0; i < c; i++) acc = ge_dbl(acc); acc = ge_add(acc, wins[w]); }
+  ge_encode(out, acc);
+  return 0;
+}
+}

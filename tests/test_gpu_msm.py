@@ -1,0 +1,122 @@
+"""GPU parity: libbpgpu's MSM (through the C ABI) against the oracle.
+
+Bit-exact bar: the 32-byte ristretto255 encodings must be identical.
+Mirrors the reference's test idiom (random inputs, reference
+src/inner_product_proof.rs:474-505) and adds the edge vectors SURVEY.md §8c lists.
+"""
+import pytest
+
+from oracle import group as G
+from tests.util import points_bytes, rand_point, rand_scalar, rng, scalars_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, ks, ps):
+    from mpc_bulletproof_b200 import msm
+
+    got = msm(ctx, scalars_bytes(ks), points_bytes(ps))
+    want = G.msm(ks, ps).encode()
+    assert got == want, (got.hex(), want.hex())
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 64, 255, 1000])
+def test_msm_random(ctx, n):
+    r = rng(100 + n)
+    _check(ctx, [rand_scalar(r) for _ in range(n)], [rand_point(r) for _ in range(n)])
+
+
+def test_msm_4096(ctx):
+    r = rng(7)
+    n = 4096
+    _check(ctx, [rand_scalar(r) for _ in range(n)], [rand_point(r) for _ in range(n)])
+
+
+def test_msm_edge_scalars(ctx):
+    r = rng(11)
+    ks = [0, 1, G.L - 1, 2**252, 2**252 + 1, G.L - 2, 2, 2**128, 2**251, (1 << 252) - 1]
+    ps = [rand_point(r) for _ in ks]
+    _check(ctx, ks, ps)
+    for k, p in zip(ks, ps):
+        _check(ctx, [k], [p])
+
+
+def test_msm_edge_points(ctx):
+    r = rng(12)
+    p, q = rand_point(r), rand_point(r)
+    k1, k2, k3 = rand_scalar(r), rand_scalar(r), rand_scalar(r)
+    _check(ctx, [k1, k2], [p, p])            # duplicate points
+    _check(ctx, [k1, k1], [p, -p])           # cancels to the identity
+    _check(ctx, [k1, k2, k3], [G.IDENTITY, p, G.IDENTITY])  # identity as an input
+    _check(ctx, [k1, G.L - k1], [p, p])      # scalars cancel
+    _check(ctx, [5, 5], [p, q])
+
+
+def test_msm_one_bucket(ctx):
+    """All scalars equal: every term of a window lands in one bucket (the
+    over-long-bucket path), as bit-valued witness vectors do in the reference's
+    range gadget (tests/r1cs.rs:629-632)."""
+    r = rng(13)
+    n = 3000
+    ps = [rand_point(r) for _ in range(n)]
+    _check(ctx, [1] * n, ps)
+    k = rand_scalar(r)
+    _check(ctx, [k] * n, ps)
+    _check(ctx, [i & 1 for i in range(n)], ps)
+
+
+@pytest.mark.parametrize("c", [3, 4, 7, 8, 11, 13, 16])
+def test_msm_all_windows(ctx, c):
+    r = rng(20 + c)
+    n = 300
+    ks = [rand_scalar(r) for _ in range(n)]
+    ps = [rand_point(r) for _ in range(n)]
+    ctx.set_window(c)
+    try:
+        _check(ctx, ks, ps)
+    finally:
+        ctx.set_window(0)
+
+
+def test_msm_table_sets_and_offset(ctx):
+    from mpc_bulletproof_b200 import Table
+
+    r = rng(31)
+    n_tab, off, n, sets = 600, 100, 384, 3
+    ps = [rand_point(r) for _ in range(n_tab)]
+    t = Table(ctx, points_bytes(ps))
+    assert len(t) == n_tab
+    ks = [[rand_scalar(r) for _ in range(n)] for _ in range(sets)]
+    got = t.msm(b"".join(scalars_bytes(k) for k in ks), n_sets=sets, offset=off, n=n)
+    for s in range(sets):
+        assert got[s] == G.msm(ks[s], ps[off : off + n]).encode()
+    t.close()
+
+
+def test_invalid_point_rejected(ctx):
+    from mpc_bulletproof_b200 import BpgError, msm
+    from mpc_bulletproof_b200._lib import BPG_ERR_DECODE
+
+    bad = bytes.fromhex("0100000000000000000000000000000000000000000000000000000000000000")
+    with pytest.raises(BpgError) as e:
+        msm(ctx, scalars_bytes([1]), bad)
+    assert e.value.code == BPG_ERR_DECODE
+
+
+def test_linearity_large(ctx):
+    """Size-independent property at 2^18 terms: tiling a 2^12-point table 64 times
+    must equal the MSM of the column-summed scalars over the 2^12 points."""
+    import numpy as np
+
+    from mpc_bulletproof_b200 import msm
+
+    r = rng(41)
+    m, reps = 4096, 64
+    ps = [rand_point(r) for _ in range(m)]
+    pb = points_bytes(ps)
+    ks = [[rand_scalar(r) for _ in range(m)] for _ in range(reps)]
+    big = msm(ctx, b"".join(scalars_bytes(k) for k in ks), pb * reps)
+    summed = [sum(ks[j][i] for j in range(reps)) % G.L for i in range(m)]
+    small = msm(ctx, scalars_bytes(summed), pb)
+    assert big == small
+    assert small == G.msm(summed, ps).encode()
