@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline measurement (BASELINE.json: "Ristretto MSM
+Mpoints/s @1/2/4/8 B200").
+
+A step = one multiscalar multiplication over synthetic inputs: every rank owns a
+2^LG-point shard (default 2^20) of a fixed table resident in HBM as affine-Niels
+plus that shard's uniform scalars, runs the whole Pippenger pipeline on it, the
+ranks' 128-byte partial sums are all-gathered over NCCL and every rank adds and
+encodes them.  At N=1 that is exactly the 2^20-point MSM of BASELINE.json's
+config 3; at N ranks it is an N*2^20-point MSM ("scaling": "weak").
+
+  python bench.py --gpus N --steps K --warmup W            # this framework
+  python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference algorithm
+
+One JSON line on stdout (rank 0).  See DESIGN.md §Measurement for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import socket
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ristretto255_msm_throughput"
+UNIT = "Mpoints/s"
+BASEPOINT = bytes.fromhex("e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lg-points", type=int, default=20, help="log2 of the points per GPU")
+    ap.add_argument("--cpu-sample-lg", type=int, default=18, help="log2 of the CPU-baseline sample size")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe), runs during the timed region
+# ---------------------------------------------------------------------------------
+class Clocks:
+    Q = (
+        "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+        "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL,
+                text=True,
+            )
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {
+            "sm_mhz": sm[len(sm) // 2] if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def int32_peak():
+    """wide multiply-add issue peak measured by tools/int32_peak (committed under profiles/)."""
+    p = os.path.join(ROOT, "profiles", "int32_peak.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
+# ---------------------------------------------------------------------------------
+# reference arm: CPU restatement of the reference algorithm (oracle/c), host cores
+# ---------------------------------------------------------------------------------
+def ensure_oracle():
+    so = os.path.join(ROOT, "oracle", "c", "libbp_oracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    from oracle import cbind
+
+    return cbind
+
+
+def host_uniform_scalars(n: int, seed: int) -> bytes:
+    import numpy as np
+
+    g = np.random.Generator(np.random.PCG64(seed))
+    a = g.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    a[:, 31] &= 0x0F  # uniform in [0, 2^252) < l
+    return a.tobytes()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cbind = ensure_oracle()
+    threads = cbind.max_threads()
+    n = 1 << args.cpu_sample_lg
+    pts = cbind.basepoint_mul(host_uniform_scalars(n, 0xB2000003), threads)
+    dec = cbind.DecodedPoints(pts, threads)
+    sc = [host_uniform_scalars(n, 0xB2000100 + i) for i in range(2)]
+    for i in range(args.warmup):
+        dec.msm(sc[i % 2], threads=threads)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        dec.msm(sc[i % 2], threads=threads)
+    dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1e3
+    val = n / ms / 1e3
+    sample = f"2^{args.cpu_sample_lg}-point MSM per step (same per-point algorithm as the 2^{args.lg_points} workload; dalek-style radix-2^8 Pippenger, digit columns over {threads} OpenMP threads; points pre-decoded)"
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": val,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u64 limbs (radix 2^51)",
+        "data": "synthetic",
+        "config": {"workload": f"msm_2^{args.lg_points}_points_per_gpu", "group": "ristretto255", "sample_points": n},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------
+# this framework
+# ---------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from mpc_bulletproof_b200 import Comb, Context, Table
+    from mpc_bulletproof_b200.api import dev_sum_encode
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = Context(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+    n = 1 << args.lg_points
+    NSETS_ROT = 4  # scalar sets rotated through so that no step re-reads the previous step's scalars
+
+    def uniform_scalars(count, seed):
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        s = torch.randint(-(2**31), 2**31, (count, 8), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+        s[:, 7] &= 0x0FFFFFFF  # uniform in [0, 2^252) < l
+        return s.contiguous()
+
+    with torch.cuda.stream(stream):
+        # synthetic table: point i of this rank = k_i * B, k_i uniform (product fixed-base path)
+        comb = Comb(ctx, BASEPOINT)
+        gen_k = uniform_scalars(n, 0xB2000003 + 1000 * rank)
+        pts_bytes = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+        comb.dev_mul(gen_k.data_ptr(), n, pts_bytes.data_ptr())
+        table = Table(ctx, dev_ptr=pts_bytes.data_ptr(), n=n)
+        scal = [uniform_scalars(n, 0xB2000100 + 1000 * rank + i) for i in range(NSETS_ROT)]
+        part = torch.zeros(32, dtype=torch.int32, device=dev)  # this rank's partial sum (extended point)
+        parts = torch.zeros(world * 32, dtype=torch.int32, device=dev)
+        result = torch.zeros(32, dtype=torch.uint8, device=dev)
+    stream.synchronize()
+
+    def step(i):
+        table.dev_msm(scal[i % NSETS_ROT].data_ptr(), 1, part.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(parts, part)
+            dev_sum_encode(ctx, parts.data_ptr(), world, 1, result.data_ptr())
+        else:
+            dev_sum_encode(ctx, part.data_ptr(), 1, 1, result.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ("value") ----------------------------------
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step(i)
+    barrier()
+    ctx.profile(True)
+    ctx.profile_reset()
+    launches0 = ctx.launches
+    clocks = Clocks(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for i in range(args.steps):
+            step(i)
+        e1.record(stream)
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launches - launches0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * n / ms_step / 1e3
+    result_hex = bytes(result.cpu().tolist()).hex()
+
+    # ---- end to end through the host-buffer C ABI ("e2e") ----------------------
+    # every step: scalars start in pinned HOST memory, go H2D, the MSM runs, the
+    # 32-byte result comes back D2H.  N=1 uses bpg_msm_table itself; N>1 adds the
+    # all-gather of partial sums between the device MSM and the encode.
+    host_sc = [s.cpu().pin_memory() for s in scal[:2]]
+    d_in = torch.empty_like(scal[0])
+    host_out = torch.empty(32, dtype=torch.uint8).pin_memory()
+
+    def e2e_step(i):
+        if world == 1:
+            import ctypes
+
+            from mpc_bulletproof_b200._lib import check, lib
+
+            check(
+                lib().bpg_msm_table(
+                    ctx._h, table._h, 0, n, ctypes.c_void_p(host_sc[i % 2].data_ptr()), 1, ctypes.c_void_p(host_out.data_ptr())
+                )
+            )
+        else:
+            with torch.cuda.stream(stream):
+                d_in.copy_(host_sc[i % 2], non_blocking=True)
+                table.dev_msm(d_in.data_ptr(), 1, part.data_ptr())
+                dist.all_gather_into_tensor(parts, part)
+                dev_sum_encode(ctx, parts.data_ptr(), world, 1, result.data_ptr())
+                host_out.copy_(result, non_blocking=True)
+            stream.synchronize()
+
+    for i in range(min(3, args.warmup)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_val = world * n / e2e_ms / 1e3
+
+    # ---- rank 0: roofline, CPU baseline, JSON ----------------------------------
+    if rank == 0:
+        peaks, peaks_kind = measured_peaks()
+        acc_ms, acc_n = prof["accum"]
+        acc_ms = acc_ms / max(acc_n, 1)
+        alg_bytes = 128.0 * n  # 32 B scalar + 96 B Niels entry per point
+        achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "accum_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        roof = {
+            "bound": "hbm",
+            "kernel": "k_accum (bucket accumulation)",
+            "achieved": achieved,
+            "peak": peaks["hbm_gbs"],
+            "peak_kind": f"{peaks_kind} (MEASURED_PEAKS.json hbm_gbs)" if peaks_kind == "measured" else "fallback",
+            "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"] if achieved else None,
+            "traffic": traffic,
+            "kernel_ms": acc_ms,
+            "kernel_share_of_step": acc_ms / ms_step if ms_step else None,
+            "note": "the kernel is INT32-issue-bound, not HBM-bound; see int32",
+        }
+        ip = int32_peak()
+        if ip and acc_ms:
+            wide = 16 * 504.0 * n  # 16 mixed adds per point x 7 fe_mul x 72 wide MADs
+            roof["int32"] = {
+                "achieved_wide_mad_per_s": wide / (ms_step * 1e-3),
+                "kernel_wide_mad_per_s": (n * prof_madds(prof, n) * 504.0) / (acc_ms * 1e-3),
+                "peak_wide_mad_per_s": ip["imad_wide_Tops"] * 1e12,
+                "frac_of_step": wide / (ms_step * 1e-3) / (ip["imad_wide_Tops"] * 1e12),
+                "peak_kind": "measured (tools/int32_peak, profiles/int32_peak.json)",
+            }
+        phases = {k: v[0] / max(v[1], 1) for k, v in prof.items() if v[1]}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(args, pts_bytes, scal[0], n)
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "u32 limbs (8x32-bit, GF(2^255-19))",
+            "data": "synthetic",
+            "config": {
+                "workload": f"msm_2^{args.lg_points}_points_per_gpu",
+                "group": "ristretto255",
+                "points_total": world * n,
+                "scalars": "uniform in [0, 2^252)",
+                "points": "k_i*B, k_i uniform (device fixed-base comb)",
+                "l2": f"{NSETS_ROT} scalar sets of {n * 32 >> 20} MiB rotated + {n * 96 >> 20} MiB table + sort/bucket workspace > 126 MB L2",
+                "gpoint_ops_per_s_eq": 16 * world * n / (ms_step * 1e-3) / 1e9,
+            },
+            "e2e": {
+                "value": e2e_val,
+                "unit": UNIT,
+                "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": n * 32,
+                "d2h_bytes_per_step": 32,
+                "api": "bpg_msm_table (host buffers)" if world == 1 else "pinned H2D + bpg_dev_msm_table + all_gather + bpg_dev_sum_encode + D2H",
+            },
+            "gpu_launches": int(launches),
+            "phases_ms": phases,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "clocks": clk,
+            "result": result_hex,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def prof_madds(prof, n):
+    return 16.0  # bucket additions per point charged by SURVEY.md §8d (16-bit windows)
+
+
+def cpu_baseline(args, pts_bytes_dev, scal_dev, n):
+    """The C restatement of the reference CPU algorithm on a bounded sample, host cores."""
+    try:
+        cbind = ensure_oracle()
+    except Exception as e:  # build tools missing on the box
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+    m = min(n, 1 << args.cpu_sample_lg)
+    pts = bytes(pts_bytes_dev[: m * 32].cpu().numpy().tobytes())
+    sc = bytes(scal_dev[:m].cpu().numpy().tobytes())
+    threads = cbind.max_threads()
+    dec = cbind.DecodedPoints(pts, threads)
+    dec.msm(sc, threads=threads)
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = dec.msm(sc, threads=threads)
+    dt = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    out1 = dec.msm(sc[: 32 * (m // 4)], 0, m // 4, threads=1)
+    dt1 = time.perf_counter() - t0
+    # parity of the sample against the GPU through the C ABI
+    from mpc_bulletproof_b200 import Context, Table
+
+    ctx2 = Context(0)
+    gpu = Table(ctx2, pts).msm(sc)[0]
+    ctx2.close()
+    return {
+        "value": m / dt / 1e6,
+        "unit": UNIT,
+        "cores": threads,
+        "kind": "port",
+        "sample": f"first 2^{m.bit_length() - 1} points+scalars of the workload, dalek-style radix-2^8 Pippenger, points pre-decoded, {reps} runs",
+        "single_thread_value": (m // 4) / dt1 / 1e6,
+        "bytes_equal_gpu": gpu == out,
+    }
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl == "b200":
+        # launched bare: re-launch under torchrun, one rank per GPU
+        cmd = [
+            sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+            "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.abspath(__file__),
+        ] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

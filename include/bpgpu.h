@@ -44,7 +44,9 @@ typedef struct bpg_table bpg_table; /* points resident in HBM in affine-Niels fo
 /* ---- context --------------------------------------------------------------------- */
 int bpg_init(int device, bpg_ctx** out);
 void bpg_free(bpg_ctx* ctx);
-int bpg_set_stream(bpg_ctx* ctx, void* cuda_stream); /* cudaStream_t; NULL = context's own */
+/* use_own != 0: the context's own non-blocking stream (the default after bpg_init);
+ * otherwise cuda_stream is a cudaStream_t used verbatim (NULL = legacy default stream). */
+int bpg_set_stream(bpg_ctx* ctx, void* cuda_stream, int use_own);
 int bpg_sync(bpg_ctx* ctx);
 const char* bpg_strerror(int code);
 int bpg_last_cuda_error(const bpg_ctx* ctx);
@@ -52,6 +54,26 @@ int bpg_last_cuda_error(const bpg_ctx* ctx);
 uint64_t bpg_launch_count(const bpg_ctx* ctx);
 /* force the Pippenger window width (0 = choose from the size); for tuning/tests */
 int bpg_set_window(bpg_ctx* ctx, int c);
+
+/* ---- per-phase device timing --------------------------------------------------------
+ * When enabled, CUDA events are recorded on the launch stream around each kernel
+ * phase; bpg_profile_read waits for the last event and returns, per phase, the
+ * summed milliseconds and the number of intervals since the last reset. */
+#define BPG_PROF_HIST 0
+#define BPG_PROF_SCAN 1
+#define BPG_PROF_SCATTER 2
+#define BPG_PROF_ACCUM 3
+#define BPG_PROF_ACCUM_BIG 4
+#define BPG_PROF_REDUCE 5
+#define BPG_PROF_COMBINE 6
+#define BPG_PROF_HORNER 7
+#define BPG_PROF_ENCODE 8
+#define BPG_PROF_OTHER 9
+#define BPG_PROF_NPHASE 10
+int bpg_profile_enable(bpg_ctx* ctx, int on);
+int bpg_profile_reset(bpg_ctx* ctx);
+int bpg_profile_read(bpg_ctx* ctx, double* ms, uint64_t* count, int n);
+const char* bpg_profile_phase_name(int phase);
 
 /* ---- point tables ------------------------------------------------------------------
  * Upload n compressed points once; they are decoded and kept as affine-Niels
@@ -90,6 +112,22 @@ int bpg_dev_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t offset, size_
  * either may be NULL. */
 int bpg_dev_sum_encode(bpg_ctx* ctx, const void* d_parts, int n_parts, int n_sets, void* d_out_bytes,
                        void* d_out_ext);
+
+/* ---- fixed-base multiplication (comb) ---------------------------------------------
+ * A comb holds, for each of nbases points P_t, the 64x8 affine-Niels multiples
+ * (d+1)*16^j*P_t, so that  out[i] = sum_t scalars[t*n + i] * P_t  costs 64 mixed
+ * additions per base and no doublings.  With bases {B, B_blinding} this is
+ * `PedersenGens::commit(v, v_blinding)` batched over i (reference
+ * src/generators.rs:41-43; src/r1cs/prover.rs:319-329,627-631; Q = w*B at :687).
+ * With one base it is `Scalar * StarkPoint` for a fixed point. */
+typedef struct bpg_comb bpg_comb;
+int bpg_comb_create(bpg_ctx* ctx, const uint8_t* bases_compressed /* nbases*32 */, int nbases, bpg_comb** out);
+void bpg_comb_free(bpg_comb* comb);
+int bpg_comb_mul(bpg_ctx* ctx, const bpg_comb* comb, const uint8_t* scalars_le /* nbases*n*32 */, size_t n,
+                 uint8_t* out /* n*32 */);
+/* device-resident: either output may be NULL (bytes: n*32, ext: n*128) */
+int bpg_dev_comb_mul(bpg_ctx* ctx, const bpg_comb* comb, const void* d_scalars, size_t n, void* d_out_bytes,
+                     void* d_out_ext);
 
 #ifdef __cplusplus
 }

@@ -5,5 +5,5 @@ renegade-fi/mpc-bulletproof's R1CS prover/verifier (ristretto255 instantiation).
 The product is the C-ABI shared library `libbpgpu.so` (include/bpgpu.h); this
 package is the thin Python host mirror used by the tests and bench.
 """
-from .api import Context, Table, msm  # noqa: F401
+from .api import Comb, Context, Table, msm  # noqa: F401
 from ._lib import BpgError  # noqa: F401

@@ -31,7 +31,11 @@ _I = ctypes.c_int
 _SIGNATURES = {
     "bpg_init": (_I, [_I, ctypes.POINTER(_P)]),
     "bpg_free": (None, [_P]),
-    "bpg_set_stream": (_I, [_P, _P]),
+    "bpg_set_stream": (_I, [_P, _P, _I]),
+    "bpg_profile_enable": (_I, [_P, _I]),
+    "bpg_profile_reset": (_I, [_P]),
+    "bpg_profile_read": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64), _I]),
+    "bpg_profile_phase_name": (ctypes.c_char_p, [_I]),
     "bpg_sync": (_I, [_P]),
     "bpg_strerror": (ctypes.c_char_p, [_I]),
     "bpg_last_cuda_error": (_I, [_P]),
@@ -45,6 +49,10 @@ _SIGNATURES = {
     "bpg_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),
     "bpg_dev_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),
     "bpg_dev_sum_encode": (_I, [_P, _P, _I, _I, _P, _P]),
+    "bpg_comb_create": (_I, [_P, _P, _I, ctypes.POINTER(_P)]),
+    "bpg_comb_free": (None, [_P]),
+    "bpg_comb_mul": (_I, [_P, _P, _P, _SZ, _P]),
+    "bpg_dev_comb_mul": (_I, [_P, _P, _P, _SZ, _P, _P]),
 }
 
 

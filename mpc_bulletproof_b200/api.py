@@ -30,7 +30,25 @@ class Context:
             pass
 
     def set_stream(self, cuda_stream: int | None):
-        check(lib().bpg_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+        """cuda_stream: a cudaStream_t handle (0 = legacy default stream); None = the context's own."""
+        if cuda_stream is None:
+            check(lib().bpg_set_stream(self._h, None, 1))
+        else:
+            check(lib().bpg_set_stream(self._h, ctypes.c_void_p(cuda_stream), 0))
+
+    def profile(self, on: bool):
+        check(lib().bpg_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        check(lib().bpg_profile_reset(self._h))
+
+    def profile_read(self) -> dict:
+        """{phase: (total_ms, intervals)} since the last reset; waits for the stream."""
+        n = 10
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_uint64 * n)()
+        check(lib().bpg_profile_read(self._h, ms, cnt, n))
+        return {lib().bpg_profile_phase_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n)}
 
     def sync(self):
         check(lib().bpg_sync(self._h))
@@ -105,3 +123,41 @@ def dev_sum_encode(ctx: Context, d_parts: int, n_parts: int, n_sets: int, d_out_
             ctx._h, ctypes.c_void_p(d_parts), n_parts, n_sets, ctypes.c_void_p(d_out_bytes or 0), ctypes.c_void_p(d_out_ext or 0)
         )
     )
+
+
+class Comb:
+    """Fixed-base comb tables for a few points (e.g. the Pedersen bases B, B_blinding)."""
+
+    def __init__(self, ctx: Context, bases: bytes):
+        assert len(bases) % 32 == 0 and bases
+        self.ctx = ctx
+        self.nbases = len(bases) // 32
+        self._h = ctypes.c_void_p()
+        check(lib().bpg_comb_create(ctx._h, bases, self.nbases, ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().bpg_comb_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def mul(self, scalars: bytes) -> bytes:
+        """out[i] = sum_t scalars[t*n+i] * base_t; scalars laid out base-major."""
+        n = len(scalars) // (32 * self.nbases)
+        if len(scalars) != 32 * n * self.nbases:
+            raise _lib.BpgError(_lib.BPG_ERR_LEN, "scalar buffer length is not nbases*n*32")
+        out = ctypes.create_string_buffer(32 * max(n, 1))
+        check(lib().bpg_comb_mul(self.ctx._h, self._h, scalars, n, out))
+        return out.raw[: 32 * n]
+
+    def dev_mul(self, d_scalars: int, n: int, d_out_bytes: int | None, d_out_ext: int | None = None):
+        check(
+            lib().bpg_dev_comb_mul(
+                self.ctx._h, self._h, ctypes.c_void_p(d_scalars), n, ctypes.c_void_p(d_out_bytes or 0), ctypes.c_void_p(d_out_ext or 0)
+            )
+        )

@@ -25,6 +25,13 @@ struct bpg_ctx {
   uint64_t launches = 0;
   int forced_c = 0;
   int sm_count = 148;
+  // per-phase device timing (bpg_profile_*): events are recorded on the launch stream
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;   // pool
+  std::vector<int> prof_phase;        // phase id of interval [ev[i], ev[i+1])
+  size_t prof_used = 0;
+  double prof_ms[BPG_PROF_NPHASE] = {0};
+  uint64_t prof_n[BPG_PROF_NPHASE] = {0};
   // workspace arena (grown on demand, reused across calls)
   uint8_t* ws = nullptr;
   size_t ws_cap = 0;
@@ -97,14 +104,67 @@ extern "C" void bpg_free(bpg_ctx* ctx) {
   if (ctx->d_small) cudaFree(ctx->d_small);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 
-extern "C" int bpg_set_stream(bpg_ctx* ctx, void* s) {
+extern "C" int bpg_set_stream(bpg_ctx* ctx, void* s, int use_own) {
   if (!ctx) return BPG_ERR_ARG;
-  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  ctx->stream = use_own ? ctx->own_stream : (cudaStream_t)s;
   return BPG_OK;
+}
+
+// ---- per-phase profiling ---------------------------------------------------
+static void prof_mark(bpg_ctx* ctx, int phase) {
+  // closes the previous interval and opens one attributed to `phase` (-1 = close only)
+  if (!ctx->prof) return;
+  if (ctx->prof_used == ctx->prof_ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    ctx->prof_ev.push_back(e);
+    ctx->prof_phase.push_back(-1);
+  }
+  cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream);
+  ctx->prof_phase[ctx->prof_used] = phase;
+  ctx->prof_used++;
+}
+static void prof_collect(bpg_ctx* ctx) {
+  if (ctx->prof_used == 0) return;
+  cudaEventSynchronize(ctx->prof_ev[ctx->prof_used - 1]);
+  for (size_t i = 0; i + 1 < ctx->prof_used; i++) {
+    int ph = ctx->prof_phase[i];
+    if (ph < 0 || ph >= BPG_PROF_NPHASE) continue;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->prof_ev[i], ctx->prof_ev[i + 1]) == cudaSuccess) {
+      ctx->prof_ms[ph] += ms;
+      ctx->prof_n[ph]++;
+    }
+  }
+  ctx->prof_used = 0;
+}
+extern "C" int bpg_profile_enable(bpg_ctx* ctx, int on) {
+  if (!ctx) return BPG_ERR_ARG;
+  if (ctx->prof) prof_collect(ctx);
+  ctx->prof = on != 0;
+  return BPG_OK;
+}
+extern "C" int bpg_profile_reset(bpg_ctx* ctx) {
+  if (!ctx) return BPG_ERR_ARG;
+  prof_collect(ctx);
+  for (int i = 0; i < BPG_PROF_NPHASE; i++) ctx->prof_ms[i] = 0, ctx->prof_n[i] = 0;
+  return BPG_OK;
+}
+extern "C" int bpg_profile_read(bpg_ctx* ctx, double* ms, uint64_t* count, int n) {
+  if (!ctx || !ms || !count) return BPG_ERR_ARG;
+  prof_collect(ctx);
+  for (int i = 0; i < n && i < BPG_PROF_NPHASE; i++) ms[i] = ctx->prof_ms[i], count[i] = ctx->prof_n[i];
+  return BPG_OK;
+}
+extern "C" const char* bpg_profile_phase_name(int phase) {
+  static const char* names[BPG_PROF_NPHASE] = {"hist",   "scan",    "scatter", "accum", "accum_big",
+                                               "reduce", "combine", "horner",  "encode", "other"};
+  return (phase >= 0 && phase < BPG_PROF_NPHASE) ? names[phase] : "?";
 }
 extern "C" int bpg_sync(bpg_ctx* ctx) {
   if (!ctx) return BPG_ERR_ARG;
@@ -236,7 +296,7 @@ static int pick_window(size_t n_per_set, int forced) {
   double best = 1e300;
   int best_c = 4;
   for (int c = 3; c <= 20; c++) {
-    int W = (254 + c - 1) / c;
+    int W = (255 + c - 1) / c;
     double nb = (double)(1u << (c - 1));
     // mixed adds (7M) for the terms, two full adds (9M) per bucket in the reduction,
     // c doublings per window on the serial tail (charged as if 64 lanes idle)
@@ -251,7 +311,7 @@ static int pick_window(size_t n_per_set, int forced) {
 
 static void make_cfg(MsmCfg& cfg, size_t n_terms, size_t n_points, int nsets, int c) {
   cfg.c = c;
-  cfg.W = (254 + c - 1) / c;
+  cfg.W = (255 + c - 1) / c;
   cfg.nb = 1u << (c - 1);
   cfg.nsets = nsets;
   cfg.n_terms = (uint32_t)n_terms;
@@ -317,32 +377,41 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   uint32_t* wins = (uint32_t*)(ctx->ws + o_wins);
   cudaStream_t st = ctx->stream;
 
+  prof_mark(ctx, BPG_PROF_HIST);
   CK(cudaMemsetAsync(counts, 0, (size_t)cfg.B * 4, st));
   CK(cudaMemsetAsync(big_count, 0, 4, st));
   unsigned gt = (unsigned)((n_terms + 255) / 256);
   k_hist<<<gt, 256, 0, st>>>(d_scalars, d_set_ids, cfg, counts);
   LAUNCH_CHECK();
+  prof_mark(ctx, BPG_PROF_SCAN);
   k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.B, tiles);
   LAUNCH_CHECK();
   k_scan_spine<<<1, 1024, 0, st>>>(tiles, (uint32_t)ntiles, offsets, cfg.B);
   LAUNCH_CHECK();
   k_scan_apply<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.B, tiles, offsets);
   LAUNCH_CHECK();
+  prof_mark(ctx, BPG_PROF_SCATTER);
   k_scatter<<<gt, 256, 0, st>>>(d_scalars, d_set_ids, d_point_ids, cfg, offsets, counts, entries);
   LAUNCH_CHECK();
+  prof_mark(ctx, BPG_PROF_ACCUM);
   k_accum<<<(cfg.B + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, st>>>(table_base, offsets, entries, cfg,
                                                                            buckets, big_count, big_list);
   LAUNCH_CHECK();
+  prof_mark(ctx, BPG_PROF_ACCUM_BIG);
   unsigned gbig = std::min<unsigned>(cfg.big_cap, (unsigned)ctx->sm_count * 2);
   k_accum_big<<<gbig, BIG_THREADS, 0, st>>>(table_base, offsets, entries, cfg, buckets, big_count, big_list);
   LAUNCH_CHECK();
+  prof_mark(ctx, BPG_PROF_REDUCE);
   unsigned nred = cfg.nwin * cfg.nchunks;
   k_reduce<<<(nred + RED_THREADS - 1) / RED_THREADS, RED_THREADS, 0, st>>>(buckets, cfg, chunks);
   LAUNCH_CHECK();
+  prof_mark(ctx, BPG_PROF_COMBINE);
   k_combine<<<cfg.nwin, COMB_THREADS, 0, st>>>(chunks, cfg, wins);
   LAUNCH_CHECK();
+  prof_mark(ctx, BPG_PROF_HORNER);
   k_horner<<<(nsets + 31) / 32, 32, 0, st>>>(wins, cfg, d_out_ext);
   LAUNCH_CHECK();
+  prof_mark(ctx, -1);
   return BPG_OK;
 }
 
@@ -359,9 +428,11 @@ extern "C" int bpg_dev_sum_encode(bpg_ctx* ctx, const void* d_parts, int n_parts
                                   void* d_out_ext) {
   if (!ctx || !d_parts || n_parts <= 0 || n_sets <= 0) return BPG_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
+  prof_mark(ctx, BPG_PROF_ENCODE);
   k_sum_encode<<<(n_sets + 31) / 32, 32, 0, ctx->stream>>>((const uint32_t*)d_parts, n_parts, n_sets,
                                                            (uint8_t*)d_out_bytes, (uint32_t*)d_out_ext);
   LAUNCH_CHECK();
+  prof_mark(ctx, -1);
   return BPG_OK;
 }
 
@@ -397,4 +468,103 @@ extern "C" int bpg_msm(bpg_ctx* ctx, const uint8_t* scalars_le, const uint8_t* p
   rc = bpg_msm_table(ctx, t, 0, n, scalars_le, 1, out);
   bpg_table_free(t);
   return rc;
+}
+
+// ---------------------------------------------------------------------------
+// fixed-base (comb) multiplication
+// ---------------------------------------------------------------------------
+struct bpg_comb {
+  bpg_ctx* ctx;
+  uint32_t* tables;  // nbases * COMB_ENTRIES * 24 words
+  int nbases;
+};
+
+extern "C" int bpg_comb_create(bpg_ctx* ctx, const uint8_t* bases_compressed, int nbases, bpg_comb** out) {
+  if (!ctx || !bases_compressed || nbases <= 0 || nbases > 64 || !out) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  bpg_comb* c = new (std::nothrow) bpg_comb();
+  if (!c) return BPG_ERR_NOMEM;
+  c->ctx = ctx;
+  c->nbases = nbases;
+  c->tables = nullptr;
+  cudaError_t e = cudaMalloc(&c->tables, (size_t)nbases * COMB_ENTRIES * 96);
+  if (e != cudaSuccess) {
+    delete c;
+    ctx->last_cuda = (int)e;
+    return BPG_ERR_NOMEM;
+  }
+  uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small);
+  uint8_t* d_bases = ctx->d_small + 256;
+  int rc = BPG_OK;
+  do {
+    memcpy(ctx->h_pinned + 256, bases_compressed, (size_t)nbases * 32);
+    if (cudaMemsetAsync(bad, 0, 4, ctx->stream) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+    if (cudaMemcpyAsync(d_bases, ctx->h_pinned + 256, (size_t)nbases * 32, cudaMemcpyHostToDevice, ctx->stream) !=
+        cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+    for (int t = 0; t < nbases; t++) {
+      k_comb_build<<<1, COMB_WINDOWS, 0, ctx->stream>>>(d_bases + 32 * t, c->tables + (size_t)t * COMB_ENTRIES * 24, bad);
+      ctx->launches++;
+    }
+    if (cudaGetLastError() != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+    uint32_t* hbad = reinterpret_cast<uint32_t*>(ctx->h_pinned);
+    if (cudaMemcpyAsync(hbad, bad, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+    cudaError_t se = cudaStreamSynchronize(ctx->stream);
+    if (se != cudaSuccess) { ctx->last_cuda = (int)se; rc = BPG_ERR_CUDA; break; }
+    if (*hbad) rc = BPG_ERR_DECODE;
+  } while (0);
+  if (rc != BPG_OK) {
+    cudaFree(c->tables);
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return BPG_OK;
+}
+
+extern "C" void bpg_comb_free(bpg_comb* c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx->device);
+  cudaStreamSynchronize(c->ctx->stream);
+  cudaFree(c->tables);
+  delete c;
+}
+
+static sc_bias bias_for(int c) {
+  sc_bias b;
+  memset(&b, 0, sizeof b);
+  int W = (255 + c - 1) / c;
+  for (int w = 0; w < W; w++) {
+    int bit = c * w + c - 1;
+    b.v[bit >> 5] |= 1u << (bit & 31);
+  }
+  return b;
+}
+
+extern "C" int bpg_dev_comb_mul(bpg_ctx* ctx, const bpg_comb* comb, const void* d_scalars, size_t n,
+                                void* d_out_bytes, void* d_out_ext) {
+  if (!ctx || !comb || (!d_scalars && n) || n >= (1u << 31)) return BPG_ERR_ARG;
+  if (n == 0) return BPG_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_comb_mul<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(comb->tables, comb->nbases,
+                                                                  (const uint32_t*)d_scalars, (uint32_t)n,
+                                                                  bias_for(4), (uint8_t*)d_out_bytes,
+                                                                  (uint32_t*)d_out_ext);
+  LAUNCH_CHECK();
+  return BPG_OK;
+}
+
+extern "C" int bpg_comb_mul(bpg_ctx* ctx, const bpg_comb* comb, const uint8_t* scalars_le, size_t n, uint8_t* out) {
+  if (!ctx || !comb || !out || (!scalars_le && n)) return BPG_ERR_ARG;
+  if (n == 0) return BPG_OK;
+  CK(cudaSetDevice(ctx->device));
+  size_t sbytes = n * (size_t)comb->nbases * 32;
+  int rc = ensure_stage(ctx, sbytes + n * 32);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->d_stage, scalars_le, sbytes, cudaMemcpyHostToDevice, ctx->stream));
+  uint8_t* d_out = ctx->d_stage + sbytes;
+  rc = bpg_dev_comb_mul(ctx, comb, ctx->d_stage, n, d_out, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out, d_out, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BPG_OK;
 }

@@ -338,9 +338,10 @@ BPG_DI fe fe_cneg(const fe& a, bool neg) {
   for (int i = 0; i < 8; i++) o.v[i] = neg ? n.v[i] : a.v[i];
   return o;
 }
+// |a|: the canonical representative of a or -a whose low bit is clear (RFC 9496 §4.1 CT_ABS)
 BPG_DI fe fe_abs(const fe& a) {
   fe c = fe_canon(a);
-  return fe_cneg(c, c.v[0] & 1u);
+  return fe_canon(fe_cneg(c, c.v[0] & 1u));
 }
 
 // n squarings

@@ -25,7 +25,7 @@ namespace bpg {
 
 struct MsmCfg {
   int c;              // window width in bits
-  int W;              // windows per scalar = ceil(254 / c)
+  int W;              // windows per scalar = ceil(255 / c)
   uint32_t nb;        // buckets per window = 2^(c-1)
   int nsets;          // independent sums in this launch
   uint32_t n_terms;   // scalars in this launch
@@ -384,6 +384,61 @@ __global__ void __launch_bounds__(128) k_encode(const uint32_t* __restrict__ ext
   ge_ext p;
   ge_load_ext(p, ext + (size_t)i * 32);
   ge_encode(out + (size_t)i * 32, p);
+}
+
+// ---------------------------------------------------------------------------
+// K-FIXED: fixed-base comb.  tab[j][d] = (d+1) * 16^j * P  (j < 64, d < 8), affine
+// Niels, so k*P is 64 mixed additions and no doublings.  Serves the two-term
+// Pedersen commitments `v*B + v_blinding*B_blinding` (reference
+// src/generators.rs:41-43; prover.rs:325,627-631,687) and synthetic point sets.
+// ---------------------------------------------------------------------------
+constexpr int COMB_WINDOWS = 64;
+constexpr int COMB_ENTRIES = COMB_WINDOWS * 8;
+
+__global__ void __launch_bounds__(COMB_WINDOWS) k_comb_build(const uint8_t* __restrict__ base32,
+                                                              uint32_t* __restrict__ table,
+                                                              uint32_t* __restrict__ bad_count) {
+  int j = threadIdx.x;
+  uint8_t buf[32];
+  for (int i = 0; i < 32; i++) buf[i] = base32[i];
+  ge_ext p;
+  if (!ge_decode(p, buf)) {
+    if (j == 0) atomicAdd(bad_count, 1u);
+    p = ge_identity();
+  }
+  for (int i = 0; i < 4 * j; i++) p = ge_dbl(p);
+  ge_ext m = p;
+  for (int d = 0; d < 8; d++) {
+    ge_store_niels(table + (size_t)(j * 8 + d) * 24, ge_to_niels(m));
+    m = ge_add(m, p);
+  }
+}
+
+// out[i] = sum_t scalars[t*n + i] * base_t  for `nbases` comb tables laid out back to back
+__global__ void __launch_bounds__(128) k_comb_mul(const uint32_t* __restrict__ tables, int nbases,
+                                                   const uint32_t* __restrict__ scalars, uint32_t n, sc_bias bias4,
+                                                   uint8_t* __restrict__ out_bytes,
+                                                   uint32_t* __restrict__ out_ext) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ge_ext acc = ge_identity();
+  for (int t = 0; t < nbases; t++) {
+    sc k;
+    sc_load(k, scalars + ((size_t)t * n + i) * 8);
+    sc_recoded r = sc_recode(k.v, bias4);
+    const uint32_t* tab = tables + (size_t)t * COMB_ENTRIES * 24;
+    for (int j = 0; j < COMB_WINDOWS; j++) {
+      int d = sc_digit(r, j, 4);
+      if (d != 0) {
+        int mag = d < 0 ? -d : d;
+        ge_niels q;
+        ge_load_niels(q, tab + (size_t)(j * 8 + mag - 1) * 24);
+        acc = ge_madd(acc, q, d < 0);
+      }
+    }
+  }
+  if (out_ext) ge_store_ext(out_ext + (size_t)i * 32, acc);
+  if (out_bytes) ge_encode(out_bytes + (size_t)i * 32, acc);
 }
 
 }  // namespace bpg

@@ -205,7 +205,7 @@ BPG_DI void sc_store(uint32_t* p, const sc& o) {
 }
 
 // ---- signed c-bit window digits ---------------------------------------------
-// For a canonical scalar k (< 2^253) and window width c, with W = ceil(254/c)
+// For a scalar k < 2^253 (canonical scalars are < l < 2^253) and window width c, with W = ceil(255/c)
 // windows:  k = sum_w d_w 2^(c w),  d_w in [-2^(c-1), 2^(c-1)).
 // Adding 2^(c-1) into every window up front turns the carry recursion into one
 // 256-bit addition; window w's digit is then a bit-field minus 2^(c-1).

@@ -48,7 +48,7 @@ static sc_bias mk_bias(int c, int W) {
 }
 // digits[W] for scalar k with window c
 int hs_digits(const uint32_t* k, int c, int* digits) {
-  int W = (254 + c - 1) / c;
+  int W = (255 + c - 1) / c;
   sc_recoded r = sc_recode(k, mk_bias(c, W));
   for (int w = 0; w < W; w++) digits[w] = sc_digit(r, w, c);
   return W;
@@ -56,7 +56,7 @@ int hs_digits(const uint32_t* k, int c, int* digits) {
 // Serial walk through the same stages as msm_kernels.cuh (buckets -> chunked
 // running sums -> window combine -> Horner), with the same device functions.
 int hs_msm(const uint8_t* scalars, const uint8_t* points, int n, int c, int chunk, uint8_t* out) {
-  int W = (254 + c - 1) / c;
+  int W = (255 + c - 1) / c;
   uint32_t nb = 1u << (c - 1);
   if ((uint32_t)chunk > nb) chunk = nb;
   sc_bias bias = mk_bias(c, W);

@@ -1,0 +1,151 @@
+"""The device arithmetic (fe.cuh / sc.cuh / ge.cuh limb schedules, digit recoding and
+the Pippenger bookkeeping) compiled for the host with the PTX carry flag modelled,
+against the big-integer oracle.  This is what can be checked without a GPU; the
+kernels themselves are checked by the -m gpu tests."""
+import ctypes
+import os
+import random
+
+import pytest
+
+from oracle import group as G
+
+HS = os.path.join(os.path.dirname(__file__), "hostsim", "libhostsim.so")
+pytestmark = pytest.mark.skipif(not os.path.exists(HS), reason="tests/hostsim/libhostsim.so not built (run __graft_entry__.build())")
+
+U32x8 = ctypes.c_uint32 * 8
+E32 = ctypes.c_uint32 * 32
+N24 = ctypes.c_uint32 * 24
+B32 = ctypes.c_uint8 * 32
+
+
+@pytest.fixture(scope="module")
+def hs():
+    return ctypes.CDLL(HS)
+
+
+def tol(x):
+    return U32x8(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+
+
+def frl(a):
+    return sum(int(a[i]) << (32 * i) for i in range(8))
+
+
+EDGE_FE = [0, 1, G.P - 1, G.P, G.P + 1, 2**255 - 1, 2**255, 2**256 - 1, 2**256 - 38, 2**256 - 39, 19, 38, 2**255 + 18]
+
+
+def rnd_fe(r):
+    return r.choice(EDGE_FE) if r.random() < 0.15 else r.getrandbits(256)
+
+
+def test_field(hs):
+    r = random.Random(1)
+    o = U32x8()
+    for _ in range(4000):
+        a, b = rnd_fe(r), rnd_fe(r)
+        hs.hs_fe_mul(tol(a), tol(b), o)
+        assert frl(o) < 2**255 and frl(o) % G.P == a * b % G.P
+        hs.hs_fe_sq(tol(a), o)
+        assert frl(o) < 2**255 and frl(o) % G.P == a * a % G.P
+        hs.hs_fe_add(tol(a), tol(b), o)
+        assert frl(o) % G.P == (a + b) % G.P
+        hs.hs_fe_sub(tol(a), tol(b), o)
+        assert frl(o) % G.P == (a - b) % G.P
+        hs.hs_fe_canon(tol(a), o)
+        assert frl(o) == a % G.P
+    for _ in range(20):
+        a = rnd_fe(r)
+        hs.hs_fe_invert(tol(a), o)
+        assert frl(o) % G.P == pow(a, G.P - 2, G.P)
+
+
+def test_scalars(hs):
+    r = random.Random(2)
+    o = U32x8()
+    R = 2**256
+    edge = [0, 1, G.L - 1, G.L - 2, 2**252, 2**252 - 1]
+    for _ in range(3000):
+        a = r.choice(edge) if r.random() < 0.1 else r.randrange(G.L)
+        b = r.choice(edge) if r.random() < 0.1 else r.randrange(G.L)
+        hs.hs_sc_montmul(tol(a), tol(b), o)
+        assert frl(o) == a * b * pow(R, -1, G.L) % G.L
+        hs.hs_sc_mul(tol(a), tol(b), o)
+        assert frl(o) == a * b % G.L
+        hs.hs_sc_add(tol(a), tol(b), o)
+        assert frl(o) == (a + b) % G.L
+        hs.hs_sc_sub(tol(a), tol(b), o)
+        assert frl(o) == (a - b) % G.L
+
+
+def test_signed_digits(hs):
+    r = random.Random(3)
+    dg = (ctypes.c_int * 200)()
+    for c in range(2, 21):
+        for k in [0, 1, G.L - 1, 2**252, 2**253 - 1] + [r.randrange(G.L) for _ in range(100)]:
+            W = hs.hs_digits(tol(k), c, dg)
+            assert W == (255 + c - 1) // c
+            assert sum(dg[w] << (c * w) for w in range(W)) == k
+            assert all(-(1 << (c - 1)) <= dg[w] < (1 << (c - 1)) for w in range(W))
+
+
+def _ext(r, pt):
+    z = r.randrange(1, G.P)
+    x, y = pt.affine()
+    vals = [x * z % G.P, y * z % G.P, z, x * y % G.P * z % G.P]
+    e = E32()
+    for j, v in enumerate(vals):
+        for i in range(8):
+            e[8 * j + i] = (v >> (32 * i)) & 0xFFFFFFFF
+    return e
+
+
+def _pt(e):
+    v = [sum(int(e[8 * j + i]) << (32 * i) for i in range(8)) for j in range(4)]
+    assert (v[0] * v[1] - v[2] * v[3]) % G.P == 0
+    assert all(x < 2**255 for x in v), "extended coordinates must stay tight"
+    return G.Point(*v)
+
+
+def test_group(hs):
+    from tests.test_oracle_group import BAD, MULTIPLES
+
+    r = random.Random(4)
+    pts = [r.randrange(G.L) * G.BASEPOINT for _ in range(8)] + [G.IDENTITY]
+    for p in pts:
+        enc = p.encode()
+        e = E32()
+        assert hs.hs_decode(B32(*enc), e) == 1 and _pt(e).encode() == enc
+        o = B32()
+        hs.hs_encode(_ext(r, p), o)
+        assert bytes(o) == enc
+        d = E32()
+        hs.hs_dbl(_ext(r, p), d)
+        assert _pt(d).encode() == (p + p).encode()
+        for q in pts[:3] + [G.IDENTITY, p, -p]:
+            s = E32()
+            hs.hs_add(_ext(r, p), _ext(r, q), s)
+            assert _pt(s).encode() == (p + q).encode()
+            n = N24()
+            hs.hs_to_niels(_ext(r, q), n)
+            for neg in (0, 1):
+                hs.hs_madd(_ext(r, p), n, neg, s)
+                assert _pt(s).encode() == ((p - q) if neg else (p + q)).encode()
+    for i, h in enumerate(MULTIPLES):
+        e = E32()
+        assert hs.hs_decode(B32(*bytes.fromhex(h)), e) == 1
+        assert _pt(e).encode() == (i * G.BASEPOINT).encode()
+    for h in BAD:
+        assert hs.hs_decode(B32(*bytes.fromhex(h)), E32()) == 0, h
+
+
+@pytest.mark.parametrize("n,c,chunk", [(1, 4, 4), (5, 3, 2), (33, 5, 4), (64, 8, 32), (100, 6, 8)])
+def test_pipeline_walkthrough(hs, n, c, chunk):
+    r = random.Random(10 * n + c)
+    ks = [r.randrange(G.L) for _ in range(n)]
+    ps = [r.randrange(G.L) * G.BASEPOINT for _ in range(n)]
+    o = B32()
+    sb = b"".join(G.sc_to_bytes(k) for k in ks)
+    pb = b"".join(p.encode() for p in ps)
+    assert hs.hs_msm(sb, pb, n, c, chunk, o) == 0
+    assert bytes(o) == G.msm_naive(ks, ps).encode()

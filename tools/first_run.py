@@ -28,5 +28,10 @@ for lg in (12, 16, 18, 20, 22):
             tab.dev_msm(sc.data_ptr(), 1, out.data_ptr())
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
-        print(f"n=2^{lg} c={c} {ms:.3f} ms  {n/ms/1e3:.1f} Mpoints/s", flush=True)
+        ctx.profile(True); ctx.profile_reset()
+        for _ in range(3):
+            tab.dev_msm(sc.data_ptr(), 1, out.data_ptr())
+        pr = ctx.profile_read(); ctx.profile(False)
+        br = " ".join(f"{k}={v[0]/max(v[1],1):.3f}" for k, v in pr.items() if v[1])
+        print(f"n=2^{lg} c={c} {ms:.3f} ms  {n/ms/1e3:.1f} Mpoints/s | {br}", flush=True)
     tab.close()
