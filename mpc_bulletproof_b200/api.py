@@ -7,6 +7,7 @@ Arguments are bytes (32-byte little-endian scalars, 32-byte compressed points).
 from __future__ import annotations
 
 import ctypes
+import weakref
 
 from . import _lib
 from ._lib import check, lib
@@ -17,9 +18,12 @@ class Context:
         self._h = ctypes.c_void_p()
         check(lib().bpg_init(device, ctypes.byref(self._h)))
         self.device = device
+        self._children = weakref.WeakSet()  # tables/combs/ipp states: freed before the context
 
     def close(self):
         if self._h:
+            for child in list(self._children):
+                child.close()
             lib().bpg_free(self._h)
             self._h = ctypes.c_void_p()
 
@@ -72,6 +76,7 @@ class Table:
             check(lib().bpg_table_upload(ctx._h, points, len(points) // 32, ctypes.byref(self._h)))
         else:
             check(lib().bpg_table_upload_dev(ctx._h, ctypes.c_void_p(dev_ptr), n, ctypes.byref(self._h)))
+        ctx._children.add(self)
 
     def __len__(self):
         return int(lib().bpg_table_len(self._h))
@@ -134,6 +139,7 @@ class Comb:
         self.nbases = len(bases) // 32
         self._h = ctypes.c_void_p()
         check(lib().bpg_comb_create(ctx._h, bases, self.nbases, ctypes.byref(self._h)))
+        ctx._children.add(self)
 
     def close(self):
         if self._h:
