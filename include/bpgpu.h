@@ -82,6 +82,14 @@ const char* bpg_profile_phase_name(int phase);
  * src/generators.rs:32-71,158-235).  BPG_ERR_DECODE if any encoding is invalid. */
 int bpg_table_upload(bpg_ctx* ctx, const uint8_t* points_compressed, size_t n, bpg_table** out);
 int bpg_table_upload_dev(bpg_ctx* ctx, const void* d_points_compressed, size_t n, bpg_table** out);
+/* Turn a table into a *windowed* table: besides P_i it then holds 2^(c w) P_i for every
+ * window w of a c-bit signed-digit decomposition (W = ceil(255/c) times the memory), so
+ * that MSMs over it need no doublings at all.  c = 0 picks c from the table length.  One-time
+ * cost of ~240 doublings per point; meant for generator tables that live in HBM for many
+ * proofs ("uploaded once in precomputed affine-Niels form").  MSMs over a windowed table
+ * always use its c. */
+int bpg_table_set_windows(bpg_ctx* ctx, bpg_table* t, int c);
+int bpg_table_window(const bpg_table* t); /* 0 = plain */
 size_t bpg_table_len(const bpg_table* t);
 void bpg_table_free(bpg_table* t);
 
@@ -100,6 +108,20 @@ int bpg_msm(bpg_ctx* ctx, const uint8_t* scalars_le, const uint8_t* points_compr
 int bpg_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t offset, size_t n,
                   const uint8_t* scalars_le, int n_sets, uint8_t* out /* n_sets*32 */);
 
+/* Indexed form: term t = scalars[t] * table[point_ids[t]], added into out[set_ids[t]]
+ * (set_ids NULL = all set 0).  One launch forms A_I, A_O and S from (B_blinding, G, H)
+ * (reference src/r1cs/prover.rs:465-494, 532-565). */
+int bpg_msm_table_indexed(bpg_ctx* ctx, const bpg_table* table, const uint32_t* point_ids, const uint8_t* set_ids,
+                          const uint8_t* scalars_le, size_t n_terms, int n_sets, uint8_t* out /* n_sets*32 */);
+
+/* One sum over n_adhoc compressed points followed by nsegs ranges of resident tables:
+ *   out = sum_{i<n_adhoc} s[i]*adhoc[i] + sum_seg sum_{k<lens[seg]} s[..]*tabs[seg][offs[seg]+k]
+ * with the scalars in that order.  This is the verifier's single "mega" MSM over
+ * [A_I1..S2, V_*, T_*, B, B_blinding | G | H | L_*, R_*] (reference
+ * src/r1cs/verifier.rs:516-547) and `InnerProductProof::verify`'s MSM (:353-368). */
+int bpg_msm_mixed(bpg_ctx* ctx, const uint8_t* adhoc_points, size_t n_adhoc, const bpg_table* const* tabs,
+                  const size_t* offs, const size_t* lens, int nsegs, const uint8_t* scalars_le, uint8_t out[32]);
+
 /* Device-resident form: d_scalars (n_sets*n*32 bytes, 16-byte aligned) already in
  * HBM; writes n_sets extended points (4x8 uint32 limbs X,Y,Z,T = 128 bytes each)
  * to d_out_ext.  This is the per-rank partial sum of a sharded MSM. */
@@ -112,6 +134,41 @@ int bpg_dev_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t offset, size_
  * either may be NULL. */
 int bpg_dev_sum_encode(bpg_ctx* ctx, const void* d_parts, int n_parts, int n_sets, void* d_out_bytes,
                        void* d_out_ext);
+
+/* ---- inner-product argument --------------------------------------------------------
+ * Device-resident state for `InnerProductProof::create` (reference
+ * src/inner_product_proof.rs:49-193).  The transcript stays with the caller, hence the
+ * split per round:
+ *     bpg_ipp_begin(...)                       // vectors go to HBM once
+ *     while (bpg_ipp_rounds_left(st)) {
+ *        bpg_ipp_round_LR(st, L, R);           // :87-114 / :156-172  cross terms + the two MSMs
+ *        transcript.append(L), append(R); u = challenge            (caller, :119-123)
+ *        bpg_ipp_round_fold(st, u, u_inv);     // fold_witness, :202-248
+ *     }
+ *     bpg_ipp_finish(st, a, b);                // :187-192
+ * G, H: tables holding the generator vectors G_vec = G[g_off .. g_off+n), H_vec likewise;
+ * G_factors/H_factors: n scalars each or NULL for all-ones (:51-52); a, b: n scalars each.
+ * Errors: BPG_ERR_POW2 if n is not a power of two (assert at :69), BPG_ERR_CAPACITY if a
+ * table is too short, BPG_ERR_DECODE for an invalid Q. */
+typedef struct bpg_ipp bpg_ipp;
+int bpg_ipp_begin(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off, size_t n,
+                  const uint8_t Q[32], const uint8_t* G_factors, const uint8_t* H_factors, const uint8_t* a,
+                  const uint8_t* b, bpg_ipp** out);
+/* same with the four scalar vectors already in HBM (device pointers; factors may be NULL) */
+int bpg_ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off, size_t n,
+                      const uint8_t Q[32], const void* d_G_factors, const void* d_H_factors, const void* d_a,
+                      const void* d_b, bpg_ipp** out);
+/* Generators and the base of Q all live in one *windowed* table: G_vec = shared[g_base..),
+ * H_vec = shared[h_base..), Q = q_mul * shared[q_id] (q_mul NULL = 1).  This is how the R1CS
+ * prover calls it (Q = w*B, reference src/r1cs/prover.rs:686-708): no per-proof table work. */
+int bpg_ipp_begin_shared(bpg_ctx* ctx, const bpg_table* shared, size_t g_base, size_t h_base, size_t q_id,
+                         const uint8_t q_mul[32], size_t n, const uint8_t* G_factors, const uint8_t* H_factors,
+                         const uint8_t* a, const uint8_t* b, bpg_ipp** out);
+size_t bpg_ipp_rounds_left(const bpg_ipp* st);
+int bpg_ipp_round_LR(bpg_ipp* st, uint8_t L[32], uint8_t R[32]);
+int bpg_ipp_round_fold(bpg_ipp* st, const uint8_t u[32], const uint8_t u_inv[32]);
+int bpg_ipp_finish(bpg_ipp* st, uint8_t a[32], uint8_t b[32]);
+void bpg_ipp_free(bpg_ipp* st);
 
 /* ---- fixed-base multiplication (comb) ---------------------------------------------
  * A comb holds, for each of nbases points P_t, the 64x8 affine-Niels multiples
@@ -128,6 +185,82 @@ int bpg_comb_mul(bpg_ctx* ctx, const bpg_comb* comb, const uint8_t* scalars_le /
 /* device-resident: either output may be NULL (bytes: n*32, ext: n*128) */
 int bpg_dev_comb_mul(bpg_ctx* ctx, const bpg_comb* comb, const void* d_scalars, size_t n, void* d_out_bytes,
                      void* d_out_ext);
+
+/* ==== host mirror of the reference's protocol layer ==================================
+ * C bindings of the C++ host code in mpc_bulletproof_b200/csrc/host/: the transcript,
+ * the generators as resident tables, InnerProductProof and the R1CS Prover/Verifier with
+ * the reference's method names, argument meaning and error behaviour.  Group work is done
+ * by the entry points above; constraint-system bookkeeping and the transcript stay on the
+ * CPU as in the reference. */
+
+/* ---- transcript: merlin::Transcript + TranscriptProtocol (reference src/transcript.rs:25-121) */
+typedef struct bpg_transcript bpg_transcript;
+bpg_transcript* bpg_transcript_new(const uint8_t* label, size_t len);
+bpg_transcript* bpg_transcript_clone(const bpg_transcript* t);
+void bpg_transcript_free(bpg_transcript* t);
+void bpg_transcript_append_message(bpg_transcript* t, const char* label, const uint8_t* msg, size_t len);
+void bpg_transcript_append_u64(bpg_transcript* t, const char* label, uint64_t v);
+void bpg_transcript_challenge_bytes(bpg_transcript* t, const char* label, uint8_t* out, size_t len);
+void bpg_transcript_challenge_scalar(bpg_transcript* t, const char* label, uint8_t out[32]);
+
+/* ---- generators: PedersenGens{B, B_blinding} + BulletproofGens party 0 (reference
+ * src/generators.rs:32-71,158-235) uploaded once as ONE windowed table
+ * [G (capacity) | H (capacity) | B | B_blinding] plus a comb for (B, B_blinding). */
+typedef struct bpg_gens bpg_gens;
+int bpg_gens_new(bpg_ctx* ctx, const uint8_t* G, const uint8_t* H, size_t capacity, const uint8_t B[32],
+                 const uint8_t B_blinding[32], bpg_gens** out);
+void bpg_gens_free(bpg_gens* g);
+size_t bpg_gens_capacity(const bpg_gens* g);
+const bpg_table* bpg_gens_table(const bpg_gens* g);
+/* PedersenGens::commit, batched: out[i] = values[i]*B + blindings[i]*B_blinding */
+int bpg_pedersen_commit(bpg_ctx* ctx, const bpg_gens* g, const uint8_t* values, const uint8_t* blindings, size_t n,
+                        uint8_t* out);
+
+/* ---- InnerProductProof::create / ::verify (reference src/inner_product_proof.rs:49-193, 317-372).
+ * Proof bytes: (L_j R_j)_j || a || b, 32 bytes each (:388-397).  create appends to the
+ * transcript exactly as the reference does (dom-sep, n, then L, R per round). */
+int bpg_ipp_create(bpg_ctx* ctx, bpg_transcript* t, const uint8_t Q[32], const uint8_t* G_factors,
+                   const uint8_t* H_factors, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off,
+                   size_t n, const uint8_t* a, const uint8_t* b, uint8_t* proof_out, size_t proof_cap,
+                   size_t* proof_len);
+/* BPG_OK, BPG_ERR_VERIFY (ProofError::VerificationError) or BPG_ERR_DECODE (FormatError) */
+int bpg_ipp_verify(bpg_ctx* ctx, bpg_transcript* t, size_t n, const uint8_t* G_factors, const uint8_t* H_factors,
+                   const uint8_t P[32], const uint8_t Q[32], const bpg_table* G, size_t g_off, const bpg_table* H,
+                   size_t h_off, const uint8_t* proof, size_t proof_len);
+
+/* ---- r1cs::Prover / r1cs::Verifier (reference src/r1cs/prover.rs, src/r1cs/verifier.rs).
+ * A bpg_cs is one of the two; both implement the ConstraintSystem methods
+ * (src/r1cs/constraint_system.rs:55-208).  Variables are opaque 64-bit handles, linear
+ * combinations are arrays of (variable, coefficient) terms. */
+typedef struct bpg_cs bpg_cs;
+typedef uint64_t bpg_var;
+typedef struct {
+  bpg_var var;
+  uint8_t coeff[32];
+} bpg_term;
+typedef int (*bpg_randomized_cb)(bpg_cs* cs, void* user);
+bpg_var bpg_var_one(void); /* Variable::One() */
+int bpg_prover_new(bpg_ctx* ctx, const bpg_gens* gens, bpg_transcript* t, bpg_cs** out);   /* Prover::new   */
+int bpg_verifier_new(bpg_ctx* ctx, const bpg_gens* gens, bpg_transcript* t, bpg_cs** out); /* Verifier::new */
+void bpg_cs_free(bpg_cs* cs);
+int bpg_prover_commit(bpg_cs* cs, const uint8_t v[32], const uint8_t v_blinding[32], uint8_t V_out[32], bpg_var* var);
+int bpg_verifier_commit(bpg_cs* cs, const uint8_t V[32], bpg_var* var);
+int bpg_cs_commit_public(bpg_cs* cs, const uint8_t value[32], bpg_var* var);
+int bpg_cs_multiply(bpg_cs* cs, const bpg_term* left, size_t nl, const bpg_term* right, size_t nr, bpg_var out[3]);
+int bpg_cs_allocate(bpg_cs* cs, const uint8_t* assignment /* NULL on the verifier */, bpg_var* out);
+int bpg_cs_allocate_multiplier(bpg_cs* cs, const uint8_t* l, const uint8_t* r, bpg_var out[3]);
+int bpg_cs_constrain(bpg_cs* cs, const bpg_term* lc, size_t n);
+int bpg_cs_specify_randomized_constraints(bpg_cs* cs, bpg_randomized_cb cb, void* user);
+int bpg_cs_challenge_scalar(bpg_cs* cs, const char* label, uint8_t out[32]); /* only inside a callback */
+int bpg_cs_eval(bpg_cs* cs, const bpg_term* lc, size_t n, uint8_t out[32]);
+size_t bpg_cs_num_multipliers(const bpg_cs* cs);
+size_t bpg_cs_num_constraints(const bpg_cs* cs);
+/* Prover::prove.  The reference draws its blinding scalars from thread_rng()
+ * (prover.rs:435-445); here they come from xoshiro256** seeded with rng_seed, in the same
+ * draw order, so that proofs are reproducible.  BPG_ERR_CAPACITY = InvalidGeneratorsLength. */
+int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+/* Verifier::verify: BPG_OK, BPG_ERR_VERIFY, BPG_ERR_DECODE (FormatError), BPG_ERR_CAPACITY */
+int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof, size_t proof_len);
 
 #ifdef __cplusplus
 }

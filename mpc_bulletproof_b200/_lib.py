@@ -28,7 +28,49 @@ _P = ctypes.c_void_p
 _SZ = ctypes.c_size_t
 _I = ctypes.c_int
 
+_U64 = ctypes.c_uint64
+_CP = ctypes.c_char_p
+
+
+class Term(ctypes.Structure):
+    _fields_ = [("var", ctypes.c_uint64), ("coeff", ctypes.c_uint8 * 32)]
+
+
+RANDOMIZED_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p)
+
 _SIGNATURES = {
+    "bpg_transcript_new": (_P, [_P, _SZ]),
+    "bpg_transcript_clone": (_P, [_P]),
+    "bpg_transcript_free": (None, [_P]),
+    "bpg_transcript_append_message": (None, [_P, _CP, _P, _SZ]),
+    "bpg_transcript_append_u64": (None, [_P, _CP, _U64]),
+    "bpg_transcript_challenge_bytes": (None, [_P, _CP, _P, _SZ]),
+    "bpg_transcript_challenge_scalar": (None, [_P, _CP, _P]),
+    "bpg_gens_new": (_I, [_P, _P, _P, _SZ, _P, _P, ctypes.POINTER(_P)]),
+    "bpg_gens_free": (None, [_P]),
+    "bpg_gens_capacity": (_SZ, [_P]),
+    "bpg_gens_table": (_P, [_P]),
+    "bpg_pedersen_commit": (_I, [_P, _P, _P, _P, _SZ, _P]),
+    "bpg_ipp_create": (_I, [_P, _P, _P, _P, _P, _P, _SZ, _P, _SZ, _SZ, _P, _P, _P, _SZ, ctypes.POINTER(_SZ)]),
+    "bpg_ipp_verify": (_I, [_P, _P, _SZ, _P, _P, _P, _P, _P, _SZ, _P, _SZ, _P, _SZ]),
+    "bpg_var_one": (_U64, []),
+    "bpg_prover_new": (_I, [_P, _P, _P, ctypes.POINTER(_P)]),
+    "bpg_verifier_new": (_I, [_P, _P, _P, ctypes.POINTER(_P)]),
+    "bpg_cs_free": (None, [_P]),
+    "bpg_prover_commit": (_I, [_P, _P, _P, _P, ctypes.POINTER(_U64)]),
+    "bpg_verifier_commit": (_I, [_P, _P, ctypes.POINTER(_U64)]),
+    "bpg_cs_commit_public": (_I, [_P, _P, ctypes.POINTER(_U64)]),
+    "bpg_cs_multiply": (_I, [_P, ctypes.POINTER(Term), _SZ, ctypes.POINTER(Term), _SZ, ctypes.POINTER(_U64)]),
+    "bpg_cs_allocate": (_I, [_P, _P, ctypes.POINTER(_U64)]),
+    "bpg_cs_allocate_multiplier": (_I, [_P, _P, _P, ctypes.POINTER(_U64)]),
+    "bpg_cs_constrain": (_I, [_P, ctypes.POINTER(Term), _SZ]),
+    "bpg_cs_specify_randomized_constraints": (_I, [_P, RANDOMIZED_CB, _P]),
+    "bpg_cs_challenge_scalar": (_I, [_P, _CP, _P]),
+    "bpg_cs_eval": (_I, [_P, ctypes.POINTER(Term), _SZ, _P]),
+    "bpg_cs_num_multipliers": (_SZ, [_P]),
+    "bpg_cs_num_constraints": (_SZ, [_P]),
+    "bpg_prover_prove": (_I, [_P, _U64, _P, _SZ, ctypes.POINTER(_SZ)]),
+    "bpg_verifier_verify": (_I, [_P, _P, _SZ]),
     "bpg_init": (_I, [_I, ctypes.POINTER(_P)]),
     "bpg_free": (None, [_P]),
     "bpg_set_stream": (_I, [_P, _P, _I]),
@@ -44,11 +86,23 @@ _SIGNATURES = {
     "bpg_table_upload": (_I, [_P, _P, _SZ, ctypes.POINTER(_P)]),
     "bpg_table_upload_dev": (_I, [_P, _P, _SZ, ctypes.POINTER(_P)]),
     "bpg_table_len": (_SZ, [_P]),
+    "bpg_table_set_windows": (_I, [_P, _P, _I]),
+    "bpg_table_window": (_I, [_P]),
     "bpg_table_free": (None, [_P]),
     "bpg_msm": (_I, [_P, _P, _P, _SZ, _P]),
     "bpg_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),
+    "bpg_msm_table_indexed": (_I, [_P, _P, _P, _P, _P, _SZ, _I, _P]),
+    "bpg_msm_mixed": (_I, [_P, _P, _SZ, _P, _P, _P, _I, _P, _P]),
     "bpg_dev_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),
     "bpg_dev_sum_encode": (_I, [_P, _P, _I, _I, _P, _P]),
+    "bpg_ipp_begin": (_I, [_P, _P, _SZ, _P, _SZ, _SZ, _P, _P, _P, _P, _P, ctypes.POINTER(_P)]),
+    "bpg_ipp_begin_dev": (_I, [_P, _P, _SZ, _P, _SZ, _SZ, _P, _P, _P, _P, _P, ctypes.POINTER(_P)]),
+    "bpg_ipp_begin_shared": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _SZ, _P, _P, _P, _P, ctypes.POINTER(_P)]),
+    "bpg_ipp_rounds_left": (_SZ, [_P]),
+    "bpg_ipp_round_LR": (_I, [_P, _P, _P]),
+    "bpg_ipp_round_fold": (_I, [_P, _P, _P]),
+    "bpg_ipp_finish": (_I, [_P, _P, _P]),
+    "bpg_ipp_free": (None, [_P]),
     "bpg_comb_create": (_I, [_P, _P, _I, ctypes.POINTER(_P)]),
     "bpg_comb_free": (None, [_P]),
     "bpg_comb_mul": (_I, [_P, _P, _P, _SZ, _P]),

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "msm_kernels.cuh"
+#include "ipp_kernels.cuh"
 
 using namespace bpg;
 
@@ -45,8 +46,10 @@ struct bpg_ctx {
 
 struct bpg_table {
   bpg_ctx* ctx;
-  uint32_t* niels;  // n * 24 words
+  uint32_t* niels;  // n * 24 words; windowed: [W][n] * 24 words
   size_t n;
+  int win_c = 0;    // 0: plain; otherwise the window width the multiples 2^(c w) P_i were built for
+  int win_W = 1;
 };
 
 #define CK(call)                                  \
@@ -309,7 +312,8 @@ static int pick_window(size_t n_per_set, int forced) {
   return best_c;
 }
 
-static void make_cfg(MsmCfg& cfg, size_t n_terms, size_t n_points, int nsets, int c) {
+static void make_cfg(MsmCfg& cfg, size_t n_terms, size_t n_points, int nsets, int c, size_t win_stride = 0) {
+  cfg.win_stride = (uint32_t)win_stride;
   cfg.c = c;
   cfg.W = (255 + c - 1) / c;
   cfg.nb = 1u << (c - 1);
@@ -336,7 +340,7 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 // be null (implicit: term t -> point t % n_points of `table_base`, set t / n_points).
 static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points, const uint32_t* d_scalars,
                        size_t n_terms, const uint8_t* d_set_ids, const uint32_t* d_point_ids, int nsets,
-                       uint32_t* d_out_ext) {
+                       uint32_t* d_out_ext, int win_c = 0, size_t win_stride = 0) {
   if (nsets <= 0) return BPG_ERR_ARG;
   if (n_terms == 0) {
     // empty sum: identity for every set
@@ -350,8 +354,8 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   }
   if (n_terms >= (1u << 31)) return BPG_ERR_ARG;
   MsmCfg cfg;
-  int c = pick_window((n_terms + nsets - 1) / nsets, ctx->forced_c);
-  make_cfg(cfg, n_terms, n_points, nsets, c);
+  int c = win_c ? win_c : pick_window((n_terms + nsets - 1) / nsets, ctx->forced_c);
+  make_cfg(cfg, n_terms, n_points, nsets, c, win_c ? win_stride : 0);
   if ((uint64_t)cfg.nwin * cfg.nb >= (1ull << 31)) return BPG_ERR_ARG;
 
   size_t ntiles = (cfg.B + SCAN_TILE - 1) / SCAN_TILE;
@@ -421,7 +425,7 @@ extern "C" int bpg_dev_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t of
   if (offset + n > table->n) return BPG_ERR_CAPACITY;
   CK(cudaSetDevice(ctx->device));
   return msm_enqueue(ctx, table->niels + offset * 24, n, (const uint32_t*)d_scalars, n * (size_t)n_sets, nullptr,
-                     nullptr, n_sets, (uint32_t*)d_out_ext);
+                     nullptr, n_sets, (uint32_t*)d_out_ext, table->win_c, table->n);
 }
 
 extern "C" int bpg_dev_sum_encode(bpg_ctx* ctx, const void* d_parts, int n_parts, int n_sets, void* d_out_bytes,
@@ -449,7 +453,7 @@ extern "C" int bpg_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t offset
   uint32_t* d_ext = (uint32_t*)ctx->d_small;
   uint8_t* d_bytes = ctx->d_small + (size_t)n_sets * 128;
   rc = msm_enqueue(ctx, table->niels + offset * 24, n, (const uint32_t*)ctx->d_stage, n * (size_t)n_sets, nullptr,
-                   nullptr, n_sets, d_ext);
+                   nullptr, n_sets, d_ext, table->win_c, table->n);
   if (rc) return rc;
   rc = bpg_dev_sum_encode(ctx, d_ext, 1, n_sets, d_bytes, nullptr);
   if (rc) return rc;
@@ -567,4 +571,405 @@ extern "C" int bpg_comb_mul(bpg_ctx* ctx, const bpg_comb* comb, const uint8_t* s
   CK(cudaMemcpyAsync(out, d_out, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return BPG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// windowed tables
+// ---------------------------------------------------------------------------
+extern "C" int bpg_table_set_windows(bpg_ctx* ctx, bpg_table* t, int c) {
+  if (!ctx || !t || c < 0 || c > 20) return BPG_ERR_ARG;
+  if (t->win_c) return BPG_ERR_ARG;  // already windowed
+  CK(cudaSetDevice(ctx->device));
+  if (c == 0) c = pick_window(t->n, ctx->forced_c);
+  if (c < 2) c = 2;
+  int W = (255 + c - 1) / c;
+  if ((uint64_t)W * t->n >= (1ull << 31)) return BPG_ERR_ARG;
+  if (t->n == 0) {
+    t->win_c = c;
+    t->win_W = W;
+    return BPG_OK;
+  }
+  uint32_t* out = nullptr;
+  cudaError_t e = cudaMalloc(&out, (size_t)W * t->n * 96);
+  if (e != cudaSuccess) {
+    ctx->last_cuda = (int)e;
+    return BPG_ERR_NOMEM;
+  }
+  const size_t CH = 1 << 16;
+  size_t chunk = std::min(CH, t->n);
+  size_t ext_bytes = align_up((size_t)(W - 1) * chunk * 128);
+  size_t zp_bytes = align_up((size_t)(W - 1) * chunk * 32);
+  int rc = ensure_ws(ctx, ext_bytes + zp_bytes);
+  if (rc) {
+    cudaFree(out);
+    return rc;
+  }
+  for (size_t first = 0; first < t->n; first += chunk) {
+    size_t cnt = std::min(chunk, t->n - first);
+    k_window_chain<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(
+        t->niels, (uint32_t)t->n, (uint32_t)first, (uint32_t)cnt, c, W, (uint32_t*)ctx->ws,
+        (uint32_t*)(ctx->ws + ext_bytes), out);
+    ctx->launches++;
+  }
+  cudaError_t se = cudaStreamSynchronize(ctx->stream);
+  if (se != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+    ctx->last_cuda = (int)se;
+    cudaFree(out);
+    return BPG_ERR_CUDA;
+  }
+  cudaFree(t->niels);
+  t->niels = out;
+  t->win_c = c;
+  t->win_W = W;
+  return BPG_OK;
+}
+extern "C" int bpg_table_window(const bpg_table* t) { return t ? t->win_c : 0; }
+
+// ---------------------------------------------------------------------------
+// inner-product argument: device-resident state, one MSM per round
+// ---------------------------------------------------------------------------
+struct bpg_ipp {
+  bpg_ctx* ctx;
+  size_t n;        // original length (power of two)
+  size_t m;        // current length
+  const bpg_table* tab;  // windowed table the round MSMs run over
+  bpg_table* own_tab;    // non-null when the state built its own [G | H | Q] table
+  bool has_qmul;         // cross terms are multiplied by q_mul (Q = q_mul * table[q_id])
+  uint8_t* buf;    // one allocation for everything below
+  uint32_t *a, *b, *wG, *wH, *scalars, *point_ids, *partials, *u_pair, *out_ext;
+  uint32_t* q_mul;
+  uint8_t *set_ids, *out_bytes;
+  bool lr_done;
+};
+
+static int table_alloc_plain(bpg_ctx* ctx, size_t n, bpg_table** out) {
+  bpg_table* t = new (std::nothrow) bpg_table();
+  if (!t) return BPG_ERR_NOMEM;
+  t->ctx = ctx;
+  t->n = n;
+  cudaError_t e = cudaMalloc(&t->niels, std::max<size_t>(n, 1) * 96);
+  if (e != cudaSuccess) {
+    delete t;
+    ctx->last_cuda = (int)e;
+    return BPG_ERR_NOMEM;
+  }
+  *out = t;
+  return BPG_OK;
+}
+
+// d_* pointers are device pointers; factors may be null (all ones).
+// Either (G, H, Q_host) are given and the state builds its own windowed [G | H | Q] table,
+// or `shared` is a windowed table that already holds the generators at g_base/h_base and a
+// base point at q_id with Q = q_mul * shared[q_id] (the R1CS prover's Q = w*B).
+static int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off, size_t n,
+                         const uint8_t* Q_host, const bpg_table* shared, size_t g_base, size_t h_base, size_t q_id,
+                         const uint8_t* q_mul_host, const uint32_t* d_gf, const uint32_t* d_hf, const uint32_t* d_a,
+                         const uint32_t* d_b, bpg_ipp** out) {
+  if (n == 0 || (n & (n - 1))) return BPG_ERR_POW2;
+  if (n >= (1u << 28)) return BPG_ERR_ARG;
+  if (shared) {
+    if (g_base + n > shared->n || h_base + n > shared->n || q_id >= shared->n) return BPG_ERR_CAPACITY;
+    if (!shared->win_c && n > 1) return BPG_ERR_ARG;
+  } else if (g_off + n > G->n || h_off + n > H->n) {
+    return BPG_ERR_CAPACITY;
+  }
+  bpg_ipp* st = new (std::nothrow) bpg_ipp();
+  if (!st) return BPG_ERR_NOMEM;
+  memset(st, 0, sizeof *st);
+  st->ctx = ctx;
+  st->n = st->m = n;
+  int rc = BPG_OK;
+  size_t T = 2 * n + 2;
+  size_t nparts = 256;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  size_t o_a = take(n * 32), o_b = take(n * 32), o_wG = take(n * 32), o_wH = take(n * 32);
+  size_t o_sc = take(T * 32), o_pid = take(T * 4), o_set = take(T), o_part = take(nparts * 64);
+  size_t o_u = take(64), o_ext = take(2 * 128), o_bytes = take(64), o_q = take(32), o_qm = take(32);
+  do {
+    cudaError_t e = cudaMalloc(&st->buf, off);
+    if (e != cudaSuccess) { ctx->last_cuda = (int)e; rc = BPG_ERR_NOMEM; break; }
+    st->a = (uint32_t*)(st->buf + o_a); st->b = (uint32_t*)(st->buf + o_b);
+    st->wG = (uint32_t*)(st->buf + o_wG); st->wH = (uint32_t*)(st->buf + o_wH);
+    st->scalars = (uint32_t*)(st->buf + o_sc); st->point_ids = (uint32_t*)(st->buf + o_pid);
+    st->set_ids = st->buf + o_set; st->partials = (uint32_t*)(st->buf + o_part);
+    st->u_pair = (uint32_t*)(st->buf + o_u); st->out_ext = (uint32_t*)(st->buf + o_ext);
+    st->out_bytes = st->buf + o_bytes;
+    st->q_mul = (uint32_t*)(st->buf + o_qm);
+    uint8_t* d_q = st->buf + o_q;
+    cudaStream_t s = ctx->stream;
+    if (cudaMemcpyAsync(st->a, d_a, n * 32, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(st->b, d_b, n * 32, cudaMemcpyDeviceToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+    unsigned gn = (unsigned)((n + 255) / 256);
+    k_ipp_init_weights<<<gn, 256, 0, s>>>(d_gf, d_hf, (uint32_t)n, st->wG, st->wH);
+    ctx->launches++;
+    if (shared) {
+      st->tab = shared;
+      st->has_qmul = q_mul_host != nullptr;
+      if (q_mul_host) {
+        memcpy(ctx->h_pinned + 512, q_mul_host, 32);
+        if (cudaMemcpyAsync(st->q_mul, ctx->h_pinned + 512, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+      }
+      k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, (uint32_t)g_base, (uint32_t)h_base, (uint32_t)q_id);
+      ctx->launches++;
+      if (cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+    } else {
+      k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, 0u, (uint32_t)n, (uint32_t)(2 * n));
+      ctx->launches++;
+      // combined table [G | H | Q]
+      rc = table_alloc_plain(ctx, 2 * n + 1, &st->own_tab);
+      if (rc) break;
+      st->tab = st->own_tab;
+      if (cudaMemcpyAsync(st->own_tab->niels, G->niels + g_off * 24, n * 96, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+          cudaMemcpyAsync(st->own_tab->niels + n * 24, H->niels + h_off * 24, n * 96, cudaMemcpyDeviceToDevice, s) !=
+              cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+      memcpy(ctx->h_pinned + 512, Q_host, 32);
+      uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small);
+      if (cudaMemsetAsync(bad, 0, 4, s) != cudaSuccess ||
+          cudaMemcpyAsync(d_q, ctx->h_pinned + 512, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+      k_decode_to_niels<<<1, 128, 0, s>>>(d_q, 1, st->own_tab->niels + 2 * n * 24, bad);
+      ctx->launches++;
+      uint32_t* hbad = reinterpret_cast<uint32_t*>(ctx->h_pinned);
+      if (cudaMemcpyAsync(hbad, bad, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+          cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+      if (*hbad) { rc = BPG_ERR_DECODE; break; }
+      if (n > 1) {
+        rc = bpg_table_set_windows(ctx, st->own_tab, pick_window(n + 1, ctx->forced_c));
+        if (rc) break;
+      }
+    }
+  } while (0);
+  if (rc != BPG_OK) {
+    if (st->own_tab) bpg_table_free(st->own_tab);
+    if (st->buf) cudaFree(st->buf);
+    delete st;
+    return rc;
+  }
+  *out = st;
+  return BPG_OK;
+}
+
+extern "C" int bpg_ipp_begin(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off,
+                             size_t n, const uint8_t Q[32], const uint8_t* G_factors, const uint8_t* H_factors,
+                             const uint8_t* a, const uint8_t* b, bpg_ipp** out) {
+  if (!ctx || !G || !H || !Q || !a || !b || !out) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_stage(ctx, 4 * n * 32 + 64);
+  if (rc) return rc;
+  uint8_t* d = ctx->d_stage;
+  CK(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d + n * 32, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (G_factors) CK(cudaMemcpyAsync(d + 2 * n * 32, G_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (H_factors) CK(cudaMemcpyAsync(d + 3 * n * 32, H_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  return ipp_begin_dev(ctx, G, g_off, H, h_off, n, Q, nullptr, 0, 0, 0, nullptr,
+                       G_factors ? (const uint32_t*)(d + 2 * n * 32) : nullptr,
+                       H_factors ? (const uint32_t*)(d + 3 * n * 32) : nullptr, (const uint32_t*)d,
+                       (const uint32_t*)(d + n * 32), out);
+}
+
+extern "C" int bpg_ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off,
+                                 size_t n, const uint8_t Q[32], const void* d_G_factors, const void* d_H_factors,
+                                 const void* d_a, const void* d_b, bpg_ipp** out) {
+  if (!ctx || !G || !H || !Q || !d_a || !d_b || !out) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  return ipp_begin_dev(ctx, G, g_off, H, h_off, n, Q, nullptr, 0, 0, 0, nullptr, (const uint32_t*)d_G_factors,
+                       (const uint32_t*)d_H_factors, (const uint32_t*)d_a, (const uint32_t*)d_b, out);
+}
+
+// Generators and the base of Q live in one windowed table (the R1CS prover: G at g_base, H at
+// h_base, Q = q_mul * shared[q_id] with q_id the Pedersen base B and q_mul the challenge w).
+extern "C" int bpg_ipp_begin_shared(bpg_ctx* ctx, const bpg_table* shared, size_t g_base, size_t h_base, size_t q_id,
+                                    const uint8_t q_mul[32], size_t n, const uint8_t* G_factors,
+                                    const uint8_t* H_factors, const uint8_t* a, const uint8_t* b, bpg_ipp** out) {
+  if (!ctx || !shared || !a || !b || !out) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_stage(ctx, 4 * n * 32 + 64);
+  if (rc) return rc;
+  uint8_t* d = ctx->d_stage;
+  CK(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d + n * 32, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (G_factors) CK(cudaMemcpyAsync(d + 2 * n * 32, G_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (H_factors) CK(cudaMemcpyAsync(d + 3 * n * 32, H_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  return ipp_begin_dev(ctx, nullptr, 0, nullptr, 0, n, nullptr, shared, g_base, h_base, q_id, q_mul,
+                       G_factors ? (const uint32_t*)(d + 2 * n * 32) : nullptr,
+                       H_factors ? (const uint32_t*)(d + 3 * n * 32) : nullptr, (const uint32_t*)d,
+                       (const uint32_t*)(d + n * 32), out);
+}
+
+extern "C" size_t bpg_ipp_rounds_left(const bpg_ipp* st) {
+  size_t r = 0;
+  if (!st) return 0;
+  for (size_t m = st->m; m > 1; m >>= 1) r++;
+  return r;
+}
+
+extern "C" int bpg_ipp_round_LR(bpg_ipp* st, uint8_t L[32], uint8_t R[32]) {
+  if (!st || !L || !R) return BPG_ERR_ARG;
+  if (st->m <= 1 || st->lr_done) return BPG_ERR_ARG;
+  bpg_ctx* ctx = st->ctx;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  size_t n = st->n, m = st->m, h = m / 2;
+  unsigned gcross = (unsigned)std::min<size_t>(256, (h + IPP_THREADS - 1) / IPP_THREADS);
+  prof_mark(ctx, BPG_PROF_OTHER);
+  k_ipp_cross<<<gcross, IPP_THREADS, 0, s>>>(st->a, st->b, (uint32_t)h, st->partials);
+  LAUNCH_CHECK();
+  k_ipp_round_scalars<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st->a, st->b, st->wG, st->wH, (uint32_t)n,
+                                                                  (uint32_t)m, st->scalars, st->set_ids);
+  LAUNCH_CHECK();
+  k_ipp_cross_finish<<<1, IPP_THREADS, 0, s>>>(st->partials, gcross, (uint32_t)n, st->has_qmul ? st->q_mul : nullptr,
+                                               st->scalars, st->set_ids);
+  LAUNCH_CHECK();
+  int rc = msm_enqueue(ctx, st->tab->niels, st->tab->n, st->scalars, 2 * n + 2, st->set_ids, st->point_ids, 2,
+                       st->out_ext, st->tab->win_c, st->tab->n);
+  if (rc) return rc;
+  rc = bpg_dev_sum_encode(ctx, st->out_ext, 1, 2, st->out_bytes, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->h_pinned, st->out_bytes, 64, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  memcpy(L, ctx->h_pinned, 32);
+  memcpy(R, ctx->h_pinned + 32, 32);
+  st->lr_done = true;
+  return BPG_OK;
+}
+
+extern "C" int bpg_ipp_round_fold(bpg_ipp* st, const uint8_t u[32], const uint8_t u_inv[32]) {
+  if (!st || !u || !u_inv) return BPG_ERR_ARG;
+  if (st->m <= 1 || !st->lr_done) return BPG_ERR_ARG;
+  bpg_ctx* ctx = st->ctx;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  memcpy(ctx->h_pinned + 1024, u, 32);
+  memcpy(ctx->h_pinned + 1056, u_inv, 32);
+  CK(cudaMemcpyAsync(st->u_pair, ctx->h_pinned + 1024, 64, cudaMemcpyHostToDevice, s));
+  prof_mark(ctx, BPG_PROF_OTHER);
+  k_ipp_fold<<<(unsigned)((st->n + 255) / 256), 256, 0, s>>>(st->a, st->b, st->wG, st->wH, (uint32_t)st->n,
+                                                             (uint32_t)st->m, st->u_pair);
+  LAUNCH_CHECK();
+  prof_mark(ctx, -1);
+  // h_pinned is reused by the next call: make sure the copy has been consumed
+  CK(cudaStreamSynchronize(s));
+  st->m /= 2;
+  st->lr_done = false;
+  return BPG_OK;
+}
+
+extern "C" int bpg_ipp_finish(bpg_ipp* st, uint8_t a[32], uint8_t b[32]) {
+  if (!st || !a || !b) return BPG_ERR_ARG;
+  if (st->m != 1) return BPG_ERR_ARG;
+  bpg_ctx* ctx = st->ctx;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->h_pinned, st->a, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_pinned + 32, st->b, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(a, ctx->h_pinned, 32);
+  memcpy(b, ctx->h_pinned + 32, 32);
+  return BPG_OK;
+}
+
+extern "C" void bpg_ipp_free(bpg_ipp* st) {
+  if (!st) return;
+  cudaSetDevice(st->ctx->device);
+  cudaStreamSynchronize(st->ctx->stream);
+  if (st->own_tab) bpg_table_free(st->own_tab);
+  if (st->buf) cudaFree(st->buf);
+  delete st;
+}
+
+// ---------------------------------------------------------------------------
+// indexed MSM: term t = scalars[t] * table[point_ids[t]] accumulated into out[set_ids[t]]
+// ---------------------------------------------------------------------------
+extern "C" int bpg_msm_table_indexed(bpg_ctx* ctx, const bpg_table* table, const uint32_t* point_ids,
+                                     const uint8_t* set_ids, const uint8_t* scalars_le, size_t n_terms, int n_sets,
+                                     uint8_t* out) {
+  if (!ctx || !table || !out || n_sets <= 0 || n_sets > 255 || (n_terms && (!point_ids || !scalars_le))) return BPG_ERR_ARG;
+  if ((size_t)n_sets * 160 > SMALL_BYTES) return BPG_ERR_ARG;
+  for (size_t t = 0; t < n_terms; t++) {
+    if (point_ids[t] >= table->n) return BPG_ERR_CAPACITY;
+    if (set_ids && set_ids[t] >= n_sets) return BPG_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  size_t o_pid = align_up(n_terms * 32), o_set = o_pid + align_up(n_terms * 4);
+  int rc = ensure_stage(ctx, o_set + align_up(n_terms) + 64);
+  if (rc) return rc;
+  uint8_t* d = ctx->d_stage;
+  cudaStream_t s = ctx->stream;
+  if (n_terms) {
+    CK(cudaMemcpyAsync(d, scalars_le, n_terms * 32, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d + o_pid, point_ids, n_terms * 4, cudaMemcpyHostToDevice, s));
+    if (set_ids) CK(cudaMemcpyAsync(d + o_set, set_ids, n_terms, cudaMemcpyHostToDevice, s));
+    else CK(cudaMemsetAsync(d + o_set, 0, n_terms, s));
+  }
+  uint32_t* d_ext = (uint32_t*)ctx->d_small;
+  uint8_t* d_bytes = ctx->d_small + (size_t)n_sets * 128;
+  rc = msm_enqueue(ctx, table->niels, table->n, (const uint32_t*)d, n_terms, d + o_set, (const uint32_t*)(d + o_pid),
+                   n_sets, d_ext, table->win_c, table->n);
+  if (rc) return rc;
+  rc = bpg_dev_sum_encode(ctx, d_ext, 1, n_sets, d_bytes, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->h_pinned, d_bytes, (size_t)n_sets * 32, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  memcpy(out, ctx->h_pinned, (size_t)n_sets * 32);
+  return BPG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// one MSM over ad-hoc (compressed) points followed by ranges of resident tables
+// ---------------------------------------------------------------------------
+extern "C" int bpg_msm_mixed(bpg_ctx* ctx, const uint8_t* adhoc_points, size_t n_adhoc,
+                             const bpg_table* const* tabs, const size_t* offs, const size_t* lens, int nsegs,
+                             const uint8_t* scalars_le, uint8_t out[32]) {
+  if (!ctx || !out || (n_adhoc && !adhoc_points) || nsegs < 0 || (nsegs && (!tabs || !offs || !lens))) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  size_t total = n_adhoc;
+  for (int i = 0; i < nsegs; i++) {
+    if (!tabs[i]) return BPG_ERR_ARG;
+    if (offs[i] + lens[i] > tabs[i]->n) return BPG_ERR_CAPACITY;
+    total += lens[i];
+  }
+  if (total && !scalars_le) return BPG_ERR_ARG;
+  bpg_table* t = nullptr;
+  int rc = table_alloc_plain(ctx, total, &t);
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream;
+  do {
+    rc = ensure_stage(ctx, std::max<size_t>(total * 32 + n_adhoc * 32, 64));
+    if (rc) break;
+    uint8_t* d_sc = ctx->d_stage;
+    uint8_t* d_pts = ctx->d_stage + total * 32;
+    uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small + 1024);
+    rc = BPG_ERR_CUDA;
+    if (cudaMemsetAsync(bad, 0, 4, s) != cudaSuccess) break;
+    if (total && cudaMemcpyAsync(d_sc, scalars_le, total * 32, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
+    if (n_adhoc) {
+      if (cudaMemcpyAsync(d_pts, adhoc_points, n_adhoc * 32, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
+      k_decode_to_niels<<<(unsigned)((n_adhoc + 127) / 128), 128, 0, s>>>(d_pts, (uint32_t)n_adhoc, t->niels, bad);
+      ctx->launches++;
+    }
+    size_t pos = n_adhoc;
+    bool ok = true;
+    for (int i = 0; i < nsegs && ok; i++) {
+      if (lens[i] && cudaMemcpyAsync(t->niels + pos * 24, tabs[i]->niels + offs[i] * 24, lens[i] * 96,
+                                     cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+        ok = false;
+      pos += lens[i];
+    }
+    if (!ok) break;
+    uint32_t* d_ext = (uint32_t*)ctx->d_small;
+    uint8_t* d_bytes = ctx->d_small + 128;
+    rc = msm_enqueue(ctx, t->niels, total, (const uint32_t*)d_sc, total, nullptr, nullptr, 1, d_ext);
+    if (rc) break;
+    rc = bpg_dev_sum_encode(ctx, d_ext, 1, 1, d_bytes, nullptr);
+    if (rc) break;
+    rc = BPG_ERR_CUDA;
+    if (cudaMemcpyAsync(ctx->h_pinned, d_bytes, 32, cudaMemcpyDeviceToHost, s) != cudaSuccess) break;
+    if (cudaMemcpyAsync(ctx->h_pinned + 64, bad, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) break;
+    cudaError_t se = cudaStreamSynchronize(s);
+    if (se != cudaSuccess) { ctx->last_cuda = (int)se; break; }
+    if (*reinterpret_cast<uint32_t*>(ctx->h_pinned + 64)) { rc = BPG_ERR_DECODE; break; }
+    memcpy(out, ctx->h_pinned, 32);
+    rc = BPG_OK;
+  } while (0);
+  bpg_table_free(t);
+  return rc;
 }

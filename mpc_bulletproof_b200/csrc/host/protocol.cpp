@@ -1,0 +1,966 @@
+// Host mirror of the reference's protocol layer on top of the CUDA engine:
+// `InnerProductProof::{create, verification_scalars, verify, to_bytes, from_bytes}`
+// (reference src/inner_product_proof.rs), `r1cs::Prover` / `r1cs::Verifier`
+// (src/r1cs/prover.rs, src/r1cs/verifier.rs), `R1CSProof` bytes (src/r1cs/proof.rs),
+// `PedersenGens` / `BulletproofGens` as resident tables (src/generators.rs).
+//
+// Everything group-valued is done by the device through include/bpgpu.h; what stays
+// here is what the reference also does serially on the CPU: the constraint-system
+// bookkeeping, the transcript, and O(n) scalar preparation.
+#include <array>
+#include <functional>
+#include <memory>
+#include <new>
+#include <vector>
+
+#include "../../../include/bpgpu.h"
+#include "merlin.hpp"
+#include "sc_host.hpp"
+
+using namespace bpg_host;
+
+typedef std::array<uint8_t, 32> Bytes32;
+
+static inline void sc_bytes(const Scalar& s, uint8_t* out) { s.to_bytes(out); }
+static std::vector<uint8_t> sc_vec_bytes(const std::vector<Scalar>& v) {
+  std::vector<uint8_t> out(v.size() * 32);
+  for (size_t i = 0; i < v.size(); i++) v[i].to_bytes(out.data() + 32 * i);
+  return out;
+}
+static bool is_identity_enc(const uint8_t p[32]) {
+  uint8_t acc = 0;
+  for (int i = 0; i < 32; i++) acc |= p[i];
+  return acc == 0;
+}
+
+// ---------------------------------------------------------------- transcript C ABI
+struct bpg_transcript {
+  Transcript t;
+  explicit bpg_transcript(const uint8_t* l, size_t n) : t(l, n) {}
+};
+extern "C" bpg_transcript* bpg_transcript_new(const uint8_t* label, size_t len) {
+  return new (std::nothrow) bpg_transcript(label, len);
+}
+extern "C" bpg_transcript* bpg_transcript_clone(const bpg_transcript* t) {
+  return t ? new (std::nothrow) bpg_transcript(*t) : nullptr;
+}
+extern "C" void bpg_transcript_free(bpg_transcript* t) { delete t; }
+extern "C" void bpg_transcript_append_message(bpg_transcript* t, const char* label, const uint8_t* msg, size_t len) {
+  t->t.append_message(label, msg, len);
+}
+extern "C" void bpg_transcript_append_u64(bpg_transcript* t, const char* label, uint64_t v) { t->t.append_u64(label, v); }
+extern "C" void bpg_transcript_challenge_bytes(bpg_transcript* t, const char* label, uint8_t* out, size_t len) {
+  t->t.challenge_bytes(label, out, len);
+}
+extern "C" void bpg_transcript_challenge_scalar(bpg_transcript* t, const char* label, uint8_t out[32]) {
+  t->t.challenge_scalar(label).to_bytes(out);
+}
+
+// ---------------------------------------------------------------- generators
+// One windowed table [G (cap) | H (cap) | B | B_blinding] plus a comb for (B, B_blinding).
+struct bpg_gens {
+  bpg_ctx* ctx;
+  size_t cap;
+  bpg_table* table;
+  bpg_comb* comb;
+  Bytes32 B, Bb;
+  size_t g_base() const { return 0; }
+  size_t h_base() const { return cap; }
+  size_t b_id() const { return 2 * cap; }
+  size_t bb_id() const { return 2 * cap + 1; }
+};
+
+extern "C" int bpg_gens_new(bpg_ctx* ctx, const uint8_t* G, const uint8_t* H, size_t capacity, const uint8_t B[32],
+                            const uint8_t B_blinding[32], bpg_gens** out) {
+  if (!ctx || !B || !B_blinding || !out || (capacity && (!G || !H))) return BPG_ERR_ARG;
+  std::vector<uint8_t> all((2 * capacity + 2) * 32);
+  memcpy(all.data(), G, capacity * 32);
+  memcpy(all.data() + capacity * 32, H, capacity * 32);
+  memcpy(all.data() + 2 * capacity * 32, B, 32);
+  memcpy(all.data() + (2 * capacity + 1) * 32, B_blinding, 32);
+  bpg_gens* g = new (std::nothrow) bpg_gens();
+  if (!g) return BPG_ERR_NOMEM;
+  g->ctx = ctx;
+  g->cap = capacity;
+  g->table = nullptr;
+  g->comb = nullptr;
+  memcpy(g->B.data(), B, 32);
+  memcpy(g->Bb.data(), B_blinding, 32);
+  int rc = bpg_table_upload(ctx, all.data(), 2 * capacity + 2, &g->table);
+  if (!rc) rc = bpg_table_set_windows(ctx, g->table, 0);
+  uint8_t bases[64];
+  memcpy(bases, B, 32);
+  memcpy(bases + 32, B_blinding, 32);
+  if (!rc) rc = bpg_comb_create(ctx, bases, 2, &g->comb);
+  if (rc) {
+    if (g->table) bpg_table_free(g->table);
+    if (g->comb) bpg_comb_free(g->comb);
+    delete g;
+    return rc;
+  }
+  *out = g;
+  return BPG_OK;
+}
+extern "C" void bpg_gens_free(bpg_gens* g) {
+  if (!g) return;
+  bpg_table_free(g->table);
+  bpg_comb_free(g->comb);
+  delete g;
+}
+extern "C" size_t bpg_gens_capacity(const bpg_gens* g) { return g ? g->cap : 0; }
+extern "C" const bpg_table* bpg_gens_table(const bpg_gens* g) { return g ? g->table : nullptr; }
+
+// PedersenGens::commit batched: out[i] = values[i]*B + blindings[i]*B_blinding (generators.rs:41-43)
+extern "C" int bpg_pedersen_commit(bpg_ctx* ctx, const bpg_gens* g, const uint8_t* values, const uint8_t* blindings,
+                                   size_t n, uint8_t* out) {
+  if (!ctx || !g || !out || (n && (!values || !blindings))) return BPG_ERR_ARG;
+  std::vector<uint8_t> sc(2 * n * 32);
+  memcpy(sc.data(), values, n * 32);
+  memcpy(sc.data() + n * 32, blindings, n * 32);
+  return bpg_comb_mul(ctx, g->comb, sc.data(), n, out);
+}
+
+// ---------------------------------------------------------------- inner product proof
+struct InnerProductProof {
+  std::vector<Bytes32> L_vec, R_vec;
+  Scalar a, b;
+
+  size_t serialized_size() const { return (2 * L_vec.size() + 2) * 32; }
+  void to_bytes(uint8_t* out) const {  // inner_product_proof.rs:388-397
+    for (size_t i = 0; i < L_vec.size(); i++) {
+      memcpy(out + 64 * i, L_vec[i].data(), 32);
+      memcpy(out + 64 * i + 32, R_vec[i].data(), 32);
+    }
+    a.to_bytes(out + 64 * L_vec.size());
+    b.to_bytes(out + 64 * L_vec.size() + 32);
+  }
+  // inner_product_proof.rs:418-455 (point validity is checked by the device when they are used)
+  static int from_bytes(const uint8_t* s, size_t len, InnerProductProof* out) {
+    if (len % 32 || len < 64) return BPG_ERR_DECODE;
+    size_t num_elements = len / 32;
+    if ((num_elements - 2) % 2) return BPG_ERR_DECODE;
+    size_t lg_n = (num_elements - 2) / 2;
+    if (lg_n >= 32) return BPG_ERR_DECODE;
+    out->L_vec.resize(lg_n);
+    out->R_vec.resize(lg_n);
+    for (size_t i = 0; i < lg_n; i++) {
+      memcpy(out->L_vec[i].data(), s + 64 * i, 32);
+      memcpy(out->R_vec[i].data(), s + 64 * i + 32, 32);
+    }
+    if (!Scalar::from_bytes(s + 64 * lg_n, &out->a) || !Scalar::from_bytes(s + 64 * lg_n + 32, &out->b))
+      return BPG_ERR_DECODE;
+    return BPG_OK;
+  }
+
+  // the round loop of inner_product_proof.rs:49-193 around a device-resident state
+  static int run_rounds(bpg_ipp* st, Transcript& tr, InnerProductProof* out) {
+    int rc = BPG_OK;
+    while (bpg_ipp_rounds_left(st)) {
+      Bytes32 L, R;
+      rc = bpg_ipp_round_LR(st, L.data(), R.data());
+      if (rc) return rc;
+      out->L_vec.push_back(L);
+      out->R_vec.push_back(R);
+      tr.append_point("L", L.data());  // :119-120
+      tr.append_point("R", R.data());
+      Scalar u = tr.challenge_scalar("u");  // :122
+      Scalar u_inv = u.invert();
+      uint8_t ub[32], uib[32];
+      u.to_bytes(ub);
+      u_inv.to_bytes(uib);
+      rc = bpg_ipp_round_fold(st, ub, uib);
+      if (rc) return rc;
+    }
+    uint8_t ab[32], bb[32];
+    rc = bpg_ipp_finish(st, ab, bb);
+    if (rc) return rc;
+    Scalar::from_bytes(ab, &out->a);
+    Scalar::from_bytes(bb, &out->b);
+    return BPG_OK;
+  }
+
+  // inner_product_proof.rs:254-310
+  int verification_scalars(size_t n, Transcript& tr, std::vector<Scalar>& u_sq, std::vector<Scalar>& u_inv_sq,
+                           std::vector<Scalar>& s) const {
+    size_t lg_n = L_vec.size();
+    if (lg_n >= 32) return BPG_ERR_VERIFY;
+    if (n != ((size_t)1 << lg_n)) return BPG_ERR_VERIFY;
+    tr.innerproduct_domain_sep(n);
+    std::vector<Scalar> ch(lg_n), ch_inv(lg_n);
+    for (size_t i = 0; i < lg_n; i++) {
+      if (!tr.validate_and_append_point("L", L_vec[i].data())) return BPG_ERR_VERIFY;
+      if (!tr.validate_and_append_point("R", R_vec[i].data())) return BPG_ERR_VERIFY;
+      ch[i] = tr.challenge_scalar("u");
+    }
+    // batch inversion (Scalar::batch_inverse): one inversion + 3 lg n multiplications
+    Scalar allinv = Scalar::one();
+    if (lg_n) {
+      std::vector<Scalar> pre(lg_n);
+      Scalar acc = Scalar::one();
+      for (size_t i = 0; i < lg_n; i++) {
+        pre[i] = acc;
+        acc = acc * ch[i];
+      }
+      Scalar inv = acc.invert();
+      allinv = inv;
+      for (size_t i = lg_n; i-- > 0;) {
+        ch_inv[i] = inv * pre[i];
+        inv = inv * ch[i];
+      }
+    }
+    u_sq.resize(lg_n);
+    u_inv_sq.resize(lg_n);
+    for (size_t i = 0; i < lg_n; i++) {
+      u_sq[i] = ch[i] * ch[i];
+      u_inv_sq[i] = ch_inv[i] * ch_inv[i];
+    }
+    s.resize(n);
+    s[0] = allinv;
+    for (size_t i = 1; i < n; i++) {
+      size_t lg_i = 63 - __builtin_clzll((unsigned long long)i);
+      size_t k = (size_t)1 << lg_i;
+      s[i] = s[i - k] * u_sq[(lg_n - 1) - lg_i];
+    }
+    return BPG_OK;
+  }
+};
+
+extern "C" int bpg_ipp_create(bpg_ctx* ctx, bpg_transcript* t, const uint8_t Q[32], const uint8_t* G_factors,
+                              const uint8_t* H_factors, const bpg_table* G, size_t g_off, const bpg_table* H,
+                              size_t h_off, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* proof_out,
+                              size_t proof_cap, size_t* proof_len) {
+  if (!ctx || !t || !Q || !G || !H || !a || !b || !proof_out || !proof_len) return BPG_ERR_ARG;
+  if (n == 0 || (n & (n - 1))) return BPG_ERR_POW2;  // assert!(n.is_power_of_two()) :69
+  t->t.innerproduct_domain_sep(n);                   // :72
+  bpg_ipp* st = nullptr;
+  int rc = bpg_ipp_begin(ctx, G, g_off, H, h_off, n, Q, G_factors, H_factors, a, b, &st);
+  if (rc) return rc;
+  InnerProductProof proof;
+  rc = InnerProductProof::run_rounds(st, t->t, &proof);
+  bpg_ipp_free(st);
+  if (rc) return rc;
+  if (proof.serialized_size() > proof_cap) return BPG_ERR_ARG;
+  proof.to_bytes(proof_out);
+  *proof_len = proof.serialized_size();
+  return BPG_OK;
+}
+
+// inner_product_proof.rs:317-372
+extern "C" int bpg_ipp_verify(bpg_ctx* ctx, bpg_transcript* t, size_t n, const uint8_t* G_factors,
+                              const uint8_t* H_factors, const uint8_t P[32], const uint8_t Q[32], const bpg_table* G,
+                              size_t g_off, const bpg_table* H, size_t h_off, const uint8_t* proof, size_t proof_len) {
+  if (!ctx || !t || !P || !Q || !G || !H || !proof) return BPG_ERR_ARG;
+  InnerProductProof p;
+  int rc = InnerProductProof::from_bytes(proof, proof_len, &p);
+  if (rc) return rc;
+  std::vector<Scalar> u_sq, u_inv_sq, s;
+  rc = p.verification_scalars(n, t->t, u_sq, u_inv_sq, s);
+  if (rc) return rc;
+  size_t lg_n = p.L_vec.size();
+  // scalars: [a*b | -u_sq | -u_inv_sq] for ad-hoc [Q | L | R], then G, H ranges
+  std::vector<Scalar> sc;
+  sc.reserve(1 + 2 * lg_n + 2 * n);
+  sc.push_back(p.a * p.b);
+  for (auto& x : u_sq) sc.push_back(-x);
+  for (auto& x : u_inv_sq) sc.push_back(-x);
+  for (size_t i = 0; i < n; i++) {
+    Scalar g = p.a * s[i];
+    if (G_factors) {
+      Scalar f;
+      if (!Scalar::from_bytes(G_factors + 32 * i, &f)) return BPG_ERR_DECODE;
+      g = g * f;
+    }
+    sc.push_back(g);
+  }
+  for (size_t i = 0; i < n; i++) {
+    Scalar h = p.b * s[n - 1 - i];  // 1/s[i] is s[!i]
+    if (H_factors) {
+      Scalar f;
+      if (!Scalar::from_bytes(H_factors + 32 * i, &f)) return BPG_ERR_DECODE;
+      h = h * f;
+    }
+    sc.push_back(h);
+  }
+  std::vector<uint8_t> pts((1 + 2 * lg_n) * 32);
+  memcpy(pts.data(), Q, 32);
+  for (size_t i = 0; i < lg_n; i++) {
+    memcpy(pts.data() + 32 * (1 + i), p.L_vec[i].data(), 32);
+    memcpy(pts.data() + 32 * (1 + lg_n + i), p.R_vec[i].data(), 32);
+  }
+  const bpg_table* tabs[2] = {G, H};
+  size_t offs[2] = {g_off, h_off}, lens[2] = {n, n};
+  uint8_t expect[32];
+  std::vector<uint8_t> scb = sc_vec_bytes(sc);
+  rc = bpg_msm_mixed(ctx, pts.data(), 1 + 2 * lg_n, tabs, offs, lens, 2, scb.data(), expect);
+  if (rc) return rc;
+  return memcmp(expect, P, 32) == 0 ? BPG_OK : BPG_ERR_VERIFY;
+}
+
+// ---------------------------------------------------------------- constraint system
+enum VarKind : uint8_t { V_LEFT = 1, V_RIGHT = 2, V_OUT = 3, V_COMMITTED = 4, V_ONE = 5, V_ZERO = 6 };
+static inline bpg_var mkvar(VarKind k, uint64_t i) { return ((uint64_t)k << 56) | i; }
+static inline VarKind var_kind(bpg_var v) { return (VarKind)(v >> 56); }
+static inline uint64_t var_idx(bpg_var v) { return v & ((1ull << 56) - 1); }
+
+struct Term {
+  bpg_var var;
+  Scalar coeff;
+};
+typedef std::vector<Term> LinComb;
+
+// SplitMix64-seeded xoshiro256**, 64 bytes -> scalar mod l: the prover's blinding source
+// (the reference draws from thread_rng, src/r1cs/prover.rs:435-445; here the seed is the input)
+struct Xoshiro {
+  uint64_t s[4];
+  explicit Xoshiro(uint64_t seed) {
+    for (int i = 0; i < 4; i++) {
+      seed += 0x9E3779B97F4A7C15ULL;
+      uint64_t z = seed;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+      s[i] = z ^ (z >> 31);
+    }
+  }
+  static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+  uint64_t next() {
+    uint64_t result = rotl(s[1] * 5, 7) * 9;
+    uint64_t t = s[1] << 17;
+    s[2] ^= s[0];
+    s[3] ^= s[1];
+    s[1] ^= s[2];
+    s[0] ^= s[3];
+    s[2] ^= t;
+    s[3] = rotl(s[3], 45);
+    return result;
+  }
+  Scalar scalar() {
+    uint8_t b[64];
+    for (int i = 0; i < 8; i++) {
+      uint64_t x = next();
+      memcpy(b + 8 * i, &x, 8);
+    }
+    return Scalar::from_wide(b);
+  }
+};
+
+typedef int (*bpg_randomized_cb)(struct bpg_cs* cs, void* user);
+
+struct bpg_cs {
+  bool is_prover;
+  bpg_ctx* ctx;
+  const bpg_gens* gens;
+  Transcript* tr;
+  std::vector<LinComb> constraints;
+  // prover
+  std::vector<Scalar> a_L, a_R, a_O, v, v_blinding;
+  // verifier
+  size_t num_vars = 0;
+  std::vector<Bytes32> V;
+  std::vector<std::pair<bpg_randomized_cb, void*>> deferred;
+  bool has_pending = false;
+  size_t pending = 0;
+  bool randomizing = false;
+
+  size_t num_multipliers() const { return is_prover ? a_O.size() : num_vars; }
+
+  Scalar eval(const LinComb& lc) const {  // prover.rs:178-194 (verifier: dummy zero, verifier.rs:168-174)
+    Scalar tot = Scalar::zero();
+    if (!is_prover) return tot;
+    for (auto& t : lc) {
+      uint64_t i = var_idx(t.var);
+      switch (var_kind(t.var)) {
+        case V_LEFT: tot += t.coeff * a_L[i]; break;
+        case V_RIGHT: tot += t.coeff * a_R[i]; break;
+        case V_OUT: tot += t.coeff * a_O[i]; break;
+        case V_COMMITTED: tot += t.coeff * v[i]; break;
+        case V_ONE: tot += t.coeff; break;
+        default: break;
+      }
+    }
+    return tot;
+  }
+  bool valid(const LinComb& lc) const {
+    for (auto& t : lc) {
+      uint64_t i = var_idx(t.var);
+      switch (var_kind(t.var)) {
+        case V_LEFT: case V_RIGHT: case V_OUT: if (i >= num_multipliers()) return false; break;
+        case V_COMMITTED: if (i >= (is_prover ? v.size() : V.size())) return false; break;
+        case V_ONE: case V_ZERO: break;
+        default: return false;
+      }
+    }
+    return true;
+  }
+  // prover.rs:99-125 / verifier.rs:100-118
+  void multiply(LinComb left, LinComb right, bpg_var out[3]) {
+    size_t i;
+    if (is_prover) {
+      Scalar l = eval(left), r = eval(right);
+      i = a_L.size();
+      a_L.push_back(l);
+      a_R.push_back(r);
+      a_O.push_back(l * r);
+    } else {
+      i = num_vars++;
+    }
+    out[0] = mkvar(V_LEFT, i);
+    out[1] = mkvar(V_RIGHT, i);
+    out[2] = mkvar(V_OUT, i);
+    left.push_back({out[0], -Scalar::one()});
+    right.push_back({out[1], -Scalar::one()});
+    constraints.push_back(std::move(left));
+    constraints.push_back(std::move(right));
+  }
+  // prover.rs:127-146 / verifier.rs:120-134
+  bpg_var allocate(const Scalar* assignment) {
+    if (!has_pending) {
+      size_t i;
+      if (is_prover) {
+        i = a_L.size();
+        a_L.push_back(*assignment);
+        a_R.push_back(Scalar::zero());
+        a_O.push_back(Scalar::zero());
+      } else {
+        i = num_vars++;
+      }
+      has_pending = true;
+      pending = i;
+      return mkvar(V_LEFT, i);
+    }
+    size_t i = pending;
+    has_pending = false;
+    if (is_prover) {
+      a_R[i] = *assignment;
+      a_O[i] = a_L[i] * a_R[i];
+    }
+    return mkvar(V_RIGHT, i);
+  }
+  // prover.rs:148-164 / verifier.rs:136-150
+  void allocate_multiplier(const Scalar* l, const Scalar* r, bpg_var out[3]) {
+    size_t i;
+    if (is_prover) {
+      i = a_L.size();
+      a_L.push_back(*l);
+      a_R.push_back(*r);
+      a_O.push_back(*l * *r);
+    } else {
+      i = num_vars++;
+    }
+    out[0] = mkvar(V_LEFT, i);
+    out[1] = mkvar(V_RIGHT, i);
+    out[2] = mkvar(V_OUT, i);
+  }
+
+  // prover.rs:342-379 / verifier.rs:323-362
+  void flattened_constraints(const Scalar& z, std::vector<Scalar>& wL, std::vector<Scalar>& wR,
+                             std::vector<Scalar>& wO, std::vector<Scalar>& wV, Scalar& wc) const {
+    size_t n = num_multipliers(), m = is_prover ? v.size() : V.size();
+    wL.assign(n, Scalar::zero());
+    wR.assign(n, Scalar::zero());
+    wO.assign(n, Scalar::zero());
+    wV.assign(m, Scalar::zero());
+    wc = Scalar::zero();
+    Scalar exp_z = z;
+    for (auto& lc : constraints) {
+      for (auto& t : lc) {
+        uint64_t i = var_idx(t.var);
+        switch (var_kind(t.var)) {
+          case V_LEFT: wL[i] += exp_z * t.coeff; break;
+          case V_RIGHT: wR[i] += exp_z * t.coeff; break;
+          case V_OUT: wO[i] += exp_z * t.coeff; break;
+          case V_COMMITTED: wV[i] -= exp_z * t.coeff; break;
+          case V_ONE: wc -= exp_z * t.coeff; break;  // the prover ignores it (prover.rs:370-372)
+          default: break;
+        }
+      }
+      exp_z *= z;
+    }
+  }
+
+  // prover.rs:383-402 / verifier.rs:366-385
+  int create_randomized_constraints() {
+    has_pending = false;
+    if (deferred.empty()) {
+      tr->r1cs_1phase_domain_sep();
+      return BPG_OK;
+    }
+    tr->r1cs_2phase_domain_sep();
+    randomizing = true;
+    auto cbs = std::move(deferred);
+    deferred.clear();
+    for (auto& cb : cbs) {
+      int rc = cb.first(this, cb.second);
+      if (rc) return rc;
+    }
+    return BPG_OK;
+  }
+};
+
+static size_t next_pow2(size_t n) {
+  size_t p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+static int parse_lc(const bpg_cs* cs, const bpg_term* t, size_t n, LinComb* out) {
+  out->resize(n);
+  for (size_t i = 0; i < n; i++) {
+    (*out)[i].var = t[i].var;
+    if (!Scalar::from_bytes(t[i].coeff, &(*out)[i].coeff)) return BPG_ERR_DECODE;
+  }
+  return cs->valid(*out) ? BPG_OK : BPG_ERR_ARG;
+}
+
+extern "C" int bpg_prover_new(bpg_ctx* ctx, const bpg_gens* gens, bpg_transcript* t, bpg_cs** out) {
+  if (!ctx || !gens || !t || !out) return BPG_ERR_ARG;
+  bpg_cs* cs = new (std::nothrow) bpg_cs();
+  if (!cs) return BPG_ERR_NOMEM;
+  cs->is_prover = true;
+  cs->ctx = ctx;
+  cs->gens = gens;
+  cs->tr = &t->t;
+  cs->tr->r1cs_domain_sep();  // prover.rs:286
+  *out = cs;
+  return BPG_OK;
+}
+extern "C" int bpg_verifier_new(bpg_ctx* ctx, const bpg_gens* gens, bpg_transcript* t, bpg_cs** out) {
+  if (!ctx || !gens || !t || !out) return BPG_ERR_ARG;
+  bpg_cs* cs = new (std::nothrow) bpg_cs();
+  if (!cs) return BPG_ERR_NOMEM;
+  cs->is_prover = false;
+  cs->ctx = ctx;
+  cs->gens = gens;
+  cs->tr = &t->t;
+  cs->tr->r1cs_domain_sep();  // verifier.rs:271
+  *out = cs;
+  return BPG_OK;
+}
+extern "C" void bpg_cs_free(bpg_cs* cs) { delete cs; }
+extern "C" size_t bpg_cs_num_multipliers(const bpg_cs* cs) { return cs ? cs->num_multipliers() : 0; }
+extern "C" size_t bpg_cs_num_constraints(const bpg_cs* cs) { return cs ? cs->constraints.size() : 0; }
+extern "C" bpg_var bpg_var_one(void) { return mkvar(V_ONE, 0); }
+
+// prover.rs:319-329
+extern "C" int bpg_prover_commit(bpg_cs* cs, const uint8_t v[32], const uint8_t v_blinding[32], uint8_t V_out[32],
+                                 bpg_var* var) {
+  if (!cs || !cs->is_prover || !v || !v_blinding || !V_out || !var) return BPG_ERR_ARG;
+  Scalar sv, sb;
+  if (!Scalar::from_bytes(v, &sv) || !Scalar::from_bytes(v_blinding, &sb)) return BPG_ERR_DECODE;
+  int rc = bpg_pedersen_commit(cs->ctx, cs->gens, v, v_blinding, 1, V_out);
+  if (rc) return rc;
+  size_t i = cs->v.size();
+  cs->v.push_back(sv);
+  cs->v_blinding.push_back(sb);
+  cs->tr->append_point("V", V_out);
+  *var = mkvar(V_COMMITTED, i);
+  return BPG_OK;
+}
+// verifier.rs:298-308
+extern "C" int bpg_verifier_commit(bpg_cs* cs, const uint8_t V[32], bpg_var* var) {
+  if (!cs || cs->is_prover || !V || !var) return BPG_ERR_ARG;
+  Bytes32 b;
+  memcpy(b.data(), V, 32);
+  size_t i = cs->V.size();
+  cs->V.push_back(b);
+  cs->tr->append_point("V", V);
+  *var = mkvar(V_COMMITTED, i);
+  return BPG_OK;
+}
+// prover.rs:169-171 / verifier.rs:153-160: blinding factor one
+extern "C" int bpg_cs_commit_public(bpg_cs* cs, const uint8_t value[32], bpg_var* var) {
+  if (!cs || !value || !var) return BPG_ERR_ARG;
+  uint8_t one[32] = {1};
+  uint8_t V[32];
+  if (cs->is_prover) return bpg_prover_commit(cs, value, one, V, var);
+  int rc = bpg_pedersen_commit(cs->ctx, cs->gens, value, one, 1, V);
+  if (rc) return rc;
+  return bpg_verifier_commit(cs, V, var);
+}
+extern "C" int bpg_cs_multiply(bpg_cs* cs, const bpg_term* left, size_t nl, const bpg_term* right, size_t nr,
+                               bpg_var out[3]) {
+  if (!cs || !out) return BPG_ERR_ARG;
+  LinComb l, r;
+  int rc = parse_lc(cs, left, nl, &l);
+  if (!rc) rc = parse_lc(cs, right, nr, &r);
+  if (rc) return rc;
+  cs->multiply(std::move(l), std::move(r), out);
+  return BPG_OK;
+}
+extern "C" int bpg_cs_allocate(bpg_cs* cs, const uint8_t* assignment, bpg_var* out) {
+  if (!cs || !out) return BPG_ERR_ARG;
+  Scalar a = Scalar::zero();
+  if (cs->is_prover) {
+    if (!assignment) return BPG_ERR_ARG;  // R1CSError::MissingAssignment
+    if (!Scalar::from_bytes(assignment, &a)) return BPG_ERR_DECODE;
+  }
+  *out = cs->allocate(&a);
+  return BPG_OK;
+}
+extern "C" int bpg_cs_allocate_multiplier(bpg_cs* cs, const uint8_t* l, const uint8_t* r, bpg_var out[3]) {
+  if (!cs || !out) return BPG_ERR_ARG;
+  Scalar sl = Scalar::zero(), sr = Scalar::zero();
+  if (cs->is_prover) {
+    if (!l || !r) return BPG_ERR_ARG;  // R1CSError::MissingAssignment
+    if (!Scalar::from_bytes(l, &sl) || !Scalar::from_bytes(r, &sr)) return BPG_ERR_DECODE;
+  }
+  cs->allocate_multiplier(&sl, &sr, out);
+  return BPG_OK;
+}
+extern "C" int bpg_cs_constrain(bpg_cs* cs, const bpg_term* lc, size_t n) {
+  if (!cs) return BPG_ERR_ARG;
+  LinComb l;
+  int rc = parse_lc(cs, lc, n, &l);
+  if (rc) return rc;
+  cs->constraints.push_back(std::move(l));
+  return BPG_OK;
+}
+extern "C" int bpg_cs_specify_randomized_constraints(bpg_cs* cs, bpg_randomized_cb cb, void* user) {
+  if (!cs || !cb) return BPG_ERR_ARG;
+  cs->deferred.push_back({cb, user});
+  return BPG_OK;
+}
+extern "C" int bpg_cs_challenge_scalar(bpg_cs* cs, const char* label, uint8_t out[32]) {
+  if (!cs || !label || !out || !cs->randomizing) return BPG_ERR_ARG;
+  cs->tr->challenge_scalar(label).to_bytes(out);
+  return BPG_OK;
+}
+// the prover's assignment of a linear combination (ConstraintSystem::eval)
+extern "C" int bpg_cs_eval(bpg_cs* cs, const bpg_term* lc, size_t n, uint8_t out[32]) {
+  if (!cs || !out) return BPG_ERR_ARG;
+  LinComb l;
+  int rc = parse_lc(cs, lc, n, &l);
+  if (rc) return rc;
+  cs->eval(l).to_bytes(out);
+  return BPG_OK;
+}
+
+// ---------------------------------------------------------------- R1CS proof bytes
+struct R1CSProof {
+  Bytes32 A_I1, A_O1, S1, A_I2, A_O2, S2, T_1, T_3, T_4, T_5, T_6;
+  Scalar t_x, t_x_blinding, e_blinding;
+  InnerProductProof ipp;
+
+  bool missing_phase2() const {  // proof.rs:121-123
+    return is_identity_enc(A_I2.data()) && is_identity_enc(A_O2.data()) && is_identity_enc(S2.data());
+  }
+  size_t serialized_size() const { return 1 + (missing_phase2() ? 11 : 14) * 32 + ipp.serialized_size(); }
+  void to_bytes(uint8_t* out) const {  // proof.rs:82-108
+    uint8_t* p = out;
+    auto put = [&](const Bytes32& b) { memcpy(p, b.data(), 32); p += 32; };
+    if (missing_phase2()) {
+      *p++ = 0;
+      put(A_I1); put(A_O1); put(S1);
+    } else {
+      *p++ = 1;
+      put(A_I1); put(A_O1); put(S1); put(A_I2); put(A_O2); put(S2);
+    }
+    put(T_1); put(T_3); put(T_4); put(T_5); put(T_6);
+    t_x.to_bytes(p); p += 32;
+    t_x_blinding.to_bytes(p); p += 32;
+    e_blinding.to_bytes(p); p += 32;
+    ipp.to_bytes(p);
+  }
+  static int from_bytes(const uint8_t* s, size_t len, R1CSProof* out) {  // proof.rs:128-207
+    if (len == 0) return BPG_ERR_DECODE;
+    uint8_t version = s[0];
+    s++;
+    len--;
+    if (len % 32) return BPG_ERR_DECODE;
+    size_t npts;
+    if (version == 0) npts = 8;
+    else if (version == 1) npts = 11;
+    else return BPG_ERR_DECODE;
+    if (len < (npts + 3) * 32) return BPG_ERR_DECODE;
+    auto get = [&](Bytes32& b) { memcpy(b.data(), s, 32); s += 32; len -= 32; };
+    get(out->A_I1); get(out->A_O1); get(out->S1);
+    if (version == 0) {
+      out->A_I2.fill(0); out->A_O2.fill(0); out->S2.fill(0);
+    } else {
+      get(out->A_I2); get(out->A_O2); get(out->S2);
+    }
+    get(out->T_1); get(out->T_3); get(out->T_4); get(out->T_5); get(out->T_6);
+    if (!Scalar::from_bytes(s, &out->t_x) || !Scalar::from_bytes(s + 32, &out->t_x_blinding) ||
+        !Scalar::from_bytes(s + 64, &out->e_blinding))
+      return BPG_ERR_DECODE;
+    s += 96;
+    len -= 96;
+    return InnerProductProof::from_bytes(s, len, &out->ipp);
+  }
+};
+
+// ---------------------------------------------------------------- Prover::prove (prover.rs:412-727)
+// one indexed-MSM launch for (A_I, A_O, S) over gens[first .. first+cnt)
+static int commit_AIOS(bpg_cs* cs, size_t first, size_t cnt, const Scalar& i_b, const Scalar& o_b, const Scalar& s_b,
+                       const Scalar* sL, const Scalar* sR, uint8_t out[96]) {
+  const bpg_gens* g = cs->gens;
+  size_t T = 5 * cnt + 3;
+  std::vector<uint32_t> pid(T);
+  std::vector<uint8_t> set(T), sc(T * 32);
+  size_t k = 0;
+  auto put = [&](uint32_t id, uint8_t s, const Scalar& x) {
+    pid[k] = id;
+    set[k] = s;
+    x.to_bytes(sc.data() + 32 * k);
+    k++;
+  };
+  put((uint32_t)g->bb_id(), 0, i_b);
+  put((uint32_t)g->bb_id(), 1, o_b);
+  put((uint32_t)g->bb_id(), 2, s_b);
+  for (size_t i = 0; i < cnt; i++) {
+    put((uint32_t)(g->g_base() + first + i), 0, cs->a_L[first + i]);
+    put((uint32_t)(g->h_base() + first + i), 0, cs->a_R[first + i]);
+    put((uint32_t)(g->g_base() + first + i), 1, cs->a_O[first + i]);
+    put((uint32_t)(g->g_base() + first + i), 2, sL[i]);
+    put((uint32_t)(g->h_base() + first + i), 2, sR[i]);
+  }
+  return bpg_msm_table_indexed(cs->ctx, g->table, pid.data(), set.data(), sc.data(), T, 3, out);
+}
+
+extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+  if (!cs || !cs->is_prover || !proof_out || !proof_len) return BPG_ERR_ARG;
+  Transcript& tr = *cs->tr;
+  const bpg_gens* g = cs->gens;
+  Xoshiro rng(rng_seed);
+  R1CSProof proof;
+  tr.append_u64("m", cs->v.size());  // :420
+  size_t n1 = cs->a_L.size();
+  if (g->cap < n1) return BPG_ERR_CAPACITY;  // :450-452
+  Scalar i_b1 = rng.scalar(), o_b1 = rng.scalar(), s_b1 = rng.scalar();  // :457-459
+  std::vector<Scalar> s_L(n1), s_R(n1);
+  for (auto& x : s_L) x = rng.scalar();
+  for (auto& x : s_R) x = rng.scalar();
+  uint8_t c3[96];
+  int rc = commit_AIOS(cs, 0, n1, i_b1, o_b1, s_b1, s_L.data(), s_R.data(), c3);  // :465-494
+  if (rc) return rc;
+  memcpy(proof.A_I1.data(), c3, 32);
+  memcpy(proof.A_O1.data(), c3 + 32, 32);
+  memcpy(proof.S1.data(), c3 + 64, 32);
+  tr.append_point("A_I1", proof.A_I1.data());
+  tr.append_point("A_O1", proof.A_O1.data());
+  tr.append_point("S1", proof.S1.data());
+  rc = cs->create_randomized_constraints();  // :501
+  if (rc) return rc;
+  size_t n = cs->a_L.size(), n2 = n - n1, padded_n = next_pow2(n), pad = padded_n - n;
+  if (g->cap < padded_n) return BPG_ERR_CAPACITY;  // :511-513
+  Scalar i_b2 = Scalar::zero(), o_b2 = Scalar::zero(), s_b2 = Scalar::zero();
+  if (n2 > 0) {  // :519-530
+    i_b2 = rng.scalar();
+    o_b2 = rng.scalar();
+    s_b2 = rng.scalar();
+  }
+  s_L.resize(n);
+  s_R.resize(n);
+  for (size_t i = n1; i < n; i++) s_L[i] = rng.scalar();
+  for (size_t i = n1; i < n; i++) s_R[i] = rng.scalar();
+  if (n2 > 0) {  // :532-565
+    rc = commit_AIOS(cs, n1, n2, i_b2, o_b2, s_b2, s_L.data() + n1, s_R.data() + n1, c3);
+    if (rc) return rc;
+    memcpy(proof.A_I2.data(), c3, 32);
+    memcpy(proof.A_O2.data(), c3 + 32, 32);
+    memcpy(proof.S2.data(), c3 + 64, 32);
+  } else {
+    proof.A_I2.fill(0);  // identity (:566-576)
+    proof.A_O2.fill(0);
+    proof.S2.fill(0);
+  }
+  tr.append_point("A_I2", proof.A_I2.data());
+  tr.append_point("A_O2", proof.A_O2.data());
+  tr.append_point("S2", proof.S2.data());
+  Scalar y = tr.challenge_scalar("y"), z = tr.challenge_scalar("z");  // :584-585
+  std::vector<Scalar> wL, wR, wO, wV;
+  Scalar wc;
+  cs->flattened_constraints(z, wL, wR, wO, wV, wc);
+  Scalar y_inv = y.invert();
+  std::vector<Scalar> exp_y_inv(padded_n);
+  {
+    Scalar e = Scalar::one();
+    for (size_t i = 0; i < padded_n; i++) {
+      exp_y_inv[i] = e;
+      e *= y_inv;
+    }
+  }
+  std::vector<Scalar> l1(n), l2(n), l3(n), r0(n), r1(n), r3(n);
+  Scalar exp_y = Scalar::one();
+  for (size_t i = 0; i < n; i++) {  // :596-617
+    l1[i] = cs->a_L[i] + exp_y_inv[i] * wR[i];
+    l2[i] = cs->a_O[i];
+    l3[i] = s_L[i];
+    r0[i] = wO[i] - exp_y;
+    r1[i] = exp_y * cs->a_R[i] + wL[i];
+    r3[i] = exp_y * s_R[i];
+    exp_y *= y;
+  }
+  auto ip = [](const std::vector<Scalar>& a, const std::vector<Scalar>& b) {
+    Scalar t = Scalar::zero();
+    for (size_t i = 0; i < a.size(); i++) t += a[i] * b[i];
+    return t;
+  };
+  // util.rs:152-170
+  Scalar t1 = ip(l1, r0), t2 = ip(l1, r1) + ip(l2, r0), t3 = ip(l2, r1) + ip(l3, r0), t4 = ip(l1, r3) + ip(l3, r1),
+         t5 = ip(l2, r3), t6 = ip(l3, r3);
+  Scalar tb1 = rng.scalar(), tb3 = rng.scalar(), tb4 = rng.scalar(), tb5 = rng.scalar(), tb6 = rng.scalar();  // :621-625
+  {
+    uint8_t vals[160], blinds[160], Ts[160];
+    t1.to_bytes(vals); t3.to_bytes(vals + 32); t4.to_bytes(vals + 64); t5.to_bytes(vals + 96); t6.to_bytes(vals + 128);
+    tb1.to_bytes(blinds); tb3.to_bytes(blinds + 32); tb4.to_bytes(blinds + 64); tb5.to_bytes(blinds + 96);
+    tb6.to_bytes(blinds + 128);
+    rc = bpg_pedersen_commit(cs->ctx, g, vals, blinds, 5, Ts);  // :627-631
+    if (rc) return rc;
+    memcpy(proof.T_1.data(), Ts, 32);
+    memcpy(proof.T_3.data(), Ts + 32, 32);
+    memcpy(proof.T_4.data(), Ts + 64, 32);
+    memcpy(proof.T_5.data(), Ts + 96, 32);
+    memcpy(proof.T_6.data(), Ts + 128, 32);
+  }
+  tr.append_point("T_1", proof.T_1.data());
+  tr.append_point("T_3", proof.T_3.data());
+  tr.append_point("T_4", proof.T_4.data());
+  tr.append_point("T_5", proof.T_5.data());
+  tr.append_point("T_6", proof.T_6.data());
+  Scalar u = tr.challenge_scalar("u"), x = tr.challenge_scalar("x");  // :639-640
+  Scalar tb2 = Scalar::zero();
+  for (size_t i = 0; i < wV.size(); i++) tb2 += wV[i] * cs->v_blinding[i];  // :644-648
+  auto poly6 = [&](const Scalar& c1, const Scalar& c2, const Scalar& c3_, const Scalar& c4, const Scalar& c5,
+                   const Scalar& c6) { return x * (c1 + x * (c2 + x * (c3_ + x * (c4 + x * (c5 + x * c6))))); };
+  proof.t_x = poly6(t1, t2, t3, t4, t5, t6);
+  proof.t_x_blinding = poly6(tb1, tb2, tb3, tb4, tb5, tb6);
+  std::vector<Scalar> l_vec(padded_n, Scalar::zero()), r_vec(padded_n, Scalar::zero());
+  for (size_t i = 0; i < n; i++) {  // util.rs:172-181 (l0 = r2 = 0)
+    l_vec[i] = x * (l1[i] + x * (l2[i] + x * l3[i]));
+    r_vec[i] = r0[i] + x * (r1[i] + x * (x * r3[i]));
+  }
+  for (size_t i = n; i < padded_n; i++) {  // :661-672
+    r_vec[i] = -exp_y;
+    exp_y *= y;
+  }
+  Scalar i_b = i_b1 + u * i_b2, o_b = o_b1 + u * o_b2, s_b = s_b1 + u * s_b2;
+  proof.e_blinding = x * (i_b + x * (o_b + x * s_b));
+  tr.append_scalar("t_x", proof.t_x);
+  tr.append_scalar("t_x_blinding", proof.t_x_blinding);
+  tr.append_scalar("e_blinding", proof.e_blinding);
+  Scalar w = tr.challenge_scalar("w");  // :686; Q = w*B is never materialised: its scalar rides on B
+  std::vector<Scalar> Gf(padded_n), Hf(padded_n);
+  for (size_t i = 0; i < padded_n; i++) {  // :689-697
+    Gf[i] = i < n1 ? Scalar::one() : u;
+    Hf[i] = exp_y_inv[i] * Gf[i];
+  }
+  tr.innerproduct_domain_sep(padded_n);  // inner_product_proof.rs:72
+  uint8_t wb[32];
+  w.to_bytes(wb);
+  bpg_ipp* st = nullptr;
+  std::vector<uint8_t> gfb = sc_vec_bytes(Gf), hfb = sc_vec_bytes(Hf), lb = sc_vec_bytes(l_vec), rb = sc_vec_bytes(r_vec);
+  rc = bpg_ipp_begin_shared(cs->ctx, g->table, g->g_base(), g->h_base(), g->b_id(), wb, padded_n, gfb.data(),
+                            hfb.data(), lb.data(), rb.data(), &st);
+  if (rc) return rc;
+  rc = InnerProductProof::run_rounds(st, tr, &proof.ipp);
+  bpg_ipp_free(st);
+  if (rc) return rc;
+  if (proof.serialized_size() > proof_cap) return BPG_ERR_ARG;
+  proof.to_bytes(proof_out);
+  *proof_len = proof.serialized_size();
+  return BPG_OK;
+}
+
+// ---------------------------------------------------------------- Verifier::verify (verifier.rs:393-554)
+extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_len) {
+  if (!cs || cs->is_prover || !proof_bytes) return BPG_ERR_ARG;
+  R1CSProof proof;
+  int rc = R1CSProof::from_bytes(proof_bytes, proof_len, &proof);
+  if (rc) return rc;
+  Transcript& tr = *cs->tr;
+  const bpg_gens* g = cs->gens;
+  tr.append_u64("m", cs->V.size());
+  size_t n1 = cs->num_vars;
+  if (!tr.validate_and_append_point("A_I1", proof.A_I1.data())) return BPG_ERR_VERIFY;
+  if (!tr.validate_and_append_point("A_O1", proof.A_O1.data())) return BPG_ERR_VERIFY;
+  if (!tr.validate_and_append_point("S1", proof.S1.data())) return BPG_ERR_VERIFY;
+  rc = cs->create_randomized_constraints();
+  if (rc) return rc;
+  size_t n = cs->num_vars, n2 = n - n1, padded_n = next_pow2(n), pad = padded_n - n;
+  (void)n2;
+  if (g->cap < padded_n) return BPG_ERR_CAPACITY;
+  tr.append_point("A_I2", proof.A_I2.data());
+  tr.append_point("A_O2", proof.A_O2.data());
+  tr.append_point("S2", proof.S2.data());
+  Scalar y = tr.challenge_scalar("y"), z = tr.challenge_scalar("z");
+  if (!tr.validate_and_append_point("T_1", proof.T_1.data())) return BPG_ERR_VERIFY;
+  if (!tr.validate_and_append_point("T_3", proof.T_3.data())) return BPG_ERR_VERIFY;
+  if (!tr.validate_and_append_point("T_4", proof.T_4.data())) return BPG_ERR_VERIFY;
+  if (!tr.validate_and_append_point("T_5", proof.T_5.data())) return BPG_ERR_VERIFY;
+  if (!tr.validate_and_append_point("T_6", proof.T_6.data())) return BPG_ERR_VERIFY;
+  Scalar u = tr.challenge_scalar("u"), x = tr.challenge_scalar("x");
+  tr.append_scalar("t_x", proof.t_x);
+  tr.append_scalar("t_x_blinding", proof.t_x_blinding);
+  tr.append_scalar("e_blinding", proof.e_blinding);
+  Scalar w = tr.challenge_scalar("w");
+  std::vector<Scalar> wL, wR, wO, wV;
+  Scalar wc;
+  cs->flattened_constraints(z, wL, wR, wO, wV, wc);
+  std::vector<Scalar> u_sq, u_inv_sq, s;
+  rc = proof.ipp.verification_scalars(padded_n, tr, u_sq, u_inv_sq, s);
+  if (rc) return BPG_ERR_VERIFY;  // map_err(|_| VerificationError) :463
+  const Scalar &a = proof.ipp.a, &b = proof.ipp.b;
+  Scalar y_inv = y.invert();
+  std::vector<Scalar> y_inv_vec(padded_n), yneg_wR(padded_n, Scalar::zero());
+  {
+    Scalar e = Scalar::one();
+    for (size_t i = 0; i < padded_n; i++) {
+      y_inv_vec[i] = e;
+      e *= y_inv;
+    }
+  }
+  Scalar delta = Scalar::zero();
+  for (size_t i = 0; i < n; i++) {
+    yneg_wR[i] = wR[i] * y_inv_vec[i];
+    delta += yneg_wR[i] * wL[i];  // :479
+  }
+  Scalar r = tr.challenge_scalar("r");  // :506
+  Scalar xx = x * x, rxx = r * xx, xxx = x * xx;
+  size_t lg_n = proof.ipp.L_vec.size(), m = cs->V.size();
+  // ad-hoc points: [A_I1 A_O1 S1 A_I2 A_O2 S2 | V_* | T_* | L_* | R_*]
+  size_t n_adhoc = 6 + m + 5 + 2 * lg_n;
+  std::vector<uint8_t> pts(n_adhoc * 32);
+  std::vector<Scalar> sc;
+  sc.reserve(n_adhoc + 2 + 2 * padded_n);
+  uint8_t* pp = pts.data();
+  auto putp = [&](const uint8_t* p, const Scalar& k) {
+    memcpy(pp, p, 32);
+    pp += 32;
+    sc.push_back(k);
+  };
+  putp(proof.A_I1.data(), x);
+  putp(proof.A_O1.data(), xx);
+  putp(proof.S1.data(), xxx);
+  putp(proof.A_I2.data(), u * x);
+  putp(proof.A_O2.data(), u * xx);
+  putp(proof.S2.data(), u * xxx);
+  for (size_t j = 0; j < m; j++) putp(cs->V[j].data(), wV[j] * rxx);
+  putp(proof.T_1.data(), r * x);
+  putp(proof.T_3.data(), rxx * x);
+  putp(proof.T_4.data(), rxx * xx);
+  putp(proof.T_5.data(), rxx * xxx);
+  putp(proof.T_6.data(), rxx * xx * xx);
+  for (size_t j = 0; j < lg_n; j++) putp(proof.ipp.L_vec[j].data(), u_sq[j]);
+  for (size_t j = 0; j < lg_n; j++) putp(proof.ipp.R_vec[j].data(), u_inv_sq[j]);
+  // table ranges: [B, B_blinding], G[0..N), H[0..N)
+  sc.push_back(w * (proof.t_x - a * b) + r * (xx * (wc + delta) - proof.t_x));  // B
+  sc.push_back(-proof.e_blinding - r * proof.t_x_blinding);                     // B_blinding
+  for (size_t i = 0; i < padded_n; i++) {  // g_scalars :487-491
+    Scalar U = i < n1 ? Scalar::one() : u;
+    sc.push_back(U * (x * yneg_wR[i] - a * s[i]));
+  }
+  for (size_t i = 0; i < padded_n; i++) {  // h_scalars :493-501
+    Scalar U = i < n1 ? Scalar::one() : u;
+    Scalar wLi = i < n ? wL[i] : Scalar::zero(), wOi = i < n ? wO[i] : Scalar::zero();
+    sc.push_back(U * (y_inv_vec[i] * (x * wLi + wOi - b * s[padded_n - 1 - i]) - Scalar::one()));
+  }
+  (void)pad;
+  const bpg_table* tabs[3] = {g->table, g->table, g->table};
+  size_t offs[3] = {g->b_id(), g->g_base(), g->h_base()}, lens[3] = {2, padded_n, padded_n};
+  uint8_t mega[32];
+  std::vector<uint8_t> scb = sc_vec_bytes(sc);
+  rc = bpg_msm_mixed(cs->ctx, pts.data(), n_adhoc, tabs, offs, lens, 3, scb.data(), mega);
+  if (rc == BPG_ERR_DECODE) return BPG_ERR_DECODE;  // a proof point that is not a valid encoding: FormatError
+  if (rc) return rc;
+  return is_identity_enc(mega) ? BPG_OK : BPG_ERR_VERIFY;  // :549
+}

@@ -36,6 +36,7 @@ struct MsmCfg {
   uint32_t nchunks;   // nb / chunk
   uint32_t big_thresh;  // buckets longer than this go to k_accum_big
   uint32_t big_cap;     // capacity of the big-bucket list
+  uint32_t win_stride;  // 0: plain table.  >0: table holds 2^(c w) P_i at index w*win_stride + i
   sc_bias bias;
 };
 
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ sc
       uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
       uint32_t b = base + (uint32_t)w * cfg.nb + mag - 1;
       uint32_t pos = offsets[b] + atomicAdd(&cursors[b], 1u);
-      entries[pos] = pid | (d < 0 ? ENTRY_NEG : 0u);
+      entries[pos] = (pid + (uint32_t)w * cfg.win_stride) | (d < 0 ? ENTRY_NEG : 0u);
     }
   }
 }
@@ -317,7 +318,9 @@ __global__ void k_horner(const uint32_t* __restrict__ window_sums, MsmCfg cfg, u
   ge_ext acc;
   ge_load_ext(acc, src + (size_t)(cfg.W - 1) * 32);
   for (int w = cfg.W - 2; w >= 0; w--) {
-    for (int i = 0; i < cfg.c; i++) acc = ge_dbl(acc);
+    // windowed tables already carry the 2^(c w) weights in their points
+    if (cfg.win_stride == 0)
+      for (int i = 0; i < cfg.c; i++) acc = ge_dbl(acc);
     ge_ext s;
     ge_load_ext(s, src + (size_t)w * 32);
     acc = ge_add(acc, s);
@@ -439,6 +442,60 @@ __global__ void __launch_bounds__(128) k_comb_mul(const uint32_t* __restrict__ t
   }
   if (out_ext) ge_store_ext(out_ext + (size_t)i * 32, acc);
   if (out_bytes) ge_encode(out_bytes + (size_t)i * 32, acc);
+}
+
+// ---------------------------------------------------------------------------
+// windowed tables: out[w][i] = 2^(c w) * P_i in affine Niels, w < W.
+// One thread per point walks the doubling chain, parks the extended multiples and
+// the running product of their Z in scratch, inverts once (Montgomery's trick) and
+// converts every multiple back to affine.  One-time cost at table upload; it removes
+// all doublings from every later MSM over the table.
+// ---------------------------------------------------------------------------
+BPG_DEF_CONST(K_INV2, 0xfffffff7u, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu,
+              0x3fffffffu)  // (p+1)/2
+
+__global__ void __launch_bounds__(128) k_window_chain(const uint32_t* __restrict__ niels_in, uint32_t n_total,
+                                                       uint32_t first, uint32_t count, int c, int W,
+                                                       uint32_t* __restrict__ ext_scratch /*[W-1][count][32]*/,
+                                                       uint32_t* __restrict__ zp_scratch /*[W-1][count][8]*/,
+                                                       uint32_t* __restrict__ out /*[W][n_total][24]*/) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  uint32_t i = first + t;
+  ge_niels q;
+  ge_load_niels(q, niels_in + (size_t)i * 24);
+  ge_store_niels(out + (size_t)i * 24, q);  // window 0
+  ge_ext p;
+  p.X = fe_sub(q.ypx, q.ymx);     // 2x
+  p.Y = fe_add(q.ypx, q.ymx);     // 2y
+  p.Z = fe_zero();
+  p.Z.v[0] = 2;
+  p.T = fe_mul(fe_mul(p.X, p.Y), fe_const(BPG_K(K_INV2)));  // XY/Z
+  p.X = fe_mul(p.X, fe_one());    // tighten
+  p.Y = fe_mul(p.Y, fe_one());
+  fe zp = fe_one();
+  for (int w = 1; w < W; w++) {
+    for (int k = 0; k < c; k++) p = ge_dbl(p);
+    zp = fe_mul(zp, p.Z);
+    ge_store_ext(ext_scratch + ((size_t)(w - 1) * count + t) * 32, p);
+    fe_store(zp_scratch + ((size_t)(w - 1) * count + t) * 8, zp);
+  }
+  fe inv = fe_invert(zp);
+  for (int w = W - 1; w >= 1; w--) {
+    ge_ext e;
+    ge_load_ext(e, ext_scratch + ((size_t)(w - 1) * count + t) * 32);
+    fe zi;
+    if (w >= 2) {
+      fe prev;
+      fe_load(prev, zp_scratch + ((size_t)(w - 2) * count + t) * 8);
+      zi = fe_mul(inv, prev);
+    } else {
+      zi = inv;
+    }
+    inv = fe_mul(inv, e.Z);
+    fe x = fe_mul(e.X, zi), y = fe_mul(e.Y, zi);
+    ge_store_niels(out + ((size_t)w * n_total + i) * 24, ge_affine_to_niels(x, y));
+  }
 }
 
 }  // namespace bpg

@@ -120,3 +120,25 @@ def test_linearity_large(ctx):
     small = msm(ctx, scalars_bytes(summed), pb)
     assert big == small
     assert small == G.msm(summed, ps).encode()
+
+
+@pytest.mark.parametrize("c", [0, 5, 8, 13])
+def test_windowed_table(ctx, c):
+    """Tables holding the precomputed window multiples 2^(c w) P_i give the same sums
+    (whole table, sub-range, several scalar sets)."""
+    from mpc_bulletproof_b200 import Table
+
+    r = rng(50 + c)
+    n_tab, off, n, sets = 500, 37, 400, 2
+    ps = [rand_point(r) for _ in range(n_tab)]
+    ps[5] = G.IDENTITY
+    t = Table(ctx, points_bytes(ps)).set_windows(c)
+    assert t.window == (c or t.window) and t.window >= 2
+    ks = [rand_scalar(r) for _ in range(n_tab)]
+    ks[0], ks[1], ks[2] = 0, G.L - 1, 2**252
+    assert t.msm(scalars_bytes(ks))[0] == G.msm(ks, ps).encode()
+    kk = [[rand_scalar(r) for _ in range(n)] for _ in range(sets)]
+    got = t.msm(b"".join(scalars_bytes(k) for k in kk), n_sets=sets, offset=off, n=n)
+    for s in range(sets):
+        assert got[s] == G.msm(kk[s], ps[off : off + n]).encode()
+    t.close()

@@ -1,0 +1,298 @@
+"""GPU parity of the protocol layer: InnerProductProof and the R1CS Prover/Verifier of the
+product (CUDA engine behind the C ABI) against the oracle's restatement of the reference,
+on the same seeded inputs.  Bar: byte-identical proofs and identical accept/reject.
+
+Mirrors the reference's own tests: make_ipp_{1,2,4,32,64}
+(src/inner_product_proof.rs:507-583), the shuffle / example / range-proof gadget tests
+(tests/r1cs.rs:136-214, 542-587, 655-703) and its serialization roundtrip."""
+import random
+
+import pytest
+
+from oracle import gadgets
+from oracle import group as G
+from oracle import protocol as O
+from tests.util import points_bytes, scalars_bytes
+
+pytestmark = pytest.mark.gpu
+L = G.L
+
+
+@pytest.fixture(scope="module")
+def env(ctx):
+    from mpc_bulletproof_b200.protocol import Gens
+
+    pc = O.PedersenGens()
+    bp = O.BulletproofGens(128, 1)
+    gens = Gens(ctx, points_bytes(bp.G(128)), points_bytes(bp.H(128)), pc.B.encode(), pc.B_blinding.encode())
+    return pc, bp, gens
+
+
+# ------------------------------------------------------------------ inner product proof
+def _ipp_case(ctx, n, seed):
+    from mpc_bulletproof_b200 import Table
+    from mpc_bulletproof_b200 import protocol as P
+
+    r = random.Random(seed)
+    bp = O.BulletproofGens(n, 1)
+    Gs, Hs = bp.G(n), bp.H(n)
+    Q = G.hash_to_group_sha512(b"test point")
+    a = [r.randrange(L) for _ in range(n)]
+    b = [r.randrange(L) for _ in range(n)]
+    c = O.inner_product(a, b)
+    y_inv = r.randrange(1, L)
+    Gf = [1] * n
+    Hf = [pow(y_inv, i, L) for i in range(n)]
+    # P = <a,G> + <b',H> + c Q with b'_i = b_i y^-i  (helper of inner_product_proof.rs:481-500)
+    Ppt = G.msm(a + [b[i] * Hf[i] % L for i in range(n)] + [c], Gs + Hs + [Q])
+    want = O.InnerProductProof.create(O.Transcript(b"innerproducttest"), Q, Gf, Hf, Gs, Hs, a, b)
+    tG, tH = Table(ctx, points_bytes(Gs)), Table(ctx, points_bytes(Hs))
+    got = P.InnerProductProof.create(ctx, P.Transcript(b"innerproducttest"), Q.encode(), Gf, Hf, tG, tH, a, b)
+    assert got.to_bytes() == want.to_bytes()
+    assert len(got.to_bytes()) == 32 * (2 * (n.bit_length() - 1) + 2)
+    # verify, then verify again from bytes (roundtrip), then a tampered proof must fail
+    got.verify(ctx, n, P.Transcript(b"innerproducttest"), Gf, Hf, Ppt.encode(), Q.encode(), tG, tH)
+    P.InnerProductProof.from_bytes(want.to_bytes()).verify(
+        ctx, n, P.Transcript(b"innerproducttest"), Gf, Hf, Ppt.encode(), Q.encode(), tG, tH
+    )
+    bad = bytearray(got.to_bytes())
+    bad[-1] ^= 1
+    with pytest.raises((P.VerificationError, P.FormatError)):
+        P.InnerProductProof(bytes(bad)).verify(ctx, n, P.Transcript(b"innerproducttest"), Gf, Hf, Ppt.encode(), Q.encode(), tG, tH)
+    with pytest.raises(P.VerificationError):
+        got.verify(ctx, n, P.Transcript(b"innerproducttest"), Gf, Hf, (Ppt + Q).encode(), Q.encode(), tG, tH)
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 32, 64])
+def test_make_ipp(ctx, n):
+    _ipp_case(ctx, n, 1000 + n)
+
+
+def test_ipp_general_factors(ctx):
+    """G_factors other than one (the R1CS prover passes u for the second phase)."""
+    from mpc_bulletproof_b200 import Table
+    from mpc_bulletproof_b200 import protocol as P
+
+    n = 16
+    r = random.Random(77)
+    bp = O.BulletproofGens(n, 1)
+    Gs, Hs = bp.G(n), bp.H(n)
+    Q = G.hash_to_group_sha512(b"another point")
+    a = [r.randrange(L) for _ in range(n)]
+    b = [r.randrange(L) for _ in range(n)]
+    Gf = [r.randrange(1, L) for _ in range(n)]
+    Hf = [r.randrange(1, L) for _ in range(n)]
+    want = O.InnerProductProof.create(O.Transcript(b"t"), Q, Gf, Hf, Gs, Hs, a, b)
+    got = P.InnerProductProof.create(
+        ctx, P.Transcript(b"t"), Q.encode(), Gf, Hf, Table(ctx, points_bytes(Gs)), Table(ctx, points_bytes(Hs)), a, b
+    )
+    assert got.to_bytes() == want.to_bytes()
+
+
+def test_ipp_rejects_non_power_of_two(ctx):
+    from mpc_bulletproof_b200 import BpgError, Table
+    from mpc_bulletproof_b200 import protocol as P
+    from mpc_bulletproof_b200._lib import BPG_ERR_POW2
+
+    bp = O.BulletproofGens(4, 1)
+    t = Table(ctx, points_bytes(bp.G(4)))
+    with pytest.raises(BpgError) as e:
+        P.InnerProductProof.create(ctx, P.Transcript(b"t"), G.BASEPOINT.encode(), [1] * 3, [1] * 3, t, t, [1, 2, 3], [4, 5, 6])
+    assert e.value.code == BPG_ERR_POW2
+
+
+# ------------------------------------------------------------------ transcript / commitments
+def test_transcript_matches_oracle():
+    from mpc_bulletproof_b200 import protocol as P
+
+    t, o = P.Transcript(b"test protocol"), O.Transcript(b"test protocol")
+    t.append_message(b"some label", b"some data")
+    o.append_message(b"some label", b"some data")
+    assert t.challenge_bytes(b"challenge", 32).hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+    for i in range(5):
+        t.append_u64(b"n", i)
+        o.append_u64(b"n", i)
+        assert t.challenge_scalar(b"c") == o.challenge_scalar(b"c")
+
+
+def test_pedersen_commit(env):
+    pc, bp, gens = env
+    r = random.Random(3)
+    vs = [0, 1, L - 1] + [r.randrange(L) for _ in range(5)]
+    bs = [0, L - 1, 1] + [r.randrange(L) for _ in range(5)]
+    got = gens.commit_batch(vs, bs)
+    for v, b, c in zip(vs, bs, got):
+        assert c == pc.commit(v, b).encode()
+
+
+# ------------------------------------------------------------------ R1CS
+def _both(env, label, build, seed):
+    """Runs `build(prover, rng)` against the oracle Prover and the product Prover with the
+    same blinding seed; returns (oracle proof bytes, product proof bytes, commitments)."""
+    from mpc_bulletproof_b200 import protocol as P
+
+    pc, bp, gens = env
+    out = []
+    for prover_cls in ("oracle", "product"):
+        r = random.Random(seed)
+        if prover_cls == "oracle":
+            p = O.Prover(pc, O.Transcript(label))
+            coms = build(p, r, lambda c: c.encode())
+            out.append((p.prove(bp, O.Blindings(seed)).to_bytes(), coms))
+        else:
+            p = P.Prover(gens, P.Transcript(label))
+            coms = build(p, r, lambda c: c)
+            out.append((p.prove(seed), coms))
+    return out
+
+
+def _verify_both(env, label, build_v, proof, coms):
+    from mpc_bulletproof_b200 import protocol as P
+
+    pc, bp, gens = env
+    ov = O.Verifier(pc, O.Transcript(label))
+    build_v(ov, [G.decode(c) for c in coms])
+    oracle_ok = True
+    try:
+        ov.verify(O.R1CSProof.from_bytes(proof), bp)
+    except O.VerificationError:
+        oracle_ok = False
+    pv = P.Verifier(gens, P.Transcript(label))
+    build_v(pv, coms)
+    product_ok = True
+    try:
+        pv.verify(proof)
+    except P.VerificationError:
+        product_ok = False
+    assert oracle_ok == product_ok
+    return product_ok
+
+
+@pytest.mark.parametrize("c2,ok", [(9, True), (10, False)])
+def test_example_gadget(env, c2, ok):
+    """tests/r1cs.rs:542-563: (3+4)*(6+1) = 40+9 holds, = 40+10 is rejected."""
+
+    def build(p, r, enc):
+        cv = [p.commit(x, r.randrange(L)) for x in (3, 4, 6, 1, 40)]
+        v = [var for _, var in cv]
+        gadgets.example_gadget(p, v[0], v[1], v[2], v[3], v[4], c2)
+        return [enc(c) for c, _ in cv]
+
+    def build_v(vf, coms):
+        v = [vf.commit(c) for c in coms]
+        gadgets.example_gadget(vf, v[0], v[1], v[2], v[3], v[4], c2)
+
+    (op, oc), (pp, pcoms) = _both(env, b"R1CSExampleGadget", build, 11)
+    assert oc == pcoms
+    assert op == pp, "proof bytes differ from the oracle"
+    assert pp[0] == 0 and len(pp) == 1 + 11 * 32 + 32 * 2  # one-phase proof, n = 1
+    assert _verify_both(env, b"R1CSExampleGadget", build_v, pp, pcoms) == ok
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 24, 42])
+def test_shuffle_gadget(env, k):
+    """tests/r1cs.rs:136-214: k-shuffles incl. non-power-of-two multiplier counts (padding)."""
+    label = b"ShuffleProofTest"
+
+    def mk(bad):
+        def build(p, r, enc):
+            inp = [r.randrange(2**64) for _ in range(k)]
+            outp = inp[:]
+            r.shuffle(outp)
+            if bad:
+                outp[0] += 1
+            p.transcript.append_message(b"dom-sep", b"ShuffleProof")
+            p.transcript.append_u64(b"k", k)
+            # re-create the prover after the transcript prefix, as the reference does
+            ic = [p.commit(v, r.randrange(L)) for v in inp]
+            oc = [p.commit(v, r.randrange(L)) for v in outp]
+            gadgets.shuffle_gadget(p, [v for _, v in ic], [v for _, v in oc])
+            return [enc(c) for c, _ in ic + oc]
+
+        return build
+
+    def build_v(vf, coms):
+        vf.transcript.append_message(b"dom-sep", b"ShuffleProof")
+        vf.transcript.append_u64(b"k", k)
+        vs = [vf.commit(c) for c in coms]
+        gadgets.shuffle_gadget(vf, vs[:k], vs[k:])
+
+    (op, oc), (pp, pcoms) = _both(env, label, mk(False), 100 + k)
+    assert oc == pcoms and op == pp
+    assert pp[0] == (0 if k == 1 else 1)
+    assert _verify_both(env, label, build_v, pp, pcoms) is True
+    if k in (2, 5):
+        (op, oc), (pp, pcoms) = _both(env, label, mk(True), 200 + k)
+        assert op == pp
+        assert _verify_both(env, label, build_v, pp, pcoms) is False
+
+
+@pytest.mark.parametrize("n", [2, 10, 32, 63])
+def test_range_proof_gadget(env, n):
+    """tests/r1cs.rs:655-703: in-range values verify, max+1 is rejected."""
+    label = b"RangeProofTest"
+    r0 = random.Random(n)
+    mx = (1 << n) - 1
+    for val, ok in [(r0.randrange(0, mx), True), (mx + 1, False)]:
+
+        def build(p, r, enc):
+            com, var = p.commit(val, r.randrange(L))
+            gadgets.range_proof_gadget(p, var, val, n)
+            return [enc(com)]
+
+        def build_v(vf, coms):
+            var = vf.commit(coms[0])
+            gadgets.range_proof_gadget(vf, var, None, n)
+
+        (op, oc), (pp, pcoms) = _both(env, label, build, 300 + n)
+        assert oc == pcoms and op == pp
+        assert _verify_both(env, label, build_v, pp, pcoms) == ok
+
+
+def test_proof_format_errors(env):
+    from mpc_bulletproof_b200 import protocol as P
+
+    pc, bp, gens = env
+
+    def build(p, r, enc):
+        cv = [p.commit(x, r.randrange(L)) for x in (3, 4, 6, 1, 40)]
+        v = [var for _, var in cv]
+        gadgets.example_gadget(p, v[0], v[1], v[2], v[3], v[4], 9)
+        return [enc(c) for c, _ in cv]
+
+    (_, _), (pp, coms) = _both(env, b"R1CSExampleGadget", build, 5)
+
+    def verifier():
+        vf = P.Verifier(gens, P.Transcript(b"R1CSExampleGadget"))
+        v = [vf.commit(c) for c in coms]
+        gadgets.example_gadget(vf, v[0], v[1], v[2], v[3], v[4], 9)
+        return vf
+
+    for bad in (b"", pp[:-1], bytes([7]) + pp[1:], pp[:40]):
+        with pytest.raises(P.FormatError):
+            verifier().verify(bad)
+    # a point that is not a valid ristretto encoding -> FormatError (proof.rs:141-145)
+    broken = bytearray(pp)
+    broken[1:33] = bytes.fromhex("01" + "00" * 31)
+    with pytest.raises(P.FormatError):
+        verifier().verify(bytes(broken))
+    # identity commitment point -> VerificationError (transcript.rs:101-113)
+    ident = bytearray(pp)
+    ident[1:33] = bytes(32)
+    with pytest.raises(P.VerificationError):
+        verifier().verify(bytes(ident))
+
+
+def test_generators_capacity_error(ctx):
+    from mpc_bulletproof_b200 import protocol as P
+
+    pc = O.PedersenGens()
+    bp = O.BulletproofGens(2, 1)
+    gens = P.Gens(ctx, points_bytes(bp.G(2)), points_bytes(bp.H(2)), pc.B.encode(), pc.B_blinding.encode())
+    p = P.Prover(gens, P.Transcript(b"cap"))
+    _, var = p.commit(5, 7)
+    out = var
+    for _ in range(3):
+        _, _, out = p.multiply(out, out)
+    with pytest.raises(P.InvalidGeneratorsLength):
+        p.prove(1)

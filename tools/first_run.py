@@ -13,12 +13,13 @@ pb = points_bytes([rand_point(r) for _ in range(m)])
 for lg in (12, 16, 18, 20, 22):
     n = 1 << lg
     tab = Table(ctx, pb * (n // m))
-    sc = torch.randint(0, 2**31 - 1, (n, 8), dtype=torch.int32, device="cuda")
+    sc = torch.randint(-2**31, 2**31, (n, 8), dtype=torch.int64, device="cuda").to(torch.int32)
     sc[:, 7] &= 0x0FFFFFFF
     out = torch.zeros(32, dtype=torch.int32, device="cuda")
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    for c in ([0] if lg < 20 else [0, 14, 15, 17]):
-        ctx.set_window(c)
+    for c in [0, -1]:
+        if c == -1:
+            tab.set_windows(0)
         for _ in range(2):
             tab.dev_msm(sc.data_ptr(), 1, out.data_ptr())
         torch.cuda.synchronize()
