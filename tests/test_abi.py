@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "bpgpu.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(bpg_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(bpg_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_exported():

@@ -101,20 +101,7 @@ def test_ipp_rejects_non_power_of_two(ctx):
     assert e.value.code == BPG_ERR_POW2
 
 
-# ------------------------------------------------------------------ transcript / commitments
-def test_transcript_matches_oracle():
-    from mpc_bulletproof_b200 import protocol as P
-
-    t, o = P.Transcript(b"test protocol"), O.Transcript(b"test protocol")
-    t.append_message(b"some label", b"some data")
-    o.append_message(b"some label", b"some data")
-    assert t.challenge_bytes(b"challenge", 32).hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
-    for i in range(5):
-        t.append_u64(b"n", i)
-        o.append_u64(b"n", i)
-        assert t.challenge_scalar(b"c") == o.challenge_scalar(b"c")
-
-
+# ------------------------------------------------------------------ commitments
 def test_pedersen_commit(env):
     pc, bp, gens = env
     r = random.Random(3)
