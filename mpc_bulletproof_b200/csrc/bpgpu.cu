@@ -407,13 +407,13 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   LAUNCH_CHECK();
   prof_mark(ctx, BPG_PROF_REDUCE);
   unsigned nred = cfg.nwin * cfg.nchunks;
-  k_reduce<<<(nred + RED_THREADS - 1) / RED_THREADS, RED_THREADS, 0, st>>>(buckets, cfg, chunks);
+  k_reduce<<<(nred * 4 + RED_THREADS - 1) / RED_THREADS, RED_THREADS, 0, st>>>(buckets, cfg, chunks);
   LAUNCH_CHECK();
   prof_mark(ctx, BPG_PROF_COMBINE);
   k_combine<<<cfg.nwin, COMB_THREADS, 0, st>>>(chunks, cfg, wins);
   LAUNCH_CHECK();
   prof_mark(ctx, BPG_PROF_HORNER);
-  k_horner<<<(nsets + 31) / 32, 32, 0, st>>>(wins, cfg, d_out_ext);
+  k_horner<<<nsets, 32, 0, st>>>(wins, cfg, d_out_ext);
   LAUNCH_CHECK();
   prof_mark(ctx, -1);
   return BPG_OK;

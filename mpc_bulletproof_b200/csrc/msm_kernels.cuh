@@ -19,6 +19,7 @@
 // any evaluation order gives the same canonical encoding.
 #pragma once
 #include "ge.cuh"
+#include "ge4.cuh"
 #include "sc.cuh"
 
 namespace bpg {
@@ -193,6 +194,51 @@ __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ sc
 // ---------------------------------------------------------------------------
 constexpr int ACC_THREADS = 128;
 
+// bucket sums are parked in the "cached" operand layout of ge4_add_cached:
+// [Y-X | Y+X | 2Z | 2dT], so that the reduction's first addition needs no conversion
+__device__ __forceinline__ void ge_store_cached(uint32_t* p, const ge_ext& a) {
+  fe_store(p, fe_sub(a.Y, a.X));
+  fe_store(p + 8, fe_add_nc(a.Y, a.X));
+  fe_store(p + 16, fe_add_nc(a.Z, a.Z));
+  fe_store(p + 24, fe_mul(a.T, fe_const(BPG_K(K_D2))));
+}
+
+// sum of one point per quad over the whole block -> quad 0 of warp 0.
+// sm: [warps][32] words.  Every thread of the block must call it.
+__device__ __forceinline__ ge4 block_sum_quads(ge4 p, uint32_t (*sm)[32]) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int off = 16; off >= 4; off >>= 1) {
+    ge4 o;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o.c.v[i] = __shfl_down_sync(BPG_FULL_MASK, p.c.v[i], off);
+    p = ge4_add(p, o);
+  }
+  if (nw == 1) return p;
+  if (lane < 4) ge4_store(sm[wid], p);
+  __syncthreads();
+  if (wid == 0) {
+    int quad = lane >> 2;
+    ge4 t = ge4_identity();
+    // up to 32 warps: each quad folds warps quad, quad+8, ...
+    for (int k = 0; k < (nw + 7) / 8; k++) {
+      int w = quad + 8 * k;
+      ge4 o = w < nw ? ge4_load(sm[w]) : ge4_identity();
+      t = ge4_add(t, o);
+    }
+#pragma unroll
+    for (int off = 16; off >= 4; off >>= 1) {
+      ge4 o;
+#pragma unroll
+      for (int i = 0; i < 8; i++) o.c.v[i] = __shfl_down_sync(BPG_FULL_MASK, t.c.v[i], off);
+      t = ge4_add(t, o);
+    }
+    p = t;
+  }
+  __syncthreads();
+  return p;
+}
+
 __global__ void __launch_bounds__(ACC_THREADS) k_accum(const uint32_t* __restrict__ table,
                                                         const uint32_t* __restrict__ offsets,
                                                         const uint32_t* __restrict__ entries, MsmCfg cfg,
@@ -214,10 +260,10 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accum(const uint32_t* __restric
     ge_load_niels(q, table + (size_t)(e & ~ENTRY_NEG) * 24);
     acc = ge_madd(acc, q, (e & ENTRY_NEG) != 0);
   }
-  ge_store_ext(bucket_sums + (size_t)b * 32, acc);
+  ge_store_cached(bucket_sums + (size_t)b * 32, acc);
 }
 
-// over-long buckets: one block per bucket, strided accumulation + shared-memory tree
+// over-long buckets: one block per bucket, strided accumulation, then a quad-cooperative block sum
 constexpr int BIG_THREADS = 256;
 __global__ void __launch_bounds__(BIG_THREADS) k_accum_big(const uint32_t* __restrict__ table,
                                                             const uint32_t* __restrict__ offsets,
@@ -225,7 +271,8 @@ __global__ void __launch_bounds__(BIG_THREADS) k_accum_big(const uint32_t* __res
                                                             uint32_t* __restrict__ bucket_sums,
                                                             const uint32_t* __restrict__ big_count,
                                                             const uint32_t* __restrict__ big_list) {
-  __shared__ uint32_t sm[BIG_THREADS / 2][32];
+  __shared__ uint32_t pts[BIG_THREADS][32];
+  __shared__ uint32_t sm[BIG_THREADS / 32][32];
   uint32_t nbig = min(*big_count, cfg.big_cap);
   for (uint32_t k = blockIdx.x; k < nbig; k += gridDim.x) {
     uint32_t b = big_list[k];
@@ -237,95 +284,100 @@ __global__ void __launch_bounds__(BIG_THREADS) k_accum_big(const uint32_t* __res
       ge_load_niels(q, table + (size_t)(e & ~ENTRY_NEG) * 24);
       acc = ge_madd(acc, q, (e & ENTRY_NEG) != 0);
     }
-    for (int half = BIG_THREADS / 2; half >= 1; half >>= 1) {
-      if (threadIdx.x >= (uint32_t)half && threadIdx.x < (uint32_t)(2 * half))
-        ge_store_ext(sm[threadIdx.x - half], acc);
-      __syncthreads();
-      if (threadIdx.x < (uint32_t)half) {
-        ge_ext o;
-        ge_load_ext(o, sm[threadIdx.x]);
-        acc = ge_add(acc, o);
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) ge_store_ext(bucket_sums + (size_t)b * 32, acc);
+    ge_store_ext(pts[threadIdx.x], acc);
+    __syncthreads();
+    // quad g sums points 4g..4g+3, then the block sum
+    int g = threadIdx.x >> 2;
+    ge4 t = ge4_load(pts[4 * g]);
+#pragma unroll
+    for (int j = 1; j < 4; j++) t = ge4_add(t, ge4_load(pts[4 * g + j]));
+    t = block_sum_quads(t, sm);
+    ge4 c = ge4_to_cached(t);  // park in cached layout like k_accum (all lanes: it shuffles)
+    if (threadIdx.x < 4) ge4_store(bucket_sums + (size_t)b * 32, c);
+    __syncthreads();
   }
 }
 
 // ---------------------------------------------------------------------------
-// bucket reduction: per (window, chunk) compute sum_j (q*chunk + j + 1) * B_j
+// bucket reduction: per (window, chunk) compute sum_j (q*chunk + j + 1) * B_j.
+// One QUAD per chunk (ge4.cuh): running sums cost 2 + 3 multiplication levels per bucket.
 // ---------------------------------------------------------------------------
-constexpr int RED_THREADS = 64;
+constexpr int RED_THREADS = 128;
 __global__ void __launch_bounds__(RED_THREADS) k_reduce(const uint32_t* __restrict__ bucket_sums, MsmCfg cfg,
                                                          uint32_t* __restrict__ chunk_sums) {
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= cfg.nwin * cfg.nchunks) return;
-  uint32_t win = g / cfg.nchunks, q = g % cfg.nchunks;
+  uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  uint32_t total = cfg.nwin * cfg.nchunks;
+  bool live = g < total;
+  uint32_t gg = live ? g : total - 1;  // idle quads shadow the last chunk: shuffles need every lane
+  uint32_t win = gg / cfg.nchunks, q = gg % cfg.nchunks;
   const uint32_t* src = bucket_sums + ((size_t)win * cfg.nb + (size_t)q * cfg.chunk) * 32;
-  ge_ext run = ge_identity(), acc = ge_identity();
+  ge4 run = ge4_identity(), acc = ge4_identity();
   for (int j = (int)cfg.chunk - 1; j >= 0; j--) {
-    ge_ext bj;
-    ge_load_ext(bj, src + (size_t)j * 32);
-    run = ge_add(run, bj);
-    acc = ge_add(acc, run);
+    ge4 bj = ge4_load(src + (size_t)j * 32);  // cached layout
+    run = ge4_add_cached(run, bj);
+    acc = ge4_add(acc, run);
   }
-  // + (q*chunk) * run, MSB-first double-and-add
+  // + (q*chunk) * run by double-and-add over a block-uniform number of bits
   uint32_t m = q * cfg.chunk;
-  if (m) {
-    ge_ext t = run;
-    int top = 31 - __clz(m);
-    for (int bit = top - 1; bit >= 0; bit--) {
-      t = ge_dbl(t);
-      if ((m >> bit) & 1u) t = ge_add(t, run);
+  uint32_t mmax = (cfg.nchunks - 1) * cfg.chunk;
+  if (mmax) {
+    int top = 31 - __clz(mmax);
+    ge4 rc = ge4_to_cached(run);
+    ge4 t = ge4_identity();
+    for (int bit = top; bit >= 0; bit--) {
+      t = ge4_dbl(t);
+      ge4 ta = ge4_add_cached(t, rc);
+      bool set = (m >> bit) & 1u;
+      t.c = fe_sel(set, ta.c, t.c);
     }
-    acc = ge_add(acc, t);
+    acc = ge4_add(acc, t);
   }
-  ge_store_ext(chunk_sums + (size_t)g * 32, acc);
+  if (live) ge4_store(chunk_sums + (size_t)g * 32, acc);
 }
 
 // one block per window: sum of its chunk sums
 constexpr int COMB_THREADS = 128;
 __global__ void __launch_bounds__(COMB_THREADS) k_combine(const uint32_t* __restrict__ chunk_sums, MsmCfg cfg,
                                                            uint32_t* __restrict__ window_sums) {
-  __shared__ uint32_t sm[COMB_THREADS / 2][32];
+  __shared__ uint32_t sm[COMB_THREADS / 32][32];
   uint32_t win = blockIdx.x;
   const uint32_t* src = chunk_sums + (size_t)win * cfg.nchunks * 32;
-  ge_ext acc = ge_identity();
-  for (uint32_t i = threadIdx.x; i < cfg.nchunks; i += COMB_THREADS) {
-    ge_ext o;
-    ge_load_ext(o, src + (size_t)i * 32);
-    acc = ge_add(acc, o);
+  uint32_t quad = threadIdx.x >> 2, nquads = COMB_THREADS / 4;
+  ge4 acc = ge4_identity();
+  for (uint32_t base = 0; base < cfg.nchunks; base += nquads) {
+    uint32_t i = base + quad;
+    ge4 o = i < cfg.nchunks ? ge4_load(src + (size_t)i * 32) : ge4_identity();
+    acc = ge4_add(acc, o);
   }
-  for (int half = COMB_THREADS / 2; half >= 1; half >>= 1) {
-    if (threadIdx.x >= (uint32_t)half && threadIdx.x < (uint32_t)(2 * half))
-      ge_store_ext(sm[threadIdx.x - half], acc);
-    __syncthreads();
-    if (threadIdx.x < (uint32_t)half) {
-      ge_ext o;
-      ge_load_ext(o, sm[threadIdx.x]);
-      acc = ge_add(acc, o);
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) ge_store_ext(window_sums + (size_t)win * 32, acc);
+  acc = block_sum_quads(acc, sm);
+  if (threadIdx.x < 4) ge4_store(window_sums + (size_t)win * 32, acc);
 }
 
-// one thread per set: Horner over windows, top window first
-__global__ void k_horner(const uint32_t* __restrict__ window_sums, MsmCfg cfg, uint32_t* __restrict__ out_ext) {
-  uint32_t set = blockIdx.x * blockDim.x + threadIdx.x;
-  if (set >= (uint32_t)cfg.nsets) return;
+// one warp per set: sum_w 2^(c w) S_w (Horner, top window first); for windowed tables the
+// weights are already in the points and it is a plain sum
+__global__ void __launch_bounds__(32) k_horner(const uint32_t* __restrict__ window_sums, MsmCfg cfg,
+                                                uint32_t* __restrict__ out_ext) {
+  uint32_t set = blockIdx.x;
   const uint32_t* src = window_sums + (size_t)set * cfg.W * 32;
-  ge_ext acc;
-  ge_load_ext(acc, src + (size_t)(cfg.W - 1) * 32);
-  for (int w = cfg.W - 2; w >= 0; w--) {
-    // windowed tables already carry the 2^(c w) weights in their points
-    if (cfg.win_stride == 0)
-      for (int i = 0; i < cfg.c; i++) acc = ge_dbl(acc);
-    ge_ext s;
-    ge_load_ext(s, src + (size_t)w * 32);
-    acc = ge_add(acc, s);
+  ge4 acc;
+  if (cfg.win_stride) {
+    uint32_t quad = threadIdx.x >> 2;
+    acc = ge4_identity();
+    for (uint32_t base = 0; base < (uint32_t)cfg.W; base += 8) {
+      uint32_t w = base + quad;
+      ge4 o = w < (uint32_t)cfg.W ? ge4_load(src + (size_t)w * 32) : ge4_identity();
+      acc = ge4_add(acc, o);
+    }
+    acc = block_sum_quads(acc, nullptr);
+  } else {
+    // every quad runs the same chain (redundantly): the cost is the chain, not the lanes
+    acc = ge4_load(src + (size_t)(cfg.W - 1) * 32);
+    for (int w = cfg.W - 2; w >= 0; w--) {
+      for (int i = 0; i < cfg.c; i++) acc = ge4_dbl(acc);
+      acc = ge4_add(acc, ge4_load(src + (size_t)w * 32));
+    }
   }
-  ge_store_ext(out_ext + (size_t)set * 32, acc);
+  if (threadIdx.x < 4) ge4_store(out_ext + (size_t)set * 32, acc);
 }
 
 // ---------------------------------------------------------------------------

@@ -1,0 +1,124 @@
+"""IPP create/verify (n = 2^10..2^18) and R1CS prove/verify at 2^16 multipliers on one B200
+(BASELINE.json configs 2 and 4), through the host mirror.  Prints one JSON object.
+Generators are synthetic: k_i*B from the device fixed-base comb (the mounted fork derives
+its generators the same way, reference src/generators.rs:117-123)."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from mpc_bulletproof_b200 import Comb, Context, Table  # noqa: E402
+from mpc_bulletproof_b200 import protocol as P  # noqa: E402
+
+L = P.L
+BASE = bytes.fromhex("e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76")
+
+
+def synth_points(ctx, comb, n, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    k = torch.randint(-(2**31), 2**31, (n, 8), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
+    k[:, 7] &= 0x0FFFFFFF
+    out = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    comb.dev_mul(k.data_ptr(), n, out.data_ptr())
+    ctx.sync()
+    return bytes(out.cpu().numpy().tobytes())
+
+
+def rand_scalars(n, seed):
+    import numpy as np
+
+    g = np.random.Generator(np.random.PCG64(seed))
+    a = g.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    a[:, 31] &= 0x0F
+    raw = a.tobytes()
+    return [int.from_bytes(raw[32 * i : 32 * i + 32], "little") for i in range(n)]
+
+
+def main():
+    lgs = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "10,12,14,16".split(","))]
+    r1cs_lg = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    ctx = Context(0)
+    comb = Comb(ctx, BASE)
+    res = {"ipp": [], "r1cs": None}
+    maxn = 1 << max(lgs + [r1cs_lg])
+    Gb = synth_points(ctx, comb, maxn, 1)
+    Hb = synth_points(ctx, comb, maxn, 2)
+    Q = synth_points(ctx, comb, 1, 3)
+    for lg in lgs:
+        n = 1 << lg
+        tG, tH = Table(ctx, Gb[: 32 * n]), Table(ctx, Hb[: 32 * n])
+        a, b = rand_scalars(n, 10 + lg), rand_scalars(n, 20 + lg)
+        Gf, Hf = rand_scalars(n, 30 + lg), rand_scalars(n, 40 + lg)
+        # warm-up + timed create (bytes conversion of the inputs is outside the library call but inside here)
+        best = 1e9
+        for it in range(3):
+            t0 = time.perf_counter()
+            proof = P.InnerProductProof.create(ctx, P.Transcript(b"bench"), Q, Gf, Hf, tG, tH, a, b)
+            best = min(best, time.perf_counter() - t0)
+        # P for verification: <a*Gf, G> + <b*Hf, H> + <a,b> Q through the MSM engine
+        c = sum(x * y for x, y in zip(a, b)) % L
+        from mpc_bulletproof_b200._lib import lib, check
+        import ctypes
+
+        sc = b"".join(P.sc_bytes(x) for x in [c] + [a[i] * Gf[i] % L for i in range(n)] + [b[i] * Hf[i] % L for i in range(n)])
+        out = ctypes.create_string_buffer(32)
+        tabs = (ctypes.c_void_p * 2)(tG._h, tH._h)
+        offs = (ctypes.c_size_t * 2)(0, 0)
+        lens = (ctypes.c_size_t * 2)(n, n)
+        check(lib().bpg_msm_mixed(ctx._h, Q, 1, tabs, offs, lens, 2, sc, out))
+        bestv = 1e9
+        for it in range(3):
+            t0 = time.perf_counter()
+            proof.verify(ctx, n, P.Transcript(b"bench"), Gf, Hf, out.raw, Q, tG, tH)
+            bestv = min(bestv, time.perf_counter() - t0)
+        res["ipp"].append({"n": n, "create_ms": best * 1e3, "verify_ms": bestv * 1e3, "proof_bytes": len(proof.to_bytes())})
+        print(res["ipp"][-1], file=sys.stderr, flush=True)
+        tG.close()
+        tH.close()
+    # R1CS: the reference's DummyCircuit (benches/r1cs.rs:24-32): commit_public(val), n chained squarings
+    n = 1 << r1cs_lg
+    t0 = time.perf_counter()
+    gens = P.Gens(ctx, Gb[: 32 * n], Hb[: 32 * n], BASE, synth_points(ctx, comb, 1, 4))
+    t_gens = time.perf_counter() - t0
+
+    def build(cs, val):
+        var = cs.commit_public(val)
+        for _ in range(n):
+            _, _, var = cs.multiply(var, var)
+
+    val = rand_scalars(1, 99)[0]
+    prove_ms, verify_ms = [], []
+    for it in range(3):
+        p = P.Prover(gens, P.Transcript(b"bench r1cs"))
+        build(p, val)
+        t0 = time.perf_counter()
+        proof = p.prove(1234 + it)
+        prove_ms.append((time.perf_counter() - t0) * 1e3)
+        v = P.Verifier(gens, P.Transcript(b"bench r1cs"))
+        build(v, val)
+        t0 = time.perf_counter()
+        v.verify(proof)
+        verify_ms.append((time.perf_counter() - t0) * 1e3)
+    # a wrong statement must be rejected at the same cost (reference benches/r1cs.rs:83)
+    v = P.Verifier(gens, P.Transcript(b"bench r1cs"))
+    build(v, (val + 1) % L)
+    rejected = False
+    try:
+        v.verify(proof)
+    except P.VerificationError:
+        rejected = True
+    res["r1cs"] = {
+        "multipliers": n, "circuit": "DummyCircuit (chain of squarings)", "prove_ms": min(prove_ms), "verify_ms": min(verify_ms),
+        "prove_ms_all": prove_ms, "verify_ms_all": verify_ms, "proof_bytes": len(proof), "false_statement_rejected": rejected,
+        "gens_upload_ms": t_gens * 1e3,
+    }
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
