@@ -8,6 +8,9 @@
 // here is what the reference also does serially on the CPU: the constraint-system
 // bookkeeping, the transcript, and O(n) scalar preparation.
 #include <array>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <memory>
 #include <new>
@@ -20,6 +23,20 @@
 using namespace bpg_host;
 
 typedef std::array<uint8_t, 32> Bytes32;
+
+// BPG_TRACE=1: per-stage wall-clock of prove/verify on stderr (development aid)
+struct StageTimer {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  const char* what;
+  explicit StageTimer(const char* w) : on(getenv("BPG_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), what(w) {}
+  void lap(const char* stage) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bpg] %s %-22s %8.3f ms\n", what, stage, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 static inline void sc_bytes(const Scalar& s, uint8_t* out) { s.to_bytes(out); }
 static std::vector<uint8_t> sc_vec_bytes(const std::vector<Scalar>& v) {
@@ -722,6 +739,7 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   const bpg_gens* g = cs->gens;
   Xoshiro rng(rng_seed);
   R1CSProof proof;
+  StageTimer tm("prove");
   tr.append_u64("m", cs->v.size());  // :420
   size_t n1 = cs->a_L.size();
   if (g->cap < n1) return BPG_ERR_CAPACITY;  // :450-452
@@ -730,8 +748,10 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   for (auto& x : s_L) x = rng.scalar();
   for (auto& x : s_R) x = rng.scalar();
   uint8_t c3[96];
+  tm.lap("blindings s_L s_R");
   int rc = commit_AIOS(cs, 0, n1, i_b1, o_b1, s_b1, s_L.data(), s_R.data(), c3);  // :465-494
   if (rc) return rc;
+  tm.lap("A_I1 A_O1 S1 msm");
   memcpy(proof.A_I1.data(), c3, 32);
   memcpy(proof.A_O1.data(), c3 + 32, 32);
   memcpy(proof.S1.data(), c3 + 64, 32);
@@ -769,7 +789,9 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   Scalar y = tr.challenge_scalar("y"), z = tr.challenge_scalar("z");  // :584-585
   std::vector<Scalar> wL, wR, wO, wV;
   Scalar wc;
+  tm.lap("phase 2");
   cs->flattened_constraints(z, wL, wR, wO, wV, wc);
+  tm.lap("flattened_constraints");
   Scalar y_inv = y.invert();
   std::vector<Scalar> exp_y_inv(padded_n);
   {
@@ -798,6 +820,7 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   // util.rs:152-170
   Scalar t1 = ip(l1, r0), t2 = ip(l1, r1) + ip(l2, r0), t3 = ip(l2, r1) + ip(l3, r0), t4 = ip(l1, r3) + ip(l3, r1),
          t5 = ip(l2, r3), t6 = ip(l3, r3);
+  tm.lap("l/r polys + t_i");
   Scalar tb1 = rng.scalar(), tb3 = rng.scalar(), tb4 = rng.scalar(), tb5 = rng.scalar(), tb6 = rng.scalar();  // :621-625
   {
     uint8_t vals[160], blinds[160], Ts[160];
@@ -844,6 +867,7 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
     Gf[i] = i < n1 ? Scalar::one() : u;
     Hf[i] = exp_y_inv[i] * Gf[i];
   }
+  tm.lap("T commits, l/r eval");
   tr.innerproduct_domain_sep(padded_n);  // inner_product_proof.rs:72
   uint8_t wb[32];
   w.to_bytes(wb);
@@ -852,9 +876,11 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   rc = bpg_ipp_begin_shared(cs->ctx, g->table, g->g_base(), g->h_base(), g->b_id(), wb, padded_n, gfb.data(),
                             hfb.data(), lb.data(), rb.data(), &st);
   if (rc) return rc;
+  tm.lap("ipp begin (H2D)");
   rc = InnerProductProof::run_rounds(st, tr, &proof.ipp);
   bpg_ipp_free(st);
   if (rc) return rc;
+  tm.lap("ipp rounds");
   if (proof.serialized_size() > proof_cap) return BPG_ERR_ARG;
   proof.to_bytes(proof_out);
   *proof_len = proof.serialized_size();
@@ -869,6 +895,7 @@ extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_
   if (rc) return rc;
   Transcript& tr = *cs->tr;
   const bpg_gens* g = cs->gens;
+  StageTimer tm("verify");
   tr.append_u64("m", cs->V.size());
   size_t n1 = cs->num_vars;
   if (!tr.validate_and_append_point("A_I1", proof.A_I1.data())) return BPG_ERR_VERIFY;
@@ -896,9 +923,11 @@ extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_
   std::vector<Scalar> wL, wR, wO, wV;
   Scalar wc;
   cs->flattened_constraints(z, wL, wR, wO, wV, wc);
+  tm.lap("replay + flatten");
   std::vector<Scalar> u_sq, u_inv_sq, s;
   rc = proof.ipp.verification_scalars(padded_n, tr, u_sq, u_inv_sq, s);
   if (rc) return BPG_ERR_VERIFY;  // map_err(|_| VerificationError) :463
+  tm.lap("verification_scalars");
   const Scalar &a = proof.ipp.a, &b = proof.ipp.b;
   Scalar y_inv = y.invert();
   std::vector<Scalar> y_inv_vec(padded_n), yneg_wR(padded_n, Scalar::zero());
@@ -959,7 +988,9 @@ extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_
   size_t offs[3] = {g->b_id(), g->g_base(), g->h_base()}, lens[3] = {2, padded_n, padded_n};
   uint8_t mega[32];
   std::vector<uint8_t> scb = sc_vec_bytes(sc);
+  tm.lap("g/h scalars");
   rc = bpg_msm_mixed(cs->ctx, pts.data(), n_adhoc, tabs, offs, lens, 3, scb.data(), mega);
+  tm.lap("mega msm");
   if (rc == BPG_ERR_DECODE) return BPG_ERR_DECODE;  // a proof point that is not a valid encoding: FormatError
   if (rc) return rc;
   return is_identity_enc(mega) ? BPG_OK : BPG_ERR_VERIFY;  // :549
