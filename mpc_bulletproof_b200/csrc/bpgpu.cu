@@ -368,6 +368,8 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   size_t o_buckets = off; off += align_up((size_t)cfg.B * 128);
   size_t o_chunks = off;  off += align_up((size_t)cfg.nwin * cfg.nchunks * 128);
   size_t o_wins = off;    off += align_up((size_t)cfg.nwin * 128);
+  size_t o_order = off;   off += align_up((size_t)cfg.B * 4);
+  size_t o_bins = off;    off += align_up(SIZE_BINS * 4);
   int rc = ensure_ws(ctx, off);
   if (rc) return rc;
   uint32_t* counts = (uint32_t*)(ctx->ws + o_counts);
@@ -379,6 +381,8 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   uint32_t* buckets = (uint32_t*)(ctx->ws + o_buckets);
   uint32_t* chunks = (uint32_t*)(ctx->ws + o_chunks);
   uint32_t* wins = (uint32_t*)(ctx->ws + o_wins);
+  uint32_t* order = (uint32_t*)(ctx->ws + o_order);
+  uint32_t* bins = (uint32_t*)(ctx->ws + o_bins);
   cudaStream_t st = ctx->stream;
 
   prof_mark(ctx, BPG_PROF_HIST);
@@ -397,8 +401,16 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   prof_mark(ctx, BPG_PROF_SCATTER);
   k_scatter<<<gt, 256, 0, st>>>(d_scalars, d_set_ids, d_point_ids, cfg, offsets, counts, entries);
   LAUNCH_CHECK();
+  // bucket schedule by decreasing length (after the scan, overlapping nothing: three tiny kernels)
+  CK(cudaMemsetAsync(bins, 0, SIZE_BINS * 4, st));
+  k_size_hist<<<std::min<unsigned>((cfg.B + 255) / 256, (unsigned)ctx->sm_count * 4), 256, 0, st>>>(offsets, cfg.B, bins);
+  LAUNCH_CHECK();
+  k_size_scan<<<1, SIZE_BINS, 0, st>>>(bins);
+  LAUNCH_CHECK();
+  k_size_scatter<<<(cfg.B + 255) / 256, 256, 0, st>>>(offsets, cfg.B, bins, order);
+  LAUNCH_CHECK();
   prof_mark(ctx, BPG_PROF_ACCUM);
-  k_accum<<<(cfg.B + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, st>>>(table_base, offsets, entries, cfg,
+  k_accum<<<(cfg.B + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, st>>>(table_base, offsets, entries, order, cfg,
                                                                            buckets, big_count, big_list);
   LAUNCH_CHECK();
   prof_mark(ctx, BPG_PROF_ACCUM_BIG);

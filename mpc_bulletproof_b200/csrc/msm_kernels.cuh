@@ -239,14 +239,77 @@ __device__ __forceinline__ ge4 block_sum_quads(ge4 p, uint32_t (*sm)[32]) {
   return p;
 }
 
+// bucket schedule: buckets ordered by decreasing length, so that the 32 buckets of a warp
+// have (almost) the same trip count and the longest ones start first
+constexpr uint32_t SIZE_BINS = 1024;
+__global__ void __launch_bounds__(256) k_size_hist(const uint32_t* __restrict__ offsets, uint32_t B,
+                                                   uint32_t* __restrict__ bins /*[SIZE_BINS], zeroed*/) {
+  __shared__ uint32_t sh[SIZE_BINS];
+  for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    uint32_t cnt = offsets[b + 1] - offsets[b];
+    atomicAdd(&sh[min(cnt, SIZE_BINS - 1)], 1u);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x)
+    if (sh[i]) atomicAdd(&bins[i], sh[i]);
+}
+// single block: bins -> starting position of each size class, largest first
+__global__ void __launch_bounds__(SIZE_BINS) k_size_scan(uint32_t* __restrict__ bins) {
+  __shared__ uint32_t smem[33];
+  uint32_t i = threadIdx.x;
+  uint32_t v = bins[SIZE_BINS - 1 - i];  // reversed: class SIZE_BINS-1 first
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(v, &total, smem);
+  bins[SIZE_BINS - 1 - i] = ex;
+}
+__global__ void __launch_bounds__(256) k_size_scatter(const uint32_t* __restrict__ offsets, uint32_t B,
+                                                      uint32_t* __restrict__ bins, uint32_t* __restrict__ order) {
+  // block-private histogram first: one global atomic per (block, occupied size class)
+  __shared__ uint32_t cnt[SIZE_BINS];
+  __shared__ uint32_t base[SIZE_BINS];
+  for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t cls = 0, rank = 0;
+  if (b < B) {
+    cls = min(offsets[b + 1] - offsets[b], SIZE_BINS - 1);
+    rank = atomicAdd(&cnt[cls], 1u);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x)
+    if (cnt[i]) base[i] = atomicAdd(&bins[i], cnt[i]);
+  __syncthreads();
+  if (b < B) order[base[cls] + rank] = b;
+}
+
+BPG_DEF_CONST(K_DINV, 0xcdc9f843u, 0x25e0f276u, 0x4279542eu, 0x0b5dd698u, 0xcdb9cf66u, 0x2b162114u, 0x14d5ce43u,
+              0x40907ed2u)  // 1/d
+
+// the point (+-) of a Niels entry as an extended point with Z = 2: one multiplication
+__device__ __forceinline__ ge_ext ge_from_niels(const ge_niels& q, bool neg) {
+  ge_ext r;
+  fe x2 = fe_sub(q.ypx, q.ymx);   // 2x
+  fe t = fe_mul(q.t2d, fe_const(BPG_K(K_DINV)));  // 2xy
+  r.X = fe_canon(fe_cneg(x2, neg));
+  r.Y = fe_canon(fe_add(q.ypx, q.ymx));  // 2y
+  r.Z = fe_zero();
+  r.Z.v[0] = 2;
+  r.T = fe_canon(fe_cneg(t, neg));
+  return r;
+}
+
 __global__ void __launch_bounds__(ACC_THREADS) k_accum(const uint32_t* __restrict__ table,
                                                         const uint32_t* __restrict__ offsets,
-                                                        const uint32_t* __restrict__ entries, MsmCfg cfg,
+                                                        const uint32_t* __restrict__ entries,
+                                                        const uint32_t* __restrict__ order, MsmCfg cfg,
                                                         uint32_t* __restrict__ bucket_sums,
                                                         uint32_t* __restrict__ big_count,
                                                         uint32_t* __restrict__ big_list) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= cfg.B) return;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cfg.B) return;
+  uint32_t b = order[t];
   uint32_t beg = offsets[b], end = offsets[b + 1];
   if (end - beg > cfg.big_thresh) {
     uint32_t slot = atomicAdd(big_count, 1u);
@@ -254,11 +317,19 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accum(const uint32_t* __restric
     return;
   }
   ge_ext acc = ge_identity();
-  for (uint32_t i = beg; i < end; i++) {
-    uint32_t e = __ldg(entries + i);
+  if (beg < end) {
+    // software pipeline: the Niels entry of step k+1 is in flight while step k multiplies
+    uint32_t e = __ldg(entries + beg);
     ge_niels q;
     ge_load_niels(q, table + (size_t)(e & ~ENTRY_NEG) * 24);
-    acc = ge_madd(acc, q, (e & ENTRY_NEG) != 0);
+    uint32_t e_next = beg + 1 < end ? __ldg(entries + beg + 1) : 0;
+    acc = ge_from_niels(q, (e & ENTRY_NEG) != 0);
+    for (uint32_t i = beg + 1; i < end; i++) {
+      e = e_next;
+      ge_load_niels(q, table + (size_t)(e & ~ENTRY_NEG) * 24);
+      e_next = i + 1 < end ? __ldg(entries + i + 1) : 0;
+      acc = ge_madd(acc, q, (e & ENTRY_NEG) != 0);
+    }
   }
   ge_store_cached(bucket_sums + (size_t)b * 32, acc);
 }
