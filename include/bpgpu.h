@@ -186,6 +186,63 @@ int bpg_comb_mul(bpg_ctx* ctx, const bpg_comb* comb, const uint8_t* scalars_le /
 int bpg_dev_comb_mul(bpg_ctx* ctx, const bpg_comb* comb, const void* d_scalars, size_t n, void* d_out_bytes,
                      void* d_out_ext);
 
+/* ---- R1CS scalar preparation on the device ------------------------------------------
+ * The O(n) scalar vectors around the prover's and verifier's MSMs are computed in HBM
+ * (reference src/r1cs/prover.rs:589-619,650-697; src/r1cs/verifier.rs:468-501;
+ * src/inner_product_proof.rs:283-307).  Vectors marked "Montgomery" are n x 8 uint32
+ * little-endian limbs of x*2^256 mod l (the host mirror's in-memory form); pow tables hold
+ * base^(2^k), k < 32, in the same form. */
+typedef struct {
+  uint32_t y_inv_pow[32][8]; /* (y^-1)^(2^k), Montgomery                                        */
+  uint32_t u_sq[32][8];      /* u_j^2 in creation order (inner_product_proof.rs:288-292)         */
+  uint32_t allinv[8], x[8], a[8], b[8], u[8];
+  uint32_t c0[8], c1[8];     /* scalar of B = c0 + c1*delta (verifier.rs:527-529)               */
+  uint32_t lg_n, n, n1, N;   /* N = 2^lg_n padded size, n multipliers, n1 first-phase           */
+} bpg_verify_params;
+/* The verifier's mega-MSM (verifier.rs:516-547) with g_scalars, h_scalars and delta computed
+ * on the device.  Terms: [adhoc points | B | B_blinding | G[0..N) | H[0..N)]; the caller
+ * supplies the adhoc scalars and the B_blinding scalar (canonical bytes) and wL, wR, wO
+ * (Montgomery, n each).  out = compressed sum; accept iff it is the identity (32 zero bytes). */
+int bpg_r1cs_verify_msm(bpg_ctx* ctx, const bpg_table* gens, size_t g_base, size_t h_base, size_t b_id,
+                        const uint8_t* adhoc_points, const uint8_t* adhoc_scalars, size_t n_adhoc,
+                        const uint8_t bb_scalar[32], const void* wL, const void* wR, const void* wO,
+                        const bpg_verify_params* params, uint8_t out[32]);
+
+/* InnerProductProof::verify (src/inner_product_proof.rs:317-372): s_i from (allinv, u_j^2) by
+ * its closed form, g_i = a s_i G_factors[i], h_i = b s_{N-1-i} H_factors[i] on the device, then
+ * one MSM over [adhoc (Q, L_*, R_*; host scalars) | G[g_off..+N) | H[h_off..+N)].  Factors are
+ * canonical bytes or NULL (all ones). */
+typedef struct {
+  uint32_t u_sq[32][8]; /* Montgomery, creation order */
+  uint32_t allinv[8], a[8], b[8];
+  uint32_t lg_n, N;
+} bpg_ipp_verify_params;
+int bpg_ipp_verify_msm(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off,
+                       const uint8_t* adhoc_points, const uint8_t* adhoc_scalars, size_t n_adhoc,
+                       const uint8_t* G_factors, const uint8_t* H_factors, const bpg_ipp_verify_params* params,
+                       uint8_t out[32]);
+
+/* Prover side: witness rows, blinding vectors and flattened weights stay resident. */
+typedef struct bpg_r1cs_dev bpg_r1cs_dev;
+int bpg_r1cs_dev_new(bpg_ctx* ctx, size_t capacity, bpg_r1cs_dev** out);
+void bpg_r1cs_dev_free(bpg_r1cs_dev* st);
+/* grow to `capacity` rows keeping a_L, a_R, a_O, s_L, s_R (second-phase multipliers, prover.rs:501-530) */
+int bpg_r1cs_dev_reserve(bpg_r1cs_dev** st, size_t capacity);
+/* (A_I, A_O, S) of one phase over gens[first .. first+cnt) (prover.rs:465-494, 532-565):
+ * aL/aR/aO Montgomery rows, raw_sL/raw_sR the 64-byte uniform blocks the blinding scalars are
+ * reduced from (on the device), blind3 = i_blinding, o_blinding, s_blinding (canonical). */
+int bpg_r1cs_dev_commit(bpg_r1cs_dev* st, const bpg_table* gens, size_t g_base, size_t h_base, size_t bb_id,
+                        size_t first, size_t cnt, const void* aL, const void* aR, const void* aO, const void* raw_sL,
+                        const void* raw_sR, const uint8_t blind3[96], uint8_t out[96]);
+/* t_1..t_6 (util.rs:152-170); uploads and keeps wL, wR, wO.  t_out: six canonical scalars. */
+int bpg_r1cs_dev_poly_t(bpg_r1cs_dev* st, size_t n, const void* wL, const void* wR, const void* wO, const void* y_pow,
+                        const void* y_inv_pow, uint8_t t_out[192]);
+/* l(x), r(x) with padding and the G/H factors (prover.rs:650-697) computed in HBM, then the IPP
+ * state over the shared generator table with Q = q_mul * gens[q_id]. */
+int bpg_r1cs_dev_ipp_begin(bpg_r1cs_dev* st, const bpg_table* gens, size_t g_base, size_t h_base, size_t q_id,
+                           const uint8_t q_mul[32], size_t n, size_t n1, size_t N, const void* x_mont,
+                           const void* u_mont, const void* y_pow, const void* y_inv_pow, bpg_ipp** out);
+
 /* ==== host mirror of the reference's protocol layer ==================================
  * C bindings of the C++ host code in mpc_bulletproof_b200/csrc/host/: the transcript,
  * the generators as resident tables, InnerProductProof and the R1CS Prover/Verifier with

@@ -12,6 +12,7 @@
 
 #include "msm_kernels.cuh"
 #include "ipp_kernels.cuh"
+#include "svec_kernels.cuh"
 
 using namespace bpg;
 
@@ -928,34 +929,20 @@ extern "C" int bpg_msm_table_indexed(bpg_ctx* ctx, const bpg_table* table, const
 // ---------------------------------------------------------------------------
 // one MSM over ad-hoc (compressed) points followed by ranges of resident tables
 // ---------------------------------------------------------------------------
-extern "C" int bpg_msm_mixed(bpg_ctx* ctx, const uint8_t* adhoc_points, size_t n_adhoc,
-                             const bpg_table* const* tabs, const size_t* offs, const size_t* lens, int nsegs,
-                             const uint8_t* scalars_le, uint8_t out[32]) {
-  if (!ctx || !out || (n_adhoc && !adhoc_points) || nsegs < 0 || (nsegs && (!tabs || !offs || !lens))) return BPG_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  size_t total = n_adhoc;
-  for (int i = 0; i < nsegs; i++) {
-    if (!tabs[i]) return BPG_ERR_ARG;
-    if (offs[i] + lens[i] > tabs[i]->n) return BPG_ERR_CAPACITY;
-    total += lens[i];
-  }
-  if (total && !scalars_le) return BPG_ERR_ARG;
+// core of the mixed MSM: scalars for all `total` terms are already in d_scalars (device)
+static int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_adhoc, const bpg_table* const* tabs,
+                          const size_t* offs, const size_t* lens, int nsegs, const uint32_t* d_scalars, size_t total,
+                          uint8_t out[32]) {
   bpg_table* t = nullptr;
   int rc = table_alloc_plain(ctx, total, &t);
   if (rc) return rc;
   cudaStream_t s = ctx->stream;
   do {
-    rc = ensure_stage(ctx, std::max<size_t>(total * 32 + n_adhoc * 32, 64));
-    if (rc) break;
-    uint8_t* d_sc = ctx->d_stage;
-    uint8_t* d_pts = ctx->d_stage + total * 32;
     uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small + 1024);
     rc = BPG_ERR_CUDA;
     if (cudaMemsetAsync(bad, 0, 4, s) != cudaSuccess) break;
-    if (total && cudaMemcpyAsync(d_sc, scalars_le, total * 32, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
     if (n_adhoc) {
-      if (cudaMemcpyAsync(d_pts, adhoc_points, n_adhoc * 32, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
-      k_decode_to_niels<<<(unsigned)((n_adhoc + 127) / 128), 128, 0, s>>>(d_pts, (uint32_t)n_adhoc, t->niels, bad);
+      k_decode_to_niels<<<(unsigned)((n_adhoc + 127) / 128), 128, 0, s>>>(d_adhoc_points, (uint32_t)n_adhoc, t->niels, bad);
       ctx->launches++;
     }
     size_t pos = n_adhoc;
@@ -969,7 +956,7 @@ extern "C" int bpg_msm_mixed(bpg_ctx* ctx, const uint8_t* adhoc_points, size_t n
     if (!ok) break;
     uint32_t* d_ext = (uint32_t*)ctx->d_small;
     uint8_t* d_bytes = ctx->d_small + 128;
-    rc = msm_enqueue(ctx, t->niels, total, (const uint32_t*)d_sc, total, nullptr, nullptr, 1, d_ext);
+    rc = msm_enqueue(ctx, t->niels, total, d_scalars, total, nullptr, nullptr, 1, d_ext);
     if (rc) break;
     rc = bpg_dev_sum_encode(ctx, d_ext, 1, 1, d_bytes, nullptr);
     if (rc) break;
@@ -985,3 +972,32 @@ extern "C" int bpg_msm_mixed(bpg_ctx* ctx, const uint8_t* adhoc_points, size_t n
   bpg_table_free(t);
   return rc;
 }
+
+static int check_segs(const bpg_table* const* tabs, const size_t* offs, const size_t* lens, int nsegs, size_t* total) {
+  for (int i = 0; i < nsegs; i++) {
+    if (!tabs[i]) return BPG_ERR_ARG;
+    if (offs[i] + lens[i] > tabs[i]->n) return BPG_ERR_CAPACITY;
+    *total += lens[i];
+  }
+  return BPG_OK;
+}
+
+extern "C" int bpg_msm_mixed(bpg_ctx* ctx, const uint8_t* adhoc_points, size_t n_adhoc,
+                             const bpg_table* const* tabs, const size_t* offs, const size_t* lens, int nsegs,
+                             const uint8_t* scalars_le, uint8_t out[32]) {
+  if (!ctx || !out || (n_adhoc && !adhoc_points) || nsegs < 0 || (nsegs && (!tabs || !offs || !lens))) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  size_t total = n_adhoc;
+  int rc = check_segs(tabs, offs, lens, nsegs, &total);
+  if (rc) return rc;
+  if (total && !scalars_le) return BPG_ERR_ARG;
+  rc = ensure_stage(ctx, std::max<size_t>(total * 32 + n_adhoc * 32, 64));
+  if (rc) return rc;
+  uint8_t* d_sc = ctx->d_stage;
+  uint8_t* d_pts = ctx->d_stage + total * 32;
+  if (total) CK(cudaMemcpyAsync(d_sc, scalars_le, total * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_adhoc) CK(cudaMemcpyAsync(d_pts, adhoc_points, n_adhoc * 32, cudaMemcpyHostToDevice, ctx->stream));
+  return msm_mixed_core(ctx, d_pts, n_adhoc, tabs, offs, lens, nsegs, (const uint32_t*)d_sc, total, out);
+}
+
+#include "r1cs_dev.inc"

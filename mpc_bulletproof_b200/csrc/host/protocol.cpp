@@ -7,6 +7,7 @@
 // Everything group-valued is done by the device through include/bpgpu.h; what stays
 // here is what the reference also does serially on the CPU: the constraint-system
 // bookkeeping, the transcript, and O(n) scalar preparation.
+#include <algorithm>
 #include <array>
 #include <chrono>
 #include <cstdio>
@@ -196,9 +197,10 @@ struct InnerProductProof {
     return BPG_OK;
   }
 
-  // inner_product_proof.rs:254-310
-  int verification_scalars(size_t n, Transcript& tr, std::vector<Scalar>& u_sq, std::vector<Scalar>& u_inv_sq,
-                           std::vector<Scalar>& s) const {
+  // inner_product_proof.rs:254-298: transcript replay, challenges, batch inversion; the n-vector s
+  // (:300-307) is produced on the device from (allinv, u_sq) by its closed form
+  int verification_challenges(size_t n, Transcript& tr, std::vector<Scalar>& u_sq, std::vector<Scalar>& u_inv_sq,
+                              Scalar& allinv) const {
     size_t lg_n = L_vec.size();
     if (lg_n >= 32) return BPG_ERR_VERIFY;
     if (n != ((size_t)1 << lg_n)) return BPG_ERR_VERIFY;
@@ -210,7 +212,7 @@ struct InnerProductProof {
       ch[i] = tr.challenge_scalar("u");
     }
     // batch inversion (Scalar::batch_inverse): one inversion + 3 lg n multiplications
-    Scalar allinv = Scalar::one();
+    allinv = Scalar::one();
     if (lg_n) {
       std::vector<Scalar> pre(lg_n);
       Scalar acc = Scalar::one();
@@ -230,13 +232,6 @@ struct InnerProductProof {
     for (size_t i = 0; i < lg_n; i++) {
       u_sq[i] = ch[i] * ch[i];
       u_inv_sq[i] = ch_inv[i] * ch_inv[i];
-    }
-    s.resize(n);
-    s[0] = allinv;
-    for (size_t i = 1; i < n; i++) {
-      size_t lg_i = 63 - __builtin_clzll((unsigned long long)i);
-      size_t k = (size_t)1 << lg_i;
-      s[i] = s[i - k] * u_sq[(lg_n - 1) - lg_i];
     }
     return BPG_OK;
   }
@@ -270,45 +265,42 @@ extern "C" int bpg_ipp_verify(bpg_ctx* ctx, bpg_transcript* t, size_t n, const u
   InnerProductProof p;
   int rc = InnerProductProof::from_bytes(proof, proof_len, &p);
   if (rc) return rc;
-  std::vector<Scalar> u_sq, u_inv_sq, s;
-  rc = p.verification_scalars(n, t->t, u_sq, u_inv_sq, s);
+  std::vector<Scalar> u_sq, u_inv_sq;
+  Scalar allinv;
+  rc = p.verification_challenges(n, t->t, u_sq, u_inv_sq, allinv);
   if (rc) return rc;
+  if (G_factors || H_factors)  // canonical scalars only (Scalar::from_canonical_bytes at the Rust boundary)
+    for (size_t i = 0; i < n; i++) {
+      Scalar f;
+      if (G_factors && !Scalar::from_bytes(G_factors + 32 * i, &f)) return BPG_ERR_DECODE;
+      if (H_factors && !Scalar::from_bytes(H_factors + 32 * i, &f)) return BPG_ERR_DECODE;
+    }
   size_t lg_n = p.L_vec.size();
-  // scalars: [a*b | -u_sq | -u_inv_sq] for ad-hoc [Q | L | R], then G, H ranges
+  // ad-hoc terms [Q | L | R] with scalars [a*b | -u_sq | -u_inv_sq]; the 2n generator scalars
+  // a s_i g_i, b s_i^-1 h_i (:335-351) are produced on the device
   std::vector<Scalar> sc;
-  sc.reserve(1 + 2 * lg_n + 2 * n);
+  sc.reserve(1 + 2 * lg_n);
   sc.push_back(p.a * p.b);
   for (auto& x : u_sq) sc.push_back(-x);
   for (auto& x : u_inv_sq) sc.push_back(-x);
-  for (size_t i = 0; i < n; i++) {
-    Scalar g = p.a * s[i];
-    if (G_factors) {
-      Scalar f;
-      if (!Scalar::from_bytes(G_factors + 32 * i, &f)) return BPG_ERR_DECODE;
-      g = g * f;
-    }
-    sc.push_back(g);
-  }
-  for (size_t i = 0; i < n; i++) {
-    Scalar h = p.b * s[n - 1 - i];  // 1/s[i] is s[!i]
-    if (H_factors) {
-      Scalar f;
-      if (!Scalar::from_bytes(H_factors + 32 * i, &f)) return BPG_ERR_DECODE;
-      h = h * f;
-    }
-    sc.push_back(h);
-  }
   std::vector<uint8_t> pts((1 + 2 * lg_n) * 32);
   memcpy(pts.data(), Q, 32);
   for (size_t i = 0; i < lg_n; i++) {
     memcpy(pts.data() + 32 * (1 + i), p.L_vec[i].data(), 32);
     memcpy(pts.data() + 32 * (1 + lg_n + i), p.R_vec[i].data(), 32);
   }
-  const bpg_table* tabs[2] = {G, H};
-  size_t offs[2] = {g_off, h_off}, lens[2] = {n, n};
+  bpg_ipp_verify_params vp;
+  memset(&vp, 0, sizeof vp);
+  for (size_t j = 0; j < lg_n; j++) memcpy(vp.u_sq[j], u_sq[j].v, 32);
+  memcpy(vp.allinv, allinv.v, 32);
+  memcpy(vp.a, p.a.v, 32);
+  memcpy(vp.b, p.b.v, 32);
+  vp.lg_n = (uint32_t)lg_n;
+  vp.N = (uint32_t)n;
   uint8_t expect[32];
   std::vector<uint8_t> scb = sc_vec_bytes(sc);
-  rc = bpg_msm_mixed(ctx, pts.data(), 1 + 2 * lg_n, tabs, offs, lens, 2, scb.data(), expect);
+  rc = bpg_ipp_verify_msm(ctx, G, g_off, H, h_off, pts.data(), scb.data(), 1 + 2 * lg_n, G_factors, H_factors, &vp,
+                          expect);
   if (rc) return rc;
   return memcmp(expect, P, 32) == 0 ? BPG_OK : BPG_ERR_VERIFY;
 }
@@ -349,6 +341,12 @@ struct Xoshiro {
     s[2] ^= t;
     s[3] = rotl(s[3], 45);
     return result;
+  }
+  void fill(uint8_t* out, size_t len) {  // len % 8 == 0; the same stream scalar() consumes
+    for (size_t i = 0; i < len; i += 8) {
+      uint64_t x = next();
+      memcpy(out + i, &x, 8);
+    }
   }
   Scalar scalar() {
     uint8_t b[64];
@@ -706,32 +704,18 @@ struct R1CSProof {
 };
 
 // ---------------------------------------------------------------- Prover::prove (prover.rs:412-727)
-// one indexed-MSM launch for (A_I, A_O, S) over gens[first .. first+cnt)
-static int commit_AIOS(bpg_cs* cs, size_t first, size_t cnt, const Scalar& i_b, const Scalar& o_b, const Scalar& s_b,
-                       const Scalar* sL, const Scalar* sR, uint8_t out[96]) {
-  const bpg_gens* g = cs->gens;
-  size_t T = 5 * cnt + 3;
-  std::vector<uint32_t> pid(T);
-  std::vector<uint8_t> set(T), sc(T * 32);
-  size_t k = 0;
-  auto put = [&](uint32_t id, uint8_t s, const Scalar& x) {
-    pid[k] = id;
-    set[k] = s;
-    x.to_bytes(sc.data() + 32 * k);
-    k++;
-  };
-  put((uint32_t)g->bb_id(), 0, i_b);
-  put((uint32_t)g->bb_id(), 1, o_b);
-  put((uint32_t)g->bb_id(), 2, s_b);
-  for (size_t i = 0; i < cnt; i++) {
-    put((uint32_t)(g->g_base() + first + i), 0, cs->a_L[first + i]);
-    put((uint32_t)(g->h_base() + first + i), 0, cs->a_R[first + i]);
-    put((uint32_t)(g->g_base() + first + i), 1, cs->a_O[first + i]);
-    put((uint32_t)(g->g_base() + first + i), 2, sL[i]);
-    put((uint32_t)(g->h_base() + first + i), 2, sR[i]);
+// base^(2^k), k < 32, Montgomery limbs: lets a device thread form base^i in <= lg i products
+static void pow_table(const Scalar& base, uint32_t out[32][8]) {
+  Scalar b = base;
+  for (int k = 0; k < 32; k++) {
+    memcpy(out[k], b.v, 32);
+    b = b * b;
   }
-  return bpg_msm_table_indexed(cs->ctx, g->table, pid.data(), set.data(), sc.data(), T, 3, out);
 }
+struct DevGuard {  // frees the resident prover state on every exit path
+  bpg_r1cs_dev* p = nullptr;
+  ~DevGuard() { bpg_r1cs_dev_free(p); }
+};
 
 extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
   if (!cs || !cs->is_prover || !proof_out || !proof_len) return BPG_ERR_ARG;
@@ -743,13 +727,22 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   tr.append_u64("m", cs->v.size());  // :420
   size_t n1 = cs->a_L.size();
   if (g->cap < n1) return BPG_ERR_CAPACITY;  // :450-452
-  Scalar i_b1 = rng.scalar(), o_b1 = rng.scalar(), s_b1 = rng.scalar();  // :457-459
-  std::vector<Scalar> s_L(n1), s_R(n1);
-  for (auto& x : s_L) x = rng.scalar();
-  for (auto& x : s_R) x = rng.scalar();
-  uint8_t c3[96];
+  // Blinding draws in the reference's order (:457-462); the 2 n1 vector blindings stay as the
+  // 64-byte uniform blocks and are reduced mod l on the device.
+  Scalar i_b1 = rng.scalar(), o_b1 = rng.scalar(), s_b1 = rng.scalar();
+  std::vector<uint8_t> raw_sL(n1 * 64), raw_sR(n1 * 64);
+  rng.fill(raw_sL.data(), raw_sL.size());
+  rng.fill(raw_sR.data(), raw_sR.size());
+  DevGuard dv;
+  int rc = bpg_r1cs_dev_new(cs->ctx, next_pow2(std::max<size_t>(n1, 1)), &dv.p);
+  if (rc) return rc;
+  uint8_t c3[96], blind3[96];
   tm.lap("blindings s_L s_R");
-  int rc = commit_AIOS(cs, 0, n1, i_b1, o_b1, s_b1, s_L.data(), s_R.data(), c3);  // :465-494
+  i_b1.to_bytes(blind3);
+  o_b1.to_bytes(blind3 + 32);
+  s_b1.to_bytes(blind3 + 64);
+  rc = bpg_r1cs_dev_commit(dv.p, g->table, g->g_base(), g->h_base(), g->bb_id(), 0, n1, cs->a_L.data(), cs->a_R.data(),
+                           cs->a_O.data(), raw_sL.data(), raw_sR.data(), blind3, c3);  // :465-494
   if (rc) return rc;
   tm.lap("A_I1 A_O1 S1 msm");
   memcpy(proof.A_I1.data(), c3, 32);
@@ -760,20 +753,25 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   tr.append_point("S1", proof.S1.data());
   rc = cs->create_randomized_constraints();  // :501
   if (rc) return rc;
-  size_t n = cs->a_L.size(), n2 = n - n1, padded_n = next_pow2(n), pad = padded_n - n;
+  size_t n = cs->a_L.size(), n2 = n - n1, padded_n = next_pow2(n);
   if (g->cap < padded_n) return BPG_ERR_CAPACITY;  // :511-513
+  rc = bpg_r1cs_dev_reserve(&dv.p, padded_n);
+  if (rc) return rc;
   Scalar i_b2 = Scalar::zero(), o_b2 = Scalar::zero(), s_b2 = Scalar::zero();
   if (n2 > 0) {  // :519-530
     i_b2 = rng.scalar();
     o_b2 = rng.scalar();
     s_b2 = rng.scalar();
-  }
-  s_L.resize(n);
-  s_R.resize(n);
-  for (size_t i = n1; i < n; i++) s_L[i] = rng.scalar();
-  for (size_t i = n1; i < n; i++) s_R[i] = rng.scalar();
-  if (n2 > 0) {  // :532-565
-    rc = commit_AIOS(cs, n1, n2, i_b2, o_b2, s_b2, s_L.data() + n1, s_R.data() + n1, c3);
+    raw_sL.resize(n2 * 64);
+    raw_sR.resize(n2 * 64);
+    rng.fill(raw_sL.data(), raw_sL.size());
+    rng.fill(raw_sR.data(), raw_sR.size());
+    i_b2.to_bytes(blind3);
+    o_b2.to_bytes(blind3 + 32);
+    s_b2.to_bytes(blind3 + 64);
+    rc = bpg_r1cs_dev_commit(dv.p, g->table, g->g_base(), g->h_base(), g->bb_id(), n1, n2, cs->a_L.data() + n1,
+                             cs->a_R.data() + n1, cs->a_O.data() + n1, raw_sL.data(), raw_sR.data(), blind3,
+                             c3);  // :532-565
     if (rc) return rc;
     memcpy(proof.A_I2.data(), c3, 32);
     memcpy(proof.A_O2.data(), c3 + 32, 32);
@@ -792,39 +790,22 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   tm.lap("phase 2");
   cs->flattened_constraints(z, wL, wR, wO, wV, wc);
   tm.lap("flattened_constraints");
+  // l(X), r(X) coefficient vectors (:596-617) and t_1..t_6 (util.rs:152-170) in HBM
   Scalar y_inv = y.invert();
-  std::vector<Scalar> exp_y_inv(padded_n);
-  {
-    Scalar e = Scalar::one();
-    for (size_t i = 0; i < padded_n; i++) {
-      exp_y_inv[i] = e;
-      e *= y_inv;
-    }
-  }
-  std::vector<Scalar> l1(n), l2(n), l3(n), r0(n), r1(n), r3(n);
-  Scalar exp_y = Scalar::one();
-  for (size_t i = 0; i < n; i++) {  // :596-617
-    l1[i] = cs->a_L[i] + exp_y_inv[i] * wR[i];
-    l2[i] = cs->a_O[i];
-    l3[i] = s_L[i];
-    r0[i] = wO[i] - exp_y;
-    r1[i] = exp_y * cs->a_R[i] + wL[i];
-    r3[i] = exp_y * s_R[i];
-    exp_y *= y;
-  }
-  auto ip = [](const std::vector<Scalar>& a, const std::vector<Scalar>& b) {
-    Scalar t = Scalar::zero();
-    for (size_t i = 0; i < a.size(); i++) t += a[i] * b[i];
-    return t;
-  };
-  // util.rs:152-170
-  Scalar t1 = ip(l1, r0), t2 = ip(l1, r1) + ip(l2, r0), t3 = ip(l2, r1) + ip(l3, r0), t4 = ip(l1, r3) + ip(l3, r1),
-         t5 = ip(l2, r3), t6 = ip(l3, r3);
+  uint32_t y_pow[32][8], y_inv_pow[32][8];
+  pow_table(y, y_pow);
+  pow_table(y_inv, y_inv_pow);
+  uint8_t tbytes[192];
+  rc = bpg_r1cs_dev_poly_t(dv.p, n, wL.data(), wR.data(), wO.data(), y_pow, y_inv_pow, tbytes);
+  if (rc) return rc;
+  Scalar t[6];
+  for (int k = 0; k < 6; k++) Scalar::from_bytes(tbytes + 32 * k, &t[k]);
   tm.lap("l/r polys + t_i");
   Scalar tb1 = rng.scalar(), tb3 = rng.scalar(), tb4 = rng.scalar(), tb5 = rng.scalar(), tb6 = rng.scalar();  // :621-625
   {
     uint8_t vals[160], blinds[160], Ts[160];
-    t1.to_bytes(vals); t3.to_bytes(vals + 32); t4.to_bytes(vals + 64); t5.to_bytes(vals + 96); t6.to_bytes(vals + 128);
+    memcpy(vals, tbytes, 32);            // t_1
+    memcpy(vals + 32, tbytes + 64, 128);  // t_3 .. t_6
     tb1.to_bytes(blinds); tb3.to_bytes(blinds + 32); tb4.to_bytes(blinds + 64); tb5.to_bytes(blinds + 96);
     tb6.to_bytes(blinds + 128);
     rc = bpg_pedersen_commit(cs->ctx, g, vals, blinds, 5, Ts);  // :627-631
@@ -845,38 +826,24 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   for (size_t i = 0; i < wV.size(); i++) tb2 += wV[i] * cs->v_blinding[i];  // :644-648
   auto poly6 = [&](const Scalar& c1, const Scalar& c2, const Scalar& c3_, const Scalar& c4, const Scalar& c5,
                    const Scalar& c6) { return x * (c1 + x * (c2 + x * (c3_ + x * (c4 + x * (c5 + x * c6))))); };
-  proof.t_x = poly6(t1, t2, t3, t4, t5, t6);
+  proof.t_x = poly6(t[0], t[1], t[2], t[3], t[4], t[5]);
   proof.t_x_blinding = poly6(tb1, tb2, tb3, tb4, tb5, tb6);
-  std::vector<Scalar> l_vec(padded_n, Scalar::zero()), r_vec(padded_n, Scalar::zero());
-  for (size_t i = 0; i < n; i++) {  // util.rs:172-181 (l0 = r2 = 0)
-    l_vec[i] = x * (l1[i] + x * (l2[i] + x * l3[i]));
-    r_vec[i] = r0[i] + x * (r1[i] + x * (x * r3[i]));
-  }
-  for (size_t i = n; i < padded_n; i++) {  // :661-672
-    r_vec[i] = -exp_y;
-    exp_y *= y;
-  }
   Scalar i_b = i_b1 + u * i_b2, o_b = o_b1 + u * o_b2, s_b = s_b1 + u * s_b2;
   proof.e_blinding = x * (i_b + x * (o_b + x * s_b));
   tr.append_scalar("t_x", proof.t_x);
   tr.append_scalar("t_x_blinding", proof.t_x_blinding);
   tr.append_scalar("e_blinding", proof.e_blinding);
   Scalar w = tr.challenge_scalar("w");  // :686; Q = w*B is never materialised: its scalar rides on B
-  std::vector<Scalar> Gf(padded_n), Hf(padded_n);
-  for (size_t i = 0; i < padded_n; i++) {  // :689-697
-    Gf[i] = i < n1 ? Scalar::one() : u;
-    Hf[i] = exp_y_inv[i] * Gf[i];
-  }
-  tm.lap("T commits, l/r eval");
+  tm.lap("T commits");
   tr.innerproduct_domain_sep(padded_n);  // inner_product_proof.rs:72
   uint8_t wb[32];
   w.to_bytes(wb);
   bpg_ipp* st = nullptr;
-  std::vector<uint8_t> gfb = sc_vec_bytes(Gf), hfb = sc_vec_bytes(Hf), lb = sc_vec_bytes(l_vec), rb = sc_vec_bytes(r_vec);
-  rc = bpg_ipp_begin_shared(cs->ctx, g->table, g->g_base(), g->h_base(), g->b_id(), wb, padded_n, gfb.data(),
-                            hfb.data(), lb.data(), rb.data(), &st);
+  // l(x), r(x), the padding (:661-672) and the G/H factors (:689-697) are evaluated on the device
+  rc = bpg_r1cs_dev_ipp_begin(dv.p, g->table, g->g_base(), g->h_base(), g->b_id(), wb, n, n1, padded_n, x.v, u.v, y_pow,
+                              y_inv_pow, &st);
   if (rc) return rc;
-  tm.lap("ipp begin (H2D)");
+  tm.lap("l/r eval + ipp begin");
   rc = InnerProductProof::run_rounds(st, tr, &proof.ipp);
   bpg_ipp_free(st);
   if (rc) return rc;
@@ -903,8 +870,7 @@ extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_
   if (!tr.validate_and_append_point("S1", proof.S1.data())) return BPG_ERR_VERIFY;
   rc = cs->create_randomized_constraints();
   if (rc) return rc;
-  size_t n = cs->num_vars, n2 = n - n1, padded_n = next_pow2(n), pad = padded_n - n;
-  (void)n2;
+  size_t n = cs->num_vars, padded_n = next_pow2(n);
   if (g->cap < padded_n) return BPG_ERR_CAPACITY;
   tr.append_point("A_I2", proof.A_I2.data());
   tr.append_point("A_O2", proof.A_O2.data());
@@ -924,25 +890,13 @@ extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_
   Scalar wc;
   cs->flattened_constraints(z, wL, wR, wO, wV, wc);
   tm.lap("replay + flatten");
-  std::vector<Scalar> u_sq, u_inv_sq, s;
-  rc = proof.ipp.verification_scalars(padded_n, tr, u_sq, u_inv_sq, s);
+  std::vector<Scalar> u_sq, u_inv_sq;
+  Scalar allinv;
+  rc = proof.ipp.verification_challenges(padded_n, tr, u_sq, u_inv_sq, allinv);
   if (rc) return BPG_ERR_VERIFY;  // map_err(|_| VerificationError) :463
-  tm.lap("verification_scalars");
+  tm.lap("verification challenges");
   const Scalar &a = proof.ipp.a, &b = proof.ipp.b;
   Scalar y_inv = y.invert();
-  std::vector<Scalar> y_inv_vec(padded_n), yneg_wR(padded_n, Scalar::zero());
-  {
-    Scalar e = Scalar::one();
-    for (size_t i = 0; i < padded_n; i++) {
-      y_inv_vec[i] = e;
-      e *= y_inv;
-    }
-  }
-  Scalar delta = Scalar::zero();
-  for (size_t i = 0; i < n; i++) {
-    yneg_wR[i] = wR[i] * y_inv_vec[i];
-    delta += yneg_wR[i] * wL[i];  // :479
-  }
   Scalar r = tr.challenge_scalar("r");  // :506
   Scalar xx = x * x, rxx = r * xx, xxx = x * xx;
   size_t lg_n = proof.ipp.L_vec.size(), m = cs->V.size();
@@ -950,7 +904,7 @@ extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_
   size_t n_adhoc = 6 + m + 5 + 2 * lg_n;
   std::vector<uint8_t> pts(n_adhoc * 32);
   std::vector<Scalar> sc;
-  sc.reserve(n_adhoc + 2 + 2 * padded_n);
+  sc.reserve(n_adhoc);
   uint8_t* pp = pts.data();
   auto putp = [&](const uint8_t* p, const Scalar& k) {
     memcpy(pp, p, 32);
@@ -971,26 +925,31 @@ extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_
   putp(proof.T_6.data(), rxx * xx * xx);
   for (size_t j = 0; j < lg_n; j++) putp(proof.ipp.L_vec[j].data(), u_sq[j]);
   for (size_t j = 0; j < lg_n; j++) putp(proof.ipp.R_vec[j].data(), u_inv_sq[j]);
-  // table ranges: [B, B_blinding], G[0..N), H[0..N)
-  sc.push_back(w * (proof.t_x - a * b) + r * (xx * (wc + delta) - proof.t_x));  // B
-  sc.push_back(-proof.e_blinding - r * proof.t_x_blinding);                     // B_blinding
-  for (size_t i = 0; i < padded_n; i++) {  // g_scalars :487-491
-    Scalar U = i < n1 ? Scalar::one() : u;
-    sc.push_back(U * (x * yneg_wR[i] - a * s[i]));
-  }
-  for (size_t i = 0; i < padded_n; i++) {  // h_scalars :493-501
-    Scalar U = i < n1 ? Scalar::one() : u;
-    Scalar wLi = i < n ? wL[i] : Scalar::zero(), wOi = i < n ? wO[i] : Scalar::zero();
-    sc.push_back(U * (y_inv_vec[i] * (x * wLi + wOi - b * s[padded_n - 1 - i]) - Scalar::one()));
-  }
-  (void)pad;
-  const bpg_table* tabs[3] = {g->table, g->table, g->table};
-  size_t offs[3] = {g->b_id(), g->g_base(), g->h_base()}, lens[3] = {2, padded_n, padded_n};
-  uint8_t mega[32];
+  // y^-i, s, delta = <y^-n o w_R, w_L> (:468-479), g_scalars (:487-491), h_scalars (:493-501) and the
+  // scalar of B = w (t_x - a b) + r (x^2 (w_c + delta) - t_x) = c0 + c1 delta (:527-529): device
+  bpg_verify_params vp;
+  memset(&vp, 0, sizeof vp);
+  pow_table(y_inv, vp.y_inv_pow);
+  for (size_t j = 0; j < lg_n; j++) memcpy(vp.u_sq[j], u_sq[j].v, 32);
+  Scalar c0 = w * (proof.t_x - a * b) + r * (xx * wc - proof.t_x), c1 = rxx;
+  memcpy(vp.allinv, allinv.v, 32);
+  memcpy(vp.x, x.v, 32);
+  memcpy(vp.a, a.v, 32);
+  memcpy(vp.b, b.v, 32);
+  memcpy(vp.u, u.v, 32);
+  memcpy(vp.c0, c0.v, 32);
+  memcpy(vp.c1, c1.v, 32);
+  vp.lg_n = (uint32_t)lg_n;
+  vp.n = (uint32_t)n;
+  vp.n1 = (uint32_t)n1;
+  vp.N = (uint32_t)padded_n;
+  uint8_t bb_scalar[32], mega[32];
+  (-proof.e_blinding - r * proof.t_x_blinding).to_bytes(bb_scalar);  // B_blinding
   std::vector<uint8_t> scb = sc_vec_bytes(sc);
-  tm.lap("g/h scalars");
-  rc = bpg_msm_mixed(cs->ctx, pts.data(), n_adhoc, tabs, offs, lens, 3, scb.data(), mega);
-  tm.lap("mega msm");
+  tm.lap("adhoc scalars");
+  rc = bpg_r1cs_verify_msm(cs->ctx, g->table, g->g_base(), g->h_base(), g->b_id(), pts.data(), scb.data(), n_adhoc,
+                           bb_scalar, wL.data(), wR.data(), wO.data(), &vp, mega);
+  tm.lap("g/h scalars + mega msm");
   if (rc == BPG_ERR_DECODE) return BPG_ERR_DECODE;  // a proof point that is not a valid encoding: FormatError
   if (rc) return rc;
   return is_identity_enc(mega) ? BPG_OK : BPG_ERR_VERIFY;  // :549
