@@ -54,6 +54,8 @@ int bpg_last_cuda_error(const bpg_ctx* ctx);
 uint64_t bpg_launch_count(const bpg_ctx* ctx);
 /* force the Pippenger window width (0 = choose from the size); for tuning/tests */
 int bpg_set_window(bpg_ctx* ctx, int c);
+/* tuning/test hook: bucket groups per set on windowed tables (0 = chosen from the launch size) */
+int bpg_set_groups(bpg_ctx* ctx, int gsub);
 
 /* ---- per-phase device timing --------------------------------------------------------
  * When enabled, CUDA events are recorded on the launch stream around each kernel

@@ -83,6 +83,7 @@ _SIGNATURES = {
     "bpg_last_cuda_error": (_I, [_P]),
     "bpg_launch_count": (ctypes.c_uint64, [_P]),
     "bpg_set_window": (_I, [_P, _I]),
+    "bpg_set_groups": (_I, [_P, _I]),
     "bpg_table_upload": (_I, [_P, _P, _SZ, ctypes.POINTER(_P)]),
     "bpg_table_upload_dev": (_I, [_P, _P, _SZ, ctypes.POINTER(_P)]),
     "bpg_table_len": (_SZ, [_P]),

@@ -60,6 +60,9 @@ class Context:
     def set_window(self, c: int):
         check(lib().bpg_set_window(self._h, c))
 
+    def set_groups(self, gsub: int):
+        check(lib().bpg_set_groups(self._h, gsub))
+
     @property
     def launches(self) -> int:
         return int(lib().bpg_launch_count(self._h))

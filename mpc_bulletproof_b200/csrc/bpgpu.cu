@@ -26,6 +26,7 @@ struct bpg_ctx {
   int last_cuda = 0;
   uint64_t launches = 0;
   int forced_c = 0;
+  int forced_gsub = 0;  // BPG_MSM_GSUB: bucket groups per set on windowed tables (tuning)
   int sm_count = 148;
   // per-phase device timing (bpg_profile_*): events are recorded on the launch stream
   bool prof = false;
@@ -96,6 +97,8 @@ extern "C" int bpg_init(int device, bpg_ctx** out) {
   ctx->stream = ctx->own_stream;
   const char* env = getenv("BPG_MSM_C");
   if (env) ctx->forced_c = atoi(env);
+  env = getenv("BPG_MSM_GSUB");
+  if (env) ctx->forced_gsub = atoi(env);
   *out = ctx;
   return BPG_OK;
 }
@@ -180,6 +183,12 @@ extern "C" uint64_t bpg_launch_count(const bpg_ctx* ctx) { return ctx ? ctx->lau
 extern "C" int bpg_set_window(bpg_ctx* ctx, int c) {
   if (!ctx || c < 0 || c > 24) return BPG_ERR_ARG;
   ctx->forced_c = c;
+  return BPG_OK;
+}
+
+extern "C" int bpg_set_groups(bpg_ctx* ctx, int gsub) {
+  if (!ctx || gsub < 0 || gsub > 128) return BPG_ERR_ARG;
+  ctx->forced_gsub = gsub;
   return BPG_OK;
 }
 
@@ -295,6 +304,7 @@ extern "C" void bpg_table_free(bpg_table* t) {
 // ---------------------------------------------------------------------------
 // MSM launch
 // ---------------------------------------------------------------------------
+// Plain tables: every window has its own bucket array, reduced separately, then Horner.
 static int pick_window(size_t n_per_set, int forced) {
   if (forced >= 2) return forced;
   double best = 1e300;
@@ -302,9 +312,35 @@ static int pick_window(size_t n_per_set, int forced) {
   for (int c = 3; c <= 20; c++) {
     int W = (255 + c - 1) / c;
     double nb = (double)(1u << (c - 1));
-    // mixed adds (7M) for the terms, two full adds (9M) per bucket in the reduction,
-    // c doublings per window on the serial tail (charged as if 64 lanes idle)
-    double cost = W * ((double)n_per_set * 7.0 + nb * 18.0);
+    // mixed adds (7M) for the terms, ~20M per bucket in the reduction tree
+    double cost = W * ((double)n_per_set * 7.0 + nb * 20.0);
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  return best_c;
+}
+// Windowed tables: all windows share one bucket array per set.  Lists of ~32 entries keep the
+// accumulation efficient; shorter lists only add merge work.
+static uint32_t pick_gsub(size_t n_per_set, int nsets, int c, int W) {
+  double nb = (double)(1u << (c - 1));
+  double lists_for_len = (double)n_per_set * W / (nb * 32.0);       // groups that make the lists ~32 long
+  double lists_for_par = (double)(1u << 18) / (nb * (double)nsets);  // groups that give ~2^18 lists
+  double avg1 = (double)n_per_set * W / nb;                          // list length with one group
+  double g = std::max(lists_for_len, std::min(lists_for_par, avg1 / 8.0));  // never below ~8 entries per list
+  uint32_t gs = (uint32_t)(g + 0.5);
+  return std::min<uint32_t>(std::max<uint32_t>(gs, 1), (uint32_t)W);
+}
+static int pick_window_table(size_t n, int forced) {
+  if (forced >= 2) return forced;
+  double best = 1e300;
+  int best_c = 4;
+  for (int c = 3; c <= 20; c++) {
+    int W = (255 + c - 1) / c;
+    double nb = (double)(1u << (c - 1));
+    uint32_t gs = pick_gsub(n, 1, c, W);
+    double cost = (double)W * n * 7.0 + (gs > 1 ? gs * nb * 8.0 : 0.0) + nb * 20.0;
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -313,7 +349,7 @@ static int pick_window(size_t n_per_set, int forced) {
   return best_c;
 }
 
-static void make_cfg(MsmCfg& cfg, size_t n_terms, size_t n_points, int nsets, int c, size_t win_stride = 0) {
+static void make_cfg(MsmCfg& cfg, size_t n_terms, size_t n_points, int nsets, int c, size_t win_stride, int forced_gsub) {
   cfg.win_stride = (uint32_t)win_stride;
   cfg.c = c;
   cfg.W = (255 + c - 1) / c;
@@ -321,13 +357,19 @@ static void make_cfg(MsmCfg& cfg, size_t n_terms, size_t n_points, int nsets, in
   cfg.nsets = nsets;
   cfg.n_terms = (uint32_t)n_terms;
   cfg.n_points = (uint32_t)std::max<size_t>(n_points, 1);
-  cfg.nwin = (uint32_t)nsets * cfg.W;
-  cfg.B = cfg.nwin * cfg.nb;
-  cfg.chunk = std::min<uint32_t>(cfg.nb, 32);
-  cfg.nchunks = cfg.nb / cfg.chunk;
+  if (win_stride) {
+    cfg.gsub = forced_gsub > 0 ? std::min<uint32_t>((uint32_t)forced_gsub, (uint32_t)cfg.W)
+                               : pick_gsub((n_terms + nsets - 1) / nsets, nsets, c, cfg.W);
+  } else {
+    cfg.gsub = (uint32_t)cfg.W;
+  }
+  cfg.narr = (uint32_t)nsets * cfg.gsub;
+  cfg.B = cfg.narr * cfg.nb;
   double avg = (double)n_terms * cfg.W / (double)cfg.B;
   cfg.big_thresh = (uint32_t)std::max(256.0, 16.0 * avg);
-  cfg.big_cap = (uint32_t)std::min<uint64_t>(cfg.B, (uint64_t)n_terms * cfg.W / cfg.big_thresh + 1);
+  // segments of over-long buckets: at most one per big bucket plus one per BIG_SEG entries
+  cfg.big_cap = (uint32_t)(std::min<uint64_t>(cfg.B, (uint64_t)n_terms * cfg.W / cfg.big_thresh + 1) +
+                           (uint64_t)n_terms * cfg.W / BIG_SEG + 1);
   memset(&cfg.bias, 0, sizeof(cfg.bias));
   for (int w = 0; w < cfg.W; w++) {
     int bit = c * w + c - 1;
@@ -356,19 +398,26 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   if (n_terms >= (1u << 31)) return BPG_ERR_ARG;
   MsmCfg cfg;
   int c = win_c ? win_c : pick_window((n_terms + nsets - 1) / nsets, ctx->forced_c);
-  make_cfg(cfg, n_terms, n_points, nsets, c, win_c ? win_stride : 0);
-  if ((uint64_t)cfg.nwin * cfg.nb >= (1ull << 31)) return BPG_ERR_ARG;
+  make_cfg(cfg, n_terms, n_points, nsets, c, win_c ? win_stride : 0, ctx->forced_gsub);
+  if ((uint64_t)cfg.narr * cfg.nb >= (1ull << 31)) return BPG_ERR_ARG;
+  const bool windowed = cfg.win_stride != 0;
 
+  // reduction geometry: `rarr` arrays of nb buckets; a leaf block takes RT_QUADS chunks of LC buckets
+  uint32_t rarr = windowed ? (uint32_t)nsets : cfg.narr;
+  const uint32_t LC = cfg.nb > (1u << 16) ? 8 : 4;
+  uint32_t tiles0 = (cfg.nb + RT_QUADS * LC - 1) / (RT_QUADS * LC);
   size_t ntiles = (cfg.B + SCAN_TILE - 1) / SCAN_TILE;
   size_t off = 0;
   size_t o_counts = off;  off += align_up((size_t)cfg.B * 4);
   size_t o_offsets = off; off += align_up(((size_t)cfg.B + 1) * 4);
   size_t o_tiles = off;   off += align_up(ntiles * 4);
-  size_t o_big = off;     off += align_up(((size_t)cfg.big_cap + 1) * 4);
+  size_t o_big = off;     off += align_up((3 * (size_t)cfg.big_cap + 1) * 4);
+  size_t o_bigpart = off; off += align_up((size_t)cfg.big_cap * 128);
   size_t o_entries = off; off += align_up((size_t)n_terms * cfg.W * 4);
   size_t o_buckets = off; off += align_up((size_t)cfg.B * 128);
-  size_t o_chunks = off;  off += align_up((size_t)cfg.nwin * cfg.nchunks * 128);
-  size_t o_wins = off;    off += align_up((size_t)cfg.nwin * 128);
+  size_t o_merged = off;  off += (windowed && cfg.gsub > 1) ? align_up((size_t)nsets * cfg.nb * 128) : 0;
+  size_t o_pairs = off;   off += 4 * align_up((size_t)rarr * tiles0 * 128);  // (A, Y) x ping-pong
+  size_t o_wins = off;    off += align_up((size_t)rarr * 128);
   size_t o_order = off;   off += align_up((size_t)cfg.B * 4);
   size_t o_bins = off;    off += align_up(SIZE_BINS * 4);
   int rc = ensure_ws(ctx, off);
@@ -378,9 +427,12 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   uint32_t* tiles = (uint32_t*)(ctx->ws + o_tiles);
   uint32_t* big_count = (uint32_t*)(ctx->ws + o_big);
   uint32_t* big_list = big_count + 1;
+  uint32_t* big_part = (uint32_t*)(ctx->ws + o_bigpart);
   uint32_t* entries = (uint32_t*)(ctx->ws + o_entries);
   uint32_t* buckets = (uint32_t*)(ctx->ws + o_buckets);
-  uint32_t* chunks = (uint32_t*)(ctx->ws + o_chunks);
+  uint32_t* merged = (uint32_t*)(ctx->ws + o_merged);
+  size_t pair_words = align_up((size_t)rarr * tiles0 * 128) / 4;
+  uint32_t* pairs = (uint32_t*)(ctx->ws + o_pairs);
   uint32_t* wins = (uint32_t*)(ctx->ws + o_wins);
   uint32_t* order = (uint32_t*)(ctx->ws + o_order);
   uint32_t* bins = (uint32_t*)(ctx->ws + o_bins);
@@ -415,19 +467,45 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
                                                                            buckets, big_count, big_list);
   LAUNCH_CHECK();
   prof_mark(ctx, BPG_PROF_ACCUM_BIG);
-  unsigned gbig = std::min<unsigned>(cfg.big_cap, (unsigned)ctx->sm_count * 2);
-  k_accum_big<<<gbig, BIG_THREADS, 0, st>>>(table_base, offsets, entries, cfg, buckets, big_count, big_list);
+  unsigned gbig = std::min<unsigned>(cfg.big_cap, (unsigned)ctx->sm_count * 4);
+  k_accum_big<<<gbig, BIG_THREADS, 0, st>>>(table_base, offsets, entries, cfg, buckets, big_count, big_list, big_part);
   LAUNCH_CHECK();
+  k_accum_big_fin<<<gbig, BIG_THREADS, 0, st>>>(cfg, buckets, big_count, big_list, big_part);
+  LAUNCH_CHECK();
+  const uint32_t* level0 = buckets;
+  if (windowed && cfg.gsub > 1) {
+    prof_mark(ctx, BPG_PROF_COMBINE);
+    unsigned nq = (unsigned)nsets * cfg.nb;
+    k_merge<<<(nq * 4 + MERGE_THREADS - 1) / MERGE_THREADS, MERGE_THREADS, 0, st>>>(buckets, cfg, merged);
+    LAUNCH_CHECK();
+    level0 = merged;
+  }
   prof_mark(ctx, BPG_PROF_REDUCE);
-  unsigned nred = cfg.nwin * cfg.nchunks;
-  k_reduce<<<(nred * 4 + RED_THREADS - 1) / RED_THREADS, RED_THREADS, 0, st>>>(buckets, cfg, chunks);
-  LAUNCH_CHECK();
-  prof_mark(ctx, BPG_PROF_COMBINE);
-  k_combine<<<cfg.nwin, COMB_THREADS, 0, st>>>(chunks, cfg, wins);
-  LAUNCH_CHECK();
-  prof_mark(ctx, BPG_PROF_HORNER);
-  k_horner<<<nsets, 32, 0, st>>>(wins, cfg, d_out_ext);
-  LAUNCH_CHECK();
+  {
+    uint32_t* final_out = windowed ? d_out_ext : wins;
+    uint32_t t = tiles0;
+    uint32_t* pa[2] = {pairs, pairs + 2 * pair_words};
+    int cur = 0;
+    uint32_t* oa = t == 1 ? final_out : pa[cur];
+    if (LC == 8) k_reduce_leaf<8><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
+    else k_reduce_leaf<4><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
+    LAUNCH_CHECK();
+    while (t > 1) {
+      uint32_t n = t;
+      t = (n + RP_THREADS / 4 - 1) / (RP_THREADS / 4);
+      const uint32_t* ia = pa[cur];
+      const uint32_t* iy = pa[cur] + pair_words;
+      cur ^= 1;
+      oa = t == 1 ? final_out : pa[cur];
+      k_reduce_pairs<<<rarr * t, RP_THREADS, 0, st>>>(ia, iy, n, t, oa, pa[cur] + pair_words);
+      LAUNCH_CHECK();
+    }
+  }
+  if (!windowed) {
+    prof_mark(ctx, BPG_PROF_HORNER);
+    k_horner<<<nsets, 32, 0, st>>>(wins, cfg, d_out_ext);
+    LAUNCH_CHECK();
+  }
   prof_mark(ctx, -1);
   return BPG_OK;
 }
@@ -593,7 +671,7 @@ extern "C" int bpg_table_set_windows(bpg_ctx* ctx, bpg_table* t, int c) {
   if (!ctx || !t || c < 0 || c > 20) return BPG_ERR_ARG;
   if (t->win_c) return BPG_ERR_ARG;  // already windowed
   CK(cudaSetDevice(ctx->device));
-  if (c == 0) c = pick_window(t->n, ctx->forced_c);
+  if (c == 0) c = pick_window_table(t->n, ctx->forced_c);
   if (c < 2) c = 2;
   int W = (255 + c - 1) / c;
   if ((uint64_t)W * t->n >= (1ull << 31)) return BPG_ERR_ARG;

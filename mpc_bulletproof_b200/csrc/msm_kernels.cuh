@@ -12,9 +12,13 @@
 //   k_scatter   counting-sort of (bucket -> point index | sign) entries
 //   k_accum     one thread per bucket: 7-mul mixed additions from the Niels table
 //   k_accum_big block-cooperative path for over-long buckets (structured scalars)
-//   k_reduce    chunked running sums: sum_j j*B_j per (window, chunk)
-//   k_combine   tree over chunks -> one point per window
-//   k_horner    sum_w 2^(c w) S_w per set -> extended point (the partial sum a rank owns)
+//   k_merge     windowed tables: the sub-bucket groups of a bucket -> one sum per (set, bucket)
+//   k_reduce_tree  radix-8 hierarchy of running sums: sum_j (j+1) B_j per bucket array
+//   k_horner    plain tables: sum_w 2^(c w) S_w per set -> extended point (the partial sum a rank owns)
+// A windowed table holds 2^(c w) P_i for every window, so all windows of a set feed ONE
+// array of 2^(c-1) buckets: no doublings, no per-window reduction, no Horner.  The entries
+// of a bucket are split into `gsub` groups (by window index) only to give the accumulation
+// enough independent lists.
 // All arithmetic is exact modular integer work; results are group elements, so
 // any evaluation order gives the same canonical encoding.
 #pragma once
@@ -31,10 +35,9 @@ struct MsmCfg {
   int nsets;          // independent sums in this launch
   uint32_t n_terms;   // scalars in this launch
   uint32_t n_points;  // implicit indexing: term t -> point t % n_points, set t / n_points
-  uint32_t nwin;      // nsets * W
-  uint32_t B;         // nwin * nb
-  uint32_t chunk;     // buckets per reduce chunk (power of two, <= nb)
-  uint32_t nchunks;   // nb / chunk
+  uint32_t gsub;      // bucket groups per set: window w accumulates into group w % gsub (plain tables: gsub = W)
+  uint32_t narr;      // nsets * gsub bucket arrays of nb buckets
+  uint32_t B;         // narr * nb
   uint32_t big_thresh;  // buckets longer than this go to k_accum_big
   uint32_t big_cap;     // capacity of the big-bucket list
   uint32_t win_stride;  // 0: plain table.  >0: table holds 2^(c w) P_i at index w*win_stride + i
@@ -55,13 +58,15 @@ __global__ void __launch_bounds__(256) k_hist(const uint32_t* __restrict__ scala
   sc_load(k, scalars + (size_t)t * 8);
   sc_recoded r = sc_recode(k.v, cfg.bias);
   uint32_t set = set_ids ? set_ids[t] : t / cfg.n_points;
-  uint32_t base = set * cfg.W * cfg.nb;
+  uint32_t base = set * cfg.gsub * cfg.nb;
+  uint32_t g = 0;
   for (int w = 0; w < cfg.W; w++) {
     int d = sc_digit(r, w, cfg.c);
     if (d != 0) {
       uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      atomicAdd(&counts[base + (uint32_t)w * cfg.nb + mag - 1], 1u);
+      atomicAdd(&counts[base + g * cfg.nb + mag - 1], 1u);
     }
+    g = g + 1 == cfg.gsub ? 0 : g + 1;
   }
 }
 
@@ -177,15 +182,17 @@ __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ sc
   sc_recoded r = sc_recode(k.v, cfg.bias);
   uint32_t set = set_ids ? set_ids[t] : t / cfg.n_points;
   uint32_t pid = point_ids ? point_ids[t] : t % cfg.n_points;
-  uint32_t base = set * cfg.W * cfg.nb;
+  uint32_t base = set * cfg.gsub * cfg.nb;
+  uint32_t g = 0;
   for (int w = 0; w < cfg.W; w++) {
     int d = sc_digit(r, w, cfg.c);
     if (d != 0) {
       uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      uint32_t b = base + (uint32_t)w * cfg.nb + mag - 1;
+      uint32_t b = base + g * cfg.nb + mag - 1;
       uint32_t pos = offsets[b] + atomicAdd(&cursors[b], 1u);
       entries[pos] = (pid + (uint32_t)w * cfg.win_stride) | (d < 0 ? ENTRY_NEG : 0u);
     }
+    g = g + 1 == cfg.gsub ? 0 : g + 1;
   }
 }
 
@@ -193,6 +200,7 @@ __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ sc
 // bucket accumulation: one thread per bucket
 // ---------------------------------------------------------------------------
 constexpr int ACC_THREADS = 128;
+constexpr uint32_t BIG_SEG = 2048;  // entries of an over-long bucket handled by one block of k_accum_big
 
 // bucket sums are parked in the "cached" operand layout of ge4_add_cached:
 // [Y-X | Y+X | 2Z | 2dT], so that the reduction's first addition needs no conversion
@@ -312,8 +320,14 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accum(const uint32_t* __restric
   uint32_t b = order[t];
   uint32_t beg = offsets[b], end = offsets[b + 1];
   if (end - beg > cfg.big_thresh) {
-    uint32_t slot = atomicAdd(big_count, 1u);
-    if (slot < cfg.big_cap) big_list[slot] = b;
+    // over-long bucket: hand it to k_accum_big in segments of BIG_SEG entries
+    uint32_t nseg = (end - beg + BIG_SEG - 1) / BIG_SEG;
+    uint32_t slot = atomicAdd(big_count, nseg);
+    for (uint32_t j = 0; j < nseg && slot + j < cfg.big_cap; j++) {
+      big_list[3 * (size_t)(slot + j)] = b;
+      big_list[3 * (size_t)(slot + j) + 1] = j;
+      big_list[3 * (size_t)(slot + j) + 2] = nseg;
+    }
     return;
   }
   ge_ext acc = ge_identity();
@@ -334,20 +348,23 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accum(const uint32_t* __restric
   ge_store_cached(bucket_sums + (size_t)b * 32, acc);
 }
 
-// over-long buckets: one block per bucket, strided accumulation, then a quad-cooperative block sum
+// over-long buckets (structured scalars: bit vectors, the nearly empty top window): one block per
+// segment of BIG_SEG entries, strided accumulation, then a quad-cooperative block sum.  A bucket
+// of one segment is finished here; longer ones leave per-segment partial sums for k_accum_big_fin.
 constexpr int BIG_THREADS = 256;
 __global__ void __launch_bounds__(BIG_THREADS) k_accum_big(const uint32_t* __restrict__ table,
                                                             const uint32_t* __restrict__ offsets,
                                                             const uint32_t* __restrict__ entries, MsmCfg cfg,
                                                             uint32_t* __restrict__ bucket_sums,
                                                             const uint32_t* __restrict__ big_count,
-                                                            const uint32_t* __restrict__ big_list) {
+                                                            const uint32_t* __restrict__ big_list,
+                                                            uint32_t* __restrict__ big_part /*[big_cap][32] ext*/) {
   __shared__ uint32_t pts[BIG_THREADS][32];
   __shared__ uint32_t sm[BIG_THREADS / 32][32];
   uint32_t nbig = min(*big_count, cfg.big_cap);
   for (uint32_t k = blockIdx.x; k < nbig; k += gridDim.x) {
-    uint32_t b = big_list[k];
-    uint32_t beg = offsets[b], end = offsets[b + 1];
+    uint32_t b = big_list[3 * (size_t)k], j = big_list[3 * (size_t)k + 1], nseg = big_list[3 * (size_t)k + 2];
+    uint32_t beg = offsets[b] + j * BIG_SEG, end = min(offsets[b + 1], beg + BIG_SEG);
     ge_ext acc = ge_identity();
     for (uint32_t i = beg + threadIdx.x; i < end; i += BIG_THREADS) {
       uint32_t e = __ldg(entries + i);
@@ -361,92 +378,191 @@ __global__ void __launch_bounds__(BIG_THREADS) k_accum_big(const uint32_t* __res
     int g = threadIdx.x >> 2;
     ge4 t = ge4_load(pts[4 * g]);
 #pragma unroll
-    for (int j = 1; j < 4; j++) t = ge4_add(t, ge4_load(pts[4 * g + j]));
+    for (int jj = 1; jj < 4; jj++) t = ge4_add(t, ge4_load(pts[4 * g + jj]));
     t = block_sum_quads(t, sm);
-    ge4 c = ge4_to_cached(t);  // park in cached layout like k_accum (all lanes: it shuffles)
+    if (nseg == 1) {
+      ge4 c = ge4_to_cached(t);  // park in cached layout like k_accum (all lanes: it shuffles)
+      if (threadIdx.x < 4) ge4_store(bucket_sums + (size_t)b * 32, c);
+    } else {
+      if (threadIdx.x < 4) ge4_store(big_part + (size_t)k * 32, t);
+    }
+    __syncthreads();
+  }
+}
+// buckets of several segments: the block that owns segment 0 sums the partials
+__global__ void __launch_bounds__(BIG_THREADS) k_accum_big_fin(MsmCfg cfg, uint32_t* __restrict__ bucket_sums,
+                                                                const uint32_t* __restrict__ big_count,
+                                                                const uint32_t* __restrict__ big_list,
+                                                                const uint32_t* __restrict__ big_part) {
+  __shared__ uint32_t sm[BIG_THREADS / 32][32];
+  uint32_t nbig = min(*big_count, cfg.big_cap);
+  for (uint32_t k = blockIdx.x; k < nbig; k += gridDim.x) {
+    uint32_t b = big_list[3 * (size_t)k], j = big_list[3 * (size_t)k + 1], nseg = big_list[3 * (size_t)k + 2];
+    if (j != 0 || nseg == 1) continue;  // block-uniform
+    uint32_t quad = threadIdx.x >> 2;
+    ge4 t = ge4_identity();
+    for (uint32_t base = 0; base < nseg; base += BIG_THREADS / 4) {
+      uint32_t i = base + quad;
+      bool have = i < nseg;
+      ge4 o = ge4_load(big_part + (size_t)(k + (have ? i : 0)) * 32);
+      o.c = fe_sel(have, o.c, ge4_identity().c);
+      t = ge4_add(t, o);
+    }
+    t = block_sum_quads(t, sm);
+    ge4 c = ge4_to_cached(t);
     if (threadIdx.x < 4) ge4_store(bucket_sums + (size_t)b * 32, c);
     __syncthreads();
   }
 }
 
 // ---------------------------------------------------------------------------
-// bucket reduction: per (window, chunk) compute sum_j (q*chunk + j + 1) * B_j.
-// One QUAD per chunk (ge4.cuh): running sums cost 2 + 3 multiplication levels per bucket.
+// windowed tables: merged[set][b] = sum_g bucket_sums[set][g][b].  One quad per (set, bucket);
+// operands and result in the cached layout.
 // ---------------------------------------------------------------------------
-constexpr int RED_THREADS = 128;
-__global__ void __launch_bounds__(RED_THREADS) k_reduce(const uint32_t* __restrict__ bucket_sums, MsmCfg cfg,
-                                                         uint32_t* __restrict__ chunk_sums) {
-  uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-  uint32_t total = cfg.nwin * cfg.nchunks;
-  bool live = g < total;
-  uint32_t gg = live ? g : total - 1;  // idle quads shadow the last chunk: shuffles need every lane
-  uint32_t win = gg / cfg.nchunks, q = gg % cfg.nchunks;
-  const uint32_t* src = bucket_sums + ((size_t)win * cfg.nb + (size_t)q * cfg.chunk) * 32;
+constexpr int MERGE_THREADS = 128;
+__global__ void __launch_bounds__(MERGE_THREADS) k_merge(const uint32_t* __restrict__ bucket_sums, MsmCfg cfg,
+                                                          uint32_t* __restrict__ merged) {
+  uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  uint32_t total = (uint32_t)cfg.nsets * cfg.nb;
+  bool live = q < total;
+  uint32_t qq = live ? q : total - 1;  // idle quads shadow the last one: shuffles need every lane
+  uint32_t set = qq / cfg.nb, b = qq % cfg.nb;
+  const uint32_t* src = bucket_sums + ((size_t)set * cfg.gsub * cfg.nb + b) * 32;
+  ge4 acc = ge4_identity();
+  ge4 x = ge4_load(src);
+  for (uint32_t g = 0; g < cfg.gsub; g++) {
+    ge4 cur = x;
+    if (g + 1 < cfg.gsub) x = ge4_load(src + (size_t)(g + 1) * cfg.nb * 32);
+    acc = ge4_add_cached(acc, cur);
+  }
+  acc = ge4_to_cached(acc);
+  if (live) ge4_store(merged + (size_t)qq * 32, acc);
+}
+
+// ---------------------------------------------------------------------------
+// bucket reduction  T = sum_{j<n} (j+1) X_j  for `narr` independent arrays.
+//
+// Invariant carried between levels: T = sum_q A_q + sum_q q Y_q over pairs (A_q, Y_q).
+//  * leaf pass (serial, one QUAD per chunk of LC buckets, ge4.cuh):
+//      A_q = sum_k (k+1) X_{LC q + k},   Y_q = LC sum_k X_{LC q + k}
+//  * binary tree step (pairs 2q', 2q'+1 -> q'):
+//      A' = A_0 + A_1 + Y_1,             Y' = 2 (Y_0 + Y_1)
+// The tree keeps the dependent chain at lg n steps of two additions; the serial leaf pass keeps
+// the total work near 5 multiplication levels per bucket.  k_reduce_leaf: a block reduces
+// 64 LC buckets to one pair; k_reduce_pairs: a block reduces up to 256 pairs to one.
+// Missing items are the identity.  Every lane of a warp runs the same instruction stream
+// (the quad arithmetic shuffles warp-wide); idle quads compute on clamped addresses and do not store.
+// ---------------------------------------------------------------------------
+constexpr int RT_THREADS = 256;
+constexpr int RT_QUADS = RT_THREADS / 4;
+
+__device__ __forceinline__ ge4 ge4_identity_cached() {
+  int q = threadIdx.x & 3;
+  ge4 r;
+  r.c = fe_zero();
+  r.c.v[0] = q == 3 ? 0u : (q == 2 ? 2u : 1u);  // (Y-X, Y+X, 2Z, 2dT) = (1, 1, 2, 0)
+  return r;
+}
+
+// in-block binary tree over `m` pairs held in shared memory (ext layout), m <= blockDim/4, any m >= 1.
+// Result in sa[0], sy[0].
+__device__ __forceinline__ void rt_block_tree(uint32_t (*sa)[32], uint32_t (*sy)[32], uint32_t m) {
+  uint32_t quad = threadIdx.x >> 2, warp = threadIdx.x >> 5;
+  while (m > 1) {
+    uint32_t half = (m + 1) >> 1;
+    bool warp_live = warp * 8 < half;  // warp-uniform
+    ge4 A, Y;
+    if (warp_live) {
+      bool live = quad < half;
+      uint32_t q = live ? quad : 0;
+      bool have1 = 2 * q + 1 < m;
+      uint32_t i0 = 2 * q, i1 = have1 ? 2 * q + 1 : 2 * q;
+      ge4 a0 = ge4_load(sa[i0]), a1 = ge4_load(sa[i1]), y0 = ge4_load(sy[i0]), y1 = ge4_load(sy[i1]);
+      const ge4 id = ge4_identity();
+      a1.c = fe_sel(have1, a1.c, id.c);
+      y1.c = fe_sel(have1, y1.c, id.c);
+      ge4 y1c = ge4_to_cached(y1);
+      A = ge4_add_cached(ge4_add(a0, a1), y1c);
+      Y = ge4_dbl(ge4_add_cached(y0, y1c));
+    }
+    __syncthreads();
+    if (warp_live && quad < half) {
+      ge4_store(sa[quad], A);
+      ge4_store(sy[quad], Y);
+    }
+    __syncthreads();
+    m = half;
+  }
+}
+
+template <int LC>
+__global__ void __launch_bounds__(RT_THREADS) k_reduce_leaf(const uint32_t* __restrict__ in /*[narr][n] cached*/,
+                                                             uint32_t n, uint32_t tiles,
+                                                             uint32_t* __restrict__ out_a, uint32_t* __restrict__ out_y) {
+  __shared__ uint32_t sa[RT_QUADS][32], sy[RT_QUADS][32];
+  uint32_t arr = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+  uint32_t quad = threadIdx.x >> 2;
+  uint32_t first = (tile * RT_QUADS + quad) * LC;
+  int valid = first >= n ? 0 : (int)min((uint32_t)LC, n - first);
+  const uint32_t* src = in + ((size_t)arr * n + min(first, n - 1)) * 32;
   ge4 run = ge4_identity(), acc = ge4_identity();
-  for (int j = (int)cfg.chunk - 1; j >= 0; j--) {
-    ge4 bj = ge4_load(src + (size_t)j * 32);  // cached layout
-    run = ge4_add_cached(run, bj);
+  const ge4 idc = ge4_identity_cached();
+#pragma unroll
+  for (int k = LC - 1; k >= 0; k--) {
+    bool have = k < valid;
+    ge4 x = ge4_load(src + (size_t)(have ? k : 0) * 32);
+    x.c = fe_sel(have, x.c, idc.c);
+    run = ge4_add_cached(run, x);
     acc = ge4_add(acc, run);
   }
-  // + (q*chunk) * run by double-and-add over a block-uniform number of bits
-  uint32_t m = q * cfg.chunk;
-  uint32_t mmax = (cfg.nchunks - 1) * cfg.chunk;
-  if (mmax) {
-    int top = 31 - __clz(mmax);
-    ge4 rc = ge4_to_cached(run);
-    ge4 t = ge4_identity();
-    for (int bit = top; bit >= 0; bit--) {
-      t = ge4_dbl(t);
-      ge4 ta = ge4_add_cached(t, rc);
-      bool set = (m >> bit) & 1u;
-      t.c = fe_sel(set, ta.c, t.c);
-    }
-    acc = ge4_add(acc, t);
+#pragma unroll
+  for (int i = 1; i < LC; i <<= 1) run = ge4_dbl(run);
+  ge4_store(sa[quad], acc);
+  ge4_store(sy[quad], run);
+  __syncthreads();
+  rt_block_tree(sa, sy, RT_QUADS);
+  if (threadIdx.x < 32) {
+    size_t o = ((size_t)arr * tiles + tile) * 32;
+    out_a[o + threadIdx.x] = sa[0][threadIdx.x];
+    out_y[o + threadIdx.x] = sy[0][threadIdx.x];
   }
-  if (live) ge4_store(chunk_sums + (size_t)g * 32, acc);
 }
 
-// one block per window: sum of its chunk sums
-constexpr int COMB_THREADS = 128;
-__global__ void __launch_bounds__(COMB_THREADS) k_combine(const uint32_t* __restrict__ chunk_sums, MsmCfg cfg,
-                                                           uint32_t* __restrict__ window_sums) {
-  __shared__ uint32_t sm[COMB_THREADS / 32][32];
-  uint32_t win = blockIdx.x;
-  const uint32_t* src = chunk_sums + (size_t)win * cfg.nchunks * 32;
-  uint32_t quad = threadIdx.x >> 2, nquads = COMB_THREADS / 4;
-  ge4 acc = ge4_identity();
-  for (uint32_t base = 0; base < cfg.nchunks; base += nquads) {
-    uint32_t i = base + quad;
-    ge4 o = i < cfg.nchunks ? ge4_load(src + (size_t)i * 32) : ge4_identity();
-    acc = ge4_add(acc, o);
+// up to RP_THREADS/4 = 128 pairs per block -> one pair (the final launch has tiles == 1 and writes T to out_a)
+constexpr int RP_THREADS = 512;
+__global__ void __launch_bounds__(RP_THREADS) k_reduce_pairs(const uint32_t* __restrict__ in_a,
+                                                              const uint32_t* __restrict__ in_y, uint32_t n,
+                                                              uint32_t tiles, uint32_t* __restrict__ out_a,
+                                                              uint32_t* __restrict__ out_y) {
+  __shared__ uint32_t sa[RP_THREADS / 4][32], sy[RP_THREADS / 4][32];
+  uint32_t arr = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+  uint32_t first = tile * (RP_THREADS / 4);
+  uint32_t m = min((uint32_t)(RP_THREADS / 4), n - first);
+  const uint32_t* ga = in_a + ((size_t)arr * n + first) * 32;
+  const uint32_t* gy = in_y + ((size_t)arr * n + first) * 32;
+  for (uint32_t w = threadIdx.x; w < m * 32; w += blockDim.x) {
+    sa[w >> 5][w & 31] = ga[w];
+    sy[w >> 5][w & 31] = gy[w];
   }
-  acc = block_sum_quads(acc, sm);
-  if (threadIdx.x < 4) ge4_store(window_sums + (size_t)win * 32, acc);
+  __syncthreads();
+  rt_block_tree(sa, sy, m);
+  if (threadIdx.x < 32) {
+    size_t o = ((size_t)arr * tiles + tile) * 32;
+    out_a[o + threadIdx.x] = sa[0][threadIdx.x];
+    out_y[o + threadIdx.x] = sy[0][threadIdx.x];
+  }
 }
 
-// one warp per set: sum_w 2^(c w) S_w (Horner, top window first); for windowed tables the
-// weights are already in the points and it is a plain sum
+// plain tables, one warp per set: sum_w 2^(c w) S_w (Horner, top window first)
 __global__ void __launch_bounds__(32) k_horner(const uint32_t* __restrict__ window_sums, MsmCfg cfg,
                                                 uint32_t* __restrict__ out_ext) {
   uint32_t set = blockIdx.x;
   const uint32_t* src = window_sums + (size_t)set * cfg.W * 32;
-  ge4 acc;
-  if (cfg.win_stride) {
-    uint32_t quad = threadIdx.x >> 2;
-    acc = ge4_identity();
-    for (uint32_t base = 0; base < (uint32_t)cfg.W; base += 8) {
-      uint32_t w = base + quad;
-      ge4 o = w < (uint32_t)cfg.W ? ge4_load(src + (size_t)w * 32) : ge4_identity();
-      acc = ge4_add(acc, o);
-    }
-    acc = block_sum_quads(acc, nullptr);
-  } else {
-    // every quad runs the same chain (redundantly): the cost is the chain, not the lanes
-    acc = ge4_load(src + (size_t)(cfg.W - 1) * 32);
-    for (int w = cfg.W - 2; w >= 0; w--) {
-      for (int i = 0; i < cfg.c; i++) acc = ge4_dbl(acc);
-      acc = ge4_add(acc, ge4_load(src + (size_t)w * 32));
-    }
+  // every quad runs the same chain (redundantly): the cost is the chain, not the lanes
+  ge4 acc = ge4_load(src + (size_t)(cfg.W - 1) * 32);
+  for (int w = cfg.W - 2; w >= 0; w--) {
+    for (int i = 0; i < cfg.c; i++) acc = ge4_dbl(acc);
+    acc = ge4_add(acc, ge4_load(src + (size_t)w * 32));
   }
   if (threadIdx.x < 4) ge4_store(out_ext + (size_t)set * 32, acc);
 }

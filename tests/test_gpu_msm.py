@@ -142,3 +142,47 @@ def test_windowed_table(ctx, c):
     for s in range(sets):
         assert got[s] == G.msm(kk[s], ps[off : off + n]).encode()
     t.close()
+
+
+def test_msm_segmented_bucket(ctx):
+    """A bucket far longer than one block's segment (2048 entries): 512 points tiled 16 times
+    with one repeated scalar is 8192 entries per occupied bucket; the sum must be 16 k sum(P_i).
+    Structured witnesses (bit vectors, reference tests/r1cs.rs:629-632) hit this path at scale."""
+    from mpc_bulletproof_b200 import Table, msm
+
+    r = rng(61)
+    m, reps = 512, 16
+    ps = [rand_point(r) for _ in range(m)]
+    pb = points_bytes(ps)
+    total = G.msm([1] * m, ps)
+    for k in (1, rand_scalar(r)):
+        want = (k * reps % G.L) * total
+        assert msm(ctx, scalars_bytes([k]) * (m * reps), pb * reps) == want.encode()
+    # same through a windowed table, bits as scalars
+    t = Table(ctx, pb * reps).set_windows(0)
+    bits = [i & 1 for i in range(m * reps)]
+    want = G.msm([reps] * (m // 2), ps[1::2])
+    assert t.msm(scalars_bytes(bits))[0] == want.encode()
+    t.close()
+
+
+@pytest.mark.parametrize("c,gsub", [(8, 1), (8, 3), (8, 32), (13, 1), (13, 2), (13, 20), (16, 1), (16, 5)])
+def test_windowed_groups(ctx, c, gsub):
+    """Windowed tables share one bucket array per set; the entries of a bucket are split into
+    `gsub` groups by window index.  Every split must give the same sum."""
+    from mpc_bulletproof_b200 import Table
+
+    r = rng(70 + c)
+    n, sets = 700, 2
+    ps = [rand_point(r) for _ in range(n)]
+    t = Table(ctx, points_bytes(ps)).set_windows(c)
+    kk = [[rand_scalar(r) for _ in range(n)] for _ in range(sets)]
+    kk[0][0], kk[0][1], kk[1][0] = G.L - 1, 0, 2**252
+    want = [G.msm(k, ps).encode() for k in kk]
+    ctx.set_groups(gsub)
+    try:
+        got = t.msm(b"".join(scalars_bytes(k) for k in kk), n_sets=sets)
+    finally:
+        ctx.set_groups(0)
+    assert got == want
+    t.close()
