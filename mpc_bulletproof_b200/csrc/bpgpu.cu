@@ -365,11 +365,8 @@ static void make_cfg(MsmCfg& cfg, size_t n_terms, size_t n_points, int nsets, in
   }
   cfg.narr = (uint32_t)nsets * cfg.gsub;
   cfg.B = cfg.narr * cfg.nb;
-  double avg = (double)n_terms * cfg.W / (double)cfg.B;
-  cfg.big_thresh = (uint32_t)std::max(256.0, 16.0 * avg);
-  // segments of over-long buckets: at most one per big bucket plus one per BIG_SEG entries
-  cfg.big_cap = (uint32_t)(std::min<uint64_t>(cfg.B, (uint64_t)n_terms * cfg.W / cfg.big_thresh + 1) +
-                           (uint64_t)n_terms * cfg.W / BIG_SEG + 1);
+  // segments of over-long buckets (> BIG_SEG entries): at most two per BIG_SEG entries
+  cfg.big_cap = (uint32_t)(2 * ((uint64_t)n_terms * cfg.W / BIG_SEG) + 2);
   memset(&cfg.bias, 0, sizeof(cfg.bias));
   for (int w = 0; w < cfg.W; w++) {
     int bit = c * w + c - 1;
@@ -404,7 +401,7 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
 
   // reduction geometry: `rarr` arrays of nb buckets; a leaf block takes RT_QUADS chunks of LC buckets
   uint32_t rarr = windowed ? (uint32_t)nsets : cfg.narr;
-  const uint32_t LC = cfg.nb > (1u << 16) ? 8 : 4;
+  const uint32_t LC = cfg.nb > (1u << 17) ? 32 : (cfg.nb > (1u << 15) ? 8 : 4);
   uint32_t tiles0 = (cfg.nb + RT_QUADS * LC - 1) / (RT_QUADS * LC);
   size_t ntiles = (cfg.B + SCAN_TILE - 1) / SCAN_TILE;
   size_t off = 0;
@@ -418,8 +415,14 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   size_t o_merged = off;  off += (windowed && cfg.gsub > 1) ? align_up((size_t)nsets * cfg.nb * 128) : 0;
   size_t o_pairs = off;   off += 4 * align_up((size_t)rarr * tiles0 * 128);  // (A, Y) x ping-pong
   size_t o_wins = off;    off += align_up((size_t)rarr * 128);
-  size_t o_order = off;   off += align_up((size_t)cfg.B * 4);
-  size_t o_bins = off;    off += align_up(SIZE_BINS * 4);
+  // accumulation schedule: at most one item per bucket plus one per ACC_SEG entries
+  size_t max_items = (size_t)cfg.B + (size_t)n_terms * cfg.W / ACC_SEG + 1;
+  size_t max_multi = (size_t)n_terms * cfg.W / ACC_SEG + 1;  // buckets longer than ACC_SEG
+  size_t o_items = off;   off += align_up(max_items * 8);
+  size_t o_segslot = off; off += align_up((size_t)cfg.B * 4);
+  size_t o_multi = off;   off += align_up(max_multi * 4);
+  size_t o_segpart = off; off += align_up(2 * max_multi * 128);  // sum of nseg over multi-segment buckets <= 2 max_multi
+  size_t o_bins = off;    off += align_up((SIZE_BINS + 4) * 4);
   int rc = ensure_ws(ctx, off);
   if (rc) return rc;
   uint32_t* counts = (uint32_t*)(ctx->ws + o_counts);
@@ -434,8 +437,16 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   size_t pair_words = align_up((size_t)rarr * tiles0 * 128) / 4;
   uint32_t* pairs = (uint32_t*)(ctx->ws + o_pairs);
   uint32_t* wins = (uint32_t*)(ctx->ws + o_wins);
-  uint32_t* order = (uint32_t*)(ctx->ws + o_order);
   uint32_t* bins = (uint32_t*)(ctx->ws + o_bins);
+  AccSched sched;
+  sched.bins = bins;
+  sched.n_items = bins + SIZE_BINS;
+  sched.part_count = bins + SIZE_BINS + 1;
+  sched.multi_count = bins + SIZE_BINS + 2;
+  sched.items = (uint2*)(ctx->ws + o_items);
+  sched.seg_slot = (uint32_t*)(ctx->ws + o_segslot);
+  sched.multi_list = (uint32_t*)(ctx->ws + o_multi);
+  uint32_t* seg_part = (uint32_t*)(ctx->ws + o_segpart);
   cudaStream_t st = ctx->stream;
 
   prof_mark(ctx, BPG_PROF_HIST);
@@ -454,19 +465,22 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   prof_mark(ctx, BPG_PROF_SCATTER);
   k_scatter<<<gt, 256, 0, st>>>(d_scalars, d_set_ids, d_point_ids, cfg, offsets, counts, entries);
   LAUNCH_CHECK();
-  // bucket schedule by decreasing length (after the scan, overlapping nothing: three tiny kernels)
-  CK(cudaMemsetAsync(bins, 0, SIZE_BINS * 4, st));
+  // accumulation schedule: (bucket, segment) items by decreasing length; over-long buckets -> big list
+  CK(cudaMemsetAsync(bins, 0, (SIZE_BINS + 4) * 4, st));
   k_size_hist<<<std::min<unsigned>((cfg.B + 255) / 256, (unsigned)ctx->sm_count * 4), 256, 0, st>>>(offsets, cfg.B, bins);
   LAUNCH_CHECK();
-  k_size_scan<<<1, SIZE_BINS, 0, st>>>(bins);
+  k_size_scan<<<1, SIZE_BINS, 0, st>>>(bins, sched.n_items);
   LAUNCH_CHECK();
-  k_size_scatter<<<(cfg.B + 255) / 256, 256, 0, st>>>(offsets, cfg.B, bins, order);
+  k_size_scatter<<<(cfg.B + 255) / 256, 256, 0, st>>>(offsets, cfg, sched, big_count, big_list);
   LAUNCH_CHECK();
   prof_mark(ctx, BPG_PROF_ACCUM);
-  k_accum<<<(cfg.B + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, st>>>(table_base, offsets, entries, order, cfg,
-                                                                           buckets, big_count, big_list);
+  k_accum<<<(unsigned)((max_items + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, st>>>(table_base, offsets, entries,
+                                                                                          sched, buckets, seg_part);
   LAUNCH_CHECK();
   prof_mark(ctx, BPG_PROF_ACCUM_BIG);
+  k_accum_fix<<<(unsigned)std::min<size_t>((max_multi * 4 + FIX_THREADS - 1) / FIX_THREADS, (size_t)ctx->sm_count * 8),
+                FIX_THREADS, 0, st>>>(offsets, sched, seg_part, buckets);
+  LAUNCH_CHECK();
   unsigned gbig = std::min<unsigned>(cfg.big_cap, (unsigned)ctx->sm_count * 4);
   k_accum_big<<<gbig, BIG_THREADS, 0, st>>>(table_base, offsets, entries, cfg, buckets, big_count, big_list, big_part);
   LAUNCH_CHECK();
@@ -487,7 +501,8 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
     uint32_t* pa[2] = {pairs, pairs + 2 * pair_words};
     int cur = 0;
     uint32_t* oa = t == 1 ? final_out : pa[cur];
-    if (LC == 8) k_reduce_leaf<8><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
+    if (LC == 32) k_reduce_leaf<32><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
+    else if (LC == 8) k_reduce_leaf<8><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
     else k_reduce_leaf<4><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
     LAUNCH_CHECK();
     while (t > 1) {

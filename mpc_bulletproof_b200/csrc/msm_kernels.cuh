@@ -10,8 +10,10 @@
 //   k_hist      digits of every scalar -> per-bucket counts (atomics)
 //   scan        exclusive prefix over the nsets*W*2^(c-1) buckets
 //   k_scatter   counting-sort of (bucket -> point index | sign) entries
-//   k_accum     one thread per bucket: 7-mul mixed additions from the Niels table
-//   k_accum_big block-cooperative path for over-long buckets (structured scalars)
+//   k_size_*    accumulation schedule: (bucket, segment <= 64 entries) items by decreasing length
+//   k_accum     one thread per item: 7-mul mixed additions from the Niels table
+//   k_accum_fix / k_accum_big  partial sums of multi-segment buckets; block-cooperative path for
+//               over-long buckets (structured scalars)
 //   k_merge     windowed tables: the sub-bucket groups of a bucket -> one sum per (set, bucket)
 //   k_reduce_tree  radix-8 hierarchy of running sums: sum_j (j+1) B_j per bucket array
 //   k_horner    plain tables: sum_w 2^(c w) S_w per set -> extended point (the partial sum a rank owns)
@@ -38,7 +40,6 @@ struct MsmCfg {
   uint32_t gsub;      // bucket groups per set: window w accumulates into group w % gsub (plain tables: gsub = W)
   uint32_t narr;      // nsets * gsub bucket arrays of nb buckets
   uint32_t B;         // narr * nb
-  uint32_t big_thresh;  // buckets longer than this go to k_accum_big
   uint32_t big_cap;     // capacity of the big-bucket list
   uint32_t win_stride;  // 0: plain table.  >0: table holds 2^(c w) P_i at index w*win_stride + i
   sc_bias bias;
@@ -247,49 +248,93 @@ __device__ __forceinline__ ge4 block_sum_quads(ge4 p, uint32_t (*sm)[32]) {
   return p;
 }
 
-// bucket schedule: buckets ordered by decreasing length, so that the 32 buckets of a warp
-// have (almost) the same trip count and the longest ones start first
-constexpr uint32_t SIZE_BINS = 1024;
+// Accumulation schedule.  The work item of k_accum is a SEGMENT: at most ACC_SEG consecutive
+// entries of one bucket.  Items are ordered by decreasing length, so the 32 items of a warp have
+// (almost) the same trip count and the longest start first.  A bucket of one segment is
+// finished by its thread; a longer one (structured scalars, or the short top window whose few
+// occupied buckets are long) leaves per-segment partial sums that k_accum_fix adds; beyond
+// BIG_SEG entries the block-cooperative k_accum_big takes over.
+constexpr uint32_t ACC_SEG = 64;
+constexpr uint32_t SIZE_BINS = 128;  // size classes 0..ACC_SEG
+struct AccSched {
+  uint32_t* bins;        // [SIZE_BINS] class counters -> class cursors
+  uint32_t* n_items;     // total work items
+  uint2* items;          // (bucket, segment)
+  uint32_t* seg_slot;    // [B] first partial-sum slot of a multi-segment bucket
+  uint32_t* part_count;  // partial-sum slots handed out
+  uint32_t* multi_count; // multi-segment buckets
+  uint32_t* multi_list;  // their ids
+};
+__device__ __forceinline__ uint32_t acc_nseg(uint32_t len) { return len == 0 ? 1u : (len + ACC_SEG - 1) / ACC_SEG; }
+
 __global__ void __launch_bounds__(256) k_size_hist(const uint32_t* __restrict__ offsets, uint32_t B,
                                                    uint32_t* __restrict__ bins /*[SIZE_BINS], zeroed*/) {
   __shared__ uint32_t sh[SIZE_BINS];
   for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
-    uint32_t cnt = offsets[b + 1] - offsets[b];
-    atomicAdd(&sh[min(cnt, SIZE_BINS - 1)], 1u);
+    uint32_t len = offsets[b + 1] - offsets[b];
+    if (len > BIG_SEG) continue;
+    uint32_t full = len / ACC_SEG, rem = len % ACC_SEG;
+    if (full) atomicAdd(&sh[ACC_SEG], full);
+    if (rem || !full) atomicAdd(&sh[rem], 1u);
   }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x)
     if (sh[i]) atomicAdd(&bins[i], sh[i]);
 }
-// single block: bins -> starting position of each size class, largest first
-__global__ void __launch_bounds__(SIZE_BINS) k_size_scan(uint32_t* __restrict__ bins) {
+// single block: bins -> starting position of each size class, largest first; total -> n_items
+__global__ void __launch_bounds__(SIZE_BINS) k_size_scan(uint32_t* __restrict__ bins, uint32_t* __restrict__ n_items) {
   __shared__ uint32_t smem[33];
   uint32_t i = threadIdx.x;
-  uint32_t v = bins[SIZE_BINS - 1 - i];  // reversed: class SIZE_BINS-1 first
+  uint32_t v = bins[SIZE_BINS - 1 - i];  // reversed: the longest class first
   uint32_t total;
   uint32_t ex = block_exclusive_scan(v, &total, smem);
   bins[SIZE_BINS - 1 - i] = ex;
+  if (i == 0) *n_items = total;
 }
-__global__ void __launch_bounds__(256) k_size_scatter(const uint32_t* __restrict__ offsets, uint32_t B,
-                                                      uint32_t* __restrict__ bins, uint32_t* __restrict__ order) {
+__global__ void __launch_bounds__(256) k_size_scatter(const uint32_t* __restrict__ offsets, MsmCfg cfg, AccSched sc,
+                                                      uint32_t* __restrict__ big_count,
+                                                      uint32_t* __restrict__ big_list) {
   // block-private histogram first: one global atomic per (block, occupied size class)
   __shared__ uint32_t cnt[SIZE_BINS];
   __shared__ uint32_t base[SIZE_BINS];
   for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) cnt[i] = 0;
   __syncthreads();
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t cls = 0, rank = 0;
-  if (b < B) {
-    cls = min(offsets[b + 1] - offsets[b], SIZE_BINS - 1);
-    rank = atomicAdd(&cnt[cls], 1u);
+  uint32_t len = 0, full = 0, rem = 0, rank_full = 0, rank_rem = 0;
+  bool small = false;
+  if (b < cfg.B) {
+    len = offsets[b + 1] - offsets[b];
+    if (len > BIG_SEG) {
+      // over-long bucket: hand it to k_accum_big in segments of BIG_SEG entries
+      uint32_t nseg = (len + BIG_SEG - 1) / BIG_SEG;
+      uint32_t slot = atomicAdd(big_count, nseg);
+      for (uint32_t j = 0; j < nseg && slot + j < cfg.big_cap; j++) {
+        big_list[3 * (size_t)(slot + j)] = b;
+        big_list[3 * (size_t)(slot + j) + 1] = j;
+        big_list[3 * (size_t)(slot + j) + 2] = nseg;
+      }
+    } else {
+      small = true;
+      full = len / ACC_SEG;
+      rem = len % ACC_SEG;
+      if (full) rank_full = atomicAdd(&cnt[ACC_SEG], full);
+      if (rem || !full) rank_rem = atomicAdd(&cnt[rem], 1u);
+    }
   }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x)
-    if (cnt[i]) base[i] = atomicAdd(&bins[i], cnt[i]);
+    if (cnt[i]) base[i] = atomicAdd(&sc.bins[i], cnt[i]);
   __syncthreads();
-  if (b < B) order[base[cls] + rank] = b;
+  if (small) {
+    for (uint32_t j = 0; j < full; j++) sc.items[base[ACC_SEG] + rank_full + j] = make_uint2(b, j);
+    if (rem || !full) sc.items[base[rem] + rank_rem] = make_uint2(b, full);
+    if (acc_nseg(len) > 1) {
+      sc.seg_slot[b] = atomicAdd(sc.part_count, acc_nseg(len));
+      sc.multi_list[atomicAdd(sc.multi_count, 1u)] = b;
+    }
+  }
 }
 
 BPG_DEF_CONST(K_DINV, 0xcdc9f843u, 0x25e0f276u, 0x4279542eu, 0x0b5dd698u, 0xcdb9cf66u, 0x2b162114u, 0x14d5ce43u,
@@ -310,29 +355,18 @@ __device__ __forceinline__ ge_ext ge_from_niels(const ge_niels& q, bool neg) {
 
 __global__ void __launch_bounds__(ACC_THREADS) k_accum(const uint32_t* __restrict__ table,
                                                         const uint32_t* __restrict__ offsets,
-                                                        const uint32_t* __restrict__ entries,
-                                                        const uint32_t* __restrict__ order, MsmCfg cfg,
+                                                        const uint32_t* __restrict__ entries, AccSched sc,
                                                         uint32_t* __restrict__ bucket_sums,
-                                                        uint32_t* __restrict__ big_count,
-                                                        uint32_t* __restrict__ big_list) {
+                                                        uint32_t* __restrict__ seg_part /*[slots][32] ext*/) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= cfg.B) return;
-  uint32_t b = order[t];
-  uint32_t beg = offsets[b], end = offsets[b + 1];
-  if (end - beg > cfg.big_thresh) {
-    // over-long bucket: hand it to k_accum_big in segments of BIG_SEG entries
-    uint32_t nseg = (end - beg + BIG_SEG - 1) / BIG_SEG;
-    uint32_t slot = atomicAdd(big_count, nseg);
-    for (uint32_t j = 0; j < nseg && slot + j < cfg.big_cap; j++) {
-      big_list[3 * (size_t)(slot + j)] = b;
-      big_list[3 * (size_t)(slot + j) + 1] = j;
-      big_list[3 * (size_t)(slot + j) + 2] = nseg;
-    }
-    return;
-  }
+  if (t >= *sc.n_items) return;
+  uint2 it = sc.items[t];
+  uint32_t b = it.x;
+  uint32_t b_beg = offsets[b], b_end = offsets[b + 1];
+  uint32_t beg = b_beg + it.y * ACC_SEG, end = min(b_end, beg + ACC_SEG);
   ge_ext acc = ge_identity();
   if (beg < end) {
-    // software pipeline: the Niels entry of step k+1 is in flight while step k multiplies
+    // software pipeline: the entry word of step k+1 is in flight while step k multiplies
     uint32_t e = __ldg(entries + beg);
     ge_niels q;
     ge_load_niels(q, table + (size_t)(e & ~ENTRY_NEG) * 24);
@@ -345,7 +379,40 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accum(const uint32_t* __restric
       acc = ge_madd(acc, q, (e & ENTRY_NEG) != 0);
     }
   }
-  ge_store_cached(bucket_sums + (size_t)b * 32, acc);
+  if (b_end - b_beg <= ACC_SEG) ge_store_cached(bucket_sums + (size_t)b * 32, acc);
+  else ge_store_ext(seg_part + (size_t)(sc.seg_slot[b] + it.y) * 32, acc);
+}
+
+// multi-segment buckets: one quad adds the (at most BIG_SEG / ACC_SEG) partial sums
+constexpr int FIX_THREADS = 128;
+__global__ void __launch_bounds__(FIX_THREADS) k_accum_fix(const uint32_t* __restrict__ offsets, AccSched sc,
+                                                            const uint32_t* __restrict__ seg_part,
+                                                            uint32_t* __restrict__ bucket_sums) {
+  uint32_t nmulti = *sc.multi_count;
+  uint32_t quads = gridDim.x * (FIX_THREADS / 4);
+  uint32_t rounds = (nmulti + quads - 1) / quads;
+  uint32_t q0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  for (uint32_t r = 0; r < rounds; r++) {
+    uint32_t k = r * quads + q0;
+    bool live = k < nmulti;
+    uint32_t b = sc.multi_list[live ? k : 0];
+    uint32_t nseg = acc_nseg(offsets[b + 1] - offsets[b]);
+    // warp-uniform trip count (the quad arithmetic shuffles warp-wide)
+    uint32_t nmax = nseg;
+#pragma unroll
+    for (int o = 16; o >= 4; o >>= 1) nmax = max(nmax, __shfl_xor_sync(BPG_FULL_MASK, nmax, o));
+    const uint32_t* src = seg_part + (size_t)sc.seg_slot[b] * 32;
+    ge4 acc = ge4_identity();
+    const ge4 id = ge4_identity();
+    for (uint32_t j = 0; j < nmax; j++) {
+      bool have = j < nseg;
+      ge4 x = ge4_load(src + (size_t)(have ? j : 0) * 32);
+      x.c = fe_sel(have, x.c, id.c);
+      acc = ge4_add(acc, x);
+    }
+    acc = ge4_to_cached(acc);
+    if (live) ge4_store(bucket_sums + (size_t)b * 32, acc);
+  }
 }
 
 // over-long buckets (structured scalars: bit vectors, the nearly empty top window): one block per
@@ -507,7 +574,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_reduce_leaf(const uint32_t* __re
   const uint32_t* src = in + ((size_t)arr * n + min(first, n - 1)) * 32;
   ge4 run = ge4_identity(), acc = ge4_identity();
   const ge4 idc = ge4_identity_cached();
-#pragma unroll
+#pragma unroll 4
   for (int k = LC - 1; k >= 0; k--) {
     bool have = k < valid;
     ge4 x = ge4_load(src + (size_t)(have ? k : 0) * 32);
