@@ -201,15 +201,6 @@ typedef struct {
   uint32_t c0[8], c1[8];     /* scalar of B = c0 + c1*delta (verifier.rs:527-529)               */
   uint32_t lg_n, n, n1, N;   /* N = 2^lg_n padded size, n multipliers, n1 first-phase           */
 } bpg_verify_params;
-/* The verifier's mega-MSM (verifier.rs:516-547) with g_scalars, h_scalars and delta computed
- * on the device.  Terms: [adhoc points | B | B_blinding | G[0..N) | H[0..N)]; the caller
- * supplies the adhoc scalars and the B_blinding scalar (canonical bytes) and wL, wR, wO
- * (Montgomery, n each).  out = compressed sum; accept iff it is the identity (32 zero bytes). */
-int bpg_r1cs_verify_msm(bpg_ctx* ctx, const bpg_table* gens, size_t g_base, size_t h_base, size_t b_id,
-                        const uint8_t* adhoc_points, const uint8_t* adhoc_scalars, size_t n_adhoc,
-                        const uint8_t bb_scalar[32], const void* wL, const void* wR, const void* wO,
-                        const bpg_verify_params* params, uint8_t out[32]);
-
 /* InnerProductProof::verify (src/inner_product_proof.rs:317-372): s_i from (allinv, u_j^2) by
  * its closed form, g_i = a s_i G_factors[i], h_i = b s_{N-1-i} H_factors[i] on the device, then
  * one MSM over [adhoc (Q, L_*, R_*; host scalars) | G[g_off..+N) | H[h_off..+N)].  Factors are
@@ -236,9 +227,22 @@ int bpg_r1cs_dev_reserve(bpg_r1cs_dev** st, size_t capacity);
 int bpg_r1cs_dev_commit(bpg_r1cs_dev* st, const bpg_table* gens, size_t g_base, size_t h_base, size_t bb_id,
                         size_t first, size_t cnt, const void* aL, const void* aR, const void* aO, const void* raw_sL,
                         const void* raw_sR, const uint8_t blind3[96], uint8_t out[96]);
-/* t_1..t_6 (util.rs:152-170); uploads and keeps wL, wR, wO.  t_out: six canonical scalars. */
-int bpg_r1cs_dev_poly_t(bpg_r1cs_dev* st, size_t n, const void* wL, const void* wR, const void* wO, const void* y_pow,
-                        const void* y_inv_pow, uint8_t t_out[192]);
+/* flattened_constraints (prover.rs:342-379, verifier.rs:323-362) as a sparse product on the
+ * device: term t of constraint row t_row[t] names variable t_code[t] = kind << 28 | index
+ * (kinds 1 left, 2 right, 3 output, 4 committed, 5 constant one) with coefficient t_coeff[t]
+ * (Montgomery); z_pow is the pow table of z.  wL, wR, wO stay resident in the state; wv_out
+ * receives wV[0..m) and w_c, (m + 1) x 32 bytes of Montgomery limbs. */
+int bpg_r1cs_dev_flatten(bpg_r1cs_dev* st, size_t n, size_t m, size_t n_terms, const uint32_t* t_code,
+                         const uint32_t* t_row, const void* t_coeff, const void* z_pow, void* wv_out);
+/* t_1..t_6 (util.rs:152-170) from the resident vectors.  t_out: six canonical scalars. */
+int bpg_r1cs_dev_poly_t(bpg_r1cs_dev* st, size_t n, const void* y_pow, const void* y_inv_pow, uint8_t t_out[192]);
+/* The verifier's mega-MSM (verifier.rs:516-547) with g_scalars, h_scalars and delta computed on
+ * the device from the resident weights.  Terms: [adhoc points | B | B_blinding | G[0..N) | H[0..N)];
+ * the caller supplies the adhoc scalars and the B_blinding scalar (canonical bytes).
+ * out = compressed sum; accept iff it is the identity (32 zero bytes). */
+int bpg_r1cs_dev_verify_msm(bpg_r1cs_dev* st, const bpg_table* gens, size_t g_base, size_t h_base, size_t b_id,
+                            const uint8_t* adhoc_points, const uint8_t* adhoc_scalars, size_t n_adhoc,
+                            const uint8_t bb_scalar[32], const bpg_verify_params* params, uint8_t out[32]);
 /* l(x), r(x) with padding and the G/H factors (prover.rs:650-697) computed in HBM, then the IPP
  * state over the shared generator table with Q = q_mul * gens[q_id]. */
 int bpg_r1cs_dev_ipp_begin(bpg_r1cs_dev* st, const bpg_table* gens, size_t g_base, size_t h_base, size_t q_id,

@@ -104,13 +104,14 @@ _SIGNATURES = {
     "bpg_ipp_round_fold": (_I, [_P, _P, _P]),
     "bpg_ipp_finish": (_I, [_P, _P, _P]),
     "bpg_ipp_free": (None, [_P]),
-    "bpg_r1cs_verify_msm": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _P, _SZ, _P, _P, _P, _P, _P, _P]),
     "bpg_r1cs_dev_new": (_I, [_P, _SZ, ctypes.POINTER(_P)]),
     "bpg_r1cs_dev_free": (None, [_P]),
     "bpg_r1cs_dev_reserve": (_I, [ctypes.POINTER(_P), _SZ]),
     "bpg_ipp_verify_msm": (_I, [_P, _P, _SZ, _P, _SZ, _P, _P, _SZ, _P, _P, _P, _P]),
     "bpg_r1cs_dev_commit": (_I, [_P, _P, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _P, _P, _P, _P]),
-    "bpg_r1cs_dev_poly_t": (_I, [_P, _SZ, _P, _P, _P, _P, _P, _P]),
+    "bpg_r1cs_dev_flatten": (_I, [_P, _SZ, _SZ, _SZ, _P, _P, _P, _P, _P]),
+    "bpg_r1cs_dev_poly_t": (_I, [_P, _SZ, _P, _P, _P]),
+    "bpg_r1cs_dev_verify_msm": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _P, _SZ, _P, _P, _P]),
     "bpg_r1cs_dev_ipp_begin": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _SZ, _SZ, _SZ, _P, _P, _P, _P, ctypes.POINTER(_P)]),
     "bpg_comb_create": (_I, [_P, _P, _I, ctypes.POINTER(_P)]),
     "bpg_comb_free": (None, [_P]),

@@ -73,6 +73,20 @@ struct bpg_table {
     }                                             \
   } while (0)
 
+// Transient device memory (tables, proof states) comes from the device's stream-ordered pool:
+// after warm-up an allocation is a pool hit (microseconds) and a free does not synchronise the
+// device, which matters when a proof allocates its state per call.
+static cudaError_t dev_alloc(bpg_ctx* ctx, void** p, size_t bytes) {
+  return cudaMallocAsync(p, std::max<size_t>(bytes, 256), ctx->stream);
+}
+template <typename T>
+static cudaError_t dev_alloc(bpg_ctx* ctx, T** p, size_t bytes) {
+  return dev_alloc(ctx, reinterpret_cast<void**>(p), bytes);
+}
+static void dev_free(bpg_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+
 static constexpr size_t SMALL_BYTES = 1 << 16;
 
 extern "C" int bpg_init(int device, bpg_ctx** out) {
@@ -95,6 +109,13 @@ extern "C" int bpg_init(int device, bpg_ctx** out) {
     return BPG_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;  // freed blocks stay in the pool for the next proof
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   const char* env = getenv("BPG_MSM_C");
   if (env) ctx->forced_c = atoi(env);
   env = getenv("BPG_MSM_GSUB");
@@ -247,7 +268,7 @@ static int table_from_dev(bpg_ctx* ctx, const uint8_t* d_comp, size_t n, bpg_tab
   t->ctx = ctx;
   t->n = n;
   t->niels = nullptr;
-  cudaError_t e = cudaMalloc(&t->niels, std::max<size_t>(n, 1) * 96);
+  cudaError_t e = dev_alloc(ctx, &t->niels, std::max<size_t>(n, 1) * 96);
   if (e != cudaSuccess) {
     delete t;
     ctx->last_cuda = (int)e;
@@ -269,7 +290,7 @@ static int table_from_dev(bpg_ctx* ctx, const uint8_t* d_comp, size_t n, bpg_tab
     if (*hbad) rc = BPG_ERR_DECODE;
   } while (0);
   if (rc != BPG_OK) {
-    cudaFree(t->niels);
+    dev_free(ctx, t->niels);
     delete t;
     return rc;
   }
@@ -296,8 +317,7 @@ extern "C" size_t bpg_table_len(const bpg_table* t) { return t ? t->n : 0; }
 extern "C" void bpg_table_free(bpg_table* t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
-  cudaStreamSynchronize(t->ctx->stream);
-  cudaFree(t->niels);
+  dev_free(t->ctx, t->niels);  // stream-ordered: work already enqueued on the table finishes first
   delete t;
 }
 
@@ -696,7 +716,7 @@ extern "C" int bpg_table_set_windows(bpg_ctx* ctx, bpg_table* t, int c) {
     return BPG_OK;
   }
   uint32_t* out = nullptr;
-  cudaError_t e = cudaMalloc(&out, (size_t)W * t->n * 96);
+  cudaError_t e = dev_alloc(ctx, &out, (size_t)W * t->n * 96);
   if (e != cudaSuccess) {
     ctx->last_cuda = (int)e;
     return BPG_ERR_NOMEM;
@@ -707,7 +727,7 @@ extern "C" int bpg_table_set_windows(bpg_ctx* ctx, bpg_table* t, int c) {
   size_t zp_bytes = align_up((size_t)(W - 1) * chunk * 32);
   int rc = ensure_ws(ctx, ext_bytes + zp_bytes);
   if (rc) {
-    cudaFree(out);
+    dev_free(ctx, out);
     return rc;
   }
   for (size_t first = 0; first < t->n; first += chunk) {
@@ -720,10 +740,10 @@ extern "C" int bpg_table_set_windows(bpg_ctx* ctx, bpg_table* t, int c) {
   cudaError_t se = cudaStreamSynchronize(ctx->stream);
   if (se != cudaSuccess || cudaGetLastError() != cudaSuccess) {
     ctx->last_cuda = (int)se;
-    cudaFree(out);
+    dev_free(ctx, out);
     return BPG_ERR_CUDA;
   }
-  cudaFree(t->niels);
+  dev_free(ctx, t->niels);
   t->niels = out;
   t->win_c = c;
   t->win_W = W;
@@ -753,7 +773,7 @@ static int table_alloc_plain(bpg_ctx* ctx, size_t n, bpg_table** out) {
   if (!t) return BPG_ERR_NOMEM;
   t->ctx = ctx;
   t->n = n;
-  cudaError_t e = cudaMalloc(&t->niels, std::max<size_t>(n, 1) * 96);
+  cudaError_t e = dev_alloc(ctx, &t->niels, std::max<size_t>(n, 1) * 96);
   if (e != cudaSuccess) {
     delete t;
     ctx->last_cuda = (int)e;
@@ -793,7 +813,7 @@ static int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const b
   size_t o_sc = take(T * 32), o_pid = take(T * 4), o_set = take(T), o_part = take(nparts * 64);
   size_t o_u = take(64), o_ext = take(2 * 128), o_bytes = take(64), o_q = take(32), o_qm = take(32);
   do {
-    cudaError_t e = cudaMalloc(&st->buf, off);
+    cudaError_t e = dev_alloc(ctx, &st->buf, off);
     if (e != cudaSuccess) { ctx->last_cuda = (int)e; rc = BPG_ERR_NOMEM; break; }
     st->a = (uint32_t*)(st->buf + o_a); st->b = (uint32_t*)(st->buf + o_b);
     st->wG = (uint32_t*)(st->buf + o_wG); st->wH = (uint32_t*)(st->buf + o_wH);
@@ -847,7 +867,7 @@ static int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const b
   } while (0);
   if (rc != BPG_OK) {
     if (st->own_tab) bpg_table_free(st->own_tab);
-    if (st->buf) cudaFree(st->buf);
+    dev_free(ctx, st->buf);
     delete st;
     return rc;
   }
@@ -976,9 +996,8 @@ extern "C" int bpg_ipp_finish(bpg_ipp* st, uint8_t a[32], uint8_t b[32]) {
 extern "C" void bpg_ipp_free(bpg_ipp* st) {
   if (!st) return;
   cudaSetDevice(st->ctx->device);
-  cudaStreamSynchronize(st->ctx->stream);
   if (st->own_tab) bpg_table_free(st->own_tab);
-  if (st->buf) cudaFree(st->buf);
+  dev_free(st->ctx, st->buf);
   delete st;
 }
 

@@ -365,7 +365,11 @@ struct bpg_cs {
   bpg_ctx* ctx;
   const bpg_gens* gens;
   Transcript* tr;
-  std::vector<LinComb> constraints;
+  // constraints in flat (CSR-like) form, appended as the gadget code constrains: row q, variable
+  // code = kind << 28 | index, Montgomery coefficient -- uploaded as is for the device flattening
+  std::vector<uint32_t> t_code, t_row;
+  std::vector<Scalar> t_coeff;
+  size_t n_rows = 0;
   // prover
   std::vector<Scalar> a_L, a_R, a_O, v, v_blinding;
   // verifier
@@ -394,12 +398,21 @@ struct bpg_cs {
     }
     return tot;
   }
+  void add_constraint(const LinComb& lc) {
+    for (auto& t : lc) {
+      t_code.push_back(((uint32_t)var_kind(t.var) << 28) | (uint32_t)var_idx(t.var));
+      t_row.push_back((uint32_t)n_rows);
+      t_coeff.push_back(t.coeff);
+    }
+    n_rows++;
+  }
   bool valid(const LinComb& lc) const {
+    if (lc.size() >= (1u << 31)) return false;
     for (auto& t : lc) {
       uint64_t i = var_idx(t.var);
       switch (var_kind(t.var)) {
-        case V_LEFT: case V_RIGHT: case V_OUT: if (i >= num_multipliers()) return false; break;
-        case V_COMMITTED: if (i >= (is_prover ? v.size() : V.size())) return false; break;
+        case V_LEFT: case V_RIGHT: case V_OUT: if (i >= num_multipliers() || i >= (1u << 27)) return false; break;
+        case V_COMMITTED: if (i >= (is_prover ? v.size() : V.size()) || i >= (1u << 27)) return false; break;
         case V_ONE: case V_ZERO: break;
         default: return false;
       }
@@ -423,8 +436,8 @@ struct bpg_cs {
     out[2] = mkvar(V_OUT, i);
     left.push_back({out[0], -Scalar::one()});
     right.push_back({out[1], -Scalar::one()});
-    constraints.push_back(std::move(left));
-    constraints.push_back(std::move(right));
+    add_constraint(left);
+    add_constraint(right);
   }
   // prover.rs:127-146 / verifier.rs:120-134
   bpg_var allocate(const Scalar* assignment) {
@@ -466,30 +479,22 @@ struct bpg_cs {
     out[2] = mkvar(V_OUT, i);
   }
 
-  // prover.rs:342-379 / verifier.rs:323-362
-  void flattened_constraints(const Scalar& z, std::vector<Scalar>& wL, std::vector<Scalar>& wR,
-                             std::vector<Scalar>& wO, std::vector<Scalar>& wV, Scalar& wc) const {
+  // prover.rs:342-379 / verifier.rs:323-362: sum_q z^(q+1) * row_q, evaluated on the device as a
+  // sparse product over the flat terms; wL, wR, wO stay in HBM, wV and wc come back
+  int flattened_constraints(bpg_r1cs_dev* dv, const Scalar& z, std::vector<Scalar>& wV, Scalar& wc) const {
     size_t n = num_multipliers(), m = is_prover ? v.size() : V.size();
-    wL.assign(n, Scalar::zero());
-    wR.assign(n, Scalar::zero());
-    wO.assign(n, Scalar::zero());
-    wV.assign(m, Scalar::zero());
-    wc = Scalar::zero();
-    Scalar exp_z = z;
-    for (auto& lc : constraints) {
-      for (auto& t : lc) {
-        uint64_t i = var_idx(t.var);
-        switch (var_kind(t.var)) {
-          case V_LEFT: wL[i] += exp_z * t.coeff; break;
-          case V_RIGHT: wR[i] += exp_z * t.coeff; break;
-          case V_OUT: wO[i] += exp_z * t.coeff; break;
-          case V_COMMITTED: wV[i] -= exp_z * t.coeff; break;
-          case V_ONE: wc -= exp_z * t.coeff; break;  // the prover ignores it (prover.rs:370-372)
-          default: break;
-        }
-      }
-      exp_z *= z;
+    uint32_t z_pow[32][8];
+    Scalar b = z;
+    for (int k = 0; k < 32; k++) {
+      memcpy(z_pow[k], b.v, 32);
+      b = b * b;
     }
+    std::vector<Scalar> out(m + 1);
+    int rc = bpg_r1cs_dev_flatten(dv, n, m, t_code.size(), t_code.data(), t_row.data(), t_coeff.data(), z_pow, out.data());
+    if (rc) return rc;
+    wV.assign(out.begin(), out.begin() + m);
+    wc = out[m];  // the prover ignores it (prover.rs:370-372)
+    return BPG_OK;
   }
 
   // prover.rs:383-402 / verifier.rs:366-385
@@ -552,7 +557,7 @@ extern "C" int bpg_verifier_new(bpg_ctx* ctx, const bpg_gens* gens, bpg_transcri
 }
 extern "C" void bpg_cs_free(bpg_cs* cs) { delete cs; }
 extern "C" size_t bpg_cs_num_multipliers(const bpg_cs* cs) { return cs ? cs->num_multipliers() : 0; }
-extern "C" size_t bpg_cs_num_constraints(const bpg_cs* cs) { return cs ? cs->constraints.size() : 0; }
+extern "C" size_t bpg_cs_num_constraints(const bpg_cs* cs) { return cs ? cs->n_rows : 0; }
 extern "C" bpg_var bpg_var_one(void) { return mkvar(V_ONE, 0); }
 
 // prover.rs:319-329
@@ -626,7 +631,7 @@ extern "C" int bpg_cs_constrain(bpg_cs* cs, const bpg_term* lc, size_t n) {
   LinComb l;
   int rc = parse_lc(cs, lc, n, &l);
   if (rc) return rc;
-  cs->constraints.push_back(std::move(l));
+  cs->add_constraint(l);
   return BPG_OK;
 }
 extern "C" int bpg_cs_specify_randomized_constraints(bpg_cs* cs, bpg_randomized_cb cb, void* user) {
@@ -785,10 +790,11 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   tr.append_point("A_O2", proof.A_O2.data());
   tr.append_point("S2", proof.S2.data());
   Scalar y = tr.challenge_scalar("y"), z = tr.challenge_scalar("z");  // :584-585
-  std::vector<Scalar> wL, wR, wO, wV;
+  std::vector<Scalar> wV;
   Scalar wc;
   tm.lap("phase 2");
-  cs->flattened_constraints(z, wL, wR, wO, wV, wc);
+  rc = cs->flattened_constraints(dv.p, z, wV, wc);
+  if (rc) return rc;
   tm.lap("flattened_constraints");
   // l(X), r(X) coefficient vectors (:596-617) and t_1..t_6 (util.rs:152-170) in HBM
   Scalar y_inv = y.invert();
@@ -796,7 +802,7 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   pow_table(y, y_pow);
   pow_table(y_inv, y_inv_pow);
   uint8_t tbytes[192];
-  rc = bpg_r1cs_dev_poly_t(dv.p, n, wL.data(), wR.data(), wO.data(), y_pow, y_inv_pow, tbytes);
+  rc = bpg_r1cs_dev_poly_t(dv.p, n, y_pow, y_inv_pow, tbytes);
   if (rc) return rc;
   Scalar t[6];
   for (int k = 0; k < 6; k++) Scalar::from_bytes(tbytes + 32 * k, &t[k]);
@@ -886,9 +892,13 @@ extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_
   tr.append_scalar("t_x_blinding", proof.t_x_blinding);
   tr.append_scalar("e_blinding", proof.e_blinding);
   Scalar w = tr.challenge_scalar("w");
-  std::vector<Scalar> wL, wR, wO, wV;
+  std::vector<Scalar> wV;
   Scalar wc;
-  cs->flattened_constraints(z, wL, wR, wO, wV, wc);
+  DevGuard dv;
+  rc = bpg_r1cs_dev_new(cs->ctx, std::max<size_t>(n, 1), &dv.p);
+  if (rc) return rc;
+  rc = cs->flattened_constraints(dv.p, z, wV, wc);
+  if (rc) return rc;
   tm.lap("replay + flatten");
   std::vector<Scalar> u_sq, u_inv_sq;
   Scalar allinv;
@@ -947,8 +957,8 @@ extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_
   (-proof.e_blinding - r * proof.t_x_blinding).to_bytes(bb_scalar);  // B_blinding
   std::vector<uint8_t> scb = sc_vec_bytes(sc);
   tm.lap("adhoc scalars");
-  rc = bpg_r1cs_verify_msm(cs->ctx, g->table, g->g_base(), g->h_base(), g->b_id(), pts.data(), scb.data(), n_adhoc,
-                           bb_scalar, wL.data(), wR.data(), wO.data(), &vp, mega);
+  rc = bpg_r1cs_dev_verify_msm(dv.p, g->table, g->g_base(), g->h_base(), g->b_id(), pts.data(), scb.data(), n_adhoc,
+                               bb_scalar, &vp, mega);
   tm.lap("g/h scalars + mega msm");
   if (rc == BPG_ERR_DECODE) return BPG_ERR_DECODE;  // a proof point that is not a valid encoding: FormatError
   if (rc) return rc;

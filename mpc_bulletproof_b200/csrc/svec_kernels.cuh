@@ -307,4 +307,73 @@ __global__ void __launch_bounds__(256) k_ipp_verify_scalars(const uint32_t* __re
   sc_store(h_out + (size_t)i * 8, h);
 }
 
+// ---- flattened constraints (prover.rs:342-379, verifier.rs:323-362) ----------------------
+// Constraint q (row q) contributes z^(q+1) * coeff to the weight of each variable it names:
+//   wL[i], wR[i], wO[i] += ...;   wV[j] -= ...;   wc -= ... (the constant term).
+// One thread per TERM forms its product and adds it into its variable's accumulator: eight
+// 64-bit counters, one per 32-bit limb of the Montgomery residue, with plain integer atomics
+// (exact and order-independent; 2^32 terms cannot overflow a counter).  The constant is named
+// by a large share of the rows of some circuits, so its terms are summed per block first.
+// k_flat_finish carries the counters, reduces mod l and applies the signs.
+constexpr uint32_t FLAT_KIND_SHIFT = 28;  // term code: kind << 28 | index; kinds as in the host mirror
+enum : uint32_t { FK_LEFT = 1, FK_RIGHT = 2, FK_OUT = 3, FK_COMMITTED = 4, FK_ONE = 5, FK_ZERO = 6 };
+
+__global__ void __launch_bounds__(SV_THREADS) k_flat_terms(const uint32_t* __restrict__ t_code,
+                                                            const uint32_t* __restrict__ t_row,
+                                                            const uint32_t* __restrict__ t_coeff /*Montgomery*/,
+                                                            uint32_t n_terms, uint32_t n, uint32_t m, PowTable z,
+                                                            unsigned long long* __restrict__ acc /*[3n+m+1][8]*/) {
+  __shared__ uint32_t sm[SV_THREADS / 2][8];
+  sc one_sum[1] = {sc_zero()};
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_terms) {
+    uint32_t code = t_code[t], kind = code >> FLAT_KIND_SHIFT, idx = code & ((1u << FLAT_KIND_SHIFT) - 1);
+    sc c;
+    sc_load(c, t_coeff + (size_t)t * 8);
+    sc v = sc_montmul(c, sc_pow(z, t_row[t] + 1));
+    if (kind == FK_ONE) {
+      one_sum[0] = v;
+    } else if (kind >= FK_LEFT && kind <= FK_COMMITTED) {
+      size_t key = kind == FK_COMMITTED ? (size_t)3 * n + idx : (size_t)(kind - 1) * n + idx;
+      unsigned long long* a = acc + key * 8;
+#pragma unroll
+      for (int j = 0; j < 8; j++) atomicAdd(a + j, (unsigned long long)v.v[j]);
+    }
+  }
+  block_sum_k<1>(one_sum, sm);
+  if (threadIdx.x == 0) {
+    unsigned long long* a = acc + ((size_t)3 * n + m) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (one_sum[0].v[j]) atomicAdd(a + j, (unsigned long long)one_sum[0].v[j]);
+  }
+}
+// counters -> Montgomery residues; keys [0,3n): +, keys [3n, 3n+m]: negated
+__global__ void __launch_bounds__(256) k_flat_finish(const unsigned long long* __restrict__ acc, uint32_t n, uint32_t m,
+                                                      uint32_t* __restrict__ w3 /*[3n][8]: wL | wR | wO*/,
+                                                      uint32_t* __restrict__ wv /*[m+1][8]: wV | wc*/) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t total = 3 * n + m + 1;
+  if (k >= total) return;
+  const unsigned long long* a = acc + (size_t)k * 8;
+  sc lo;
+  unsigned long long carry = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    unsigned long long x = a[j] + carry;  // a[j] < 2^64 - 2^32 in practice: no wrap for < 2^31 terms
+    lo.v[j] = (uint32_t)x;
+    carry = x >> 32;
+  }
+  // value = lo + carry * 2^256, carry < 2^33:  lo mod l  +  carry * (2^256 mod l)
+  sc hi = sc_zero();
+  hi.v[0] = (uint32_t)carry;
+  hi.v[1] = (uint32_t)(carry >> 32);
+  sc r = sc_add(sc_montmul(lo, sc_const(BPG_K(K_R1))), sc_to_mont(hi));
+  if (k >= 3 * n) {
+    sc_store(wv + (size_t)(k - 3 * n) * 8, sc_neg(r));
+  } else {
+    sc_store(w3 + (size_t)k * 8, r);
+  }
+}
+
 }  // namespace bpg
