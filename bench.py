@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--lg-points", type=int, default=20, help="log2 of the points per GPU")
     ap.add_argument("--cpu-sample-lg", type=int, default=18, help="log2 of the CPU-baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-r1cs", action="store_true", help="skip the R1CS prove/verify timing at 2^16 multipliers")
+    ap.add_argument("--r1cs-lg", type=int, default=16)
     return ap.parse_args()
 
 
@@ -231,6 +233,7 @@ def run_b200(args, rank, local_rank, world):
         comb.dev_mul(gen_k.data_ptr(), n, pts_bytes.data_ptr())
         # resident generator-style table: window multiples precomputed once at upload
         table = Table(ctx, dev_ptr=pts_bytes.data_ptr(), n=n).set_windows(0)
+        table_windows = (255 + table.window - 1) // table.window
         scal = [uniform_scalars(n, 0xB2000100 + 1000 * rank + i) for i in range(NSETS_ROT)]
         part = torch.zeros(32, dtype=torch.int32, device=dev)  # this rank's partial sum (extended point)
         parts = torch.zeros(world * 32, dtype=torch.int32, device=dev)
@@ -353,15 +356,21 @@ def run_b200(args, rank, local_rank, world):
             wide = 16 * 504.0 * n  # 16 mixed adds per point x 7 fe_mul x 72 wide MADs
             roof["int32"] = {
                 "achieved_wide_mad_per_s": wide / (ms_step * 1e-3),
-                "kernel_wide_mad_per_s": (n * prof_madds(prof, n) * 504.0) / (acc_ms * 1e-3),
+                # what k_accum really executes: one mixed addition per (point, window) of the table
+                "kernel_wide_mad_per_s": (n * table_windows * 504.0) / (acc_ms * 1e-3),
+                "kernel_frac_of_peak": (n * table_windows * 504.0) / (acc_ms * 1e-3) / (ip["imad_wide_Tops"] * 1e12),
+                "kernel_frac_of_chained_peak": (n * table_windows * 504.0) / (acc_ms * 1e-3) / (ip["imad_wide_x_Tops"] * 1e12),
                 "peak_wide_mad_per_s": ip["imad_wide_Tops"] * 1e12,
                 "frac_of_step": wide / (ms_step * 1e-3) / (ip["imad_wide_Tops"] * 1e12),
                 "peak_kind": "measured (tools/int32_peak, profiles/int32_peak.json)",
             }
-        phases = {k: v[0] / max(v[1], 1) for k, v in prof.items() if v[1]}
+        phases = {k: v[0] / args.steps for k, v in prof.items() if v[1]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(args, pts_bytes, scal[0], n)
+        r1cs = None
+        if world == 1 and not args.no_r1cs:
+            r1cs = r1cs_timing(ctx, comb, args.r1cs_lg, dev)
         line = {
             "metric": METRIC,
             "value": value,
@@ -397,6 +406,7 @@ def run_b200(args, rank, local_rank, world):
             "phases_ms": phases,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "r1cs": r1cs,
             "clocks": clk,
             "result": result_hex,
         }
@@ -406,8 +416,62 @@ def run_b200(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def prof_madds(prof, n):
-    return 16.0  # bucket additions per point charged by SURVEY.md §8d (16-bit windows)
+def r1cs_timing(ctx, comb, lg, dev):
+    """BASELINE.json's other half: R1CS prove / verify wall-clock at 2^lg multipliers through the
+    host mirror's C ABI (bpg_prover_prove / bpg_verifier_verify), on the reference's own benchmark
+    circuit (benches/r1cs.rs:24-32: a chain of squarings).  Host buffers in, proof bytes out."""
+    import torch
+
+    from mpc_bulletproof_b200 import protocol as P
+
+    n = 1 << lg
+
+    def synth(count, seed):
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        k = torch.randint(-(2**31), 2**31, (count, 8), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+        k[:, 7] &= 0x0FFFFFFF
+        out = torch.empty(count * 32, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)
+        comb.dev_mul(k.data_ptr(), count, out.data_ptr())
+        ctx.sync()
+        return bytes(out.cpu().numpy().tobytes())
+
+    gens = P.Gens(ctx, synth(n, 11), synth(n, 12), BASEPOINT, synth(1, 13))
+    val = 0x1234567890ABCDEF1234567890ABCDEF
+    pm, vm = [], []
+    proof = None
+    for it in range(6):
+        p = P.Prover(gens, P.Transcript(b"bench r1cs"))
+        p.square_chain(p.commit_public(val), n)
+        t0 = time.perf_counter()
+        proof = p.prove(1234 + it)
+        pm.append((time.perf_counter() - t0) * 1e3)
+        v = P.Verifier(gens, P.Transcript(b"bench r1cs"))
+        v.square_chain(v.commit_public(val), n)
+        t0 = time.perf_counter()
+        v.verify(proof)
+        vm.append((time.perf_counter() - t0) * 1e3)
+    v = P.Verifier(gens, P.Transcript(b"bench r1cs"))
+    v.square_chain(v.commit_public(val + 1), n)
+    rejected = False
+    try:
+        v.verify(proof)
+    except P.VerificationError:
+        rejected = True
+    gens.close()
+    pm, vm = sorted(pm[1:]), sorted(vm[1:])  # first run warms the pools
+    return {
+        "multipliers": n,
+        "circuit": "chain of squarings (reference benches/r1cs.rs:24-32)",
+        "prove_ms": pm[len(pm) // 2],
+        "verify_ms": vm[len(vm) // 2],
+        "prove_ms_min": pm[0],
+        "verify_ms_min": vm[0],
+        "proof_bytes": len(proof),
+        "false_statement_rejected": rejected,
+        "timed": "bpg_prover_prove / bpg_verifier_verify wall-clock, median of 5 after one warm-up",
+    }
 
 
 def cpu_baseline(args, pts_bytes_dev, scal_dev, n):

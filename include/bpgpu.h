@@ -316,6 +316,9 @@ int bpg_cs_constrain(bpg_cs* cs, const bpg_term* lc, size_t n);
 int bpg_cs_specify_randomized_constraints(bpg_cs* cs, bpg_randomized_cb cb, void* user);
 int bpg_cs_challenge_scalar(bpg_cs* cs, const char* label, uint8_t out[32]); /* only inside a callback */
 int bpg_cs_eval(bpg_cs* cs, const bpg_term* lc, size_t n, uint8_t out[32]);
+/* The reference's benchmark circuit (benches/r1cs.rs:24-32): n chained squarings starting from `var`;
+ * equivalent to n calls of bpg_cs_multiply(var, var).  out (may be NULL) = the last output variable. */
+int bpg_gadget_square_chain(bpg_cs* cs, bpg_var var, size_t n, bpg_var* out);
 size_t bpg_cs_num_multipliers(const bpg_cs* cs);
 size_t bpg_cs_num_constraints(const bpg_cs* cs);
 /* Prover::prove.  The reference draws its blinding scalars from thread_rng()

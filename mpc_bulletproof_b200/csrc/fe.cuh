@@ -224,7 +224,90 @@ BPG_DI fe fe_mul(const fe& A, const fe& B) {
   return fe_reduce512(r);
 }
 
-BPG_DI fe fe_sq(const fe& A) { return fe_mul(A, A); }
+// Dedicated squaring: the 28 cross products a_i a_j (i < j) in the same even/odd column chains,
+// doubled once as a 512-bit shift, plus the 8 squares: 36 + 8 wide multiply-adds instead of 64 + 8.
+// Measured on B200 (tools/scratch/fe_lat.cu): 207 ns against 262 ns for fe_mul(a, a) on a lone
+// warp, 119 against 165 ns per warp at full occupancy.
+BPG_DI fe fe_sq(const fe& A) {
+  const uint32_t* a = A.v;
+  uint32_t e[16], o[16];
+  e[0] = e[1] = 0;
+  e[15] = 0;
+  // i = 0: columns 1..7
+  mul_wide(e[2], e[3], a[0], a[2]);
+  mul_wide(e[4], e[5], a[0], a[4]);
+  mul_wide(e[6], e[7], a[0], a[6]);
+  mul_wide(o[0], o[1], a[0], a[1]);
+  mul_wide(o[2], o[3], a[0], a[3]);
+  mul_wide(o[4], o[5], a[0], a[5]);
+  mul_wide(o[6], o[7], a[0], a[7]);
+  // i = 1: columns 3..8
+  mad_wide_cc(o[2], o[3], a[1], a[2]);
+  madc_wide_cc(o[4], o[5], a[1], a[4]);
+  madc_wide_cc(o[6], o[7], a[1], a[6]);
+  o[8] = addc(0u, 0u);
+  e[8] = 0;
+  mad_wide_cc(e[4], e[5], a[1], a[3]);
+  madc_wide_cc(e[6], e[7], a[1], a[5]);
+  madc_wide_top(e[8], e[9], a[1], a[7]);
+  // i = 2: columns 5..9
+  o[9] = 0;
+  mad_wide_cc(o[4], o[5], a[2], a[3]);
+  madc_wide_cc(o[6], o[7], a[2], a[5]);
+  madc_wide_cc(o[8], o[9], a[2], a[7]);
+  o[10] = addc(0u, 0u);
+  mad_wide_cc(e[6], e[7], a[2], a[4]);
+  madc_wide_cc(e[8], e[9], a[2], a[6]);
+  e[10] = addc(0u, 0u);
+  // i = 3: columns 7..10
+  mad_wide_cc(o[6], o[7], a[3], a[4]);
+  madc_wide_cc(o[8], o[9], a[3], a[6]);
+  o[10] = addc(o[10], 0u);
+  e[11] = 0;
+  mad_wide_cc(e[8], e[9], a[3], a[5]);
+  madc_wide_cc(e[10], e[11], a[3], a[7]);
+  e[12] = addc(0u, 0u);
+  // i = 4: columns 9..11
+  o[11] = 0;
+  mad_wide_cc(o[8], o[9], a[4], a[5]);
+  madc_wide_cc(o[10], o[11], a[4], a[7]);
+  o[12] = addc(0u, 0u);
+  mad_wide_cc(e[10], e[11], a[4], a[6]);
+  e[12] = addc(e[12], 0u);
+  // i = 5: columns 11, 12
+  mad_wide_cc(o[10], o[11], a[5], a[6]);
+  o[12] = addc(o[12], 0u);
+  e[13] = 0;
+  mad_wide_cc(e[12], e[13], a[5], a[7]);
+  e[14] = addc(0u, 0u);
+  // i = 6: column 13
+  o[13] = 0;
+  mad_wide_cc(o[12], o[13], a[6], a[7]);
+  o[14] = addc(0u, 0u);
+  // cross = e + (o << 32), then doubled
+  uint32_t r[16];
+  r[0] = 0;
+  r[1] = o[0];
+  r[2] = add_cc(e[2], o[1]);
+#pragma unroll
+  for (int k = 3; k < 15; k++) r[k] = addc_cc(e[k], o[k - 1]);
+  r[15] = addc(e[15], o[14]);
+#pragma unroll
+  for (int k = 15; k >= 2; k--) r[k] = (r[k] << 1) | (r[k - 1] >> 31);
+  r[1] <<= 1;
+  // + squares
+  uint32_t lo, hi;
+  mul_wide(lo, hi, a[0], a[0]);
+  r[0] = lo;
+  r[1] = add_cc(r[1], hi);
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    mul_wide(lo, hi, a[i], a[i]);
+    r[2 * i] = addc_cc(r[2 * i], lo);
+    r[2 * i + 1] = addc_cc(r[2 * i + 1], hi);
+  }
+  return fe_reduce512(r);
+}
 
 // ---- addition / subtraction -------------------------------------------------
 // loose + loose -> loose.  Carry out of 2^256 folds as +38; a second carry can

@@ -654,6 +654,26 @@ extern "C" int bpg_cs_eval(bpg_cs* cs, const bpg_term* lc, size_t n, uint8_t out
   return BPG_OK;
 }
 
+// The reference's benchmark circuit (benches/r1cs.rs:24-32, DummyCircuit): starting from `var`,
+// n chained squarings  var <- var * var.  Native so that building 2^16 multipliers is not
+// dominated by per-call binding overhead; semantically n calls of bpg_cs_multiply.
+extern "C" int bpg_gadget_square_chain(bpg_cs* cs, bpg_var var, size_t n, bpg_var* out) {
+  if (!cs) return BPG_ERR_ARG;
+  LinComb l(1);
+  l[0].var = var;
+  l[0].coeff = Scalar::one();
+  if (!cs->valid(l)) return BPG_ERR_ARG;
+  bpg_var o[3] = {var, var, var};
+  for (size_t i = 0; i < n; i++) {
+    LinComb a(1), b(1);
+    a[0].var = b[0].var = o[2];
+    a[0].coeff = b[0].coeff = Scalar::one();
+    cs->multiply(std::move(a), std::move(b), o);
+  }
+  if (out) *out = o[2];
+  return BPG_OK;
+}
+
 // ---------------------------------------------------------------- R1CS proof bytes
 struct R1CSProof {
   Bytes32 A_I1, A_O1, S1, A_I2, A_O2, S2, T_1, T_3, T_4, T_5, T_6;

@@ -230,6 +230,13 @@ class _CS:
         )
         return _var(out[0]), _var(out[1]), _var(out[2])
 
+    def square_chain(self, var, n: int):
+        """The reference's DummyCircuit (benches/r1cs.rs:24-32): n chained squarings of `var`."""
+        out = ctypes.c_uint64()
+        idx = var[1] if len(var) > 1 else 0
+        _raise(lib().bpg_gadget_square_chain(self._h, (_KIND[var[0]] << 56) | idx, n, ctypes.byref(out)))
+        return _var(out.value)
+
     def constrain(self, lc):
         arr, n = _terms(lc)
         _raise(lib().bpg_cs_constrain(self._h, arr, n))

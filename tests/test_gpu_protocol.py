@@ -283,3 +283,36 @@ def test_generators_capacity_error(ctx):
         _, _, out = p.multiply(out, out)
     with pytest.raises(P.InvalidGeneratorsLength):
         p.prove(1)
+
+
+def test_square_chain_gadget(ctx, env):
+    """bpg_gadget_square_chain (the reference's bench circuit, benches/r1cs.rs:24-32) is n calls of
+    multiply(var, var): byte-identical proofs, and the oracle accepts them."""
+    from mpc_bulletproof_b200 import protocol as P
+
+    pc, bp, gens = env
+    n, val = 37, 0xDEADBEEF
+
+    def loop(cs):
+        var = cs.commit_public(val)
+        for _ in range(n):
+            _, _, var = cs.multiply(var, var)
+
+    def native(cs):
+        cs.square_chain(cs.commit_public(val), n)
+
+    proofs = []
+    for build in (loop, native):
+        p = P.Prover(gens, P.Transcript(b"chain"))
+        build(p)
+        proofs.append(p.prove(99))
+    assert proofs[0] == proofs[1]
+    for build in (loop, native):
+        v = P.Verifier(gens, P.Transcript(b"chain"))
+        build(v)
+        v.verify(proofs[0])
+    ov = O.Verifier(pc, O.Transcript(b"chain"))
+    var = ov.commit_public(val)
+    for _ in range(n):
+        _, _, var = ov.multiply(var, var)
+    ov.verify(O.R1CSProof.from_bytes(proofs[0]), bp)

@@ -87,9 +87,7 @@ def main():
     t_gens = time.perf_counter() - t0
 
     def build(cs, val):
-        var = cs.commit_public(val)
-        for _ in range(n):
-            _, _, var = cs.multiply(var, var)
+        cs.square_chain(cs.commit_public(val), n)
 
     val = rand_scalars(1, 99)[0]
     prove_ms, verify_ms = [], []
