@@ -521,22 +521,22 @@ def free_port():
 
 def main():
     args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl == "b200":
+        # launched bare: re-launch under torchrun, one rank per GPU (the ranks inherit this stdout)
+        cmd = [
+            sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+            "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.abspath(__file__),
+        ] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd, stdout=sys.stdout.fileno()))
     # Only the JSON line may reach stdout (NCCL and friends print banners there): route fd 1 to
     # stderr for the whole run and keep the real stdout for the final line.
     global _REAL_STDOUT
     sys.stdout.flush()
     _REAL_STDOUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl == "b200":
-        # launched bare: re-launch under torchrun, one rank per GPU
-        cmd = [
-            sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-            "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.abspath(__file__),
-        ] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -136,6 +136,15 @@ int bpg_dev_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t offset, size_
  * either may be NULL. */
 int bpg_dev_sum_encode(bpg_ctx* ctx, const void* d_parts, int n_parts, int n_sets, void* d_out_bytes,
                        void* d_out_ext);
+/* Host-buffer forms of the two halves of a sharded sum: the partial sums of one
+ * rank / one MPC party as extended points (n_sets x 128 bytes: X|Y|Z|T, 32 bytes LE each), and
+ * the combine step  out[s] = encode(sum_p parts[p][s])  once the partials have been exchanged
+ * (parts laid out [part][set]).  For the MPC prover (reference src/r1cs_mpc/mpc_prover.rs:621-657)
+ * a party's additive share of the scalars gives its additive share of the commitment; "open" is
+ * the exchange plus bpg_sum_encode. */
+int bpg_msm_table_partial(bpg_ctx* ctx, const bpg_table* table, size_t offset, size_t n, const uint8_t* scalars_le,
+                          int n_sets, uint8_t* out_ext);
+int bpg_sum_encode(bpg_ctx* ctx, const uint8_t* parts_ext, int n_parts, int n_sets, uint8_t* out);
 
 /* ---- inner-product argument --------------------------------------------------------
  * Device-resident state for `InnerProductProof::create` (reference
@@ -327,6 +336,12 @@ size_t bpg_cs_num_constraints(const bpg_cs* cs);
 int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
 /* Verifier::verify: BPG_OK, BPG_ERR_VERIFY, BPG_ERR_DECODE (FormatError), BPG_ERR_CAPACITY */
 int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof, size_t proof_len);
+/* Many proofs, proof by proof as the reference does (verifier.rs:393); every verifier is consumed.
+ * ok[i] = 1 iff proof i verifies (a malformed proof is a reject).  Non-zero return only for
+ * failures of the machinery.  Across GPUs whole proofs are sharded by the caller (one context
+ * per GPU); there is no data-path collective. */
+int bpg_batch_verify(bpg_cs* const* verifiers, const uint8_t* const* proofs, const size_t* proof_lens, size_t n,
+                     uint8_t* ok);
 
 #ifdef __cplusplus
 }

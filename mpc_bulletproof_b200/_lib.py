@@ -72,6 +72,7 @@ _SIGNATURES = {
     "bpg_cs_num_constraints": (_SZ, [_P]),
     "bpg_prover_prove": (_I, [_P, _U64, _P, _SZ, ctypes.POINTER(_SZ)]),
     "bpg_verifier_verify": (_I, [_P, _P, _SZ]),
+    "bpg_batch_verify": (_I, [_P, _P, _P, _SZ, _P]),
     "bpg_init": (_I, [_I, ctypes.POINTER(_P)]),
     "bpg_free": (None, [_P]),
     "bpg_set_stream": (_I, [_P, _P, _I]),
@@ -97,6 +98,8 @@ _SIGNATURES = {
     "bpg_msm_mixed": (_I, [_P, _P, _SZ, _P, _P, _P, _I, _P, _P]),
     "bpg_dev_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),
     "bpg_dev_sum_encode": (_I, [_P, _P, _I, _I, _P, _P]),
+    "bpg_msm_table_partial": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),
+    "bpg_sum_encode": (_I, [_P, _P, _I, _I, _P]),
     "bpg_ipp_begin": (_I, [_P, _P, _SZ, _P, _SZ, _SZ, _P, _P, _P, _P, _P, ctypes.POINTER(_P)]),
     "bpg_ipp_begin_dev": (_I, [_P, _P, _SZ, _P, _SZ, _SZ, _P, _P, _P, _P, _P, ctypes.POINTER(_P)]),
     "bpg_ipp_begin_shared": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _SZ, _P, _P, _P, _P, ctypes.POINTER(_P)]),

@@ -114,6 +114,17 @@ class Table:
         check(lib().bpg_msm_table(self.ctx._h, self._h, offset, n, scalars, n_sets, out))
         return [out.raw[32 * i : 32 * i + 32] for i in range(n_sets)]
 
+    def msm_partial(self, scalars: bytes, n_sets: int = 1, offset: int = 0, n: int | None = None) -> bytes:
+        """The sums as extended points (n_sets x 128 bytes), not encoded: one rank's / one MPC party's
+        partial result, to be combined with `sum_encode` after the exchange."""
+        if n is None:
+            n = len(self) - offset
+        if len(scalars) != 32 * n * n_sets:
+            raise _lib.BpgError(_lib.BPG_ERR_LEN, "scalar buffer length does not match n * n_sets")
+        out = ctypes.create_string_buffer(128 * n_sets)
+        check(lib().bpg_msm_table_partial(self.ctx._h, self._h, offset, n, scalars, n_sets, out))
+        return out.raw
+
     def dev_msm(self, d_scalars: int, n_sets: int, d_out_ext: int, offset: int = 0, n: int | None = None):
         """Device-resident form; enqueues on the context's stream."""
         if n is None:
@@ -132,6 +143,15 @@ def msm(ctx: Context, scalars: bytes, points: bytes) -> bytes:
     out = ctypes.create_string_buffer(32)
     check(lib().bpg_msm(ctx._h, scalars, points, len(scalars) // 32, out))
     return out.raw
+
+
+def sum_encode(ctx: Context, parts: bytes, n_parts: int, n_sets: int = 1) -> list[bytes]:
+    """out[s] = encode(sum_p parts[p][s]) for partial sums laid out [part][set] x 128 bytes."""
+    if len(parts) != 128 * n_parts * n_sets:
+        raise _lib.BpgError(_lib.BPG_ERR_LEN, "partials buffer length is not n_parts * n_sets * 128")
+    out = ctypes.create_string_buffer(32 * n_sets)
+    check(lib().bpg_sum_encode(ctx._h, parts, n_parts, n_sets, out))
+    return [out.raw[32 * i : 32 * i + 32] for i in range(n_sets)]
 
 
 def dev_sum_encode(ctx: Context, d_parts: int, n_parts: int, n_sets: int, d_out_bytes: int | None, d_out_ext: int | None = None):

@@ -589,6 +589,43 @@ extern "C" int bpg_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t offset
   return BPG_OK;
 }
 
+// Partial sums for a caller that combines them itself (a rank of a sharded MSM, a party of the
+// MPC prover working on its share): out_ext = n_sets extended points (X|Y|Z|T, 4 x 32 bytes LE).
+extern "C" int bpg_msm_table_partial(bpg_ctx* ctx, const bpg_table* table, size_t offset, size_t n,
+                                     const uint8_t* scalars_le, int n_sets, uint8_t* out_ext) {
+  if (!ctx || !table || !out_ext || (!scalars_le && n) || n_sets <= 0) return BPG_ERR_ARG;
+  if ((size_t)n_sets * 128 > SMALL_BYTES) return BPG_ERR_ARG;
+  if (offset + n > table->n) return BPG_ERR_CAPACITY;
+  CK(cudaSetDevice(ctx->device));
+  size_t sbytes = n * (size_t)n_sets * 32;
+  int rc = ensure_stage(ctx, std::max<size_t>(sbytes, 32));
+  if (rc) return rc;
+  if (sbytes) CK(cudaMemcpyAsync(ctx->d_stage, scalars_le, sbytes, cudaMemcpyHostToDevice, ctx->stream));
+  uint32_t* d_ext = (uint32_t*)ctx->d_small;
+  rc = msm_enqueue(ctx, table->niels + offset * 24, n, (const uint32_t*)ctx->d_stage, n * (size_t)n_sets, nullptr,
+                   nullptr, n_sets, d_ext, table->win_c, table->n);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->h_pinned, d_ext, (size_t)n_sets * 128, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(out_ext, ctx->h_pinned, (size_t)n_sets * 128);
+  return BPG_OK;
+}
+// out[s] = encode(sum_p parts[p][s]): the combine step after the ranks' / parties' partial sums met
+extern "C" int bpg_sum_encode(bpg_ctx* ctx, const uint8_t* parts_ext, int n_parts, int n_sets, uint8_t* out) {
+  if (!ctx || !parts_ext || !out || n_parts <= 0 || n_sets <= 0) return BPG_ERR_ARG;
+  size_t in_bytes = (size_t)n_parts * n_sets * 128, out_bytes = (size_t)n_sets * 32;
+  if (in_bytes + out_bytes > SMALL_BYTES) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  memcpy(ctx->h_pinned, parts_ext, in_bytes);
+  CK(cudaMemcpyAsync(ctx->d_small, ctx->h_pinned, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = bpg_dev_sum_encode(ctx, ctx->d_small, n_parts, n_sets, ctx->d_small + in_bytes, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_small + in_bytes, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->h_pinned, out_bytes);
+  return BPG_OK;
+}
+
 extern "C" int bpg_msm(bpg_ctx* ctx, const uint8_t* scalars_le, const uint8_t* points_compressed, size_t n,
                        uint8_t out[32]) {
   if (!ctx || !out || ((!scalars_le || !points_compressed) && n)) return BPG_ERR_ARG;

@@ -984,3 +984,19 @@ extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_
   if (rc) return rc;
   return is_identity_enc(mega) ? BPG_OK : BPG_ERR_VERIFY;  // :549
 }
+
+// Batch verification (BASELINE.json config 4): the reference verifies proof by proof
+// (`Verifier::verify`, verifier.rs:393), so per-proof accept/reject is the parity surface.  Every
+// verifier is consumed.  ok[i] = 1 iff proof i verifies; a malformed proof is a reject, not an
+// error.  Returns non-zero only for failures of the machinery (bad handle, CUDA, memory).
+extern "C" int bpg_batch_verify(bpg_cs* const* verifiers, const uint8_t* const* proofs, const size_t* proof_lens,
+                                size_t n, uint8_t* ok) {
+  if (n && (!verifiers || !proofs || !proof_lens || !ok)) return BPG_ERR_ARG;
+  for (size_t i = 0; i < n; i++) {
+    int rc = bpg_verifier_verify(verifiers[i], proofs[i], proof_lens[i]);
+    if (rc == BPG_OK) ok[i] = 1;
+    else if (rc == BPG_ERR_VERIFY || rc == BPG_ERR_DECODE || rc == BPG_ERR_CAPACITY) ok[i] = 0;
+    else return rc;
+  }
+  return BPG_OK;
+}

@@ -328,3 +328,22 @@ class Verifier(_CS):
         code = lib().bpg_verifier_verify(self._h, proof, len(proof))
         self._reraise()
         _raise(code)
+
+
+def batch_verify(jobs) -> list[bool]:
+    """jobs: [(Verifier with its constraint system built, proof bytes), ...] -> per-proof accept.
+    The reference verifies proof by proof (verifier.rs:393); so does this, in one library call.
+    Across GPUs shard the jobs with `multi.batch_verify_sharded`."""
+    n = len(jobs)
+    if n == 0:
+        return []
+    hs = (ctypes.c_void_p * n)(*[v._h for v, _ in jobs])
+    bufs = [ctypes.create_string_buffer(p, len(p)) for _, p in jobs]
+    ptrs = (ctypes.c_void_p * n)(*[ctypes.cast(b, ctypes.c_void_p) for b in bufs])
+    lens = (ctypes.c_size_t * n)(*[len(p) for _, p in jobs])
+    ok = ctypes.create_string_buffer(n)
+    code = lib().bpg_batch_verify(hs, ptrs, lens, n, ok)
+    for v, _ in jobs:
+        v._reraise()
+    _raise(code)
+    return [b != 0 for b in ok.raw]

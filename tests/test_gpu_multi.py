@@ -1,0 +1,109 @@
+"""GPU parity of the multi-GPU building blocks on ONE device (the driver's GPU box has one):
+partial sums + combine (the two halves of a stride-sharded MSM), the MPC open of additive
+shares (reference src/r1cs_mpc/mpc_prover.rs:621-657: msm_authenticated_iter on shares, then
+open), and batch verification.  The two-rank exchange itself is covered on the CPU by
+tests/test_multi_gloo.py and on two B200s by tools/multi_gpu_check.py."""
+import pytest
+
+from oracle import gadgets
+from oracle import group as G
+from oracle import protocol as O
+from tests.util import points_bytes, rand_point, rand_scalar, rng, scalars_bytes
+
+pytestmark = pytest.mark.gpu
+L = G.L
+
+
+def test_partials_combine_like_two_ranks(ctx):
+    from mpc_bulletproof_b200 import Table, multi
+    from mpc_bulletproof_b200.api import sum_encode
+
+    r = rng(301)
+    n, sets, world = 301, 2, 2
+    ps = [rand_point(r) for _ in range(n)]
+    ks = [[rand_scalar(r) for _ in range(n)] for _ in range(sets)]
+    parts = b""
+    for rank in range(world):
+        mine = list(multi.shard_indices(n, rank, world))
+        t = Table(ctx, points_bytes([ps[i] for i in mine])).set_windows(0)
+        parts += t.msm_partial(b"".join(scalars_bytes([k[i] for i in mine]) for k in ks), n_sets=sets)
+        t.close()
+    got = sum_encode(ctx, parts, world, sets)
+    assert got == [G.msm(k, ps).encode() for k in ks]
+    # world = 1 degenerates to the plain MSM through the same engine interface
+    t = Table(ctx, points_bytes(ps))
+    eng = multi.CudaEngine(ctx, t)
+    assert multi.sharded_msm(eng, b"".join(scalars_bytes(k) for k in ks), n_sets=sets) == got
+    t.close()
+
+
+def test_mpc_open_of_shares(ctx):
+    """Each party commits to its additive share (and its MAC share) of a_L, a_R and the blinding
+    over the shared generators; opening adds the parties' partial sums.  The result must be the
+    single prover's A_I (prover.rs:465-475) and key * A_I."""
+    from mpc_bulletproof_b200 import Table
+    from mpc_bulletproof_b200.api import sum_encode
+
+    r = rng(302)
+    n = 64
+    bp, pc = O.BulletproofGens(n, 1), O.PedersenGens()
+    pts = bp.G(n) + bp.H(n) + [pc.B_blinding]
+    t = Table(ctx, points_bytes(pts)).set_windows(0)
+    aL = [r.randrange(2) for _ in range(n)]  # bits, as in the range gadget
+    aR = [(x - 1) % L for x in aL]
+    blind, key = rand_scalar(r), rand_scalar(r)
+    plain = aL + aR + [blind]
+    s0 = [rand_scalar(r) for _ in plain]
+    m0 = [rand_scalar(r) for _ in plain]
+    shares = [s0, [(x - a) % L for x, a in zip(plain, s0)]]
+    macs = [m0, [(key * x - a) % L for x, a in zip(plain, m0)]]
+    parts = b"".join(t.msm_partial(scalars_bytes(shares[p]) + scalars_bytes(macs[p]), n_sets=2) for p in range(2))
+    opened = sum_encode(ctx, parts, 2, 2)
+    A_I = G.msm(plain, pts)
+    assert opened[0] == A_I.encode()
+    assert opened[1] == (key * A_I).encode()
+    # and it is what the single-prover path computes for the same vectors
+    assert t.msm(scalars_bytes(plain))[0] == A_I.encode()
+    t.close()
+
+
+def test_batch_verify(ctx):
+    from mpc_bulletproof_b200 import protocol as P
+    from mpc_bulletproof_b200.protocol import Gens
+
+    pc = O.PedersenGens()
+    bp = O.BulletproofGens(64, 1)
+    gens = Gens(ctx, points_bytes(bp.G(64)), points_bytes(bp.H(64)), pc.B.encode(), pc.B_blinding.encode())
+
+    def circuit(cs, val, n):
+        cs.square_chain(cs.commit_public(val), n)
+
+    cases = [(5, 9), (7, 33), (11, 16), (13, 1)]
+    proofs = []
+    for val, n in cases:
+        p = P.Prover(gens, P.Transcript(b"batch"))
+        circuit(p, val, n)
+        proofs.append(p.prove(1000 + n))
+    bad = bytearray(proofs[1])
+    bad[40] ^= 1
+    jobs, want = [], []
+    for k, (val, n) in enumerate(cases):
+        v = P.Verifier(gens, P.Transcript(b"batch"))
+        circuit(v, val, n)
+        jobs.append((v, proofs[k]))
+        want.append(True)
+    v = P.Verifier(gens, P.Transcript(b"batch"))  # tampered proof
+    circuit(v, *cases[1])
+    jobs.append((v, bytes(bad)))
+    want.append(False)
+    v = P.Verifier(gens, P.Transcript(b"batch"))  # wrong statement
+    circuit(v, cases[2][0] + 1, cases[2][1])
+    jobs.append((v, proofs[2]))
+    want.append(False)
+    v = P.Verifier(gens, P.Transcript(b"batch"))  # truncated bytes: FormatError in the reference, a reject here
+    circuit(v, *cases[0])
+    jobs.append((v, proofs[0][:-7]))
+    want.append(False)
+    assert P.batch_verify(jobs) == want
+    assert P.batch_verify([]) == []
+    gens.close()
