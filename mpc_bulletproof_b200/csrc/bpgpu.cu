@@ -419,10 +419,12 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   if ((uint64_t)cfg.narr * cfg.nb >= (1ull << 31)) return BPG_ERR_ARG;
   const bool windowed = cfg.win_stride != 0;
 
-  // reduction geometry: `rarr` arrays of nb buckets; a leaf block takes RT_QUADS chunks of LC buckets
+  // reduction geometry: `rarr` arrays of nb buckets.  Small arrays: a leaf block of RT_QUADS quad
+  // chunks of LC buckets plus its in-block tree; large arrays: one thread per chunk of 16.
   uint32_t rarr = windowed ? (uint32_t)nsets : cfg.narr;
-  const uint32_t LC = cfg.nb > (1u << 17) ? 32 : (cfg.nb > (1u << 15) ? 8 : 4);
-  uint32_t tiles0 = (cfg.nb + RT_QUADS * LC - 1) / (RT_QUADS * LC);
+  const bool thread_leaf = cfg.nb >= (1u << 17);
+  const uint32_t LC = thread_leaf ? 16 : (cfg.nb > (1u << 15) ? 8 : 4);
+  uint32_t tiles0 = thread_leaf ? (cfg.nb + LC - 1) / LC : (cfg.nb + RT_QUADS * LC - 1) / (RT_QUADS * LC);
   size_t ntiles = (cfg.B + SCAN_TILE - 1) / SCAN_TILE;
   size_t off = 0;
   size_t o_counts = off;  off += align_up((size_t)cfg.B * 4);
@@ -521,13 +523,18 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
     uint32_t* pa[2] = {pairs, pairs + 2 * pair_words};
     int cur = 0;
     uint32_t* oa = t == 1 ? final_out : pa[cur];
-    if (LC == 32) k_reduce_leaf<32><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
-    else if (LC == 8) k_reduce_leaf<8><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
-    else k_reduce_leaf<4><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
+    if (thread_leaf) {
+      k_reduce_leaf_thread<16><<<(rarr * t + RL_THREADS - 1) / RL_THREADS, RL_THREADS, 0, st>>>(level0, cfg.nb, t, rarr, oa,
+                                                                                               pa[cur] + pair_words);
+    } else if (LC == 8) {
+      k_reduce_leaf<8><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
+    } else {
+      k_reduce_leaf<4><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
+    }
     LAUNCH_CHECK();
     while (t > 1) {
       uint32_t n = t;
-      t = (n + RP_THREADS / 4 - 1) / (RP_THREADS / 4);
+      t = (n + RP_PAIRS - 1) / RP_PAIRS;
       const uint32_t* ia = pa[cur];
       const uint32_t* iy = pa[cur] + pair_words;
       cur ^= 1;

@@ -50,23 +50,26 @@ constexpr uint32_t ENTRY_NEG = 0x80000000u;
 // ---------------------------------------------------------------------------
 // digits -> histogram
 // ---------------------------------------------------------------------------
+// Warp-aggregated: lanes whose digit lands in the same bucket (structured scalars: bit vectors,
+// repeated values, the short top window) issue ONE atomic for the group.
 __global__ void __launch_bounds__(256) k_hist(const uint32_t* __restrict__ scalars,
                                               const uint8_t* __restrict__ set_ids, MsmCfg cfg,
                                               uint32_t* __restrict__ counts) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= cfg.n_terms) return;
-  sc k;
-  sc_load(k, scalars + (size_t)t * 8);
+  const bool valid = t < cfg.n_terms;
+  const uint32_t lane = threadIdx.x & 31;
+  sc k = sc_zero();
+  if (valid) sc_load(k, scalars + (size_t)t * 8);
   sc_recoded r = sc_recode(k.v, cfg.bias);
-  uint32_t set = set_ids ? set_ids[t] : t / cfg.n_points;
+  uint32_t set = valid ? (set_ids ? set_ids[t] : t / cfg.n_points) : 0;
   uint32_t base = set * cfg.gsub * cfg.nb;
   uint32_t g = 0;
   for (int w = 0; w < cfg.W; w++) {
-    int d = sc_digit(r, w, cfg.c);
-    if (d != 0) {
-      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      atomicAdd(&counts[base + g * cfg.nb + mag - 1], 1u);
-    }
+    int d = valid ? sc_digit(r, w, cfg.c) : 0;
+    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    uint32_t b = base + g * cfg.nb + mag - 1;
+    uint32_t peers = __match_any_sync(0xffffffffu, d != 0 ? b : 0xffffffffu - lane);
+    if (d != 0 && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&counts[b], (uint32_t)__popc(peers));
     g = g + 1 == cfg.gsub ? 0 : g + 1;
   }
 }
@@ -177,20 +180,27 @@ __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ sc
                                                  const uint32_t* __restrict__ offsets,
                                                  uint32_t* __restrict__ cursors, uint32_t* __restrict__ entries) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= cfg.n_terms) return;
-  sc k;
-  sc_load(k, scalars + (size_t)t * 8);
+  const bool valid = t < cfg.n_terms;
+  const uint32_t lane = threadIdx.x & 31;
+  sc k = sc_zero();
+  if (valid) sc_load(k, scalars + (size_t)t * 8);
   sc_recoded r = sc_recode(k.v, cfg.bias);
-  uint32_t set = set_ids ? set_ids[t] : t / cfg.n_points;
-  uint32_t pid = point_ids ? point_ids[t] : t % cfg.n_points;
+  uint32_t set = valid ? (set_ids ? set_ids[t] : t / cfg.n_points) : 0;
+  uint32_t pid = valid ? (point_ids ? point_ids[t] : t % cfg.n_points) : 0;
   uint32_t base = set * cfg.gsub * cfg.nb;
   uint32_t g = 0;
   for (int w = 0; w < cfg.W; w++) {
-    int d = sc_digit(r, w, cfg.c);
+    int d = valid ? sc_digit(r, w, cfg.c) : 0;
+    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    uint32_t b = base + g * cfg.nb + mag - 1;
+    // one cursor atomic per group of lanes that share the bucket; the group's lanes take consecutive slots
+    uint32_t peers = __match_any_sync(0xffffffffu, d != 0 ? b : 0xffffffffu - lane);
+    uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+    uint32_t first = 0;
+    if (d != 0 && lane == leader) first = atomicAdd(&cursors[b], (uint32_t)__popc(peers));
+    first = __shfl_sync(0xffffffffu, first, leader);
     if (d != 0) {
-      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      uint32_t b = base + g * cfg.nb + mag - 1;
-      uint32_t pos = offsets[b] + atomicAdd(&cursors[b], 1u);
+      uint32_t pos = offsets[b] + first + (uint32_t)__popc(peers & ((1u << lane) - 1u));
       entries[pos] = (pid + (uint32_t)w * cfg.win_stride) | (d < 0 ? ENTRY_NEG : 0u);
     }
     g = g + 1 == cfg.gsub ? 0 : g + 1;
@@ -595,16 +605,63 @@ __global__ void __launch_bounds__(RT_THREADS) k_reduce_leaf(const uint32_t* __re
   }
 }
 
-// up to RP_THREADS/4 = 128 pairs per block -> one pair (the final launch has tiles == 1 and writes T to out_a)
-constexpr int RP_THREADS = 512;
+// Large bucket arrays (>= 2^17): the leaf pass is throughput-bound, so ONE THREAD owns a chunk
+// (8 + 9 multiplications per bucket instead of five quad levels) and writes its pair; the
+// binary tree over the pairs is k_reduce_pairs.
+constexpr int RL_THREADS = 128;
+// p + q with q in the cached layout (Y-X, Y+X, 2Z, 2dT): 8 multiplications
+__device__ __forceinline__ ge_ext ge_add_cached(const ge_ext& p, const fe& ymx, const fe& ypx, const fe& z2,
+                                                const fe& t2d) {
+  fe A = fe_mul(fe_sub(p.Y, p.X), ymx);
+  fe B = fe_mul(fe_add_nc(p.Y, p.X), ypx);
+  fe C = fe_mul(p.T, t2d);
+  fe D = fe_mul(p.Z, z2);
+  fe E = fe_sub(B, A), H = fe_add_nc(B, A), F = fe_sub(D, C), G = fe_add(D, C);
+  ge_ext r;
+  r.X = fe_mul(E, F);
+  r.Y = fe_mul(G, H);
+  r.Z = fe_mul(F, G);
+  r.T = fe_mul(E, H);
+  return r;
+}
+template <int LC>
+__global__ void __launch_bounds__(RL_THREADS) k_reduce_leaf_thread(const uint32_t* __restrict__ in /*[narr][n] cached*/,
+                                                                   uint32_t n, uint32_t chunks /*per array*/,
+                                                                   uint32_t narr, uint32_t* __restrict__ out_a,
+                                                                   uint32_t* __restrict__ out_y) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= narr * chunks) return;
+  uint32_t arr = t / chunks, q = t % chunks;
+  uint32_t first = q * LC;
+  int valid = (int)min((uint32_t)LC, n - first);  // chunks = ceil(n / LC): first < n
+  const uint32_t* src = in + ((size_t)arr * n + first) * 32;
+  ge_ext run = ge_identity(), acc = ge_identity();
+  for (int k = valid - 1; k >= 0; k--) {
+    fe ymx, ypx, z2, t2d;
+    fe_load(ymx, src + (size_t)k * 32);
+    fe_load(ypx, src + (size_t)k * 32 + 8);
+    fe_load(z2, src + (size_t)k * 32 + 16);
+    fe_load(t2d, src + (size_t)k * 32 + 24);
+    run = ge_add_cached(run, ymx, ypx, z2, t2d);
+    acc = ge_add(acc, run);
+  }
+#pragma unroll
+  for (int i = 1; i < LC; i <<= 1) run = ge_dbl(run);
+  ge_store_ext(out_a + (size_t)t * 32, acc);
+  ge_store_ext(out_y + (size_t)t * 32, run);
+}
+
+// up to RP_THREADS/2 = 64 pairs per block -> one pair (the final launch has tiles == 1 and writes T to out_a)
+constexpr int RP_THREADS = 128;
+constexpr uint32_t RP_PAIRS = RP_THREADS / 2;
 __global__ void __launch_bounds__(RP_THREADS) k_reduce_pairs(const uint32_t* __restrict__ in_a,
                                                               const uint32_t* __restrict__ in_y, uint32_t n,
                                                               uint32_t tiles, uint32_t* __restrict__ out_a,
                                                               uint32_t* __restrict__ out_y) {
-  __shared__ uint32_t sa[RP_THREADS / 4][32], sy[RP_THREADS / 4][32];
+  __shared__ uint32_t sa[RP_PAIRS][32], sy[RP_PAIRS][32];
   uint32_t arr = blockIdx.x / tiles, tile = blockIdx.x % tiles;
-  uint32_t first = tile * (RP_THREADS / 4);
-  uint32_t m = min((uint32_t)(RP_THREADS / 4), n - first);
+  uint32_t first = tile * RP_PAIRS;
+  uint32_t m = min(RP_PAIRS, n - first);
   const uint32_t* ga = in_a + ((size_t)arr * n + first) * 32;
   const uint32_t* gy = in_y + ((size_t)arr * n + first) * 32;
   for (uint32_t w = threadIdx.x; w < m * 32; w += blockDim.x) {
