@@ -231,11 +231,16 @@ void bpg_r1cs_dev_free(bpg_r1cs_dev* st);
 /* grow to `capacity` rows keeping a_L, a_R, a_O, s_L, s_R (second-phase multipliers, prover.rs:501-530) */
 int bpg_r1cs_dev_reserve(bpg_r1cs_dev** st, size_t capacity);
 /* (A_I, A_O, S) of one phase over gens[first .. first+cnt) (prover.rs:465-494, 532-565):
- * aL/aR/aO Montgomery rows, raw_sL/raw_sR the 64-byte uniform blocks the blinding scalars are
- * reduced from (on the device), blind3 = i_blinding, o_blinding, s_blinding (canonical). */
+ * aL/aR/aO Montgomery rows; the blinding vectors s_L, s_R are generated on the device as the
+ * consecutive 64-byte blocks s_L[0], s_R[0], s_L[1], ... of the SplitMix64 stream keyed by
+ * vec_key, each reduced mod l; blind3 = i_blinding, o_blinding, s_blinding (canonical). */
 int bpg_r1cs_dev_commit(bpg_r1cs_dev* st, const bpg_table* gens, size_t g_base, size_t h_base, size_t bb_id,
-                        size_t first, size_t cnt, const void* aL, const void* aR, const void* aO, const void* raw_sL,
-                        const void* raw_sR, const uint8_t blind3[96], uint8_t out[96]);
+                        size_t first, size_t cnt, const void* aL, const void* aR, const void* aO, uint64_t vec_key,
+                        const uint8_t blind3[96], uint8_t out[96]);
+/* Page-locked host memory for buffers the library reads repeatedly (witness rows, constraint
+ * terms): uploads from it run at PCIe rate.  Falls back to malloc when pinning fails. */
+void* bpg_host_alloc(size_t bytes);
+void bpg_host_free(void* p);
 /* flattened_constraints (prover.rs:342-379, verifier.rs:323-362) as a sparse product on the
  * device: term t of constraint row t_row[t] names variable t_code[t] = kind << 28 | index
  * (kinds 1 left, 2 right, 3 output, 4 committed, 5 constant one) with coefficient t_coeff[t]

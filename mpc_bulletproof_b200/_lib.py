@@ -112,7 +112,9 @@ _SIGNATURES = {
     "bpg_r1cs_dev_free": (None, [_P]),
     "bpg_r1cs_dev_reserve": (_I, [ctypes.POINTER(_P), _SZ]),
     "bpg_ipp_verify_msm": (_I, [_P, _P, _SZ, _P, _SZ, _P, _P, _SZ, _P, _P, _P, _P]),
-    "bpg_r1cs_dev_commit": (_I, [_P, _P, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _P, _P, _P, _P]),
+    "bpg_r1cs_dev_commit": (_I, [_P, _P, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, ctypes.c_uint64, _P, _P]),
+    "bpg_host_alloc": (_P, [_SZ]),
+    "bpg_host_free": (None, [_P]),
     "bpg_r1cs_dev_flatten": (_I, [_P, _SZ, _SZ, _SZ, _P, _P, _P, _P, _P]),
     "bpg_r1cs_dev_poly_t": (_I, [_P, _SZ, _P, _P, _P]),
     "bpg_r1cs_dev_verify_msm": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _P, _SZ, _P, _P, _P]),

@@ -35,9 +35,14 @@ struct bpg_ctx {
   size_t prof_used = 0;
   double prof_ms[BPG_PROF_NPHASE] = {0};
   uint64_t prof_n[BPG_PROF_NPHASE] = {0};
-  // workspace arena (grown on demand, reused across calls)
+  // workspace arenas (grown on demand, reused across calls): [0] for the launch stream, [1] for the
+  // auxiliary stream that runs a small independent MSM beside the main one (verifier: proof points)
   uint8_t* ws = nullptr;
   size_t ws_cap = 0;
+  uint8_t* ws_aux = nullptr;
+  size_t ws_aux_cap = 0;
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // small staging buffers
   uint8_t* d_small = nullptr;   // device scratch for results (>= 64 KB)
   uint8_t* h_pinned = nullptr;  // pinned host scratch (>= 64 KB)
@@ -101,6 +106,9 @@ extern "C" int bpg_init(int device, bpg_ctx** out) {
   ctx->device = device;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_small, SMALL_BYTES);
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_pinned, SMALL_BYTES);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -128,7 +136,12 @@ extern "C" void bpg_free(bpg_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->ws_aux) cudaFree(ctx->ws_aux);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->d_small) cudaFree(ctx->d_small);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -207,6 +220,26 @@ extern "C" int bpg_set_window(bpg_ctx* ctx, int c) {
   return BPG_OK;
 }
 
+// Page-locked host buffers (tagged so that bpg_host_free knows how each was obtained)
+extern "C" void* bpg_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  size_t total = bytes + 64;
+  bool pinned = cudaHostAlloc(&p, total, cudaHostAllocDefault) == cudaSuccess;
+  if (!pinned) {
+    cudaGetLastError();
+    p = malloc(total);
+    if (!p) return nullptr;
+  }
+  *reinterpret_cast<uint64_t*>(p) = pinned ? 0x50494e4eull : 0x4d414c4cull;
+  return static_cast<uint8_t*>(p) + 64;
+}
+extern "C" void bpg_host_free(void* q) {
+  if (!q) return;
+  uint8_t* p = static_cast<uint8_t*>(q) - 64;
+  if (*reinterpret_cast<uint64_t*>(p) == 0x50494e4eull) cudaFreeHost(p);
+  else free(p);
+}
+
 extern "C" int bpg_set_groups(bpg_ctx* ctx, int gsub) {
   if (!ctx || gsub < 0 || gsub > 128) return BPG_ERR_ARG;
   ctx->forced_gsub = gsub;
@@ -228,20 +261,22 @@ extern "C" const char* bpg_strerror(int code) {
   }
 }
 
-static int ensure_ws(bpg_ctx* ctx, size_t bytes) {
-  if (bytes <= ctx->ws_cap) return BPG_OK;
+static int ensure_ws(bpg_ctx* ctx, size_t bytes, int lane = 0) {
+  uint8_t*& ws = lane ? ctx->ws_aux : ctx->ws;
+  size_t& cap = lane ? ctx->ws_aux_cap : ctx->ws_cap;
+  if (bytes <= cap) return BPG_OK;
   // the arena may still be in use by enqueued work
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (ctx->ws) cudaFree(ctx->ws);
-  ctx->ws = nullptr;
-  ctx->ws_cap = 0;
+  CK(cudaStreamSynchronize(lane ? ctx->aux_stream : ctx->stream));
+  if (ws) cudaFree(ws);
+  ws = nullptr;
+  cap = 0;
   size_t want = bytes + bytes / 8;
-  cudaError_t e = cudaMalloc(&ctx->ws, want);
+  cudaError_t e = cudaMalloc(&ws, want);
   if (e != cudaSuccess) {
     ctx->last_cuda = (int)e;
     return e == cudaErrorMemoryAllocation ? BPG_ERR_NOMEM : BPG_ERR_CUDA;
   }
-  ctx->ws_cap = want;
+  cap = want;
   return BPG_OK;
 }
 static int ensure_stage(bpg_ctx* ctx, size_t bytes) {
@@ -400,16 +435,21 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 // be null (implicit: term t -> point t % n_points of `table_base`, set t / n_points).
 static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points, const uint32_t* d_scalars,
                        size_t n_terms, const uint8_t* d_set_ids, const uint32_t* d_point_ids, int nsets,
-                       uint32_t* d_out_ext, int win_c = 0, size_t win_stride = 0) {
+                       uint32_t* d_out_ext, int win_c = 0, size_t win_stride = 0, int lane = 0) {
   if (nsets <= 0) return BPG_ERR_ARG;
+  // lane 1: the auxiliary stream and arena (no phase profiling there)
+  struct ProfOff {
+    bpg_ctx* c;
+    bool saved;
+    ProfOff(bpg_ctx* c_, bool off) : c(c_), saved(c_->prof) { if (off) c->prof = false; }
+    ~ProfOff() { c->prof = saved; }
+  } prof_off(ctx, lane != 0);
+  cudaStream_t st = lane ? ctx->aux_stream : ctx->stream;
+  uint8_t* const& ws = lane ? ctx->ws_aux : ctx->ws;
   if (n_terms == 0) {
     // empty sum: identity for every set
-    std::vector<uint32_t> id(32 * (size_t)nsets, 0);
-    for (int s = 0; s < nsets; s++) id[32 * s + 8] = id[32 * s + 16] = 1;
-    if ((size_t)nsets * 128 > SMALL_BYTES) return BPG_ERR_ARG;
-    memcpy(ctx->h_pinned, id.data(), id.size() * 4);
-    CK(cudaMemcpyAsync(d_out_ext, ctx->h_pinned, id.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    k_set_identity<<<nsets, 32, 0, st>>>(d_out_ext);
+    LAUNCH_CHECK();
     return BPG_OK;
   }
   if (n_terms >= (1u << 31)) return BPG_ERR_ARG;
@@ -445,31 +485,30 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   size_t o_multi = off;   off += align_up(max_multi * 4);
   size_t o_segpart = off; off += align_up(2 * max_multi * 128);  // sum of nseg over multi-segment buckets <= 2 max_multi
   size_t o_bins = off;    off += align_up((SIZE_BINS + 4) * 4);
-  int rc = ensure_ws(ctx, off);
+  int rc = ensure_ws(ctx, off, lane);
   if (rc) return rc;
-  uint32_t* counts = (uint32_t*)(ctx->ws + o_counts);
-  uint32_t* offsets = (uint32_t*)(ctx->ws + o_offsets);
-  uint32_t* tiles = (uint32_t*)(ctx->ws + o_tiles);
-  uint32_t* big_count = (uint32_t*)(ctx->ws + o_big);
+  uint32_t* counts = (uint32_t*)(ws + o_counts);
+  uint32_t* offsets = (uint32_t*)(ws + o_offsets);
+  uint32_t* tiles = (uint32_t*)(ws + o_tiles);
+  uint32_t* big_count = (uint32_t*)(ws + o_big);
   uint32_t* big_list = big_count + 1;
-  uint32_t* big_part = (uint32_t*)(ctx->ws + o_bigpart);
-  uint32_t* entries = (uint32_t*)(ctx->ws + o_entries);
-  uint32_t* buckets = (uint32_t*)(ctx->ws + o_buckets);
-  uint32_t* merged = (uint32_t*)(ctx->ws + o_merged);
+  uint32_t* big_part = (uint32_t*)(ws + o_bigpart);
+  uint32_t* entries = (uint32_t*)(ws + o_entries);
+  uint32_t* buckets = (uint32_t*)(ws + o_buckets);
+  uint32_t* merged = (uint32_t*)(ws + o_merged);
   size_t pair_words = align_up((size_t)rarr * tiles0 * 128) / 4;
-  uint32_t* pairs = (uint32_t*)(ctx->ws + o_pairs);
-  uint32_t* wins = (uint32_t*)(ctx->ws + o_wins);
-  uint32_t* bins = (uint32_t*)(ctx->ws + o_bins);
+  uint32_t* pairs = (uint32_t*)(ws + o_pairs);
+  uint32_t* wins = (uint32_t*)(ws + o_wins);
+  uint32_t* bins = (uint32_t*)(ws + o_bins);
   AccSched sched;
   sched.bins = bins;
   sched.n_items = bins + SIZE_BINS;
   sched.part_count = bins + SIZE_BINS + 1;
   sched.multi_count = bins + SIZE_BINS + 2;
-  sched.items = (uint2*)(ctx->ws + o_items);
-  sched.seg_slot = (uint32_t*)(ctx->ws + o_segslot);
-  sched.multi_list = (uint32_t*)(ctx->ws + o_multi);
-  uint32_t* seg_part = (uint32_t*)(ctx->ws + o_segpart);
-  cudaStream_t st = ctx->stream;
+  sched.items = (uint2*)(ws + o_items);
+  sched.seg_slot = (uint32_t*)(ws + o_segslot);
+  sched.multi_list = (uint32_t*)(ws + o_multi);
+  uint32_t* seg_part = (uint32_t*)(ws + o_segpart);
 
   prof_mark(ctx, BPG_PROF_HIST);
   CK(cudaMemsetAsync(counts, 0, (size_t)cfg.B * 4, st));
@@ -1089,14 +1128,75 @@ extern "C" int bpg_msm_table_indexed(bpg_ctx* ctx, const bpg_table* table, const
 static int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_adhoc, const bpg_table* const* tabs,
                           const size_t* offs, const size_t* lens, int nsegs, const uint32_t* d_scalars, size_t total,
                           uint8_t out[32]) {
+  cudaStream_t s = ctx->stream;
+  uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small + 1024);
+  uint32_t* d_ext = (uint32_t*)ctx->d_small;  // up to two partial sums
+  uint8_t* d_bytes = ctx->d_small + 256;
+  CK(cudaMemsetAsync(bad, 0, 4, s));
+  // Fast path: every range lies in ONE windowed table (the R1CS verifier: B, B_blinding, G, H of the
+  // generator table).  The table terms run as an indexed MSM over the window multiples (no doublings)
+  // on the launch stream while the few ad-hoc points (proof points: decoded, no precomputation) run
+  // as a small plain MSM on the auxiliary stream; the two partial sums are added at the end.
+  bool one_windowed = nsegs >= 1 && nsegs <= 4 && tabs[0]->win_c != 0;
+  for (int i = 1; i < nsegs && one_windowed; i++) one_windowed = tabs[i] == tabs[0];
+  size_t n_tab = total - n_adhoc;
+  if (one_windowed && n_tab > 0) {
+    const bpg_table* T = tabs[0];
+    bpg_table* ta = nullptr;
+    uint32_t* d_ids = nullptr;
+    int rc = BPG_OK;
+    int n_parts = 1;
+    do {
+      if (dev_alloc(ctx, &d_ids, n_tab * 4) != cudaSuccess) { rc = BPG_ERR_NOMEM; break; }
+      if (n_adhoc) {
+        rc = table_alloc_plain(ctx, n_adhoc, &ta);
+        if (rc) break;
+        rc = BPG_ERR_CUDA;
+        if (cudaEventRecord(ctx->ev_fork, s) != cudaSuccess) break;
+        if (cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0) != cudaSuccess) break;
+        k_decode_to_niels<<<(unsigned)((n_adhoc + 127) / 128), 128, 0, ctx->aux_stream>>>(d_adhoc_points, (uint32_t)n_adhoc,
+                                                                                          ta->niels, bad);
+        ctx->launches++;
+        rc = msm_enqueue(ctx, ta->niels, n_adhoc, d_scalars, n_adhoc, nullptr, nullptr, 1, d_ext + 32, 0, 0, /*lane=*/1);
+        if (rc) break;
+        rc = BPG_ERR_CUDA;
+        if (cudaEventRecord(ctx->ev_join, ctx->aux_stream) != cudaSuccess) break;
+        n_parts = 2;
+      }
+      SegIds sg;
+      sg.n = nsegs;
+      for (int i = 0; i < 4; i++) {
+        sg.off[i] = i < nsegs ? (uint32_t)offs[i] : 0;
+        sg.len[i] = i < nsegs ? (uint32_t)lens[i] : 0;
+      }
+      k_seg_point_ids<<<(unsigned)((n_tab + 255) / 256), 256, 0, s>>>(sg, (uint32_t)n_tab, d_ids);
+      ctx->launches++;
+      rc = msm_enqueue(ctx, T->niels, T->n, d_scalars + n_adhoc * 8, n_tab, nullptr, d_ids, 1, d_ext, T->win_c, T->n);
+      if (rc) break;
+      rc = BPG_ERR_CUDA;
+      if (n_adhoc && cudaStreamWaitEvent(s, ctx->ev_join, 0) != cudaSuccess) break;
+      rc = bpg_dev_sum_encode(ctx, d_ext, n_parts, 1, d_bytes, nullptr);
+      if (rc) break;
+      rc = BPG_ERR_CUDA;
+      if (cudaMemcpyAsync(ctx->h_pinned, d_bytes, 32, cudaMemcpyDeviceToHost, s) != cudaSuccess) break;
+      if (cudaMemcpyAsync(ctx->h_pinned + 64, bad, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) break;
+      cudaError_t se = cudaStreamSynchronize(s);
+      if (se != cudaSuccess) { ctx->last_cuda = (int)se; break; }
+      if (*reinterpret_cast<uint32_t*>(ctx->h_pinned + 64)) { rc = BPG_ERR_DECODE; break; }
+      memcpy(out, ctx->h_pinned, 32);
+      rc = BPG_OK;
+    } while (0);
+    if (rc != BPG_OK && n_parts == 2) cudaStreamSynchronize(ctx->aux_stream);  // do not free under the aux lane
+    if (ta) bpg_table_free(ta);
+    dev_free(ctx, d_ids);
+    return rc;
+  }
+  // General path: one plain table [adhoc | range copies], one MSM with Horner.
   bpg_table* t = nullptr;
   int rc = table_alloc_plain(ctx, total, &t);
   if (rc) return rc;
-  cudaStream_t s = ctx->stream;
   do {
-    uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small + 1024);
     rc = BPG_ERR_CUDA;
-    if (cudaMemsetAsync(bad, 0, 4, s) != cudaSuccess) break;
     if (n_adhoc) {
       k_decode_to_niels<<<(unsigned)((n_adhoc + 127) / 128), 128, 0, s>>>(d_adhoc_points, (uint32_t)n_adhoc, t->niels, bad);
       ctx->launches++;
@@ -1110,8 +1210,6 @@ static int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_
       pos += lens[i];
     }
     if (!ok) break;
-    uint32_t* d_ext = (uint32_t*)ctx->d_small;
-    uint8_t* d_bytes = ctx->d_small + 128;
     rc = msm_enqueue(ctx, t->niels, total, d_scalars, total, nullptr, nullptr, 1, d_ext);
     if (rc) break;
     rc = bpg_dev_sum_encode(ctx, d_ext, 1, 1, d_bytes, nullptr);

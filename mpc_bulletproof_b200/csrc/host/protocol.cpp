@@ -25,6 +25,37 @@ using namespace bpg_host;
 
 typedef std::array<uint8_t, 32> Bytes32;
 
+// Growable array in page-locked host memory (trivially copyable T): the witness rows and the flat
+// constraint terms are uploaded straight from it at PCIe rate.
+template <typename T>
+struct PinnedVec {
+  T* p = nullptr;
+  size_t n = 0, cap = 0;
+  PinnedVec() = default;
+  PinnedVec(const PinnedVec&) = delete;
+  PinnedVec& operator=(const PinnedVec&) = delete;
+  ~PinnedVec() { bpg_host_free(p); }
+  void reserve(size_t want) {
+    if (want <= cap) return;
+    size_t nc = std::max<size_t>(want, std::max<size_t>(cap * 2, 1024));
+    T* q = static_cast<T*>(bpg_host_alloc(nc * sizeof(T)));
+    if (!q) throw std::bad_alloc();
+    if (n) memcpy(q, p, n * sizeof(T));
+    bpg_host_free(p);
+    p = q;
+    cap = nc;
+  }
+  void push_back(const T& x) {
+    if (n == cap) reserve(n + 1);
+    p[n++] = x;
+  }
+  size_t size() const { return n; }
+  T* data() { return p; }
+  const T* data() const { return p; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+};
+
 // BPG_TRACE=1: per-stage wall-clock of prove/verify on stderr (development aid)
 struct StageTimer {
   bool on;
@@ -342,12 +373,6 @@ struct Xoshiro {
     s[3] = rotl(s[3], 45);
     return result;
   }
-  void fill(uint8_t* out, size_t len) {  // len % 8 == 0; the same stream scalar() consumes
-    for (size_t i = 0; i < len; i += 8) {
-      uint64_t x = next();
-      memcpy(out + i, &x, 8);
-    }
-  }
   Scalar scalar() {
     uint8_t b[64];
     for (int i = 0; i < 8; i++) {
@@ -367,11 +392,12 @@ struct bpg_cs {
   Transcript* tr;
   // constraints in flat (CSR-like) form, appended as the gadget code constrains: row q, variable
   // code = kind << 28 | index, Montgomery coefficient -- uploaded as is for the device flattening
-  std::vector<uint32_t> t_code, t_row;
-  std::vector<Scalar> t_coeff;
+  PinnedVec<uint32_t> t_code, t_row;
+  PinnedVec<Scalar> t_coeff;
   size_t n_rows = 0;
   // prover
-  std::vector<Scalar> a_L, a_R, a_O, v, v_blinding;
+  PinnedVec<Scalar> a_L, a_R, a_O;
+  std::vector<Scalar> v, v_blinding;
   // verifier
   size_t num_vars = 0;
   std::vector<Bytes32> V;
@@ -752,12 +778,10 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   tr.append_u64("m", cs->v.size());  // :420
   size_t n1 = cs->a_L.size();
   if (g->cap < n1) return BPG_ERR_CAPACITY;  // :450-452
-  // Blinding draws in the reference's order (:457-462); the 2 n1 vector blindings stay as the
-  // 64-byte uniform blocks and are reduced mod l on the device.
+  // Blinding draws in the reference's order (:457-462); the 2 n1 vector blindings s_L, s_R are
+  // generated on the device from one drawn key (none drawn for an empty phase)
   Scalar i_b1 = rng.scalar(), o_b1 = rng.scalar(), s_b1 = rng.scalar();
-  std::vector<uint8_t> raw_sL(n1 * 64), raw_sR(n1 * 64);
-  rng.fill(raw_sL.data(), raw_sL.size());
-  rng.fill(raw_sR.data(), raw_sR.size());
+  uint64_t vec_key = n1 ? rng.next() : 0;
   DevGuard dv;
   int rc = bpg_r1cs_dev_new(cs->ctx, next_pow2(std::max<size_t>(n1, 1)), &dv.p);
   if (rc) return rc;
@@ -767,7 +791,7 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   o_b1.to_bytes(blind3 + 32);
   s_b1.to_bytes(blind3 + 64);
   rc = bpg_r1cs_dev_commit(dv.p, g->table, g->g_base(), g->h_base(), g->bb_id(), 0, n1, cs->a_L.data(), cs->a_R.data(),
-                           cs->a_O.data(), raw_sL.data(), raw_sR.data(), blind3, c3);  // :465-494
+                           cs->a_O.data(), vec_key, blind3, c3);  // :465-494
   if (rc) return rc;
   tm.lap("A_I1 A_O1 S1 msm");
   memcpy(proof.A_I1.data(), c3, 32);
@@ -787,16 +811,12 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
     i_b2 = rng.scalar();
     o_b2 = rng.scalar();
     s_b2 = rng.scalar();
-    raw_sL.resize(n2 * 64);
-    raw_sR.resize(n2 * 64);
-    rng.fill(raw_sL.data(), raw_sL.size());
-    rng.fill(raw_sR.data(), raw_sR.size());
+    vec_key = rng.next();
     i_b2.to_bytes(blind3);
     o_b2.to_bytes(blind3 + 32);
     s_b2.to_bytes(blind3 + 64);
     rc = bpg_r1cs_dev_commit(dv.p, g->table, g->g_base(), g->h_base(), g->bb_id(), n1, n2, cs->a_L.data() + n1,
-                             cs->a_R.data() + n1, cs->a_O.data() + n1, raw_sL.data(), raw_sR.data(), blind3,
-                             c3);  // :532-565
+                             cs->a_R.data() + n1, cs->a_O.data() + n1, vec_key, blind3, c3);  // :532-565
     if (rc) return rc;
     memcpy(proof.A_I2.data(), c3, 32);
     memcpy(proof.A_O2.data(), c3 + 32, 32);

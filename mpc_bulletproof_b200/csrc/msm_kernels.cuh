@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) k_hist(const uint32_t* __restrict__ scala
   sc k = sc_zero();
   if (valid) sc_load(k, scalars + (size_t)t * 8);
   sc_recoded r = sc_recode(k.v, cfg.bias);
-  uint32_t set = valid ? (set_ids ? set_ids[t] : t / cfg.n_points) : 0;
+  uint32_t set = (valid && cfg.nsets > 1) ? (set_ids ? set_ids[t] : t / cfg.n_points) : 0;
   uint32_t base = set * cfg.gsub * cfg.nb;
   uint32_t g = 0;
   for (int w = 0; w < cfg.W; w++) {
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ sc
   sc k = sc_zero();
   if (valid) sc_load(k, scalars + (size_t)t * 8);
   sc_recoded r = sc_recode(k.v, cfg.bias);
-  uint32_t set = valid ? (set_ids ? set_ids[t] : t / cfg.n_points) : 0;
+  uint32_t set = (valid && cfg.nsets > 1) ? (set_ids ? set_ids[t] : t / cfg.n_points) : 0;
   uint32_t pid = valid ? (point_ids ? point_ids[t] : t % cfg.n_points) : 0;
   uint32_t base = set * cfg.gsub * cfg.nb;
   uint32_t g = 0;
@@ -689,6 +689,34 @@ __global__ void __launch_bounds__(32) k_horner(const uint32_t* __restrict__ wind
     acc = ge4_add(acc, ge4_load(src + (size_t)w * 32));
   }
   if (threadIdx.x < 4) ge4_store(out_ext + (size_t)set * 32, acc);
+}
+
+// out[set] = identity (X, Y, Z, T) = (0, 1, 1, 0)
+__global__ void k_set_identity(uint32_t* __restrict__ out_ext) {
+  out_ext[(size_t)blockIdx.x * 32 + threadIdx.x] = (threadIdx.x == 8 || threadIdx.x == 16) ? 1u : 0u;
+}
+
+// point ids of up to four consecutive ranges [off_i, off_i + len_i) of one table
+struct SegIds {
+  uint32_t off[4], len[4];
+  int n;
+};
+__global__ void __launch_bounds__(256) k_seg_point_ids(SegIds sg, uint32_t total, uint32_t* __restrict__ ids) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  uint32_t r = t, id = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    if (i < sg.n) {
+      if (r < sg.len[i]) {
+        id = sg.off[i] + r;
+        r = 0xffffffffu;
+      } else if (r != 0xffffffffu) {
+        r -= sg.len[i];
+      }
+    }
+  }
+  ids[t] = id;
 }
 
 // ---------------------------------------------------------------------------

@@ -65,19 +65,39 @@ __device__ __forceinline__ void block_sum_k(sc (&x)[K], uint32_t (*sm)[8 * K]) {
   }
 }
 
-// 64 uniform bytes -> scalar mod l (Montgomery form): lo*R + hi*R^2
-__global__ void __launch_bounds__(256) k_wide_reduce(const uint32_t* __restrict__ raw /*[n][16]*/, uint32_t n,
-                                                      uint32_t* __restrict__ out /*[n][8] mont*/) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// The two blinding vectors of a phase (s_L, s_R; prover.rs:460-461, 523-528), generated where
+// they are consumed: consecutive 64-byte blocks of the SplitMix64 stream keyed by one draw of
+// the prover's PRNG are s_L[0], s_R[0], s_L[1], ...; each block is reduced mod l as
+// lo*R + hi*R^2 (Montgomery form of lo + hi 2^256).  Same definition as oracle/protocol.py
+// Blindings.vector_pair.
+__device__ __forceinline__ unsigned long long splitmix_word(unsigned long long key, unsigned long long counter) {
+  unsigned long long z = key + 0x9E3779B97F4A7C15ULL * (counter + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ sc sc_from_stream_block(unsigned long long key, unsigned long long block) {
   sc lo, hi;
-  sc_load(lo, raw + (size_t)i * 16);
-  sc_load(hi, raw + (size_t)i * 16 + 8);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    unsigned long long a = splitmix_word(key, 8 * block + k), b = splitmix_word(key, 8 * block + 4 + k);
+    lo.v[2 * k] = (uint32_t)a;
+    lo.v[2 * k + 1] = (uint32_t)(a >> 32);
+    hi.v[2 * k] = (uint32_t)b;
+    hi.v[2 * k + 1] = (uint32_t)(b >> 32);
+  }
   sc rr = sc_const(BPG_K(K_RR));
   // montmul accepts any 256-bit left operand against rr < l: (x * R^2)/R = x R
   sc lo_m = sc_montmul(lo, rr);
   sc hi_m = sc_montmul(sc_montmul(hi, rr), rr);  // hi R -> hi R^2 = Montgomery form of hi*R
-  sc_store(out + (size_t)i * 8, sc_add(lo_m, hi_m));
+  return sc_add(lo_m, hi_m);
+}
+__global__ void __launch_bounds__(256) k_blind_vectors(unsigned long long key, uint32_t n, uint32_t* __restrict__ sL,
+                                                        uint32_t* __restrict__ sR /*[n][8] mont*/) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  sc_store(sL + (size_t)i * 8, sc_from_stream_block(key, 2ull * i));
+  sc_store(sR + (size_t)i * 8, sc_from_stream_block(key, 2ull * i + 1));
 }
 
 // ---- prover: terms of the (A_I, A_O, S) launch over gens[first .. first+cnt) -------------

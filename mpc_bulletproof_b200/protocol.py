@@ -53,7 +53,14 @@ def sc_bytes(x: int) -> bytes:
 
 
 def _scs(xs) -> bytes:
+    """ints mod l -> canonical bytes; a bytes object is taken as already serialised scalars"""
+    if isinstance(xs, (bytes, bytearray)):
+        return bytes(xs)
     return b"".join(sc_bytes(x) for x in xs)
+
+
+def _count(xs) -> int:
+    return len(xs) // 32 if isinstance(xs, (bytes, bytearray)) else len(xs)
 
 
 class Transcript:
@@ -155,8 +162,8 @@ class InnerProductProof:
     def create(ctx: Context, transcript: Transcript, Q: bytes, G_factors, H_factors, G_vec: Table, H_vec: Table, a_vec, b_vec,
                g_off: int = 0, h_off: int = 0) -> "InnerProductProof":
         """reference src/inner_product_proof.rs:49-58 — G_vec/H_vec are resident tables."""
-        n = len(a_vec)
-        if not (len(b_vec) == n and len(G_factors) == n and len(H_factors) == n):
+        n = _count(a_vec)
+        if not (_count(b_vec) == n and _count(G_factors) == n and _count(H_factors) == n):
             raise BpgError(_lib.BPG_ERR_LEN, "vector lengths differ")
         cap = 64 * 32 + 64
         out = ctypes.create_string_buffer(cap)

@@ -68,6 +68,29 @@ class Blindings:
     def scalar(self) -> int:
         return self.rng.scalar()
 
+    def vector_pair(self, n: int):
+        """The two blinding vectors of a phase (s_L, s_R; src/r1cs/prover.rs:460-461, 523-528).
+        One xoshiro draw keys a SplitMix64 stream whose consecutive 64-byte blocks are
+        s_L[0], s_R[0], s_L[1], s_R[1], ... (each block reduced mod l like `scalar`), so that
+        element j is a pure function of (key, j) and can be produced where it is consumed.
+        No draw for n = 0."""
+        if n == 0:
+            return [], []
+        M = (1 << 64) - 1
+        key = self.rng.next_u64()
+
+        def word(counter):
+            z = (key + 0x9E3779B97F4A7C15 * (counter + 1)) & M
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+            return z ^ (z >> 31)
+
+        def block(idx):
+            b = b"".join(word(8 * idx + k).to_bytes(8, "little") for k in range(8))
+            return int.from_bytes(b, "little") % L
+
+        return [block(2 * j) for j in range(n)], [block(2 * j + 1) for j in range(n)]
+
 
 # ---------------------------------------------------------------- generators
 @dataclass
@@ -515,8 +538,7 @@ class Prover(_CSBase):
             raise InvalidGeneratorsLength()
         Bb = self.pc_gens.B_blinding
         i_b1, o_b1, s_b1 = blind.scalar(), blind.scalar(), blind.scalar()  # :457-459
-        s_L1 = [blind.scalar() for _ in range(n1)]
-        s_R1 = [blind.scalar() for _ in range(n1)]
+        s_L1, s_R1 = blind.vector_pair(n1)
         Gn, Hn = bp_gens.G(n1), bp_gens.H(n1)
         A_I1 = G.msm([i_b1] + self.a_L + self.a_R, [Bb] + Gn + Hn)  # :465
         A_O1 = G.msm([o_b1] + self.a_O, [Bb] + Gn)  # :477
@@ -544,8 +566,7 @@ class Prover(_CSBase):
             i_b2, o_b2, s_b2 = blind.scalar(), blind.scalar(), blind.scalar()
         else:
             i_b2 = o_b2 = s_b2 = 0
-        s_L2 = [blind.scalar() for _ in range(n2)]
-        s_R2 = [blind.scalar() for _ in range(n2)]
+        s_L2, s_R2 = blind.vector_pair(n2)
         if n2 > 0:  # :532-565
             G2, H2 = bp_gens.G(n)[n1:], bp_gens.H(n)[n1:]
             A_I2 = G.msm([i_b2] + self.a_L[n1:] + self.a_R[n1:], [Bb] + G2 + H2)
