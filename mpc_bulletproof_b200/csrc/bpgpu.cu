@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 #include "msm_kernels.cuh"
@@ -43,6 +44,9 @@ struct bpg_ctx {
   size_t ws_aux_cap = 0;
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // transient-allocation cache (dev_alloc / dev_free)
+  std::vector<std::pair<void*, size_t>> cache;
+  std::unordered_map<void*, size_t> live;
   // small staging buffers
   uint8_t* d_small = nullptr;   // device scratch for results (>= 64 KB)
   uint8_t* h_pinned = nullptr;  // pinned host scratch (>= 64 KB)
@@ -78,18 +82,47 @@ struct bpg_table {
     }                                             \
   } while (0)
 
-// Transient device memory (tables, proof states) comes from the device's stream-ordered pool:
-// after warm-up an allocation is a pool hit (microseconds) and a free does not synchronise the
-// device, which matters when a proof allocates its state per call.
+// Transient device memory (tables, proof states).  Freed blocks are parked in a small per-context
+// cache and handed out again (best fit within 4x) before falling back to the device's stream-ordered
+// pool: a proof allocates its state per call, and neither a cudaMalloc nor a pool miss (both cost
+// milliseconds at these sizes) may sit on that path.  Everything a context allocates is used on its
+// launch stream (the auxiliary lane is fenced by events), so reuse is ordered by the stream.
+static constexpr size_t CACHE_SLOTS = 24;
 static cudaError_t dev_alloc(bpg_ctx* ctx, void** p, size_t bytes) {
-  return cudaMallocAsync(p, std::max<size_t>(bytes, 256), ctx->stream);
+  bytes = std::max<size_t>((bytes + 255) / 256 * 256, 256);
+  int best = -1;
+  for (size_t i = 0; i < ctx->cache.size(); i++) {
+    size_t sz = ctx->cache[i].second;
+    if (sz >= bytes && sz <= 4 * bytes && (best < 0 || sz < ctx->cache[best].second)) best = (int)i;
+  }
+  if (best >= 0) {
+    *p = ctx->cache[best].first;
+    ctx->live[*p] = ctx->cache[best].second;
+    ctx->cache.erase(ctx->cache.begin() + best);
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+  if (e == cudaSuccess) ctx->live[*p] = bytes;
+  return e;
 }
 template <typename T>
 static cudaError_t dev_alloc(bpg_ctx* ctx, T** p, size_t bytes) {
   return dev_alloc(ctx, reinterpret_cast<void**>(p), bytes);
 }
 static void dev_free(bpg_ctx* ctx, void* p) {
-  if (p) cudaFreeAsync(p, ctx->stream);
+  if (!p) return;
+  auto it = ctx->live.find(p);
+  size_t sz = it == ctx->live.end() ? 0 : it->second;
+  if (it != ctx->live.end()) ctx->live.erase(it);
+  if (sz == 0 || sz > ((size_t)1 << 31)) {  // unknown or huge (a user's big table): give it back
+    cudaFreeAsync(p, ctx->stream);
+    return;
+  }
+  ctx->cache.push_back({p, sz});
+  if (ctx->cache.size() > CACHE_SLOTS) {
+    cudaFreeAsync(ctx->cache.front().first, ctx->stream);
+    ctx->cache.erase(ctx->cache.begin());
+  }
 }
 
 static constexpr size_t SMALL_BYTES = 1 << 16;
@@ -137,6 +170,9 @@ extern "C" void bpg_free(bpg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+  for (auto& b : ctx->cache) cudaFreeAsync(b.first, ctx->stream);
+  ctx->cache.clear();
+  cudaStreamSynchronize(ctx->stream);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws_aux) cudaFree(ctx->ws_aux);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
