@@ -50,22 +50,39 @@ constexpr uint32_t ENTRY_NEG = 0x80000000u;
 // ---------------------------------------------------------------------------
 // digits -> histogram
 // ---------------------------------------------------------------------------
+// The recoded scalar is parked in shared memory (limb-major, conflict-free) so that a window's
+// digit is two LDS and a funnel shift for a run-time window width, instead of a predicated
+// scan over the nine limbs held in registers.
+constexpr int SORT_THREADS = 256;
+__device__ __forceinline__ void digits_park(uint32_t (*sh)[SORT_THREADS], const sc_recoded& r) {
+#pragma unroll
+  for (int i = 0; i < 9; i++) sh[i][threadIdx.x] = r.v[i];
+}
+__device__ __forceinline__ int digit_at(const uint32_t (*sh)[SORT_THREADS], int w, int c) {
+  int bit = c * w;
+  int limb = bit >> 5, s = bit & 31;
+  uint32_t lo = sh[limb][threadIdx.x], hi = sh[limb + 1][threadIdx.x];  // limb <= 7: c (W - 1) <= 254
+  uint32_t raw = __funnelshift_r(lo, hi, s) & ((1u << c) - 1u);
+  return (int)raw - (1 << (c - 1));
+}
+
 // Warp-aggregated: lanes whose digit lands in the same bucket (structured scalars: bit vectors,
 // repeated values, the short top window) issue ONE atomic for the group.
-__global__ void __launch_bounds__(256) k_hist(const uint32_t* __restrict__ scalars,
-                                              const uint8_t* __restrict__ set_ids, MsmCfg cfg,
-                                              uint32_t* __restrict__ counts) {
+__global__ void __launch_bounds__(SORT_THREADS) k_hist(const uint32_t* __restrict__ scalars,
+                                                       const uint8_t* __restrict__ set_ids, MsmCfg cfg,
+                                                       uint32_t* __restrict__ counts) {
+  __shared__ uint32_t sh[9][SORT_THREADS];
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = t < cfg.n_terms;
   const uint32_t lane = threadIdx.x & 31;
   sc k = sc_zero();
   if (valid) sc_load(k, scalars + (size_t)t * 8);
-  sc_recoded r = sc_recode(k.v, cfg.bias);
+  digits_park(sh, sc_recode(k.v, cfg.bias));  // each thread reads back only its own column: no barrier
   uint32_t set = (valid && cfg.nsets > 1) ? (set_ids ? set_ids[t] : t / cfg.n_points) : 0;
   uint32_t base = set * cfg.gsub * cfg.nb;
   uint32_t g = 0;
   for (int w = 0; w < cfg.W; w++) {
-    int d = valid ? sc_digit(r, w, cfg.c) : 0;
+    int d = valid ? digit_at(sh, w, cfg.c) : 0;
     uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
     uint32_t b = base + g * cfg.nb + mag - 1;
     uint32_t peers = __match_any_sync(0xffffffffu, d != 0 ? b : 0xffffffffu - lane);
@@ -174,36 +191,51 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t* __restric
 // ---------------------------------------------------------------------------
 // scatter entries into bucket order (order inside a bucket is irrelevant)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(const uint32_t* __restrict__ scalars,
-                                                 const uint8_t* __restrict__ set_ids,
-                                                 const uint32_t* __restrict__ point_ids, MsmCfg cfg,
-                                                 const uint32_t* __restrict__ offsets,
-                                                 uint32_t* __restrict__ cursors, uint32_t* __restrict__ entries) {
+__global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t* __restrict__ scalars,
+                                                          const uint8_t* __restrict__ set_ids,
+                                                          const uint32_t* __restrict__ point_ids, MsmCfg cfg,
+                                                          const uint32_t* __restrict__ offsets,
+                                                          uint32_t* __restrict__ cursors, uint32_t* __restrict__ entries) {
+  __shared__ uint32_t sh[9][SORT_THREADS];
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = t < cfg.n_terms;
   const uint32_t lane = threadIdx.x & 31;
   sc k = sc_zero();
   if (valid) sc_load(k, scalars + (size_t)t * 8);
-  sc_recoded r = sc_recode(k.v, cfg.bias);
+  digits_park(sh, sc_recode(k.v, cfg.bias));
   uint32_t set = (valid && cfg.nsets > 1) ? (set_ids ? set_ids[t] : t / cfg.n_points) : 0;
   uint32_t pid = valid ? (point_ids ? point_ids[t] : t % cfg.n_points) : 0;
   uint32_t base = set * cfg.gsub * cfg.nb;
   uint32_t g = 0;
-  for (int w = 0; w < cfg.W; w++) {
-    int d = valid ? sc_digit(r, w, cfg.c) : 0;
-    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-    uint32_t b = base + g * cfg.nb + mag - 1;
-    // one cursor atomic per group of lanes that share the bucket; the group's lanes take consecutive slots
-    uint32_t peers = __match_any_sync(0xffffffffu, d != 0 ? b : 0xffffffffu - lane);
-    uint32_t leader = (uint32_t)(__ffs(peers) - 1);
-    uint32_t first = 0;
-    if (d != 0 && lane == leader) first = atomicAdd(&cursors[b], (uint32_t)__popc(peers));
-    first = __shfl_sync(0xffffffffu, first, leader);
-    if (d != 0) {
-      uint32_t pos = offsets[b] + first + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-      entries[pos] = (pid + (uint32_t)w * cfg.win_stride) | (d < 0 ? ENTRY_NEG : 0u);
+  // Windows go through in batches of four: the four cursor atomics (one per group of lanes that
+  // share a bucket; the group's lanes take consecutive slots) and the four offset loads are in
+  // flight together before any entry is written.
+  for (int w0 = 0; w0 < cfg.W; w0 += 4) {
+    uint32_t b[4], peers[4], first[4], off[4];
+    int d[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int w = w0 + j;
+      d[j] = (valid && w < cfg.W) ? digit_at(sh, min(w, cfg.W - 1), cfg.c) : 0;
+      uint32_t mag = d[j] < 0 ? (uint32_t)(-d[j]) : (uint32_t)d[j];
+      b[j] = base + g * cfg.nb + mag - 1;
+      g = g + 1 == cfg.gsub ? 0 : g + 1;
+      peers[j] = __match_any_sync(0xffffffffu, d[j] != 0 ? b[j] : 0xffffffffu - lane);
+      first[j] = 0;
+      off[j] = 0;
+      if (d[j] != 0) {
+        if (lane == (uint32_t)(__ffs(peers[j]) - 1)) first[j] = atomicAdd(&cursors[b[j]], (uint32_t)__popc(peers[j]));
+        off[j] = __ldg(offsets + b[j]);
+      }
     }
-    g = g + 1 == cfg.gsub ? 0 : g + 1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint32_t f = __shfl_sync(0xffffffffu, first[j], __ffs(peers[j]) - 1);
+      if (d[j] != 0) {
+        uint32_t pos = off[j] + f + (uint32_t)__popc(peers[j] & ((1u << lane) - 1u));
+        entries[pos] = (pid + (uint32_t)(w0 + j) * cfg.win_stride) | (d[j] < 0 ? ENTRY_NEG : 0u);
+      }
+    }
   }
 }
 
