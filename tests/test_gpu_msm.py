@@ -186,3 +186,30 @@ def test_windowed_groups(ctx, c, gsub):
         ctx.set_groups(0)
     assert got == want
     t.close()
+
+
+@pytest.mark.parametrize("c", [18, 20])
+def test_windowed_large_bucket_array(ctx, c):
+    """Window widths used at the benchmark sizes (c = 20 at 2^20 points): one array of 2^(c-1)
+    buckets per set, the thread-per-chunk reduction leaf and several k_reduce_pairs rounds.
+    Checked on a table small enough for the oracle; sparse buckets and empty chunks included."""
+    from mpc_bulletproof_b200 import Table
+
+    r = rng(90 + c)
+    n = 1500
+    ps = [rand_point(r) for _ in range(n)]
+    t = Table(ctx, points_bytes(ps)).set_windows(c)
+    assert t.window == c
+    ks = [rand_scalar(r) for _ in range(n)]
+    ks[0], ks[1], ks[2], ks[3] = 0, 1, G.L - 1, 2**252
+    assert t.msm(scalars_bytes(ks))[0] == G.msm(ks, ps).encode()
+    # two sets, a sub-range, and a bucket schedule forced to several groups
+    kk = [[rand_scalar(r) for _ in range(700)] for _ in range(2)]
+    want = [G.msm(k, ps[100:800]).encode() for k in kk]
+    for gsub in (0, 3):
+        ctx.set_groups(gsub)
+        try:
+            assert t.msm(b"".join(scalars_bytes(k) for k in kk), n_sets=2, offset=100, n=700) == want
+        finally:
+            ctx.set_groups(0)
+    t.close()
