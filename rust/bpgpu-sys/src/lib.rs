@@ -1,0 +1,158 @@
+//! Raw bindings to `include/bpgpu.h`.  One declaration per entry point; comments name the
+//! reference interface each one stands behind (paths relative to renegade-fi/mpc-bulletproof).
+#![allow(non_camel_case_types)]
+
+use std::os::raw::{c_char, c_int, c_void};
+
+macro_rules! opaque {
+    ($($name:ident),*) => { $( #[repr(C)] pub struct $name { _private: [u8; 0] } )* };
+}
+opaque!(bpg_ctx, bpg_table, bpg_ipp, bpg_comb, bpg_r1cs_dev);
+
+pub const BPG_OK: c_int = 0;
+pub const BPG_ERR_ARG: c_int = -1;
+pub const BPG_ERR_LEN: c_int = -2;
+/// `assert!(n.is_power_of_two())`, src/inner_product_proof.rs:69
+pub const BPG_ERR_POW2: c_int = -3;
+/// `R1CSError::InvalidGeneratorsLength`, src/r1cs/prover.rs:450
+pub const BPG_ERR_CAPACITY: c_int = -4;
+/// `ProofError::FormatError` / `R1CSError::FormatError`
+pub const BPG_ERR_DECODE: c_int = -5;
+/// `ProofError::VerificationError` / `R1CSError::VerificationError`
+pub const BPG_ERR_VERIFY: c_int = -6;
+pub const BPG_ERR_CUDA: c_int = -7;
+pub const BPG_ERR_NOMEM: c_int = -8;
+
+/// Montgomery limbs (x * 2^256 mod l), eight little-endian u32 words.
+pub type Mont = [u32; 8];
+/// base^(2^k), k < 32, Montgomery limbs.
+pub type PowTable = [Mont; 32];
+
+/// Parameters of the verifier's scalar preparation, src/r1cs/verifier.rs:468-501, 527-529.
+#[repr(C)]
+pub struct bpg_verify_params {
+    pub y_inv_pow: PowTable,
+    /// u_j^2 in creation order, src/inner_product_proof.rs:288-292
+    pub u_sq: [Mont; 32],
+    pub allinv: Mont,
+    pub x: Mont,
+    pub a: Mont,
+    pub b: Mont,
+    pub u: Mont,
+    /// scalar of B = c0 + c1 * delta
+    pub c0: Mont,
+    pub c1: Mont,
+    pub lg_n: u32,
+    pub n: u32,
+    pub n1: u32,
+    pub padded_n: u32,
+}
+
+/// Parameters of `InnerProductProof::verify`'s scalars, src/inner_product_proof.rs:283-307.
+#[repr(C)]
+pub struct bpg_ipp_verify_params {
+    pub u_sq: [Mont; 32],
+    pub allinv: Mont,
+    pub a: Mont,
+    pub b: Mont,
+    pub lg_n: u32,
+    pub padded_n: u32,
+}
+
+extern "C" {
+    // ---- context -----------------------------------------------------------------------
+    pub fn bpg_init(device: c_int, out: *mut *mut bpg_ctx) -> c_int;
+    pub fn bpg_free(ctx: *mut bpg_ctx);
+    pub fn bpg_sync(ctx: *mut bpg_ctx) -> c_int;
+    pub fn bpg_strerror(code: c_int) -> *const c_char;
+    pub fn bpg_last_cuda_error(ctx: *const bpg_ctx) -> c_int;
+
+    // ---- generator tables: BulletproofGens / PedersenGens as data, src/generators.rs:158-235
+    pub fn bpg_table_upload(ctx: *mut bpg_ctx, points: *const u8, n: usize, out: *mut *mut bpg_table) -> c_int;
+    pub fn bpg_table_set_windows(ctx: *mut bpg_ctx, t: *mut bpg_table, c: c_int) -> c_int;
+    pub fn bpg_table_len(t: *const bpg_table) -> usize;
+    pub fn bpg_table_free(t: *mut bpg_table);
+
+    // ---- StarkPoint::msm_iter / ::msm (all call sites of SURVEY.md 2.2) ---------------
+    pub fn bpg_msm(ctx: *mut bpg_ctx, scalars: *const u8, points: *const u8, n: usize, out: *mut u8) -> c_int;
+    pub fn bpg_msm_table(
+        ctx: *mut bpg_ctx, t: *const bpg_table, offset: usize, n: usize, scalars: *const u8, n_sets: c_int, out: *mut u8,
+    ) -> c_int;
+    pub fn bpg_msm_table_indexed(
+        ctx: *mut bpg_ctx, t: *const bpg_table, point_ids: *const u32, set_ids: *const u8, scalars: *const u8,
+        n_terms: usize, n_sets: c_int, out: *mut u8,
+    ) -> c_int;
+    pub fn bpg_msm_mixed(
+        ctx: *mut bpg_ctx, adhoc_points: *const u8, n_adhoc: usize, tabs: *const *const bpg_table, offs: *const usize,
+        lens: *const usize, nsegs: c_int, scalars: *const u8, out: *mut u8,
+    ) -> c_int;
+    /// one rank's / one MPC party's partial sums: n_sets x 128 bytes (X|Y|Z|T)
+    pub fn bpg_msm_table_partial(
+        ctx: *mut bpg_ctx, t: *const bpg_table, offset: usize, n: usize, scalars: *const u8, n_sets: c_int,
+        out_ext: *mut u8,
+    ) -> c_int;
+    /// out[s] = encode(sum_p parts[p][s])
+    pub fn bpg_sum_encode(ctx: *mut bpg_ctx, parts_ext: *const u8, n_parts: c_int, n_sets: c_int, out: *mut u8) -> c_int;
+
+    // ---- InnerProductProof::create, src/inner_product_proof.rs:49-193 -------------------
+    pub fn bpg_ipp_begin(
+        ctx: *mut bpg_ctx, g: *const bpg_table, g_off: usize, h: *const bpg_table, h_off: usize, n: usize, q: *const u8,
+        g_factors: *const u8, h_factors: *const u8, a: *const u8, b: *const u8, out: *mut *mut bpg_ipp,
+    ) -> c_int;
+    pub fn bpg_ipp_begin_shared(
+        ctx: *mut bpg_ctx, shared: *const bpg_table, g_base: usize, h_base: usize, q_id: usize, q_mul: *const u8,
+        n: usize, g_factors: *const u8, h_factors: *const u8, a: *const u8, b: *const u8, out: *mut *mut bpg_ipp,
+    ) -> c_int;
+    pub fn bpg_ipp_rounds_left(st: *const bpg_ipp) -> usize;
+    pub fn bpg_ipp_round_LR(st: *mut bpg_ipp, l: *mut u8, r: *mut u8) -> c_int;
+    pub fn bpg_ipp_round_fold(st: *mut bpg_ipp, u: *const u8, u_inv: *const u8) -> c_int;
+    pub fn bpg_ipp_finish(st: *mut bpg_ipp, a: *mut u8, b: *mut u8) -> c_int;
+    pub fn bpg_ipp_free(st: *mut bpg_ipp);
+    /// InnerProductProof::verify, src/inner_product_proof.rs:317-372
+    pub fn bpg_ipp_verify_msm(
+        ctx: *mut bpg_ctx, g: *const bpg_table, g_off: usize, h: *const bpg_table, h_off: usize, adhoc_points: *const u8,
+        adhoc_scalars: *const u8, n_adhoc: usize, g_factors: *const u8, h_factors: *const u8,
+        params: *const bpg_ipp_verify_params, out: *mut u8,
+    ) -> c_int;
+
+    // ---- PedersenGens::commit, src/generators.rs:41-43 -----------------------------------
+    pub fn bpg_comb_create(ctx: *mut bpg_ctx, bases: *const u8, nbases: c_int, out: *mut *mut bpg_comb) -> c_int;
+    pub fn bpg_comb_mul(ctx: *mut bpg_ctx, comb: *const bpg_comb, scalars: *const u8, n: usize, out: *mut u8) -> c_int;
+    pub fn bpg_comb_free(c: *mut bpg_comb);
+
+    // ---- R1CS scalar preparation in HBM --------------------------------------------------
+    pub fn bpg_r1cs_dev_new(ctx: *mut bpg_ctx, capacity: usize, out: *mut *mut bpg_r1cs_dev) -> c_int;
+    pub fn bpg_r1cs_dev_reserve(st: *mut *mut bpg_r1cs_dev, capacity: usize) -> c_int;
+    pub fn bpg_r1cs_dev_free(st: *mut bpg_r1cs_dev);
+    /// (A_I, A_O, S) of one phase, src/r1cs/prover.rs:465-494, 532-565
+    pub fn bpg_r1cs_dev_commit(
+        st: *mut bpg_r1cs_dev, gens: *const bpg_table, g_base: usize, h_base: usize, bb_id: usize, first: usize,
+        cnt: usize, a_l: *const c_void, a_r: *const c_void, a_o: *const c_void, vec_key: u64, blind3: *const u8,
+        out: *mut u8,
+    ) -> c_int;
+    /// flattened_constraints, src/r1cs/prover.rs:342-379, src/r1cs/verifier.rs:323-362
+    pub fn bpg_r1cs_dev_flatten(
+        st: *mut bpg_r1cs_dev, n: usize, m: usize, n_terms: usize, t_code: *const u32, t_row: *const u32,
+        t_coeff: *const c_void, z_pow: *const c_void, wv_out: *mut c_void,
+    ) -> c_int;
+    /// t_1..t_6, src/util.rs:152-170
+    pub fn bpg_r1cs_dev_poly_t(
+        st: *mut bpg_r1cs_dev, n: usize, y_pow: *const c_void, y_inv_pow: *const c_void, t_out: *mut u8,
+    ) -> c_int;
+    /// l(x), r(x), padding, factors, then the IPP state, src/r1cs/prover.rs:650-708
+    pub fn bpg_r1cs_dev_ipp_begin(
+        st: *mut bpg_r1cs_dev, gens: *const bpg_table, g_base: usize, h_base: usize, q_id: usize, q_mul: *const u8,
+        n: usize, n1: usize, padded_n: usize, x: *const c_void, u: *const c_void, y_pow: *const c_void,
+        y_inv_pow: *const c_void, out: *mut *mut bpg_ipp,
+    ) -> c_int;
+    /// the verifier's mega-MSM, src/r1cs/verifier.rs:468-547
+    pub fn bpg_r1cs_dev_verify_msm(
+        st: *mut bpg_r1cs_dev, gens: *const bpg_table, g_base: usize, h_base: usize, b_id: usize,
+        adhoc_points: *const u8, adhoc_scalars: *const u8, n_adhoc: usize, bb_scalar: *const u8,
+        params: *const bpg_verify_params, out: *mut u8,
+    ) -> c_int;
+
+    // ---- page-locked staging ---------------------------------------------------------------
+    pub fn bpg_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn bpg_host_free(p: *mut c_void);
+}
