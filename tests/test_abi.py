@@ -48,3 +48,20 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(base, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "bp_oracle" not in txt, f
+
+
+def test_rust_sys_crate_names_exist():
+    """rust/bpgpu-sys declares a subset of include/bpgpu.h: every `pub fn bpg_*` it names must be
+    an exported symbol of the library (the crate cannot be compiled here: no Rust toolchain)."""
+    import re
+
+    from mpc_bulletproof_b200 import _lib
+
+    src = open(os.path.join(ROOT, "rust", "bpgpu-sys", "src", "lib.rs")).read()
+    names = set(re.findall(r"pub fn (bpg_\w+)\s*\(", src))
+    assert len(names) > 30
+    missing = names - set(_lib.exported_symbols())
+    assert not missing, f"declared in the Rust bindings but not exported: {sorted(missing)}"
+    hdr = open(os.path.join(ROOT, "include", "bpgpu.h")).read()
+    for code in re.findall(r"pub const (BPG_\w+): c_int = (-?\d+);", src):
+        assert re.search(rf"#define {code[0]} {code[1]}\b", hdr), code
