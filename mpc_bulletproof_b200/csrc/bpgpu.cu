@@ -880,6 +880,8 @@ struct bpg_ipp {
   const bpg_table* tab;  // windowed table the round MSMs run over
   bpg_table* own_tab;    // non-null when the state built its own [G | H | Q] table
   bool has_qmul;         // cross terms are multiplied by q_mul (Q = q_mul * table[q_id])
+  bool q_sep;            // Q is outside the (caller's windowed) table: c_L Q, c_R Q come from a comb of Q
+  uint32_t *q_comb, *q_side;
   uint8_t* buf;    // one allocation for everything below
   uint32_t *a, *b, *wG, *wH, *scalars, *point_ids, *partials, *u_pair, *out_ext;
   uint32_t* q_mul;
@@ -930,7 +932,8 @@ static int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const b
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
   size_t o_a = take(n * 32), o_b = take(n * 32), o_wG = take(n * 32), o_wH = take(n * 32);
   size_t o_sc = take(T * 32), o_pid = take(T * 4), o_set = take(T), o_part = take(nparts * 64);
-  size_t o_u = take(64), o_ext = take(2 * 128), o_bytes = take(64), o_q = take(32), o_qm = take(32);
+  size_t o_u = take(64), o_ext = take(4 * 128), o_bytes = take(64), o_q = take(32), o_qm = take(32);
+  size_t o_qside = take(64), o_qcomb = take((size_t)COMB_ENTRIES * 96);
   do {
     cudaError_t e = dev_alloc(ctx, &st->buf, off);
     if (e != cudaSuccess) { ctx->last_cuda = (int)e; rc = BPG_ERR_NOMEM; break; }
@@ -941,6 +944,8 @@ static int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const b
     st->u_pair = (uint32_t*)(st->buf + o_u); st->out_ext = (uint32_t*)(st->buf + o_ext);
     st->out_bytes = st->buf + o_bytes;
     st->q_mul = (uint32_t*)(st->buf + o_qm);
+    st->q_side = (uint32_t*)(st->buf + o_qside);
+    st->q_comb = (uint32_t*)(st->buf + o_qcomb);
     uint8_t* d_q = st->buf + o_q;
     cudaStream_t s = ctx->stream;
     if (cudaMemcpyAsync(st->a, d_a, n * 32, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
@@ -958,6 +963,24 @@ static int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const b
       k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, (uint32_t)g_base, (uint32_t)h_base, (uint32_t)q_id);
       ctx->launches++;
       if (cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+    } else if (G == H && G->win_c && n > 1) {
+      // The caller's generators already live in ONE windowed table (a resident BulletproofGens):
+      // run the round MSMs over it as they are and form c_L Q, c_R Q from a fixed-base comb of Q
+      // built here once, on the auxiliary stream beside each round's MSM.
+      st->tab = G;
+      st->q_sep = true;
+      k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, (uint32_t)g_off, (uint32_t)h_off, (uint32_t)g_off);
+      ctx->launches++;
+      memcpy(ctx->h_pinned + 512, Q_host, 32);
+      uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small);
+      if (cudaMemsetAsync(bad, 0, 4, s) != cudaSuccess ||
+          cudaMemcpyAsync(d_q, ctx->h_pinned + 512, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+      k_comb_build<<<1, COMB_WINDOWS, 0, s>>>(d_q, st->q_comb, bad);
+      ctx->launches++;
+      uint32_t* hbad = reinterpret_cast<uint32_t*>(ctx->h_pinned);
+      if (cudaMemcpyAsync(hbad, bad, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+          cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+      if (*hbad) { rc = BPG_ERR_DECODE; break; }
     } else {
       k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, 0u, (uint32_t)n, (uint32_t)(2 * n));
       ctx->launches++;
@@ -1063,12 +1086,21 @@ extern "C" int bpg_ipp_round_LR(bpg_ipp* st, uint8_t L[32], uint8_t R[32]) {
                                                                   (uint32_t)m, st->scalars, st->set_ids);
   LAUNCH_CHECK();
   k_ipp_cross_finish<<<1, IPP_THREADS, 0, s>>>(st->partials, gcross, (uint32_t)n, st->has_qmul ? st->q_mul : nullptr,
-                                               st->scalars, st->set_ids);
+                                               st->scalars, st->set_ids, st->q_sep ? st->q_side : nullptr);
   LAUNCH_CHECK();
+  if (st->q_sep) {
+    // c_L Q, c_R Q: 64 mixed additions each from the comb of Q, beside the MSM
+    CK(cudaEventRecord(ctx->ev_fork, s));
+    CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    k_comb_mul<<<1, 128, 0, ctx->aux_stream>>>(st->q_comb, 1, st->q_side, 2u, bias_for(4), nullptr, st->out_ext + 64);
+    LAUNCH_CHECK();
+    CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+  }
   int rc = msm_enqueue(ctx, st->tab->niels, st->tab->n, st->scalars, 2 * n + 2, st->set_ids, st->point_ids, 2,
                        st->out_ext, st->tab->win_c, st->tab->n);
   if (rc) return rc;
-  rc = bpg_dev_sum_encode(ctx, st->out_ext, 1, 2, st->out_bytes, nullptr);
+  if (st->q_sep) CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+  rc = bpg_dev_sum_encode(ctx, st->out_ext, st->q_sep ? 2 : 1, 2, st->out_bytes, nullptr);
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->h_pinned, st->out_bytes, 64, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -1115,6 +1147,7 @@ extern "C" int bpg_ipp_finish(bpg_ipp* st, uint8_t a[32], uint8_t b[32]) {
 extern "C" void bpg_ipp_free(bpg_ipp* st) {
   if (!st) return;
   cudaSetDevice(st->ctx->device);
+  if (st->q_sep) cudaStreamSynchronize(st->ctx->aux_stream);
   if (st->own_tab) bpg_table_free(st->own_tab);
   dev_free(st->ctx, st->buf);
   delete st;

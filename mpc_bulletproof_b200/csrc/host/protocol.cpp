@@ -302,9 +302,8 @@ extern "C" int bpg_ipp_verify(bpg_ctx* ctx, bpg_transcript* t, size_t n, const u
   if (rc) return rc;
   if (G_factors || H_factors)  // canonical scalars only (Scalar::from_canonical_bytes at the Rust boundary)
     for (size_t i = 0; i < n; i++) {
-      Scalar f;
-      if (G_factors && !Scalar::from_bytes(G_factors + 32 * i, &f)) return BPG_ERR_DECODE;
-      if (H_factors && !Scalar::from_bytes(H_factors + 32 * i, &f)) return BPG_ERR_DECODE;
+      if (G_factors && !Scalar::is_canonical(G_factors + 32 * i)) return BPG_ERR_DECODE;
+      if (H_factors && !Scalar::is_canonical(H_factors + 32 * i)) return BPG_ERR_DECODE;
     }
   size_t lg_n = p.L_vec.size();
   // ad-hoc terms [Q | L | R] with scalars [a*b | -u_sq | -u_inv_sq]; the 2n generator scalars

@@ -87,6 +87,12 @@ struct Scalar {
     *out = montmul(a, RR());
     return true;
   }
+  // canonical encoding? (x < l), without converting
+  static bool is_canonical(const uint8_t b[32]) {
+    uint64_t a[4];
+    memcpy(a, b, 32);
+    return !geq_l(a);
+  }
   // any 32 bytes, reduced mod l
   static Scalar from_bytes_mod_order(const uint8_t b[32]) {
     uint64_t a[4];

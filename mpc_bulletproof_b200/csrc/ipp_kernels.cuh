@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(IPP_THREADS) k_ipp_cross_finish(const uint32_t
                                                                    uint32_t nparts, uint32_t n,
                                                                    const uint32_t* __restrict__ q_mul /*null or scalar*/,
                                                                    uint32_t* __restrict__ scalars,
-                                                                   uint8_t* __restrict__ set_ids) {
+                                                                   uint8_t* __restrict__ set_ids,
+                                                                   uint32_t* __restrict__ q_side /*null, or c_L | c_R go here*/) {
   __shared__ uint32_t sm[IPP_THREADS / 2][16];
   sc cl = sc_zero(), cr = sc_zero();
   for (uint32_t i = threadIdx.x; i < nparts; i += blockDim.x) {
@@ -114,8 +115,16 @@ __global__ void __launch_bounds__(IPP_THREADS) k_ipp_cross_finish(const uint32_t
       sc_load(q, q_mul);
       f = sc_montmul(sc_to_mont(q), f);  // q * R^2
     }
-    sc_store(scalars + (size_t)(2 * n) * 8, sc_montmul(cl, f));      // c_L * Q -> L
-    sc_store(scalars + (size_t)(2 * n + 1) * 8, sc_montmul(cr, f));  // c_R * Q -> R
+    sc vl = sc_montmul(cl, f), vr = sc_montmul(cr, f);
+    if (q_side) {
+      // Q is not in the table: c_L Q, c_R Q are formed beside the MSM (fixed-base comb of Q)
+      sc_store(q_side, vl);
+      sc_store(q_side + 8, vr);
+      vl = sc_zero();
+      vr = sc_zero();
+    }
+    sc_store(scalars + (size_t)(2 * n) * 8, vl);      // c_L * Q -> L
+    sc_store(scalars + (size_t)(2 * n + 1) * 8, vr);  // c_R * Q -> R
     set_ids[2 * n] = 0;
     set_ids[2 * n + 1] = 1;
   }

@@ -395,7 +395,12 @@ __device__ __forceinline__ ge_ext ge_from_niels(const ge_niels& q, bool neg) {
   return r;
 }
 
-__global__ void __launch_bounds__(ACC_THREADS) k_accum(const uint32_t* __restrict__ table,
+// Software pipeline: the Niels entry of step k+1 (and the entry word of step k+2) are loaded
+// before step k multiplies.  Measured at 2^20 points (13.6 M additions): 0.899 ms, against 0.947 ms
+// with only the entry word prefetched (112 registers), the same 0.948 ms when that form is
+// compiled for 5 blocks/SM (96 registers: occupancy is not the limiter), and 0.925 ms with two
+// entries in flight (150 registers).
+__global__ void __launch_bounds__(ACC_THREADS, 1) k_accum(const uint32_t* __restrict__ table,
                                                         const uint32_t* __restrict__ offsets,
                                                         const uint32_t* __restrict__ entries, AccSched sc,
                                                         uint32_t* __restrict__ bucket_sums,
@@ -408,16 +413,18 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accum(const uint32_t* __restric
   uint32_t beg = b_beg + it.y * ACC_SEG, end = min(b_end, beg + ACC_SEG);
   ge_ext acc = ge_identity();
   if (beg < end) {
-    // software pipeline: the entry word of step k+1 is in flight while step k multiplies
     uint32_t e = __ldg(entries + beg);
     ge_niels q;
     ge_load_niels(q, table + (size_t)(e & ~ENTRY_NEG) * 24);
     uint32_t e_next = beg + 1 < end ? __ldg(entries + beg + 1) : 0;
     acc = ge_from_niels(q, (e & ENTRY_NEG) != 0);
+    ge_niels qn;
+    if (beg + 1 < end) ge_load_niels(qn, table + (size_t)(e_next & ~ENTRY_NEG) * 24);
     for (uint32_t i = beg + 1; i < end; i++) {
       e = e_next;
-      ge_load_niels(q, table + (size_t)(e & ~ENTRY_NEG) * 24);
-      e_next = i + 1 < end ? __ldg(entries + i + 1) : 0;
+      q = qn;
+      e_next = i + 1 < end ? __ldg(entries + i + 1) : e;
+      ge_load_niels(qn, table + (size_t)(e_next & ~ENTRY_NEG) * 24);  // next point (or a harmless re-read)
       acc = ge_madd(acc, q, (e & ENTRY_NEG) != 0);
     }
   }

@@ -316,3 +316,33 @@ def test_square_chain_gadget(ctx, env):
     for _ in range(n):
         _, _, var = ov.multiply(var, var)
     ov.verify(O.R1CSProof.from_bytes(proofs[0]), bp)
+
+
+@pytest.mark.parametrize("n", [2, 8, 64])
+def test_ipp_on_shared_windowed_table(ctx, n):
+    """G and H as two ranges of ONE windowed table (a resident BulletproofGens) and an arbitrary Q:
+    the round MSMs run over the caller's table, c_L Q and c_R Q come from a comb of Q.  Same proof
+    bytes as the oracle; verification through the same table."""
+    from mpc_bulletproof_b200 import Table
+    from mpc_bulletproof_b200 import protocol as P
+
+    r = random.Random(5000 + n)
+    bp = O.BulletproofGens(n, 1)
+    Gs, Hs = bp.G(n), bp.H(n)
+    Q = G.hash_to_group_sha512(b"shared table q")
+    a = [r.randrange(L) for _ in range(n)]
+    b = [r.randrange(L) for _ in range(n)]
+    Gf = [r.randrange(1, L) for _ in range(n)]
+    Hf = [r.randrange(1, L) for _ in range(n)]
+    want = O.InnerProductProof.create(O.Transcript(b"shared"), Q, Gf, Hf, Gs, Hs, a, b)
+    pad = [G.BASEPOINT] * 3  # ranges need not start at 0 nor be adjacent
+    t = Table(ctx, points_bytes(pad + Gs + pad + Hs)).set_windows(0)
+    g_off, h_off = 3, 3 + n + 3
+    got = P.InnerProductProof.create(ctx, P.Transcript(b"shared"), Q.encode(), Gf, Hf, t, t, a, b, g_off=g_off, h_off=h_off)
+    assert got.to_bytes() == want.to_bytes()
+    c = O.inner_product(a, b)
+    Ppt = G.msm([a[i] * Gf[i] % L for i in range(n)] + [b[i] * Hf[i] % L for i in range(n)] + [c], Gs + Hs + [Q])
+    got.verify(ctx, n, P.Transcript(b"shared"), Gf, Hf, Ppt.encode(), Q.encode(), t, t, g_off=g_off, h_off=h_off)
+    with pytest.raises(P.VerificationError):
+        got.verify(ctx, n, P.Transcript(b"shared"), Gf, Hf, (Ppt + Q).encode(), Q.encode(), t, t, g_off=g_off, h_off=h_off)
+    t.close()
