@@ -417,7 +417,7 @@ static int pick_window(size_t n_per_set, int forced) {
 static uint32_t pick_gsub(size_t n_per_set, int nsets, int c, int W) {
   double nb = (double)(1u << (c - 1));
   double lists_for_len = (double)n_per_set * W / (nb * 32.0);       // groups that make the lists ~32 long
-  double lists_for_par = (double)(1u << 18) / (nb * (double)nsets);  // groups that give ~2^18 lists
+  double lists_for_par = (double)(1u << 17) / (nb * (double)nsets);  // groups that give ~2^17 lists (more only add merge work)
   double avg1 = (double)n_per_set * W / nb;                          // list length with one group
   double g = std::max(lists_for_len, std::min(lists_for_par, avg1 / 8.0));  // never below ~8 entries per list
   uint32_t gs = (uint32_t)(g + 0.5);
