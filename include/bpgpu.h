@@ -333,6 +333,10 @@ int bpg_cs_eval(bpg_cs* cs, const bpg_term* lc, size_t n, uint8_t out[32]);
 /* The reference's benchmark circuit (benches/r1cs.rs:24-32): n chained squarings starting from `var`;
  * equivalent to n calls of bpg_cs_multiply(var, var).  out (may be NULL) = the last output variable. */
 int bpg_gadget_square_chain(bpg_cs* cs, bpg_var var, size_t n, bpg_var* out);
+/* BASELINE.json config 4: n_mult multipliers with uniform a_L, a_R and n_cons random
+ * linear constraints over (a_L, a_R, a_O, v) with constants c0 fixed from the witness; everything from
+ * xoshiro256**(seed).  c0: n_cons x 32 bytes, written by the prover, read by the verifier. */
+int bpg_gadget_random_circuit(bpg_cs* cs, uint64_t seed, size_t n_mult, size_t n_cons, uint8_t* c0);
 size_t bpg_cs_num_multipliers(const bpg_cs* cs);
 size_t bpg_cs_num_constraints(const bpg_cs* cs);
 /* Prover::prove.  The reference draws its blinding scalars from thread_rng()

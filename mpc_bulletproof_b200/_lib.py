@@ -68,6 +68,7 @@ _SIGNATURES = {
     "bpg_cs_challenge_scalar": (_I, [_P, _CP, _P]),
     "bpg_cs_eval": (_I, [_P, ctypes.POINTER(Term), _SZ, _P]),
     "bpg_cs_num_multipliers": (_SZ, [_P]),
+    "bpg_gadget_random_circuit": (_I, [_P, ctypes.c_uint64, _SZ, _SZ, _P]),
     "bpg_gadget_square_chain": (_I, [_P, ctypes.c_uint64, _SZ, ctypes.POINTER(ctypes.c_uint64)]),
     "bpg_cs_num_constraints": (_SZ, [_P]),
     "bpg_prover_prove": (_I, [_P, _U64, _P, _SZ, ctypes.POINTER(_SZ)]),

@@ -699,6 +699,43 @@ extern "C" int bpg_gadget_square_chain(bpg_cs* cs, bpg_var var, size_t n, bpg_va
   return BPG_OK;
 }
 
+// BASELINE.json config 4 / SURVEY.md 8d: the synthetic random circuit.  n_mult multipliers with uniform
+// a_L, a_R and n_cons constraints  c1 a_L[i1] + c2 a_R[i2] + c3 a_O[i3] + c4 v[j] - c0 = 0  over the
+// variables committed so far; indices and coefficients from xoshiro256**(seed) in a fixed draw order
+// (oracle/gadgets.py random_circuit is the same definition).  The prover writes the public constants
+// c0 (n_cons x 32 bytes, fixed from its witness), the verifier reads them.
+extern "C" int bpg_gadget_random_circuit(bpg_cs* cs, uint64_t seed, size_t n_mult, size_t n_cons, uint8_t* c0) {
+  if (!cs || !c0 || n_mult == 0) return BPG_ERR_ARG;
+  size_t m = cs->is_prover ? cs->v.size() : cs->V.size();
+  if (m == 0) return BPG_ERR_ARG;
+  Xoshiro rng(seed);
+  size_t base = cs->num_multipliers();
+  for (size_t i = 0; i < n_mult; i++) {
+    Scalar l = rng.scalar(), r = rng.scalar();
+    bpg_var o[3];
+    cs->allocate_multiplier(&l, &r, o);
+  }
+  const Scalar minus_one = -Scalar::one();
+  for (size_t q = 0; q < n_cons; q++) {
+    uint64_t i1 = rng.next() % n_mult, i2 = rng.next() % n_mult, i3 = rng.next() % n_mult, j = rng.next() % m;
+    Scalar c1 = rng.scalar(), c2 = rng.scalar(), c3 = rng.scalar(), c4 = rng.scalar(), k0;
+    if (cs->is_prover) {
+      k0 = c1 * cs->a_L[base + i1] + c2 * cs->a_R[base + i2] + c3 * cs->a_O[base + i3] + c4 * cs->v[j];
+      k0.to_bytes(c0 + 32 * q);
+    } else if (!Scalar::from_bytes(c0 + 32 * q, &k0)) {
+      return BPG_ERR_DECODE;
+    }
+    LinComb lc(5);
+    lc[0] = {mkvar(V_LEFT, base + i1), c1};
+    lc[1] = {mkvar(V_RIGHT, base + i2), c2};
+    lc[2] = {mkvar(V_OUT, base + i3), c3};
+    lc[3] = {mkvar(V_COMMITTED, j), c4};
+    lc[4] = {mkvar(V_ONE, 0), minus_one * k0};
+    cs->add_constraint(lc);
+  }
+  return BPG_OK;
+}
+
 // ---------------------------------------------------------------- R1CS proof bytes
 struct R1CSProof {
   Bytes32 A_I1, A_O1, S1, A_I2, A_O2, S2, T_1, T_3, T_4, T_5, T_6;

@@ -116,6 +116,15 @@ class Gens:
         except Exception:
             pass
 
+    @property
+    def table(self) -> Table:
+        """The resident windowed table [G (capacity) | H (capacity) | B | B_blinding] (borrowed)."""
+        t = Table.__new__(Table)
+        t.ctx = self.ctx
+        t._h = ctypes.c_void_p(lib().bpg_gens_table(self._h))
+        t.close = lambda: None  # owned by the Gens
+        return t
+
     def commit(self, value: int, blinding: int) -> bytes:
         """PedersenGens::commit (reference src/generators.rs:41-43)"""
         return self.commit_batch([value], [blinding])[0]
@@ -243,6 +252,13 @@ class _CS:
         idx = var[1] if len(var) > 1 else 0
         _raise(lib().bpg_gadget_square_chain(self._h, (_KIND[var[0]] << 56) | idx, n, ctypes.byref(out)))
         return _var(out.value)
+
+    def random_circuit(self, seed: int, n_mult: int, n_cons: int, c0: bytes | None = None) -> bytes:
+        """BASELINE.json config 4: the synthetic random circuit over the variables committed so far.
+        Prover: returns the public constants c0 (n_cons x 32 bytes); verifier: pass them in."""
+        buf = ctypes.create_string_buffer(c0 if c0 is not None else b"", 32 * n_cons)
+        _raise(lib().bpg_gadget_random_circuit(self._h, seed, n_mult, n_cons, buf))
+        return buf.raw
 
     def constrain(self, lc):
         arr, n = _terms(lc)

@@ -59,3 +59,39 @@ def dummy_circuit(cs, n_constraints, val):
     var = cs.commit_public(val)
     for _ in range(n_constraints):
         _, _, var = cs.multiply(_lc(var), _lc(var))
+
+
+def random_circuit(cs, seed, n_mult, n_cons, v_assignment=None, c0=None):
+    """SURVEY.md §8d config 4 (BASELINE.json "synthetic random R1CS circuit"): n_mult multipliers
+    with uniform a_L, a_R (a_O = a_L o a_R) and n_cons linear constraints
+        c1 a_L[i1] + c2 a_R[i2] + c3 a_O[i3] + c4 v[j] - c0 = 0
+    over the m variables already committed, indices and coefficients from xoshiro256**(seed),
+    c0 fixed from the witness so that the system is satisfied.  The prover passes the committed
+    values and gets the public constants c0 back; the verifier passes those constants.
+    The draw order is part of the definition (the product's native gadget follows it)."""
+    from .protocol import Xoshiro256ss
+
+    rng = Xoshiro256ss(seed)
+    proving = v_assignment is not None
+    m = len(v_assignment) if proving else len(cs.V)
+    assert m >= 1
+    aL, aR, aO, vars_ = [], [], [], []
+    for _ in range(n_mult):
+        l, r = rng.scalar(), rng.scalar()
+        aL.append(l)
+        aR.append(r)
+        aO.append(l * r % L)
+        vars_.append(cs.allocate_multiplier(l, r) if proving else cs.allocate_multiplier(None, None))
+    out = []
+    for q in range(n_cons):
+        i1, i2, i3 = rng.next_u64() % n_mult, rng.next_u64() % n_mult, rng.next_u64() % n_mult
+        j = rng.next_u64() % m
+        c1, c2, c3, c4 = rng.scalar(), rng.scalar(), rng.scalar(), rng.scalar()
+        if proving:
+            k0 = (c1 * aL[i1] + c2 * aR[i2] + c3 * aO[i3] + c4 * v_assignment[j]) % L
+        else:
+            k0 = c0[q]
+        out.append(k0)
+        lc = LC([(vars_[i1][0], c1), (vars_[i2][1], c2), (vars_[i3][2], c3), (("V", j), c4), (ONE, (-k0) % L)])
+        cs.constrain(lc)
+    return out

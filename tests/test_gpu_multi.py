@@ -107,3 +107,39 @@ def test_batch_verify(ctx):
     assert P.batch_verify(jobs) == want
     assert P.batch_verify([]) == []
     gens.close()
+
+
+def test_mpc_share_commitments_equal_the_provers(ctx):
+    """Config 5 in miniature (reference integration/mpc_prover.rs): two parties hold additive shares
+    of the witness rows and of the blinding factors; each commits to its shares over the shared
+    generator table (one partial-sum launch, sets = A_I and A_O), the partials are exchanged and
+    added.  The opened A_I1, A_O1 must be the very points the single prover puts in its proof."""
+    from mpc_bulletproof_b200 import protocol as P
+    from mpc_bulletproof_b200.api import sum_encode
+    from mpc_bulletproof_b200.protocol import Gens
+
+    n, seed, val = 16, 4242, 3
+    pc, bp = O.PedersenGens(), O.BulletproofGens(n, 1)
+    gens = Gens(ctx, points_bytes(bp.G(n)), points_bytes(bp.H(n)), pc.B.encode(), pc.B_blinding.encode())
+    p = P.Prover(gens, P.Transcript(b"mpc"))
+    p.square_chain(p.commit_public(val), n)
+    proof = p.prove(seed)
+    A_I1, A_O1 = proof[1:33], proof[33:65]
+    # the witness of the squaring chain and the prover's first two blinding draws (prover.rs:457-458)
+    aL, x = [], val
+    for _ in range(n):
+        aL.append(x)
+        x = x * x % L
+    aR, aO = list(aL), [v * v % L for v in aL]
+    blind = O.Blindings(seed)
+    i_b, o_b = blind.scalar(), blind.scalar()
+    # table order [G | H | B | B_blinding]; set 0 = A_I terms, set 1 = A_O terms
+    plain = [aL + aR + [0, i_b], aO + [0] * n + [0, o_b]]
+    r = rng(303)
+    share0 = [[rand_scalar(r) for _ in row] for row in plain]
+    shares = [share0, [[(v - s) % L for v, s in zip(row, s0)] for row, s0 in zip(plain, share0)]]
+    t = gens.table
+    parts = b"".join(t.msm_partial(b"".join(scalars_bytes(row) for row in shares[party]), n_sets=2) for party in range(2))
+    opened = sum_encode(ctx, parts, 2, 2)
+    assert opened == [A_I1, A_O1]
+    gens.close()

@@ -346,3 +346,49 @@ def test_ipp_on_shared_windowed_table(ctx, n):
     with pytest.raises(P.VerificationError):
         got.verify(ctx, n, P.Transcript(b"shared"), Gf, Hf, (Ppt + Q).encode(), Q.encode(), t, t, g_off=g_off, h_off=h_off)
     t.close()
+
+
+def test_random_circuit_gadget(ctx, env):
+    """BASELINE.json config 4 in miniature: random linear constraints over (a_L, a_R, a_O, v) with
+    public constants (the constant term of every row exercises the device flattening's w_c path).
+    The native gadget and the oracle's build the same system: byte-identical proofs."""
+    from mpc_bulletproof_b200 import protocol as P
+
+    pc, bp, gens = env
+    seed, n_mult, n_cons, m = 77, 23, 51, 3
+    r = random.Random(9)
+    vs = [r.randrange(L) for _ in range(m)]
+    vb = [r.randrange(L) for _ in range(m)]
+    # oracle
+    op = O.Prover(pc, O.Transcript(b"rand"))
+    Vs = [op.commit(v, b)[0] for v, b in zip(vs, vb)]
+    c0 = gadgets.random_circuit(op, seed, n_mult, n_cons, v_assignment=vs)
+    want = op.prove(bp, O.Blindings(31)).to_bytes()
+    # product, native gadget
+    p = P.Prover(gens, P.Transcript(b"rand"))
+    got_V = [p.commit(v, b)[0] for v, b in zip(vs, vb)]
+    assert got_V == [V.encode() for V in Vs]
+    c0_native = p.random_circuit(seed, n_mult, n_cons)
+    assert c0_native == b"".join(G.sc_to_bytes(k) for k in c0)
+    proof = p.prove(31)
+    assert proof == want
+    # verifier: native gadget with the public constants; the oracle's verifier agrees
+    v = P.Verifier(gens, P.Transcript(b"rand"))
+    for V in got_V:
+        v.commit(V)
+    v.random_circuit(seed, n_mult, n_cons, c0_native)
+    v.verify(proof)
+    ov = O.Verifier(pc, O.Transcript(b"rand"))
+    for V in Vs:
+        ov.commit(V)
+    gadgets.random_circuit(ov, seed, n_mult, n_cons, c0=c0)
+    ov.verify(O.R1CSProof.from_bytes(proof), bp)
+    # a wrong constant is a false statement
+    bad = bytearray(c0_native)
+    bad[0] ^= 1
+    v = P.Verifier(gens, P.Transcript(b"rand"))
+    for V in got_V:
+        v.commit(V)
+    v.random_circuit(seed, n_mult, n_cons, bytes(bad))
+    with pytest.raises(P.VerificationError):
+        v.verify(proof)

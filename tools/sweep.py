@@ -158,6 +158,34 @@ def sweep_r1cs(ctx, comb, lgs):
     return rows
 
 
+def random_circuit(ctx, comb, lg=16, m=16):
+    """BASELINE.json config 4: 2^lg multipliers, 2^(lg+1) random linear constraints, m committed values."""
+    n = 1 << lg
+    Gb = bytes(dev_points(ctx, comb, n, 1).cpu().numpy().tobytes())
+    Hb = bytes(dev_points(ctx, comb, n, 2).cpu().numpy().tobytes())
+    Bb = bytes(dev_points(ctx, comb, 1, 4).cpu().numpy().tobytes())
+    gens = P.Gens(ctx, Gb, Hb, BASE, Bb)
+    vals = [1000 + 7 * j for j in range(m)]
+    pm, vm, proof, c0 = [], [], None, None
+    for it in range(5):
+        p = P.Prover(gens, P.Transcript(b"bench rand"))
+        Vs = [p.commit(v, 5 + j)[0] for j, v in enumerate(vals)]
+        c0 = p.random_circuit(99, n, 2 * n)
+        t0 = time.perf_counter()
+        proof = p.prove(4321 + it)
+        pm.append((time.perf_counter() - t0) * 1e3)
+        v = P.Verifier(gens, P.Transcript(b"bench rand"))
+        for V in Vs:
+            v.commit(V)
+        v.random_circuit(99, n, 2 * n, c0)
+        t0 = time.perf_counter()
+        v.verify(proof)
+        vm.append((time.perf_counter() - t0) * 1e3)
+    gens.close()
+    return {"lg_multipliers": lg, "constraints": 2 * n, "terms": 10 * n, "committed": m, "prove_ms": round(med(pm[1:]), 3),
+            "verify_ms": round(med(vm[1:]), 3), "proof_bytes": len(proof)}
+
+
 def main():
     what = (sys.argv[1] if len(sys.argv) > 1 else "msm,ipp,r1cs").split(",")
     max_lg = int(sys.argv[2]) if len(sys.argv) > 2 else 24
@@ -170,6 +198,8 @@ def main():
         out["ipp"] = sweep_ipp(ctx, comb, [10, 12, 14, 16, 18])
     if "r1cs" in what:
         out["r1cs"] = sweep_r1cs(ctx, comb, [10, 12, 14, 16, 18])
+    if "rand" in what:
+        out["random_circuit"] = random_circuit(ctx, comb)
     print(json.dumps(out))
 
 
