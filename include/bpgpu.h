@@ -263,6 +263,24 @@ int bpg_r1cs_dev_ipp_begin(bpg_r1cs_dev* st, const bpg_table* gens, size_t g_bas
                            const uint8_t q_mul[32], size_t n, size_t n1, size_t N, const void* x_mont,
                            const void* u_mont, const void* y_pow, const void* y_inv_pow, bpg_ipp** out);
 
+/* ==== Stark-curve policy ============================================
+ * The mounted fork computes over the Stark curve (y^2 = x^3 + x + beta over F_p,
+ * p = 2^251 + 17*2^192 + 1) through mpc-stark's StarkPoint (reference Cargo.toml:13,21,
+ * src/generators.rs:11-16).  Same Pippenger pipeline, second field/curve policy.  Points cross
+ * the boundary as affine x || y, 32 bytes little-endian each (the fork's transcript encoding,
+ * src/util.rs:274-289); the identity is 64 zero bytes; scalars are 32 bytes little-endian, reduced
+ * mod the group order.  BPG_ERR_DECODE for a coordinate >= p or a point off the curve.
+ * Round 1 covers `StarkPoint::msm_iter` / `::msm`; the protocol layers above keep using the
+ * ristretto255 instantiation. */
+typedef struct bpg_stark_table bpg_stark_table;
+int bpg_stark_table_upload(bpg_ctx* ctx, const uint8_t* points_xy /* n*64 */, size_t n, bpg_stark_table** out);
+size_t bpg_stark_table_len(const bpg_stark_table* t);
+void bpg_stark_table_free(bpg_stark_table* t);
+/* out[s] = sum_i scalars[s*n + i] * table[offset + i], n_sets x 64 bytes */
+int bpg_stark_msm_table(bpg_ctx* ctx, const bpg_stark_table* table, size_t offset, size_t n, const uint8_t* scalars_le,
+                        int n_sets, uint8_t* out_xy);
+int bpg_stark_msm(bpg_ctx* ctx, const uint8_t* scalars_le, const uint8_t* points_xy, size_t n, uint8_t out_xy[64]);
+
 /* ==== host mirror of the reference's protocol layer ==================================
  * C bindings of the C++ host code in mpc_bulletproof_b200/csrc/host/: the transcript,
  * the generators as resident tables, InnerProductProof and the R1CS Prover/Verifier with

@@ -14,6 +14,7 @@
 #include "msm_kernels.cuh"
 #include "ipp_kernels.cuh"
 #include "svec_kernels.cuh"
+#include "stark_msm.cuh"
 
 using namespace bpg;
 
@@ -471,8 +472,10 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 // be null (implicit: term t -> point t % n_points of `table_base`, set t / n_points).
 static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points, const uint32_t* d_scalars,
                        size_t n_terms, const uint8_t* d_set_ids, const uint32_t* d_point_ids, int nsets,
-                       uint32_t* d_out_ext, int win_c = 0, size_t win_stride = 0, int lane = 0) {
-  if (nsets <= 0) return BPG_ERR_ARG;
+                       uint32_t* d_out_ext, int win_c = 0, size_t win_stride = 0, int lane = 0, int curve = 0) {
+  // curve 0: ristretto255 (Niels table, 24 words per entry); curve 1: Stark curve (affine table, 16 words
+  // per entry, plain tables only).  Sort and schedule are shared; the bucket arithmetic differs.
+  if (nsets <= 0 || (curve == 1 && win_c)) return BPG_ERR_ARG;
   // lane 1: the auxiliary stream and arena (no phase profiling there)
   struct ProfOff {
     bpg_ctx* c;
@@ -484,7 +487,8 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   uint8_t* const& ws = lane ? ctx->ws_aux : ctx->ws;
   if (n_terms == 0) {
     // empty sum: identity for every set
-    k_set_identity<<<nsets, 32, 0, st>>>(d_out_ext);
+    if (curve == 1) k_stark_set_identity<<<nsets, 32, 0, st>>>(d_out_ext);
+    else k_set_identity<<<nsets, 32, 0, st>>>(d_out_ext);
     LAUNCH_CHECK();
     return BPG_OK;
   }
@@ -511,6 +515,10 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   size_t o_entries = off; off += align_up((size_t)n_terms * cfg.W * 4);
   size_t o_buckets = off; off += align_up((size_t)cfg.B * 128);
   size_t o_merged = off;  off += (windowed && cfg.gsub > 1) ? align_up((size_t)nsets * cfg.nb * 128) : 0;
+  if (curve == 1) {
+    rarr = cfg.narr;
+    tiles0 = (cfg.nb + SLEAF_LC - 1) / SLEAF_LC;
+  }
   size_t o_pairs = off;   off += 4 * align_up((size_t)rarr * tiles0 * 128);  // (A, Y) x ping-pong
   size_t o_wins = off;    off += align_up((size_t)rarr * 128);
   // accumulation schedule: at most one item per bucket plus one per ACC_SEG entries
@@ -570,6 +578,45 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   LAUNCH_CHECK();
   k_size_scatter<<<(cfg.B + 255) / 256, 256, 0, st>>>(offsets, cfg, sched, big_count, big_list);
   LAUNCH_CHECK();
+  if (curve == 1) {
+    // ---- Stark-curve policy: same stages, short-Weierstrass bucket arithmetic (stark_msm.cuh) ----
+    prof_mark(ctx, BPG_PROF_ACCUM);
+    k_stark_accum<<<(unsigned)((max_items + SACC_THREADS - 1) / SACC_THREADS), SACC_THREADS, 0, st>>>(
+        table_base, offsets, entries, sched, buckets, seg_part);
+    LAUNCH_CHECK();
+    prof_mark(ctx, BPG_PROF_ACCUM_BIG);
+    k_stark_fix<<<(unsigned)std::min<size_t>((max_multi + 127) / 128, (size_t)ctx->sm_count * 8), 128, 0, st>>>(
+        offsets, sched, seg_part, buckets);
+    LAUNCH_CHECK();
+    unsigned gb = std::min<unsigned>(cfg.big_cap, (unsigned)ctx->sm_count * 4);
+    k_stark_big<<<gb, SBIG_THREADS, 0, st>>>(table_base, offsets, entries, cfg, buckets, big_count, big_list, big_part);
+    LAUNCH_CHECK();
+    k_stark_big_fin<<<std::min<unsigned>((cfg.big_cap + 127) / 128, (unsigned)ctx->sm_count), 128, 0, st>>>(
+        cfg, buckets, big_count, big_list, big_part);
+    LAUNCH_CHECK();
+    prof_mark(ctx, BPG_PROF_REDUCE);
+    uint32_t t = (cfg.nb + SLEAF_LC - 1) / SLEAF_LC;  // pairs per array after the leaf pass
+    uint32_t* pa[2] = {pairs, pairs + 2 * pair_words};
+    int cur = 0;
+    uint32_t* oa = t == 1 ? wins : pa[cur];
+    k_stark_leaf<<<(cfg.narr * t + 127) / 128, 128, 0, st>>>(buckets, cfg.nb, t, cfg.narr, oa, pa[cur] + pair_words);
+    LAUNCH_CHECK();
+    while (t > 1) {
+      uint32_t n = t;
+      t = (n + SPAIR_N - 1) / SPAIR_N;
+      const uint32_t* ia = pa[cur];
+      const uint32_t* iy = pa[cur] + pair_words;
+      cur ^= 1;
+      oa = t == 1 ? wins : pa[cur];
+      k_stark_pairs<<<cfg.narr * t, SPAIR_N, 0, st>>>(ia, iy, n, t, oa, pa[cur] + pair_words);
+      LAUNCH_CHECK();
+    }
+    prof_mark(ctx, BPG_PROF_HORNER);
+    k_stark_horner<<<(nsets + 31) / 32, 32, 0, st>>>(wins, cfg, d_out_ext);
+    LAUNCH_CHECK();
+    prof_mark(ctx, -1);
+    return BPG_OK;
+  }
   prof_mark(ctx, BPG_PROF_ACCUM);
   k_accum<<<(unsigned)((max_items + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, st>>>(table_base, offsets, entries,
                                                                                           sched, buckets, seg_part);
@@ -1324,3 +1371,4 @@ extern "C" int bpg_msm_mixed(bpg_ctx* ctx, const uint8_t* adhoc_points, size_t n
 }
 
 #include "r1cs_dev.inc"
+#include "stark_msm.inc"

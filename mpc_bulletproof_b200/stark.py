@@ -1,0 +1,55 @@
+"""Stark-curve instantiation of the group-level seam: the mounted fork's
+`StarkPoint::msm_iter(scalars, points)` (mpc-stark; reference src/inner_product_proof.rs:90,
+src/r1cs/verifier.rs:516) as `msm(ctx, scalars, points)`, generator tables as `StarkTable`.
+Scalars are 32-byte little-endian (mod the group order), points are affine x || y, 32 bytes
+little-endian each (reference src/util.rs:274-289), the identity 64 zero bytes."""
+from __future__ import annotations
+
+import ctypes
+
+from . import _lib
+from ._lib import check, lib
+from .api import Context
+
+
+class StarkTable:
+    """Stark-curve points resident in HBM (affine, Montgomery form)."""
+
+    def __init__(self, ctx: Context, points_xy: bytes):
+        assert len(points_xy) % 64 == 0
+        self.ctx = ctx
+        self._h = ctypes.c_void_p()
+        check(lib().bpg_stark_table_upload(ctx._h, points_xy, len(points_xy) // 64, ctypes.byref(self._h)))
+        ctx._children.add(self)
+
+    def __len__(self):
+        return int(lib().bpg_stark_table_len(self._h))
+
+    def close(self):
+        if self._h:
+            lib().bpg_stark_table_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def msm(self, scalars: bytes, n_sets: int = 1, offset: int = 0, n: int | None = None) -> list[bytes]:
+        if n is None:
+            n = len(self) - offset
+        if len(scalars) != 32 * n * n_sets:
+            raise _lib.BpgError(_lib.BPG_ERR_LEN, "scalar buffer length does not match n * n_sets")
+        out = ctypes.create_string_buffer(64 * n_sets)
+        check(lib().bpg_stark_msm_table(self.ctx._h, self._h, offset, n, scalars, n_sets, out))
+        return [out.raw[64 * i : 64 * i + 64] for i in range(n_sets)]
+
+
+def msm(ctx: Context, scalars: bytes, points_xy: bytes) -> bytes:
+    """sum_i scalars[i] * points[i] -> 64-byte affine x || y."""
+    if len(scalars) * 2 != len(points_xy) or len(scalars) % 32:
+        raise _lib.BpgError(_lib.BPG_ERR_LEN, "scalars and points differ in length")
+    out = ctypes.create_string_buffer(64)
+    check(lib().bpg_stark_msm(ctx._h, scalars, points_xy, len(scalars) // 32, out))
+    return out.raw

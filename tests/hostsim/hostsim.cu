@@ -6,6 +6,7 @@
 #include <cstring>
 #include "../../mpc_bulletproof_b200/csrc/ge.cuh"
 #include "../../mpc_bulletproof_b200/csrc/sc.cuh"
+#include "../../mpc_bulletproof_b200/csrc/stark_pt.cuh"
 using namespace bpg;
 
 static fe ld(const uint32_t* p) { fe a; for (int i = 0; i < 8; i++) a.v[i] = p[i]; return a; }
@@ -15,7 +16,25 @@ static void ste(uint32_t* p, const ge_ext& e) { st(p, e.X); st(p + 8, e.Y); st(p
 static ge_niels ldn(const uint32_t* p) { ge_niels e; e.ypx = ld(p); e.ymx = ld(p + 8); e.t2d = ld(p + 16); return e; }
 static void stn(uint32_t* p, const ge_niels& e) { st(p, e.ypx); st(p + 8, e.ymx); st(p + 16, e.t2d); }
 
+static fp ldp(const uint32_t* p) { fp a; for (int i = 0; i < 8; i++) a.v[i] = p[i]; return a; }
+static void stp(uint32_t* p, const fp& a) { for (int i = 0; i < 8; i++) p[i] = a.v[i]; }
+static sp_xyzz ldx(const uint32_t* p) { sp_xyzz e; e.X = ldp(p); e.Y = ldp(p + 8); e.ZZ = ldp(p + 16); e.ZZZ = ldp(p + 24); return e; }
+static void stx(uint32_t* p, const sp_xyzz& e) { stp(p, e.X); stp(p + 8, e.Y); stp(p + 16, e.ZZ); stp(p + 24, e.ZZZ); }
+
 extern "C" {
+// ---- Stark-curve policy (stark_fp.cuh, stark_pt.cuh) ----
+void hs_fp_mul(const uint32_t* a, const uint32_t* b, uint32_t* o) { stp(o, fp_mul(ldp(a), ldp(b))); }
+void hs_fp_add(const uint32_t* a, const uint32_t* b, uint32_t* o) { stp(o, fp_add(ldp(a), ldp(b))); }
+void hs_fp_sub(const uint32_t* a, const uint32_t* b, uint32_t* o) { stp(o, fp_sub(ldp(a), ldp(b))); }
+void hs_fp_invert(const uint32_t* a, uint32_t* o) { stp(o, fp_invert(ldp(a))); }
+void hs_fp_to_mont(const uint32_t* a, uint32_t* o) { stp(o, fp_to_mont(ldp(a))); }
+void hs_fp_from_mont(const uint32_t* a, uint32_t* o) { stp(o, fp_from_mont(ldp(a))); }
+int hs_sp_from_affine(const uint32_t* xy, uint32_t* aff) { sp_aff q; bool ok = sp_from_affine_words(q, xy); stp(aff, q.x); stp(aff + 8, q.y); return ok; }
+void hs_sp_to_affine(const uint32_t* x, uint32_t* xy) { sp_to_affine_words(xy, ldx(x)); }
+void hs_sp_from_aff(const uint32_t* aff, uint32_t* o) { sp_aff q; q.x = ldp(aff); q.y = ldp(aff + 8); stx(o, sp_from_aff(q)); }
+void hs_sp_madd(const uint32_t* x, const uint32_t* aff, int neg, uint32_t* o) { sp_aff q; q.x = ldp(aff); q.y = ldp(aff + 8); stx(o, sp_madd(ldx(x), q, neg)); }
+void hs_sp_add(const uint32_t* a, const uint32_t* b, uint32_t* o) { stx(o, sp_add(ldx(a), ldx(b))); }
+void hs_sp_dbl(const uint32_t* a, uint32_t* o) { stx(o, sp_dbl(ldx(a))); }
 void hs_fe_mul(const uint32_t* a, const uint32_t* b, uint32_t* o) { st(o, fe_mul(ld(a), ld(b))); }
 void hs_fe_sq(const uint32_t* a, uint32_t* o) { st(o, fe_sq(ld(a))); }
 void hs_fe_add(const uint32_t* a, const uint32_t* b, uint32_t* o) { st(o, fe_add(ld(a), ld(b))); }

@@ -1,0 +1,134 @@
+"""GPU parity of the Stark-curve MSM (the group the mounted fork computes over)
+against oracle/stark.py: identical affine coordinates, byte for byte.  Same edge vectors as the
+ristretto255 suite: zero / one / n-1 scalars, the identity as an input, duplicate points (the
+short-Weierstrass formulas are not unified: P + P and P + (-P) take their own paths), repeated
+scalars (over-long buckets), several window widths, several sets."""
+import pytest
+
+from oracle import stark as S
+from tests.util import rng
+
+pytestmark = pytest.mark.gpu
+N = S.N
+
+
+def _pts(r, n):
+    return [r.randrange(1, N) * S.GENERATOR for _ in range(n)]
+
+
+def _sb(ks):
+    return b"".join(S.sc_to_bytes(k) for k in ks)
+
+
+def _pb(ps):
+    return b"".join(p.encode() for p in ps)
+
+
+def _check(ctx, ks, ps):
+    from mpc_bulletproof_b200 import stark
+
+    got = stark.msm(ctx, _sb(ks), _pb(ps))
+    want = S.msm(ks, ps).encode()
+    assert got == want, (got.hex(), want.hex())
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 64, 300])
+def test_msm_random(ctx, n):
+    r = rng(700 + n)
+    _check(ctx, [r.randrange(N) for _ in range(n)], _pts(r, n))
+
+
+def test_msm_edge_scalars(ctx):
+    r = rng(711)
+    ks = [0, 1, N - 1, N - 2, 2, 2**128, 2**251, (1 << 251) - 1, N >> 1]
+    ps = _pts(r, len(ks))
+    _check(ctx, ks, ps)
+    for k, p in zip(ks, ps):
+        _check(ctx, [k], [p])
+
+
+def test_msm_edge_points(ctx):
+    r = rng(712)
+    p, q = _pts(r, 2)
+    k1, k2, k3 = (r.randrange(N) for _ in range(3))
+    _check(ctx, [k1, k2], [p, p])  # the same point twice: doubling inside a bucket when digits agree
+    _check(ctx, [k1, k1], [p, p])
+    _check(ctx, [k1, k1], [p, -p])  # cancels to the identity
+    _check(ctx, [k1, k2, k3], [S.IDENTITY, p, S.IDENTITY])
+    _check(ctx, [k1, N - k1], [p, p])
+    _check(ctx, [5, 5, 5], [p, q, p])
+    _check(ctx, [0, 0], [p, q])
+
+
+def test_msm_one_bucket_and_segments(ctx):
+    """Repeated scalars: every term of a window in one bucket (multi-segment and block paths)."""
+    from mpc_bulletproof_b200 import stark
+
+    r = rng(713)
+    m, reps = 256, 12
+    ps = _pts(r, m)
+    total = S.msm([1] * m, ps)
+    k = r.randrange(N)
+    for kk in (1, k):
+        want = (kk * reps % N) * total
+        assert stark.msm(ctx, _sb([kk]) * (m * reps), _pb(ps) * reps) == want.encode()
+    bits = [i & 1 for i in range(m)]
+    _check(ctx, bits, ps)
+
+
+@pytest.mark.parametrize("c", [3, 5, 8, 11, 13])
+def test_msm_all_windows(ctx, c):
+    r = rng(720 + c)
+    n = 200
+    ks = [r.randrange(N) for _ in range(n)]
+    ps = _pts(r, n)
+    ctx.set_window(c)
+    try:
+        _check(ctx, ks, ps)
+    finally:
+        ctx.set_window(0)
+
+
+def test_table_sets_and_offset(ctx):
+    from mpc_bulletproof_b200.stark import StarkTable
+
+    r = rng(731)
+    n_tab, off, n, sets = 400, 60, 256, 3
+    ps = _pts(r, n_tab)
+    ps[70] = S.IDENTITY
+    t = StarkTable(ctx, _pb(ps))
+    assert len(t) == n_tab
+    ks = [[r.randrange(N) for _ in range(n)] for _ in range(sets)]
+    got = t.msm(b"".join(_sb(k) for k in ks), n_sets=sets, offset=off, n=n)
+    for s in range(sets):
+        assert got[s] == S.msm(ks[s], ps[off : off + n]).encode()
+    t.close()
+
+
+def test_invalid_point_rejected(ctx):
+    from mpc_bulletproof_b200 import BpgError, stark
+    from mpc_bulletproof_b200._lib import BPG_ERR_DECODE
+
+    g = S.GENERATOR
+    off_curve = g.x.to_bytes(32, "little") + ((g.y + 1) % S.P).to_bytes(32, "little")
+    not_canonical = S.P.to_bytes(32, "little") + g.y.to_bytes(32, "little")
+    for bad in (off_curve, not_canonical):
+        with pytest.raises(BpgError) as e:
+            stark.msm(ctx, _sb([1]), bad)
+        assert e.value.code == BPG_ERR_DECODE
+
+
+def test_linearity_large(ctx):
+    """2^16 terms: tiling a 1024-point table 64 times equals the MSM of the column sums."""
+    from mpc_bulletproof_b200 import stark
+
+    r = rng(741)
+    m, reps = 1024, 64
+    ps = _pts(r, 64)
+    ps = [ps[i % 64] + (i // 64) * S.GENERATOR for i in range(m)]  # cheap distinct points
+    pb = _pb(ps)
+    ks = [[r.randrange(N) for _ in range(m)] for _ in range(reps)]
+    big = stark.msm(ctx, b"".join(_sb(k) for k in ks), pb * reps)
+    summed = [sum(ks[j][i] for j in range(reps)) % N for i in range(m)]
+    small = stark.msm(ctx, _sb(summed), pb)
+    assert big == small
