@@ -7,7 +7,7 @@ use std::os::raw::{c_char, c_int, c_void};
 macro_rules! opaque {
     ($($name:ident),*) => { $( #[repr(C)] pub struct $name { _private: [u8; 0] } )* };
 }
-opaque!(bpg_ctx, bpg_table, bpg_ipp, bpg_comb, bpg_r1cs_dev);
+opaque!(bpg_ctx, bpg_table, bpg_ipp, bpg_comb, bpg_r1cs_dev, bpg_stark_table);
 
 pub const BPG_OK: c_int = 0;
 pub const BPG_ERR_ARG: c_int = -1;
@@ -151,6 +151,17 @@ extern "C" {
         adhoc_points: *const u8, adhoc_scalars: *const u8, n_adhoc: usize, bb_scalar: *const u8,
         params: *const bpg_verify_params, out: *mut u8,
     ) -> c_int;
+
+    // ---- Stark-curve policy: mpc_stark::algebra::stark_curve::StarkPoint::msm_iter / ::msm ----
+    // points are affine x || y, 32 bytes little-endian each (src/util.rs:274-289); identity = 64 zero bytes
+    pub fn bpg_stark_table_upload(ctx: *mut bpg_ctx, points_xy: *const u8, n: usize, out: *mut *mut bpg_stark_table) -> c_int;
+    pub fn bpg_stark_table_len(t: *const bpg_stark_table) -> usize;
+    pub fn bpg_stark_table_free(t: *mut bpg_stark_table);
+    pub fn bpg_stark_msm_table(
+        ctx: *mut bpg_ctx, t: *const bpg_stark_table, offset: usize, n: usize, scalars: *const u8, n_sets: c_int,
+        out_xy: *mut u8,
+    ) -> c_int;
+    pub fn bpg_stark_msm(ctx: *mut bpg_ctx, scalars: *const u8, points_xy: *const u8, n: usize, out_xy: *mut u8) -> c_int;
 
     // ---- page-locked staging ---------------------------------------------------------------
     pub fn bpg_host_alloc(bytes: usize) -> *mut c_void;
