@@ -274,6 +274,9 @@ int bpg_r1cs_dev_ipp_begin(bpg_r1cs_dev* st, const bpg_table* gens, size_t g_bas
  * ristretto255 instantiation. */
 typedef struct bpg_stark_table bpg_stark_table;
 int bpg_stark_table_upload(bpg_ctx* ctx, const uint8_t* points_xy /* n*64 */, size_t n, bpg_stark_table** out);
+/* precompute 2^(c w) P_i for every window (c = 0: chosen from the table length); one-time cost, no doublings afterwards */
+int bpg_stark_table_set_windows(bpg_ctx* ctx, bpg_stark_table* t, int c);
+int bpg_stark_table_window(const bpg_stark_table* t);
 size_t bpg_stark_table_len(const bpg_stark_table* t);
 void bpg_stark_table_free(bpg_stark_table* t);
 /* out[s] = sum_i scalars[s*n + i] * table[offset + i], n_sets x 64 bytes */

@@ -121,6 +121,8 @@ _SIGNATURES = {
     "bpg_r1cs_dev_verify_msm": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _P, _SZ, _P, _P, _P]),
     "bpg_r1cs_dev_ipp_begin": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _SZ, _SZ, _SZ, _P, _P, _P, _P, ctypes.POINTER(_P)]),
     "bpg_stark_table_upload": (_I, [_P, _P, _SZ, ctypes.POINTER(_P)]),
+    "bpg_stark_table_set_windows": (_I, [_P, _P, _I]),
+    "bpg_stark_table_window": (_I, [_P]),
     "bpg_stark_table_len": (_SZ, [_P]),
     "bpg_stark_table_free": (None, [_P]),
     "bpg_stark_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),

@@ -475,7 +475,7 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
                        uint32_t* d_out_ext, int win_c = 0, size_t win_stride = 0, int lane = 0, int curve = 0) {
   // curve 0: ristretto255 (Niels table, 24 words per entry); curve 1: Stark curve (affine table, 16 words
   // per entry, plain tables only).  Sort and schedule are shared; the bucket arithmetic differs.
-  if (nsets <= 0 || (curve == 1 && win_c)) return BPG_ERR_ARG;
+  if (nsets <= 0) return BPG_ERR_ARG;
   // lane 1: the auxiliary stream and arena (no phase profiling there)
   struct ProfOff {
     bpg_ctx* c;
@@ -516,7 +516,7 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   size_t o_buckets = off; off += align_up((size_t)cfg.B * 128);
   size_t o_merged = off;  off += (windowed && cfg.gsub > 1) ? align_up((size_t)nsets * cfg.nb * 128) : 0;
   if (curve == 1) {
-    rarr = cfg.narr;
+    rarr = windowed ? (uint32_t)nsets : cfg.narr;
     tiles0 = (cfg.nb + SLEAF_LC - 1) / SLEAF_LC;
   }
   size_t o_pairs = off;   off += 4 * align_up((size_t)rarr * tiles0 * 128);  // (A, Y) x ping-pong
@@ -594,12 +594,21 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
     k_stark_big_fin<<<std::min<unsigned>((cfg.big_cap + 127) / 128, (unsigned)ctx->sm_count), 128, 0, st>>>(
         cfg, buckets, big_count, big_list, big_part);
     LAUNCH_CHECK();
+    const uint32_t* lvl0 = buckets;
+    if (windowed && cfg.gsub > 1) {
+      prof_mark(ctx, BPG_PROF_COMBINE);
+      k_stark_merge<<<((unsigned)nsets * cfg.nb + 127) / 128, 128, 0, st>>>(buckets, cfg, merged);
+      LAUNCH_CHECK();
+      lvl0 = merged;
+    }
     prof_mark(ctx, BPG_PROF_REDUCE);
+    uint32_t arrays = windowed ? (uint32_t)nsets : cfg.narr;
+    uint32_t* fin = windowed ? d_out_ext : wins;
     uint32_t t = (cfg.nb + SLEAF_LC - 1) / SLEAF_LC;  // pairs per array after the leaf pass
     uint32_t* pa[2] = {pairs, pairs + 2 * pair_words};
     int cur = 0;
-    uint32_t* oa = t == 1 ? wins : pa[cur];
-    k_stark_leaf<<<(cfg.narr * t + 127) / 128, 128, 0, st>>>(buckets, cfg.nb, t, cfg.narr, oa, pa[cur] + pair_words);
+    uint32_t* oa = t == 1 ? fin : pa[cur];
+    k_stark_leaf<<<(arrays * t + 127) / 128, 128, 0, st>>>(lvl0, cfg.nb, t, arrays, oa, pa[cur] + pair_words);
     LAUNCH_CHECK();
     while (t > 1) {
       uint32_t n = t;
@@ -607,13 +616,15 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
       const uint32_t* ia = pa[cur];
       const uint32_t* iy = pa[cur] + pair_words;
       cur ^= 1;
-      oa = t == 1 ? wins : pa[cur];
-      k_stark_pairs<<<cfg.narr * t, SPAIR_N, 0, st>>>(ia, iy, n, t, oa, pa[cur] + pair_words);
+      oa = t == 1 ? fin : pa[cur];
+      k_stark_pairs<<<arrays * t, SPAIR_N, 0, st>>>(ia, iy, n, t, oa, pa[cur] + pair_words);
       LAUNCH_CHECK();
     }
-    prof_mark(ctx, BPG_PROF_HORNER);
-    k_stark_horner<<<(nsets + 31) / 32, 32, 0, st>>>(wins, cfg, d_out_ext);
-    LAUNCH_CHECK();
+    if (!windowed) {
+      prof_mark(ctx, BPG_PROF_HORNER);
+      k_stark_horner<<<(nsets + 31) / 32, 32, 0, st>>>(wins, cfg, d_out_ext);
+      LAUNCH_CHECK();
+    }
     prof_mark(ctx, -1);
     return BPG_OK;
   }

@@ -264,4 +264,69 @@ __global__ void k_stark_set_identity(uint32_t* __restrict__ out) {
   out[(size_t)blockIdx.x * 32 + threadIdx.x] = 0u;
 }
 
+// windowed tables: out[w][i] = 2^(c w) * P_i, affine, w < W.  One thread per point walks the doubling
+// chain in XYZZ, parks the multiples and the running product of their ZZ*ZZZ in scratch, inverts
+// once (Montgomery's trick) and converts every multiple back to affine (1/ZZ = t ZZZ, 1/ZZZ = t ZZ
+// with t = 1/(ZZ ZZZ)).  One-time cost at table upload; it removes every doubling from later MSMs.
+__global__ void __launch_bounds__(128) k_stark_window_chain(const uint32_t* __restrict__ aff_in, uint32_t n_total,
+                                                             uint32_t first, uint32_t count, int c, int W,
+                                                             uint32_t* __restrict__ pt_scratch /*[W-1][count][32]*/,
+                                                             uint32_t* __restrict__ dp_scratch /*[W-1][count][8]*/,
+                                                             uint32_t* __restrict__ out /*[W][n_total][16]*/) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  uint32_t i = first + t;
+  sp_aff q;
+  sp_aff_load(q, aff_in + (size_t)i * 16);
+  sp_aff_store(out + (size_t)i * 16, q);  // window 0
+  if (sp_aff_is_identity(q)) {
+    for (int w = 1; w < W; w++) sp_aff_store(out + ((size_t)w * n_total + i) * 16, q);
+    return;
+  }
+  sp_xyzz p = sp_from_aff(q);
+  fp dp = fp_one();
+  for (int w = 1; w < W; w++) {
+    for (int k = 0; k < c; k++) p = sp_dbl(p);  // prime order: never the identity
+    dp = fp_mul(dp, fp_mul(p.ZZ, p.ZZZ));
+    sp_store(pt_scratch + ((size_t)(w - 1) * count + t) * 32, p);
+    fp_store(dp_scratch + ((size_t)(w - 1) * count + t) * 8, dp);
+  }
+  fp inv = fp_invert(dp);
+  for (int w = W - 1; w >= 1; w--) {
+    sp_xyzz e;
+    sp_load(e, pt_scratch + ((size_t)(w - 1) * count + t) * 32);
+    fp ti;
+    if (w >= 2) {
+      fp prev;
+      fp_load(prev, dp_scratch + ((size_t)(w - 2) * count + t) * 8);
+      ti = fp_mul(inv, prev);
+    } else {
+      ti = inv;
+    }
+    inv = fp_mul(inv, fp_mul(e.ZZ, e.ZZZ));
+    sp_aff a;
+    a.x = fp_mul(e.X, fp_mul(ti, e.ZZZ));
+    a.y = fp_mul(e.Y, fp_mul(ti, e.ZZ));
+    sp_aff_store(out + ((size_t)w * n_total + i) * 16, a);
+  }
+}
+
+// windowed tables with several bucket groups per set: merged[set][b] = sum_g bucket_sums[set][g][b]
+__global__ void __launch_bounds__(128) k_stark_merge(const uint32_t* __restrict__ bucket_sums, MsmCfg cfg,
+                                                      uint32_t* __restrict__ merged) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t total = (uint32_t)cfg.nsets * cfg.nb;
+  if (q >= total) return;
+  uint32_t set = q / cfg.nb, b = q % cfg.nb;
+  const uint32_t* src = bucket_sums + ((size_t)set * cfg.gsub * cfg.nb + b) * 32;
+  sp_xyzz acc;
+  sp_load(acc, src);
+  for (uint32_t g = 1; g < cfg.gsub; g++) {
+    sp_xyzz o;
+    sp_load(o, src + (size_t)g * cfg.nb * 32);
+    acc = sp_add(acc, o);
+  }
+  sp_store(merged + (size_t)q * 32, acc);
+}
+
 }  // namespace bpg

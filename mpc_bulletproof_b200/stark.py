@@ -25,6 +25,15 @@ class StarkTable:
     def __len__(self):
         return int(lib().bpg_stark_table_len(self._h))
 
+    def set_windows(self, c: int = 0):
+        """Precompute 2^(c w) P_i for every window (c = 0: chosen from the table length)."""
+        check(lib().bpg_stark_table_set_windows(self.ctx._h, self._h, c))
+        return self
+
+    @property
+    def window(self) -> int:
+        return int(lib().bpg_stark_table_window(self._h))
+
     def close(self):
         if self._h:
             lib().bpg_stark_table_free(self._h)

@@ -155,6 +155,7 @@ extern "C" {
     // ---- Stark-curve policy: mpc_stark::algebra::stark_curve::StarkPoint::msm_iter / ::msm ----
     // points are affine x || y, 32 bytes little-endian each (src/util.rs:274-289); identity = 64 zero bytes
     pub fn bpg_stark_table_upload(ctx: *mut bpg_ctx, points_xy: *const u8, n: usize, out: *mut *mut bpg_stark_table) -> c_int;
+    pub fn bpg_stark_table_set_windows(ctx: *mut bpg_ctx, t: *mut bpg_stark_table, c: c_int) -> c_int;
     pub fn bpg_stark_table_len(t: *const bpg_stark_table) -> usize;
     pub fn bpg_stark_table_free(t: *mut bpg_stark_table);
     pub fn bpg_stark_msm_table(

@@ -132,3 +132,31 @@ def test_linearity_large(ctx):
     summed = [sum(ks[j][i] for j in range(reps)) % N for i in range(m)]
     small = stark.msm(ctx, _sb(summed), pb)
     assert big == small
+
+
+@pytest.mark.parametrize("c,gsub", [(0, 0), (5, 0), (8, 3), (13, 1), (13, 20), (16, 0)])
+def test_windowed_table(ctx, c, gsub):
+    """Tables holding 2^(c w) P_i (affine, batch-inverted): one bucket array per set, no Horner.
+    Whole table, a sub-range, two sets, forced bucket groups, identity and edge scalars."""
+    from mpc_bulletproof_b200.stark import StarkTable
+
+    r = rng(750 + c)
+    n_tab, off, n, sets = 300, 21, 256, 2
+    ps = _pts(r, n_tab)
+    ps[5] = S.IDENTITY
+    t = StarkTable(ctx, _pb(ps)).set_windows(c)
+    assert t.window == (c or t.window) and t.window >= 2
+    ks = [r.randrange(N) for _ in range(n_tab)]
+    ks[0], ks[1], ks[2] = 0, N - 1, 1
+    ctx.set_groups(gsub)
+    try:
+        assert t.msm(_sb(ks))[0] == S.msm(ks, ps).encode()
+        kk = [[r.randrange(N) for _ in range(n)] for _ in range(sets)]
+        got = t.msm(b"".join(_sb(k) for k in kk), n_sets=sets, offset=off, n=n)
+    finally:
+        ctx.set_groups(0)
+    for s in range(sets):
+        assert got[s] == S.msm(kk[s], ps[off : off + n]).encode()
+    # repeated scalars over a windowed table: long buckets
+    assert t.msm(_sb([7] * n_tab))[0] == (7 * S.msm([1] * n_tab, ps)).encode()
+    t.close()

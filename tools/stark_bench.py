@@ -8,8 +8,11 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import ctypes  # noqa: E402
 
 from mpc_bulletproof_b200 import Context  # noqa: E402
+from mpc_bulletproof_b200._lib import check, lib  # noqa: E402
 from mpc_bulletproof_b200.stark import StarkTable  # noqa: E402
 
 P = 2**251 + 17 * 2**192 + 1
@@ -30,6 +33,7 @@ def add(p, q):
 
 def main():
     lgs = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "12,16,18,20").split(",")]
+    windowed = not (len(sys.argv) > 2 and sys.argv[2] == "plain")
     ctx = Context(0)
     base, pts, cur = 4096, [], (GX, GY)
     for _ in range(base):
@@ -41,23 +45,31 @@ def main():
         n = 1 << lg
         pb = tile * (n // base) if n >= base else tile[: 64 * n]
         t = StarkTable(ctx, pb)
+        if windowed:
+            t.set_windows(0)
         g = np.random.Generator(np.random.PCG64(lg))
         a = g.integers(0, 256, size=(n, 32), dtype=np.uint8)
         a[:, 31] &= 0x07  # < 2^251 < group order
-        sc = a.tobytes()
+        sc_t = torch.from_numpy(a).pin_memory()  # scalars start in page-locked host memory
+        res = ctypes.create_string_buffer(64)
+
+        def run():
+            check(lib().bpg_stark_msm_table(ctx._h, t._h, 0, n, ctypes.c_void_p(sc_t.data_ptr()), 1, res))
+            return res.raw
+
         for _ in range(2):
-            r0 = t.msm(sc)[0]
+            r0 = run()
         ctx.profile(True)
         ctx.profile_reset()
         reps = 5
         t0 = time.perf_counter()
         for _ in range(reps):
-            r = t.msm(sc)[0]
+            r = run()
         dt = (time.perf_counter() - t0) / reps * 1e3
         prof = ctx.profile_read()
         ctx.profile(False)
         assert r == r0
-        out["rows"].append({"lg_n": lg, "e2e_ms": round(dt, 3), "mpoints_s": round(n / dt / 1e3, 1),
+        out["rows"].append({"lg_n": lg, "window": t.window, "e2e_ms": round(dt, 3), "mpoints_s": round(n / dt / 1e3, 1),
                             "phases_ms": {k: round(v[0] / reps, 3) for k, v in prof.items() if v[1]}, "result_x": r[:32].hex()})
         print(out["rows"][-1], file=sys.stderr, flush=True)
         t.close()
