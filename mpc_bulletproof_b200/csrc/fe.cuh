@@ -226,7 +226,7 @@ BPG_DI fe fe_mul(const fe& A, const fe& B) {
 
 // Dedicated squaring: the 28 cross products a_i a_j (i < j) in the same even/odd column chains,
 // doubled once as a 512-bit shift, plus the 8 squares: 36 + 8 wide multiply-adds instead of 64 + 8.
-// Measured on B200 (tools/scratch/fe_lat.cu): 207 ns against 262 ns for fe_mul(a, a) on a lone
+// Measured on B200 (tools/fe_lat.cu): 207 ns against 262 ns for fe_mul(a, a) on a lone
 // warp, 119 against 165 ns per warp at full occupancy.
 BPG_DI fe fe_sq(const fe& A) {
   const uint32_t* a = A.v;

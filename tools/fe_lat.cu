@@ -1,7 +1,7 @@
 // latency of dependent squarings / multiplications for ONE warp (the encode / inversion regime)
 #include <cstdio>
 #include <cuda_runtime.h>
-#include "../../mpc_bulletproof_b200/csrc/ge.cuh"
+#include "../mpc_bulletproof_b200/csrc/ge.cuh"
 using namespace bpg;
 
 // (b) dedicated squaring, chained: 28 cross products (doubled once) + 8 squares
