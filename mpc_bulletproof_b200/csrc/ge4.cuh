@@ -2,7 +2,7 @@
 //
 // A single warp keeps the INT32 multiply pipe of its SM sub-partition busy for
 // ~260 ns per field multiplication no matter how many of its lanes are active
-// (profiles/int32_peak.json, tools/scratch notes in DESIGN.md), so the serial phases
+// (profiles/int32_peak.json, tools/fe_lat.cu), so the serial phases
 // of Pippenger — running sums over buckets, the window combine, the doubling chain —
 // cost (#dependent multiplications) x 260 ns when one thread owns a point.  Here FOUR
 // adjacent lanes own one extended point, one coordinate each (lane&3 = 0:X 1:Y 2:Z
