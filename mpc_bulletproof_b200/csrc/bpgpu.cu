@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <unordered_map>
 #include <vector>
@@ -257,24 +258,73 @@ extern "C" int bpg_set_window(bpg_ctx* ctx, int c) {
   return BPG_OK;
 }
 
-// Page-locked host buffers (tagged so that bpg_host_free knows how each was obtained)
+// Page-locked host buffers.  cudaHostAlloc costs milliseconds per call, and a constraint system grows
+// its vectors while it is being built, so freed buffers are parked in a small process-wide cache
+// and handed out again (best fit within 4x).  Header: [tag, capacity]; tag says how it was obtained.
+namespace {
+struct HostCache {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_list;  // raw pointers (header included), capacity
+  size_t bytes = 0;
+  ~HostCache() {
+    for (auto& b : free_list) cudaFreeHost(b.first);
+  }
+};
+HostCache& host_cache() {
+  static HostCache* c = new HostCache();  // leaked on purpose: buffers may outlive static destruction order
+  return *c;
+}
+constexpr uint64_t TAG_PINNED = 0x50494e4eull, TAG_MALLOC = 0x4d414c4cull;
+constexpr size_t HOST_CACHE_MAX = (size_t)2 << 30, HOST_CACHE_SLOTS = 64;
+}  // namespace
+
 extern "C" void* bpg_host_alloc(size_t bytes) {
-  void* p = nullptr;
   size_t total = bytes + 64;
+  {
+    HostCache& hc = host_cache();
+    std::lock_guard<std::mutex> lk(hc.mu);
+    int best = -1;
+    for (size_t i = 0; i < hc.free_list.size(); i++) {
+      size_t cap = hc.free_list[i].second;
+      if (cap >= total && cap <= 4 * total && (best < 0 || cap < hc.free_list[best].second)) best = (int)i;
+    }
+    if (best >= 0) {
+      void* p = hc.free_list[best].first;
+      hc.bytes -= hc.free_list[best].second;
+      hc.free_list.erase(hc.free_list.begin() + best);
+      return static_cast<uint8_t*>(p) + 64;
+    }
+  }
+  void* p = nullptr;
   bool pinned = cudaHostAlloc(&p, total, cudaHostAllocDefault) == cudaSuccess;
   if (!pinned) {
     cudaGetLastError();
     p = malloc(total);
     if (!p) return nullptr;
   }
-  *reinterpret_cast<uint64_t*>(p) = pinned ? 0x50494e4eull : 0x4d414c4cull;
+  uint64_t* h = reinterpret_cast<uint64_t*>(p);
+  h[0] = pinned ? TAG_PINNED : TAG_MALLOC;
+  h[1] = total;
   return static_cast<uint8_t*>(p) + 64;
 }
 extern "C" void bpg_host_free(void* q) {
   if (!q) return;
   uint8_t* p = static_cast<uint8_t*>(q) - 64;
-  if (*reinterpret_cast<uint64_t*>(p) == 0x50494e4eull) cudaFreeHost(p);
-  else free(p);
+  uint64_t* h = reinterpret_cast<uint64_t*>(p);
+  if (h[0] != TAG_PINNED) {
+    free(p);
+    return;
+  }
+  HostCache& hc = host_cache();
+  {
+    std::lock_guard<std::mutex> lk(hc.mu);
+    if (hc.free_list.size() < HOST_CACHE_SLOTS && hc.bytes + h[1] <= HOST_CACHE_MAX) {
+      hc.free_list.push_back({p, (size_t)h[1]});
+      hc.bytes += h[1];
+      return;
+    }
+  }
+  cudaFreeHost(p);
 }
 
 extern "C" int bpg_set_groups(bpg_ctx* ctx, int gsub) {

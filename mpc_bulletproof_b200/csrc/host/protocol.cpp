@@ -37,7 +37,7 @@ struct PinnedVec {
   ~PinnedVec() { bpg_host_free(p); }
   void reserve(size_t want) {
     if (want <= cap) return;
-    size_t nc = std::max<size_t>(want, std::max<size_t>(cap * 2, 1024));
+    size_t nc = std::max<size_t>(want, std::max<size_t>(cap * 4, 4096));
     T* q = static_cast<T*>(bpg_host_alloc(nc * sizeof(T)));
     if (!q) throw std::bad_alloc();
     if (n) memcpy(q, p, n * sizeof(T));
