@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--lg-points", type=int, default=20, help="log2 of the points per GPU")
     ap.add_argument("--cpu-sample-lg", type=int, default=18, help="log2 of the CPU-baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-combine", action="store_true", help="N>1: NCCL all-gather + combine launch instead of the fused peer exchange")
     ap.add_argument("--no-r1cs", action="store_true", help="skip the R1CS prove/verify timing at 2^16 multipliers")
     ap.add_argument("--r1cs-lg", type=int, default=16)
     return ap.parse_args()
@@ -240,9 +241,21 @@ def run_b200(args, rank, local_rank, world):
         result = torch.zeros(32, dtype=torch.uint8, device=dev)
     stream.synchronize()
 
+    # N>1: the ranks' 128-byte partial sums meet in peer-mapped buffers; ONE kernel per rank pushes,
+    # waits, adds and encodes (mpc_bulletproof_b200.multi.PeerExchange).  --nccl-combine keeps the
+    # all-gather + combine-launch form for comparison.
+    peer = None
+    if world > 1 and not args.nccl_combine:
+        from mpc_bulletproof_b200.multi import PeerExchange
+
+        peer = PeerExchange(ctx, max_sets=1)
+    combine = "single GPU" if world == 1 else ("NCCL all_gather + combine kernel" if peer is None else "fused peer exchange (P2P stores + flags, one kernel)")
+
     def step(i):
         table.dev_msm(scal[i % NSETS_ROT].data_ptr(), 1, part.data_ptr())
-        if world > 1:
+        if peer is not None:
+            peer.exchange_sum_encode(part.data_ptr(), 1, result.data_ptr())
+        elif world > 1:
             dist.all_gather_into_tensor(parts, part)
             dev_sum_encode(ctx, parts.data_ptr(), world, 1, result.data_ptr())
         else:
@@ -307,8 +320,11 @@ def run_b200(args, rank, local_rank, world):
             with torch.cuda.stream(stream):
                 d_in.copy_(host_sc[i % 2], non_blocking=True)
                 table.dev_msm(d_in.data_ptr(), 1, part.data_ptr())
-                dist.all_gather_into_tensor(parts, part)
-                dev_sum_encode(ctx, parts.data_ptr(), world, 1, result.data_ptr())
+                if peer is not None:
+                    peer.exchange_sum_encode(part.data_ptr(), 1, result.data_ptr())
+                else:
+                    dist.all_gather_into_tensor(parts, part)
+                    dev_sum_encode(ctx, parts.data_ptr(), world, 1, result.data_ptr())
                 host_out.copy_(result, non_blocking=True)
             stream.synchronize()
 
@@ -393,6 +409,7 @@ def run_b200(args, rank, local_rank, world):
                 "table": f"windowed affine-Niels, c={table.window}, {(n * 96 * ((255 + table.window - 1) // table.window)) >> 20} MiB resident",
                 "l2": f"{NSETS_ROT} scalar sets of {n * 32 >> 20} MiB rotated + the table + sort/bucket workspace, all far above the 126 MB L2",
                 "gpoint_ops_per_s_eq": 16 * world * n / (ms_step * 1e-3) / 1e9,
+                "combine": combine,
             },
             "e2e": {
                 "value": e2e_val,
@@ -400,7 +417,7 @@ def run_b200(args, rank, local_rank, world):
                 "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": n * 32,
                 "d2h_bytes_per_step": 32,
-                "api": "bpg_msm_table (host buffers)" if world == 1 else "pinned H2D + bpg_dev_msm_table + all_gather + bpg_dev_sum_encode + D2H",
+                "api": "bpg_msm_table (host buffers)" if world == 1 else f"pinned H2D + bpg_dev_msm_table + {combine} + D2H",
             },
             "gpu_launches": int(launches),
             "phases_ms": phases,
@@ -411,6 +428,11 @@ def run_b200(args, rank, local_rank, world):
             "result": result_hex,
         }
         emit(line)
+    if peer is not None:
+        if not peer.ok():
+            print("peer exchange timed out on rank", rank, file=sys.stderr)
+        barrier()
+        peer.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

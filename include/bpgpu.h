@@ -146,6 +146,21 @@ int bpg_msm_table_partial(bpg_ctx* ctx, const bpg_table* table, size_t offset, s
                           int n_sets, uint8_t* out_ext);
 int bpg_sum_encode(bpg_ctx* ctx, const uint8_t* parts_ext, int n_parts, int n_sets, uint8_t* out);
 
+/* Exchange fused with the combine, for one process per GPU on one node: each rank
+ * owns an exchange buffer that its peers map through CUDA IPC; bpg_dev_exchange_sum_encode is ONE
+ * kernel that stores this rank's partial sums into every rank's buffer over NVLink, raises its flag,
+ * waits for all ranks' flags, adds the partials and encodes -- in place of an all-gather followed by a
+ * combine launch.  Setup: every rank calls bpg_peer_create, the 64-byte handles are exchanged by the
+ * caller (any channel) and passed in rank order to bpg_peer_connect.  world <= 8.  Every rank must call
+ * the exchange the same number of times.  A peer that does not show up within ~1 s sets the status. */
+typedef struct bpg_peer bpg_peer;
+int bpg_peer_create(bpg_ctx* ctx, int world, int rank, int max_sets, bpg_peer** out, uint8_t handle_out[64]);
+int bpg_peer_connect(bpg_peer* p, const uint8_t* handles /* world*64 */);
+int bpg_dev_exchange_sum_encode(bpg_ctx* ctx, bpg_peer* p, const void* d_part, int n_sets, void* d_out_bytes,
+                                void* d_out_ext);
+int bpg_peer_status(bpg_peer* p, int* status_out);
+void bpg_peer_free(bpg_peer* p);
+
 /* ---- inner-product argument --------------------------------------------------------
  * Device-resident state for `InnerProductProof::create` (reference
  * src/inner_product_proof.rs:49-193).  The transcript stays with the caller, hence the

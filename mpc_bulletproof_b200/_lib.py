@@ -101,6 +101,11 @@ _SIGNATURES = {
     "bpg_dev_sum_encode": (_I, [_P, _P, _I, _I, _P, _P]),
     "bpg_msm_table_partial": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),
     "bpg_sum_encode": (_I, [_P, _P, _I, _I, _P]),
+    "bpg_peer_create": (_I, [_P, _I, _I, _I, ctypes.POINTER(_P), _P]),
+    "bpg_peer_connect": (_I, [_P, _P]),
+    "bpg_dev_exchange_sum_encode": (_I, [_P, _P, _P, _I, _P, _P]),
+    "bpg_peer_status": (_I, [_P, ctypes.POINTER(_I)]),
+    "bpg_peer_free": (None, [_P]),
     "bpg_ipp_begin": (_I, [_P, _P, _SZ, _P, _SZ, _SZ, _P, _P, _P, _P, _P, ctypes.POINTER(_P)]),
     "bpg_ipp_begin_dev": (_I, [_P, _P, _SZ, _P, _SZ, _SZ, _P, _P, _P, _P, _P, ctypes.POINTER(_P)]),
     "bpg_ipp_begin_shared": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _SZ, _P, _P, _P, _P, ctypes.POINTER(_P)]),

@@ -756,6 +756,111 @@ extern "C" int bpg_dev_sum_encode(bpg_ctx* ctx, const void* d_parts, int n_parts
   return BPG_OK;
 }
 
+// ---------------------------------------------------------------------------
+// peer exchange: the ranks' partial sums meet in peer-mapped buffers (one process per GPU)
+// ---------------------------------------------------------------------------
+struct bpg_peer {
+  bpg_ctx* ctx;
+  int world, rank, max_sets;
+  uint8_t* local;      // cudaMalloc: parts [2][world][max_sets][32] words | flags [2][world] | status
+  size_t parts_bytes;
+  void* opened[8];     // peers' buffers opened through IPC (null for our own)
+  PeerPtrs ptrs;
+  uint32_t seq;
+  bool connected;
+};
+
+extern "C" int bpg_peer_create(bpg_ctx* ctx, int world, int rank, int max_sets, bpg_peer** out, uint8_t handle_out[64]) {
+  if (!ctx || !out || !handle_out || world < 1 || world > 8 || rank < 0 || rank >= world || max_sets < 1 ||
+      max_sets > XCH_THREADS)
+    return BPG_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CK(cudaSetDevice(ctx->device));
+  bpg_peer* p = new (std::nothrow) bpg_peer();
+  if (!p) return BPG_ERR_NOMEM;
+  memset(p, 0, sizeof *p);
+  p->ctx = ctx;
+  p->world = world;
+  p->rank = rank;
+  p->max_sets = max_sets;
+  p->parts_bytes = align_up((size_t)2 * world * max_sets * 128);
+  size_t total = p->parts_bytes + align_up((size_t)2 * world * 4) + 256;
+  cudaError_t e = cudaMalloc(&p->local, total);  // IPC needs a plain allocation, not the pool
+  if (e == cudaSuccess) e = cudaMemset(p->local, 0, total);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p->local);
+  if (e != cudaSuccess) {
+    ctx->last_cuda = (int)e;
+    if (p->local) cudaFree(p->local);
+    delete p;
+    return BPG_ERR_CUDA;
+  }
+  memcpy(handle_out, &h, 64);
+  *out = p;
+  return BPG_OK;
+}
+// handles: world x 64 bytes, in rank order (every rank's bpg_peer_create output, exchanged by the caller)
+extern "C" int bpg_peer_connect(bpg_peer* p, const uint8_t* handles) {
+  if (!p || !handles) return BPG_ERR_ARG;
+  bpg_ctx* ctx = p->ctx;
+  CK(cudaSetDevice(ctx->device));
+  for (int r = 0; r < p->world; r++) {
+    uint8_t* base = p->local;
+    if (r != p->rank) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles + 64 * (size_t)r, 64);
+      void* ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        ctx->last_cuda = (int)e;
+        return BPG_ERR_CUDA;
+      }
+      p->opened[r] = ptr;
+      base = static_cast<uint8_t*>(ptr);
+    }
+    p->ptrs.parts[r] = reinterpret_cast<uint32_t*>(base);
+    p->ptrs.flags[r] = reinterpret_cast<uint32_t*>(base + p->parts_bytes);
+  }
+  p->connected = true;
+  return BPG_OK;
+}
+extern "C" void bpg_peer_free(bpg_peer* p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  for (int r = 0; r < p->world; r++)
+    if (p->opened[r]) cudaIpcCloseMemHandle(p->opened[r]);
+  cudaFree(p->local);
+  delete p;
+}
+// One kernel: push this rank's partial sums to every rank, wait for all, add, encode.  Every rank
+// must call it the same number of times (the step counter is part of the protocol).
+extern "C" int bpg_dev_exchange_sum_encode(bpg_ctx* ctx, bpg_peer* p, const void* d_part, int n_sets, void* d_out_bytes,
+                                           void* d_out_ext) {
+  if (!ctx || !p || !d_part || n_sets <= 0 || n_sets > p->max_sets || !p->connected) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  p->seq++;
+  uint32_t* status = reinterpret_cast<uint32_t*>(p->local + p->parts_bytes + align_up((size_t)2 * p->world * 4));
+  prof_mark(ctx, BPG_PROF_ENCODE);
+  k_exchange_sum_encode<<<1, XCH_THREADS, 0, ctx->stream>>>((const uint32_t*)d_part, p->ptrs, p->world, p->rank, n_sets,
+                                                            p->max_sets, p->seq, (uint8_t*)d_out_bytes, (uint32_t*)d_out_ext,
+                                                            status);
+  LAUNCH_CHECK();
+  prof_mark(ctx, -1);
+  return BPG_OK;
+}
+// 0 = every exchange so far completed; 1 = a peer did not show up within the kernel's bound
+extern "C" int bpg_peer_status(bpg_peer* p, int* status_out) {
+  if (!p || !status_out) return BPG_ERR_ARG;
+  bpg_ctx* ctx = p->ctx;
+  CK(cudaSetDevice(ctx->device));
+  uint32_t* status = reinterpret_cast<uint32_t*>(p->local + p->parts_bytes + align_up((size_t)2 * p->world * 4));
+  CK(cudaMemcpyAsync(ctx->h_pinned + 2048, status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *status_out = (int)*reinterpret_cast<uint32_t*>(ctx->h_pinned + 2048);
+  return BPG_OK;
+}
+
 extern "C" int bpg_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t offset, size_t n,
                              const uint8_t* scalars_le, int n_sets, uint8_t* out) {
   if (!ctx || !table || !out || (!scalars_le && n) || n_sets <= 0) return BPG_ERR_ARG;

@@ -779,6 +779,85 @@ __global__ void k_sum_encode(const uint32_t* __restrict__ parts, int nparts, int
 }
 
 // ---------------------------------------------------------------------------
+// Sharded MSM, the exchange step fused with the combine: ONE kernel per rank
+//   1. stores this rank's partial sums (n_sets x 128 B) into slot [rank] of EVERY rank's exchange
+//      buffer over NVLink (peer-mapped pointers, plain stores), fences system-wide and raises its
+//      flag in every rank's flag array;
+//   2. waits until all ranks' flags show this step's sequence number;
+//   3. adds the `world` partials per set and encodes.
+// The payload is 128 B per rank and set, so the cost is latency: this replaces an NCCL all-gather
+// plus a separate combine launch.  Buffers are double-buffered by step parity: a rank can be at
+// most one step ahead of the slowest one (it needs that rank's flag to finish a step).
+// ---------------------------------------------------------------------------
+// extended point from words written by a peer: volatile loads (never served from a stale L1 line)
+__device__ __forceinline__ ge_ext ge_load_ext_volatile(const uint32_t* p) {
+  const volatile uint32_t* src = p;
+  ge_ext q;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    q.X.v[i] = src[i];
+    q.Y.v[i] = src[8 + i];
+    q.Z.v[i] = src[16 + i];
+    q.T.v[i] = src[24 + i];
+  }
+  return q;
+}
+struct PeerPtrs {
+  uint32_t* parts[8];  // rank p's parts buffer:  [2][world][max_sets][32] words
+  uint32_t* flags[8];  // rank p's flags:          [2][world]
+};
+constexpr int XCH_THREADS = 256;
+__global__ void __launch_bounds__(XCH_THREADS) k_exchange_sum_encode(const uint32_t* __restrict__ local_part, PeerPtrs peers,
+                                                                      int world, int rank, int nsets, int max_sets,
+                                                                      uint32_t seq, uint8_t* __restrict__ out_bytes,
+                                                                      uint32_t* __restrict__ out_ext,
+                                                                      uint32_t* __restrict__ status /*0 ok, 1 timeout*/) {
+  const uint32_t slot = seq & 1u;
+  const size_t slot_words = (size_t)world * max_sets * 32;
+  // 1. push
+  for (int p = 0; p < world; p++) {
+    uint32_t* dst = peers.parts[p] + slot * slot_words + (size_t)rank * max_sets * 32;
+    for (int w = threadIdx.x; w < nsets * 32; w += blockDim.x) dst[w] = local_part[w];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < (uint32_t)world) {
+    volatile uint32_t* f = peers.flags[threadIdx.x] + slot * world + rank;
+    *f = seq;
+  }
+  // 2. wait for every rank's flag (bounded: a dead peer must not hang the GPU)
+  __shared__ uint32_t timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  if (threadIdx.x < (uint32_t)world) {
+    volatile uint32_t* f = peers.flags[rank] + slot * world + threadIdx.x;
+    uint32_t spins = 0;
+    while (*f != seq) {
+      __nanosleep(64);
+      if (++spins > (1u << 24)) {  // > 1 s
+        timed_out = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  if (timed_out) {
+    if (threadIdx.x == 0) *status = 1;
+    return;
+  }
+  // 3. combine: one thread per set, partials read past the L1 (they were written by peers)
+  int set = threadIdx.x;
+  if (set < nsets) {
+    const uint32_t* base = peers.parts[rank] + slot * slot_words;
+    ge_ext acc = ge_load_ext_volatile(base + (size_t)set * 32);
+    for (int p = 1; p < world; p++) acc = ge_add(acc, ge_load_ext_volatile(base + ((size_t)p * max_sets + set) * 32));
+    if (out_ext) ge_store_ext(out_ext + (size_t)set * 32, acc);
+    if (out_bytes) ge_encode(out_bytes + (size_t)set * 32, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // table construction: compressed ristretto -> affine Niels
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_decode_to_niels(const uint8_t* __restrict__ comp, uint32_t n,

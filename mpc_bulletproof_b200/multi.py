@@ -21,6 +21,7 @@ with a checker engine supplied by the tests:
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Callable, Sequence
 
 
@@ -68,6 +69,60 @@ class CudaEngine:
         self.ctx.sync()
         raw = bytes(out.cpu().numpy().tobytes())
         return [raw[32 * i : 32 * i + 32] for i in range(n_sets)]
+
+
+class PeerExchange:
+    """The exchange fused with the combine: ONE kernel per rank stores its partial sums into every
+    rank's peer-mapped buffer over NVLink, waits for all flags, adds and encodes
+    (`bpg_dev_exchange_sum_encode`), in place of an NCCL all-gather followed by a combine launch.
+    One process per GPU on one node; the 64-byte IPC handles travel once over the process group."""
+
+    def __init__(self, ctx, max_sets: int = 4, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from ._lib import check, lib
+
+        self.ctx = ctx
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._h = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        check(lib().bpg_peer_create(ctx._h, self.world, self.rank, max_sets, ctypes.byref(self._h), handle))
+        dev = torch.device("cuda", ctx.device)
+        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(dev)
+        if self.world > 1:
+            allh = torch.empty(64 * self.world, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+        else:
+            allh = mine
+        check(lib().bpg_peer_connect(self._h, bytes(allh.cpu().numpy().tobytes())))
+        if self.world > 1:
+            dist.barrier(group=group)  # every rank has mapped every buffer before the first exchange
+
+    def exchange_sum_encode(self, d_part: int, n_sets: int, d_out_bytes: int | None, d_out_ext: int | None = None):
+        """Enqueue on the context's stream; d_part: this rank's n_sets x 128-byte partial sums."""
+        from ._lib import check, lib
+
+        check(
+            lib().bpg_dev_exchange_sum_encode(
+                self.ctx._h, self._h, ctypes.c_void_p(d_part), n_sets, ctypes.c_void_p(d_out_bytes or 0), ctypes.c_void_p(d_out_ext or 0)
+            )
+        )
+
+    def ok(self) -> bool:
+        from ._lib import check, lib
+
+        st = ctypes.c_int()
+        check(lib().bpg_peer_status(self._h, ctypes.byref(st)))
+        return st.value == 0
+
+    def close(self):
+        from ._lib import lib
+
+        if self._h:
+            lib().bpg_peer_free(self._h)
+            self._h = ctypes.c_void_p()
 
 
 def allgather_combine(engine, part, n_sets: int = 1, group=None) -> list[bytes]:

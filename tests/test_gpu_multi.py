@@ -143,3 +143,34 @@ def test_mpc_share_commitments_equal_the_provers(ctx):
     opened = sum_encode(ctx, parts, 2, 2)
     assert opened == [A_I1, A_O1]
     gens.close()
+
+
+def test_fused_exchange_single_rank(ctx):
+    """The fused exchange + combine kernel with world = 1 (push to its own buffer, wait on its own
+    flag, add one partial, encode): same bytes as the plain path, step after step (both parities of
+    the double buffer).  The multi-rank form is checked on real peers by bench.py --gpus N, whose
+    result must equal the NCCL form's, and by tools/multi_gpu_check.py."""
+    import torch
+
+    from mpc_bulletproof_b200 import Table
+    from mpc_bulletproof_b200.multi import PeerExchange
+
+    r = rng(401)
+    n, sets = 120, 2
+    ps = [rand_point(r) for _ in range(n)]
+    t = Table(ctx, points_bytes(ps)).set_windows(0)
+    px = PeerExchange(ctx, max_sets=4)
+    dev = torch.device("cuda", ctx.device)
+    for step in range(3):
+        ks = [[rand_scalar(r) for _ in range(n)] for _ in range(sets)]
+        raw = t.msm_partial(b"".join(scalars_bytes(k) for k in ks), n_sets=sets)
+        part = torch.frombuffer(bytearray(raw), dtype=torch.int32).to(dev)
+        out = torch.zeros(32 * sets, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        px.exchange_sum_encode(part.data_ptr(), sets, out.data_ptr())
+        ctx.sync()
+        got = bytes(out.cpu().numpy().tobytes())
+        assert [got[:32], got[32:]] == [G.msm(k, ps).encode() for k in ks]
+    assert px.ok()
+    px.close()
+    t.close()

@@ -56,6 +56,37 @@ def main():
         multi.sharded_msm(eng, loc_sc, n_sets=sets)
     out["sharded_msm_ms"] = (time.perf_counter() - t0) / 5 * 1e3
 
+    # 1b. the same sum with the exchange fused into the combine kernel (peer-mapped buffers, no NCCL)
+    px = multi.PeerExchange(ctx, max_sets=sets)
+    part = eng.partial(loc_sc, sets)
+    outb = torch.zeros(32 * sets, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    fused_ok = True
+    for _ in range(4):  # both buffer parities, twice
+        px.exchange_sum_encode(part.data_ptr(), sets, outb.data_ptr())
+        ctx.sync()
+        raw = bytes(outb.cpu().numpy().tobytes())
+        fused_ok = fused_ok and [raw[32 * i : 32 * i + 32] for i in range(sets)] == want
+    out["fused_exchange_equal"] = fused_ok and px.ok()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        px.exchange_sum_encode(part.data_ptr(), sets, outb.data_ptr())
+    ctx.sync()
+    out["fused_exchange_us"] = (time.perf_counter() - t0) / 50 * 1e6
+    parts = torch.empty(world * part.numel(), dtype=part.dtype, device=dev)
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        dist.all_gather_into_tensor(parts, part)
+        torch.cuda.synchronize()
+        from mpc_bulletproof_b200.api import dev_sum_encode
+        dev_sum_encode(ctx, parts.data_ptr(), world, sets, outb.data_ptr())
+        ctx.sync()
+    out["nccl_allgather_plus_combine_us"] = (time.perf_counter() - t0) / 50 * 1e6
+    dist.barrier()
+    px.close()
+
     # 2. MPC open: party p = rank p holds additive shares of the scalars over ALL points
     x = ks[0]
     xs = [int.from_bytes(x[32 * i : 32 * i + 32], "little") for i in range(1024)]
