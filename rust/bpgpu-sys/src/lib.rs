@@ -7,7 +7,7 @@ use std::os::raw::{c_char, c_int, c_void};
 macro_rules! opaque {
     ($($name:ident),*) => { $( #[repr(C)] pub struct $name { _private: [u8; 0] } )* };
 }
-opaque!(bpg_ctx, bpg_table, bpg_ipp, bpg_comb, bpg_r1cs_dev, bpg_stark_table);
+opaque!(bpg_ctx, bpg_table, bpg_ipp, bpg_comb, bpg_r1cs_dev, bpg_stark_table, bpg_peer);
 
 pub const BPG_OK: c_int = 0;
 pub const BPG_ERR_ARG: c_int = -1;
@@ -93,6 +93,22 @@ extern "C" {
     ) -> c_int;
     /// out[s] = encode(sum_p parts[p][s])
     pub fn bpg_sum_encode(ctx: *mut bpg_ctx, parts_ext: *const u8, n_parts: c_int, n_sets: c_int, out: *mut u8) -> c_int;
+
+    // ---- sharded sums, one process per GPU: exchange fused with the combine (peer-mapped buffers) ----
+    pub fn bpg_dev_msm_table(
+        ctx: *mut bpg_ctx, t: *const bpg_table, offset: usize, n: usize, d_scalars: *const c_void, n_sets: c_int,
+        d_out_ext: *mut c_void,
+    ) -> c_int;
+    pub fn bpg_peer_create(
+        ctx: *mut bpg_ctx, world: c_int, rank: c_int, max_sets: c_int, out: *mut *mut bpg_peer, handle_out: *mut u8,
+    ) -> c_int;
+    pub fn bpg_peer_connect(p: *mut bpg_peer, handles: *const u8) -> c_int;
+    pub fn bpg_dev_exchange_sum_encode(
+        ctx: *mut bpg_ctx, p: *mut bpg_peer, d_part: *const c_void, n_sets: c_int, d_out_bytes: *mut c_void,
+        d_out_ext: *mut c_void,
+    ) -> c_int;
+    pub fn bpg_peer_status(p: *mut bpg_peer, status_out: *mut c_int) -> c_int;
+    pub fn bpg_peer_free(p: *mut bpg_peer);
 
     // ---- InnerProductProof::create, src/inner_product_proof.rs:49-193 -------------------
     pub fn bpg_ipp_begin(
