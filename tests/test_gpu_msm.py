@@ -213,3 +213,33 @@ def test_windowed_large_bucket_array(ctx, c):
         finally:
             ctx.set_groups(0)
     t.close()
+
+
+def test_full_size_linearity_windowed(ctx):
+    """BASELINE.json's headline size (2^20 terms over a resident windowed table, c chosen by the
+    library: 20) through a size-independent property: a 2^10-point set tiled 1024 times must give
+    the MSM of the column-summed scalars over the 2^10 points, which the oracle confirms."""
+    import numpy as np
+
+    from mpc_bulletproof_b200 import Table
+
+    r = rng(97)
+    m, reps = 1024, 1024
+    ps = [rand_point(r) for _ in range(m)]
+    pb = points_bytes(ps)
+    big_table = Table(ctx, pb * reps).set_windows(0)
+    assert len(big_table) == 1 << 20 and big_table.window >= 18
+    g = np.random.Generator(np.random.PCG64(5))
+    raw = g.integers(0, 256, size=(m * reps, 32), dtype=np.uint8)
+    raw[:, 31] &= 0x0F  # < 2^252 < l
+    big = big_table.msm(raw.tobytes())[0]
+    big_table.close()
+    # column sums mod l with exact integers (object dtype would be slow: split into 4 x 64-bit limbs)
+    limbs = raw.view("<u8").reshape(reps, m, 4).astype(object)
+    col = limbs.sum(axis=0)
+    summed = [sum(int(col[i][k]) << (64 * k) for k in range(4)) % G.L for i in range(m)]
+    small_table = Table(ctx, pb)
+    small = small_table.msm(scalars_bytes(summed))[0]
+    small_table.close()
+    assert big == small
+    assert small == G.msm(summed, ps).encode()

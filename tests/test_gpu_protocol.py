@@ -392,3 +392,53 @@ def test_random_circuit_gadget(ctx, env):
     v.random_circuit(seed, n_mult, n_cons, bytes(bad))
     with pytest.raises(P.VerificationError):
         v.verify(proof)
+
+
+def test_full_size_r1cs_roundtrip(ctx):
+    """BASELINE.json's 2^16-multiplier size (too large for the Python oracle) through the properties
+    the reference's own tests use (tests/r1cs.rs: prove -> verify, serialization roundtrip, a false
+    statement and a tampered proof are rejected), for the bench circuit and the random circuit."""
+    import hashlib
+
+    from mpc_bulletproof_b200 import Comb, protocol as P
+
+    n = 1 << 16
+    comb = Comb(ctx, G.BASEPOINT.encode())
+
+    def pts(seed, count):
+        ks = b"".join(hashlib.sha512(seed + i.to_bytes(4, "little")).digest()[:31] + b"\x00" for i in range(count))
+        return comb.mul(ks)
+
+    gens = P.Gens(ctx, pts(b"G", n), pts(b"H", n), G.BASEPOINT.encode(), pts(b"B", 1))
+    p = P.Prover(gens, P.Transcript(b"full"))
+    p.square_chain(p.commit_public(123456789), n)
+    proof = p.prove(2024)
+    assert len(proof) == 1 + 11 * 32 + (2 * 16 + 2) * 32  # one phase, lg n = 16 (proof.rs:82-108)
+    p2 = P.Prover(gens, P.Transcript(b"full"))
+    p2.square_chain(p2.commit_public(123456789), n)
+    assert p2.prove(2024) == proof  # deterministic given the seed
+
+    def verifier(val):
+        v = P.Verifier(gens, P.Transcript(b"full"))
+        v.square_chain(v.commit_public(val), n)
+        return v
+
+    verifier(123456789).verify(proof)
+    with pytest.raises(P.VerificationError):
+        verifier(123456790).verify(proof)
+    bad = bytearray(proof)
+    bad[500] ^= 0x10
+    with pytest.raises((P.VerificationError, P.FormatError)):
+        verifier(123456789).verify(bytes(bad))
+    # random circuit: 2^15 multipliers, 2^16 constraints, 4 commitments
+    pr = P.Prover(gens, P.Transcript(b"full rand"))
+    Vs = [pr.commit(1000 + j, 77 + j)[0] for j in range(4)]
+    c0 = pr.random_circuit(11, 1 << 15, 1 << 16)
+    proof2 = pr.prove(5)
+    vr = P.Verifier(gens, P.Transcript(b"full rand"))
+    for V in Vs:
+        vr.commit(V)
+    vr.random_circuit(11, 1 << 15, 1 << 16, c0)
+    vr.verify(proof2)
+    gens.close()
+    comb.close()
