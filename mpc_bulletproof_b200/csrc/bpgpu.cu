@@ -1007,10 +1007,18 @@ extern "C" int bpg_dev_comb_mul(bpg_ctx* ctx, const bpg_comb* comb, const void* 
   if (!ctx || !comb || (!d_scalars && n) || n >= (1u << 31)) return BPG_ERR_ARG;
   if (n == 0) return BPG_OK;
   CK(cudaSetDevice(ctx->device));
-  k_comb_mul<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(comb->tables, comb->nbases,
-                                                                  (const uint32_t*)d_scalars, (uint32_t)n,
-                                                                  bias_for(4), (uint8_t*)d_out_bytes,
-                                                                  (uint32_t*)d_out_ext);
+  if (n <= 2048) {
+    // latency form: one warp per output
+    k_comb_mul_warp<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->stream>>>(comb->tables, comb->nbases,
+                                                                              (const uint32_t*)d_scalars, (uint32_t)n,
+                                                                              bias_for(4), (uint8_t*)d_out_bytes,
+                                                                              (uint32_t*)d_out_ext);
+  } else {
+    k_comb_mul<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(comb->tables, comb->nbases,
+                                                                    (const uint32_t*)d_scalars, (uint32_t)n,
+                                                                    bias_for(4), (uint8_t*)d_out_bytes,
+                                                                    (uint32_t*)d_out_ext);
+  }
   LAUNCH_CHECK();
   return BPG_OK;
 }

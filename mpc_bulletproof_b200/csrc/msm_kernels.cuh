@@ -953,6 +953,50 @@ __global__ void __launch_bounds__(128) k_comb_mul(const uint32_t* __restrict__ t
   if (out_bytes) ge_encode(out_bytes + (size_t)i * 32, acc);
 }
 
+// Few outputs (the five T_i of a proof, a V_j): one WARP per output.  The nbases*64 table lookups
+// are spread over the lanes (a handful of mixed additions each), then a shuffle tree of five full
+// additions; 128 dependent additions become ~4 + 5.
+__global__ void __launch_bounds__(128) k_comb_mul_warp(const uint32_t* __restrict__ tables, int nbases,
+                                                        const uint32_t* __restrict__ scalars, uint32_t n, sc_bias bias4,
+                                                        uint8_t* __restrict__ out_bytes, uint32_t* __restrict__ out_ext) {
+  uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint32_t lane = threadIdx.x & 31;
+  bool live = i < n;
+  uint32_t ii = live ? i : n - 1;  // idle warps shadow the last output (whole warps, shuffles stay uniform)
+  ge_ext acc = ge_identity();
+  for (int t = 0; t < nbases; t++) {
+    sc k;
+    sc_load(k, scalars + ((size_t)t * n + ii) * 8);
+    sc_recoded r = sc_recode(k.v, bias4);
+    const uint32_t* tab = tables + (size_t)t * COMB_ENTRIES * 24;
+    for (int j = lane; j < COMB_WINDOWS; j += 32) {
+      int d = sc_digit(r, j, 4);
+      if (d != 0) {
+        int mag = d < 0 ? -d : d;
+        ge_niels q;
+        ge_load_niels(q, tab + (size_t)(j * 8 + mag - 1) * 24);
+        acc = ge_madd(acc, q, d < 0);
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    ge_ext o;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      o.X.v[w] = __shfl_down_sync(0xffffffffu, acc.X.v[w], off);
+      o.Y.v[w] = __shfl_down_sync(0xffffffffu, acc.Y.v[w], off);
+      o.Z.v[w] = __shfl_down_sync(0xffffffffu, acc.Z.v[w], off);
+      o.T.v[w] = __shfl_down_sync(0xffffffffu, acc.T.v[w], off);
+    }
+    acc = ge_add(acc, o);
+  }
+  if (live && lane == 0) {
+    if (out_ext) ge_store_ext(out_ext + (size_t)i * 32, acc);
+    if (out_bytes) ge_encode(out_bytes + (size_t)i * 32, acc);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // windowed tables: out[w][i] = 2^(c w) * P_i in affine Niels, w < W.
 // One thread per point walks the doubling chain, parks the extended multiples and
