@@ -299,6 +299,22 @@ int bpg_stark_msm_table(bpg_ctx* ctx, const bpg_stark_table* table, size_t offse
                         int n_sets, uint8_t* out_xy);
 int bpg_stark_msm(bpg_ctx* ctx, const uint8_t* scalars_le, const uint8_t* points_xy, size_t n, uint8_t out_xy[64]);
 
+/* Inner-product-argument rounds over the Stark curve: `InnerProductProof::create`
+ * (src/inner_product_proof.rs:49-193) with the vectors resident in HBM, split at the transcript as
+ * bpg_ipp_* is (the fork's hash-chain transcript stays with the caller): round_LR returns the two
+ * points (x || y), the caller derives u and passes (u, u^-1) to round_fold; finish returns the last
+ * a, b.  G, H: ranges of resident Stark tables; factors may be NULL (all ones); scalars 32 bytes LE,
+ * canonical mod the Stark group order. */
+typedef struct bpg_stark_ipp bpg_stark_ipp;
+int bpg_stark_ipp_begin(bpg_ctx* ctx, const bpg_stark_table* G, size_t g_off, const bpg_stark_table* H, size_t h_off,
+                        size_t n, const uint8_t Q_xy[64], const uint8_t* G_factors, const uint8_t* H_factors,
+                        const uint8_t* a, const uint8_t* b, bpg_stark_ipp** out);
+size_t bpg_stark_ipp_rounds_left(const bpg_stark_ipp* st);
+int bpg_stark_ipp_round_LR(bpg_stark_ipp* st, uint8_t L_xy[64], uint8_t R_xy[64]);
+int bpg_stark_ipp_round_fold(bpg_stark_ipp* st, const uint8_t u[32], const uint8_t u_inv[32]);
+int bpg_stark_ipp_finish(bpg_stark_ipp* st, uint8_t a[32], uint8_t b[32]);
+void bpg_stark_ipp_free(bpg_stark_ipp* st);
+
 /* ==== host mirror of the reference's protocol layer ==================================
  * C bindings of the C++ host code in mpc_bulletproof_b200/csrc/host/: the transcript,
  * the generators as resident tables, InnerProductProof and the R1CS Prover/Verifier with

@@ -132,6 +132,12 @@ _SIGNATURES = {
     "bpg_stark_table_free": (None, [_P]),
     "bpg_stark_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),
     "bpg_stark_msm": (_I, [_P, _P, _P, _SZ, _P]),
+    "bpg_stark_ipp_begin": (_I, [_P, _P, _SZ, _P, _SZ, _SZ, _P, _P, _P, _P, _P, ctypes.POINTER(_P)]),
+    "bpg_stark_ipp_rounds_left": (_SZ, [_P]),
+    "bpg_stark_ipp_round_LR": (_I, [_P, _P, _P]),
+    "bpg_stark_ipp_round_fold": (_I, [_P, _P, _P]),
+    "bpg_stark_ipp_finish": (_I, [_P, _P, _P]),
+    "bpg_stark_ipp_free": (None, [_P]),
     "bpg_comb_create": (_I, [_P, _P, _I, ctypes.POINTER(_P)]),
     "bpg_comb_free": (None, [_P]),
     "bpg_comb_mul": (_I, [_P, _P, _P, _SZ, _P]),

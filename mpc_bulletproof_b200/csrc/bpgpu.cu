@@ -16,6 +16,7 @@
 #include "ipp_kernels.cuh"
 #include "svec_kernels.cuh"
 #include "stark_msm.cuh"
+#include "ipp_kernels_t.cuh"
 
 using namespace bpg;
 
@@ -1546,3 +1547,4 @@ extern "C" int bpg_msm_mixed(bpg_ctx* ctx, const uint8_t* adhoc_points, size_t n
 
 #include "r1cs_dev.inc"
 #include "stark_msm.inc"
+#include "stark_ipp.inc"

@@ -62,3 +62,49 @@ def msm(ctx: Context, scalars: bytes, points_xy: bytes) -> bytes:
     out = ctypes.create_string_buffer(64)
     check(lib().bpg_stark_msm(ctx._h, scalars, points_xy, len(scalars) // 32, out))
     return out.raw
+
+
+class StarkIpp:
+    """Device-resident state of `InnerProductProof::create` over the Stark curve (reference
+    src/inner_product_proof.rs:49-193); the caller owns the transcript:
+
+        st = StarkIpp(ctx, tG, tH, Q, Gf, Hf, a, b)
+        while st.rounds_left():
+            L, R = st.round_lr();  u = challenge(L, R);  st.round_fold(u, u_inv)
+        a, b = st.finish()
+    """
+
+    def __init__(self, ctx: Context, G: StarkTable, H: StarkTable, Q_xy: bytes, G_factors, H_factors, a: bytes, b: bytes,
+                 g_off: int = 0, h_off: int = 0):
+        n = len(a) // 32
+        self.ctx = ctx
+        self._h = ctypes.c_void_p()
+        check(lib().bpg_stark_ipp_begin(ctx._h, G._h, g_off, H._h, h_off, n, Q_xy, G_factors, H_factors, a, b, ctypes.byref(self._h)))
+        ctx._children.add(self)
+
+    def rounds_left(self) -> int:
+        return int(lib().bpg_stark_ipp_rounds_left(self._h))
+
+    def round_lr(self):
+        L, R = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64)
+        check(lib().bpg_stark_ipp_round_LR(self._h, L, R))
+        return L.raw, R.raw
+
+    def round_fold(self, u: bytes, u_inv: bytes):
+        check(lib().bpg_stark_ipp_round_fold(self._h, u, u_inv))
+
+    def finish(self):
+        a, b = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+        check(lib().bpg_stark_ipp_finish(self._h, a, b))
+        return a.raw, b.raw
+
+    def close(self):
+        if self._h:
+            lib().bpg_stark_ipp_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

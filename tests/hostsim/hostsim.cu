@@ -7,6 +7,7 @@
 #include "../../mpc_bulletproof_b200/csrc/ge.cuh"
 #include "../../mpc_bulletproof_b200/csrc/sc.cuh"
 #include "../../mpc_bulletproof_b200/csrc/stark_pt.cuh"
+#include "../../mpc_bulletproof_b200/csrc/stark_sc.cuh"
 using namespace bpg;
 
 static fe ld(const uint32_t* p) { fe a; for (int i = 0; i < 8; i++) a.v[i] = p[i]; return a; }
@@ -35,6 +36,15 @@ void hs_sp_from_aff(const uint32_t* aff, uint32_t* o) { sp_aff q; q.x = ldp(aff)
 void hs_sp_madd(const uint32_t* x, const uint32_t* aff, int neg, uint32_t* o) { sp_aff q; q.x = ldp(aff); q.y = ldp(aff + 8); stx(o, sp_madd(ldx(x), q, neg)); }
 void hs_sp_add(const uint32_t* a, const uint32_t* b, uint32_t* o) { stx(o, sp_add(ldx(a), ldx(b))); }
 void hs_sp_dbl(const uint32_t* a, uint32_t* o) { stx(o, sp_dbl(ldx(a))); }
+void hs_scs_montmul(const uint32_t* a, const uint32_t* b, uint32_t* o) {
+  sc x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); sc r = scs_montmul(x, y); memcpy(o, r.v, 32);
+}
+void hs_scs_add(const uint32_t* a, const uint32_t* b, uint32_t* o) {
+  sc x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); sc r = scs_add(x, y); memcpy(o, r.v, 32);
+}
+void hs_scs_sub(const uint32_t* a, const uint32_t* b, uint32_t* o) {
+  sc x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); sc r = scs_sub(x, y); memcpy(o, r.v, 32);
+}
 void hs_fe_mul(const uint32_t* a, const uint32_t* b, uint32_t* o) { st(o, fe_mul(ld(a), ld(b))); }
 void hs_fe_sq(const uint32_t* a, uint32_t* o) { st(o, fe_sq(ld(a))); }
 void hs_fe_add(const uint32_t* a, const uint32_t* b, uint32_t* o) { st(o, fe_add(ld(a), ld(b))); }

@@ -160,3 +160,50 @@ def test_windowed_table(ctx, c, gsub):
     # repeated scalars over a windowed table: long buckets
     assert t.msm(_sb([7] * n_tab))[0] == (7 * S.msm([1] * n_tab, ps)).encode()
     t.close()
+
+
+def _challenge(j, Lb, Rb):
+    import hashlib
+
+    return int.from_bytes(hashlib.sha256(b"stark ipp test" + bytes([j]) + Lb + Rb).digest(), "little") % N
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 32, 64])
+def test_ipp_rounds(ctx, n):
+    """`InnerProductProof::create` over the Stark curve, round by round (the transcript is the
+    caller's): L_j, R_j and the final a, b equal the oracle's, which FOLDS the generators as the
+    reference does (src/inner_product_proof.rs:125-134, 226-227) while the product never does; the
+    oracle's verifier accepts the result.  Sizes as the reference's make_ipp_* tests (:507-583)."""
+    from mpc_bulletproof_b200.stark import StarkIpp, StarkTable
+    from oracle import stark_ipp as I
+
+    r = rng(800 + n)
+    Gs, Hs = _pts(r, n), _pts(r, n)
+    Q = r.randrange(1, N) * S.GENERATOR
+    a = [r.randrange(N) for _ in range(n)]
+    b = [r.randrange(N) for _ in range(n)]
+    y_inv = r.randrange(1, N)
+    Gf = [1 if i < n // 2 else 7 for i in range(n)]  # as the R1CS prover: one, then a challenge
+    Hf = [pow(y_inv, i, N) for i in range(n)]
+    want_L, want_R, want_a, want_b = I.create(lambda j, L, R: _challenge(j, L.encode(), R.encode()), Q, Gf, Hf, Gs, Hs, a, b)
+    tG, tH = StarkTable(ctx, _pb(Gs)), StarkTable(ctx, _pb(Hs)).set_windows(0)
+    st = StarkIpp(ctx, tG, tH, Q.encode(), _sb(Gf), _sb(Hf), _sb(a), _sb(b))
+    assert st.rounds_left() == n.bit_length() - 1
+    Ls, Rs = [], []
+    j = 0
+    while st.rounds_left():
+        L, R = st.round_lr()
+        assert L == want_L[j].encode() and R == want_R[j].encode(), f"round {j}"
+        u = _challenge(j, L, R)
+        st.round_fold(S.sc_to_bytes(u), S.sc_to_bytes(pow(u, -1, N)))
+        Ls.append(S.Point.decode(L))
+        Rs.append(S.Point.decode(R))
+        j += 1
+    fa, fb = st.finish()
+    assert fa == S.sc_to_bytes(want_a) and fb == S.sc_to_bytes(want_b)
+    c = I.inner_product(a, b)
+    P = S.msm([a[i] * Gf[i] for i in range(n)] + [b[i] * Hf[i] for i in range(n)] + [c], Gs + Hs + [Q])
+    assert I.verify(lambda k, L, R: _challenge(k, L.encode(), R.encode()), n, Ls, Rs, want_a, want_b, Gf, Hf, P, Q, Gs, Hs)
+    st.close()
+    tG.close()
+    tH.close()

@@ -118,3 +118,26 @@ def test_decode_rejects(hs):
     big = (S.P).to_bytes(32, "little") + g.y.to_bytes(32, "little")  # x = p: not canonical
     assert hs.hs_sp_from_affine(U16(*[int.from_bytes(big[4 * i : 4 * i + 4], "little") for i in range(16)]), aff) == 0
     assert hs.hs_sp_from_affine(_aff_words(S.IDENTITY), aff) == 1
+
+
+def test_scalar_field(hs):
+    """stark_sc.cuh: Montgomery arithmetic modulo the Stark group order."""
+    r = random.Random(13)
+    o = U8()
+    n = S.N
+    rinv = pow(R, -1, n)
+    edge = [0, 1, n - 1, n - 2, (1 << 251), 0xFFFFFFFF, (1 << 192) - 1]
+    for _ in range(4000):
+        a = r.choice(edge) if r.random() < 0.2 else r.randrange(n)
+        b = r.choice(edge) if r.random() < 0.2 else r.randrange(n)
+        hs.hs_scs_montmul(w8(a), w8(b), o)
+        assert val(o) == a * b * rinv % n
+        hs.hs_scs_add(w8(a), w8(b), o)
+        assert val(o) == (a + b) % n
+        hs.hs_scs_sub(w8(a), w8(b), o)
+        assert val(o) == (a - b) % n
+    # any 256-bit left operand is reduced (conversion of canonical bytes and of products)
+    for _ in range(200):
+        a, b = r.getrandbits(256), r.randrange(n)
+        hs.hs_scs_montmul(w8(a), w8(b), o)
+        assert val(o) == a * b * rinv % n
