@@ -7,7 +7,7 @@ use std::os::raw::{c_char, c_int, c_void};
 macro_rules! opaque {
     ($($name:ident),*) => { $( #[repr(C)] pub struct $name { _private: [u8; 0] } )* };
 }
-opaque!(bpg_ctx, bpg_table, bpg_ipp, bpg_comb, bpg_r1cs_dev, bpg_stark_table, bpg_peer);
+opaque!(bpg_ctx, bpg_table, bpg_ipp, bpg_comb, bpg_r1cs_dev, bpg_stark_table, bpg_stark_ipp, bpg_peer);
 
 pub const BPG_OK: c_int = 0;
 pub const BPG_ERR_ARG: c_int = -1;
@@ -179,6 +179,18 @@ extern "C" {
         out_xy: *mut u8,
     ) -> c_int;
     pub fn bpg_stark_msm(ctx: *mut bpg_ctx, scalars: *const u8, points_xy: *const u8, n: usize, out_xy: *mut u8) -> c_int;
+
+    // InnerProductProof::create over the Stark curve, split at the transcript (src/inner_product_proof.rs:49-193)
+    pub fn bpg_stark_ipp_begin(
+        ctx: *mut bpg_ctx, g: *const bpg_stark_table, g_off: usize, h: *const bpg_stark_table, h_off: usize, n: usize,
+        q_xy: *const u8, g_factors: *const u8, h_factors: *const u8, a: *const u8, b: *const u8,
+        out: *mut *mut bpg_stark_ipp,
+    ) -> c_int;
+    pub fn bpg_stark_ipp_rounds_left(st: *const bpg_stark_ipp) -> usize;
+    pub fn bpg_stark_ipp_round_LR(st: *mut bpg_stark_ipp, l_xy: *mut u8, r_xy: *mut u8) -> c_int;
+    pub fn bpg_stark_ipp_round_fold(st: *mut bpg_stark_ipp, u: *const u8, u_inv: *const u8) -> c_int;
+    pub fn bpg_stark_ipp_finish(st: *mut bpg_stark_ipp, a: *mut u8, b: *mut u8) -> c_int;
+    pub fn bpg_stark_ipp_free(st: *mut bpg_stark_ipp);
 
     // ---- page-locked staging ---------------------------------------------------------------
     pub fn bpg_host_alloc(bytes: usize) -> *mut c_void;

@@ -73,6 +73,41 @@ def main():
                             "phases_ms": {k: round(v[0] / reps, 3) for k, v in prof.items() if v[1]}, "result_x": r[:32].hex()})
         print(out["rows"][-1], file=sys.stderr, flush=True)
         t.close()
+    # InnerProductProof::create rounds over the Stark curve (transcript stand-in: SHA-256 of L || R)
+    import hashlib
+
+    from mpc_bulletproof_b200.stark import StarkIpp
+
+    out["ipp"] = []
+    for lg in (10, 14, 16):
+        n = 1 << lg
+        pb = tile * (2 * n // base) if 2 * n >= base else tile[: 64 * 2 * n]
+        tG = StarkTable(ctx, pb[: 64 * n])
+        tH = StarkTable(ctx, pb[64 * n : 128 * n])
+        g = np.random.Generator(np.random.PCG64(100 + lg))
+        vecs = []
+        for _ in range(4):
+            a = g.integers(0, 256, size=(n, 32), dtype=np.uint8)
+            a[:, 31] &= 0x07
+            vecs.append(a.tobytes())
+        Q = tile[64 * 7 : 64 * 8]
+        best = 1e9
+        for it in range(3):
+            t0 = time.perf_counter()
+            st = StarkIpp(ctx, tG, tH, Q, vecs[2], vecs[3], vecs[0], vecs[1])
+            j = 0
+            while st.rounds_left():
+                L, R = st.round_lr()
+                u = int.from_bytes(hashlib.sha256(bytes([j]) + L + R).digest(), "little") % N
+                st.round_fold(u.to_bytes(32, "little"), pow(u, -1, N).to_bytes(32, "little"))
+                j += 1
+            fa, fb = st.finish()
+            best = min(best, (time.perf_counter() - t0) * 1e3)
+            st.close()
+        out["ipp"].append({"lg_n": lg, "create_ms": round(best, 3), "rounds": lg})
+        print(out["ipp"][-1], file=sys.stderr, flush=True)
+        tG.close()
+        tH.close()
     print(json.dumps(out))
 
 
