@@ -655,25 +655,29 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
     prof_mark(ctx, BPG_PROF_REDUCE);
     uint32_t arrays = windowed ? (uint32_t)nsets : cfg.narr;
     uint32_t* fin = windowed ? d_out_ext : wins;
-    uint32_t t = (cfg.nb + SLEAF_LC - 1) / SLEAF_LC;  // pairs per array after the leaf pass
+    // leaf: large arrays one thread per chunk of 8 (throughput), small ones one quad per chunk of 4
+    // plus the in-block tree (latency); the pairs levels and Horner are quad-cooperative
+    const bool sthread_leaf = cfg.nb >= (1u << 17);
+    uint32_t t = sthread_leaf ? (cfg.nb + SLEAF_LC - 1) / SLEAF_LC : (cfg.nb + SRT_QUADS * 4 - 1) / (SRT_QUADS * 4);
     uint32_t* pa[2] = {pairs, pairs + 2 * pair_words};
     int cur = 0;
     uint32_t* oa = t == 1 ? fin : pa[cur];
-    k_stark_leaf<<<(arrays * t + 127) / 128, 128, 0, st>>>(lvl0, cfg.nb, t, arrays, oa, pa[cur] + pair_words);
+    if (sthread_leaf) k_stark_leaf<<<(arrays * t + 127) / 128, 128, 0, st>>>(lvl0, cfg.nb, t, arrays, oa, pa[cur] + pair_words);
+    else k_stark_leaf4<4><<<arrays * t, SRT_THREADS, 0, st>>>(lvl0, cfg.nb, t, oa, pa[cur] + pair_words);
     LAUNCH_CHECK();
     while (t > 1) {
       uint32_t n = t;
-      t = (n + SPAIR_N - 1) / SPAIR_N;
+      t = (n + SRP_PAIRS - 1) / SRP_PAIRS;
       const uint32_t* ia = pa[cur];
       const uint32_t* iy = pa[cur] + pair_words;
       cur ^= 1;
       oa = t == 1 ? fin : pa[cur];
-      k_stark_pairs<<<arrays * t, SPAIR_N, 0, st>>>(ia, iy, n, t, oa, pa[cur] + pair_words);
+      k_stark_pairs4<<<arrays * t, SRP_THREADS, 0, st>>>(ia, iy, n, t, oa, pa[cur] + pair_words);
       LAUNCH_CHECK();
     }
     if (!windowed) {
       prof_mark(ctx, BPG_PROF_HORNER);
-      k_stark_horner<<<(nsets + 31) / 32, 32, 0, st>>>(wins, cfg, d_out_ext);
+      k_stark_horner4<<<nsets, 32, 0, st>>>(wins, cfg, d_out_ext);
       LAUNCH_CHECK();
     }
     prof_mark(ctx, -1);

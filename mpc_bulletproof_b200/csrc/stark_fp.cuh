@@ -191,20 +191,24 @@ BPG_DI fp fp_from_mont(const fp& a) {
   return fp_redc(t);
 }
 
-// a^(p-2); p - 2 = 2^251 + 17*2^192 - 1
+BPG_DI fp fp_sqn(fp a, int n) {
+  for (int i = 0; i < n; i++) a = fp_sq(a);
+  return a;
+}
+// a^(p-2);  p - 2 = 2^251 + 2^196 + (2^192 - 1)
 BPG_DI fp fp_invert(const fp& a) {
-  // exponent bits: bit 251; bits 196 and 192 of 17*2^192 minus one -> 17*2^192 - 1 = 16*2^192 + (2^192 - 1)
-  // p - 2 = 2^251 + 2^196 + (2^192 - 1)
-  fp x = a;             // a^(2^1 - 1)
-  fp acc = a;           // running a^(2^k - 1)
-  // a^(2^192 - 1) by square-and-multiply (every bit set)
-  for (int i = 1; i < 192; i++) acc = fp_mul(fp_sq(acc), x);
-  fp low = acc;         // a^(2^192 - 1)
-  // high part: a^(2^251 + 2^196) = (a^(2^55 + 1))^(2^196)
-  fp h = a;
-  for (int i = 0; i < 55; i++) h = fp_sq(h);  // a^(2^55)
-  h = fp_mul(h, a);                             // a^(2^55 + 1)
-  for (int i = 0; i < 196; i++) h = fp_sq(h);  // a^(2^251 + 2^196)
+  // a^(2^192 - 1) by the doubling ladder a^(2^2k - 1) = (a^(2^k - 1))^(2^k) * a^(2^k - 1): 191 squarings, 8 products
+  fp x2 = fp_mul(fp_sq(a), a);
+  fp x3 = fp_mul(fp_sq(x2), a);
+  fp x6 = fp_mul(fp_sqn(x3, 3), x3);
+  fp x12 = fp_mul(fp_sqn(x6, 6), x6);
+  fp x24 = fp_mul(fp_sqn(x12, 12), x12);
+  fp x48 = fp_mul(fp_sqn(x24, 24), x24);
+  fp x96 = fp_mul(fp_sqn(x48, 48), x48);
+  fp low = fp_mul(fp_sqn(x96, 96), x96);
+  // a^(2^251 + 2^196) = (a^(2^55 + 1))^(2^196)
+  fp h = fp_mul(fp_sqn(a, 55), a);
+  h = fp_sqn(h, 196);
   return fp_mul(h, low);
 }
 

@@ -14,6 +14,7 @@
 #pragma once
 #include "msm_kernels.cuh"
 #include "stark_pt.cuh"
+#include "stark_pt4.cuh"
 
 namespace bpg {
 
@@ -327,6 +328,110 @@ __global__ void __launch_bounds__(128) k_stark_merge(const uint32_t* __restrict_
     acc = sp_add(acc, o);
   }
   sp_store(merged + (size_t)q * 32, acc);
+}
+
+// ---- quad-cooperative tails (stark_pt4.cuh): the same pair hierarchy with four lanes per point ----
+constexpr int SRT_THREADS = 256;
+constexpr int SRT_QUADS = SRT_THREADS / 4;
+
+// in-block binary tree over `m` pairs in shared memory (m <= blockDim/4): A' = A0 + A1 + Y1, Y' = 2 (Y0 + Y1)
+__device__ __forceinline__ void srt_block_tree(uint32_t (*sa)[32], uint32_t (*sy)[32], uint32_t m) {
+  uint32_t quad = threadIdx.x >> 2, warp = threadIdx.x >> 5;
+  while (m > 1) {
+    uint32_t half = (m + 1) >> 1;
+    bool warp_live = warp * 8 < half;  // warp-uniform
+    sp4 A, Y;
+    if (warp_live) {
+      bool live = quad < half;
+      uint32_t q = live ? quad : 0;
+      bool have1 = 2 * q + 1 < m;
+      uint32_t i0 = 2 * q, i1 = have1 ? 2 * q + 1 : 2 * q;
+      sp4 a0 = sp4_load(sa[i0]), a1 = sp4_load(sa[i1]), y0 = sp4_load(sy[i0]), y1 = sp4_load(sy[i1]);
+      a1.c = fp_sel(have1, a1.c, fp_zero());
+      y1.c = fp_sel(have1, y1.c, fp_zero());
+      A = sp4_add(sp4_add(a0, a1), y1);
+      Y = sp4_dbl(sp4_add(y0, y1));
+    }
+    __syncthreads();
+    if (warp_live && quad < half) {
+      sp4_store(sa[quad], A);
+      sp4_store(sy[quad], Y);
+    }
+    __syncthreads();
+    m = half;
+  }
+}
+
+// leaf pass, one quad per chunk of LC buckets, then the in-block tree: a block reduces 64 LC buckets to one pair
+template <int LC>
+__global__ void __launch_bounds__(SRT_THREADS) k_stark_leaf4(const uint32_t* __restrict__ in /*[narr][n] XYZZ*/,
+                                                              uint32_t n, uint32_t tiles, uint32_t* __restrict__ out_a,
+                                                              uint32_t* __restrict__ out_y) {
+  __shared__ uint32_t sa[SRT_QUADS][32], sy[SRT_QUADS][32];
+  uint32_t arr = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+  uint32_t quad = threadIdx.x >> 2;
+  uint32_t first = (tile * SRT_QUADS + quad) * LC;
+  int valid = first >= n ? 0 : (int)min((uint32_t)LC, n - first);
+  const uint32_t* src = in + ((size_t)arr * n + min(first, n - 1)) * 32;
+  sp4 run = sp4_identity(), acc = sp4_identity();
+#pragma unroll 2
+  for (int k = LC - 1; k >= 0; k--) {
+    bool have = k < valid;
+    sp4 x = sp4_load(src + (size_t)(have ? k : 0) * 32);
+    x.c = fp_sel(have, x.c, fp_zero());
+    run = sp4_add(run, x);
+    acc = sp4_add(acc, run);
+  }
+#pragma unroll
+  for (int i = 1; i < LC; i <<= 1) run = sp4_dbl(run);
+  sp4_store(sa[quad], acc);
+  sp4_store(sy[quad], run);
+  __syncthreads();
+  srt_block_tree(sa, sy, SRT_QUADS);
+  if (threadIdx.x < 32) {
+    size_t o = ((size_t)arr * tiles + tile) * 32;
+    out_a[o + threadIdx.x] = sa[0][threadIdx.x];
+    out_y[o + threadIdx.x] = sy[0][threadIdx.x];
+  }
+}
+
+// up to 64 pairs per block -> one (the final launch has tiles == 1 and writes T to out_a)
+constexpr int SRP_THREADS = 128;
+constexpr uint32_t SRP_PAIRS = SRP_THREADS / 2;
+__global__ void __launch_bounds__(SRP_THREADS) k_stark_pairs4(const uint32_t* __restrict__ in_a,
+                                                               const uint32_t* __restrict__ in_y, uint32_t n,
+                                                               uint32_t tiles, uint32_t* __restrict__ out_a,
+                                                               uint32_t* __restrict__ out_y) {
+  __shared__ uint32_t sa[SRP_PAIRS][32], sy[SRP_PAIRS][32];
+  uint32_t arr = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+  uint32_t first = tile * SRP_PAIRS;
+  uint32_t m = min(SRP_PAIRS, n - first);
+  const uint32_t* ga = in_a + ((size_t)arr * n + first) * 32;
+  const uint32_t* gy = in_y + ((size_t)arr * n + first) * 32;
+  for (uint32_t w = threadIdx.x; w < m * 32; w += blockDim.x) {
+    sa[w >> 5][w & 31] = ga[w];
+    sy[w >> 5][w & 31] = gy[w];
+  }
+  __syncthreads();
+  srt_block_tree(sa, sy, m);
+  if (threadIdx.x < 32) {
+    size_t o = ((size_t)arr * tiles + tile) * 32;
+    out_a[o + threadIdx.x] = sa[0][threadIdx.x];
+    out_y[o + threadIdx.x] = sy[0][threadIdx.x];
+  }
+}
+
+// plain tables, one warp per set: sum_w 2^(c w) S_w, every quad runs the same chain
+__global__ void __launch_bounds__(32) k_stark_horner4(const uint32_t* __restrict__ window_sums, MsmCfg cfg,
+                                                       uint32_t* __restrict__ out) {
+  uint32_t set = blockIdx.x;
+  const uint32_t* src = window_sums + (size_t)set * cfg.W * 32;
+  sp4 acc = sp4_load(src + (size_t)(cfg.W - 1) * 32);
+  for (int w = cfg.W - 2; w >= 0; w--) {
+    for (int i = 0; i < cfg.c; i++) acc = sp4_dbl(acc);
+    acc = sp4_add(acc, sp4_load(src + (size_t)w * 32));
+  }
+  if (threadIdx.x < 4) sp4_store(out + (size_t)set * 32, acc);
 }
 
 }  // namespace bpg
