@@ -522,15 +522,58 @@ def cpu_baseline(args, pts_bytes_dev, scal_dev, n):
     ctx2 = Context(0)
     gpu = Table(ctx2, pts).msm(sc)[0]
     ctx2.close()
+    ipp = cpu_ipp_baseline(cbind, threads, pts, sc, 14)
     return {
         "value": m / dt / 1e6,
         "unit": UNIT,
         "cores": threads,
         "kind": "port",
+        "ipp_create": ipp,
         "sample": f"first 2^{m.bit_length() - 1} points+scalars of the workload, dalek-style radix-2^8 Pippenger, points pre-decoded, {reps} runs",
         "single_thread_value": (m // 4) / dt1 / 1e6,
         "bytes_equal_gpu": gpu == out,
     }
+
+
+def cpu_ipp_baseline(cbind, threads, pts, sc, lg):
+    """BASELINE.json config 2 beside the GPU numbers: the C restatement of the reference's CPU
+    `InnerProductProof::create` (src/inner_product_proof.rs:49-193: factor multiplications one after
+    the other, two-term MSM folds on all threads above the threshold) at n = 2^lg, and the product's
+    `bpg_ipp_create` on the same inputs; the final a, b must agree byte for byte (the challenges fed
+    to the CPU run are the ones the product's transcript produced)."""
+    import ctypes
+
+    from mpc_bulletproof_b200 import Context, Table
+    from mpc_bulletproof_b200 import protocol as P
+
+    n = 1 << lg
+    Gb, Hb, Q = pts[: 32 * n], pts[32 * n : 64 * n], pts[64 * n : 64 * n + 32]
+    a, b, Gf, Hf = sc[: 32 * n], sc[32 * n : 64 * n], sc[64 * n : 96 * n], sc[96 * n : 128 * n]
+    ctx = Context(0)
+    tab = Table(ctx, Gb + Hb).set_windows(0)
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        proof = P.InnerProductProof.create(ctx, P.Transcript(b"bench ipp"), Q, Gf, Hf, tab, tab, a, b, h_off=n)
+        best = min(best, time.perf_counter() - t0)
+    # replay the transcript on the host mirror to recover the challenges u_j
+    tr = P.Transcript(b"bench ipp")
+    tr.append_message(b"dom-sep", b"ipp v1")
+    tr.append_u64(b"n", n)
+    us = b""
+    for L, R in zip(proof.L_vec, proof.R_vec):
+        tr.append_message(b"L", L)
+        tr.append_message(b"R", R)
+        us += P.sc_bytes(tr.challenge_scalar(b"u"))
+    t0 = time.perf_counter()
+    lr, fa, fb = cbind.ipp_create(Q, Gf, Hf, Gb, Hb, a, b, us, threads)
+    cpu_s = time.perf_counter() - t0
+    same = [x for pair in lr for x in pair] == [x for pair in zip(proof.L_vec, proof.R_vec) for x in pair]
+    same = same and fa == P.sc_bytes(proof.a) and fb == P.sc_bytes(proof.b)
+    tab.close()
+    ctx.close()
+    return {"n": n, "cpu_ms": cpu_s * 1e3, "cores": threads, "gpu_ms": best * 1e3, "kind": "port",
+            "bytes_equal_gpu": same, "note": "points decoded inside the CPU run; GPU generators resident in one windowed table"}
 
 
 def free_port():

@@ -537,6 +537,153 @@ void oracle_basepoint_mul(const uint8_t* scalars, size_t n, uint8_t* out, int th
   }
 }
 
+/* ---------------------------------------------------------------- scalars mod l (4x64 Montgomery)
+ * For the CPU restatement of InnerProductProof::create below (the reference's scalars are a
+ * Montgomery 4x64 field too: ark-ff Fp256). */
+typedef unsigned __int128 u128;
+typedef struct { uint64_t v[4]; } scm;
+static const uint64_t SC_L[4] = {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0x0ULL, 0x1000000000000000ULL};
+static const uint64_t SC_RR[4] = {0xa40611e3449c0f01ULL, 0xd00e1ba768859347ULL, 0xceec73d217f5be65ULL, 0x0399411b7c309a3dULL};
+static const uint64_t SC_NINV = 0xd2b51da312547e1bULL; /* -l^-1 mod 2^64 */
+static int scm_geq_l(const uint64_t x[4]) {
+  for (int i = 3; i >= 0; i--) { if (x[i] > SC_L[i]) return 1; if (x[i] < SC_L[i]) return 0; }
+  return 1;
+}
+static void scm_sub_l(uint64_t x[4]) {
+  u128 bw = 0;
+  for (int i = 0; i < 4; i++) { u128 t = (u128)x[i] - SC_L[i] - bw; x[i] = (uint64_t)t; bw = (t >> 64) & 1; }
+}
+static void scm_montmul(scm* r, const scm* a, const scm* b) {
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) { u128 s = (u128)a->v[j] * b->v[i] + t[j] + c; t[j] = (uint64_t)s; c = s >> 64; }
+    u128 s = (u128)t[4] + c; t[4] = (uint64_t)s; t[5] = (uint64_t)(s >> 64);
+    uint64_t m = t[0] * SC_NINV;
+    c = ((u128)m * SC_L[0] + t[0]) >> 64;
+    for (int j = 1; j < 4; j++) { u128 s2 = (u128)m * SC_L[j] + t[j] + c; t[j - 1] = (uint64_t)s2; c = s2 >> 64; }
+    s = (u128)t[4] + c; t[3] = (uint64_t)s; t[4] = t[5] + (uint64_t)(s >> 64); t[5] = 0;
+  }
+  memcpy(r->v, t, 32);
+  if (t[4] || scm_geq_l(r->v)) scm_sub_l(r->v);
+}
+static void scm_add(scm* r, const scm* a, const scm* b) {
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) { u128 s = (u128)a->v[i] + b->v[i] + c; r->v[i] = (uint64_t)s; c = s >> 64; }
+  if (scm_geq_l(r->v)) scm_sub_l(r->v);
+}
+static void scm_from_bytes(scm* r, const uint8_t b[32]) { scm a, rr; memcpy(a.v, b, 32); memcpy(rr.v, SC_RR, 32); scm_montmul(r, &a, &rr); }
+static void scm_to_bytes(uint8_t out[32], const scm* a) { scm one = {{1, 0, 0, 0}}, n; scm_montmul(&n, a, &one); memcpy(out, n.v, 32); }
+static void scm_invert(scm* r, const scm* a) { /* a^(l-2) */
+  static const uint64_t e[4] = {0x5812631a5cf5d3ebULL, 0x14def9dea2f79cd6ULL, 0x0ULL, 0x1000000000000000ULL};
+  scm one_b = {{1, 0, 0, 0}}, rr, acc, base = *a;
+  memcpy(rr.v, SC_RR, 32);
+  scm_montmul(&acc, &one_b, &rr); /* Montgomery one */
+  for (int i = 0; i < 256; i++) {
+    if ((e[i >> 6] >> (i & 63)) & 1) scm_montmul(&acc, &acc, &base);
+    scm_montmul(&base, &base, &base);
+  }
+  *r = acc;
+}
+
+/* ---------------------------------------------------------------- InnerProductProof::create on the CPU
+ * Restates reference src/inner_product_proof.rs:49-193 and fold_witness :202-248 as the fork runs
+ * them on the CPU: cross terms serially, L and R as variable-time MSMs, in round 0 the 2n
+ * generators multiplied by their factors one after the other (:125-134), every fold a two-term
+ * MSM per generator, thread-parallel (rayon there, OpenMP here) only at or above
+ * PARALLELISM_THRESHOLD = 10 (:26, :217).  The challenges are inputs (u_j, canonical), so that the
+ * result can be compared with oracle/protocol.py and the run timed without a transcript.
+ * out_LR: lg n x 64 bytes (L_j | R_j); out_ab: a | b.  Returns 0, -3 (not a power of two), -5. */
+static void msm_any(ge* r, const uint8_t* scalars, const ge* pts, size_t n, int threads) {
+  if (n == 0) ge_identity(r);
+  else if (n < 190) straus(r, scalars, pts, n);
+  else pippenger(r, scalars, pts, n, threads);
+}
+int oracle_ipp_create(size_t n, const uint8_t Q_enc[32], const uint8_t* G_factors, const uint8_t* H_factors,
+                      const uint8_t* G_enc, const uint8_t* H_enc, const uint8_t* a_in, const uint8_t* b_in,
+                      const uint8_t* challenges, uint8_t* out_LR, uint8_t out_ab[64], int threads) {
+  k_init();
+  if (n == 0 || (n & (n - 1))) return -3;
+  ge* G = malloc(n * sizeof(ge));
+  ge* H = malloc(n * sizeof(ge));
+  ge Q;
+  scm* a = malloc(n * sizeof(scm));
+  scm* b = malloc(n * sizeof(scm));
+  int bad = !ge_decode(&Q, Q_enc);
+  for (size_t i = 0; i < n; i++) {
+    bad |= !ge_decode(&G[i], G_enc + 32 * i);
+    bad |= !ge_decode(&H[i], H_enc + 32 * i);
+    scm_from_bytes(&a[i], a_in + 32 * i);
+    scm_from_bytes(&b[i], b_in + 32 * i);
+  }
+  if (bad) { free(G); free(H); free(a); free(b); return -5; }
+  uint8_t* sc = malloc((n + 1) * 32);
+  ge* pts = malloc((n + 1) * sizeof(ge));
+  size_t m = n;
+  int round = 0;
+  while (m != 1) {
+    size_t h = m / 2;
+    /* c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo>  (:87-88, :156-157) */
+    scm cl = {{0, 0, 0, 0}}, cr = {{0, 0, 0, 0}}, t;
+    for (size_t i = 0; i < h; i++) {
+      scm_montmul(&t, &a[i], &b[h + i]); scm_add(&cl, &cl, &t);
+      scm_montmul(&t, &a[h + i], &b[i]); scm_add(&cr, &cr, &t);
+    }
+    for (int side = 0; side < 2; side++) { /* L then R (:90-114, :159-172) */
+      for (size_t i = 0; i < h; i++) {
+        scm x = side == 0 ? a[i] : a[h + i];       /* a_lo with G_hi | a_hi with G_lo */
+        scm y = side == 0 ? b[h + i] : b[i];       /* b_hi with H_lo | b_lo with H_hi */
+        if (round == 0 && G_factors) { scm f; scm_from_bytes(&f, G_factors + 32 * (side == 0 ? h + i : i)); scm_montmul(&x, &x, &f); }
+        if (round == 0 && H_factors) { scm f; scm_from_bytes(&f, H_factors + 32 * (side == 0 ? i : h + i)); scm_montmul(&y, &y, &f); }
+        scm_to_bytes(sc + 32 * i, &x);
+        scm_to_bytes(sc + 32 * (h + i), &y);
+        pts[i] = side == 0 ? G[h + i] : G[i];
+        pts[h + i] = side == 0 ? H[i] : H[h + i];
+      }
+      scm_to_bytes(sc + 32 * m, side == 0 ? &cl : &cr);
+      pts[m] = Q;
+      ge r;
+      msm_any(&r, sc, pts, m + 1, threads);
+      ge_encode(out_LR + 64 * round + 32 * side, &r);
+    }
+    scm u, ui;
+    scm_from_bytes(&u, challenges + 32 * round);
+    scm_invert(&ui, &u);
+    if (round == 0) { /* G_i <- g_i G_i, H_i <- h_i H_i, one after the other (:125-134) */
+      for (size_t i = 0; i < m; i++) {
+        if (G_factors) { ge r; straus(&r, G_factors + 32 * i, &G[i], 1); G[i] = r; }
+        if (H_factors) { ge r; straus(&r, H_factors + 32 * i, &H[i], 1); H[i] = r; }
+      }
+    }
+    uint8_t ub[32], uib[32];
+    scm_to_bytes(ub, &u);
+    scm_to_bytes(uib, &ui);
+    /* fold_witness (:202-248): serial below the threshold, thread-parallel at or above it */
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(threads > 1 ? threads : 1) if (h >= 10 && threads > 1)
+#endif
+    for (size_t i = 0; i < h; i++) {
+      scm t1, t2;
+      scm_montmul(&t1, &a[i], &u); scm_montmul(&t2, &a[h + i], &ui); scm_add(&a[i], &t1, &t2);   /* a_lo u + u^-1 a_hi */
+      scm_montmul(&t1, &b[i], &ui); scm_montmul(&t2, &b[h + i], &u); scm_add(&b[i], &t1, &t2);   /* b_lo u^-1 + u b_hi */
+      uint8_t s2[64];
+      ge p2[2], r;
+      memcpy(s2, uib, 32); memcpy(s2 + 32, ub, 32);
+      p2[0] = G[i]; p2[1] = G[h + i];
+      straus(&r, s2, p2, 2); G[i] = r;                                                              /* u^-1 G_lo + u G_hi */
+      memcpy(s2, ub, 32); memcpy(s2 + 32, uib, 32);
+      p2[0] = H[i]; p2[1] = H[h + i];
+      straus(&r, s2, p2, 2); H[i] = r;                                                              /* u H_lo + u^-1 H_hi */
+    }
+    m = h;
+    round++;
+  }
+  scm_to_bytes(out_ab, &a[0]);
+  scm_to_bytes(out_ab + 32, &b[0]);
+  free(G); free(H); free(a); free(b); free(sc); free(pts);
+  return 0;
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -22,6 +22,8 @@ def lib():
         L.oracle_msm_decoded.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_int]
         L.oracle_basepoint_mul.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_int]
         L.oracle_max_threads.restype = ctypes.c_int
+        L.oracle_ipp_create.restype = ctypes.c_int
+        L.oracle_ipp_create.argtypes = [ctypes.c_size_t] + [ctypes.c_char_p] * 10 + [ctypes.c_int]
         _lib = L
     return _lib
 
@@ -66,3 +68,17 @@ class DecodedPoints:
         if getattr(self, "_h", None):
             lib().oracle_points_free(self._h)
             self._h = None
+
+
+def ipp_create(Q: bytes, G_factors, H_factors, G: bytes, H: bytes, a: bytes, b: bytes, challenges: bytes, threads: int = 1):
+    """CPU restatement of InnerProductProof::create with the challenges as inputs
+    -> ([(L_j, R_j)], a, b) as bytes."""
+    n = len(a) // 32
+    lg = n.bit_length() - 1
+    out_lr = ctypes.create_string_buffer(64 * max(lg, 1))
+    out_ab = ctypes.create_string_buffer(64)
+    rc = lib().oracle_ipp_create(n, Q, G_factors, H_factors, G, H, a, b, challenges, out_lr, out_ab, threads)
+    if rc:
+        raise ValueError(f"oracle_ipp_create rc={rc}")
+    lr = [(out_lr.raw[64 * j : 64 * j + 32], out_lr.raw[64 * j + 32 : 64 * j + 64]) for j in range(lg)]
+    return lr, out_ab.raw[:32], out_ab.raw[32:]

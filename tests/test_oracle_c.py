@@ -34,3 +34,43 @@ def test_c_basepoint_mul_and_rfc_vectors():
 def test_c_rejects_bad_point():
     with pytest.raises(ValueError):
         cbind.msm(scalars_bytes([1]), bytes.fromhex("01" + "00" * 31))
+
+
+def test_cpu_ipp_create_matches_protocol_oracle():
+    """oracle_ipp_create (the timed CPU restatement of InnerProductProof::create,
+    src/inner_product_proof.rs:49-193) against oracle/protocol.py on the same inputs, the
+    challenges being those the Merlin transcript produced: same L_j, R_j, a, b."""
+    import random
+
+    from oracle import cbind
+    from oracle import group as G
+    from oracle import protocol as O
+
+    class Recorder(O.Transcript):
+        def __init__(self, label):
+            super().__init__(label)
+            self.us = []
+
+        def challenge_scalar(self, label):
+            u = super().challenge_scalar(label)
+            if label == b"u":
+                self.us.append(u)
+            return u
+
+    r = random.Random(21)
+    for n in (1, 2, 8, 32):
+        bp = O.BulletproofGens(n, 1)
+        Gs, Hs = bp.G(n), bp.H(n)
+        Q = G.hash_to_group_sha512(b"cpu ipp")
+        a = [r.randrange(G.L) for _ in range(n)]
+        b = [r.randrange(G.L) for _ in range(n)]
+        Gf = [1 if i < n // 2 else 5 for i in range(n)]
+        Hf = [pow(7, i, G.L) for i in range(n)]
+        tr = Recorder(b"cpu ipp test")
+        want = O.InnerProductProof.create(tr, Q, Gf, Hf, Gs, Hs, a, b)
+        sb = lambda xs: b"".join(G.sc_to_bytes(x) for x in xs)
+        pb = lambda ps: b"".join(p.encode() for p in ps)
+        for threads in (1, 4):
+            lr, fa, fb = cbind.ipp_create(Q.encode(), sb(Gf), sb(Hf), pb(Gs), pb(Hs), sb(a), sb(b), sb(tr.us) or b"\0" * 32, threads)
+            assert [x for pair in lr for x in pair] == [p.encode() for pair in zip(want.L_vec, want.R_vec) for p in pair]
+            assert fa == G.sc_to_bytes(want.a) and fb == G.sc_to_bytes(want.b)
