@@ -553,8 +553,17 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   // reduction geometry: `rarr` arrays of nb buckets.  Small arrays: a leaf block of RT_QUADS quad
   // chunks of LC buckets plus its in-block tree; large arrays: one thread per chunk of 16.
   uint32_t rarr = windowed ? (uint32_t)nsets : cfg.narr;
-  const bool thread_leaf = cfg.nb >= (1u << 17);
-  const uint32_t LC = thread_leaf ? 16 : (cfg.nb > (1u << 15) ? 8 : 4);
+  bool thread_leaf = cfg.nb >= (1u << 17);
+  uint32_t LC = thread_leaf ? 16 : (cfg.nb > (1u << 15) ? 8 : 4);
+  {
+    // tuning experiment: BPG_LEAF=t4|t8|t16|q4|q8 overrides the leaf geometry
+    static const char* leaf_env = getenv("BPG_LEAF");
+    if (leaf_env && (leaf_env[0] == 't' || leaf_env[0] == 'q') && curve == 0) {
+      int v = atoi(leaf_env + 1);
+      if (leaf_env[0] == 't' && (v == 4 || v == 8 || v == 16)) { thread_leaf = true; LC = (uint32_t)v; }
+      if (leaf_env[0] == 'q' && (v == 4 || v == 8)) { thread_leaf = false; LC = (uint32_t)v; }
+    }
+  }
   uint32_t tiles0 = thread_leaf ? (cfg.nb + LC - 1) / LC : (cfg.nb + RT_QUADS * LC - 1) / (RT_QUADS * LC);
   size_t ntiles = (cfg.B + SCAN_TILE - 1) / SCAN_TILE;
   size_t off = 0;
@@ -711,9 +720,15 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
     uint32_t* pa[2] = {pairs, pairs + 2 * pair_words};
     int cur = 0;
     uint32_t* oa = t == 1 ? final_out : pa[cur];
-    if (thread_leaf) {
+    if (thread_leaf && LC == 16) {
       k_reduce_leaf_thread<16><<<(rarr * t + RL_THREADS - 1) / RL_THREADS, RL_THREADS, 0, st>>>(level0, cfg.nb, t, rarr, oa,
                                                                                                pa[cur] + pair_words);
+    } else if (thread_leaf && LC == 8) {
+      k_reduce_leaf_thread<8><<<(rarr * t + RL_THREADS - 1) / RL_THREADS, RL_THREADS, 0, st>>>(level0, cfg.nb, t, rarr, oa,
+                                                                                              pa[cur] + pair_words);
+    } else if (thread_leaf) {
+      k_reduce_leaf_thread<4><<<(rarr * t + RL_THREADS - 1) / RL_THREADS, RL_THREADS, 0, st>>>(level0, cfg.nb, t, rarr, oa,
+                                                                                              pa[cur] + pair_words);
     } else if (LC == 8) {
       k_reduce_leaf<8><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
     } else {
@@ -754,7 +769,7 @@ extern "C" int bpg_dev_sum_encode(bpg_ctx* ctx, const void* d_parts, int n_parts
   if (!ctx || !d_parts || n_parts <= 0 || n_sets <= 0) return BPG_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   prof_mark(ctx, BPG_PROF_ENCODE);
-  k_sum_encode<<<(n_sets + 31) / 32, 32, 0, ctx->stream>>>((const uint32_t*)d_parts, n_parts, n_sets,
+  k_sum_encode<<<(n_sets + 1) / 2, ENC_THREADS, 0, ctx->stream>>>((const uint32_t*)d_parts, n_parts, n_sets,
                                                            (uint8_t*)d_out_bytes, (uint32_t*)d_out_ext);
   LAUNCH_CHECK();
   prof_mark(ctx, -1);
@@ -1342,16 +1357,16 @@ extern "C" int bpg_ipp_round_fold(bpg_ipp* st, const uint8_t u[32], const uint8_
   bpg_ctx* ctx = st->ctx;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  memcpy(ctx->h_pinned + 1024, u, 32);
-  memcpy(ctx->h_pinned + 1056, u_inv, 32);
-  CK(cudaMemcpyAsync(st->u_pair, ctx->h_pinned + 1024, 64, cudaMemcpyHostToDevice, s));
+  // the challenge pair travels as kernel arguments: no staging copy, and no wait here -- the
+  // next round's launches queue up behind the fold
+  ScPair up;
+  memcpy(up.v, u, 32);
+  memcpy(up.v + 8, u_inv, 32);
   prof_mark(ctx, BPG_PROF_OTHER);
   k_ipp_fold<<<(unsigned)((st->n + 255) / 256), 256, 0, s>>>(st->a, st->b, st->wG, st->wH, (uint32_t)st->n,
-                                                             (uint32_t)st->m, st->u_pair);
+                                                             (uint32_t)st->m, up);
   LAUNCH_CHECK();
   prof_mark(ctx, -1);
-  // h_pinned is reused by the next call: make sure the copy has been consumed
-  CK(cudaStreamSynchronize(s));
   st->m /= 2;
   st->lr_done = false;
   return BPG_OK;

@@ -154,15 +154,23 @@ __global__ void __launch_bounds__(256) k_ipp_round_scalars(const uint32_t* __res
   set_ids[n + i] = hi ? 1 : 0;
 }
 
+// the round's challenge and its inverse (canonical words), passed by value
+struct ScPair {
+  uint32_t v[16];
+};
+
 // fold_witness (:202-248) for a, b; the generator fold becomes a weight update
 __global__ void __launch_bounds__(256) k_ipp_fold(uint32_t* __restrict__ a, uint32_t* __restrict__ b,
                                                    uint32_t* __restrict__ wG, uint32_t* __restrict__ wH, uint32_t n,
-                                                   uint32_t m, const uint32_t* __restrict__ u_pair /*u, u_inv*/) {
+                                                   uint32_t m, ScPair u_pair /*u, u_inv: kernel arguments, no copy*/) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   sc u, ui;
-  sc_load(u, u_pair);
-  sc_load(ui, u_pair + 8);
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    u.v[w] = u_pair.v[w];
+    ui.v[w] = u_pair.v[8 + w];
+  }
   u = sc_to_mont(u);
   ui = sc_to_mont(ui);
   uint32_t h = m >> 1;

@@ -127,12 +127,15 @@ __global__ void __launch_bounds__(256) k_ipp_round_scalars_t(const uint32_t* __r
 template <class SP>
 __global__ void __launch_bounds__(256) k_ipp_fold_t(uint32_t* __restrict__ a, uint32_t* __restrict__ b,
                                                      uint32_t* __restrict__ wG, uint32_t* __restrict__ wH, uint32_t n,
-                                                     uint32_t m, const uint32_t* __restrict__ u_pair /*u, u_inv: normal form*/) {
+                                                     uint32_t m, ScPair u_pair /*u, u_inv: normal form, by value*/) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   sc u, ui;
-  sc_load(u, u_pair);
-  sc_load(ui, u_pair + 8);
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    u.v[w] = u_pair.v[w];
+    ui.v[w] = u_pair.v[8 + w];
+  }
   u = SP::montmul(u, SP::rr());
   ui = SP::montmul(ui, SP::rr());
   uint32_t h = m >> 1;

@@ -26,6 +26,7 @@
 #pragma once
 #include "ge.cuh"
 #include "ge4.cuh"
+#include "fe16.cuh"
 #include "sc.cuh"
 
 namespace bpg {
@@ -762,11 +763,30 @@ __global__ void __launch_bounds__(256) k_seg_point_ids(SegIds sg, uint32_t total
 // finishing: sum `nparts` partial sums per set (one per rank), encode
 // ---------------------------------------------------------------------------
 // parts layout: [part][set][32 words]
-__global__ void k_sum_encode(const uint32_t* __restrict__ parts, int nparts, int nsets,
-                             uint8_t* __restrict__ out_bytes /*nsets*32*/,
-                             uint32_t* __restrict__ out_ext /*nsets*32 words, may be null*/) {
-  int set = blockIdx.x * blockDim.x + threadIdx.x;
-  if (set >= nsets) return;
+// One HALF-WARP per set: the sum of the parts is computed redundantly by its sixteen lanes, the
+// encoding (one inverse square root, 252 dependent squarings) runs on the sixteen-lane field
+// layer of fe16.cuh.  Idle groups shadow the last set, so that every warp-wide exchange sees
+// all 32 lanes.
+constexpr int ENC_THREADS = 32;
+__device__ __forceinline__ void store_s_bytes(uint8_t* out, const fe& s, uint32_t k) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) w = (k >> 1) == (uint32_t)i ? s.v[i] : w;
+  w = (k & 1u) ? (w >> 16) : w;
+  out[2 * k] = (uint8_t)w;
+  out[2 * k + 1] = (uint8_t)(w >> 8);
+}
+__global__ void __launch_bounds__(ENC_THREADS) k_sum_encode(const uint32_t* __restrict__ parts, int nparts, int nsets,
+                                                             uint8_t* __restrict__ out_bytes /*nsets*32*/,
+                                                             uint32_t* __restrict__ out_ext /*nsets*32 words, may be null*/) {
+  __shared__ __align__(16) uint32_t sm[(ENC_THREADS / 16) * G16_WORDS];
+  uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  bool live = gid < (uint32_t)nsets;
+  uint32_t set = live ? gid : (uint32_t)nsets - 1;
+  grp16 g;
+  g.sm = sm + (threadIdx.x >> 4) * G16_WORDS;
+  g.k = threadIdx.x & 15u;
+  g.par = 0;
   ge_ext acc;
   ge_load_ext(acc, parts + (size_t)set * 32);
   for (int p = 1; p < nparts; p++) {
@@ -774,8 +794,11 @@ __global__ void k_sum_encode(const uint32_t* __restrict__ parts, int nparts, int
     ge_load_ext(o, parts + ((size_t)p * nsets + set) * 32);
     acc = ge_add(acc, o);
   }
-  if (out_ext) ge_store_ext(out_ext + (size_t)set * 32, acc);
-  if (out_bytes) ge_encode(out_bytes + (size_t)set * 32, acc);
+  if (out_ext && live && g.k == 0) ge_store_ext(out_ext + (size_t)set * 32, acc);
+  if (out_bytes) {
+    fe s = ge_encode16(g, acc);
+    if (live) store_s_bytes(out_bytes + (size_t)set * 32, s, g.k);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -991,9 +1014,24 @@ __global__ void __launch_bounds__(128) k_comb_mul_warp(const uint32_t* __restric
     }
     acc = ge_add(acc, o);
   }
-  if (live && lane == 0) {
-    if (out_ext) ge_store_ext(out_ext + (size_t)i * 32, acc);
-    if (out_bytes) ge_encode(out_bytes + (size_t)i * 32, acc);
+  if (live && lane == 0 && out_ext) ge_store_ext(out_ext + (size_t)i * 32, acc);
+  if (out_bytes) {
+    // the total sits in lane 0: hand it to every lane, encode on sixteen lanes (fe16.cuh; the
+    // upper half-warp shadows the lower one)
+    __shared__ __align__(16) uint32_t sm[(128 / 16) * G16_WORDS];
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      acc.X.v[w] = __shfl_sync(0xffffffffu, acc.X.v[w], 0);
+      acc.Y.v[w] = __shfl_sync(0xffffffffu, acc.Y.v[w], 0);
+      acc.Z.v[w] = __shfl_sync(0xffffffffu, acc.Z.v[w], 0);
+      acc.T.v[w] = __shfl_sync(0xffffffffu, acc.T.v[w], 0);
+    }
+    grp16 g;
+    g.sm = sm + (threadIdx.x >> 4) * G16_WORDS;
+    g.k = threadIdx.x & 15u;
+    g.par = 0;
+    fe s = ge_encode16(g, acc);
+    if (live && lane < 16) store_s_bytes(out_bytes + (size_t)i * 32, s, g.k);
   }
 }
 

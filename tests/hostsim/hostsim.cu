@@ -4,7 +4,11 @@
 // Nothing in the product loads this library.
 #include <vector>
 #include <cstring>
+#define BPG_HOSTSIM 1
+#include <thread>
+#include <pthread.h>
 #include "../../mpc_bulletproof_b200/csrc/ge.cuh"
+#include "../../mpc_bulletproof_b200/csrc/fe16.cuh"
 #include "../../mpc_bulletproof_b200/csrc/sc.cuh"
 #include "../../mpc_bulletproof_b200/csrc/stark_pt.cuh"
 #include "../../mpc_bulletproof_b200/csrc/stark_sc.cuh"
@@ -121,5 +125,69 @@ int hs_msm(const uint8_t* scalars, const uint8_t* points, int n, int c, int chun
   for (int w = W - 2; w >= 0; w--) { for (int i = 0; i < c; i++) acc = ge_dbl(acc); acc = ge_add(acc, wins[w]); }
   ge_encode(out, acc);
   return 0;
+}
+}  // extern "C"
+
+// ---- sixteen-lane field layer (fe16.cuh): one host thread per lane ----
+struct Team16 {
+  pthread_barrier_t bar;
+  uint32_t slots[16];
+  alignas(16) uint32_t sm[G16_WORDS];
+};
+template <class F>
+static void run16(F f) {
+  Team16 t;
+  pthread_barrier_init(&t.bar, nullptr, 16);
+  std::thread th[16];
+  for (uint32_t k = 0; k < 16; k++)
+    th[k] = std::thread([&t, &f, k] {
+      grp16 g;
+      g.sm = t.sm; g.k = k; g.par = 0; g.bar = &t.bar; g.slots = t.slots;
+      f(g);
+    });
+  for (auto& x : th) x.join();
+  pthread_barrier_destroy(&t.bar);
+}
+extern "C" {
+// op 0: a*b, 1: a+b, 2: a-b, 3: (a*b)^(2^n) by n squarings of the product; limbs = the raw lazy limbs
+void hs_fe16_op(const uint32_t* a, const uint32_t* b, int op, int n, uint32_t* o, uint32_t* limbs) {
+  fe A = ld(a), B = ld(b);
+  run16([&](grp16& g) {
+    fe16 x = fe16_from_fe(g, A), y = fe16_from_fe(g, B), r;
+    if (op == 0) r = fe16_mul(g, x, y);
+    else if (op == 1) r = fe16_add(g, x, y);
+    else if (op == 2) r = fe16_sub(g, x, y);
+    else { r = fe16_mul(g, x, y); for (int i = 0; i < n; i++) { r = fe16_sq(g, r); if (limbs[g.k] < r.l) limbs[g.k] = r.l; } }
+    if (op != 3) limbs[g.k] = r.l;
+    fe c = fe16_to_fe(g, r);
+    if (g.k == 5) st(o, c);
+  });
+}
+// ((a - b) * (a + b) - a)^2 with every intermediate lazy: exercises products of carried sums and differences
+void hs_fe16_mix(const uint32_t* a, const uint32_t* b, uint32_t* o) {
+  fe A = ld(a), B = ld(b);
+  run16([&](grp16& g) {
+    fe16 x = fe16_from_fe(g, A), y = fe16_from_fe(g, B);
+    fe16 m = fe16_mul(g, fe16_sub(g, x, y), fe16_add(g, x, y));
+    fe16 d = fe16_sub(g, m, x);
+    fe16 zero; zero.l = 0;
+    fe16 r = fe16_mul(g, fe16_sub(g, zero, d), fe16_sub(g, zero, d));
+    fe c = fe16_to_fe(g, r);
+    if (g.k == 0) st(o, c);
+  });
+}
+void hs_fe16_pow22523(const uint32_t* a, uint32_t* o) {
+  fe A = ld(a);
+  run16([&](grp16& g) {
+    fe c = fe16_to_fe(g, fe16_pow22523(g, fe16_from_fe(g, A)));
+    if (g.k == 15) st(o, c);
+  });
+}
+void hs_encode16(const uint32_t* ext, uint8_t* b) {
+  ge_ext e = lde(ext);
+  run16([&](grp16& g) {
+    fe s = ge_encode16(g, e);
+    if (g.k == 3) fe_to_bytes(b, s);
+  });
 }
 }

@@ -149,3 +149,52 @@ def test_pipeline_walkthrough(hs, n, c, chunk):
     pb = b"".join(p.encode() for p in ps)
     assert hs.hs_msm(sb, pb, n, c, chunk, o) == 0
     assert bytes(o) == G.msm_naive(ks, ps).encode()
+
+
+def test_field_on_sixteen_lanes(hs):
+    """fe16.cuh (the latency form of the field layer: radix 2^16, one limb per lane of a half-warp,
+    lazy carries) with one host thread per lane: products, carried sums and differences, the
+    steady-state limb bounds the header states, and the 252-squaring chain."""
+    U16 = ctypes.c_uint32 * 16
+    r = random.Random(16)
+    o = U32x8()
+    for _ in range(150):
+        a, b = rnd_fe(r) % 2**255, rnd_fe(r) % 2**255  # operands are tight, as everywhere on the device
+        limbs = U16()
+        hs.hs_fe16_op(tol(a), tol(b), 0, 0, o, limbs)
+        assert frl(o) == a * b % G.P
+        assert limbs[0] < 2**22 and all(limbs[k] < 2**18 for k in range(1, 16))
+        hs.hs_fe16_op(tol(a), tol(b), 1, 0, o, limbs)
+        assert frl(o) == (a + b) % G.P and all(limbs[k] < 2**17 for k in range(16))
+        hs.hs_fe16_op(tol(a), tol(b), 2, 0, o, limbs)
+        assert frl(o) == (a - b) % G.P and all(limbs[k] < 2**17 for k in range(16))
+        hs.hs_fe16_mix(tol(a), tol(b), o)
+        assert frl(o) == pow(((a - b) * (a + b) - a), 2, G.P)
+    for a, b in [(2**255 - 1, 2**255 - 1), (G.P - 1, G.P - 1), (0, 5), (1, 1), (2**255 - 1, 1)]:
+        limbs = U16()
+        hs.hs_fe16_op(tol(a), tol(b), 3, 40, o, limbs)  # 40 squarings of the product: bounds are a fixed point
+        assert frl(o) == pow(a * b, 2**40, G.P)
+        assert limbs[0] < 2**22 and all(limbs[k] < 2**18 for k in range(1, 16))
+    for a in [3, G.P - 2, r.getrandbits(255)]:
+        hs.hs_fe16_pow22523(tol(a), o)
+        assert frl(o) == pow(a, 2**252 - 3, G.P)
+
+
+def test_encode_on_sixteen_lanes(hs):
+    """ge_encode16 = ge_encode byte for byte: RFC 9496 multiples of the generator, random points in
+    random projective representations (both rotations, negative x / y), the identity and the other
+    points of its coset."""
+    from tests.test_oracle_group import MULTIPLES
+
+    r = random.Random(17)
+    pts = [k * G.BASEPOINT for k in range(16)] + [r.randrange(G.L) * G.BASEPOINT for _ in range(24)]
+    for i, p in enumerate(pts):
+        want = p.encode()
+        if i < 16:
+            assert want.hex() == MULTIPLES[i]
+        for _ in range(2):
+            e = _ext(r, p)
+            o, o1 = B32(), B32()
+            hs.hs_encode16(e, o)
+            hs.hs_encode(e, o1)
+            assert bytes(o) == want == bytes(o1)
