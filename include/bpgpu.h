@@ -338,6 +338,19 @@ void bpg_transcript_challenge_scalar(bpg_transcript* t, const char* label, uint8
 typedef struct bpg_gens bpg_gens;
 int bpg_gens_new(bpg_ctx* ctx, const uint8_t* G, const uint8_t* H, size_t capacity, const uint8_t B[32],
                  const uint8_t B_blinding[32], bpg_gens** out);
+/* Generator derivation on the device, ristretto255 instantiation.
+ * bpg_points_from_uniform: out[i] = element derivation (RFC 9496 4.3.4, dalek's from_uniform_bytes) of
+ *   the i-th 64-byte block: the per-point work of GeneratorsChain::next (reference src/generators.rs:107-125).
+ * bpg_gens_chain: points [skip, skip+n) of the chain SHAKE256("GeneratorsChain" || label) -- the XOF is
+ *   squeezed on the host, `skip` is GeneratorsChain::fast_forward (src/generators.rs:80-100).
+ * bpg_gens_derive: BulletproofGens::new(gens_capacity, ..).share(party) (src/generators.rs:182-235, labels
+ *   "G"/"H" || u32le(party)) + PedersenGens::default() (src/generators.rs:61-71: B = basepoint,
+ *   B_blinding = hash-to-group(SHA3-512(B))), resident as bpg_gens_new leaves them; the compressed
+ *   generators are also returned where the pointers are not NULL. */
+int bpg_points_from_uniform(bpg_ctx* ctx, const uint8_t* uniform64 /* n*64 */, size_t n, uint8_t* out_compressed /* n*32 */);
+int bpg_gens_chain(bpg_ctx* ctx, const uint8_t* label, size_t label_len, size_t skip, size_t n, uint8_t* out /* n*32 */);
+int bpg_gens_derive(bpg_ctx* ctx, size_t gens_capacity, uint32_t party, uint8_t* G_out, uint8_t* H_out,
+                    uint8_t B_out[32], uint8_t Bb_out[32], bpg_gens** out);
 void bpg_gens_free(bpg_gens* g);
 size_t bpg_gens_capacity(const bpg_gens* g);
 const bpg_table* bpg_gens_table(const bpg_gens* g);

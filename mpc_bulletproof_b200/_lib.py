@@ -47,6 +47,9 @@ _SIGNATURES = {
     "bpg_transcript_challenge_bytes": (None, [_P, _CP, _P, _SZ]),
     "bpg_transcript_challenge_scalar": (None, [_P, _CP, _P]),
     "bpg_gens_new": (_I, [_P, _P, _P, _SZ, _P, _P, ctypes.POINTER(_P)]),
+    "bpg_points_from_uniform": (_I, [_P, _P, _SZ, _P]),
+    "bpg_gens_chain": (_I, [_P, _P, _SZ, _SZ, _SZ, _P]),
+    "bpg_gens_derive": (_I, [_P, _SZ, ctypes.c_uint32, _P, _P, _P, _P, ctypes.POINTER(_P)]),
     "bpg_gens_free": (None, [_P]),
     "bpg_gens_capacity": (_SZ, [_P]),
     "bpg_gens_table": (_P, [_P]),

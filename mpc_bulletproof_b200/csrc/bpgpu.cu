@@ -1059,6 +1059,23 @@ extern "C" int bpg_comb_mul(bpg_ctx* ctx, const bpg_comb* comb, const uint8_t* s
   return BPG_OK;
 }
 
+// Element derivation for generator chains: out[i] = from_uniform_bytes(uniform[64 i .. 64 i + 64)).
+extern "C" int bpg_points_from_uniform(bpg_ctx* ctx, const uint8_t* uniform64, size_t n, uint8_t* out_compressed) {
+  if (!ctx || (n && (!uniform64 || !out_compressed))) return BPG_ERR_ARG;
+  if (n == 0) return BPG_OK;
+  if (n >= (1ull << 31)) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_stage(ctx, n * 96);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->d_stage, uniform64, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  uint8_t* d_out = ctx->d_stage + n * 64;
+  k_from_uniform<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_stage, (uint32_t)n, d_out);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(out_compressed, d_out, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BPG_OK;
+}
+
 // ---------------------------------------------------------------------------
 // windowed tables
 // ---------------------------------------------------------------------------

@@ -30,6 +30,14 @@ BPG_DEF_CONST(K_SQRT_M1, 0x4a0ea0b0u, 0xc4ee1b27u, 0xad2fe478u, 0x2f431806u, 0x3
 BPG_DEF_CONST(K_INVSQRT_A_MINUS_D, 0x805d40eau, 0x99c8fdaau, 0x5a4172beu, 0x9d2f1617u, 0xfe01d840u,
               0x16c27b91u, 0xcfaffca2u, 0x786c8905u)
 
+// RFC 9496 §4.1 constants of the Elligator map (element derivation, §4.3.4)
+BPG_DEF_CONST(K_ONE_MINUS_D_SQ, 0x945fc176u, 0xe27c09c1u, 0xcd5e350fu, 0x2c81a138u, 0xbe70dfe4u, 0x9994abddu,
+              0xb2b3e0d7u, 0x029072a8u)
+BPG_DEF_CONST(K_D_MINUS_ONE_SQ, 0x44ed4d20u, 0x31ad5aaau, 0xb01e1999u, 0xd29e4a2cu, 0x529b4eebu, 0x4cdcd32fu,
+              0xf66c2241u, 0x5968b37au)
+BPG_DEF_CONST(K_SQRT_AD_MINUS_ONE, 0x497b2e1bu, 0x7e97f6a0u, 0x1b7854bdu, 0xaf9d8e0cu, 0x31f5d1fdu, 0x0f3cfcc9u,
+              0x2b8348acu, 0x376931bfu)
+
 BPG_DI fe fe_const(const uint32_t* k) {
   fe o;
 #pragma unroll
@@ -251,6 +259,49 @@ BPG_DI bool ge_decode(ge_ext& r, const uint8_t in[32]) {
   r.Z = one;
   r.T = t;
   return ok;
+}
+
+// RFC 9496 §4.3.4 MAP (Elligator 2): field element -> point of the prime-order group.
+BPG_DI ge_ext ge_elligator_map(const fe& t) {
+  fe one = fe_one();
+  fe d = fe_const(BPG_K(K_D));
+  fe r = fe_mul(fe_const(BPG_K(K_SQRT_M1)), fe_sq(t));
+  fe u = fe_mul(fe_add(r, one), fe_const(BPG_K(K_ONE_MINUS_D_SQ)));
+  fe v = fe_mul(fe_sub(fe_neg(one), fe_mul(r, d)), fe_add(r, d));
+  fe s;
+  bool was_square = fe_sqrt_ratio_m1(s, u, v);
+  fe s_prime = fe_neg(fe_abs(fe_mul(s, t)));
+  fe c = fe_neg(one);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    s.v[k] = was_square ? s.v[k] : s_prime.v[k];
+    c.v[k] = was_square ? c.v[k] : r.v[k];
+  }
+  fe N = fe_sub(fe_mul(fe_mul(c, fe_sub(r, one)), fe_const(BPG_K(K_D_MINUS_ONE_SQ))), v);
+  fe ss = fe_sq(s);
+  fe w0 = fe_mul(fe_add(s, s), v);
+  fe w1 = fe_mul(N, fe_const(BPG_K(K_SQRT_AD_MINUS_ONE)));
+  fe w2 = fe_sub(one, ss);
+  fe w3 = fe_add(one, ss);
+  ge_ext q;
+  q.X = fe_mul(w0, w3);
+  q.Y = fe_mul(w2, w1);
+  q.Z = fe_mul(w1, w3);
+  q.T = fe_mul(w0, w2);
+  return q;
+}
+
+// RFC 9496 §4.3.4 element derivation: 64 uniform bytes -> MAP(lo mod 2^255) + MAP(hi mod 2^255)
+// (what dalek's RistrettoPoint::from_uniform_bytes computes for the generator chains,
+// reference src/generators.rs:107-125 in its ristretto255 form).
+BPG_DI fe fe_from_bytes_255(const uint8_t in[32]) {
+  fe t;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    t.v[i] = (uint32_t)in[4 * i] | ((uint32_t)in[4 * i + 1] << 8) | ((uint32_t)in[4 * i + 2] << 16) |
+             ((uint32_t)in[4 * i + 3] << 24);
+  t.v[7] &= 0x7fffffffu;
+  return t;
 }
 
 BPG_DI void ge_store_niels(uint32_t* p, const ge_niels& q) {

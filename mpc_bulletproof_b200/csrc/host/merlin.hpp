@@ -36,6 +36,48 @@ inline void keccak_f1600(uint64_t st[25]) {
   }
 }
 
+// Keccak sponge for the generator chains (reference src/generators.rs:80-125 in its ristretto255
+// form: SHAKE256("GeneratorsChain" || label) as an XOF, 64 bytes per point) and for
+// PedersenGens::default's B_blinding = hash-to-group(SHA3-512(B)) (src/generators.rs:61-71).
+class KeccakSponge {
+ public:
+  KeccakSponge(size_t rate, uint8_t suffix) : rate_(rate), suffix_(suffix), pos_(0), squeezing_(false) { memset(st_, 0, sizeof st_); }
+  void absorb(const uint8_t* d, size_t n) {
+    uint8_t* s = reinterpret_cast<uint8_t*>(st_);
+    for (size_t i = 0; i < n; i++) {
+      s[pos_++] ^= d[i];
+      if (pos_ == rate_) { keccak_f1600(st_); pos_ = 0; }
+    }
+  }
+  void squeeze(uint8_t* out, size_t n) {
+    uint8_t* s = reinterpret_cast<uint8_t*>(st_);
+    if (!squeezing_) {
+      s[pos_] ^= suffix_;
+      s[rate_ - 1] ^= 0x80;
+      keccak_f1600(st_);
+      pos_ = 0;
+      squeezing_ = true;
+    }
+    for (size_t i = 0; i < n; i++) {
+      if (pos_ == rate_) { keccak_f1600(st_); pos_ = 0; }
+      out[i] = s[pos_++];
+    }
+  }
+
+ private:
+  uint64_t st_[25];
+  size_t rate_;
+  uint8_t suffix_;
+  size_t pos_;
+  bool squeezing_;
+};
+inline KeccakSponge shake256() { return KeccakSponge(136, 0x1f); }
+inline void sha3_512(const uint8_t* d, size_t n, uint8_t out[64]) {
+  KeccakSponge k(72, 0x06);
+  k.absorb(d, n);
+  k.squeeze(out, 64);
+}
+
 class Strobe128 {
  public:
   explicit Strobe128(const char* protocol_label) {

@@ -150,6 +150,45 @@ extern "C" int bpg_gens_new(bpg_ctx* ctx, const uint8_t* G, const uint8_t* H, si
   *out = g;
   return BPG_OK;
 }
+// BulletproofGens::new(gens_capacity, ..) for one party (reference src/generators.rs:182-235) together
+// with PedersenGens::default (src/generators.rs:61-71), ristretto255 instantiation: the chains
+// "G" || u32le(party) and "H" || u32le(party) are squeezed here (a sequential XOF), the points are derived
+// on the device (k_from_uniform), then the table is built as in bpg_gens_new.  G_out / H_out (capacity*32
+// bytes each, may be NULL) and B_out / Bb_out (32 bytes, may be NULL) receive the compressed generators.
+static const uint8_t RISTRETTO_BASEPOINT_COMPRESSED[32] = {
+    0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0xbc, 0x4e, 0x71, 0xa8, 0x84, 0xa9, 0x61, 0xc5, 0x00, 0x51, 0x5f,
+    0x58, 0xe3, 0x0b, 0x6a, 0xa5, 0x82, 0xdd, 0x8d, 0xb6, 0xa6, 0x59, 0x45, 0xe0, 0x8d, 0x2d, 0x76};
+extern "C" int bpg_gens_chain(bpg_ctx* ctx, const uint8_t* label, size_t label_len, size_t skip, size_t n, uint8_t* out) {
+  if (!ctx || (n && !out) || (label_len && !label)) return BPG_ERR_ARG;
+  bpg_host::KeccakSponge xof = bpg_host::shake256();
+  xof.absorb((const uint8_t*)"GeneratorsChain", 15);
+  xof.absorb(label, label_len);
+  uint8_t discard[64];
+  for (size_t i = 0; i < skip; i++) xof.squeeze(discard, 64);  // fast_forward (src/generators.rs:92-100)
+  std::vector<uint8_t> stream(n * 64);
+  xof.squeeze(stream.data(), n * 64);
+  return bpg_points_from_uniform(ctx, stream.data(), n, out);
+}
+extern "C" int bpg_gens_derive(bpg_ctx* ctx, size_t gens_capacity, uint32_t party, uint8_t* G_out, uint8_t* H_out,
+                               uint8_t* B_out, uint8_t* Bb_out, bpg_gens** out) {
+  if (!ctx || !out) return BPG_ERR_ARG;
+  std::vector<uint8_t> G(gens_capacity * 32), H(gens_capacity * 32);
+  uint8_t label[5] = {'G', (uint8_t)party, (uint8_t)(party >> 8), (uint8_t)(party >> 16), (uint8_t)(party >> 24)};
+  int rc = bpg_gens_chain(ctx, label, 5, 0, gens_capacity, G.data());
+  if (rc) return rc;
+  label[0] = 'H';
+  rc = bpg_gens_chain(ctx, label, 5, 0, gens_capacity, H.data());
+  if (rc) return rc;
+  uint8_t digest[64], Bb[32];
+  bpg_host::sha3_512(RISTRETTO_BASEPOINT_COMPRESSED, 32, digest);
+  rc = bpg_points_from_uniform(ctx, digest, 1, Bb);
+  if (rc) return rc;
+  if (G_out) memcpy(G_out, G.data(), G.size());
+  if (H_out) memcpy(H_out, H.data(), H.size());
+  if (B_out) memcpy(B_out, RISTRETTO_BASEPOINT_COMPRESSED, 32);
+  if (Bb_out) memcpy(Bb_out, Bb, 32);
+  return bpg_gens_new(ctx, G.data(), H.data(), gens_capacity, RISTRETTO_BASEPOINT_COMPRESSED, Bb, out);
+}
 extern "C" void bpg_gens_free(bpg_gens* g) {
   if (!g) return;
   bpg_table_free(g->table);

@@ -1036,6 +1036,22 @@ __global__ void __launch_bounds__(128) k_comb_mul_warp(const uint32_t* __restric
 }
 
 // ---------------------------------------------------------------------------
+// Generator chains (reference src/generators.rs:107-125, 210-235): point i of a
+// chain = element derivation (RFC 9496 §4.3.4) of the i-th 64-byte block of the chain's XOF
+// stream.  The stream is squeezed on the host (sequential, ~1 GB/s); the two Elligator maps, the
+// addition and the encoding (three inverse-square-root chains, ~900 field products per point)
+// run here, one thread per point.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_from_uniform(const uint8_t* __restrict__ in /*n*64*/, uint32_t n,
+                                                       uint8_t* __restrict__ out /*n*32*/) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ge_ext p = ge_add(ge_elligator_map(fe_from_bytes_255(in + (size_t)i * 64)),
+                    ge_elligator_map(fe_from_bytes_255(in + (size_t)i * 64 + 32)));
+  ge_encode(out + (size_t)i * 32, p);
+}
+
+// ---------------------------------------------------------------------------
 // windowed tables: out[w][i] = 2^(c w) * P_i in affine Niels, w < W.
 // One thread per point walks the doubling chain, parks the extended multiples and
 // the running product of their Z in scratch, inverts once (Montgomery's trick) and

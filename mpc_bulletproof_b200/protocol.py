@@ -105,6 +105,24 @@ class Gens:
         _raise(lib().bpg_gens_new(ctx._h, G, H, self.gens_capacity, B, B_blinding, ctypes.byref(self._h)))
         ctx._children.add(self)
 
+    @classmethod
+    def derive(cls, ctx: Context, gens_capacity: int, party: int = 0) -> "Gens":
+        """BulletproofGens::new(gens_capacity, ..).share(party) + PedersenGens::default()
+        (reference src/generators.rs:61-71, 182-235), derived on the device; `.G`, `.H` hold the
+        compressed generators."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.gens_capacity = gens_capacity
+        G = ctypes.create_string_buffer(32 * max(gens_capacity, 1))
+        H = ctypes.create_string_buffer(32 * max(gens_capacity, 1))
+        B, Bb = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+        self._h = ctypes.c_void_p()
+        _raise(lib().bpg_gens_derive(ctx._h, gens_capacity, party, G, H, B, Bb, ctypes.byref(self._h)))
+        self.G, self.H = G.raw[: 32 * gens_capacity], H.raw[: 32 * gens_capacity]
+        self.B, self.B_blinding = B.raw, Bb.raw
+        ctx._children.add(self)
+        return self
+
     def close(self):
         if self._h:
             lib().bpg_gens_free(self._h)
@@ -370,3 +388,18 @@ def batch_verify(jobs) -> list[bool]:
         v._reraise()
     _raise(code)
     return [b != 0 for b in ok.raw]
+
+
+def points_from_uniform(ctx: Context, uniform: bytes) -> bytes:
+    """from_uniform_bytes of every 64-byte block (RFC 9496 4.3.4), on the device."""
+    n = len(uniform) // 64
+    out = ctypes.create_string_buffer(32 * max(n, 1))
+    _raise(lib().bpg_points_from_uniform(ctx._h, uniform, n, out))
+    return out.raw[: 32 * n]
+
+
+def gens_chain(ctx: Context, label: bytes, skip: int, n: int) -> bytes:
+    """Points [skip, skip+n) of GeneratorsChain::new(label) (reference src/generators.rs:80-125)."""
+    out = ctypes.create_string_buffer(32 * max(n, 1))
+    _raise(lib().bpg_gens_chain(ctx._h, label, len(label), skip, n, out))
+    return out.raw[: 32 * n]

@@ -72,6 +72,9 @@ extern "C" {
     pub fn bpg_table_set_windows(ctx: *mut bpg_ctx, t: *mut bpg_table, c: c_int) -> c_int;
     pub fn bpg_table_len(t: *const bpg_table) -> usize;
     pub fn bpg_table_free(t: *mut bpg_table);
+    // generator derivation on the device (GeneratorsChain, src/generators.rs:80-125, ristretto255 form)
+    pub fn bpg_points_from_uniform(ctx: *mut bpg_ctx, uniform64: *const u8, n: usize, out: *mut u8) -> c_int;
+    pub fn bpg_gens_chain(ctx: *mut bpg_ctx, label: *const u8, label_len: usize, skip: usize, n: usize, out: *mut u8) -> c_int;
 
     // ---- StarkPoint::msm_iter / ::msm (all call sites of SURVEY.md 2.2) ---------------
     pub fn bpg_msm(ctx: *mut bpg_ctx, scalars: *const u8, points: *const u8, n: usize, out: *mut u8) -> c_int;

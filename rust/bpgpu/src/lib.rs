@@ -53,6 +53,12 @@ pub trait PointBytes: Sized {
     fn from_compressed(bytes: &[u8; 32]) -> Option<Self>;
 }
 
+/// Raw encodings are points too (generators that were derived on the device never leave byte form).
+impl PointBytes for [u8; 32] {
+    fn to_compressed(&self) -> [u8; 32] { *self }
+    fn from_compressed(bytes: &[u8; 32]) -> Option<Self> { Some(*bytes) }
+}
+
 /// One GPU, one proving thread (`&mut Transcript` exclusivity, src/r1cs/prover.rs:27-28).
 pub struct Context {
     raw: *mut sys::bpg_ctx,
@@ -135,6 +141,20 @@ impl<'c> GpuGens<'c> {
         let bases = &all[2 * cap * 32..];
         check(unsafe { sys::bpg_comb_create(ctx.raw, bases.as_ptr(), 2, &mut gens.comb) })?;
         Ok(gens)
+    }
+    /// `BulletproofGens::new(capacity, ..).share(party)` + `PedersenGens::default()` with the chains
+    /// derived on the device (src/generators.rs:61-71, 80-125, 182-235): labels "G"/"H" || u32le(party).
+    /// Returns the resident generators and the compressed (G, H) for the host-side structs.
+    pub fn derive(ctx: &'c Context, capacity: usize, party: u32, b: &[u8; 32], b_blinding: &[u8; 32]) -> Result<(Self, Vec<[u8; 32]>, Vec<[u8; 32]>), Error> {
+        let mut g = vec![[0u8; 32]; capacity];
+        let mut h = vec![[0u8; 32]; capacity];
+        for (tag, out) in [(b'G', &mut g), (b'H', &mut h)] {
+            let mut label = vec![tag];
+            label.extend_from_slice(&party.to_le_bytes());
+            check(unsafe { sys::bpg_gens_chain(ctx.raw, label.as_ptr(), label.len(), 0, capacity, out.as_mut_ptr() as *mut u8) })?;
+        }
+        let gens = Self::new(ctx, &g, &h, b, b_blinding)?;
+        Ok((gens, g, h))
     }
     pub fn g_base(&self) -> usize { 0 }
     pub fn h_base(&self) -> usize { self.capacity }

@@ -183,6 +183,10 @@ void hs_fe16_pow22523(const uint32_t* a, uint32_t* o) {
     if (g.k == 15) st(o, c);
   });
 }
+void hs_from_uniform(const uint8_t* in64, uint8_t* out32) {
+  ge_ext p = ge_add(ge_elligator_map(fe_from_bytes_255(in64)), ge_elligator_map(fe_from_bytes_255(in64 + 32)));
+  ge_encode(out32, p);
+}
 void hs_encode16(const uint32_t* ext, uint8_t* b) {
   ge_ext e = lde(ext);
   run16([&](grp16& g) {

@@ -198,3 +198,18 @@ def test_encode_on_sixteen_lanes(hs):
             hs.hs_encode16(e, o)
             hs.hs_encode(e, o1)
             assert bytes(o) == want == bytes(o1)
+
+
+def test_element_derivation(hs):
+    """ge_elligator_map / from_uniform_bytes (generator chains, reference src/generators.rs:107-125)
+    against the oracle, which RFC 9496 A.3's hash-to-group vectors pin (tests/test_oracle_group.py)."""
+    import hashlib
+
+    r = random.Random(18)
+    blocks = [bytes(64), b"\xff" * 64, hashlib.sha512(b"Ristretto is traditionally a short shot of espresso coffee").digest()]
+    blocks += [r.randbytes(64) for _ in range(40)]
+    for b in blocks:
+        o = B32()
+        hs.hs_from_uniform((ctypes.c_uint8 * 64)(*b), o)
+        assert bytes(o) == G.from_uniform_bytes(b).encode()
+    assert bytes(o) != bytes(32)

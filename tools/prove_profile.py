@@ -15,16 +15,29 @@ from mpc_bulletproof_b200 import protocol as P  # noqa: E402
 def main():
     lg = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    table_c = int(sys.argv[3]) if len(sys.argv) > 3 else 0  # window width of the generator table (0: the library picks)
     n = 1 << lg
     ctx = Context(0)
+    ctx.set_window(table_c)
     comb = Comb(ctx, BASE)
     gens = P.Gens(ctx, synth_points(ctx, comb, n, 1), synth_points(ctx, comb, n, 2), BASE, synth_points(ctx, comb, 1, 4))
+
+    ctx.set_window(0)
 
     def build(cs, val):
         cs.square_chain(cs.commit_public(val), n)
 
     val = rand_scalars(1, 99)[0]
-    out = {"lg": lg, "runs": []}
+    out = {"lg": lg, "table_c": gens.table.window, "leaf": os.environ.get("BPG_LEAF", ""), "runs": []}
+    # unprofiled wall-clock first (the profile's events serialise the auxiliary stream)
+    walls = []
+    for it in range(6):
+        p = P.Prover(gens, P.Transcript(b"bench r1cs"))
+        build(p, val)
+        t0 = time.perf_counter()
+        p.prove(99 + it)
+        walls.append((time.perf_counter() - t0) * 1e3)
+    out["prove_ms_unprofiled"] = sorted(walls[1:])
     for it in range(reps):
         p = P.Prover(gens, P.Transcript(b"bench r1cs"))
         build(p, val)
