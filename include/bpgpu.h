@@ -268,7 +268,9 @@ int bpg_r1cs_dev_poly_t(bpg_r1cs_dev* st, size_t n, const void* y_pow, const voi
 /* The verifier's mega-MSM (verifier.rs:516-547) with g_scalars, h_scalars and delta computed on
  * the device from the resident weights.  Terms: [adhoc points | B | B_blinding | G[0..N) | H[0..N)];
  * the caller supplies the adhoc scalars and the B_blinding scalar (canonical bytes).
- * out = compressed sum; accept iff it is the identity (32 zero bytes). */
+ * out = 32 zero bytes iff the sum is the identity (verifier.rs:549; tested projectively, X = 0 or Y = 0,
+ * so no encoding and no inversion); anything else means reject.  When the generators are not one
+ * windowed table the general path returns the compressed sum, to be compared with 32 zero bytes as well. */
 int bpg_r1cs_dev_verify_msm(bpg_r1cs_dev* st, const bpg_table* gens, size_t g_base, size_t h_base, size_t b_id,
                             const uint8_t* adhoc_points, const uint8_t* adhoc_scalars, size_t n_adhoc,
                             const uint8_t bb_scalar[32], const bpg_verify_params* params, uint8_t out[32]);

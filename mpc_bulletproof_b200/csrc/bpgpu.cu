@@ -47,6 +47,7 @@ struct bpg_ctx {
   size_t ws_aux_cap = 0;
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_chunk[8] = {};  // scalar upload in pieces (host_feed), created on first use
   // transient-allocation cache (dev_alloc / dev_free)
   std::vector<std::pair<void*, size_t>> cache;
   std::unordered_map<void*, size_t> live;
@@ -179,6 +180,8 @@ extern "C" void bpg_free(bpg_ctx* ctx) {
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws_aux) cudaFree(ctx->ws_aux);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (auto& e : ctx->ev_chunk)
+    if (e) cudaEventDestroy(e);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->d_small) cudaFree(ctx->d_small);
@@ -523,7 +526,8 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 // be null (implicit: term t -> point t % n_points of `table_base`, set t / n_points).
 static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points, const uint32_t* d_scalars,
                        size_t n_terms, const uint8_t* d_set_ids, const uint32_t* d_point_ids, int nsets,
-                       uint32_t* d_out_ext, int win_c = 0, size_t win_stride = 0, int lane = 0, int curve = 0) {
+                       uint32_t* d_out_ext, int win_c = 0, size_t win_stride = 0, int lane = 0, int curve = 0,
+                       const uint8_t* h_scalars = nullptr /*scalars still on the host: uploaded here, in pieces*/) {
   // curve 0: ristretto255 (Niels table, 24 words per entry); curve 1: Stark curve (affine table, 16 words
   // per entry, plain tables only).  Sort and schedule are shared; the bucket arithmetic differs.
   if (nsets <= 0) return BPG_ERR_ARG;
@@ -553,24 +557,19 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   // reduction geometry: `rarr` arrays of nb buckets.  Small arrays: a leaf block of RT_QUADS quad
   // chunks of LC buckets plus its in-block tree; large arrays: one thread per chunk of 16.
   uint32_t rarr = windowed ? (uint32_t)nsets : cfg.narr;
-  bool thread_leaf = cfg.nb >= (1u << 17);
-  uint32_t LC = thread_leaf ? 16 : (cfg.nb > (1u << 15) ? 8 : 4);
-  {
-    // tuning experiment: BPG_LEAF=t4|t8|t16|q4|q8 overrides the leaf geometry
-    static const char* leaf_env = getenv("BPG_LEAF");
-    if (leaf_env && (leaf_env[0] == 't' || leaf_env[0] == 'q') && curve == 0) {
-      int v = atoi(leaf_env + 1);
-      if (leaf_env[0] == 't' && (v == 4 || v == 8 || v == 16)) { thread_leaf = true; LC = (uint32_t)v; }
-      if (leaf_env[0] == 'q' && (v == 4 || v == 8)) { thread_leaf = false; LC = (uint32_t)v; }
-    }
-  }
+  // (measured at 2 x 2^16 buckets, an IPP round at n = 2^16: quad chunks of 8 and thread chunks of 4 tie,
+  // thread chunks of 8 / 16 and quad chunks of 4 are 2-11 % of a proof slower; gpurun_out/r1i_tune.jsonl)
+  const bool thread_leaf = cfg.nb >= (1u << 17);
+  const uint32_t LC = thread_leaf ? 16 : (cfg.nb > (1u << 15) ? 8 : 4);
   uint32_t tiles0 = thread_leaf ? (cfg.nb + LC - 1) / LC : (cfg.nb + RT_QUADS * LC - 1) / (RT_QUADS * LC);
   size_t ntiles = (cfg.B + SCAN_TILE - 1) / SCAN_TILE;
   size_t off = 0;
+  // counts and the schedule's control words are adjacent: ONE memset per launch
   size_t o_counts = off;  off += align_up((size_t)cfg.B * 4);
+  size_t o_bins = off;    off += align_up((2 * SIZE_BINS + 4) * 4);  // bins | n_items, part, multi, big_count | cursors
   size_t o_offsets = off; off += align_up(((size_t)cfg.B + 1) * 4);
   size_t o_tiles = off;   off += align_up(ntiles * 4);
-  size_t o_big = off;     off += align_up((3 * (size_t)cfg.big_cap + 1) * 4);
+  size_t o_big = off;     off += align_up(3 * (size_t)cfg.big_cap * 4);
   size_t o_bigpart = off; off += align_up((size_t)cfg.big_cap * 128);
   size_t o_entries = off; off += align_up((size_t)n_terms * cfg.W * 4);
   size_t o_buckets = off; off += align_up((size_t)cfg.B * 128);
@@ -588,14 +587,12 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   size_t o_segslot = off; off += align_up((size_t)cfg.B * 4);
   size_t o_multi = off;   off += align_up(max_multi * 4);
   size_t o_segpart = off; off += align_up(2 * max_multi * 128);  // sum of nseg over multi-segment buckets <= 2 max_multi
-  size_t o_bins = off;    off += align_up((SIZE_BINS + 4) * 4);
   int rc = ensure_ws(ctx, off, lane);
   if (rc) return rc;
   uint32_t* counts = (uint32_t*)(ws + o_counts);
   uint32_t* offsets = (uint32_t*)(ws + o_offsets);
   uint32_t* tiles = (uint32_t*)(ws + o_tiles);
-  uint32_t* big_count = (uint32_t*)(ws + o_big);
-  uint32_t* big_list = big_count + 1;
+  uint32_t* big_list = (uint32_t*)(ws + o_big);
   uint32_t* big_part = (uint32_t*)(ws + o_bigpart);
   uint32_t* entries = (uint32_t*)(ws + o_entries);
   uint32_t* buckets = (uint32_t*)(ws + o_buckets);
@@ -605,7 +602,9 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   uint32_t* wins = (uint32_t*)(ws + o_wins);
   uint32_t* bins = (uint32_t*)(ws + o_bins);
   AccSched sched;
+  uint32_t* big_count = bins + SIZE_BINS + 3;
   sched.bins = bins;
+  sched.cursors = bins + SIZE_BINS + 4;
   sched.n_items = bins + SIZE_BINS;
   sched.part_count = bins + SIZE_BINS + 1;
   sched.multi_count = bins + SIZE_BINS + 2;
@@ -615,27 +614,44 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
   uint32_t* seg_part = (uint32_t*)(ws + o_segpart);
 
   prof_mark(ctx, BPG_PROF_HIST);
-  CK(cudaMemsetAsync(counts, 0, (size_t)cfg.B * 4, st));
-  CK(cudaMemsetAsync(big_count, 0, 4, st));
+  CK(cudaMemsetAsync(counts, 0, o_bins - o_counts + (2 * SIZE_BINS + 4) * 4, st));
   unsigned gt = (unsigned)((n_terms + 255) / 256);
-  k_hist<<<gt, 256, 0, st>>>(d_scalars, d_set_ids, cfg, counts);
-  LAUNCH_CHECK();
+  if (h_scalars && lane == 0 && n_terms >= (1u << 18)) {
+    // Host scalars: the copy runs on the auxiliary stream in pieces and the digit histogram of
+    // piece i runs while piece i+1 is still on the bus (hides the 0.12 ms histogram of a 2^20-term
+    // launch; measured against one copy on two boxes: 2.26-2.45 vs 2.39-2.62 ms end to end, the
+    // spread being the PCIe rate of the box).
+    const int pieces = 4;
+    size_t per = (((n_terms + pieces - 1) / pieces) + 255) / 256 * 256;
+    CK(cudaEventRecord(ctx->ev_fork, st));  // d_scalars (staging) is free once earlier work is done
+    CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    for (int i = 0; i < pieces; i++) {
+      size_t t0 = (size_t)i * per, t1 = std::min(n_terms, t0 + per);
+      if (t0 >= t1) break;
+      if (!ctx->ev_chunk[i]) CK(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+      CK(cudaMemcpyAsync((uint8_t*)d_scalars + t0 * 32, h_scalars + t0 * 32, (t1 - t0) * 32, cudaMemcpyHostToDevice,
+                         ctx->aux_stream));
+      CK(cudaEventRecord(ctx->ev_chunk[i], ctx->aux_stream));
+      CK(cudaStreamWaitEvent(st, ctx->ev_chunk[i], 0));
+      k_hist<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, st>>>(d_scalars, d_set_ids, cfg, counts, (uint32_t)t0, (uint32_t)t1);
+      LAUNCH_CHECK();
+    }
+  } else {
+    if (h_scalars) CK(cudaMemcpyAsync((void*)d_scalars, h_scalars, n_terms * 32, cudaMemcpyHostToDevice, st));
+    k_hist<<<gt, 256, 0, st>>>(d_scalars, d_set_ids, cfg, counts, 0u, (uint32_t)n_terms);
+    LAUNCH_CHECK();
+  }
   prof_mark(ctx, BPG_PROF_SCAN);
   k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.B, tiles);
   LAUNCH_CHECK();
   k_scan_spine<<<1, 1024, 0, st>>>(tiles, (uint32_t)ntiles, offsets, cfg.B);
   LAUNCH_CHECK();
-  k_scan_apply<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.B, tiles, offsets);
+  k_scan_apply<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.B, tiles, offsets, bins);
   LAUNCH_CHECK();
   prof_mark(ctx, BPG_PROF_SCATTER);
   k_scatter<<<gt, 256, 0, st>>>(d_scalars, d_set_ids, d_point_ids, cfg, offsets, counts, entries);
   LAUNCH_CHECK();
   // accumulation schedule: (bucket, segment) items by decreasing length; over-long buckets -> big list
-  CK(cudaMemsetAsync(bins, 0, (SIZE_BINS + 4) * 4, st));
-  k_size_hist<<<std::min<unsigned>((cfg.B + 255) / 256, (unsigned)ctx->sm_count * 4), 256, 0, st>>>(offsets, cfg.B, bins);
-  LAUNCH_CHECK();
-  k_size_scan<<<1, SIZE_BINS, 0, st>>>(bins, sched.n_items);
-  LAUNCH_CHECK();
   k_size_scatter<<<(cfg.B + 255) / 256, 256, 0, st>>>(offsets, cfg, sched, big_count, big_list);
   LAUNCH_CHECK();
   if (curve == 1) {
@@ -720,15 +736,9 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
     uint32_t* pa[2] = {pairs, pairs + 2 * pair_words};
     int cur = 0;
     uint32_t* oa = t == 1 ? final_out : pa[cur];
-    if (thread_leaf && LC == 16) {
+    if (thread_leaf) {
       k_reduce_leaf_thread<16><<<(rarr * t + RL_THREADS - 1) / RL_THREADS, RL_THREADS, 0, st>>>(level0, cfg.nb, t, rarr, oa,
                                                                                                pa[cur] + pair_words);
-    } else if (thread_leaf && LC == 8) {
-      k_reduce_leaf_thread<8><<<(rarr * t + RL_THREADS - 1) / RL_THREADS, RL_THREADS, 0, st>>>(level0, cfg.nb, t, rarr, oa,
-                                                                                              pa[cur] + pair_words);
-    } else if (thread_leaf) {
-      k_reduce_leaf_thread<4><<<(rarr * t + RL_THREADS - 1) / RL_THREADS, RL_THREADS, 0, st>>>(level0, cfg.nb, t, rarr, oa,
-                                                                                              pa[cur] + pair_words);
     } else if (LC == 8) {
       k_reduce_leaf<8><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
     } else {
@@ -890,11 +900,10 @@ extern "C" int bpg_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t offset
   size_t sbytes = n * (size_t)n_sets * 32;
   int rc = ensure_stage(ctx, std::max<size_t>(sbytes, 32));
   if (rc) return rc;
-  if (sbytes) CK(cudaMemcpyAsync(ctx->d_stage, scalars_le, sbytes, cudaMemcpyHostToDevice, ctx->stream));
   uint32_t* d_ext = (uint32_t*)ctx->d_small;
   uint8_t* d_bytes = ctx->d_small + (size_t)n_sets * 128;
   rc = msm_enqueue(ctx, table->niels + offset * 24, n, (const uint32_t*)ctx->d_stage, n * (size_t)n_sets, nullptr,
-                   nullptr, n_sets, d_ext, table->win_c, table->n);
+                   nullptr, n_sets, d_ext, table->win_c, table->n, 0, 0, sbytes ? scalars_le : nullptr);
   if (rc) return rc;
   rc = bpg_dev_sum_encode(ctx, d_ext, 1, n_sets, d_bytes, nullptr);
   if (rc) return rc;
@@ -1454,7 +1463,7 @@ extern "C" int bpg_msm_table_indexed(bpg_ctx* ctx, const bpg_table* table, const
 // core of the mixed MSM: scalars for all `total` terms are already in d_scalars (device)
 static int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_adhoc, const bpg_table* const* tabs,
                           const size_t* offs, const size_t* lens, int nsegs, const uint32_t* d_scalars, size_t total,
-                          uint8_t out[32]) {
+                          uint8_t out[32], bool identity_only = false /*out: zeros iff the sum is the identity*/) {
   cudaStream_t s = ctx->stream;
   uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small + 1024);
   uint32_t* d_ext = (uint32_t*)ctx->d_small;  // up to two partial sums
@@ -1502,8 +1511,15 @@ static int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_
       if (rc) break;
       rc = BPG_ERR_CUDA;
       if (n_adhoc && cudaStreamWaitEvent(s, ctx->ev_join, 0) != cudaSuccess) break;
-      rc = bpg_dev_sum_encode(ctx, d_ext, n_parts, 1, d_bytes, nullptr);
-      if (rc) break;
+      if (identity_only) {
+        prof_mark(ctx, BPG_PROF_ENCODE);
+        k_sum_is_identity<<<1, 32, 0, s>>>(d_ext, n_parts, d_bytes);
+        ctx->launches++;
+        prof_mark(ctx, -1);
+      } else {
+        rc = bpg_dev_sum_encode(ctx, d_ext, n_parts, 1, d_bytes, nullptr);
+        if (rc) break;
+      }
       rc = BPG_ERR_CUDA;
       if (cudaMemcpyAsync(ctx->h_pinned, d_bytes, 32, cudaMemcpyDeviceToHost, s) != cudaSuccess) break;
       if (cudaMemcpyAsync(ctx->h_pinned + 64, bad, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) break;

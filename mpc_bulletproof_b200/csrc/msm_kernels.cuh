@@ -47,6 +47,9 @@ struct MsmCfg {
 };
 
 constexpr uint32_t ENTRY_NEG = 0x80000000u;
+constexpr uint32_t ACC_SEG = 64;     // entries per work item of k_accum
+constexpr uint32_t SIZE_BINS = 128;  // size classes 0..ACC_SEG of the accumulation schedule
+constexpr uint32_t BIG_SEG = 2048;   // entries of an over-long bucket handled by one block of k_accum_big
 
 // ---------------------------------------------------------------------------
 // digits -> histogram
@@ -71,10 +74,11 @@ __device__ __forceinline__ int digit_at(const uint32_t (*sh)[SORT_THREADS], int 
 // repeated values, the short top window) issue ONE atomic for the group.
 __global__ void __launch_bounds__(SORT_THREADS) k_hist(const uint32_t* __restrict__ scalars,
                                                        const uint8_t* __restrict__ set_ids, MsmCfg cfg,
-                                                       uint32_t* __restrict__ counts) {
+                                                       uint32_t* __restrict__ counts, uint32_t t_begin,
+                                                       uint32_t t_end /*this launch: terms [t_begin, t_end)*/) {
   __shared__ uint32_t sh[9][SORT_THREADS];
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = t < cfg.n_terms;
+  uint32_t t = t_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = t < t_end;
   const uint32_t lane = threadIdx.x & 31;
   sc k = sc_zero();
   if (valid) sc_load(k, scalars + (size_t)t * 8);
@@ -163,10 +167,16 @@ __global__ void __launch_bounds__(1024) k_scan_spine(uint32_t* __restrict__ tile
   if (threadIdx.x == 0) offsets[B] = carry_s;
 }
 
+// Also the size histogram of the accumulation schedule (the list lengths pass through here):
+// bins[r] += buckets whose last segment has r entries, bins[ACC_SEG] += full segments.
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t* __restrict__ counts, uint32_t B,
                                                              const uint32_t* __restrict__ tile_sums,
-                                                             uint32_t* __restrict__ offsets) {
+                                                             uint32_t* __restrict__ offsets,
+                                                             uint32_t* __restrict__ bins /*[SIZE_BINS], zeroed*/) {
   __shared__ uint32_t smem[33];
+  __shared__ uint32_t sh[SIZE_BINS];
+  for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
   uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS];
   uint32_t s = 0;
@@ -184,9 +194,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t* __restric
     if (idx < B) {
       offsets[idx] = ex;
       counts[idx] = 0;
+      uint32_t len = v[i];
+      if (len <= BIG_SEG) {
+        uint32_t full = len / ACC_SEG, rem = len % ACC_SEG;
+        if (full) atomicAdd(&sh[ACC_SEG], full);
+        if (rem || !full) atomicAdd(&sh[rem], 1u);
+      }
     }
     ex += v[i];
   }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x)
+    if (sh[i]) atomicAdd(&bins[i], sh[i]);
 }
 
 // ---------------------------------------------------------------------------
@@ -244,7 +263,6 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t* __rest
 // bucket accumulation: one thread per bucket
 // ---------------------------------------------------------------------------
 constexpr int ACC_THREADS = 128;
-constexpr uint32_t BIG_SEG = 2048;  // entries of an over-long bucket handled by one block of k_accum_big
 
 // bucket sums are parked in the "cached" operand layout of ge4_add_cached:
 // [Y-X | Y+X | 2Z | 2dT], so that the reduction's first addition needs no conversion
@@ -297,10 +315,9 @@ __device__ __forceinline__ ge4 block_sum_quads(ge4 p, uint32_t (*sm)[32]) {
 // finished by its thread; a longer one (structured scalars, or the short top window whose few
 // occupied buckets are long) leaves per-segment partial sums that k_accum_fix adds; beyond
 // BIG_SEG entries the block-cooperative k_accum_big takes over.
-constexpr uint32_t ACC_SEG = 64;
-constexpr uint32_t SIZE_BINS = 128;  // size classes 0..ACC_SEG
 struct AccSched {
-  uint32_t* bins;        // [SIZE_BINS] class counters -> class cursors
+  uint32_t* bins;        // [SIZE_BINS] class counts (k_scan_apply)
+  uint32_t* cursors;     // [SIZE_BINS] items handed out per class (zeroed)
   uint32_t* n_items;     // total work items
   uint2* items;          // (bucket, segment)
   uint32_t* seg_slot;    // [B] first partial-sum slot of a multi-segment bucket
@@ -310,40 +327,28 @@ struct AccSched {
 };
 __device__ __forceinline__ uint32_t acc_nseg(uint32_t len) { return len == 0 ? 1u : (len + ACC_SEG - 1) / ACC_SEG; }
 
-__global__ void __launch_bounds__(256) k_size_hist(const uint32_t* __restrict__ offsets, uint32_t B,
-                                                   uint32_t* __restrict__ bins /*[SIZE_BINS], zeroed*/) {
-  __shared__ uint32_t sh[SIZE_BINS];
-  for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) sh[i] = 0;
-  __syncthreads();
-  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
-    uint32_t len = offsets[b + 1] - offsets[b];
-    if (len > BIG_SEG) continue;
-    uint32_t full = len / ACC_SEG, rem = len % ACC_SEG;
-    if (full) atomicAdd(&sh[ACC_SEG], full);
-    if (rem || !full) atomicAdd(&sh[rem], 1u);
-  }
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x)
-    if (sh[i]) atomicAdd(&bins[i], sh[i]);
-}
-// single block: bins -> starting position of each size class, largest first; total -> n_items
-__global__ void __launch_bounds__(SIZE_BINS) k_size_scan(uint32_t* __restrict__ bins, uint32_t* __restrict__ n_items) {
-  __shared__ uint32_t smem[33];
-  uint32_t i = threadIdx.x;
-  uint32_t v = bins[SIZE_BINS - 1 - i];  // reversed: the longest class first
-  uint32_t total;
-  uint32_t ex = block_exclusive_scan(v, &total, smem);
-  bins[SIZE_BINS - 1 - i] = ex;
-  if (i == 0) *n_items = total;
-}
 __global__ void __launch_bounds__(256) k_size_scatter(const uint32_t* __restrict__ offsets, MsmCfg cfg, AccSched sc,
                                                       uint32_t* __restrict__ big_count,
                                                       uint32_t* __restrict__ big_list) {
-  // block-private histogram first: one global atomic per (block, occupied size class)
+  // class start positions, longest class first: every block scans the 128 class counts itself
+  // (no separate single-block launch); block 0 publishes the total
   __shared__ uint32_t cnt[SIZE_BINS];
   __shared__ uint32_t base[SIZE_BINS];
-  for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) cnt[i] = 0;
+  __shared__ uint32_t start[SIZE_BINS];
+  __shared__ uint32_t smem[33];
+  {
+    uint32_t i = threadIdx.x;
+    uint32_t v = i < SIZE_BINS ? sc.bins[SIZE_BINS - 1 - i] : 0;  // reversed
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(v, &total, smem);
+    if (i < SIZE_BINS) {
+      start[SIZE_BINS - 1 - i] = ex;
+      cnt[i] = 0;
+    }
+    if (blockIdx.x == 0 && i == 0) *sc.n_items = total;
+  }
   __syncthreads();
+  // block-private histogram first: one global atomic per (block, occupied size class)
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t len = 0, full = 0, rem = 0, rank_full = 0, rank_rem = 0;
   bool small = false;
@@ -368,7 +373,7 @@ __global__ void __launch_bounds__(256) k_size_scatter(const uint32_t* __restrict
   }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x)
-    if (cnt[i]) base[i] = atomicAdd(&sc.bins[i], cnt[i]);
+    if (cnt[i]) base[i] = start[i] + atomicAdd(&sc.cursors[i], cnt[i]);
   __syncthreads();
   if (small) {
     for (uint32_t j = 0; j < full; j++) sc.items[base[ACC_SEG] + rank_full + j] = make_uint2(b, j);
@@ -801,6 +806,27 @@ __global__ void __launch_bounds__(ENC_THREADS) k_sum_encode(const uint32_t* __re
   }
 }
 
+// Accept-iff-identity (Verifier::verify, reference src/r1cs/verifier.rs:549): no encoding, hence no
+// inverse square root.  A ristretto255 element equals the identity iff X = 0 or Y = 0 (RFC 9496
+// §4.3.3: X1 Y2 == Y1 X2 or Y1 Y2 == X1 X2 against (0 : 1 : 1 : 0)).  out: 32 zero bytes (the
+// identity's encoding) or 0x01 0x00.. (odd, so not a canonical encoding of anything).
+__global__ void __launch_bounds__(32) k_sum_is_identity(const uint32_t* __restrict__ parts, int nparts,
+                                                        uint8_t* __restrict__ out_bytes) {
+  if (threadIdx.x != 0) return;
+  ge_ext acc;
+  ge_load_ext(acc, parts);
+  for (int p = 1; p < nparts; p++) {
+    ge_ext o;
+    ge_load_ext(o, parts + (size_t)p * 32);
+    acc = ge_add(acc, o);
+  }
+  bool id = fe_is_zero(acc.X) | fe_is_zero(acc.Y);
+  uint32_t* w = reinterpret_cast<uint32_t*>(out_bytes);
+#pragma unroll
+  for (int i = 0; i < 8; i++) w[i] = 0;
+  if (!id) w[0] = 1;
+}
+
 // ---------------------------------------------------------------------------
 // Sharded MSM, the exchange step fused with the combine: ONE kernel per rank
 //   1. stores this rank's partial sums (n_sets x 128 B) into slot [rank] of EVERY rank's exchange
@@ -869,14 +895,25 @@ __global__ void __launch_bounds__(XCH_THREADS) k_exchange_sum_encode(const uint3
     if (threadIdx.x == 0) *status = 1;
     return;
   }
-  // 3. combine: one thread per set, partials read past the L1 (they were written by peers)
-  int set = threadIdx.x;
-  if (set < nsets) {
-    const uint32_t* base = peers.parts[rank] + slot * slot_words;
+  // 3. combine: one half-warp per set (the sum computed by each of its lanes, the encoding on
+  // sixteen lanes, fe16.cuh); partials read past the L1 (they were written by peers)
+  __shared__ __align__(16) uint32_t sm16[(XCH_THREADS / 16) * G16_WORDS];
+  grp16 g;
+  g.sm = sm16 + (threadIdx.x >> 4) * G16_WORDS;
+  g.k = threadIdx.x & 15u;
+  g.par = 0;
+  const uint32_t* base = peers.parts[rank] + slot * slot_words;
+  for (int first = 0; first < nsets; first += XCH_THREADS / 16) {  // block-uniform trip count
+    int set = first + (int)(threadIdx.x >> 4);
+    bool live = set < nsets;
+    if (!live) set = nsets - 1;  // idle groups shadow the last set: the exchanges are warp-wide
     ge_ext acc = ge_load_ext_volatile(base + (size_t)set * 32);
     for (int p = 1; p < world; p++) acc = ge_add(acc, ge_load_ext_volatile(base + ((size_t)p * max_sets + set) * 32));
-    if (out_ext) ge_store_ext(out_ext + (size_t)set * 32, acc);
-    if (out_bytes) ge_encode(out_bytes + (size_t)set * 32, acc);
+    if (out_ext && live && g.k == 0) ge_store_ext(out_ext + (size_t)set * 32, acc);
+    if (out_bytes) {
+      fe s = ge_encode16(g, acc);
+      if (live) store_s_bytes(out_bytes + (size_t)set * 32, s, g.k);
+    }
   }
 }
 

@@ -243,3 +243,49 @@ def test_full_size_linearity_windowed(ctx):
     small_table.close()
     assert big == small
     assert small == G.msm(summed, ps).encode()
+
+
+def test_host_scalars_in_pieces_ragged(ctx):
+    """Host scalars of a large launch are uploaded in pieces with the digit histogram of each piece
+    running behind its copy (bpg_msm_table, >= 2^18 terms).  A term count that is not a multiple of
+    the piece granularity, two sets, and the same launch from device-resident scalars must agree,
+    and the column-sum property ties the result to the oracle."""
+    import numpy as np
+    import torch
+
+    from mpc_bulletproof_b200 import Table
+    from mpc_bulletproof_b200.api import dev_sum_encode
+
+    r = rng(98)
+    m, reps = 1024, 257
+    n = (1 << 18) + 777
+    ps = [rand_point(r) for _ in range(m)]
+    pb = points_bytes(ps)
+    t = Table(ctx, pb * reps).set_windows(0)
+    g = np.random.Generator(np.random.PCG64(6))
+    raw = g.integers(0, 256, size=(2, n, 32), dtype=np.uint8)
+    raw[:, :, 31] &= 0x0F
+    got = t.msm(raw.tobytes(), n_sets=2, n=n)
+    # device-resident scalars: no upload, one histogram launch
+    dev = torch.device("cuda", 0)
+    d_sc = torch.from_numpy(raw.reshape(-1).copy()).to(dev)
+    d_ext = torch.empty(2 * 128, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(64, dtype=torch.uint8, device=dev)
+    t.dev_msm(d_sc.data_ptr(), 2, d_ext.data_ptr(), n=n)
+    dev_sum_encode(ctx, d_ext.data_ptr(), 1, 2, d_out.data_ptr())
+    ctx.sync()
+    res = bytes(d_out.cpu().tolist())
+    assert got == [res[:32], res[32:]]
+    # oracle: column sums over the tiled 1024 points
+    for s in range(2):
+        col = [0] * m
+        limbs = raw[s].view("<u8").astype(object)
+        for k in range(4):
+            part = np.zeros(m, dtype=object)
+            idx = np.arange(n) % m
+            np.add.at(part, idx, limbs[:, k])
+            for i in range(m):
+                col[i] += int(part[i]) << (64 * k)
+        summed = [c % G.L for c in col]
+        assert got[s] == G.msm(summed, ps).encode()
+    t.close()

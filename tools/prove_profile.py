@@ -53,6 +53,27 @@ def main():
         out["runs"].append({"prove_ms": t_prove, "launches": launches,
                             "phases_ms_total": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
                             "phase_counts": {k: v[1] for k, v in prof.items() if v[1]}})
+    # verification of the last proof: wall-clock unprofiled, then the phases
+    walls = []
+    for it in range(6):
+        v = P.Verifier(gens, P.Transcript(b"bench r1cs"))
+        build(v, val)
+        t0 = time.perf_counter()
+        v.verify(proof)
+        walls.append((time.perf_counter() - t0) * 1e3)
+    out["verify_ms_unprofiled"] = sorted(walls[1:])
+    v = P.Verifier(gens, P.Transcript(b"bench r1cs"))
+    build(v, val)
+    ctx.profile(True)
+    ctx.profile_reset()
+    l0 = ctx.launches
+    t0 = time.perf_counter()
+    v.verify(proof)
+    t_verify = (time.perf_counter() - t0) * 1e3
+    prof = ctx.profile_read()
+    out["verify"] = {"verify_ms": t_verify, "launches": ctx.launches - l0,
+                     "phases_ms_total": {k: round(v_[0], 3) for k, v_ in prof.items() if v_[1]}}
+    ctx.profile(False)
     print(json.dumps(out))
 
 
