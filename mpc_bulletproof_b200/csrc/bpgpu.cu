@@ -148,6 +148,8 @@ extern "C" int bpg_init(int device, bpg_ctx** out) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_small, SMALL_BYTES);
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_pinned, SMALL_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_reduce_pairs_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RPB_SMEM);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) {
     delete ctx;
@@ -747,9 +749,15 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
     LAUNCH_CHECK();
     while (t > 1) {
       uint32_t n = t;
-      t = (n + RP_PAIRS - 1) / RP_PAIRS;
       const uint32_t* ia = pa[cur];
       const uint32_t* iy = pa[cur] + pair_words;
+      if (n <= RPB_PAIRS) {
+        // what is left fits one block per array: finish here
+        k_reduce_pairs_final<<<rarr, RPB_THREADS, RPB_SMEM, st>>>(ia, iy, n, final_out);
+        LAUNCH_CHECK();
+        break;
+      }
+      t = (n + RP_PAIRS - 1) / RP_PAIRS;
       cur ^= 1;
       oa = t == 1 ? final_out : pa[cur];
       k_reduce_pairs<<<rarr * t, RP_THREADS, 0, st>>>(ia, iy, n, t, oa, pa[cur] + pair_words);

@@ -722,6 +722,33 @@ __global__ void __launch_bounds__(RP_THREADS) k_reduce_pairs(const uint32_t* __r
   }
 }
 
+// The last levels in ONE block: up to RPB_PAIRS pairs of an array -> its total.  A tree level costs
+// its depth (about ten dependent field products), not its width, so finishing 256 pairs here
+// takes 8 levels where two k_reduce_pairs launches took 6 + 2 (+ a launch gap and a round trip
+// through global memory).  Dynamic shared memory: 2 x RPB_PAIRS x 128 bytes.
+constexpr int RPB_THREADS = 512;  // 128 registers per thread stay available to the quad arithmetic
+constexpr uint32_t RPB_PAIRS = 256;
+constexpr size_t RPB_SMEM = 2 * (size_t)RPB_PAIRS * 128;
+__global__ void __launch_bounds__(RPB_THREADS) k_reduce_pairs_final(const uint32_t* __restrict__ in_a,
+                                                                     const uint32_t* __restrict__ in_y, uint32_t n,
+                                                                     uint32_t* __restrict__ out_a) {
+  extern __shared__ __align__(16) uint32_t rpb_smem[];
+  uint32_t(*sa)[32] = reinterpret_cast<uint32_t(*)[32]>(rpb_smem);
+  uint32_t(*sy)[32] = reinterpret_cast<uint32_t(*)[32]>(rpb_smem + RPB_PAIRS * 32);
+  uint32_t arr = blockIdx.x;
+  const uint4* ga = reinterpret_cast<const uint4*>(in_a + (size_t)arr * n * 32);
+  const uint4* gy = reinterpret_cast<const uint4*>(in_y + (size_t)arr * n * 32);
+  uint4* da = reinterpret_cast<uint4*>(rpb_smem);
+  uint4* dy = reinterpret_cast<uint4*>(rpb_smem + RPB_PAIRS * 32);
+  for (uint32_t w = threadIdx.x; w < n * 8; w += blockDim.x) {
+    da[w] = ga[w];
+    dy[w] = gy[w];
+  }
+  __syncthreads();
+  rt_block_tree(sa, sy, n);
+  if (threadIdx.x < 32) out_a[(size_t)arr * 32 + threadIdx.x] = sa[0][threadIdx.x];
+}
+
 // plain tables, one warp per set: sum_w 2^(c w) S_w (Horner, top window first)
 __global__ void __launch_bounds__(32) k_horner(const uint32_t* __restrict__ window_sums, MsmCfg cfg,
                                                 uint32_t* __restrict__ out_ext) {
