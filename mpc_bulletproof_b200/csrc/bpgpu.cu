@@ -497,6 +497,7 @@ static int pick_window_table(size_t n, int forced) {
   return best_c;
 }
 
+static sc_bias bias_for(int c);
 static void make_cfg(MsmCfg& cfg, size_t n_terms, size_t n_points, int nsets, int c, size_t win_stride, int forced_gsub) {
   cfg.win_stride = (uint32_t)win_stride;
   cfg.c = c;
@@ -550,6 +551,29 @@ static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points
     return BPG_OK;
   }
   if (n_terms >= (1u << 31)) return BPG_ERR_ARG;
+  if (curve == 0 && win_c == 0 && n_terms <= SMALL_MAX_TERMS && nsets <= SMALL_MAX_SETS && ctx->forced_c < 2) {
+    // a handful of terms over a plain table: one quad per term walks the doubling chain (k_msm_small);
+    // a forced window width (bpg_set_window) keeps the bucket pipeline, which is how the tests reach it
+    if (h_scalars) CK(cudaMemcpyAsync((void*)d_scalars, h_scalars, n_terms * 32, cudaMemcpyHostToDevice, st));
+    unsigned nblk = (unsigned)((n_terms + SMALL_QUADS - 1) / SMALL_QUADS);
+    prof_mark(ctx, BPG_PROF_ACCUM);
+    if (nblk == 1) {
+      k_msm_small<<<1, SMALL_THREADS, 0, st>>>(table_base, d_scalars, d_set_ids, d_point_ids, (uint32_t)n_terms,
+                                               (uint32_t)std::max<size_t>(n_points, 1), nsets, bias_for(4), d_out_ext);
+      LAUNCH_CHECK();
+    } else {
+      int rc = ensure_ws(ctx, (size_t)nblk * nsets * 128, lane);
+      if (rc) return rc;
+      uint32_t* parts = (uint32_t*)ws;
+      k_msm_small<<<nblk, SMALL_THREADS, 0, st>>>(table_base, d_scalars, d_set_ids, d_point_ids, (uint32_t)n_terms,
+                                                  (uint32_t)std::max<size_t>(n_points, 1), nsets, bias_for(4), parts);
+      LAUNCH_CHECK();
+      k_msm_small_fin<<<1, SMALL_THREADS, 0, st>>>(parts, nblk, nsets, d_out_ext);
+      LAUNCH_CHECK();
+    }
+    prof_mark(ctx, -1);
+    return BPG_OK;
+  }
   MsmCfg cfg;
   int c = win_c ? win_c : pick_window((n_terms + nsets - 1) / nsets, ctx->forced_c);
   make_cfg(cfg, n_terms, n_points, nsets, c, win_c ? win_stride : 0, ctx->forced_gsub);

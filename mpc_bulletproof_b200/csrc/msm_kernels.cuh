@@ -749,6 +749,114 @@ __global__ void __launch_bounds__(RPB_THREADS) k_reduce_pairs_final(const uint32
   if (threadIdx.x < 32) out_a[(size_t)arr * 32 + threadIdx.x] = sa[0][threadIdx.x];
 }
 
+// ---------------------------------------------------------------------------
+// A few ad-hoc terms (the proof points of a verification, an `msm_iter` over a handful of points;
+// reference src/r1cs/verifier.rs:516-547, src/inner_product_proof.rs:359-371): nothing is
+// precomputed for them, so the cost is the 252-doubling chain of a scalar multiplication, and
+// the sort / bucket / tree pipeline (fifteen dependent launches) only adds to it.  Here ONE QUAD
+// per term walks the chain -- signed 4-bit windows, eight cached multiples of the point in
+// shared memory, 4 doublings + 1 addition per window at two multiplication levels each -- and a
+// tree over the block's quads adds the terms of each set.  One launch (+ one to add the blocks'
+// sums when there are more than 32 terms).
+// ---------------------------------------------------------------------------
+constexpr int COMB_WINDOWS = 64;  // signed 4-bit windows of a 256-bit scalar (also the fixed-base comb)
+constexpr int SMALL_THREADS = 128;
+constexpr int SMALL_QUADS = SMALL_THREADS / 4;
+constexpr uint32_t SMALL_MAX_TERMS = 1024;  // 32 blocks: what k_msm_small_fin adds in one pass
+constexpr int SMALL_MAX_SETS = 4;
+
+// sum over the block's quads of `mine` for the quads whose `member` is set; result in every quad that
+// reads slot 0 afterwards (sm: [SMALL_QUADS][32] words)
+__device__ __forceinline__ ge4 small_block_sum(ge4 mine, bool member, uint32_t (*sm)[32]) {
+  uint32_t quad = threadIdx.x >> 2;
+  ge4 v;
+  v.c = fe_sel(member, mine.c, ge4_identity().c);
+  __syncthreads();
+  ge4_store(sm[quad], v);
+  __syncthreads();
+  for (uint32_t m = SMALL_QUADS; m > 1; m >>= 1) {
+    uint32_t half = m >> 1;
+    uint32_t q = quad < half ? quad : 0;
+    ge4 a = ge4_load(sm[2 * q]), b = ge4_load(sm[2 * q + 1]);
+    ge4 r = ge4_add(a, b);
+    __syncthreads();
+    if (quad < half) ge4_store(sm[quad], r);
+    __syncthreads();
+  }
+  return ge4_load(sm[0]);
+}
+
+__global__ void __launch_bounds__(SMALL_THREADS) k_msm_small(const uint32_t* __restrict__ table /*affine Niels*/,
+                                                              const uint32_t* __restrict__ scalars,
+                                                              const uint8_t* __restrict__ set_ids,
+                                                              const uint32_t* __restrict__ point_ids, uint32_t n_terms,
+                                                              uint32_t n_points, int nsets, sc_bias bias4,
+                                                              uint32_t* __restrict__ out /*[gridDim.x][nsets][32] ext*/) {
+  __shared__ __align__(16) uint32_t mult[SMALL_QUADS][8][32];  // cached multiples 1..8 of each quad's point
+  __shared__ __align__(16) uint32_t red[SMALL_QUADS][32];
+  const uint32_t quad = threadIdx.x >> 2;
+  const int q = threadIdx.x & 3;
+  uint32_t t = blockIdx.x * SMALL_QUADS + quad;
+  const bool live = t < n_terms;
+  if (!live) t = 0;  // idle quads shadow term 0 (every lane takes part in the shuffles) and add nothing
+  const uint32_t pid = point_ids ? point_ids[t] : t % n_points;
+  const uint32_t set = nsets > 1 ? (set_ids ? set_ids[t] : t / n_points) : 0;
+  sc k;
+  sc_load(k, scalars + (size_t)t * 8);
+  const sc_recoded rec = sc_recode(k.v, bias4);
+  // the point, one coordinate per lane
+  ge_niels nq;
+  ge_load_niels(nq, table + (size_t)pid * 24);
+  ge_ext pe = ge_from_niels(nq, false);
+  ge4 P;
+  P.c = q == 0 ? pe.X : (q == 1 ? pe.Y : (q == 2 ? pe.Z : pe.T));
+  const ge4 Pc = ge4_to_cached(P);
+  ge4 run = P;
+  ge4_store(mult[quad][0], Pc);
+#pragma unroll 1
+  for (int d = 1; d < 8; d++) {
+    run = ge4_add_cached(run, Pc);
+    ge4_store(mult[quad][d], ge4_to_cached(run));
+  }
+  __syncwarp();
+  const ge4 idc = ge4_identity_cached();
+  ge4 acc = ge4_identity();
+#pragma unroll 1
+  for (int j = COMB_WINDOWS - 1; j >= 0; j--) {
+    if (j != COMB_WINDOWS - 1) {
+      acc = ge4_dbl(acc);
+      acc = ge4_dbl(acc);
+      acc = ge4_dbl(acc);
+      acc = ge4_dbl(acc);
+    }
+    int d = sc_digit(rec, j, 4);
+    int mag = d < 0 ? -d : d;
+    ge4 m = ge4_load(mult[quad][mag ? mag - 1 : 0]);
+    // -(cached): Y-X <-> Y+X, 2dT -> -2dT
+    fe other = fe_quad_get(m.c, q ^ 1);
+    fe neg = q < 2 ? other : (q == 3 ? fe_neg(m.c) : m.c);
+    m.c = fe_sel(d < 0, neg, m.c);
+    m.c = fe_sel(mag != 0, m.c, idc.c);
+    acc = ge4_add_cached(acc, m);
+  }
+  for (int s = 0; s < nsets; s++) {
+    ge4 tot = small_block_sum(acc, live && set == (uint32_t)s, red);
+    if (threadIdx.x < 4) ge4_store(out + ((size_t)blockIdx.x * nsets + s) * 32, tot);
+  }
+}
+// out[s] = sum_b parts[b][s], b < nblocks <= SMALL_QUADS
+__global__ void __launch_bounds__(SMALL_THREADS) k_msm_small_fin(const uint32_t* __restrict__ parts, uint32_t nblocks,
+                                                                  int nsets, uint32_t* __restrict__ out) {
+  __shared__ __align__(16) uint32_t red[SMALL_QUADS][32];
+  const uint32_t quad = threadIdx.x >> 2;
+  for (int s = 0; s < nsets; s++) {
+    bool have = quad < nblocks;
+    ge4 v = ge4_load(parts + ((size_t)(have ? quad : 0) * nsets + s) * 32);
+    ge4 tot = small_block_sum(v, have, red);
+    if (threadIdx.x < 4) ge4_store(out + (size_t)s * 32, tot);
+  }
+}
+
 // plain tables, one warp per set: sum_w 2^(c w) S_w (Horner, top window first)
 __global__ void __launch_bounds__(32) k_horner(const uint32_t* __restrict__ window_sums, MsmCfg cfg,
                                                 uint32_t* __restrict__ out_ext) {
@@ -991,7 +1099,6 @@ __global__ void __launch_bounds__(128) k_encode(const uint32_t* __restrict__ ext
 // Pedersen commitments `v*B + v_blinding*B_blinding` (reference
 // src/generators.rs:41-43; prover.rs:325,627-631,687) and synthetic point sets.
 // ---------------------------------------------------------------------------
-constexpr int COMB_WINDOWS = 64;
 constexpr int COMB_ENTRIES = COMB_WINDOWS * 8;
 
 __global__ void __launch_bounds__(COMB_WINDOWS) k_comb_build(const uint8_t* __restrict__ base32,

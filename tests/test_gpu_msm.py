@@ -289,3 +289,42 @@ def test_host_scalars_in_pieces_ragged(ctx):
         summed = [c % G.L for c in col]
         assert got[s] == G.msm(summed, ps).encode()
     t.close()
+
+
+@pytest.mark.parametrize("n", [31, 32, 33, 46, 1024, 1025])
+def test_msm_few_terms_path(ctx, n):
+    """Up to 1024 terms over a plain table take the quad-per-term path (k_msm_small: no sort, no
+    buckets); 1025 is the first size of the bucket pipeline.  Block boundaries (32 terms per block),
+    edge scalars and cancelling points included; the same inputs through the bucket pipeline
+    (forced window) must give the same bytes."""
+    r = rng(300 + n)
+    ks = [rand_scalar(r) for _ in range(n)]
+    ps = [rand_point(r) for _ in range(n)]
+    ks[0], ks[1], ks[2] = 0, G.L - 1, 2**252
+    ps[3] = G.IDENTITY
+    ps[5], ks[5] = -ps[4], ks[4]  # k P + k (-P)
+    _check(ctx, ks, ps)
+    from mpc_bulletproof_b200 import msm
+
+    direct = msm(ctx, scalars_bytes(ks), points_bytes(ps))
+    ctx.set_window(6)
+    try:
+        assert msm(ctx, scalars_bytes(ks), points_bytes(ps)) == direct
+    finally:
+        ctx.set_window(0)
+
+
+def test_few_terms_sets(ctx):
+    """Several output sets over a plain table on the quad-per-term path (terms of a block belong to
+    different sets; blocks are added by k_msm_small_fin)."""
+    from mpc_bulletproof_b200 import Table
+
+    r = rng(77)
+    n = 75
+    ps = [rand_point(r) for _ in range(n)]
+    t = Table(ctx, points_bytes(ps))
+    kk = [[rand_scalar(r) for _ in range(n)] for _ in range(3)]
+    assert t.msm(b"".join(scalars_bytes(k) for k in kk), n_sets=3) == [G.msm(k, ps).encode() for k in kk]
+    kk2 = [[rand_scalar(r) for _ in range(20)] for _ in range(2)]
+    assert t.msm(b"".join(scalars_bytes(k) for k in kk2), n_sets=2, offset=30, n=20) == [G.msm(k, ps[30:50]).encode() for k in kk2]
+    t.close()
