@@ -811,7 +811,7 @@ extern "C" int bpg_dev_sum_encode(bpg_ctx* ctx, const void* d_parts, int n_parts
   if (!ctx || !d_parts || n_parts <= 0 || n_sets <= 0) return BPG_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   prof_mark(ctx, BPG_PROF_ENCODE);
-  k_sum_encode<<<(n_sets + 1) / 2, ENC_THREADS, 0, ctx->stream>>>((const uint32_t*)d_parts, n_parts, n_sets,
+  k_sum_encode<<<n_sets, ENC_THREADS, 0, ctx->stream>>>((const uint32_t*)d_parts, n_parts, n_sets,
                                                            (uint8_t*)d_out_bytes, (uint32_t*)d_out_ext);
   LAUNCH_CHECK();
   prof_mark(ctx, -1);

@@ -34,8 +34,9 @@ constexpr int G16_WORDS = 112;  // per-group exchange buffer: 2 x 48 words, padd
 
 struct grp16 {
   uint32_t* sm;   // this half-warp's exchange buffer (G16_WORDS words, 16-byte aligned)
-  uint32_t k;     // lane within the group
+  uint32_t k;     // lane within the group (limb index)
   uint32_t par;   // which half of the buffer the next exchange uses
+  uint32_t half;  // WIDE mode only: which half-warp this lane is in (lane >> 4)
 #if defined(BPG_HOSTSIM)  // tests/hostsim only
   pthread_barrier_t* bar;
   uint32_t* slots;  // 16 words for the shuffle model
@@ -48,18 +49,34 @@ __device__ __forceinline__ void g16_sync(const grp16&) { __syncwarp(); }
 __device__ __forceinline__ uint32_t g16_shfl(const grp16&, uint32_t v, uint32_t src) {
   return __shfl_sync(0xffffffffu, v, (int)src, 16);
 }
+// WIDE mode: the value held by the same limb's lane in the other half-warp
+__device__ __forceinline__ uint64_t g16_other_half(const grp16&, uint64_t v) {
+  uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, 16);
+  uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), 16);
+  return ((uint64_t)hi << 32) | lo;
+}
 #elif defined(BPG_HOSTSIM)
+// slots: 2 x 32 words; a half-warp of the model uses its own 16 (half = 0 when only 16 threads run)
 inline void g16_sync(const grp16& g) { pthread_barrier_wait(g.bar); }
 inline uint32_t g16_shfl(const grp16& g, uint32_t v, uint32_t src) {
-  g.slots[g.k] = v;
+  g.slots[g.half * 16 + g.k] = v;
   pthread_barrier_wait(g.bar);
-  uint32_t r = g.slots[src];
+  uint32_t r = g.slots[g.half * 16 + src];
+  pthread_barrier_wait(g.bar);
+  return r;
+}
+inline uint64_t g16_other_half(const grp16& g, uint64_t v) {
+  g.slots[g.half * 16 + g.k] = (uint32_t)v;
+  g.slots[32 + g.half * 16 + g.k] = (uint32_t)(v >> 32);
+  pthread_barrier_wait(g.bar);
+  uint64_t r = ((uint64_t)g.slots[32 + (g.half ^ 1) * 16 + g.k] << 32) | g.slots[(g.half ^ 1) * 16 + g.k];
   pthread_barrier_wait(g.bar);
   return r;
 }
 #else  // host pass of the product build: never called
 inline void g16_sync(const grp16&) {}
 inline uint32_t g16_shfl(const grp16&, uint32_t v, uint32_t) { return v; }
+inline uint64_t g16_other_half(const grp16&, uint64_t v) { return v; }
 #endif
 
 struct fe16 {
@@ -82,23 +99,45 @@ BPG_DI fe16 fe16_carry(grp16& g, fe16 a) {
 }
 
 // a * b.  Operands: limb 0 < 2^23, others < 2^19 (any product, carried sum or carried difference).
+// WIDE: both half-warps work on the SAME element (same exchange buffer, same limb on lanes k and
+// k + 16); each half forms eight of the sixteen column terms and the halves swap their partial
+// columns, so a product is 8 multiply-adds + 10 loads per lane instead of 16 + 20.
+template <bool WIDE>
 BPG_DI fe16 fe16_mul(grp16& g, fe16 a, fe16 b) {
   uint32_t* buf = g16_next_buf(g);
   buf[g.k] = 38u * b.l;
   buf[16 + g.k] = b.l;
   buf[32 + g.k] = a.l;
   g16_sync(g);
-  const uint32_t* rot = buf + 16 + g.k;  // rot[-i] = b'_(k-i)
-  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+  uint64_t T;
+  if (WIDE) {
+    const uint32_t hb = g.half * 8u;
+    const uint32_t* rot = buf + 16 + g.k - hb;  // rot[-j] = b'_(k - hb - j)
+    const uint32_t* av = buf + 32 + hb;
+    uint64_t t0 = 0, t1 = 0;
 #pragma unroll
-  for (int i = 0; i < 16; i += 4) {
-    uint4 av = *reinterpret_cast<const uint4*>(buf + 32 + i);
-    t0 += (uint64_t)av.x * rot[-i];
-    t1 += (uint64_t)av.y * rot[-i - 1];
-    t2 += (uint64_t)av.z * rot[-i - 2];
-    t3 += (uint64_t)av.w * rot[-i - 3];
+    for (int j = 0; j < 8; j += 4) {
+      uint4 x = *reinterpret_cast<const uint4*>(av + j);
+      t0 += (uint64_t)x.x * rot[-j];
+      t1 += (uint64_t)x.y * rot[-j - 1];
+      t0 += (uint64_t)x.z * rot[-j - 2];
+      t1 += (uint64_t)x.w * rot[-j - 3];
+    }
+    uint64_t part = t0 + t1;
+    T = part + g16_other_half(g, part);
+  } else {
+    const uint32_t* rot = buf + 16 + g.k;  // rot[-i] = b'_(k-i)
+    uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      uint4 x = *reinterpret_cast<const uint4*>(buf + 32 + i);
+      t0 += (uint64_t)x.x * rot[-i];
+      t1 += (uint64_t)x.y * rot[-i - 1];
+      t2 += (uint64_t)x.z * rot[-i - 2];
+      t3 += (uint64_t)x.w * rot[-i - 3];
+    }
+    T = (t0 + t1) + (t2 + t3);
   }
-  uint64_t T = (t0 + t1) + (t2 + t3);
   uint32_t lo = (uint32_t)T;
   uint32_t s1 = g16_shfl(g, lo >> 16, (g.k + 15u) & 15u);
   uint32_t s2 = g16_shfl(g, (uint32_t)(T >> 32), (g.k + 14u) & 15u);
@@ -108,9 +147,11 @@ BPG_DI fe16 fe16_mul(grp16& g, fe16 a, fe16 b) {
   r.l = (lo & 0xffffu) + s1 + s2;
   return r;
 }
-BPG_DI fe16 fe16_sq(grp16& g, fe16 a) { return fe16_mul(g, a, a); }
+template <bool WIDE>
+BPG_DI fe16 fe16_sq(grp16& g, fe16 a) { return fe16_mul<WIDE>(g, a, a); }
+template <bool WIDE>
 BPG_DI fe16 fe16_sqn(grp16& g, fe16 a, int n) {
-  for (int i = 0; i < n; i++) a = fe16_sq(g, a);
+  for (int i = 0; i < n; i++) a = fe16_sq<WIDE>(g, a);
   return a;
 }
 
@@ -172,46 +213,48 @@ BPG_DI fe fe16_to_fe(grp16& g, fe16 a) {
 }
 
 // a^(2^252 - 3), the chain of fe_pow22523
+template <bool WIDE>
 BPG_DI fe16 fe16_pow22523(grp16& g, fe16 z) {
-  fe16 t0 = fe16_sq(g, z);
-  fe16 t1 = fe16_sqn(g, t0, 2);
-  t1 = fe16_mul(g, z, t1);
-  t0 = fe16_mul(g, t0, t1);
-  t0 = fe16_sq(g, t0);
-  t0 = fe16_mul(g, t1, t0);
-  t1 = fe16_sqn(g, t0, 5);
-  t0 = fe16_mul(g, t1, t0);
-  t1 = fe16_sqn(g, t0, 10);
-  t1 = fe16_mul(g, t1, t0);
-  fe16 t2 = fe16_sqn(g, t1, 20);
-  t1 = fe16_mul(g, t2, t1);
-  t1 = fe16_sqn(g, t1, 10);
-  t0 = fe16_mul(g, t1, t0);
-  t1 = fe16_sqn(g, t0, 50);
-  t1 = fe16_mul(g, t1, t0);
-  t2 = fe16_sqn(g, t1, 100);
-  t1 = fe16_mul(g, t2, t1);
-  t1 = fe16_sqn(g, t1, 50);
-  t0 = fe16_mul(g, t1, t0);
-  t0 = fe16_sqn(g, t0, 2);
-  return fe16_mul(g, t0, z);
+  fe16 t0 = fe16_sq<WIDE>(g, z);
+  fe16 t1 = fe16_sqn<WIDE>(g, t0, 2);
+  t1 = fe16_mul<WIDE>(g, z, t1);
+  t0 = fe16_mul<WIDE>(g, t0, t1);
+  t0 = fe16_sq<WIDE>(g, t0);
+  t0 = fe16_mul<WIDE>(g, t1, t0);
+  t1 = fe16_sqn<WIDE>(g, t0, 5);
+  t0 = fe16_mul<WIDE>(g, t1, t0);
+  t1 = fe16_sqn<WIDE>(g, t0, 10);
+  t1 = fe16_mul<WIDE>(g, t1, t0);
+  fe16 t2 = fe16_sqn<WIDE>(g, t1, 20);
+  t1 = fe16_mul<WIDE>(g, t2, t1);
+  t1 = fe16_sqn<WIDE>(g, t1, 10);
+  t0 = fe16_mul<WIDE>(g, t1, t0);
+  t1 = fe16_sqn<WIDE>(g, t0, 50);
+  t1 = fe16_mul<WIDE>(g, t1, t0);
+  t2 = fe16_sqn<WIDE>(g, t1, 100);
+  t1 = fe16_mul<WIDE>(g, t2, t1);
+  t1 = fe16_sqn<WIDE>(g, t1, 50);
+  t0 = fe16_mul<WIDE>(g, t1, t0);
+  t0 = fe16_sqn<WIDE>(g, t0, 2);
+  return fe16_mul<WIDE>(g, t0, z);
 }
 
 // RFC 9496 §4.3.2 on a half-warp: the same steps as ge_encode (ge.cuh), hence the same bytes.
 // `p` is replicated in the group's lanes; the canonical s comes back replicated.
+template <bool WIDE>
 BPG_DI fe ge_encode16(grp16& g, const ge_ext& p) {
   fe16 X = fe16_from_fe(g, p.X), Y = fe16_from_fe(g, p.Y), Z = fe16_from_fe(g, p.Z), T = fe16_from_fe(g, p.T);
   fe16 I = fe16_from_fe(g, fe_const(BPG_K(K_SQRT_M1)));
   fe16 zero;
   zero.l = 0;
-  fe16 u1 = fe16_mul(g, fe16_add(g, Z, Y), fe16_sub(g, Z, Y));
-  fe16 u2 = fe16_mul(g, X, Y);
+  fe16 u1 = fe16_mul<WIDE>(g, fe16_add(g, Z, Y), fe16_sub(g, Z, Y));
+  fe16 u2 = fe16_mul<WIDE>(g, X, Y);
   // invsqrt = sqrt_ratio_m1(1, v), v = u1 u2^2
-  fe16 v = fe16_mul(g, u1, fe16_sq(g, u2));
-  fe16 v3 = fe16_mul(g, fe16_sq(g, v), v);
-  fe16 v7 = fe16_mul(g, fe16_sq(g, v3), v);
-  fe16 r = fe16_mul(g, v3, fe16_pow22523(g, v7));
-  fe check = fe16_to_fe(g, fe16_mul(g, v, fe16_sq(g, r)));
+  fe16 v = fe16_mul<WIDE>(g, u1, fe16_sq<WIDE>(g, u2));
+  fe16 v3 = fe16_mul<WIDE>(g, fe16_sq<WIDE>(g, v), v);
+  fe16 v7 = fe16_mul<WIDE>(g, fe16_sq<WIDE>(g, v3), v);
+  fe16 r = fe16_mul<WIDE>(g, v3, fe16_pow22523<WIDE>(g, v7));
+  fe check = fe16_to_fe(g, fe16_mul<WIDE>(g, v, fe16_sq<WIDE>(g, r)));
   // check against u = 1: -u = p - 1, -u i = -sqrt(-1)
   fe m1 = fe_canon(fe_neg(fe_one()));
   fe mi = fe_canon(fe_neg(fe_const(BPG_K(K_SQRT_M1))));
@@ -222,22 +265,22 @@ BPG_DI fe ge_encode16(grp16& g, const ge_ext& p) {
     di |= check.v[i] ^ mi.v[i];
   }
   bool flip = (d1 == 0) | (di == 0);
-  r = fe16_sel(flip, fe16_mul(g, r, I), r);
+  r = fe16_sel(flip, fe16_mul<WIDE>(g, r, I), r);
   bool rneg = fe16_to_fe(g, r).v[0] & 1u;
   fe16 invsqrt = fe16_sel(rneg, fe16_sub(g, zero, r), r);
-  fe16 den1 = fe16_mul(g, invsqrt, u1);
-  fe16 den2 = fe16_mul(g, invsqrt, u2);
-  fe16 z_inv = fe16_mul(g, fe16_mul(g, den1, den2), T);
-  fe16 ix0 = fe16_mul(g, X, I);
-  fe16 iy0 = fe16_mul(g, Y, I);
-  fe16 enchanted = fe16_mul(g, den1, fe16_from_fe(g, fe_const(BPG_K(K_INVSQRT_A_MINUS_D))));
-  bool rotate = fe16_to_fe(g, fe16_mul(g, T, z_inv)).v[0] & 1u;
+  fe16 den1 = fe16_mul<WIDE>(g, invsqrt, u1);
+  fe16 den2 = fe16_mul<WIDE>(g, invsqrt, u2);
+  fe16 z_inv = fe16_mul<WIDE>(g, fe16_mul<WIDE>(g, den1, den2), T);
+  fe16 ix0 = fe16_mul<WIDE>(g, X, I);
+  fe16 iy0 = fe16_mul<WIDE>(g, Y, I);
+  fe16 enchanted = fe16_mul<WIDE>(g, den1, fe16_from_fe(g, fe_const(BPG_K(K_INVSQRT_A_MINUS_D))));
+  bool rotate = fe16_to_fe(g, fe16_mul<WIDE>(g, T, z_inv)).v[0] & 1u;
   fe16 x = fe16_sel(rotate, iy0, X);
   fe16 y = fe16_sel(rotate, ix0, Y);
   fe16 den_inv = fe16_sel(rotate, enchanted, den2);
-  bool yneg = fe16_to_fe(g, fe16_mul(g, x, z_inv)).v[0] & 1u;
+  bool yneg = fe16_to_fe(g, fe16_mul<WIDE>(g, x, z_inv)).v[0] & 1u;
   y = fe16_sel(yneg, fe16_sub(g, zero, y), y);
-  fe16 s = fe16_mul(g, den_inv, fe16_sub(g, Z, y));
+  fe16 s = fe16_mul<WIDE>(g, den_inv, fe16_sub(g, Z, y));
   fe sc = fe16_to_fe(g, s);
   return fe_canon(fe_cneg(sc, sc.v[0] & 1u));
 }

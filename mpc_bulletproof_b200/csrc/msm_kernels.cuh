@@ -903,10 +903,9 @@ __global__ void __launch_bounds__(256) k_seg_point_ids(SegIds sg, uint32_t total
 // finishing: sum `nparts` partial sums per set (one per rank), encode
 // ---------------------------------------------------------------------------
 // parts layout: [part][set][32 words]
-// One HALF-WARP per set: the sum of the parts is computed redundantly by its sixteen lanes, the
-// encoding (one inverse square root, 252 dependent squarings) runs on the sixteen-lane field
-// layer of fe16.cuh.  Idle groups shadow the last set, so that every warp-wide exchange sees
-// all 32 lanes.
+// One WARP per set: the sum of the parts is computed redundantly by its lanes, the encoding (one
+// inverse square root, 252 dependent squarings) runs on the sixteen-lane field layer of fe16.cuh
+// in its whole-warp form (the half-warps split every product).
 constexpr int ENC_THREADS = 32;
 __device__ __forceinline__ void store_s_bytes(uint8_t* out, const fe& s, uint32_t k) {
   uint32_t w = 0;
@@ -916,17 +915,20 @@ __device__ __forceinline__ void store_s_bytes(uint8_t* out, const fe& s, uint32_
   out[2 * k] = (uint8_t)w;
   out[2 * k + 1] = (uint8_t)(w >> 8);
 }
+__device__ __forceinline__ grp16 warp_group(uint32_t* sm_of_warp) {
+  grp16 g;
+  g.sm = sm_of_warp;
+  g.k = threadIdx.x & 15u;
+  g.half = (threadIdx.x >> 4) & 1u;
+  g.par = 0;
+  return g;
+}
 __global__ void __launch_bounds__(ENC_THREADS) k_sum_encode(const uint32_t* __restrict__ parts, int nparts, int nsets,
                                                              uint8_t* __restrict__ out_bytes /*nsets*32*/,
                                                              uint32_t* __restrict__ out_ext /*nsets*32 words, may be null*/) {
-  __shared__ __align__(16) uint32_t sm[(ENC_THREADS / 16) * G16_WORDS];
-  uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-  bool live = gid < (uint32_t)nsets;
-  uint32_t set = live ? gid : (uint32_t)nsets - 1;
-  grp16 g;
-  g.sm = sm + (threadIdx.x >> 4) * G16_WORDS;
-  g.k = threadIdx.x & 15u;
-  g.par = 0;
+  __shared__ __align__(16) uint32_t sm[G16_WORDS];
+  const uint32_t set = blockIdx.x;  // grid = nsets
+  grp16 g = warp_group(sm);
   ge_ext acc;
   ge_load_ext(acc, parts + (size_t)set * 32);
   for (int p = 1; p < nparts; p++) {
@@ -934,10 +936,10 @@ __global__ void __launch_bounds__(ENC_THREADS) k_sum_encode(const uint32_t* __re
     ge_load_ext(o, parts + ((size_t)p * nsets + set) * 32);
     acc = ge_add(acc, o);
   }
-  if (out_ext && live && g.k == 0) ge_store_ext(out_ext + (size_t)set * 32, acc);
+  if (out_ext && threadIdx.x == 0) ge_store_ext(out_ext + (size_t)set * 32, acc);
   if (out_bytes) {
-    fe s = ge_encode16(g, acc);
-    if (live) store_s_bytes(out_bytes + (size_t)set * 32, s, g.k);
+    fe s = ge_encode16<true>(g, acc);
+    if (threadIdx.x < 16) store_s_bytes(out_bytes + (size_t)set * 32, s, g.k);
   }
 }
 
@@ -1030,24 +1032,20 @@ __global__ void __launch_bounds__(XCH_THREADS) k_exchange_sum_encode(const uint3
     if (threadIdx.x == 0) *status = 1;
     return;
   }
-  // 3. combine: one half-warp per set (the sum computed by each of its lanes, the encoding on
-  // sixteen lanes, fe16.cuh); partials read past the L1 (they were written by peers)
-  __shared__ __align__(16) uint32_t sm16[(XCH_THREADS / 16) * G16_WORDS];
-  grp16 g;
-  g.sm = sm16 + (threadIdx.x >> 4) * G16_WORDS;
-  g.k = threadIdx.x & 15u;
-  g.par = 0;
+  // 3. combine: one warp per set (the sum computed by each of its lanes, the encoding on the
+  // whole-warp form of fe16.cuh); partials read past the L1 (they were written by peers)
+  __shared__ __align__(16) uint32_t sm16[(XCH_THREADS / 32) * G16_WORDS];
+  grp16 g = warp_group(sm16 + (threadIdx.x >> 5) * G16_WORDS);
   const uint32_t* base = peers.parts[rank] + slot * slot_words;
-  for (int first = 0; first < nsets; first += XCH_THREADS / 16) {  // block-uniform trip count
-    int set = first + (int)(threadIdx.x >> 4);
-    bool live = set < nsets;
-    if (!live) set = nsets - 1;  // idle groups shadow the last set: the exchanges are warp-wide
+  for (int first = 0; first < nsets; first += XCH_THREADS / 32) {  // block-uniform trip count
+    int set = first + (int)(threadIdx.x >> 5);
+    if (set >= nsets) continue;  // whole warps drop out: the exchanges are warp-wide
     ge_ext acc = ge_load_ext_volatile(base + (size_t)set * 32);
     for (int p = 1; p < world; p++) acc = ge_add(acc, ge_load_ext_volatile(base + ((size_t)p * max_sets + set) * 32));
-    if (out_ext && live && g.k == 0) ge_store_ext(out_ext + (size_t)set * 32, acc);
+    if (out_ext && (threadIdx.x & 31) == 0) ge_store_ext(out_ext + (size_t)set * 32, acc);
     if (out_bytes) {
-      fe s = ge_encode16(g, acc);
-      if (live) store_s_bytes(out_bytes + (size_t)set * 32, s, g.k);
+      fe s = ge_encode16<true>(g, acc);
+      if ((threadIdx.x & 31) < 16) store_s_bytes(out_bytes + (size_t)set * 32, s, g.k);
     }
   }
 }
@@ -1187,9 +1185,8 @@ __global__ void __launch_bounds__(128) k_comb_mul_warp(const uint32_t* __restric
   }
   if (live && lane == 0 && out_ext) ge_store_ext(out_ext + (size_t)i * 32, acc);
   if (out_bytes) {
-    // the total sits in lane 0: hand it to every lane, encode on sixteen lanes (fe16.cuh; the
-    // upper half-warp shadows the lower one)
-    __shared__ __align__(16) uint32_t sm[(128 / 16) * G16_WORDS];
+    // the total sits in lane 0: hand it to every lane, encode on the whole warp (fe16.cuh)
+    __shared__ __align__(16) uint32_t sm[(128 / 32) * G16_WORDS];
 #pragma unroll
     for (int w = 0; w < 8; w++) {
       acc.X.v[w] = __shfl_sync(0xffffffffu, acc.X.v[w], 0);
@@ -1197,11 +1194,8 @@ __global__ void __launch_bounds__(128) k_comb_mul_warp(const uint32_t* __restric
       acc.Z.v[w] = __shfl_sync(0xffffffffu, acc.Z.v[w], 0);
       acc.T.v[w] = __shfl_sync(0xffffffffu, acc.T.v[w], 0);
     }
-    grp16 g;
-    g.sm = sm + (threadIdx.x >> 4) * G16_WORDS;
-    g.k = threadIdx.x & 15u;
-    g.par = 0;
-    fe s = ge_encode16(g, acc);
+    grp16 g = warp_group(sm + (threadIdx.x >> 5) * G16_WORDS);
+    fe s = ge_encode16<true>(g, acc);
     if (live && lane < 16) store_s_bytes(out_bytes + (size_t)i * 32, s, g.k);
   }
 }

@@ -131,33 +131,35 @@ int hs_msm(const uint8_t* scalars, const uint8_t* points, int n, int c, int chun
 // ---- sixteen-lane field layer (fe16.cuh): one host thread per lane ----
 struct Team16 {
   pthread_barrier_t bar;
-  uint32_t slots[16];
+  uint32_t slots[64];
   alignas(16) uint32_t sm[G16_WORDS];
 };
 template <class F>
-static void run16(F f) {
+static void run_lanes(int lanes, F f) {  // 16: one half-warp; 32: a whole warp (the WIDE form)
   Team16 t;
-  pthread_barrier_init(&t.bar, nullptr, 16);
-  std::thread th[16];
-  for (uint32_t k = 0; k < 16; k++)
-    th[k] = std::thread([&t, &f, k] {
+  pthread_barrier_init(&t.bar, nullptr, lanes);
+  std::vector<std::thread> th;
+  for (uint32_t k = 0; k < (uint32_t)lanes; k++)
+    th.emplace_back([&t, &f, k] {
       grp16 g;
-      g.sm = t.sm; g.k = k; g.par = 0; g.bar = &t.bar; g.slots = t.slots;
+      g.sm = t.sm; g.k = k & 15; g.half = k >> 4; g.par = 0; g.bar = &t.bar; g.slots = t.slots;
       f(g);
     });
   for (auto& x : th) x.join();
   pthread_barrier_destroy(&t.bar);
 }
+template <class F>
+static void run16(F f) { run_lanes(16, f); }
 extern "C" {
 // op 0: a*b, 1: a+b, 2: a-b, 3: (a*b)^(2^n) by n squarings of the product; limbs = the raw lazy limbs
 void hs_fe16_op(const uint32_t* a, const uint32_t* b, int op, int n, uint32_t* o, uint32_t* limbs) {
   fe A = ld(a), B = ld(b);
   run16([&](grp16& g) {
     fe16 x = fe16_from_fe(g, A), y = fe16_from_fe(g, B), r;
-    if (op == 0) r = fe16_mul(g, x, y);
+    if (op == 0) r = fe16_mul<false>(g, x, y);
     else if (op == 1) r = fe16_add(g, x, y);
     else if (op == 2) r = fe16_sub(g, x, y);
-    else { r = fe16_mul(g, x, y); for (int i = 0; i < n; i++) { r = fe16_sq(g, r); if (limbs[g.k] < r.l) limbs[g.k] = r.l; } }
+    else { r = fe16_mul<false>(g, x, y); for (int i = 0; i < n; i++) { r = fe16_sq<false>(g, r); if (limbs[g.k] < r.l) limbs[g.k] = r.l; } }
     if (op != 3) limbs[g.k] = r.l;
     fe c = fe16_to_fe(g, r);
     if (g.k == 5) st(o, c);
@@ -168,10 +170,10 @@ void hs_fe16_mix(const uint32_t* a, const uint32_t* b, uint32_t* o) {
   fe A = ld(a), B = ld(b);
   run16([&](grp16& g) {
     fe16 x = fe16_from_fe(g, A), y = fe16_from_fe(g, B);
-    fe16 m = fe16_mul(g, fe16_sub(g, x, y), fe16_add(g, x, y));
+    fe16 m = fe16_mul<false>(g, fe16_sub(g, x, y), fe16_add(g, x, y));
     fe16 d = fe16_sub(g, m, x);
     fe16 zero; zero.l = 0;
-    fe16 r = fe16_mul(g, fe16_sub(g, zero, d), fe16_sub(g, zero, d));
+    fe16 r = fe16_mul<false>(g, fe16_sub(g, zero, d), fe16_sub(g, zero, d));
     fe c = fe16_to_fe(g, r);
     if (g.k == 0) st(o, c);
   });
@@ -179,7 +181,7 @@ void hs_fe16_mix(const uint32_t* a, const uint32_t* b, uint32_t* o) {
 void hs_fe16_pow22523(const uint32_t* a, uint32_t* o) {
   fe A = ld(a);
   run16([&](grp16& g) {
-    fe c = fe16_to_fe(g, fe16_pow22523(g, fe16_from_fe(g, A)));
+    fe c = fe16_to_fe(g, fe16_pow22523<false>(g, fe16_from_fe(g, A)));
     if (g.k == 15) st(o, c);
   });
 }
@@ -190,8 +192,25 @@ void hs_from_uniform(const uint8_t* in64, uint8_t* out32) {
 void hs_encode16(const uint32_t* ext, uint8_t* b) {
   ge_ext e = lde(ext);
   run16([&](grp16& g) {
-    fe s = ge_encode16(g, e);
+    fe s = ge_encode16<false>(g, e);
     if (g.k == 3) fe_to_bytes(b, s);
+  });
+}
+// the whole-warp form: 32 lanes, the half-warps split every product
+void hs_encode32(const uint32_t* ext, uint8_t* b) {
+  ge_ext e = lde(ext);
+  run_lanes(32, [&](grp16& g) {
+    fe s = ge_encode16<true>(g, e);
+    if (g.k == 3 && g.half == 1) fe_to_bytes(b, s);
+  });
+}
+void hs_fe16_wide_chain(const uint32_t* a, const uint32_t* b, int n, uint32_t* o, uint32_t* limbs) {
+  fe A = ld(a), B = ld(b);
+  run_lanes(32, [&](grp16& g) {
+    fe16 r = fe16_mul<true>(g, fe16_from_fe(g, A), fe16_from_fe(g, B));
+    for (int i = 0; i < n; i++) { r = fe16_sq<true>(g, r); if (g.half == 0 && limbs[g.k] < r.l) limbs[g.k] = r.l; }
+    fe c = fe16_to_fe(g, r);
+    if (g.k == 0 && g.half == 0) st(o, c);
   });
 }
 }

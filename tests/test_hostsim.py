@@ -175,6 +175,11 @@ def test_field_on_sixteen_lanes(hs):
         hs.hs_fe16_op(tol(a), tol(b), 3, 40, o, limbs)  # 40 squarings of the product: bounds are a fixed point
         assert frl(o) == pow(a * b, 2**40, G.P)
         assert limbs[0] < 2**22 and all(limbs[k] < 2**18 for k in range(1, 16))
+    for a, b in [(2**255 - 1, 2**255 - 1), (r.getrandbits(255), r.getrandbits(255)), (1, 0)]:
+        limbs = U16()
+        hs.hs_fe16_wide_chain(tol(a), tol(b), 25, o, limbs)  # whole-warp products: same values, same bounds
+        assert frl(o) == pow(a * b, 2**25, G.P)
+        assert limbs[0] < 2**22 and all(limbs[k] < 2**18 for k in range(1, 16))
     for a in [3, G.P - 2, r.getrandbits(255)]:
         hs.hs_fe16_pow22523(tol(a), o)
         assert frl(o) == pow(a, 2**252 - 3, G.P)
@@ -198,6 +203,10 @@ def test_encode_on_sixteen_lanes(hs):
             hs.hs_encode16(e, o)
             hs.hs_encode(e, o1)
             assert bytes(o) == want == bytes(o1)
+            if i in (0, 1, 7, 16, 17, 18):  # 32 host threads per run: keep the CPU suite short
+                o2 = B32()
+                hs.hs_encode32(e, o2)  # whole-warp form: the half-warps split every product
+                assert bytes(o2) == want
 
 
 def test_element_derivation(hs):
