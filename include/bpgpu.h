@@ -252,6 +252,11 @@ int bpg_r1cs_dev_reserve(bpg_r1cs_dev** st, size_t capacity);
 int bpg_r1cs_dev_commit(bpg_r1cs_dev* st, const bpg_table* gens, size_t g_base, size_t h_base, size_t bb_id,
                         size_t first, size_t cnt, const void* aL, const void* aR, const void* aO, uint64_t vec_key,
                         const uint8_t blind3[96], uint8_t out[96]);
+/* same with s_L, s_R expanded from a 256-bit key: ChaCha20 (RFC 8439) blocks 2j, 2j+1 under vec_key with
+ * nonce "bpg sLsR v01", each 64-byte block reduced mod l -- the production form (bpg_prover_prove) */
+int bpg_r1cs_dev_commit_keyed(bpg_r1cs_dev* st, const bpg_table* gens, size_t g_base, size_t h_base, size_t bb_id,
+                              size_t first, size_t cnt, const void* aL, const void* aR, const void* aO,
+                              const uint8_t vec_key[32], const uint8_t blind3[96], uint8_t out[96]);
 /* Page-locked host memory for buffers the library reads repeatedly (witness rows, constraint
  * terms): uploads from it run at PCIe rate.  Falls back to malloc when pinning fails. */
 void* bpg_host_alloc(size_t bytes);
@@ -334,6 +339,16 @@ void bpg_transcript_append_u64(bpg_transcript* t, const char* label, uint64_t v)
 void bpg_transcript_challenge_bytes(bpg_transcript* t, const char* label, uint8_t* out, size_t len);
 void bpg_transcript_challenge_scalar(bpg_transcript* t, const char* label, uint8_t out[32]);
 
+/* merlin::TranscriptRngBuilder / TranscriptRng (the prover's blinding source, reference
+ * src/r1cs/prover.rs:435-445): build_rng clones the transcript state; rekey binds witness bytes;
+ * finalize mixes in 32 bytes of external randomness; fill_bytes squeezes. */
+typedef struct bpg_transcript_rng bpg_transcript_rng;
+bpg_transcript_rng* bpg_transcript_build_rng(const bpg_transcript* t);
+void bpg_transcript_rng_rekey_with_witness_bytes(bpg_transcript_rng* r, const char* label, const uint8_t* witness, size_t len);
+void bpg_transcript_rng_finalize(bpg_transcript_rng* r, const uint8_t random_bytes[32]);
+void bpg_transcript_rng_fill_bytes(bpg_transcript_rng* r, uint8_t* out, size_t len);
+void bpg_transcript_rng_free(bpg_transcript_rng* r);
+
 /* ---- generators: PedersenGens{B, B_blinding} + BulletproofGens party 0 (reference
  * src/generators.rs:32-71,158-235) uploaded once as ONE windowed table
  * [G (capacity) | H (capacity) | B | B_blinding] plus a comb for (B, B_blinding). */
@@ -406,12 +421,32 @@ int bpg_gadget_square_chain(bpg_cs* cs, bpg_var var, size_t n, bpg_var* out);
 int bpg_gadget_random_circuit(bpg_cs* cs, uint64_t seed, size_t n_mult, size_t n_cons, uint8_t* c0);
 size_t bpg_cs_num_multipliers(const bpg_cs* cs);
 size_t bpg_cs_num_constraints(const bpg_cs* cs);
-/* Prover::prove.  The reference draws its blinding scalars from thread_rng()
- * (prover.rs:435-445); here they come from xoshiro256** seeded with rng_seed, in the same
- * draw order, so that proofs are reproducible.  BPG_ERR_CAPACITY = InvalidGeneratorsLength. */
-int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
-/* Verifier::verify: BPG_OK, BPG_ERR_VERIFY, BPG_ERR_DECODE (FormatError), BPG_ERR_CAPACITY */
+/* Prover::prove (prover.rs:412-727).  BPG_ERR_CAPACITY = InvalidGeneratorsLength.
+ * Blinding scalars as in the reference (prover.rs:435-445): a merlin TranscriptRng forked from the
+ * transcript after "m", rekeyed with every v_blinding and finalized with 32 bytes of external
+ * randomness, drawn in the reference's order (:457-462, 519-530, 621-625).  The two blinding vectors
+ * of a phase, s_L and s_R, are expanded on the device from ONE 32-byte draw of that RNG (ChaCha20
+ * blocks 2j / 2j+1 reduced mod l) instead of 2n sequential draws.
+ *   bpg_prover_prove                 the 32 bytes come from the operating system (getrandom): THE entry
+ *                                    point for production use;
+ *   bpg_prover_prove_with_rng_bytes  the caller supplies them (its own CSPRNG; fixed bytes make the
+ *                                    proof reproducible -- parity tests);
+ *   bpg_prover_prove_deterministic   TEST / BENCH ONLY: every blinding from xoshiro256**(rng_seed), a
+ *                                    64-bit non-cryptographic seed.  Reusing a seed leaks the witness. */
+int bpg_prover_prove(bpg_cs* cs, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+int bpg_prover_prove_with_rng_bytes(bpg_cs* cs, const uint8_t rng_bytes[32], uint8_t* proof_out, size_t proof_cap,
+                                    size_t* proof_len);
+int bpg_prover_prove_deterministic(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_out, size_t proof_cap,
+                                   size_t* proof_len);
+/* Verifier::verify: BPG_OK, BPG_ERR_VERIFY, BPG_ERR_DECODE (FormatError), BPG_ERR_CAPACITY.
+ * bpg_verifier_verify derives the scalar r that batches the t(x) check with the inner-product check
+ * as the mounted fork does, r = challenge_scalar("r") (verifier.rs:506): a public function of the
+ * transcript.  bpg_verifier_verify_with_rng_bytes draws r from a TranscriptRng finalized with 32 bytes
+ * the prover cannot know (rng_bytes; NULL = from the operating system), as upstream's
+ * `build_rng().finalize(&mut thread_rng())` does: same accept set, and r is unpredictable to whoever
+ * produced the proof.  Use it whenever proofs come from an untrusted party. */
 int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof, size_t proof_len);
+int bpg_verifier_verify_with_rng_bytes(bpg_cs* cs, const uint8_t* proof, size_t proof_len, const uint8_t* rng_bytes);
 /* Many proofs, proof by proof as the reference does (verifier.rs:393); every verifier is consumed.
  * ok[i] = 1 iff proof i verifies (a malformed proof is a reject).  Non-zero return only for
  * failures of the machinery.  Across GPUs whole proofs are sharded by the caller (one context

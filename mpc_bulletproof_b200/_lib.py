@@ -46,6 +46,11 @@ _SIGNATURES = {
     "bpg_transcript_append_u64": (None, [_P, _CP, _U64]),
     "bpg_transcript_challenge_bytes": (None, [_P, _CP, _P, _SZ]),
     "bpg_transcript_challenge_scalar": (None, [_P, _CP, _P]),
+    "bpg_transcript_build_rng": (_P, [_P]),
+    "bpg_transcript_rng_rekey_with_witness_bytes": (None, [_P, _CP, _P, _SZ]),
+    "bpg_transcript_rng_finalize": (None, [_P, _P]),
+    "bpg_transcript_rng_fill_bytes": (None, [_P, _P, _SZ]),
+    "bpg_transcript_rng_free": (None, [_P]),
     "bpg_gens_new": (_I, [_P, _P, _P, _SZ, _P, _P, ctypes.POINTER(_P)]),
     "bpg_points_from_uniform": (_I, [_P, _P, _SZ, _P]),
     "bpg_gens_chain": (_I, [_P, _P, _SZ, _SZ, _SZ, _P]),
@@ -74,8 +79,11 @@ _SIGNATURES = {
     "bpg_gadget_random_circuit": (_I, [_P, ctypes.c_uint64, _SZ, _SZ, _P]),
     "bpg_gadget_square_chain": (_I, [_P, ctypes.c_uint64, _SZ, ctypes.POINTER(ctypes.c_uint64)]),
     "bpg_cs_num_constraints": (_SZ, [_P]),
-    "bpg_prover_prove": (_I, [_P, _U64, _P, _SZ, ctypes.POINTER(_SZ)]),
+    "bpg_prover_prove": (_I, [_P, _P, _SZ, ctypes.POINTER(_SZ)]),
+    "bpg_prover_prove_with_rng_bytes": (_I, [_P, _P, _P, _SZ, ctypes.POINTER(_SZ)]),
+    "bpg_prover_prove_deterministic": (_I, [_P, _U64, _P, _SZ, ctypes.POINTER(_SZ)]),
     "bpg_verifier_verify": (_I, [_P, _P, _SZ]),
+    "bpg_verifier_verify_with_rng_bytes": (_I, [_P, _P, _SZ, _P]),
     "bpg_batch_verify": (_I, [_P, _P, _P, _SZ, _P]),
     "bpg_init": (_I, [_I, ctypes.POINTER(_P)]),
     "bpg_free": (None, [_P]),
@@ -122,6 +130,7 @@ _SIGNATURES = {
     "bpg_r1cs_dev_reserve": (_I, [ctypes.POINTER(_P), _SZ]),
     "bpg_ipp_verify_msm": (_I, [_P, _P, _SZ, _P, _SZ, _P, _P, _SZ, _P, _P, _P, _P]),
     "bpg_r1cs_dev_commit": (_I, [_P, _P, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, ctypes.c_uint64, _P, _P]),
+    "bpg_r1cs_dev_commit_keyed": (_I, [_P, _P, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P, _P, _P, _P, _P]),
     "bpg_host_alloc": (_P, [_SZ]),
     "bpg_host_free": (None, [_P]),
     "bpg_r1cs_dev_flatten": (_I, [_P, _SZ, _SZ, _SZ, _P, _P, _P, _P, _P]),

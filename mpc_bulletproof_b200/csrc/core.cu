@@ -1,90 +1,9 @@
-// libbpgpu: C ABI (include/bpgpu.h) over the sm_100a kernels.
-#include "../../include/bpgpu.h"
-
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <mutex>
-#include <new>
-#include <unordered_map>
-#include <vector>
-
-#include "msm_kernels.cuh"
-#include "ipp_kernels.cuh"
-#include "svec_kernels.cuh"
-#include "stark_msm.cuh"
-#include "ipp_kernels_t.cuh"
+// libbpgpu: context, memory, tables, fixed-base comb, peer exchange and the host-buffer MSM entry points
+// of the C ABI (include/bpgpu.h).  The Pippenger launch itself is msm.cu.
+#include "internal.cuh"
+#include "point_kernels.cuh"
 
 using namespace bpg;
-
-// ---------------------------------------------------------------------------
-// context
-// ---------------------------------------------------------------------------
-struct bpg_ctx {
-  int device = 0;
-  cudaStream_t own_stream = nullptr;
-  cudaStream_t stream = nullptr;
-  int last_cuda = 0;
-  uint64_t launches = 0;
-  int forced_c = 0;
-  int forced_gsub = 0;  // BPG_MSM_GSUB: bucket groups per set on windowed tables (tuning)
-  int sm_count = 148;
-  // per-phase device timing (bpg_profile_*): events are recorded on the launch stream
-  bool prof = false;
-  std::vector<cudaEvent_t> prof_ev;   // pool
-  std::vector<int> prof_phase;        // phase id of interval [ev[i], ev[i+1])
-  size_t prof_used = 0;
-  double prof_ms[BPG_PROF_NPHASE] = {0};
-  uint64_t prof_n[BPG_PROF_NPHASE] = {0};
-  // workspace arenas (grown on demand, reused across calls): [0] for the launch stream, [1] for the
-  // auxiliary stream that runs a small independent MSM beside the main one (verifier: proof points)
-  uint8_t* ws = nullptr;
-  size_t ws_cap = 0;
-  uint8_t* ws_aux = nullptr;
-  size_t ws_aux_cap = 0;
-  cudaStream_t aux_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  cudaEvent_t ev_chunk[8] = {};  // scalar upload in pieces (host_feed), created on first use
-  // transient-allocation cache (dev_alloc / dev_free)
-  std::vector<std::pair<void*, size_t>> cache;
-  std::unordered_map<void*, size_t> live;
-  // small staging buffers
-  uint8_t* d_small = nullptr;   // device scratch for results (>= 64 KB)
-  uint8_t* h_pinned = nullptr;  // pinned host scratch (>= 64 KB)
-  // staging for host-buffer calls
-  uint8_t* d_stage = nullptr;
-  size_t d_stage_cap = 0;
-};
-
-struct bpg_table {
-  bpg_ctx* ctx;
-  uint32_t* niels;  // n * 24 words; windowed: [W][n] * 24 words
-  size_t n;
-  int win_c = 0;    // 0: plain; otherwise the window width the multiples 2^(c w) P_i were built for
-  int win_W = 1;
-};
-
-#define CK(call)                                  \
-  do {                                            \
-    cudaError_t e_ = (call);                      \
-    if (e_ != cudaSuccess) {                      \
-      ctx->last_cuda = (int)e_;                   \
-      return BPG_ERR_CUDA;                        \
-    }                                             \
-  } while (0)
-
-#define LAUNCH_CHECK()                            \
-  do {                                            \
-    ctx->launches++;                              \
-    cudaError_t e_ = cudaGetLastError();          \
-    if (e_ != cudaSuccess) {                      \
-      ctx->last_cuda = (int)e_;                   \
-      return BPG_ERR_CUDA;                        \
-    }                                             \
-  } while (0)
 
 // Transient device memory (tables, proof states).  Freed blocks are parked in a small per-context
 // cache and handed out again (best fit within 4x) before falling back to the device's stream-ordered
@@ -92,7 +11,7 @@ struct bpg_table {
 // milliseconds at these sizes) may sit on that path.  Everything a context allocates is used on its
 // launch stream (the auxiliary lane is fenced by events), so reuse is ordered by the stream.
 static constexpr size_t CACHE_SLOTS = 24;
-static cudaError_t dev_alloc(bpg_ctx* ctx, void** p, size_t bytes) {
+cudaError_t dev_alloc(bpg_ctx* ctx, void** p, size_t bytes) {
   bytes = std::max<size_t>((bytes + 255) / 256 * 256, 256);
   int best = -1;
   for (size_t i = 0; i < ctx->cache.size(); i++) {
@@ -109,11 +28,7 @@ static cudaError_t dev_alloc(bpg_ctx* ctx, void** p, size_t bytes) {
   if (e == cudaSuccess) ctx->live[*p] = bytes;
   return e;
 }
-template <typename T>
-static cudaError_t dev_alloc(bpg_ctx* ctx, T** p, size_t bytes) {
-  return dev_alloc(ctx, reinterpret_cast<void**>(p), bytes);
-}
-static void dev_free(bpg_ctx* ctx, void* p) {
+void dev_free(bpg_ctx* ctx, void* p) {
   if (!p) return;
   auto it = ctx->live.find(p);
   size_t sz = it == ctx->live.end() ? 0 : it->second;
@@ -129,7 +44,6 @@ static void dev_free(bpg_ctx* ctx, void* p) {
   }
 }
 
-static constexpr size_t SMALL_BYTES = 1 << 16;
 
 extern "C" int bpg_init(int device, bpg_ctx** out) {
   if (!out) return BPG_ERR_ARG;
@@ -148,8 +62,7 @@ extern "C" int bpg_init(int device, bpg_ctx** out) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_small, SMALL_BYTES);
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_pinned, SMALL_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_reduce_pairs_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RPB_SMEM);
+  if (e == cudaSuccess) e = msm_kernels_init();
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) {
     delete ctx;
@@ -196,12 +109,20 @@ extern "C" void bpg_free(bpg_ctx* ctx) {
 
 extern "C" int bpg_set_stream(bpg_ctx* ctx, void* s, int use_own) {
   if (!ctx) return BPG_ERR_ARG;
-  ctx->stream = use_own ? ctx->own_stream : (cudaStream_t)s;
+  cudaStream_t next = use_own ? ctx->own_stream : (cudaStream_t)s;
+  if (next != ctx->stream) {
+    // the arenas, the staging buffers and the block cache are ordered by the launch stream: work already
+    // enqueued on the old stream must finish before anything on the new one may reuse them
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(next, ctx->ev_fork, 0));
+  }
+  ctx->stream = next;
   return BPG_OK;
 }
 
 // ---- per-phase profiling ---------------------------------------------------
-static void prof_mark(bpg_ctx* ctx, int phase) {
+void prof_mark(bpg_ctx* ctx, int phase) {
   // closes the previous interval and opens one attributed to `phase` (-1 = close only)
   if (!ctx->prof) return;
   if (ctx->prof_used == ctx->prof_ev.size()) {
@@ -354,7 +275,7 @@ extern "C" const char* bpg_strerror(int code) {
   }
 }
 
-static int ensure_ws(bpg_ctx* ctx, size_t bytes, int lane = 0) {
+int ensure_ws(bpg_ctx* ctx, size_t bytes, int lane) {
   uint8_t*& ws = lane ? ctx->ws_aux : ctx->ws;
   size_t& cap = lane ? ctx->ws_aux_cap : ctx->ws_cap;
   if (bytes <= cap) return BPG_OK;
@@ -372,7 +293,7 @@ static int ensure_ws(bpg_ctx* ctx, size_t bytes, int lane = 0) {
   cap = want;
   return BPG_OK;
 }
-static int ensure_stage(bpg_ctx* ctx, size_t bytes) {
+int ensure_stage(bpg_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->d_stage_cap) return BPG_OK;
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->d_stage) cudaFree(ctx->d_stage);
@@ -448,355 +369,6 @@ extern "C" void bpg_table_free(bpg_table* t) {
   dev_free(t->ctx, t->niels);  // stream-ordered: work already enqueued on the table finishes first
   delete t;
 }
-
-// ---------------------------------------------------------------------------
-// MSM launch
-// ---------------------------------------------------------------------------
-// Plain tables: every window has its own bucket array, reduced separately, then Horner.
-static int pick_window(size_t n_per_set, int forced) {
-  if (forced >= 2) return forced;
-  double best = 1e300;
-  int best_c = 4;
-  for (int c = 3; c <= 20; c++) {
-    int W = (255 + c - 1) / c;
-    double nb = (double)(1u << (c - 1));
-    // mixed adds (7M) for the terms, ~20M per bucket in the reduction tree
-    double cost = W * ((double)n_per_set * 7.0 + nb * 20.0);
-    if (cost < best) {
-      best = cost;
-      best_c = c;
-    }
-  }
-  return best_c;
-}
-// Windowed tables: all windows share one bucket array per set.  Lists of ~32 entries keep the
-// accumulation efficient; shorter lists only add merge work.
-static uint32_t pick_gsub(size_t n_per_set, int nsets, int c, int W) {
-  double nb = (double)(1u << (c - 1));
-  double lists_for_len = (double)n_per_set * W / (nb * 32.0);       // groups that make the lists ~32 long
-  double lists_for_par = (double)(1u << 17) / (nb * (double)nsets);  // groups that give ~2^17 lists (more only add merge work)
-  double avg1 = (double)n_per_set * W / nb;                          // list length with one group
-  double g = std::max(lists_for_len, std::min(lists_for_par, avg1 / 8.0));  // never below ~8 entries per list
-  uint32_t gs = (uint32_t)(g + 0.5);
-  return std::min<uint32_t>(std::max<uint32_t>(gs, 1), (uint32_t)W);
-}
-static int pick_window_table(size_t n, int forced) {
-  if (forced >= 2) return forced;
-  double best = 1e300;
-  int best_c = 4;
-  for (int c = 3; c <= 20; c++) {
-    int W = (255 + c - 1) / c;
-    double nb = (double)(1u << (c - 1));
-    uint32_t gs = pick_gsub(n, 1, c, W);
-    double cost = (double)W * n * 7.0 + (gs > 1 ? gs * nb * 8.0 : 0.0) + nb * 20.0;
-    if (cost < best) {
-      best = cost;
-      best_c = c;
-    }
-  }
-  return best_c;
-}
-
-static sc_bias bias_for(int c);
-static void make_cfg(MsmCfg& cfg, size_t n_terms, size_t n_points, int nsets, int c, size_t win_stride, int forced_gsub) {
-  cfg.win_stride = (uint32_t)win_stride;
-  cfg.c = c;
-  cfg.W = (255 + c - 1) / c;
-  cfg.nb = 1u << (c - 1);
-  cfg.nsets = nsets;
-  cfg.n_terms = (uint32_t)n_terms;
-  cfg.n_points = (uint32_t)std::max<size_t>(n_points, 1);
-  if (win_stride) {
-    cfg.gsub = forced_gsub > 0 ? std::min<uint32_t>((uint32_t)forced_gsub, (uint32_t)cfg.W)
-                               : pick_gsub((n_terms + nsets - 1) / nsets, nsets, c, cfg.W);
-  } else {
-    cfg.gsub = (uint32_t)cfg.W;
-  }
-  cfg.narr = (uint32_t)nsets * cfg.gsub;
-  cfg.B = cfg.narr * cfg.nb;
-  // segments of over-long buckets (> BIG_SEG entries): at most two per BIG_SEG entries
-  cfg.big_cap = (uint32_t)(2 * ((uint64_t)n_terms * cfg.W / BIG_SEG) + 2);
-  memset(&cfg.bias, 0, sizeof(cfg.bias));
-  for (int w = 0; w < cfg.W; w++) {
-    int bit = c * w + c - 1;
-    cfg.bias.v[bit >> 5] |= 1u << (bit & 31);
-  }
-}
-
-static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
-
-// Enqueue one Pippenger launch.  d_scalars: n_terms*32 B; d_set_ids / d_point_ids may
-// be null (implicit: term t -> point t % n_points of `table_base`, set t / n_points).
-static int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points, const uint32_t* d_scalars,
-                       size_t n_terms, const uint8_t* d_set_ids, const uint32_t* d_point_ids, int nsets,
-                       uint32_t* d_out_ext, int win_c = 0, size_t win_stride = 0, int lane = 0, int curve = 0,
-                       const uint8_t* h_scalars = nullptr /*scalars still on the host: uploaded here, in pieces*/) {
-  // curve 0: ristretto255 (Niels table, 24 words per entry); curve 1: Stark curve (affine table, 16 words
-  // per entry, plain tables only).  Sort and schedule are shared; the bucket arithmetic differs.
-  if (nsets <= 0) return BPG_ERR_ARG;
-  // lane 1: the auxiliary stream and arena (no phase profiling there)
-  struct ProfOff {
-    bpg_ctx* c;
-    bool saved;
-    ProfOff(bpg_ctx* c_, bool off) : c(c_), saved(c_->prof) { if (off) c->prof = false; }
-    ~ProfOff() { c->prof = saved; }
-  } prof_off(ctx, lane != 0);
-  cudaStream_t st = lane ? ctx->aux_stream : ctx->stream;
-  uint8_t* const& ws = lane ? ctx->ws_aux : ctx->ws;
-  if (n_terms == 0) {
-    // empty sum: identity for every set
-    if (curve == 1) k_stark_set_identity<<<nsets, 32, 0, st>>>(d_out_ext);
-    else k_set_identity<<<nsets, 32, 0, st>>>(d_out_ext);
-    LAUNCH_CHECK();
-    return BPG_OK;
-  }
-  if (n_terms >= (1u << 31)) return BPG_ERR_ARG;
-  if (curve == 0 && win_c == 0 && n_terms <= SMALL_MAX_TERMS && nsets <= SMALL_MAX_SETS && ctx->forced_c < 2) {
-    // a handful of terms over a plain table: one quad per term walks the doubling chain (k_msm_small);
-    // a forced window width (bpg_set_window) keeps the bucket pipeline, which is how the tests reach it
-    if (h_scalars) CK(cudaMemcpyAsync((void*)d_scalars, h_scalars, n_terms * 32, cudaMemcpyHostToDevice, st));
-    unsigned nblk = (unsigned)((n_terms + SMALL_QUADS - 1) / SMALL_QUADS);
-    prof_mark(ctx, BPG_PROF_ACCUM);
-    if (nblk == 1) {
-      k_msm_small<<<1, SMALL_THREADS, 0, st>>>(table_base, d_scalars, d_set_ids, d_point_ids, (uint32_t)n_terms,
-                                               (uint32_t)std::max<size_t>(n_points, 1), nsets, bias_for(4), d_out_ext);
-      LAUNCH_CHECK();
-    } else {
-      int rc = ensure_ws(ctx, (size_t)nblk * nsets * 128, lane);
-      if (rc) return rc;
-      uint32_t* parts = (uint32_t*)ws;
-      k_msm_small<<<nblk, SMALL_THREADS, 0, st>>>(table_base, d_scalars, d_set_ids, d_point_ids, (uint32_t)n_terms,
-                                                  (uint32_t)std::max<size_t>(n_points, 1), nsets, bias_for(4), parts);
-      LAUNCH_CHECK();
-      k_msm_small_fin<<<1, SMALL_THREADS, 0, st>>>(parts, nblk, nsets, d_out_ext);
-      LAUNCH_CHECK();
-    }
-    prof_mark(ctx, -1);
-    return BPG_OK;
-  }
-  MsmCfg cfg;
-  int c = win_c ? win_c : pick_window((n_terms + nsets - 1) / nsets, ctx->forced_c);
-  make_cfg(cfg, n_terms, n_points, nsets, c, win_c ? win_stride : 0, ctx->forced_gsub);
-  if ((uint64_t)cfg.narr * cfg.nb >= (1ull << 31)) return BPG_ERR_ARG;
-  const bool windowed = cfg.win_stride != 0;
-
-  // reduction geometry: `rarr` arrays of nb buckets.  Small arrays: a leaf block of RT_QUADS quad
-  // chunks of LC buckets plus its in-block tree; large arrays: one thread per chunk of 16.
-  uint32_t rarr = windowed ? (uint32_t)nsets : cfg.narr;
-  // (measured at 2 x 2^16 buckets, an IPP round at n = 2^16: quad chunks of 8 and thread chunks of 4 tie,
-  // thread chunks of 8 / 16 and quad chunks of 4 are 2-11 % of a proof slower; gpurun_out/r1i_tune.jsonl)
-  const bool thread_leaf = cfg.nb >= (1u << 17);
-  const uint32_t LC = thread_leaf ? 16 : (cfg.nb > (1u << 15) ? 8 : 4);
-  uint32_t tiles0 = thread_leaf ? (cfg.nb + LC - 1) / LC : (cfg.nb + RT_QUADS * LC - 1) / (RT_QUADS * LC);
-  size_t ntiles = (cfg.B + SCAN_TILE - 1) / SCAN_TILE;
-  size_t off = 0;
-  // counts and the schedule's control words are adjacent: ONE memset per launch
-  size_t o_counts = off;  off += align_up((size_t)cfg.B * 4);
-  size_t o_bins = off;    off += align_up((2 * SIZE_BINS + 4) * 4);  // bins | n_items, part, multi, big_count | cursors
-  size_t o_offsets = off; off += align_up(((size_t)cfg.B + 1) * 4);
-  size_t o_tiles = off;   off += align_up(ntiles * 4);
-  size_t o_big = off;     off += align_up(3 * (size_t)cfg.big_cap * 4);
-  size_t o_bigpart = off; off += align_up((size_t)cfg.big_cap * 128);
-  size_t o_entries = off; off += align_up((size_t)n_terms * cfg.W * 4);
-  size_t o_buckets = off; off += align_up((size_t)cfg.B * 128);
-  size_t o_merged = off;  off += (windowed && cfg.gsub > 1) ? align_up((size_t)nsets * cfg.nb * 128) : 0;
-  if (curve == 1) {
-    rarr = windowed ? (uint32_t)nsets : cfg.narr;
-    tiles0 = (cfg.nb + SLEAF_LC - 1) / SLEAF_LC;
-  }
-  size_t o_pairs = off;   off += 4 * align_up((size_t)rarr * tiles0 * 128);  // (A, Y) x ping-pong
-  size_t o_wins = off;    off += align_up((size_t)rarr * 128);
-  // accumulation schedule: at most one item per bucket plus one per ACC_SEG entries
-  size_t max_items = (size_t)cfg.B + (size_t)n_terms * cfg.W / ACC_SEG + 1;
-  size_t max_multi = (size_t)n_terms * cfg.W / ACC_SEG + 1;  // buckets longer than ACC_SEG
-  size_t o_items = off;   off += align_up(max_items * 8);
-  size_t o_segslot = off; off += align_up((size_t)cfg.B * 4);
-  size_t o_multi = off;   off += align_up(max_multi * 4);
-  size_t o_segpart = off; off += align_up(2 * max_multi * 128);  // sum of nseg over multi-segment buckets <= 2 max_multi
-  int rc = ensure_ws(ctx, off, lane);
-  if (rc) return rc;
-  uint32_t* counts = (uint32_t*)(ws + o_counts);
-  uint32_t* offsets = (uint32_t*)(ws + o_offsets);
-  uint32_t* tiles = (uint32_t*)(ws + o_tiles);
-  uint32_t* big_list = (uint32_t*)(ws + o_big);
-  uint32_t* big_part = (uint32_t*)(ws + o_bigpart);
-  uint32_t* entries = (uint32_t*)(ws + o_entries);
-  uint32_t* buckets = (uint32_t*)(ws + o_buckets);
-  uint32_t* merged = (uint32_t*)(ws + o_merged);
-  size_t pair_words = align_up((size_t)rarr * tiles0 * 128) / 4;
-  uint32_t* pairs = (uint32_t*)(ws + o_pairs);
-  uint32_t* wins = (uint32_t*)(ws + o_wins);
-  uint32_t* bins = (uint32_t*)(ws + o_bins);
-  AccSched sched;
-  uint32_t* big_count = bins + SIZE_BINS + 3;
-  sched.bins = bins;
-  sched.cursors = bins + SIZE_BINS + 4;
-  sched.n_items = bins + SIZE_BINS;
-  sched.part_count = bins + SIZE_BINS + 1;
-  sched.multi_count = bins + SIZE_BINS + 2;
-  sched.items = (uint2*)(ws + o_items);
-  sched.seg_slot = (uint32_t*)(ws + o_segslot);
-  sched.multi_list = (uint32_t*)(ws + o_multi);
-  uint32_t* seg_part = (uint32_t*)(ws + o_segpart);
-
-  prof_mark(ctx, BPG_PROF_HIST);
-  CK(cudaMemsetAsync(counts, 0, o_bins - o_counts + (2 * SIZE_BINS + 4) * 4, st));
-  unsigned gt = (unsigned)((n_terms + 255) / 256);
-  if (h_scalars && lane == 0 && n_terms >= (1u << 18)) {
-    // Host scalars: the copy runs on the auxiliary stream in pieces and the digit histogram of
-    // piece i runs while piece i+1 is still on the bus (hides the 0.12 ms histogram of a 2^20-term
-    // launch; measured against one copy on two boxes: 2.26-2.45 vs 2.39-2.62 ms end to end, the
-    // spread being the PCIe rate of the box).
-    const int pieces = 4;
-    size_t per = (((n_terms + pieces - 1) / pieces) + 255) / 256 * 256;
-    CK(cudaEventRecord(ctx->ev_fork, st));  // d_scalars (staging) is free once earlier work is done
-    CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
-    for (int i = 0; i < pieces; i++) {
-      size_t t0 = (size_t)i * per, t1 = std::min(n_terms, t0 + per);
-      if (t0 >= t1) break;
-      if (!ctx->ev_chunk[i]) CK(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
-      CK(cudaMemcpyAsync((uint8_t*)d_scalars + t0 * 32, h_scalars + t0 * 32, (t1 - t0) * 32, cudaMemcpyHostToDevice,
-                         ctx->aux_stream));
-      CK(cudaEventRecord(ctx->ev_chunk[i], ctx->aux_stream));
-      CK(cudaStreamWaitEvent(st, ctx->ev_chunk[i], 0));
-      k_hist<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, st>>>(d_scalars, d_set_ids, cfg, counts, (uint32_t)t0, (uint32_t)t1);
-      LAUNCH_CHECK();
-    }
-  } else {
-    if (h_scalars) CK(cudaMemcpyAsync((void*)d_scalars, h_scalars, n_terms * 32, cudaMemcpyHostToDevice, st));
-    k_hist<<<gt, 256, 0, st>>>(d_scalars, d_set_ids, cfg, counts, 0u, (uint32_t)n_terms);
-    LAUNCH_CHECK();
-  }
-  prof_mark(ctx, BPG_PROF_SCAN);
-  k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.B, tiles);
-  LAUNCH_CHECK();
-  k_scan_spine<<<1, 1024, 0, st>>>(tiles, (uint32_t)ntiles, offsets, cfg.B);
-  LAUNCH_CHECK();
-  k_scan_apply<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.B, tiles, offsets, bins);
-  LAUNCH_CHECK();
-  prof_mark(ctx, BPG_PROF_SCATTER);
-  k_scatter<<<gt, 256, 0, st>>>(d_scalars, d_set_ids, d_point_ids, cfg, offsets, counts, entries);
-  LAUNCH_CHECK();
-  // accumulation schedule: (bucket, segment) items by decreasing length; over-long buckets -> big list
-  k_size_scatter<<<(cfg.B + 255) / 256, 256, 0, st>>>(offsets, cfg, sched, big_count, big_list);
-  LAUNCH_CHECK();
-  if (curve == 1) {
-    // ---- Stark-curve policy: same stages, short-Weierstrass bucket arithmetic (stark_msm.cuh) ----
-    prof_mark(ctx, BPG_PROF_ACCUM);
-    k_stark_accum<<<(unsigned)((max_items + SACC_THREADS - 1) / SACC_THREADS), SACC_THREADS, 0, st>>>(
-        table_base, offsets, entries, sched, buckets, seg_part);
-    LAUNCH_CHECK();
-    prof_mark(ctx, BPG_PROF_ACCUM_BIG);
-    k_stark_fix<<<(unsigned)std::min<size_t>((max_multi + 127) / 128, (size_t)ctx->sm_count * 8), 128, 0, st>>>(
-        offsets, sched, seg_part, buckets);
-    LAUNCH_CHECK();
-    unsigned gb = std::min<unsigned>(cfg.big_cap, (unsigned)ctx->sm_count * 4);
-    k_stark_big<<<gb, SBIG_THREADS, 0, st>>>(table_base, offsets, entries, cfg, buckets, big_count, big_list, big_part);
-    LAUNCH_CHECK();
-    k_stark_big_fin<<<std::min<unsigned>((cfg.big_cap + 127) / 128, (unsigned)ctx->sm_count), 128, 0, st>>>(
-        cfg, buckets, big_count, big_list, big_part);
-    LAUNCH_CHECK();
-    const uint32_t* lvl0 = buckets;
-    if (windowed && cfg.gsub > 1) {
-      prof_mark(ctx, BPG_PROF_COMBINE);
-      k_stark_merge<<<((unsigned)nsets * cfg.nb + 127) / 128, 128, 0, st>>>(buckets, cfg, merged);
-      LAUNCH_CHECK();
-      lvl0 = merged;
-    }
-    prof_mark(ctx, BPG_PROF_REDUCE);
-    uint32_t arrays = windowed ? (uint32_t)nsets : cfg.narr;
-    uint32_t* fin = windowed ? d_out_ext : wins;
-    // leaf: large arrays one thread per chunk of 8 (throughput), small ones one quad per chunk of 4
-    // plus the in-block tree (latency); the pairs levels and Horner are quad-cooperative
-    const bool sthread_leaf = cfg.nb >= (1u << 17);
-    uint32_t t = sthread_leaf ? (cfg.nb + SLEAF_LC - 1) / SLEAF_LC : (cfg.nb + SRT_QUADS * 4 - 1) / (SRT_QUADS * 4);
-    uint32_t* pa[2] = {pairs, pairs + 2 * pair_words};
-    int cur = 0;
-    uint32_t* oa = t == 1 ? fin : pa[cur];
-    if (sthread_leaf) k_stark_leaf<<<(arrays * t + 127) / 128, 128, 0, st>>>(lvl0, cfg.nb, t, arrays, oa, pa[cur] + pair_words);
-    else k_stark_leaf4<4><<<arrays * t, SRT_THREADS, 0, st>>>(lvl0, cfg.nb, t, oa, pa[cur] + pair_words);
-    LAUNCH_CHECK();
-    while (t > 1) {
-      uint32_t n = t;
-      t = (n + SRP_PAIRS - 1) / SRP_PAIRS;
-      const uint32_t* ia = pa[cur];
-      const uint32_t* iy = pa[cur] + pair_words;
-      cur ^= 1;
-      oa = t == 1 ? fin : pa[cur];
-      k_stark_pairs4<<<arrays * t, SRP_THREADS, 0, st>>>(ia, iy, n, t, oa, pa[cur] + pair_words);
-      LAUNCH_CHECK();
-    }
-    if (!windowed) {
-      prof_mark(ctx, BPG_PROF_HORNER);
-      k_stark_horner4<<<nsets, 32, 0, st>>>(wins, cfg, d_out_ext);
-      LAUNCH_CHECK();
-    }
-    prof_mark(ctx, -1);
-    return BPG_OK;
-  }
-  prof_mark(ctx, BPG_PROF_ACCUM);
-  k_accum<<<(unsigned)((max_items + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, st>>>(table_base, offsets, entries,
-                                                                                          sched, buckets, seg_part);
-  LAUNCH_CHECK();
-  prof_mark(ctx, BPG_PROF_ACCUM_BIG);
-  k_accum_fix<<<(unsigned)std::min<size_t>((max_multi * 4 + FIX_THREADS - 1) / FIX_THREADS, (size_t)ctx->sm_count * 8),
-                FIX_THREADS, 0, st>>>(offsets, sched, seg_part, buckets);
-  LAUNCH_CHECK();
-  unsigned gbig = std::min<unsigned>(cfg.big_cap, (unsigned)ctx->sm_count * 4);
-  k_accum_big<<<gbig, BIG_THREADS, 0, st>>>(table_base, offsets, entries, cfg, buckets, big_count, big_list, big_part);
-  LAUNCH_CHECK();
-  k_accum_big_fin<<<gbig, BIG_THREADS, 0, st>>>(cfg, buckets, big_count, big_list, big_part);
-  LAUNCH_CHECK();
-  const uint32_t* level0 = buckets;
-  if (windowed && cfg.gsub > 1) {
-    prof_mark(ctx, BPG_PROF_COMBINE);
-    unsigned nq = (unsigned)nsets * cfg.nb;
-    k_merge<<<(nq * 4 + MERGE_THREADS - 1) / MERGE_THREADS, MERGE_THREADS, 0, st>>>(buckets, cfg, merged);
-    LAUNCH_CHECK();
-    level0 = merged;
-  }
-  prof_mark(ctx, BPG_PROF_REDUCE);
-  {
-    uint32_t* final_out = windowed ? d_out_ext : wins;
-    uint32_t t = tiles0;
-    uint32_t* pa[2] = {pairs, pairs + 2 * pair_words};
-    int cur = 0;
-    uint32_t* oa = t == 1 ? final_out : pa[cur];
-    if (thread_leaf) {
-      k_reduce_leaf_thread<16><<<(rarr * t + RL_THREADS - 1) / RL_THREADS, RL_THREADS, 0, st>>>(level0, cfg.nb, t, rarr, oa,
-                                                                                               pa[cur] + pair_words);
-    } else if (LC == 8) {
-      k_reduce_leaf<8><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
-    } else {
-      k_reduce_leaf<4><<<rarr * t, RT_THREADS, 0, st>>>(level0, cfg.nb, t, oa, pa[cur] + pair_words);
-    }
-    LAUNCH_CHECK();
-    while (t > 1) {
-      uint32_t n = t;
-      const uint32_t* ia = pa[cur];
-      const uint32_t* iy = pa[cur] + pair_words;
-      if (n <= RPB_PAIRS) {
-        // what is left fits one block per array: finish here
-        k_reduce_pairs_final<<<rarr, RPB_THREADS, RPB_SMEM, st>>>(ia, iy, n, final_out);
-        LAUNCH_CHECK();
-        break;
-      }
-      t = (n + RP_PAIRS - 1) / RP_PAIRS;
-      cur ^= 1;
-      oa = t == 1 ? final_out : pa[cur];
-      k_reduce_pairs<<<rarr * t, RP_THREADS, 0, st>>>(ia, iy, n, t, oa, pa[cur] + pair_words);
-      LAUNCH_CHECK();
-    }
-  }
-  if (!windowed) {
-    prof_mark(ctx, BPG_PROF_HORNER);
-    k_horner<<<nsets, 32, 0, st>>>(wins, cfg, d_out_ext);
-    LAUNCH_CHECK();
-  }
-  prof_mark(ctx, -1);
-  return BPG_OK;
-}
-
 extern "C" int bpg_dev_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t offset, size_t n,
                                  const void* d_scalars, int n_sets, void* d_out_ext) {
   if (!ctx || !table || !d_out_ext || (!d_scalars && n) || n_sets <= 0) return BPG_ERR_ARG;
@@ -901,13 +473,13 @@ extern "C" int bpg_dev_exchange_sum_encode(bpg_ctx* ctx, bpg_peer* p, const void
                                            void* d_out_ext) {
   if (!ctx || !p || !d_part || n_sets <= 0 || n_sets > p->max_sets || !p->connected) return BPG_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  p->seq++;
   uint32_t* status = reinterpret_cast<uint32_t*>(p->local + p->parts_bytes + align_up((size_t)2 * p->world * 4));
   prof_mark(ctx, BPG_PROF_ENCODE);
   k_exchange_sum_encode<<<1, XCH_THREADS, 0, ctx->stream>>>((const uint32_t*)d_part, p->ptrs, p->world, p->rank, n_sets,
-                                                            p->max_sets, p->seq, (uint8_t*)d_out_bytes, (uint32_t*)d_out_ext,
-                                                            status);
+                                                            p->max_sets, p->seq + 1, (uint8_t*)d_out_bytes,
+                                                            (uint32_t*)d_out_ext, status);
   LAUNCH_CHECK();
+  p->seq++;  // only a launch that went out advances the step counter the ranks share
   prof_mark(ctx, -1);
   return BPG_OK;
 }
@@ -1052,17 +624,6 @@ extern "C" void bpg_comb_free(bpg_comb* c) {
   delete c;
 }
 
-static sc_bias bias_for(int c) {
-  sc_bias b;
-  memset(&b, 0, sizeof b);
-  int W = (255 + c - 1) / c;
-  for (int w = 0; w < W; w++) {
-    int bit = c * w + c - 1;
-    b.v[bit >> 5] |= 1u << (bit & 31);
-  }
-  return b;
-}
-
 extern "C" int bpg_dev_comb_mul(bpg_ctx* ctx, const bpg_comb* comb, const void* d_scalars, size_t n,
                                 void* d_out_bytes, void* d_out_ext) {
   if (!ctx || !comb || (!d_scalars && n) || n >= (1u << 31)) return BPG_ERR_ARG;
@@ -1168,27 +729,7 @@ extern "C" int bpg_table_set_windows(bpg_ctx* ctx, bpg_table* t, int c) {
   return BPG_OK;
 }
 extern "C" int bpg_table_window(const bpg_table* t) { return t ? t->win_c : 0; }
-
-// ---------------------------------------------------------------------------
-// inner-product argument: device-resident state, one MSM per round
-// ---------------------------------------------------------------------------
-struct bpg_ipp {
-  bpg_ctx* ctx;
-  size_t n;        // original length (power of two)
-  size_t m;        // current length
-  const bpg_table* tab;  // windowed table the round MSMs run over
-  bpg_table* own_tab;    // non-null when the state built its own [G | H | Q] table
-  bool has_qmul;         // cross terms are multiplied by q_mul (Q = q_mul * table[q_id])
-  bool q_sep;            // Q is outside the (caller's windowed) table: c_L Q, c_R Q come from a comb of Q
-  uint32_t *q_comb, *q_side;
-  uint8_t* buf;    // one allocation for everything below
-  uint32_t *a, *b, *wG, *wH, *scalars, *point_ids, *partials, *u_pair, *out_ext;
-  uint32_t* q_mul;
-  uint8_t *set_ids, *out_bytes;
-  bool lr_done;
-};
-
-static int table_alloc_plain(bpg_ctx* ctx, size_t n, bpg_table** out) {
+int table_alloc_plain(bpg_ctx* ctx, size_t n, bpg_table** out) {
   bpg_table* t = new (std::nothrow) bpg_table();
   if (!t) return BPG_ERR_NOMEM;
   t->ctx = ctx;
@@ -1202,256 +743,6 @@ static int table_alloc_plain(bpg_ctx* ctx, size_t n, bpg_table** out) {
   *out = t;
   return BPG_OK;
 }
-
-// d_* pointers are device pointers; factors may be null (all ones).
-// Either (G, H, Q_host) are given and the state builds its own windowed [G | H | Q] table,
-// or `shared` is a windowed table that already holds the generators at g_base/h_base and a
-// base point at q_id with Q = q_mul * shared[q_id] (the R1CS prover's Q = w*B).
-static int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off, size_t n,
-                         const uint8_t* Q_host, const bpg_table* shared, size_t g_base, size_t h_base, size_t q_id,
-                         const uint8_t* q_mul_host, const uint32_t* d_gf, const uint32_t* d_hf, const uint32_t* d_a,
-                         const uint32_t* d_b, bpg_ipp** out) {
-  if (n == 0 || (n & (n - 1))) return BPG_ERR_POW2;
-  if (n >= (1u << 28)) return BPG_ERR_ARG;
-  if (shared) {
-    if (g_base + n > shared->n || h_base + n > shared->n || q_id >= shared->n) return BPG_ERR_CAPACITY;
-    if (!shared->win_c && n > 1) return BPG_ERR_ARG;
-  } else if (g_off + n > G->n || h_off + n > H->n) {
-    return BPG_ERR_CAPACITY;
-  }
-  bpg_ipp* st = new (std::nothrow) bpg_ipp();
-  if (!st) return BPG_ERR_NOMEM;
-  memset(st, 0, sizeof *st);
-  st->ctx = ctx;
-  st->n = st->m = n;
-  int rc = BPG_OK;
-  size_t T = 2 * n + 2;
-  size_t nparts = 256;
-  size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
-  size_t o_a = take(n * 32), o_b = take(n * 32), o_wG = take(n * 32), o_wH = take(n * 32);
-  size_t o_sc = take(T * 32), o_pid = take(T * 4), o_set = take(T), o_part = take(nparts * 64);
-  size_t o_u = take(64), o_ext = take(4 * 128), o_bytes = take(64), o_q = take(32), o_qm = take(32);
-  size_t o_qside = take(64), o_qcomb = take((size_t)COMB_ENTRIES * 96);
-  do {
-    cudaError_t e = dev_alloc(ctx, &st->buf, off);
-    if (e != cudaSuccess) { ctx->last_cuda = (int)e; rc = BPG_ERR_NOMEM; break; }
-    st->a = (uint32_t*)(st->buf + o_a); st->b = (uint32_t*)(st->buf + o_b);
-    st->wG = (uint32_t*)(st->buf + o_wG); st->wH = (uint32_t*)(st->buf + o_wH);
-    st->scalars = (uint32_t*)(st->buf + o_sc); st->point_ids = (uint32_t*)(st->buf + o_pid);
-    st->set_ids = st->buf + o_set; st->partials = (uint32_t*)(st->buf + o_part);
-    st->u_pair = (uint32_t*)(st->buf + o_u); st->out_ext = (uint32_t*)(st->buf + o_ext);
-    st->out_bytes = st->buf + o_bytes;
-    st->q_mul = (uint32_t*)(st->buf + o_qm);
-    st->q_side = (uint32_t*)(st->buf + o_qside);
-    st->q_comb = (uint32_t*)(st->buf + o_qcomb);
-    uint8_t* d_q = st->buf + o_q;
-    cudaStream_t s = ctx->stream;
-    if (cudaMemcpyAsync(st->a, d_a, n * 32, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
-        cudaMemcpyAsync(st->b, d_b, n * 32, cudaMemcpyDeviceToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
-    unsigned gn = (unsigned)((n + 255) / 256);
-    k_ipp_init_weights<<<gn, 256, 0, s>>>(d_gf, d_hf, (uint32_t)n, st->wG, st->wH);
-    ctx->launches++;
-    if (shared) {
-      st->tab = shared;
-      st->has_qmul = q_mul_host != nullptr;
-      if (q_mul_host) {
-        memcpy(ctx->h_pinned + 512, q_mul_host, 32);
-        if (cudaMemcpyAsync(st->q_mul, ctx->h_pinned + 512, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
-      }
-      k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, (uint32_t)g_base, (uint32_t)h_base, (uint32_t)q_id);
-      ctx->launches++;
-      if (cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
-    } else if (G == H && G->win_c && n > 1) {
-      // The caller's generators already live in ONE windowed table (a resident BulletproofGens):
-      // run the round MSMs over it as they are and form c_L Q, c_R Q from a fixed-base comb of Q
-      // built here once, on the auxiliary stream beside each round's MSM.
-      st->tab = G;
-      st->q_sep = true;
-      k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, (uint32_t)g_off, (uint32_t)h_off, (uint32_t)g_off);
-      ctx->launches++;
-      memcpy(ctx->h_pinned + 512, Q_host, 32);
-      uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small);
-      if (cudaMemsetAsync(bad, 0, 4, s) != cudaSuccess ||
-          cudaMemcpyAsync(d_q, ctx->h_pinned + 512, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
-      k_comb_build<<<1, COMB_WINDOWS, 0, s>>>(d_q, st->q_comb, bad);
-      ctx->launches++;
-      uint32_t* hbad = reinterpret_cast<uint32_t*>(ctx->h_pinned);
-      if (cudaMemcpyAsync(hbad, bad, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-          cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
-      if (*hbad) { rc = BPG_ERR_DECODE; break; }
-    } else {
-      k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, 0u, (uint32_t)n, (uint32_t)(2 * n));
-      ctx->launches++;
-      // combined table [G | H | Q]
-      rc = table_alloc_plain(ctx, 2 * n + 1, &st->own_tab);
-      if (rc) break;
-      st->tab = st->own_tab;
-      if (cudaMemcpyAsync(st->own_tab->niels, G->niels + g_off * 24, n * 96, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
-          cudaMemcpyAsync(st->own_tab->niels + n * 24, H->niels + h_off * 24, n * 96, cudaMemcpyDeviceToDevice, s) !=
-              cudaSuccess) { rc = BPG_ERR_CUDA; break; }
-      memcpy(ctx->h_pinned + 512, Q_host, 32);
-      uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small);
-      if (cudaMemsetAsync(bad, 0, 4, s) != cudaSuccess ||
-          cudaMemcpyAsync(d_q, ctx->h_pinned + 512, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
-      k_decode_to_niels<<<1, 128, 0, s>>>(d_q, 1, st->own_tab->niels + 2 * n * 24, bad);
-      ctx->launches++;
-      uint32_t* hbad = reinterpret_cast<uint32_t*>(ctx->h_pinned);
-      if (cudaMemcpyAsync(hbad, bad, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-          cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
-      if (*hbad) { rc = BPG_ERR_DECODE; break; }
-      if (n > 1) {
-        rc = bpg_table_set_windows(ctx, st->own_tab, pick_window(n + 1, ctx->forced_c));
-        if (rc) break;
-      }
-    }
-  } while (0);
-  if (rc != BPG_OK) {
-    if (st->own_tab) bpg_table_free(st->own_tab);
-    dev_free(ctx, st->buf);
-    delete st;
-    return rc;
-  }
-  *out = st;
-  return BPG_OK;
-}
-
-extern "C" int bpg_ipp_begin(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off,
-                             size_t n, const uint8_t Q[32], const uint8_t* G_factors, const uint8_t* H_factors,
-                             const uint8_t* a, const uint8_t* b, bpg_ipp** out) {
-  if (!ctx || !G || !H || !Q || !a || !b || !out) return BPG_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  int rc = ensure_stage(ctx, 4 * n * 32 + 64);
-  if (rc) return rc;
-  uint8_t* d = ctx->d_stage;
-  CK(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d + n * 32, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  if (G_factors) CK(cudaMemcpyAsync(d + 2 * n * 32, G_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  if (H_factors) CK(cudaMemcpyAsync(d + 3 * n * 32, H_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  return ipp_begin_dev(ctx, G, g_off, H, h_off, n, Q, nullptr, 0, 0, 0, nullptr,
-                       G_factors ? (const uint32_t*)(d + 2 * n * 32) : nullptr,
-                       H_factors ? (const uint32_t*)(d + 3 * n * 32) : nullptr, (const uint32_t*)d,
-                       (const uint32_t*)(d + n * 32), out);
-}
-
-extern "C" int bpg_ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off,
-                                 size_t n, const uint8_t Q[32], const void* d_G_factors, const void* d_H_factors,
-                                 const void* d_a, const void* d_b, bpg_ipp** out) {
-  if (!ctx || !G || !H || !Q || !d_a || !d_b || !out) return BPG_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  return ipp_begin_dev(ctx, G, g_off, H, h_off, n, Q, nullptr, 0, 0, 0, nullptr, (const uint32_t*)d_G_factors,
-                       (const uint32_t*)d_H_factors, (const uint32_t*)d_a, (const uint32_t*)d_b, out);
-}
-
-// Generators and the base of Q live in one windowed table (the R1CS prover: G at g_base, H at
-// h_base, Q = q_mul * shared[q_id] with q_id the Pedersen base B and q_mul the challenge w).
-extern "C" int bpg_ipp_begin_shared(bpg_ctx* ctx, const bpg_table* shared, size_t g_base, size_t h_base, size_t q_id,
-                                    const uint8_t q_mul[32], size_t n, const uint8_t* G_factors,
-                                    const uint8_t* H_factors, const uint8_t* a, const uint8_t* b, bpg_ipp** out) {
-  if (!ctx || !shared || !a || !b || !out) return BPG_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  int rc = ensure_stage(ctx, 4 * n * 32 + 64);
-  if (rc) return rc;
-  uint8_t* d = ctx->d_stage;
-  CK(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d + n * 32, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  if (G_factors) CK(cudaMemcpyAsync(d + 2 * n * 32, G_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  if (H_factors) CK(cudaMemcpyAsync(d + 3 * n * 32, H_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  return ipp_begin_dev(ctx, nullptr, 0, nullptr, 0, n, nullptr, shared, g_base, h_base, q_id, q_mul,
-                       G_factors ? (const uint32_t*)(d + 2 * n * 32) : nullptr,
-                       H_factors ? (const uint32_t*)(d + 3 * n * 32) : nullptr, (const uint32_t*)d,
-                       (const uint32_t*)(d + n * 32), out);
-}
-
-extern "C" size_t bpg_ipp_rounds_left(const bpg_ipp* st) {
-  size_t r = 0;
-  if (!st) return 0;
-  for (size_t m = st->m; m > 1; m >>= 1) r++;
-  return r;
-}
-
-extern "C" int bpg_ipp_round_LR(bpg_ipp* st, uint8_t L[32], uint8_t R[32]) {
-  if (!st || !L || !R) return BPG_ERR_ARG;
-  if (st->m <= 1 || st->lr_done) return BPG_ERR_ARG;
-  bpg_ctx* ctx = st->ctx;
-  CK(cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  size_t n = st->n, m = st->m, h = m / 2;
-  unsigned gcross = (unsigned)std::min<size_t>(256, (h + IPP_THREADS - 1) / IPP_THREADS);
-  prof_mark(ctx, BPG_PROF_OTHER);
-  k_ipp_cross<<<gcross, IPP_THREADS, 0, s>>>(st->a, st->b, (uint32_t)h, st->partials);
-  LAUNCH_CHECK();
-  k_ipp_round_scalars<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st->a, st->b, st->wG, st->wH, (uint32_t)n,
-                                                                  (uint32_t)m, st->scalars, st->set_ids);
-  LAUNCH_CHECK();
-  k_ipp_cross_finish<<<1, IPP_THREADS, 0, s>>>(st->partials, gcross, (uint32_t)n, st->has_qmul ? st->q_mul : nullptr,
-                                               st->scalars, st->set_ids, st->q_sep ? st->q_side : nullptr);
-  LAUNCH_CHECK();
-  if (st->q_sep) {
-    // c_L Q, c_R Q: 64 mixed additions each from the comb of Q, beside the MSM
-    CK(cudaEventRecord(ctx->ev_fork, s));
-    CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
-    k_comb_mul<<<1, 128, 0, ctx->aux_stream>>>(st->q_comb, 1, st->q_side, 2u, bias_for(4), nullptr, st->out_ext + 64);
-    LAUNCH_CHECK();
-    CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
-  }
-  int rc = msm_enqueue(ctx, st->tab->niels, st->tab->n, st->scalars, 2 * n + 2, st->set_ids, st->point_ids, 2,
-                       st->out_ext, st->tab->win_c, st->tab->n);
-  if (rc) return rc;
-  if (st->q_sep) CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-  rc = bpg_dev_sum_encode(ctx, st->out_ext, st->q_sep ? 2 : 1, 2, st->out_bytes, nullptr);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(ctx->h_pinned, st->out_bytes, 64, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  memcpy(L, ctx->h_pinned, 32);
-  memcpy(R, ctx->h_pinned + 32, 32);
-  st->lr_done = true;
-  return BPG_OK;
-}
-
-extern "C" int bpg_ipp_round_fold(bpg_ipp* st, const uint8_t u[32], const uint8_t u_inv[32]) {
-  if (!st || !u || !u_inv) return BPG_ERR_ARG;
-  if (st->m <= 1 || !st->lr_done) return BPG_ERR_ARG;
-  bpg_ctx* ctx = st->ctx;
-  CK(cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  // the challenge pair travels as kernel arguments: no staging copy, and no wait here -- the
-  // next round's launches queue up behind the fold
-  ScPair up;
-  memcpy(up.v, u, 32);
-  memcpy(up.v + 8, u_inv, 32);
-  prof_mark(ctx, BPG_PROF_OTHER);
-  k_ipp_fold<<<(unsigned)((st->n + 255) / 256), 256, 0, s>>>(st->a, st->b, st->wG, st->wH, (uint32_t)st->n,
-                                                             (uint32_t)st->m, up);
-  LAUNCH_CHECK();
-  prof_mark(ctx, -1);
-  st->m /= 2;
-  st->lr_done = false;
-  return BPG_OK;
-}
-
-extern "C" int bpg_ipp_finish(bpg_ipp* st, uint8_t a[32], uint8_t b[32]) {
-  if (!st || !a || !b) return BPG_ERR_ARG;
-  if (st->m != 1) return BPG_ERR_ARG;
-  bpg_ctx* ctx = st->ctx;
-  CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpyAsync(ctx->h_pinned, st->a, 32, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_pinned + 32, st->b, 32, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  memcpy(a, ctx->h_pinned, 32);
-  memcpy(b, ctx->h_pinned + 32, 32);
-  return BPG_OK;
-}
-
-extern "C" void bpg_ipp_free(bpg_ipp* st) {
-  if (!st) return;
-  cudaSetDevice(st->ctx->device);
-  if (st->q_sep) cudaStreamSynchronize(st->ctx->aux_stream);
-  if (st->own_tab) bpg_table_free(st->own_tab);
-  dev_free(st->ctx, st->buf);
-  delete st;
-}
-
 // ---------------------------------------------------------------------------
 // indexed MSM: term t = scalars[t] * table[point_ids[t]] accumulated into out[set_ids[t]]
 // ---------------------------------------------------------------------------
@@ -1493,9 +784,9 @@ extern "C" int bpg_msm_table_indexed(bpg_ctx* ctx, const bpg_table* table, const
 // one MSM over ad-hoc (compressed) points followed by ranges of resident tables
 // ---------------------------------------------------------------------------
 // core of the mixed MSM: scalars for all `total` terms are already in d_scalars (device)
-static int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_adhoc, const bpg_table* const* tabs,
+int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_adhoc, const bpg_table* const* tabs,
                           const size_t* offs, const size_t* lens, int nsegs, const uint32_t* d_scalars, size_t total,
-                          uint8_t out[32], bool identity_only = false /*out: zeros iff the sum is the identity*/) {
+                          uint8_t out[32], bool identity_only /*out: zeros iff the sum is the identity*/) {
   cudaStream_t s = ctx->stream;
   uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small + 1024);
   uint32_t* d_ext = (uint32_t*)ctx->d_small;  // up to two partial sums
@@ -1629,6 +920,20 @@ extern "C" int bpg_msm_mixed(bpg_ctx* ctx, const uint8_t* adhoc_points, size_t n
   return msm_mixed_core(ctx, d_pts, n_adhoc, tabs, offs, lens, nsegs, (const uint32_t*)d_sc, total, out);
 }
 
-#include "r1cs_dev.inc"
-#include "stark_msm.inc"
-#include "stark_ipp.inc"
+// ---------------------------------------------------------------------------
+// launch helpers for other translation units (the kernels live here)
+// ---------------------------------------------------------------------------
+void launch_decode_to_niels(bpg_ctx* ctx, cudaStream_t s, const uint8_t* d_comp, size_t n, uint32_t* niels, uint32_t* bad) {
+  k_decode_to_niels<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_comp, (uint32_t)n, niels, bad);
+  ctx->launches++;
+}
+void launch_comb_build(bpg_ctx* ctx, cudaStream_t s, const uint8_t* d_base32, uint32_t* table, uint32_t* bad) {
+  k_comb_build<<<1, COMB_WINDOWS, 0, s>>>(d_base32, table, bad);
+  ctx->launches++;
+}
+void launch_comb_mul(bpg_ctx* ctx, cudaStream_t s, const uint32_t* tables, int nbases, const uint32_t* d_scalars, size_t n,
+                     uint8_t* d_out_bytes, uint32_t* d_out_ext) {
+  k_comb_mul<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(tables, nbases, d_scalars, (uint32_t)n, bias_for(4), d_out_bytes,
+                                                        d_out_ext);
+  ctx->launches++;
+}

@@ -13,7 +13,7 @@ namespace bpg {
 // Constants live in constant memory on the device; the host copies exist only for
 // tests/hostsim (see fe.cuh).
 #define BPG_DEF_CONST(name, ...)                                   \
-  __device__ __constant__ uint32_t name[8] = {__VA_ARGS__};        \
+  static __device__ __constant__ uint32_t name[8] = {__VA_ARGS__};        \
   static const uint32_t name##_h[8] = {__VA_ARGS__};
 #if defined(__CUDA_ARCH__)
 #define BPG_K(name) name
@@ -326,5 +326,22 @@ BPG_DI void ge_load_ext(ge_ext& q, const uint32_t* p) {
   fe_load(q.Z, p + 16);
   fe_load(q.T, p + 24);
 }
+
+BPG_DEF_CONST(K_DINV, 0xcdc9f843u, 0x25e0f276u, 0x4279542eu, 0x0b5dd698u, 0xcdb9cf66u, 0x2b162114u, 0x14d5ce43u,
+              0x40907ed2u)  // 1/d
+
+// the point (+-) of a Niels entry as an extended point with Z = 2: one multiplication
+BPG_DI ge_ext ge_from_niels(const ge_niels& q, bool neg) {
+  ge_ext r;
+  fe x2 = fe_sub(q.ypx, q.ymx);   // 2x
+  fe t = fe_mul(q.t2d, fe_const(BPG_K(K_DINV)));  // 2xy
+  r.X = fe_canon(fe_cneg(x2, neg));
+  r.Y = fe_canon(fe_add(q.ypx, q.ymx));  // 2y
+  r.Z = fe_zero();
+  r.Z.v[0] = 2;
+  r.T = fe_canon(fe_cneg(t, neg));
+  return r;
+}
+
 
 }  // namespace bpg

@@ -93,6 +93,7 @@ class Strobe128 {
   void meta_ad(const uint8_t* d, size_t n, bool more) { begin_op(FLAG_M | FLAG_A, more); absorb(d, n); }
   void ad(const uint8_t* d, size_t n, bool more) { begin_op(FLAG_A, more); absorb(d, n); }
   void prf(uint8_t* out, size_t n, bool more) { begin_op(FLAG_I | FLAG_A | FLAG_C, more); squeeze(out, n); }
+  void key(const uint8_t* d, size_t n, bool more) { begin_op(FLAG_A | FLAG_C, more); overwrite(d, n); }
 
  private:
   static constexpr uint8_t R = 166;
@@ -116,6 +117,13 @@ class Strobe128 {
       if (++pos_ == R) run_f();
     }
   }
+  void overwrite(const uint8_t* d, size_t n) {
+    uint8_t* s = bytes();
+    for (size_t i = 0; i < n; i++) {
+      s[pos_] = d[i];
+      if (++pos_ == R) run_f();
+    }
+  }
   void squeeze(uint8_t* out, size_t n) {
     uint8_t* s = bytes();
     for (size_t i = 0; i < n; i++) {
@@ -133,6 +141,40 @@ class Strobe128 {
     absorb(hdr, 2);
     if ((flags & (FLAG_C | FLAG_K)) && pos_ != 0) run_f();
   }
+};
+
+// merlin::TranscriptRng (merlin transcript.rs: TranscriptRngBuilder / TranscriptRng): a clone of the
+// transcript's STROBE state rekeyed with witness bytes and finalized with 32 bytes of external
+// randomness; every fill is a length-framed PRF output.  The prover's blinding source (reference
+// src/r1cs/prover.rs:435-445) and, in the hardened form, the verifier's batching scalar.
+class TranscriptRng {
+ public:
+  explicit TranscriptRng(const Strobe128& s) : strobe_(s) {}
+  void rekey_with_witness_bytes(const char* label, const uint8_t* w, size_t n) {
+    uint32_t len = (uint32_t)n;
+    uint8_t le[4] = {(uint8_t)len, (uint8_t)(len >> 8), (uint8_t)(len >> 16), (uint8_t)(len >> 24)};
+    strobe_.meta_ad((const uint8_t*)label, strlen(label), false);
+    strobe_.meta_ad(le, 4, true);
+    strobe_.key(w, n, false);
+  }
+  void finalize(const uint8_t random_bytes[32]) {
+    strobe_.meta_ad((const uint8_t*)"rng", 3, false);
+    strobe_.key(random_bytes, 32, false);
+  }
+  void fill_bytes(uint8_t* out, size_t n) {
+    uint32_t len = (uint32_t)n;
+    uint8_t le[4] = {(uint8_t)len, (uint8_t)(len >> 8), (uint8_t)(len >> 16), (uint8_t)(len >> 24)};
+    strobe_.meta_ad(le, 4, false);
+    strobe_.prf(out, n, false);
+  }
+  Scalar scalar() {  // Scalar::random(&mut rng): 64 bytes, wide reduction
+    uint8_t b[64];
+    fill_bytes(b, 64);
+    return Scalar::from_wide(b);
+  }
+
+ private:
+  Strobe128 strobe_;
 };
 
 // merlin::Transcript + the reference's TranscriptProtocol
@@ -187,6 +229,7 @@ class Transcript {
     challenge_bytes(label, b, 64);
     return Scalar::from_wide(b);
   }
+  TranscriptRng build_rng() const { return TranscriptRng(strobe_); }
 
  private:
   Strobe128 strobe_;

@@ -17,6 +17,9 @@
 #include <new>
 #include <vector>
 
+#include <errno.h>
+#include <sys/random.h>
+
 #include "../../../include/bpgpu.h"
 #include "merlin.hpp"
 #include "sc_host.hpp"
@@ -104,6 +107,21 @@ extern "C" void bpg_transcript_challenge_bytes(bpg_transcript* t, const char* la
 extern "C" void bpg_transcript_challenge_scalar(bpg_transcript* t, const char* label, uint8_t out[32]) {
   t->t.challenge_scalar(label).to_bytes(out);
 }
+
+struct bpg_transcript_rng {
+  TranscriptRng r;
+  explicit bpg_transcript_rng(const TranscriptRng& x) : r(x) {}
+};
+extern "C" bpg_transcript_rng* bpg_transcript_build_rng(const bpg_transcript* t) {
+  return t ? new (std::nothrow) bpg_transcript_rng(t->t.build_rng()) : nullptr;
+}
+extern "C" void bpg_transcript_rng_rekey_with_witness_bytes(bpg_transcript_rng* r, const char* label, const uint8_t* w,
+                                                            size_t len) {
+  r->r.rekey_with_witness_bytes(label, w, len);
+}
+extern "C" void bpg_transcript_rng_finalize(bpg_transcript_rng* r, const uint8_t random_bytes[32]) { r->r.finalize(random_bytes); }
+extern "C" void bpg_transcript_rng_fill_bytes(bpg_transcript_rng* r, uint8_t* out, size_t len) { r->r.fill_bytes(out, len); }
+extern "C" void bpg_transcript_rng_free(bpg_transcript_rng* r) { delete r; }
 
 // ---------------------------------------------------------------- generators
 // One windowed table [G (cap) | H (cap) | B | B_blinding] plus a comb for (B, B_blinding).
@@ -420,6 +438,52 @@ struct Xoshiro {
     return Scalar::from_wide(b);
   }
 };
+
+// The prover's blinding source, consumed in the reference's draw order (prover.rs:457-462, 519-530,
+// 621-625).  Production: merlin's TranscriptRng (transcript state + v_blinding witnesses + 32 bytes of
+// external randomness, prover.rs:435-445); the two blinding vectors of a phase come from ONE 32-byte
+// draw that keys a ChaCha20 stream expanded on the device (k_blind_vectors_chacha).  Tests and
+// benches: xoshiro256** from a 64-bit seed (reproducible; not a secure source).
+struct Blinder {
+  bool keyed;
+  Xoshiro xo;
+  TranscriptRng rng;
+  Blinder(uint64_t seed, const Transcript& tr) : keyed(false), xo(seed), rng(tr.build_rng()) {}
+  Blinder(const Transcript& tr, const std::vector<Scalar>& v_blinding, const uint8_t random_bytes[32])
+      : keyed(true), xo(0), rng(tr.build_rng()) {
+    for (auto& vb : v_blinding) {
+      uint8_t b[32];
+      vb.to_bytes(b);
+      rng.rekey_with_witness_bytes("v_blinding", b, 32);
+    }
+    rng.finalize(random_bytes);
+  }
+  Scalar scalar() { return keyed ? rng.scalar() : xo.scalar(); }
+  // key of a phase's (s_L, s_R): 8 bytes of the seeded stream, or 32 bytes of the transcript RNG
+  void vec_key(uint64_t* k64, uint8_t k32[32]) {
+    if (keyed) rng.fill_bytes(k32, 32);
+    else *k64 = xo.next();
+  }
+};
+
+// 32 bytes from the operating system (what `thread_rng()` stands on): getrandom(2), /dev/urandom as a fallback
+static bool os_random(uint8_t out[32]) {
+  size_t got = 0;
+  while (got < 32) {
+    ssize_t r = getrandom(out + got, 32 - got, 0);
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      break;
+    }
+    got += (size_t)r;
+  }
+  if (got == 32) return true;
+  FILE* f = fopen("/dev/urandom", "rb");
+  if (!f) return false;
+  bool ok = fread(out, 1, 32, f) == 32;
+  fclose(f);
+  return ok;
+}
 
 typedef int (*bpg_randomized_cb)(struct bpg_cs* cs, void* user);
 
@@ -843,20 +907,32 @@ struct DevGuard {  // frees the resident prover state on every exit path
   ~DevGuard() { bpg_r1cs_dev_free(p); }
 };
 
-extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+static int prover_prove(bpg_cs* cs, bool keyed, uint64_t rng_seed, const uint8_t* random_bytes, uint8_t* proof_out,
+                        size_t proof_cap, size_t* proof_len) {
   if (!cs || !cs->is_prover || !proof_out || !proof_len) return BPG_ERR_ARG;
   Transcript& tr = *cs->tr;
   const bpg_gens* g = cs->gens;
-  Xoshiro rng(rng_seed);
   R1CSProof proof;
   StageTimer tm("prove");
   tr.append_u64("m", cs->v.size());  // :420
+  // :435-445: the RNG is forked from the transcript here, keyed with the v_blindings and external randomness
+  Blinder rng = keyed ? Blinder(tr, cs->v_blinding, random_bytes) : Blinder(rng_seed, tr);
   size_t n1 = cs->a_L.size();
   if (g->cap < n1) return BPG_ERR_CAPACITY;  // :450-452
   // Blinding draws in the reference's order (:457-462); the 2 n1 vector blindings s_L, s_R are
   // generated on the device from one drawn key (none drawn for an empty phase)
   Scalar i_b1 = rng.scalar(), o_b1 = rng.scalar(), s_b1 = rng.scalar();
-  uint64_t vec_key = n1 ? rng.next() : 0;
+  uint64_t vec_key = 0;
+  uint8_t vec_key32[32] = {0};
+  if (n1) rng.vec_key(&vec_key, vec_key32);
+  auto commit = [&](bpg_r1cs_dev* dvp, size_t first, size_t cnt, const uint8_t* b3, uint8_t* out3) {
+    return keyed ? bpg_r1cs_dev_commit_keyed(dvp, g->table, g->g_base(), g->h_base(), g->bb_id(), first, cnt,
+                                             cs->a_L.data() + first, cs->a_R.data() + first, cs->a_O.data() + first,
+                                             vec_key32, b3, out3)
+                 : bpg_r1cs_dev_commit(dvp, g->table, g->g_base(), g->h_base(), g->bb_id(), first, cnt,
+                                       cs->a_L.data() + first, cs->a_R.data() + first, cs->a_O.data() + first, vec_key, b3,
+                                       out3);
+  };
   DevGuard dv;
   int rc = bpg_r1cs_dev_new(cs->ctx, next_pow2(std::max<size_t>(n1, 1)), &dv.p);
   if (rc) return rc;
@@ -865,8 +941,7 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   i_b1.to_bytes(blind3);
   o_b1.to_bytes(blind3 + 32);
   s_b1.to_bytes(blind3 + 64);
-  rc = bpg_r1cs_dev_commit(dv.p, g->table, g->g_base(), g->h_base(), g->bb_id(), 0, n1, cs->a_L.data(), cs->a_R.data(),
-                           cs->a_O.data(), vec_key, blind3, c3);  // :465-494
+  rc = commit(dv.p, 0, n1, blind3, c3);  // :465-494
   if (rc) return rc;
   tm.lap("A_I1 A_O1 S1 msm");
   memcpy(proof.A_I1.data(), c3, 32);
@@ -886,12 +961,11 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
     i_b2 = rng.scalar();
     o_b2 = rng.scalar();
     s_b2 = rng.scalar();
-    vec_key = rng.next();
+    rng.vec_key(&vec_key, vec_key32);
     i_b2.to_bytes(blind3);
     o_b2.to_bytes(blind3 + 32);
     s_b2.to_bytes(blind3 + 64);
-    rc = bpg_r1cs_dev_commit(dv.p, g->table, g->g_base(), g->h_base(), g->bb_id(), n1, n2, cs->a_L.data() + n1,
-                             cs->a_R.data() + n1, cs->a_O.data() + n1, vec_key, blind3, c3);  // :532-565
+    rc = commit(dv.p, n1, n2, blind3, c3);  // :532-565
     if (rc) return rc;
     memcpy(proof.A_I2.data(), c3, 32);
     memcpy(proof.A_O2.data(), c3 + 32, 32);
@@ -975,8 +1049,34 @@ extern "C" int bpg_prover_prove(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_ou
   return BPG_OK;
 }
 
+// Prover::prove (prover.rs:412-727).  Blindings: merlin TranscriptRng bound to the transcript, the
+// v_blinding witnesses and 32 bytes from the operating system (what `thread_rng()` supplies at :443-444).
+extern "C" int bpg_prover_prove(bpg_cs* cs, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+  uint8_t rb[32];
+  if (!os_random(rb)) return BPG_ERR_ARG;
+  int rc = prover_prove(cs, true, 0, rb, proof_out, proof_cap, proof_len);
+  volatile uint8_t* z = rb;
+  for (int i = 0; i < 32; i++) z[i] = 0;
+  return rc;
+}
+// same with the 32 bytes `finalize(&mut rng)` draws supplied by the caller (its own CSPRNG; fixed bytes
+// make the proof reproducible, which is how the parity tests compare proof bytes with the oracle)
+extern "C" int bpg_prover_prove_with_rng_bytes(bpg_cs* cs, const uint8_t rng_bytes[32], uint8_t* proof_out,
+                                               size_t proof_cap, size_t* proof_len) {
+  if (!rng_bytes) return BPG_ERR_ARG;
+  return prover_prove(cs, true, 0, rng_bytes, proof_out, proof_cap, proof_len);
+}
+// TEST / BENCH ONLY: every blinding from xoshiro256**(rng_seed) -- reproducible, NOT hiding
+extern "C" int bpg_prover_prove_deterministic(bpg_cs* cs, uint64_t rng_seed, uint8_t* proof_out, size_t proof_cap,
+                                              size_t* proof_len) {
+  return prover_prove(cs, false, rng_seed, nullptr, proof_out, proof_cap, proof_len);
+}
+
 // ---------------------------------------------------------------- Verifier::verify (verifier.rs:393-554)
-extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_len) {
+// r_bytes == nullptr: r = challenge_scalar("r") as the mounted fork does (verifier.rs:506).  Otherwise r is
+// drawn from a TranscriptRng finalized with r_bytes (upstream's build_rng().finalize(&mut thread_rng())),
+// so that a prover cannot predict the scalar that batches the two checks.
+static int verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_len, const uint8_t* r_bytes) {
   if (!cs || cs->is_prover || !proof_bytes) return BPG_ERR_ARG;
   R1CSProof proof;
   int rc = R1CSProof::from_bytes(proof_bytes, proof_len, &proof);
@@ -1022,7 +1122,14 @@ extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_
   tm.lap("verification challenges");
   const Scalar &a = proof.ipp.a, &b = proof.ipp.b;
   Scalar y_inv = y.invert();
-  Scalar r = tr.challenge_scalar("r");  // :506
+  Scalar r;
+  if (r_bytes) {
+    TranscriptRng vr = tr.build_rng();
+    vr.finalize(r_bytes);
+    r = vr.scalar();
+  } else {
+    r = tr.challenge_scalar("r");  // :506
+  }
   Scalar xx = x * x, rxx = r * xx, xxx = x * xx;
   size_t lg_n = proof.ipp.L_vec.size(), m = cs->V.size();
   // ad-hoc points: [A_I1 A_O1 S1 A_I2 A_O2 S2 | V_* | T_* | L_* | R_*]
@@ -1078,6 +1185,21 @@ extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_
   if (rc == BPG_ERR_DECODE) return BPG_ERR_DECODE;  // a proof point that is not a valid encoding: FormatError
   if (rc) return rc;
   return is_identity_enc(mega) ? BPG_OK : BPG_ERR_VERIFY;  // :549
+}
+extern "C" int bpg_verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_len) {
+  return verifier_verify(cs, proof_bytes, proof_len, nullptr);
+}
+// Hardened form: the batching scalar r is bound to the whole transcript AND to 32 bytes the prover cannot
+// know (rng_bytes; NULL = read from the operating system).  Accepts exactly the proofs bpg_verifier_verify
+// accepts (an honest proof satisfies both checks separately), rejects with overwhelming probability otherwise.
+extern "C" int bpg_verifier_verify_with_rng_bytes(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_len,
+                                                  const uint8_t* rng_bytes) {
+  uint8_t rb[32];
+  if (!rng_bytes) {
+    if (!os_random(rb)) return BPG_ERR_ARG;
+    rng_bytes = rb;
+  }
+  return verifier_verify(cs, proof_bytes, proof_len, rng_bytes);
 }
 
 // Batch verification (BASELINE.json config 4): the reference verifies proof by proof

@@ -1,0 +1,128 @@
+// Internal declarations shared by the translation units of libbpgpu (not part of the ABI).
+// Kernels are `static __global__` (BPG_GLOBAL): every translation unit compiles only the ones it launches.
+#pragma once
+#include "../../include/bpgpu.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <unordered_map>
+#include <vector>
+
+#include "sc.cuh"
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct bpg_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int last_cuda = 0;
+  uint64_t launches = 0;
+  int forced_c = 0;
+  int forced_gsub = 0;  // BPG_MSM_GSUB: bucket groups per set on windowed tables (tuning)
+  int sm_count = 148;
+  // per-phase device timing (bpg_profile_*): events are recorded on the launch stream
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;   // pool
+  std::vector<int> prof_phase;        // phase id of interval [ev[i], ev[i+1])
+  size_t prof_used = 0;
+  double prof_ms[BPG_PROF_NPHASE] = {0};
+  uint64_t prof_n[BPG_PROF_NPHASE] = {0};
+  // workspace arenas (grown on demand, reused across calls): [0] for the launch stream, [1] for the
+  // auxiliary stream that runs a small independent MSM beside the main one (verifier: proof points)
+  uint8_t* ws = nullptr;
+  size_t ws_cap = 0;
+  uint8_t* ws_aux = nullptr;
+  size_t ws_aux_cap = 0;
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_chunk[8] = {};  // scalar upload in pieces (host_feed), created on first use
+  // transient-allocation cache (dev_alloc / dev_free)
+  std::vector<std::pair<void*, size_t>> cache;
+  std::unordered_map<void*, size_t> live;
+  // small staging buffers
+  uint8_t* d_small = nullptr;   // device scratch for results (>= 64 KB)
+  uint8_t* h_pinned = nullptr;  // pinned host scratch (>= 64 KB)
+  // staging for host-buffer calls
+  uint8_t* d_stage = nullptr;
+  size_t d_stage_cap = 0;
+};
+
+struct bpg_table {
+  bpg_ctx* ctx;
+  uint32_t* niels;  // n * 24 words; windowed: [W][n] * 24 words
+  size_t n;
+  int win_c = 0;    // 0: plain; otherwise the window width the multiples 2^(c w) P_i were built for
+  int win_W = 1;
+};
+
+#define CK(call)                                  \
+  do {                                            \
+    cudaError_t e_ = (call);                      \
+    if (e_ != cudaSuccess) {                      \
+      ctx->last_cuda = (int)e_;                   \
+      return BPG_ERR_CUDA;                        \
+    }                                             \
+  } while (0)
+
+#define LAUNCH_CHECK()                            \
+  do {                                            \
+    ctx->launches++;                              \
+    cudaError_t e_ = cudaGetLastError();          \
+    if (e_ != cudaSuccess) {                      \
+      ctx->last_cuda = (int)e_;                   \
+      return BPG_ERR_CUDA;                        \
+    }                                             \
+  } while (0)
+
+cudaError_t dev_alloc(bpg_ctx* ctx, void** p, size_t bytes);
+template <typename T>
+static inline cudaError_t dev_alloc(bpg_ctx* ctx, T** p, size_t bytes) {
+  return dev_alloc(ctx, reinterpret_cast<void**>(p), bytes);
+}
+void dev_free(bpg_ctx* ctx, void* p);
+constexpr size_t SMALL_BYTES = 1 << 16;
+void prof_mark(bpg_ctx* ctx, int phase);
+int ensure_ws(bpg_ctx* ctx, size_t bytes, int lane = 0);
+int ensure_stage(bpg_ctx* ctx, size_t bytes);
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+int pick_window(size_t n_per_set, int forced);
+int pick_window_table(size_t n, int forced);
+int table_alloc_plain(bpg_ctx* ctx, size_t n, bpg_table** out);
+static inline bpg::sc_bias bias_for(int c) {
+  bpg::sc_bias b;
+  memset(&b, 0, sizeof b);
+  int W = (255 + c - 1) / c;
+  for (int w = 0; w < W; w++) {
+    int bit = c * w + c - 1;
+    b.v[bit >> 5] |= 1u << (bit & 31);
+  }
+  return b;
+}
+// Enqueue one Pippenger launch (msm.cu).  d_scalars: n_terms*32 B; d_set_ids / d_point_ids may be null
+// (implicit: term t -> point t % n_points of `table_base`, set t / n_points).
+int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points, const uint32_t* d_scalars, size_t n_terms,
+                const uint8_t* d_set_ids, const uint32_t* d_point_ids, int nsets, uint32_t* d_out_ext, int win_c = 0,
+                size_t win_stride = 0, int lane = 0, int curve = 0, const uint8_t* h_scalars = nullptr);
+// one sum over ad-hoc compressed points + ranges of resident tables, scalars already on the device (core.cu)
+int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_adhoc, const bpg_table* const* tabs,
+                   const size_t* offs, const size_t* lens, int nsegs, const uint32_t* d_scalars, size_t total,
+                   uint8_t out[32], bool identity_only = false);
+cudaError_t msm_kernels_init();  // msm.cu: function attributes of the pipeline kernels
+// point-level kernels launched on behalf of other translation units (core.cu)
+void launch_decode_to_niels(bpg_ctx* ctx, cudaStream_t s, const uint8_t* d_comp, size_t n, uint32_t* niels, uint32_t* bad);
+void launch_comb_build(bpg_ctx* ctx, cudaStream_t s, const uint8_t* d_base32, uint32_t* table, uint32_t* bad);
+void launch_comb_mul(bpg_ctx* ctx, cudaStream_t s, const uint32_t* tables, int nbases, const uint32_t* d_scalars, size_t n,
+                     uint8_t* d_out_bytes, uint32_t* d_out_ext);
+// IPP state over device-resident vectors (ipp.cu)
+int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off, size_t n,
+                  const uint8_t* Q_host, const bpg_table* shared, size_t g_base, size_t h_base, size_t q_id,
+                  const uint8_t* q_mul_host, const uint32_t* d_gf, const uint32_t* d_hf, const uint32_t* d_a,
+                  const uint32_t* d_b, bpg_ipp** out);

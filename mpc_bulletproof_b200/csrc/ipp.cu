@@ -1,0 +1,271 @@
+// libbpgpu: inner-product argument, device-resident state, one MSM per round.
+#include "internal.cuh"
+#include "ipp_kernels.cuh"
+
+using namespace bpg;
+
+// ---------------------------------------------------------------------------
+// inner-product argument: device-resident state, one MSM per round
+// ---------------------------------------------------------------------------
+struct bpg_ipp {
+  bpg_ctx* ctx;
+  size_t n;        // original length (power of two)
+  size_t m;        // current length
+  const bpg_table* tab;  // windowed table the round MSMs run over
+  bpg_table* own_tab;    // non-null when the state built its own [G | H | Q] table
+  bool has_qmul;         // cross terms are multiplied by q_mul (Q = q_mul * table[q_id])
+  bool q_sep;            // Q is outside the (caller's windowed) table: c_L Q, c_R Q come from a comb of Q
+  uint32_t *q_comb, *q_side;
+  uint8_t* buf;    // one allocation for everything below
+  uint32_t *a, *b, *wG, *wH, *scalars, *point_ids, *partials, *u_pair, *out_ext;
+  uint32_t* q_mul;
+  uint8_t *set_ids, *out_bytes;
+  bool lr_done;
+};
+
+
+// d_* pointers are device pointers; factors may be null (all ones).
+// Either (G, H, Q_host) are given and the state builds its own windowed [G | H | Q] table,
+// or `shared` is a windowed table that already holds the generators at g_base/h_base and a
+// base point at q_id with Q = q_mul * shared[q_id] (the R1CS prover's Q = w*B).
+int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off, size_t n,
+                         const uint8_t* Q_host, const bpg_table* shared, size_t g_base, size_t h_base, size_t q_id,
+                         const uint8_t* q_mul_host, const uint32_t* d_gf, const uint32_t* d_hf, const uint32_t* d_a,
+                         const uint32_t* d_b, bpg_ipp** out) {
+  if (n == 0 || (n & (n - 1))) return BPG_ERR_POW2;
+  if (n >= (1u << 28)) return BPG_ERR_ARG;
+  if (shared) {
+    if (g_base + n > shared->n || h_base + n > shared->n || q_id >= shared->n) return BPG_ERR_CAPACITY;
+    if (!shared->win_c && n > 1) return BPG_ERR_ARG;
+  } else if (g_off + n > G->n || h_off + n > H->n) {
+    return BPG_ERR_CAPACITY;
+  }
+  bpg_ipp* st = new (std::nothrow) bpg_ipp();
+  if (!st) return BPG_ERR_NOMEM;
+  memset(st, 0, sizeof *st);
+  st->ctx = ctx;
+  st->n = st->m = n;
+  int rc = BPG_OK;
+  size_t T = 2 * n + 2;
+  size_t nparts = 256;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  size_t o_a = take(n * 32), o_b = take(n * 32), o_wG = take(n * 32), o_wH = take(n * 32);
+  size_t o_sc = take(T * 32), o_pid = take(T * 4), o_set = take(T), o_part = take(nparts * 64);
+  size_t o_u = take(64), o_ext = take(4 * 128), o_bytes = take(64), o_q = take(32), o_qm = take(32);
+  size_t o_qside = take(64), o_qcomb = take((size_t)COMB_ENTRIES * 96);
+  do {
+    cudaError_t e = dev_alloc(ctx, &st->buf, off);
+    if (e != cudaSuccess) { ctx->last_cuda = (int)e; rc = BPG_ERR_NOMEM; break; }
+    st->a = (uint32_t*)(st->buf + o_a); st->b = (uint32_t*)(st->buf + o_b);
+    st->wG = (uint32_t*)(st->buf + o_wG); st->wH = (uint32_t*)(st->buf + o_wH);
+    st->scalars = (uint32_t*)(st->buf + o_sc); st->point_ids = (uint32_t*)(st->buf + o_pid);
+    st->set_ids = st->buf + o_set; st->partials = (uint32_t*)(st->buf + o_part);
+    st->u_pair = (uint32_t*)(st->buf + o_u); st->out_ext = (uint32_t*)(st->buf + o_ext);
+    st->out_bytes = st->buf + o_bytes;
+    st->q_mul = (uint32_t*)(st->buf + o_qm);
+    st->q_side = (uint32_t*)(st->buf + o_qside);
+    st->q_comb = (uint32_t*)(st->buf + o_qcomb);
+    uint8_t* d_q = st->buf + o_q;
+    cudaStream_t s = ctx->stream;
+    if (cudaMemcpyAsync(st->a, d_a, n * 32, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(st->b, d_b, n * 32, cudaMemcpyDeviceToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+    unsigned gn = (unsigned)((n + 255) / 256);
+    k_ipp_init_weights<<<gn, 256, 0, s>>>(d_gf, d_hf, (uint32_t)n, st->wG, st->wH);
+    ctx->launches++;
+    if (shared) {
+      st->tab = shared;
+      st->has_qmul = q_mul_host != nullptr;
+      if (q_mul_host) {
+        memcpy(ctx->h_pinned + 512, q_mul_host, 32);
+        if (cudaMemcpyAsync(st->q_mul, ctx->h_pinned + 512, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+      }
+      k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, (uint32_t)g_base, (uint32_t)h_base, (uint32_t)q_id);
+      ctx->launches++;
+      if (cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+    } else if (G == H && G->win_c && n > 1) {
+      // The caller's generators already live in ONE windowed table (a resident BulletproofGens):
+      // run the round MSMs over it as they are and form c_L Q, c_R Q from a fixed-base comb of Q
+      // built here once, on the auxiliary stream beside each round's MSM.
+      st->tab = G;
+      st->q_sep = true;
+      k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, (uint32_t)g_off, (uint32_t)h_off, (uint32_t)g_off);
+      ctx->launches++;
+      memcpy(ctx->h_pinned + 512, Q_host, 32);
+      uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small);
+      if (cudaMemsetAsync(bad, 0, 4, s) != cudaSuccess ||
+          cudaMemcpyAsync(d_q, ctx->h_pinned + 512, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+      launch_comb_build(ctx, s, d_q, st->q_comb, bad);
+      uint32_t* hbad = reinterpret_cast<uint32_t*>(ctx->h_pinned);
+      if (cudaMemcpyAsync(hbad, bad, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+          cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+      if (*hbad) { rc = BPG_ERR_DECODE; break; }
+    } else {
+      k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, 0u, (uint32_t)n, (uint32_t)(2 * n));
+      ctx->launches++;
+      // combined table [G | H | Q]
+      rc = table_alloc_plain(ctx, 2 * n + 1, &st->own_tab);
+      if (rc) break;
+      st->tab = st->own_tab;
+      if (cudaMemcpyAsync(st->own_tab->niels, G->niels + g_off * 24, n * 96, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+          cudaMemcpyAsync(st->own_tab->niels + n * 24, H->niels + h_off * 24, n * 96, cudaMemcpyDeviceToDevice, s) !=
+              cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+      memcpy(ctx->h_pinned + 512, Q_host, 32);
+      uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small);
+      if (cudaMemsetAsync(bad, 0, 4, s) != cudaSuccess ||
+          cudaMemcpyAsync(d_q, ctx->h_pinned + 512, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+      launch_decode_to_niels(ctx, s, d_q, 1, st->own_tab->niels + 2 * n * 24, bad);
+      uint32_t* hbad = reinterpret_cast<uint32_t*>(ctx->h_pinned);
+      if (cudaMemcpyAsync(hbad, bad, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+          cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+      if (*hbad) { rc = BPG_ERR_DECODE; break; }
+      if (n > 1) {
+        rc = bpg_table_set_windows(ctx, st->own_tab, pick_window(n + 1, ctx->forced_c));
+        if (rc) break;
+      }
+    }
+  } while (0);
+  if (rc != BPG_OK) {
+    if (st->own_tab) bpg_table_free(st->own_tab);
+    dev_free(ctx, st->buf);
+    delete st;
+    return rc;
+  }
+  *out = st;
+  return BPG_OK;
+}
+
+extern "C" int bpg_ipp_begin(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off,
+                             size_t n, const uint8_t Q[32], const uint8_t* G_factors, const uint8_t* H_factors,
+                             const uint8_t* a, const uint8_t* b, bpg_ipp** out) {
+  if (!ctx || !G || !H || !Q || !a || !b || !out) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_stage(ctx, 4 * n * 32 + 64);
+  if (rc) return rc;
+  uint8_t* d = ctx->d_stage;
+  CK(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d + n * 32, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (G_factors) CK(cudaMemcpyAsync(d + 2 * n * 32, G_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (H_factors) CK(cudaMemcpyAsync(d + 3 * n * 32, H_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  return ipp_begin_dev(ctx, G, g_off, H, h_off, n, Q, nullptr, 0, 0, 0, nullptr,
+                       G_factors ? (const uint32_t*)(d + 2 * n * 32) : nullptr,
+                       H_factors ? (const uint32_t*)(d + 3 * n * 32) : nullptr, (const uint32_t*)d,
+                       (const uint32_t*)(d + n * 32), out);
+}
+
+extern "C" int bpg_ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off,
+                                 size_t n, const uint8_t Q[32], const void* d_G_factors, const void* d_H_factors,
+                                 const void* d_a, const void* d_b, bpg_ipp** out) {
+  if (!ctx || !G || !H || !Q || !d_a || !d_b || !out) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  return ipp_begin_dev(ctx, G, g_off, H, h_off, n, Q, nullptr, 0, 0, 0, nullptr, (const uint32_t*)d_G_factors,
+                       (const uint32_t*)d_H_factors, (const uint32_t*)d_a, (const uint32_t*)d_b, out);
+}
+
+// Generators and the base of Q live in one windowed table (the R1CS prover: G at g_base, H at
+// h_base, Q = q_mul * shared[q_id] with q_id the Pedersen base B and q_mul the challenge w).
+extern "C" int bpg_ipp_begin_shared(bpg_ctx* ctx, const bpg_table* shared, size_t g_base, size_t h_base, size_t q_id,
+                                    const uint8_t q_mul[32], size_t n, const uint8_t* G_factors,
+                                    const uint8_t* H_factors, const uint8_t* a, const uint8_t* b, bpg_ipp** out) {
+  if (!ctx || !shared || !a || !b || !out) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_stage(ctx, 4 * n * 32 + 64);
+  if (rc) return rc;
+  uint8_t* d = ctx->d_stage;
+  CK(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d + n * 32, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (G_factors) CK(cudaMemcpyAsync(d + 2 * n * 32, G_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (H_factors) CK(cudaMemcpyAsync(d + 3 * n * 32, H_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  return ipp_begin_dev(ctx, nullptr, 0, nullptr, 0, n, nullptr, shared, g_base, h_base, q_id, q_mul,
+                       G_factors ? (const uint32_t*)(d + 2 * n * 32) : nullptr,
+                       H_factors ? (const uint32_t*)(d + 3 * n * 32) : nullptr, (const uint32_t*)d,
+                       (const uint32_t*)(d + n * 32), out);
+}
+
+extern "C" size_t bpg_ipp_rounds_left(const bpg_ipp* st) {
+  size_t r = 0;
+  if (!st) return 0;
+  for (size_t m = st->m; m > 1; m >>= 1) r++;
+  return r;
+}
+
+extern "C" int bpg_ipp_round_LR(bpg_ipp* st, uint8_t L[32], uint8_t R[32]) {
+  if (!st || !L || !R) return BPG_ERR_ARG;
+  if (st->m <= 1 || st->lr_done) return BPG_ERR_ARG;
+  bpg_ctx* ctx = st->ctx;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  size_t n = st->n, m = st->m, h = m / 2;
+  unsigned gcross = (unsigned)std::min<size_t>(256, (h + IPP_THREADS - 1) / IPP_THREADS);
+  prof_mark(ctx, BPG_PROF_OTHER);
+  k_ipp_cross<<<gcross, IPP_THREADS, 0, s>>>(st->a, st->b, (uint32_t)h, st->partials);
+  LAUNCH_CHECK();
+  k_ipp_round_scalars<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st->a, st->b, st->wG, st->wH, (uint32_t)n,
+                                                                  (uint32_t)m, st->scalars, st->set_ids);
+  LAUNCH_CHECK();
+  k_ipp_cross_finish<<<1, IPP_THREADS, 0, s>>>(st->partials, gcross, (uint32_t)n, st->has_qmul ? st->q_mul : nullptr,
+                                               st->scalars, st->set_ids, st->q_sep ? st->q_side : nullptr);
+  LAUNCH_CHECK();
+  if (st->q_sep) {
+    // c_L Q, c_R Q: 64 mixed additions each from the comb of Q, beside the MSM
+    CK(cudaEventRecord(ctx->ev_fork, s));
+    CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    launch_comb_mul(ctx, ctx->aux_stream, st->q_comb, 1, st->q_side, 2, nullptr, st->out_ext + 64);
+    CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+  }
+  int rc = msm_enqueue(ctx, st->tab->niels, st->tab->n, st->scalars, 2 * n + 2, st->set_ids, st->point_ids, 2,
+                       st->out_ext, st->tab->win_c, st->tab->n);
+  if (rc) return rc;
+  if (st->q_sep) CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+  rc = bpg_dev_sum_encode(ctx, st->out_ext, st->q_sep ? 2 : 1, 2, st->out_bytes, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->h_pinned, st->out_bytes, 64, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  memcpy(L, ctx->h_pinned, 32);
+  memcpy(R, ctx->h_pinned + 32, 32);
+  st->lr_done = true;
+  return BPG_OK;
+}
+
+extern "C" int bpg_ipp_round_fold(bpg_ipp* st, const uint8_t u[32], const uint8_t u_inv[32]) {
+  if (!st || !u || !u_inv) return BPG_ERR_ARG;
+  if (st->m <= 1 || !st->lr_done) return BPG_ERR_ARG;
+  bpg_ctx* ctx = st->ctx;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  // the challenge pair travels as kernel arguments: no staging copy, and no wait here -- the
+  // next round's launches queue up behind the fold
+  ScPair up;
+  memcpy(up.v, u, 32);
+  memcpy(up.v + 8, u_inv, 32);
+  prof_mark(ctx, BPG_PROF_OTHER);
+  k_ipp_fold<<<(unsigned)((st->n + 255) / 256), 256, 0, s>>>(st->a, st->b, st->wG, st->wH, (uint32_t)st->n,
+                                                             (uint32_t)st->m, up);
+  LAUNCH_CHECK();
+  prof_mark(ctx, -1);
+  st->m /= 2;
+  st->lr_done = false;
+  return BPG_OK;
+}
+
+extern "C" int bpg_ipp_finish(bpg_ipp* st, uint8_t a[32], uint8_t b[32]) {
+  if (!st || !a || !b) return BPG_ERR_ARG;
+  if (st->m != 1) return BPG_ERR_ARG;
+  bpg_ctx* ctx = st->ctx;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->h_pinned, st->a, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_pinned + 32, st->b, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(a, ctx->h_pinned, 32);
+  memcpy(b, ctx->h_pinned + 32, 32);
+  return BPG_OK;
+}
+
+extern "C" void bpg_ipp_free(bpg_ipp* st) {
+  if (!st) return;
+  cudaSetDevice(st->ctx->device);
+  if (st->q_sep) cudaStreamSynchronize(st->ctx->aux_stream);
+  if (st->own_tab) bpg_table_free(st->own_tab);
+  dev_free(st->ctx, st->buf);
+  delete st;
+}

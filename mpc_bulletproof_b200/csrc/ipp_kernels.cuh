@@ -22,7 +22,7 @@
 namespace bpg {
 
 // wG/wH are kept in Montgomery form so that montmul(normal, mont) lands in normal form.
-__global__ void __launch_bounds__(256) k_ipp_init_weights(const uint32_t* __restrict__ g_factors,
+static __global__ void __launch_bounds__(256) k_ipp_init_weights(const uint32_t* __restrict__ g_factors,
                                                            const uint32_t* __restrict__ h_factors, uint32_t n,
                                                            uint32_t* __restrict__ wG, uint32_t* __restrict__ wH) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,7 +69,7 @@ __device__ __forceinline__ void block_sum2(sc& x, sc& y, uint32_t (*sm)[16]) {
 
 // partial cross terms: c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo> (:87-88, :156-157); Montgomery-scaled
 constexpr int IPP_THREADS = 256;
-__global__ void __launch_bounds__(IPP_THREADS) k_ipp_cross(const uint32_t* __restrict__ a,
+static __global__ void __launch_bounds__(IPP_THREADS) k_ipp_cross(const uint32_t* __restrict__ a,
                                                             const uint32_t* __restrict__ b, uint32_t h,
                                                             uint32_t* __restrict__ partials /*[grid][16]*/) {
   __shared__ uint32_t sm[IPP_THREADS / 2][16];
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(IPP_THREADS) k_ipp_cross(const uint32_t* __res
 }
 
 // single block: finish the cross terms and append them as the Q terms of the round's MSM
-__global__ void __launch_bounds__(IPP_THREADS) k_ipp_cross_finish(const uint32_t* __restrict__ partials,
+static __global__ void __launch_bounds__(IPP_THREADS) k_ipp_cross_finish(const uint32_t* __restrict__ partials,
                                                                    uint32_t nparts, uint32_t n,
                                                                    const uint32_t* __restrict__ q_mul /*null or scalar*/,
                                                                    uint32_t* __restrict__ scalars,
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(IPP_THREADS) k_ipp_cross_finish(const uint32_t
 }
 
 // the round's 2n generator scalars and their output set (0 = L, 1 = R)
-__global__ void __launch_bounds__(256) k_ipp_round_scalars(const uint32_t* __restrict__ a,
+static __global__ void __launch_bounds__(256) k_ipp_round_scalars(const uint32_t* __restrict__ a,
                                                             const uint32_t* __restrict__ b,
                                                             const uint32_t* __restrict__ wG,
                                                             const uint32_t* __restrict__ wH, uint32_t n, uint32_t m,
@@ -160,7 +160,7 @@ struct ScPair {
 };
 
 // fold_witness (:202-248) for a, b; the generator fold becomes a weight update
-__global__ void __launch_bounds__(256) k_ipp_fold(uint32_t* __restrict__ a, uint32_t* __restrict__ b,
+static __global__ void __launch_bounds__(256) k_ipp_fold(uint32_t* __restrict__ a, uint32_t* __restrict__ b,
                                                    uint32_t* __restrict__ wG, uint32_t* __restrict__ wH, uint32_t n,
                                                    uint32_t m, ScPair u_pair /*u, u_inv: kernel arguments, no copy*/) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) k_ipp_fold(uint32_t* __restrict__ a, uint
 }
 
 // point ids of the round MSM's 2n+2 terms: G_i, H_i, Q, Q
-__global__ void k_ipp_point_ids(uint32_t* out, uint32_t n, uint32_t g_base, uint32_t h_base, uint32_t q_id) {
+static __global__ void k_ipp_point_ids(uint32_t* out, uint32_t n, uint32_t g_base, uint32_t h_base, uint32_t q_id) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     out[i] = g_base + i;

@@ -15,8 +15,12 @@ struct sc {
   uint32_t v[8];
 };
 
+// signed 4-bit windows of a 256-bit scalar: the fixed-base comb (64 x 8 multiples) and the few-term MSM
+constexpr int COMB_WINDOWS = 64;
+constexpr int COMB_ENTRIES = COMB_WINDOWS * 8;
+
 #define BPG_DEF_CONST_SC(name, ...)                         \
-  __device__ __constant__ uint32_t name[8] = {__VA_ARGS__}; \
+  static __device__ __constant__ uint32_t name[8] = {__VA_ARGS__}; \
   static const uint32_t name##_h[8] = {__VA_ARGS__};
 #ifndef BPG_K
 #if defined(__CUDA_ARCH__)
@@ -237,6 +241,45 @@ BPG_DI int sc_digit(const sc_recoded& r, int w, int c) {
   uint64_t two = ((uint64_t)hi << 32) | lo;
   uint32_t raw = (uint32_t)(two >> sh) & ((1u << c) - 1u);
   return (int)raw - (1 << (c - 1));
+}
+
+// ---- ChaCha20 block -> scalar (the device side of the keyed blinding vectors, svec_kernels.cuh) ----
+struct ChaKey {
+  uint32_t k[8];
+};
+BPG_DI void chacha_qr(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  a += b; d ^= a; d = (d << 16) | (d >> 16);
+  c += d; b ^= c; b = (b << 12) | (b >> 20);
+  a += b; d ^= a; d = (d << 8) | (d >> 24);
+  c += d; b ^= c; b = (b << 7) | (b >> 25);
+}
+BPG_DI sc sc_from_chacha_block(const ChaKey& key, uint32_t block) {
+  uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key.k[0], key.k[1], key.k[2], key.k[3],
+                     key.k[4],    key.k[5],    key.k[6],    key.k[7],    block,    0x20677062u, 0x52734c73u, 0x31307620u};
+  uint32_t x[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) x[i] = in[i];
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    chacha_qr(x[0], x[4], x[8], x[12]);
+    chacha_qr(x[1], x[5], x[9], x[13]);
+    chacha_qr(x[2], x[6], x[10], x[14]);
+    chacha_qr(x[3], x[7], x[11], x[15]);
+    chacha_qr(x[0], x[5], x[10], x[15]);
+    chacha_qr(x[1], x[6], x[11], x[12]);
+    chacha_qr(x[2], x[7], x[8], x[13]);
+    chacha_qr(x[3], x[4], x[9], x[14]);
+  }
+  sc lo, hi;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    lo.v[i] = x[i] + in[i];
+    hi.v[i] = x[8 + i] + in[8 + i];
+  }
+  sc rr = sc_const(BPG_K(K_RR));
+  sc lo_m = sc_montmul(lo, rr);
+  sc hi_m = sc_montmul(sc_montmul(hi, rr), rr);
+  return sc_add(lo_m, hi_m);
 }
 
 }  // namespace bpg

@@ -20,7 +20,7 @@ struct fp {
 };
 
 #define BPG_DEF_CONST_FP(name, ...)                         \
-  __device__ __constant__ uint32_t name[8] = {__VA_ARGS__}; \
+  static __device__ __constant__ uint32_t name[8] = {__VA_ARGS__}; \
   static const uint32_t name##_h[8] = {__VA_ARGS__};
 
 BPG_DEF_CONST_FP(KS_P, 0x00000001u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000011u,

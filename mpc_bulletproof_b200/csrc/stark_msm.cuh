@@ -12,35 +12,14 @@
 // Replaces `StarkPoint::msm_iter` / `::msm` (mpc-stark over ark-ec) at the call sites of
 // SURVEY.md 2.2 for the instantiation the mounted fork itself uses.
 #pragma once
-#include "msm_kernels.cuh"
+#include "msm_sort_kernels.cuh"
 #include "stark_pt.cuh"
 #include "stark_pt4.cuh"
 
 namespace bpg {
 
-__global__ void __launch_bounds__(128) k_stark_decode(const uint8_t* __restrict__ xy, uint32_t n,
-                                                       uint32_t* __restrict__ table /*[n][16]*/,
-                                                       uint32_t* __restrict__ bad_count) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint4* src = reinterpret_cast<const uint4*>(xy + (size_t)i * 64);
-  uint32_t w[16];
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    uint4 a = src[k];
-    w[4 * k] = a.x; w[4 * k + 1] = a.y; w[4 * k + 2] = a.z; w[4 * k + 3] = a.w;
-  }
-  sp_aff q;
-  if (!sp_from_affine_words(q, w)) {
-    q.x = fp_zero();
-    q.y = fp_zero();
-    atomicAdd(bad_count, 1u);
-  }
-  sp_aff_store(table + (size_t)i * 16, q);
-}
-
 constexpr int SACC_THREADS = 128;
-__global__ void __launch_bounds__(SACC_THREADS, 1) k_stark_accum(const uint32_t* __restrict__ table,
+static __global__ void __launch_bounds__(SACC_THREADS, 1) k_stark_accum(const uint32_t* __restrict__ table,
                                                                   const uint32_t* __restrict__ offsets,
                                                                   const uint32_t* __restrict__ entries, AccSched sc,
                                                                   uint32_t* __restrict__ bucket_sums,
@@ -73,7 +52,7 @@ __global__ void __launch_bounds__(SACC_THREADS, 1) k_stark_accum(const uint32_t*
 }
 
 // multi-segment buckets (<= BIG_SEG / ACC_SEG partial sums): one thread adds them
-__global__ void __launch_bounds__(128) k_stark_fix(const uint32_t* __restrict__ offsets, AccSched sc,
+static __global__ void __launch_bounds__(128) k_stark_fix(const uint32_t* __restrict__ offsets, AccSched sc,
                                                     const uint32_t* __restrict__ seg_part,
                                                     uint32_t* __restrict__ bucket_sums) {
   uint32_t nmulti = *sc.multi_count;
@@ -94,7 +73,7 @@ __global__ void __launch_bounds__(128) k_stark_fix(const uint32_t* __restrict__ 
 
 // over-long buckets: one block per segment of BIG_SEG entries, strided accumulation, shared-memory tree
 constexpr int SBIG_THREADS = 256;
-__global__ void __launch_bounds__(SBIG_THREADS) k_stark_big(const uint32_t* __restrict__ table,
+static __global__ void __launch_bounds__(SBIG_THREADS) k_stark_big(const uint32_t* __restrict__ table,
                                                              const uint32_t* __restrict__ offsets,
                                                              const uint32_t* __restrict__ entries, MsmCfg cfg,
                                                              uint32_t* __restrict__ bucket_sums,
@@ -131,7 +110,7 @@ __global__ void __launch_bounds__(SBIG_THREADS) k_stark_big(const uint32_t* __re
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(128) k_stark_big_fin(MsmCfg cfg, uint32_t* __restrict__ bucket_sums,
+static __global__ void __launch_bounds__(128) k_stark_big_fin(MsmCfg cfg, uint32_t* __restrict__ bucket_sums,
                                                         const uint32_t* __restrict__ big_count,
                                                         const uint32_t* __restrict__ big_list,
                                                         const uint32_t* __restrict__ big_part) {
@@ -152,7 +131,7 @@ __global__ void __launch_bounds__(128) k_stark_big_fin(MsmCfg cfg, uint32_t* __r
 
 // ---- bucket reduction: T = sum_{j<n} (j+1) X_j per array, pairs (A, Y) with T = sum A_q + sum q Y_q ----
 constexpr uint32_t SLEAF_LC = 8;
-__global__ void __launch_bounds__(128) k_stark_leaf(const uint32_t* __restrict__ in /*[narr][n] XYZZ*/, uint32_t n,
+static __global__ void __launch_bounds__(128) k_stark_leaf(const uint32_t* __restrict__ in /*[narr][n] XYZZ*/, uint32_t n,
                                                      uint32_t chunks, uint32_t narr, uint32_t* __restrict__ out_a,
                                                      uint32_t* __restrict__ out_y) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,7 +155,7 @@ __global__ void __launch_bounds__(128) k_stark_leaf(const uint32_t* __restrict__
 
 // up to 64 pairs per block -> one: binary tree A' = A0 + A1 + Y1, Y' = 2 (Y0 + Y1), one thread per output pair
 constexpr uint32_t SPAIR_N = 64;
-__global__ void __launch_bounds__(SPAIR_N) k_stark_pairs(const uint32_t* __restrict__ in_a,
+static __global__ void __launch_bounds__(SPAIR_N) k_stark_pairs(const uint32_t* __restrict__ in_a,
                                                           const uint32_t* __restrict__ in_y, uint32_t n,
                                                           uint32_t tiles, uint32_t* __restrict__ out_a,
                                                           uint32_t* __restrict__ out_y) {
@@ -227,7 +206,7 @@ __global__ void __launch_bounds__(SPAIR_N) k_stark_pairs(const uint32_t* __restr
 }
 
 // one thread per set: sum_w 2^(c w) S_w, top window first
-__global__ void __launch_bounds__(32) k_stark_horner(const uint32_t* __restrict__ window_sums, MsmCfg cfg,
+static __global__ void __launch_bounds__(32) k_stark_horner(const uint32_t* __restrict__ window_sums, MsmCfg cfg,
                                                       uint32_t* __restrict__ out) {
   uint32_t set = blockIdx.x * blockDim.x + threadIdx.x;
   if (set >= (uint32_t)cfg.nsets) return;
@@ -243,77 +222,12 @@ __global__ void __launch_bounds__(32) k_stark_horner(const uint32_t* __restrict_
   sp_store(out + (size_t)set * 32, acc);
 }
 
-// parts laid out [part][set][32 words]: sum over parts, then affine bytes (x || y, 32 LE each; identity = 0)
-__global__ void k_stark_finish(const uint32_t* __restrict__ parts, int nparts, int nsets, uint8_t* __restrict__ out_xy) {
-  int set = blockIdx.x * blockDim.x + threadIdx.x;
-  if (set >= nsets) return;
-  sp_xyzz acc;
-  sp_load(acc, parts + (size_t)set * 32);
-  for (int p = 1; p < nparts; p++) {
-    sp_xyzz o;
-    sp_load(o, parts + ((size_t)p * nsets + set) * 32);
-    acc = sp_add(acc, o);
-  }
-  uint32_t w[16];
-  sp_to_affine_words(w, acc);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(out_xy + (size_t)set * 64);
-#pragma unroll
-  for (int i = 0; i < 16; i++) dst[i] = w[i];
-}
-
-__global__ void k_stark_set_identity(uint32_t* __restrict__ out) {
+static __global__ void k_stark_set_identity(uint32_t* __restrict__ out) {
   out[(size_t)blockIdx.x * 32 + threadIdx.x] = 0u;
 }
 
-// windowed tables: out[w][i] = 2^(c w) * P_i, affine, w < W.  One thread per point walks the doubling
-// chain in XYZZ, parks the multiples and the running product of their ZZ*ZZZ in scratch, inverts
-// once (Montgomery's trick) and converts every multiple back to affine (1/ZZ = t ZZZ, 1/ZZZ = t ZZ
-// with t = 1/(ZZ ZZZ)).  One-time cost at table upload; it removes every doubling from later MSMs.
-__global__ void __launch_bounds__(128) k_stark_window_chain(const uint32_t* __restrict__ aff_in, uint32_t n_total,
-                                                             uint32_t first, uint32_t count, int c, int W,
-                                                             uint32_t* __restrict__ pt_scratch /*[W-1][count][32]*/,
-                                                             uint32_t* __restrict__ dp_scratch /*[W-1][count][8]*/,
-                                                             uint32_t* __restrict__ out /*[W][n_total][16]*/) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  uint32_t i = first + t;
-  sp_aff q;
-  sp_aff_load(q, aff_in + (size_t)i * 16);
-  sp_aff_store(out + (size_t)i * 16, q);  // window 0
-  if (sp_aff_is_identity(q)) {
-    for (int w = 1; w < W; w++) sp_aff_store(out + ((size_t)w * n_total + i) * 16, q);
-    return;
-  }
-  sp_xyzz p = sp_from_aff(q);
-  fp dp = fp_one();
-  for (int w = 1; w < W; w++) {
-    for (int k = 0; k < c; k++) p = sp_dbl(p);  // prime order: never the identity
-    dp = fp_mul(dp, fp_mul(p.ZZ, p.ZZZ));
-    sp_store(pt_scratch + ((size_t)(w - 1) * count + t) * 32, p);
-    fp_store(dp_scratch + ((size_t)(w - 1) * count + t) * 8, dp);
-  }
-  fp inv = fp_invert(dp);
-  for (int w = W - 1; w >= 1; w--) {
-    sp_xyzz e;
-    sp_load(e, pt_scratch + ((size_t)(w - 1) * count + t) * 32);
-    fp ti;
-    if (w >= 2) {
-      fp prev;
-      fp_load(prev, dp_scratch + ((size_t)(w - 2) * count + t) * 8);
-      ti = fp_mul(inv, prev);
-    } else {
-      ti = inv;
-    }
-    inv = fp_mul(inv, fp_mul(e.ZZ, e.ZZZ));
-    sp_aff a;
-    a.x = fp_mul(e.X, fp_mul(ti, e.ZZZ));
-    a.y = fp_mul(e.Y, fp_mul(ti, e.ZZ));
-    sp_aff_store(out + ((size_t)w * n_total + i) * 16, a);
-  }
-}
-
 // windowed tables with several bucket groups per set: merged[set][b] = sum_g bucket_sums[set][g][b]
-__global__ void __launch_bounds__(128) k_stark_merge(const uint32_t* __restrict__ bucket_sums, MsmCfg cfg,
+static __global__ void __launch_bounds__(128) k_stark_merge(const uint32_t* __restrict__ bucket_sums, MsmCfg cfg,
                                                       uint32_t* __restrict__ merged) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t total = (uint32_t)cfg.nsets * cfg.nb;
@@ -398,7 +312,7 @@ __global__ void __launch_bounds__(SRT_THREADS) k_stark_leaf4(const uint32_t* __r
 // up to 64 pairs per block -> one (the final launch has tiles == 1 and writes T to out_a)
 constexpr int SRP_THREADS = 128;
 constexpr uint32_t SRP_PAIRS = SRP_THREADS / 2;
-__global__ void __launch_bounds__(SRP_THREADS) k_stark_pairs4(const uint32_t* __restrict__ in_a,
+static __global__ void __launch_bounds__(SRP_THREADS) k_stark_pairs4(const uint32_t* __restrict__ in_a,
                                                                const uint32_t* __restrict__ in_y, uint32_t n,
                                                                uint32_t tiles, uint32_t* __restrict__ out_a,
                                                                uint32_t* __restrict__ out_y) {
@@ -422,7 +336,7 @@ __global__ void __launch_bounds__(SRP_THREADS) k_stark_pairs4(const uint32_t* __
 }
 
 // plain tables, one warp per set: sum_w 2^(c w) S_w, every quad runs the same chain
-__global__ void __launch_bounds__(32) k_stark_horner4(const uint32_t* __restrict__ window_sums, MsmCfg cfg,
+static __global__ void __launch_bounds__(32) k_stark_horner4(const uint32_t* __restrict__ window_sums, MsmCfg cfg,
                                                        uint32_t* __restrict__ out) {
   uint32_t set = blockIdx.x;
   const uint32_t* src = window_sums + (size_t)set * cfg.W * 32;

@@ -92,7 +92,7 @@ __device__ __forceinline__ sc sc_from_stream_block(unsigned long long key, unsig
   sc hi_m = sc_montmul(sc_montmul(hi, rr), rr);  // hi R -> hi R^2 = Montgomery form of hi*R
   return sc_add(lo_m, hi_m);
 }
-__global__ void __launch_bounds__(256) k_blind_vectors(unsigned long long key, uint32_t n, uint32_t* __restrict__ sL,
+static __global__ void __launch_bounds__(256) k_blind_vectors(unsigned long long key, uint32_t n, uint32_t* __restrict__ sL,
                                                         uint32_t* __restrict__ sR /*[n][8] mont*/) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -100,9 +100,21 @@ __global__ void __launch_bounds__(256) k_blind_vectors(unsigned long long key, u
   sc_store(sR + (size_t)i * 8, sc_from_stream_block(key, 2ull * i + 1));
 }
 
+// Production form of the blinding vectors: the 64-byte blocks are ChaCha20 blocks (RFC 8439 2.3:
+// 20 rounds, 32-bit block counter, 96-bit nonce "bpg sLsR v01") under a 256-bit key that the host draws
+// from the transcript-bound RNG (reference src/r1cs/prover.rs:435-445: transcript state, v_blinding
+// witnesses and external entropy); block 2j -> s_L[j], block 2j+1 -> s_R[j], each reduced mod l.
+static __global__ void __launch_bounds__(256) k_blind_vectors_chacha(ChaKey key, uint32_t n, uint32_t* __restrict__ sL,
+                                                               uint32_t* __restrict__ sR /*[n][8] mont*/) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  sc_store(sL + (size_t)i * 8, sc_from_chacha_block(key, 2u * i));
+  sc_store(sR + (size_t)i * 8, sc_from_chacha_block(key, 2u * i + 1u));
+}
+
 // ---- prover: terms of the (A_I, A_O, S) launch over gens[first .. first+cnt) -------------
 // term layout (5 cnt + 3): [i_b o_b s_b | a_L | a_R | a_O | s_L | s_R]
-__global__ void __launch_bounds__(256) k_aios_terms(const uint32_t* __restrict__ aL, const uint32_t* __restrict__ aR,
+static __global__ void __launch_bounds__(256) k_aios_terms(const uint32_t* __restrict__ aL, const uint32_t* __restrict__ aR,
                                                      const uint32_t* __restrict__ aO, const uint32_t* __restrict__ sL,
                                                      const uint32_t* __restrict__ sR, uint32_t first, uint32_t cnt,
                                                      const uint32_t* __restrict__ blind3 /*3 canonical scalars*/,
@@ -136,7 +148,7 @@ __global__ void __launch_bounds__(256) k_aios_terms(const uint32_t* __restrict__
 struct PolyParams {
   PowTable y, y_inv;
 };
-__global__ void __launch_bounds__(SV_THREADS) k_poly_t(const uint32_t* __restrict__ aL, const uint32_t* __restrict__ aR,
+static __global__ void __launch_bounds__(SV_THREADS) k_poly_t(const uint32_t* __restrict__ aL, const uint32_t* __restrict__ aR,
                                                         const uint32_t* __restrict__ aO, const uint32_t* __restrict__ sL,
                                                         const uint32_t* __restrict__ sR, const uint32_t* __restrict__ wL,
                                                         const uint32_t* __restrict__ wR, const uint32_t* __restrict__ wO,
@@ -195,7 +207,7 @@ struct EvalParams {
   uint32_t x[8], u[8];  // Montgomery
   uint32_t n, n1, N;
 };
-__global__ void __launch_bounds__(256) k_lr_eval(const uint32_t* __restrict__ aL, const uint32_t* __restrict__ aR,
+static __global__ void __launch_bounds__(256) k_lr_eval(const uint32_t* __restrict__ aL, const uint32_t* __restrict__ aR,
                                                   const uint32_t* __restrict__ aO, const uint32_t* __restrict__ sL,
                                                   const uint32_t* __restrict__ sR, const uint32_t* __restrict__ wL,
                                                   const uint32_t* __restrict__ wR, const uint32_t* __restrict__ wO,
@@ -237,7 +249,7 @@ struct VerifyParams {
   uint32_t c0[8], c1[8];  // B scalar = c0 + c1 * delta
   uint32_t lg_n, n, n1, N;
 };
-__global__ void __launch_bounds__(SV_THREADS) k_verify_scalars(const uint32_t* __restrict__ wL,
+static __global__ void __launch_bounds__(SV_THREADS) k_verify_scalars(const uint32_t* __restrict__ wL,
                                                                 const uint32_t* __restrict__ wR,
                                                                 const uint32_t* __restrict__ wO, VerifyParams vp,
                                                                 uint32_t* __restrict__ g_out, uint32_t* __restrict__ h_out,
@@ -273,7 +285,7 @@ __global__ void __launch_bounds__(SV_THREADS) k_verify_scalars(const uint32_t* _
   if (threadIdx.x == 0) sc_store(partials + (size_t)blockIdx.x * 8, delta[0]);
 }
 // single block: delta -> the scalar of B = c0 + c1*delta (verifier.rs:527-529), canonical
-__global__ void __launch_bounds__(SV_THREADS) k_verify_finish(const uint32_t* __restrict__ partials, uint32_t nparts,
+static __global__ void __launch_bounds__(SV_THREADS) k_verify_finish(const uint32_t* __restrict__ partials, uint32_t nparts,
                                                                VerifyParams vp, uint32_t* __restrict__ b_scalar_out) {
   __shared__ uint32_t sm[SV_THREADS / 2][8];
   sc d[1] = {sc_zero()};
@@ -296,7 +308,7 @@ struct IppVerifyParams {
   uint32_t allinv[8], a[8], b[8];
   uint32_t lg_n, N;
 };
-__global__ void __launch_bounds__(256) k_ipp_verify_scalars(const uint32_t* __restrict__ Gf /*canonical or null*/,
+static __global__ void __launch_bounds__(256) k_ipp_verify_scalars(const uint32_t* __restrict__ Gf /*canonical or null*/,
                                                              const uint32_t* __restrict__ Hf, IppVerifyParams vp,
                                                              uint32_t* __restrict__ g_out, uint32_t* __restrict__ h_out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -338,7 +350,7 @@ __global__ void __launch_bounds__(256) k_ipp_verify_scalars(const uint32_t* __re
 constexpr uint32_t FLAT_KIND_SHIFT = 28;  // term code: kind << 28 | index; kinds as in the host mirror
 enum : uint32_t { FK_LEFT = 1, FK_RIGHT = 2, FK_OUT = 3, FK_COMMITTED = 4, FK_ONE = 5, FK_ZERO = 6 };
 
-__global__ void __launch_bounds__(SV_THREADS) k_flat_terms(const uint32_t* __restrict__ t_code,
+static __global__ void __launch_bounds__(SV_THREADS) k_flat_terms(const uint32_t* __restrict__ t_code,
                                                             const uint32_t* __restrict__ t_row,
                                                             const uint32_t* __restrict__ t_coeff /*Montgomery*/,
                                                             uint32_t n_terms, uint32_t n, uint32_t m, PowTable z,
@@ -369,7 +381,7 @@ __global__ void __launch_bounds__(SV_THREADS) k_flat_terms(const uint32_t* __res
   }
 }
 // counters -> Montgomery residues; keys [0,3n): +, keys [3n, 3n+m]: negated
-__global__ void __launch_bounds__(256) k_flat_finish(const unsigned long long* __restrict__ acc, uint32_t n, uint32_t m,
+static __global__ void __launch_bounds__(256) k_flat_finish(const unsigned long long* __restrict__ acc, uint32_t n, uint32_t m,
                                                       uint32_t* __restrict__ w3 /*[3n][8]: wL | wR | wO*/,
                                                       uint32_t* __restrict__ wv /*[m+1][8]: wV | wc*/) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -92,6 +92,36 @@ class Transcript:
         lib().bpg_transcript_challenge_scalar(self._h, label, out)
         return int.from_bytes(out.raw, "little")
 
+    def build_rng(self) -> "TranscriptRng":
+        return TranscriptRng(ctypes.c_void_p(lib().bpg_transcript_build_rng(self._h)))
+
+
+class TranscriptRng:
+    """merlin::TranscriptRngBuilder / TranscriptRng over the host mirror's transcript."""
+
+    def __init__(self, h):
+        self._h = h
+
+    def __del__(self):
+        try:
+            lib().bpg_transcript_rng_free(self._h)
+        except Exception:
+            pass
+
+    def rekey_with_witness_bytes(self, label: bytes, witness: bytes) -> "TranscriptRng":
+        lib().bpg_transcript_rng_rekey_with_witness_bytes(self._h, label, witness, len(witness))
+        return self
+
+    def finalize(self, random_bytes: bytes) -> "TranscriptRng":
+        assert len(random_bytes) == 32
+        lib().bpg_transcript_rng_finalize(self._h, random_bytes)
+        return self
+
+    def fill_bytes(self, n: int) -> bytes:
+        out = ctypes.create_string_buffer(n)
+        lib().bpg_transcript_rng_fill_bytes(self._h, out, n)
+        return out.raw
+
 
 class Gens:
     """PedersenGens {B, B_blinding} and BulletproofGens (party 0) resident in HBM."""
@@ -340,12 +370,21 @@ class Prover(_CS):
         _raise(lib().bpg_prover_commit(self._h, sc_bytes(v), sc_bytes(v_blinding), V, ctypes.byref(var)))
         return V.raw, _var(var.value)
 
-    def prove(self, rng_seed: int) -> bytes:
-        """Prover::prove(bp_gens) -> R1CSProof bytes (reference src/r1cs/proof.rs:82-108)."""
+    def prove(self, rng_seed: int | None = None, rng_bytes: bytes | None = None) -> bytes:
+        """Prover::prove(bp_gens) -> R1CSProof bytes (reference src/r1cs/proof.rs:82-108).
+        No argument: blindings from the transcript-bound RNG finalized with operating-system randomness
+        (bpg_prover_prove, the production entry point).  rng_bytes (32): the same with the caller's
+        bytes in place of the OS draw (reproducible).  rng_seed: TEST ONLY xoshiro256** blindings."""
         cap = 1 + 14 * 32 + 66 * 32
         out = ctypes.create_string_buffer(cap)
         ln = ctypes.c_size_t()
-        code = lib().bpg_prover_prove(self._h, rng_seed, out, cap, ctypes.byref(ln))
+        if rng_seed is not None:
+            code = lib().bpg_prover_prove_deterministic(self._h, rng_seed, out, cap, ctypes.byref(ln))
+        elif rng_bytes is not None:
+            assert len(rng_bytes) == 32
+            code = lib().bpg_prover_prove_with_rng_bytes(self._h, rng_bytes, out, cap, ctypes.byref(ln))
+        else:
+            code = lib().bpg_prover_prove(self._h, out, cap, ctypes.byref(ln))
         self._reraise()
         _raise(code)
         return out.raw[: ln.value]
@@ -365,8 +404,13 @@ class Verifier(_CS):
         _raise(lib().bpg_verifier_commit(self._h, V, ctypes.byref(var)))
         return _var(var.value)
 
-    def verify(self, proof: bytes):
-        code = lib().bpg_verifier_verify(self._h, proof, len(proof))
+    def verify(self, proof: bytes, hardened: bool = False, rng_bytes: bytes | None = None):
+        """Verifier::verify.  Default: r = challenge_scalar("r") as the mounted fork (verifier.rs:506).
+        hardened / rng_bytes: r from a TranscriptRng finalized with 32 bytes unknown to the prover."""
+        if hardened or rng_bytes is not None:
+            code = lib().bpg_verifier_verify_with_rng_bytes(self._h, proof, len(proof), rng_bytes)
+        else:
+            code = lib().bpg_verifier_verify(self._h, proof, len(proof))
         self._reraise()
         _raise(code)
 

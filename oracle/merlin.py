@@ -129,6 +129,47 @@ class Strobe128:
         self._begin_op(_FLAG_I | _FLAG_A | _FLAG_C, more)
         return self._squeeze(n)
 
+    def key(self, data: bytes, more: bool):
+        """STROBE KEY (flags A|C): the key bytes OVERWRITE the rate (merlin strobe.rs `overwrite`)."""
+        self._begin_op(_FLAG_A | _FLAG_C, more)
+        for b in data:
+            self.state[self.pos] = b
+            self.pos += 1
+            if self.pos == _R:
+                self._run_f()
+
+    def clone(self) -> "Strobe128":
+        c = Strobe128.__new__(Strobe128)
+        c.state = bytearray(self.state)
+        c.pos, c.pos_begin, c.cur_flags = self.pos, self.pos_begin, self.cur_flags
+        return c
+
+
+class TranscriptRng:
+    """merlin::TranscriptRngBuilder + TranscriptRng (merlin v1.0 transcript.rs): a clone of the
+    transcript's STROBE state, rekeyed with witness bytes, finalized with 32 external random bytes;
+    fill_bytes(n) = meta_ad(u32le(n)) then prf(n).  The reference's prover forks its blinding RNG this
+    way (src/r1cs/prover.rs:435-445)."""
+
+    def __init__(self, strobe: Strobe128):
+        self.strobe = strobe.clone()
+
+    def rekey_with_witness_bytes(self, label: bytes, witness: bytes) -> "TranscriptRng":
+        self.strobe.meta_ad(label, False)
+        self.strobe.meta_ad(len(witness).to_bytes(4, "little"), True)
+        self.strobe.key(witness, False)
+        return self
+
+    def finalize(self, random_bytes: bytes) -> "TranscriptRng":
+        assert len(random_bytes) == 32
+        self.strobe.meta_ad(b"rng", False)
+        self.strobe.key(random_bytes, False)
+        return self
+
+    def fill_bytes(self, n: int) -> bytes:
+        self.strobe.meta_ad(n.to_bytes(4, "little"), False)
+        return self.strobe.prf(n, False)
+
 
 class Transcript:
     def __init__(self, label: bytes):
@@ -147,3 +188,6 @@ class Transcript:
         self.strobe.meta_ad(label, False)
         self.strobe.meta_ad(n.to_bytes(4, "little"), True)
         return self.strobe.prf(n, False)
+
+    def build_rng(self) -> TranscriptRng:
+        return TranscriptRng(self.strobe)

@@ -12,6 +12,7 @@ reproducible; the reference itself draws it from `thread_rng()`
 from __future__ import annotations
 
 import hashlib
+import struct
 from dataclasses import dataclass, field
 
 from . import group as G
@@ -88,6 +89,63 @@ class Blindings:
         def block(idx):
             b = b"".join(word(8 * idx + k).to_bytes(8, "little") for k in range(8))
             return int.from_bytes(b, "little") % L
+
+        return [block(2 * j) for j in range(n)], [block(2 * j + 1) for j in range(n)]
+
+
+def chacha20_block(key: bytes, counter: int, nonce: bytes) -> bytes:
+    """RFC 8439 section 2.3 (pinned by its 2.3.2 test vector in tests/test_oracle_group.py)."""
+    M = 0xFFFFFFFF
+
+    def rotl(v, c):
+        return ((v << c) & M) | (v >> (32 - c))
+
+    def qr(x, a, b, c, d):
+        x[a] = (x[a] + x[b]) & M; x[d] = rotl(x[d] ^ x[a], 16)
+        x[c] = (x[c] + x[d]) & M; x[b] = rotl(x[b] ^ x[c], 12)
+        x[a] = (x[a] + x[b]) & M; x[d] = rotl(x[d] ^ x[a], 8)
+        x[c] = (x[c] + x[d]) & M; x[b] = rotl(x[b] ^ x[c], 7)
+
+    init = list(struct.unpack("<4I", b"expand 32-byte k")) + list(struct.unpack("<8I", key)) + [counter & M] + list(struct.unpack("<3I", nonce))
+    x = list(init)
+    for _ in range(10):
+        qr(x, 0, 4, 8, 12); qr(x, 1, 5, 9, 13); qr(x, 2, 6, 10, 14); qr(x, 3, 7, 11, 15)
+        qr(x, 0, 5, 10, 15); qr(x, 1, 6, 11, 12); qr(x, 2, 7, 8, 13); qr(x, 3, 4, 9, 14)
+    return struct.pack("<16I", *[(a + b) & M for a, b in zip(x, init)])
+
+
+BLIND_NONCE = b"bpg sLsR v01"
+
+
+class TranscriptBlindings:
+    """The production blinding source: merlin's TranscriptRng forked from the prover's transcript after
+    "m", rekeyed with every v_blinding and finalized with 32 external random bytes (reference
+    src/r1cs/prover.rs:435-445), drawn in the reference's order.  `Prover.prove` calls `bind` at the fork
+    point.  The two blinding vectors of a phase come from ONE 32-byte draw that keys ChaCha20: block
+    2j -> s_L[j], block 2j+1 -> s_R[j], each 64-byte block reduced mod l (the product expands them on
+    the device instead of drawing 2n scalars from the sequential RNG)."""
+
+    def __init__(self, random_bytes: bytes):
+        assert len(random_bytes) == 32
+        self.random_bytes = random_bytes
+        self.rng = None
+
+    def bind(self, transcript, v_blinding):
+        rng = transcript.build_rng()
+        for vb in v_blinding:
+            rng.rekey_with_witness_bytes(b"v_blinding", G.sc_to_bytes(vb))
+        self.rng = rng.finalize(self.random_bytes)
+
+    def scalar(self) -> int:
+        return int.from_bytes(self.rng.fill_bytes(64), "little") % L
+
+    def vector_pair(self, n: int):
+        if n == 0:
+            return [], []
+        key = self.rng.fill_bytes(32)
+
+        def block(idx):
+            return int.from_bytes(chacha20_block(key, idx, BLIND_NONCE), "little") % L
 
         return [block(2 * j) for j in range(n)], [block(2 * j + 1) for j in range(n)]
 
@@ -533,6 +591,8 @@ class Prover(_CSBase):
     def prove(self, bp_gens: BulletproofGens, blind: Blindings, trace=None) -> R1CSProof:
         tr = self.transcript
         tr.append_u64(b"m", len(self.v))  # :420
+        if hasattr(blind, "bind"):
+            blind.bind(tr, self.v_blinding)  # :435-445
         n1 = len(self.a_L)
         if bp_gens.gens_capacity < n1:
             raise InvalidGeneratorsLength()
@@ -712,7 +772,7 @@ class Verifier(_CSBase):
             exp_z = exp_z * z % L
         return wL, wR, wO, wV, wc
 
-    def verification_inputs(self, proof: R1CSProof, bp_gens: BulletproofGens):
+    def verification_inputs(self, proof: R1CSProof, bp_gens: BulletproofGens, rng_bytes: bytes | None = None):
         """Transcript replay and scalar preparation of `verify` (:398-514): returns the
         mega-MSM's (scalars, points) in the reference's order (:516-547)."""
         tr = self.transcript
@@ -760,7 +820,10 @@ class Verifier(_CSBase):
         wLp, wOp = wL + [0] * pad, wO + [0] * pad
         g_scalars = [U[i] * (x * yneg_wR[i] - a * s[i]) % L for i in range(padded_n)]
         h_scalars = [U[i] * (y_inv_vec[i] * (x * wLp[i] + wOp[i] - b * s[padded_n - 1 - i]) - 1) % L for i in range(padded_n)]
-        r = tr.challenge_scalar(b"r")
+        if rng_bytes is None:
+            r = tr.challenge_scalar(b"r")  # :506 (the mounted fork: a public function of the transcript)
+        else:  # upstream: transcript.build_rng().finalize(&mut thread_rng()), then Scalar::random
+            r = int.from_bytes(tr.build_rng().finalize(rng_bytes).fill_bytes(64), "little") % L
         xx = x * x % L
         rxx = r * xx % L
         xxx = x * xx % L
@@ -789,7 +852,7 @@ class Verifier(_CSBase):
         return scalars, points
 
     # :393-554
-    def verify(self, proof: R1CSProof, bp_gens: BulletproofGens):
-        scalars, points = self.verification_inputs(proof, bp_gens)
+    def verify(self, proof: R1CSProof, bp_gens: BulletproofGens, rng_bytes: bytes | None = None):
+        scalars, points = self.verification_inputs(proof, bp_gens, rng_bytes)
         if not G.msm(scalars, points).is_identity():
             raise VerificationError("mega check failed")

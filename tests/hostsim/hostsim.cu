@@ -74,6 +74,10 @@ void hs_sc_add(const uint32_t* a, const uint32_t* b, uint32_t* o) {
 void hs_sc_sub(const uint32_t* a, const uint32_t* b, uint32_t* o) {
   sc x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); sc r = sc_sub(x, y); memcpy(o, r.v, 32);
 }
+// Montgomery form of (ChaCha20 block `block` under `key`, nonce "bpg sLsR v01") mod l
+void hs_chacha_scalar(const uint32_t* key, uint32_t block, uint32_t* o) {
+  ChaKey k; memcpy(k.k, key, 32); sc r = sc_from_mont(sc_from_chacha_block(k, block)); memcpy(o, r.v, 32);
+}
 static sc_bias mk_bias(int c, int W) {
   sc_bias b; memset(&b, 0, sizeof b);
   for (int w = 0; w < W; w++) { int bit = c * w + c - 1; b.v[bit >> 5] |= 1u << (bit & 31); }

@@ -442,3 +442,94 @@ def test_full_size_r1cs_roundtrip(ctx):
     vr.verify(proof2)
     gens.close()
     comb.close()
+
+
+# ------------------------------------------------------------------ transcript-bound blinding (prover.rs:435-445)
+@pytest.mark.parametrize("k", [1, 4, 7])
+def test_keyed_blinding_matches_oracle(env, k):
+    """The production blinding path -- merlin TranscriptRng (transcript + v_blindings + 32 external bytes)
+    in the reference's draw order, s_L / s_R expanded from one draw through ChaCha20 on the device --
+    gives the oracle's proof bytes when the 32 external bytes are fixed; shuffle gadget, so two phases
+    (two vector keys) and, for k = 7, the padding path."""
+    from mpc_bulletproof_b200 import protocol as P
+
+    pc, bp, gens = env
+    label = b"ShuffleProofTest"
+    rb = bytes((37 * i + k) & 0xFF for i in range(32))
+
+    def build(p, r, enc):
+        inp = [r.randrange(2**64) for _ in range(k)]
+        outp = inp[:]
+        r.shuffle(outp)
+        ic = [p.commit(v, r.randrange(L)) for v in inp]
+        oc = [p.commit(v, r.randrange(L)) for v in outp]
+        gadgets.shuffle_gadget(p, [v for _, v in ic], [v for _, v in oc])
+        return [enc(c) for c, _ in ic + oc]
+
+    op = O.Prover(pc, O.Transcript(label))
+    ocoms = build(op, random.Random(900 + k), lambda c: c.encode())
+    want = op.prove(bp, O.TranscriptBlindings(rb)).to_bytes()
+    pp = P.Prover(gens, P.Transcript(label))
+    pcoms = build(pp, random.Random(900 + k), lambda c: c)
+    got = pp.prove(rng_bytes=rb)
+    assert ocoms == pcoms and got == want, "keyed-blinding proof bytes differ from the oracle"
+    # other external bytes -> other blindings -> another proof of the same statement
+    p2 = P.Prover(gens, P.Transcript(label))
+    build(p2, random.Random(900 + k), lambda c: c)
+    assert p2.prove(rng_bytes=bytes(32)) != got
+
+    def verifier(cls, tr):
+        vf = cls(gens if cls is P.Verifier else pc, tr(label))
+        vs = [vf.commit(c if cls is P.Verifier else G.decode(c)) for c in pcoms]
+        gadgets.shuffle_gadget(vf, vs[:k], vs[k:])
+        return vf
+
+    verifier(P.Verifier, P.Transcript).verify(got)
+    verifier(O.Verifier, O.Transcript).verify(O.R1CSProof.from_bytes(got), bp)
+
+
+def test_os_entropy_prove_and_hardened_verify(env):
+    """bpg_prover_prove (operating-system entropy): two proofs of one statement differ and both verify,
+    under the fork's deterministic r (verifier.rs:506) and under the hardened verifier whose r the
+    prover cannot predict; a false statement is rejected by both; the hardened r equals the oracle's."""
+    from mpc_bulletproof_b200 import protocol as P
+
+    pc, bp, gens = env
+
+    def stmt(cs, commit, c2):
+        cv = [commit(cs, x) for x in (3, 4, 6, 1, 40)]
+        gadgets.example_gadget(cs, cv[0], cv[1], cv[2], cv[3], cv[4], c2)
+
+    proofs, coms = [], None
+    for _ in range(2):
+        p = P.Prover(gens, P.Transcript(b"R1CSExampleGadget"))
+        cs_coms = []
+
+        def commit(cs, x):
+            c, var = cs.commit(x, 12345 + x)
+            cs_coms.append(c)
+            return var
+
+        stmt(p, commit, 9)
+        proofs.append(p.prove())
+        coms = cs_coms
+    assert proofs[0] != proofs[1]
+
+    def verifier(c2):
+        vf = P.Verifier(gens, P.Transcript(b"R1CSExampleGadget"))
+        it = iter(coms)
+        stmt(vf, lambda cs, x: cs.commit(next(it)), c2)
+        return vf
+
+    for pr in proofs:
+        verifier(9).verify(pr)
+        verifier(9).verify(pr, hardened=True)
+        verifier(9).verify(pr, rng_bytes=bytes(range(32)))
+        for kw in ({}, {"hardened": True}):
+            with pytest.raises(P.VerificationError):
+                verifier(10).verify(pr, **kw)
+    # the oracle's hardened verifier (same TranscriptRng draw) accepts the same proof
+    ov = O.Verifier(pc, O.Transcript(b"R1CSExampleGadget"))
+    it = iter(coms)
+    stmt(ov, lambda cs, x: cs.commit(G.decode(next(it))), 9)
+    ov.verify(O.R1CSProof.from_bytes(proofs[0]), bp, rng_bytes=bytes(range(32)))

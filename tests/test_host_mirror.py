@@ -25,3 +25,26 @@ def test_transcript_matches_oracle():
         assert t.challenge_bytes(b"bytes", 200) == o.challenge_bytes(b"bytes", 200)
     c = t.clone()
     assert c.challenge_scalar(b"x") == t.challenge_scalar(b"x") == o.challenge_scalar(b"x")
+
+
+def test_transcript_rng_matches_oracle():
+    """merlin TranscriptRng (the prover's blinding source, reference src/r1cs/prover.rs:435-445):
+    host mirror against the oracle's restatement, across the STROBE rate boundary, and bound to the
+    transcript, the witness and the external bytes."""
+    from mpc_bulletproof_b200 import protocol as P
+
+    t, o = P.Transcript(b"rng"), O.Transcript(b"rng")
+    for tr in (t, o):
+        tr.append_message(b"stmt", bytes(range(200)))
+    w1, w2, ext = bytes(range(32)), bytes(range(100, 132)), bytes([7] * 32)
+    r = t.build_rng().rekey_with_witness_bytes(b"v_blinding", w1).rekey_with_witness_bytes(b"v_blinding", w2).finalize(ext)
+    q = o.build_rng().rekey_with_witness_bytes(b"v_blinding", w1).rekey_with_witness_bytes(b"v_blinding", w2).finalize(ext)
+    for n in (64, 32, 1, 400, 64):
+        assert r.fill_bytes(n) == q.fill_bytes(n)
+    # the fork leaves the transcript itself untouched
+    assert t.challenge_bytes(b"c", 32) == o.challenge_bytes(b"c", 32)
+    base = o.build_rng().rekey_with_witness_bytes(b"v_blinding", w1).finalize(ext).fill_bytes(64)
+    assert base != o.build_rng().rekey_with_witness_bytes(b"v_blinding", w2).finalize(ext).fill_bytes(64)
+    assert base != o.build_rng().rekey_with_witness_bytes(b"v_blinding", w1).finalize(bytes(32)).fill_bytes(64)
+    o2 = O.Transcript(b"rng")
+    assert base != o2.build_rng().rekey_with_witness_bytes(b"v_blinding", w1).finalize(ext).fill_bytes(64)

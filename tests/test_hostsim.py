@@ -222,3 +222,20 @@ def test_element_derivation(hs):
         hs.hs_from_uniform((ctypes.c_uint8 * 64)(*b), o)
         assert bytes(o) == G.from_uniform_bytes(b).encode()
     assert bytes(o) != bytes(32)
+
+
+def test_chacha_blinding_scalar(hs):
+    """The device side of the keyed blinding vectors (sc.cuh: sc_from_chacha_block) against the oracle's
+    ChaCha20 block (RFC 8439) reduced mod l: element e of a phase is block e under the drawn key."""
+    import struct
+
+    from oracle import protocol as O
+
+    r = random.Random(77)
+    for _ in range(20):
+        key = bytes(r.getrandbits(8) for _ in range(32))
+        block = r.choice([0, 1, 2, 2**31, 2**32 - 1, r.getrandbits(32)])
+        out = U32x8()
+        hs.hs_chacha_scalar(U32x8(*struct.unpack("<8I", key)), ctypes.c_uint32(block), out)
+        want = int.from_bytes(O.chacha20_block(key, block, O.BLIND_NONCE), "little") % G.L
+        assert frl(out) == want

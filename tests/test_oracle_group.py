@@ -117,3 +117,15 @@ def test_msm_bucket_method_equals_definition():
         ks = [r.randrange(G.L) for _ in range(n)]
         ps = [r.randrange(G.L) * G.BASEPOINT for _ in range(n)]
         assert G.msm(ks, ps).encode() == G.msm_naive(ks, ps).encode()
+
+
+def test_chacha20_block_rfc8439_vector():
+    """RFC 8439 section 2.3.2: the block function behind the keyed blinding vectors."""
+    from oracle import protocol as O
+
+    key, nonce = bytes(range(32)), bytes.fromhex("000000090000004a00000000")
+    want = (
+        "10f1e7e4d13b5915500fdd1fa32071c4c7d1f4c733c068030422aa9ac3d46c4e"
+        "d2826446079faa0914c2d705d98b02a2b5129cd1de164eb9cbd083e8a2503c4e"
+    )
+    assert O.chacha20_block(key, 1, nonce).hex() == want
