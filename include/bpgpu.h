@@ -146,6 +146,12 @@ int bpg_msm_table_partial(bpg_ctx* ctx, const bpg_table* table, size_t offset, s
                           int n_sets, uint8_t* out_ext);
 int bpg_sum_encode(bpg_ctx* ctx, const uint8_t* parts_ext, int n_parts, int n_sets, uint8_t* out);
 
+/* Open of additively shared points that crossed the party-to-party link as compressed encodings (the MPC
+ * prover: `.open()` / `open_authenticated` of a commitment, reference src/r1cs_mpc/mpc_prover.rs:630-657,
+ * mpc_inner_product.rs:131,191): out[s] = encode(sum_p decode(points[p][s])), points laid out [part][set],
+ * n_parts <= 32.  BPG_ERR_DECODE if any share is not a valid encoding. */
+int bpg_points_sum(bpg_ctx* ctx, const uint8_t* points, int n_parts, int n_sets, uint8_t* out /* n_sets*32 */);
+
 /* Exchange fused with the combine, for one process per GPU on one node: each rank
  * owns an exchange buffer that its peers map through CUDA IPC; bpg_dev_exchange_sum_encode is ONE
  * kernel that stores this rank's partial sums into every rank's buffer over NVLink, raises its flag,
@@ -195,6 +201,36 @@ int bpg_ipp_round_LR(bpg_ipp* st, uint8_t L[32], uint8_t R[32]);
 int bpg_ipp_round_fold(bpg_ipp* st, const uint8_t u[32], const uint8_t u_inv[32]);
 int bpg_ipp_finish(bpg_ipp* st, uint8_t a[32], uint8_t b[32]);
 void bpg_ipp_free(bpg_ipp* st);
+
+/* The same rounds on SECRET SHARES: `SharedInnerProductProof::create` (reference
+ * src/r1cs_mpc/mpc_inner_product.rs:52-228).  A party holds additive shares of a and b -- `lanes` (a, b)
+ * pairs: lane 0 the value shares, further lanes e.g. the MAC shares of an authenticated fabric (all lanes
+ * fold with the same public challenge) -- while G, H, the factors and Q are public.  Everything linear is
+ * local and runs here: the party's shares of L and R (ONE MSM with 2 x lanes outputs over one pass of the
+ * generator table, :104-126, 172-186) and the folds (:136-137, 196-197).  The cross terms c_L = <a_lo, b_hi>,
+ * c_R = <a_hi, b_lo> multiply shared values: they come out of the fabric's multiplication protocol (Beaver
+ * triples over the network, :104-105, 172-173), which is the caller's:
+ *     bpg_ipp_begin_shares(...)                          // share (and MAC) vectors go to HBM once
+ *     while (bpg_ipp_rounds_left(st)) {
+ *        bpg_ipp_read_ab(st, a_cur, b_cur);              // what the multiplication protocol needs
+ *        (c_L, c_R) = fabric: shares of <a_lo, b_hi>, <a_hi, b_lo>                       (caller, network)
+ *        bpg_ipp_round_LR_shares(st, c_L, c_R, L_sh, R_sh);   // this party's shares of L, R (compressed)
+ *        L, R = open (exchange + bpg_points_sum); transcript; u                          (caller, network)
+ *        bpg_ipp_round_fold(st, u, u_inv);
+ *     }
+ *     bpg_ipp_finish_shares(st, a_sh, b_sh);             // shares of the final a, b (:217-228), opened by the caller
+ * Generators: G_vec = shared[g_base..), H_vec = shared[h_base..) of ONE windowed table, Q = q_mul * shared[q_id]
+ * (the MPC prover's Q = w*B, src/r1cs_mpc/mpc_prover.rs:926-927).  a, b: lanes x n x 32 bytes, lane-major. */
+#define BPG_IPP_MAX_LANES 4
+int bpg_ipp_begin_shares(bpg_ctx* ctx, const bpg_table* shared, size_t g_base, size_t h_base, size_t q_id,
+                         const uint8_t q_mul[32], size_t n, int lanes, const uint8_t* G_factors,
+                         const uint8_t* H_factors, const uint8_t* a, const uint8_t* b, bpg_ipp** out);
+int bpg_ipp_lanes(const bpg_ipp* st);
+size_t bpg_ipp_len(const bpg_ipp* st); /* current vector length m */
+int bpg_ipp_read_ab(bpg_ipp* st, uint8_t* a_out /* lanes*m*32 */, uint8_t* b_out);
+int bpg_ipp_round_LR_shares(bpg_ipp* st, const uint8_t* c_L /* lanes*32 */, const uint8_t* c_R, uint8_t* L_out /* lanes*32 */,
+                            uint8_t* R_out);
+int bpg_ipp_finish_shares(bpg_ipp* st, uint8_t* a /* lanes*32 */, uint8_t* b);
 
 /* ---- fixed-base multiplication (comb) ---------------------------------------------
  * A comb holds, for each of nbases points P_t, the 64x8 affine-Niels multiples

@@ -125,6 +125,13 @@ _SIGNATURES = {
     "bpg_ipp_round_fold": (_I, [_P, _P, _P]),
     "bpg_ipp_finish": (_I, [_P, _P, _P]),
     "bpg_ipp_free": (None, [_P]),
+    "bpg_ipp_begin_shares": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _SZ, _I, _P, _P, _P, _P, ctypes.POINTER(_P)]),
+    "bpg_ipp_lanes": (_I, [_P]),
+    "bpg_ipp_len": (_SZ, [_P]),
+    "bpg_ipp_read_ab": (_I, [_P, _P, _P]),
+    "bpg_ipp_round_LR_shares": (_I, [_P, _P, _P, _P, _P]),
+    "bpg_ipp_finish_shares": (_I, [_P, _P, _P]),
+    "bpg_points_sum": (_I, [_P, _P, _I, _I, _P]),
     "bpg_r1cs_dev_new": (_I, [_P, _SZ, ctypes.POINTER(_P)]),
     "bpg_r1cs_dev_free": (None, [_P]),
     "bpg_r1cs_dev_reserve": (_I, [ctypes.POINTER(_P), _SZ]),

@@ -554,6 +554,30 @@ extern "C" int bpg_sum_encode(bpg_ctx* ctx, const uint8_t* parts_ext, int n_part
   return BPG_OK;
 }
 
+// out[s] = encode(sum_p decode(points[p][s])), points laid out [part][set], n_parts <= 32: the open of
+// additively shared points that travelled as compressed encodings (the MPC prover's party-to-party link)
+extern "C" int bpg_points_sum(bpg_ctx* ctx, const uint8_t* points, int n_parts, int n_sets, uint8_t* out) {
+  if (!ctx || !points || !out || n_parts <= 0 || n_parts > 32 || n_sets <= 0) return BPG_ERR_ARG;
+  size_t in_bytes = (size_t)n_parts * n_sets * 32, out_bytes = (size_t)n_sets * 32;
+  if (in_bytes + out_bytes + 256 > SMALL_BYTES) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small);
+  uint8_t* d_in = ctx->d_small + 256;
+  uint8_t* d_out = d_in + in_bytes;
+  memcpy(ctx->h_pinned + 256, points, in_bytes);
+  CK(cudaMemsetAsync(bad, 0, 4, s));
+  CK(cudaMemcpyAsync(d_in, ctx->h_pinned + 256, in_bytes, cudaMemcpyHostToDevice, s));
+  k_points_sum<<<n_sets, ENC_THREADS, 0, s>>>(d_in, n_parts, n_sets, d_out, bad);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(ctx->h_pinned, bad, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ctx->h_pinned + 256, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (*reinterpret_cast<uint32_t*>(ctx->h_pinned)) return BPG_ERR_DECODE;
+  memcpy(out, ctx->h_pinned + 256, out_bytes);
+  return BPG_OK;
+}
+
 extern "C" int bpg_msm(bpg_ctx* ctx, const uint8_t* scalars_le, const uint8_t* points_compressed, size_t n,
                        uint8_t out[32]) {
   if (!ctx || !out || ((!scalars_le || !points_compressed) && n)) return BPG_ERR_ARG;

@@ -125,4 +125,5 @@ void launch_comb_mul(bpg_ctx* ctx, cudaStream_t s, const uint32_t* tables, int n
 int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off, size_t n,
                   const uint8_t* Q_host, const bpg_table* shared, size_t g_base, size_t h_base, size_t q_id,
                   const uint8_t* q_mul_host, const uint32_t* d_gf, const uint32_t* d_hf, const uint32_t* d_a,
-                  const uint32_t* d_b, bpg_ipp** out);
+                  const uint32_t* d_b, bpg_ipp** out, int lanes = 1);
+constexpr int IPP_MAX_LANES = 4;

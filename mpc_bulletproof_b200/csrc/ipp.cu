@@ -21,6 +21,8 @@ struct bpg_ipp {
   uint32_t* q_mul;
   uint8_t *set_ids, *out_bytes;
   bool lr_done;
+  int lanes;        // (a, b) pairs folding together: 1, or a party's share + MAC vectors (r1cs_mpc)
+  uint32_t* c_ext;  // [lanes][2] caller-supplied cross terms of the current round (shares path)
 };
 
 
@@ -31,9 +33,10 @@ struct bpg_ipp {
 int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off, size_t n,
                          const uint8_t* Q_host, const bpg_table* shared, size_t g_base, size_t h_base, size_t q_id,
                          const uint8_t* q_mul_host, const uint32_t* d_gf, const uint32_t* d_hf, const uint32_t* d_a,
-                         const uint32_t* d_b, bpg_ipp** out) {
+                         const uint32_t* d_b, bpg_ipp** out, int lanes) {
   if (n == 0 || (n & (n - 1))) return BPG_ERR_POW2;
   if (n >= (1u << 28)) return BPG_ERR_ARG;
+  if (lanes < 1 || lanes > IPP_MAX_LANES || (lanes > 1 && !shared)) return BPG_ERR_ARG;
   if (shared) {
     if (g_base + n > shared->n || h_base + n > shared->n || q_id >= shared->n) return BPG_ERR_CAPACITY;
     if (!shared->win_c && n > 1) return BPG_ERR_ARG;
@@ -45,15 +48,18 @@ int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_tabl
   memset(st, 0, sizeof *st);
   st->ctx = ctx;
   st->n = st->m = n;
+  st->lanes = lanes;
   int rc = BPG_OK;
   size_t T = 2 * n + 2;
   size_t nparts = 256;
   size_t off = 0;
+  const size_t NL = (size_t)lanes;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
-  size_t o_a = take(n * 32), o_b = take(n * 32), o_wG = take(n * 32), o_wH = take(n * 32);
-  size_t o_sc = take(T * 32), o_pid = take(T * 4), o_set = take(T), o_part = take(nparts * 64);
-  size_t o_u = take(64), o_ext = take(4 * 128), o_bytes = take(64), o_q = take(32), o_qm = take(32);
-  size_t o_qside = take(64), o_qcomb = take((size_t)COMB_ENTRIES * 96);
+  size_t o_a = take(NL * n * 32), o_b = take(NL * n * 32), o_wG = take(n * 32), o_wH = take(n * 32);
+  size_t o_sc = take(NL * T * 32), o_pid = take(NL * T * 4), o_set = take(NL * T), o_part = take(nparts * 64);
+  size_t o_u = take(64), o_ext = take(std::max<size_t>(4, 2 * NL) * 128), o_bytes = take(64 * NL), o_q = take(32),
+         o_qm = take(32);
+  size_t o_qside = take(64), o_qcomb = take((size_t)COMB_ENTRIES * 96), o_cext = take(NL * 64);
   do {
     cudaError_t e = dev_alloc(ctx, &st->buf, off);
     if (e != cudaSuccess) { ctx->last_cuda = (int)e; rc = BPG_ERR_NOMEM; break; }
@@ -66,10 +72,11 @@ int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_tabl
     st->q_mul = (uint32_t*)(st->buf + o_qm);
     st->q_side = (uint32_t*)(st->buf + o_qside);
     st->q_comb = (uint32_t*)(st->buf + o_qcomb);
+    st->c_ext = (uint32_t*)(st->buf + o_cext);
     uint8_t* d_q = st->buf + o_q;
     cudaStream_t s = ctx->stream;
-    if (cudaMemcpyAsync(st->a, d_a, n * 32, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
-        cudaMemcpyAsync(st->b, d_b, n * 32, cudaMemcpyDeviceToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+    if (cudaMemcpyAsync(st->a, d_a, NL * n * 32, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(st->b, d_b, NL * n * 32, cudaMemcpyDeviceToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
     unsigned gn = (unsigned)((n + 255) / 256);
     k_ipp_init_weights<<<gn, 256, 0, s>>>(d_gf, d_hf, (uint32_t)n, st->wG, st->wH);
     ctx->launches++;
@@ -80,7 +87,8 @@ int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_tabl
         memcpy(ctx->h_pinned + 512, q_mul_host, 32);
         if (cudaMemcpyAsync(st->q_mul, ctx->h_pinned + 512, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
       }
-      k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, (uint32_t)g_base, (uint32_t)h_base, (uint32_t)q_id);
+      k_ipp_point_ids<<<dim3(gn, (unsigned)lanes), 256, 0, s>>>(st->point_ids, (uint32_t)n, (uint32_t)g_base, (uint32_t)h_base,
+                                                                (uint32_t)q_id);
       ctx->launches++;
       if (cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
     } else if (G == H && G->win_c && n > 1) {
@@ -191,7 +199,7 @@ extern "C" size_t bpg_ipp_rounds_left(const bpg_ipp* st) {
 
 extern "C" int bpg_ipp_round_LR(bpg_ipp* st, uint8_t L[32], uint8_t R[32]) {
   if (!st || !L || !R) return BPG_ERR_ARG;
-  if (st->m <= 1 || st->lr_done) return BPG_ERR_ARG;
+  if (st->m <= 1 || st->lr_done || st->lanes != 1) return BPG_ERR_ARG;
   bpg_ctx* ctx = st->ctx;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
@@ -239,13 +247,102 @@ extern "C" int bpg_ipp_round_fold(bpg_ipp* st, const uint8_t u[32], const uint8_
   memcpy(up.v, u, 32);
   memcpy(up.v + 8, u_inv, 32);
   prof_mark(ctx, BPG_PROF_OTHER);
-  k_ipp_fold<<<(unsigned)((st->n + 255) / 256), 256, 0, s>>>(st->a, st->b, st->wG, st->wH, (uint32_t)st->n,
-                                                             (uint32_t)st->m, up);
+  k_ipp_fold<<<dim3((unsigned)((st->n + 255) / 256), (unsigned)st->lanes), 256, 0, s>>>(st->a, st->b, st->wG, st->wH,
+                                                                                       (uint32_t)st->n, (uint32_t)st->m, up);
   LAUNCH_CHECK();
   prof_mark(ctx, -1);
   st->m /= 2;
   st->lr_done = false;
   return BPG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// the same rounds on secret shares (r1cs_mpc): SharedInnerProductProof::create, reference
+// src/r1cs_mpc/mpc_inner_product.rs:52-228.  A party holds additive shares of a and b -- `lanes` (a, b) pairs:
+// the value shares and, in an authenticated fabric, the MAC shares -- while G, H, the factors and Q are
+// public.  Everything linear is local: the party's shares of L and R are MSMs of its share vectors
+// (:104-126, 172-186) and the folds use the public challenge (:136-137, 196-197).  The cross terms
+// c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo> are products of shared values, i.e. the fabric's multiplication
+// protocol over the network: the caller reads the current vectors (bpg_ipp_read_ab), runs that protocol,
+// and hands this party's shares of c_L, c_R to bpg_ipp_round_LR_shares.
+// ---------------------------------------------------------------------------
+extern "C" int bpg_ipp_begin_shares(bpg_ctx* ctx, const bpg_table* shared, size_t g_base, size_t h_base, size_t q_id,
+                                    const uint8_t q_mul[32], size_t n, int lanes, const uint8_t* G_factors,
+                                    const uint8_t* H_factors, const uint8_t* a, const uint8_t* b, bpg_ipp** out) {
+  if (!ctx || !shared || !a || !b || !out || lanes < 1 || lanes > IPP_MAX_LANES) return BPG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const size_t NL = (size_t)lanes;
+  int rc = ensure_stage(ctx, (2 * NL + 2) * n * 32 + 64);
+  if (rc) return rc;
+  uint8_t* d = ctx->d_stage;
+  uint8_t *d_a = d, *d_b = d + NL * n * 32, *d_gf = d + 2 * NL * n * 32, *d_hf = d_gf + n * 32;
+  CK(cudaMemcpyAsync(d_a, a, NL * n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_b, b, NL * n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (G_factors) CK(cudaMemcpyAsync(d_gf, G_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (H_factors) CK(cudaMemcpyAsync(d_hf, H_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  return ipp_begin_dev(ctx, nullptr, 0, nullptr, 0, n, nullptr, shared, g_base, h_base, q_id, q_mul,
+                       G_factors ? (const uint32_t*)d_gf : nullptr, H_factors ? (const uint32_t*)d_hf : nullptr,
+                       (const uint32_t*)d_a, (const uint32_t*)d_b, out, lanes);
+}
+extern "C" int bpg_ipp_lanes(const bpg_ipp* st) { return st ? st->lanes : 0; }
+extern "C" size_t bpg_ipp_len(const bpg_ipp* st) { return st ? st->m : 0; }
+// current vectors, lane-major: a_out, b_out = lanes x m x 32 bytes (m = bpg_ipp_len)
+extern "C" int bpg_ipp_read_ab(bpg_ipp* st, uint8_t* a_out, uint8_t* b_out) {
+  if (!st || !a_out || !b_out) return BPG_ERR_ARG;
+  bpg_ctx* ctx = st->ctx;
+  CK(cudaSetDevice(ctx->device));
+  for (int l = 0; l < st->lanes; l++) {
+    CK(cudaMemcpyAsync(a_out + (size_t)l * st->m * 32, st->a + (size_t)l * st->n * 8, st->m * 32, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaMemcpyAsync(b_out + (size_t)l * st->m * 32, st->b + (size_t)l * st->n * 8, st->m * 32, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BPG_OK;
+}
+// c_L, c_R: lanes x 32 bytes each, this party's shares of the cross terms; L_out, R_out: lanes x 32 bytes,
+// the compressed encodings of this party's shares of L and R (per lane)
+extern "C" int bpg_ipp_round_LR_shares(bpg_ipp* st, const uint8_t* c_L, const uint8_t* c_R, uint8_t* L_out,
+                                       uint8_t* R_out) {
+  if (!st || !c_L || !c_R || !L_out || !R_out) return BPG_ERR_ARG;
+  if (st->m <= 1 || st->lr_done || st->q_sep || st->own_tab) return BPG_ERR_ARG;
+  bpg_ctx* ctx = st->ctx;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const size_t n = st->n, m = st->m;
+  const int NL = st->lanes;
+  uint8_t* hp = ctx->h_pinned + 4096;
+  for (int l = 0; l < NL; l++) {
+    memcpy(hp + 64 * l, c_L + 32 * l, 32);
+    memcpy(hp + 64 * l + 32, c_R + 32 * l, 32);
+  }
+  CK(cudaMemcpyAsync(st->c_ext, hp, 64 * (size_t)NL, cudaMemcpyHostToDevice, s));
+  prof_mark(ctx, BPG_PROF_OTHER);
+  k_ipp_round_scalars<<<dim3((unsigned)((n + 255) / 256), (unsigned)NL), 256, 0, s>>>(st->a, st->b, st->wG, st->wH, (uint32_t)n,
+                                                                                     (uint32_t)m, st->scalars, st->set_ids);
+  LAUNCH_CHECK();
+  k_ipp_q_terms_ext<<<1, 32, 0, s>>>(st->c_ext, st->has_qmul ? st->q_mul : nullptr, (uint32_t)n, (uint32_t)NL, st->scalars,
+                                     st->set_ids);
+  LAUNCH_CHECK();
+  int rc = msm_enqueue(ctx, st->tab->niels, st->tab->n, st->scalars, (size_t)NL * (2 * n + 2), st->set_ids, st->point_ids,
+                       2 * NL, st->out_ext, st->tab->win_c, st->tab->n);
+  if (rc) return rc;
+  rc = bpg_dev_sum_encode(ctx, st->out_ext, 1, 2 * NL, st->out_bytes, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->h_pinned, st->out_bytes, 64 * (size_t)NL, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (int l = 0; l < NL; l++) {
+    memcpy(L_out + 32 * l, ctx->h_pinned + 64 * l, 32);
+    memcpy(R_out + 32 * l, ctx->h_pinned + 64 * l + 32, 32);
+  }
+  st->lr_done = true;
+  return BPG_OK;
+}
+// final a, b of every lane (lanes x 32 bytes each): this party's shares (:217-228)
+extern "C" int bpg_ipp_finish_shares(bpg_ipp* st, uint8_t* a, uint8_t* b) {
+  if (!st || !a || !b) return BPG_ERR_ARG;
+  if (st->m != 1) return BPG_ERR_ARG;
+  return bpg_ipp_read_ab(st, a, b);
 }
 
 extern "C" int bpg_ipp_finish(bpg_ipp* st, uint8_t a[32], uint8_t b[32]) {

@@ -139,6 +139,14 @@ static __global__ void __launch_bounds__(256) k_ipp_round_scalars(const uint32_t
                                                             uint8_t* __restrict__ set_ids) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  // lane = blockIdx.y: a party's share vectors and their MAC vectors (r1cs_mpc) are further (a, b) pairs that
+  // meet the same generator weights; lane k's sums are output sets 2k (L) and 2k + 1 (R)
+  const uint32_t lane = blockIdx.y;
+  const size_t T = 2 * (size_t)n + 2;
+  a += (size_t)lane * n * 8;
+  b += (size_t)lane * n * 8;
+  scalars += lane * T * 8;
+  set_ids += lane * T;
   uint32_t h = m >> 1;
   uint32_t p = i & (m - 1);
   bool hi = (p & h) != 0;
@@ -150,8 +158,29 @@ static __global__ void __launch_bounds__(256) k_ipp_round_scalars(const uint32_t
   sc_load(hh, wH + (size_t)i * 8);
   sc_store(scalars + (size_t)i * 8, sc_montmul(av, g));         // G_i: a_lo with G_hi -> L, a_hi with G_lo -> R
   sc_store(scalars + (size_t)(n + i) * 8, sc_montmul(bv, hh));  // H_i: b_hi with H_lo -> L, b_lo with H_hi -> R
-  set_ids[i] = hi ? 0 : 1;
-  set_ids[n + i] = hi ? 1 : 0;
+  set_ids[i] = (uint8_t)(2 * lane + (hi ? 0 : 1));
+  set_ids[n + i] = (uint8_t)(2 * lane + (hi ? 1 : 0));
+}
+
+// Cross terms supplied by the caller (r1cs_mpc: c_L, c_R are products of SHARED vectors, so they come out of
+// the fabric's multiplication protocol, reference src/r1cs_mpc/mpc_inner_product.rs:104-105, 172-173):
+// c[lane][0..1] canonical scalars -> the two Q terms of every lane, times q_mul when Q = q_mul * base point.
+static __global__ void k_ipp_q_terms_ext(const uint32_t* __restrict__ c /*[lanes][2][8]*/, const uint32_t* __restrict__ q_mul,
+                                         uint32_t n, uint32_t lanes, uint32_t* __restrict__ scalars,
+                                         uint8_t* __restrict__ set_ids) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * lanes) return;
+  uint32_t lane = t >> 1, side = t & 1;
+  const size_t T = 2 * (size_t)n + 2;
+  sc v;
+  sc_load(v, c + (size_t)t * 8);
+  if (q_mul) {
+    sc q;
+    sc_load(q, q_mul);
+    v = sc_montmul(v, sc_to_mont(q));
+  }
+  sc_store(scalars + (lane * T + 2 * (size_t)n + side) * 8, v);
+  set_ids[lane * T + 2 * (size_t)n + side] = (uint8_t)(2 * lane + side);
 }
 
 // the round's challenge and its inverse (canonical words), passed by value
@@ -165,6 +194,9 @@ static __global__ void __launch_bounds__(256) k_ipp_fold(uint32_t* __restrict__ 
                                                    uint32_t m, ScPair u_pair /*u, u_inv: kernel arguments, no copy*/) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const uint32_t lane = blockIdx.y;  // further (a, b) pairs folding with the same public challenge (r1cs_mpc lanes)
+  a += (size_t)lane * n * 8;
+  b += (size_t)lane * n * 8;
   sc u, ui;
 #pragma unroll
   for (int w = 0; w < 8; w++) {
@@ -176,11 +208,13 @@ static __global__ void __launch_bounds__(256) k_ipp_fold(uint32_t* __restrict__ 
   uint32_t h = m >> 1;
   uint32_t p = i & (m - 1);
   bool hi = (p & h) != 0;
-  sc g, hh;
-  sc_load(g, wG + (size_t)i * 8);
-  sc_load(hh, wH + (size_t)i * 8);
-  sc_store(wG + (size_t)i * 8, sc_montmul(g, hi ? u : ui));   // G' = u^-1 G_lo + u G_hi
-  sc_store(wH + (size_t)i * 8, sc_montmul(hh, hi ? ui : u));  // H' = u H_lo + u^-1 H_hi
+  if (lane == 0) {
+    sc g, hh;
+    sc_load(g, wG + (size_t)i * 8);
+    sc_load(hh, wH + (size_t)i * 8);
+    sc_store(wG + (size_t)i * 8, sc_montmul(g, hi ? u : ui));   // G' = u^-1 G_lo + u G_hi
+    sc_store(wH + (size_t)i * 8, sc_montmul(hh, hi ? ui : u));  // H' = u H_lo + u^-1 H_hi
+  }
   if (i < h) {
     sc alo, ahi, blo, bhi;
     sc_load(alo, a + (size_t)i * 8);
@@ -195,6 +229,7 @@ static __global__ void __launch_bounds__(256) k_ipp_fold(uint32_t* __restrict__ 
 // point ids of the round MSM's 2n+2 terms: G_i, H_i, Q, Q
 static __global__ void k_ipp_point_ids(uint32_t* out, uint32_t n, uint32_t g_base, uint32_t h_base, uint32_t q_id) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  out += (size_t)blockIdx.y * (2 * (size_t)n + 2);  // one copy per lane
   if (i < n) {
     out[i] = g_base + i;
     out[n + i] = h_base + i;

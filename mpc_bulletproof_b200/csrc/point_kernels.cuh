@@ -76,6 +76,40 @@ static __global__ void __launch_bounds__(ENC_THREADS) k_sum_encode(const uint32_
   }
 }
 
+// out[set] = encode(sum_p decode(points[p][set])): the "open" of additively shared points (r1cs_mpc: the
+// parties' shares of a commitment, exchanged as compressed encodings, reference
+// src/r1cs_mpc/mpc_prover.rs:630-657, mpc_inner_product.rs:131,191).  One warp per set: lane p decodes
+// part p (an inverse square root each), lane 0 adds, the warp encodes.  bad_count: invalid encodings.
+static __global__ void __launch_bounds__(ENC_THREADS) k_points_sum(const uint8_t* __restrict__ points, int nparts, int nsets,
+                                                             uint8_t* __restrict__ out_bytes,
+                                                             uint32_t* __restrict__ bad_count) {
+  __shared__ __align__(16) uint32_t sm[G16_WORDS];
+  __shared__ __align__(16) uint32_t dec[32][32];
+  const uint32_t set = blockIdx.x;
+  grp16 g = warp_group(sm);
+  if ((int)threadIdx.x < nparts) {
+    uint8_t buf[32];
+    const uint8_t* src = points + ((size_t)threadIdx.x * nsets + set) * 32;
+    for (int i = 0; i < 32; i++) buf[i] = src[i];
+    ge_ext p;
+    if (!ge_decode(p, buf)) {
+      atomicAdd(bad_count, 1u);
+      p = ge_identity();
+    }
+    ge_store_ext(dec[threadIdx.x], p);
+  }
+  __syncwarp();
+  ge_ext acc;
+  ge_load_ext(acc, dec[0]);
+  for (int p = 1; p < nparts; p++) {
+    ge_ext o;
+    ge_load_ext(o, dec[p]);
+    acc = ge_add(acc, o);
+  }
+  fe s = ge_encode16<true>(g, acc);
+  if (threadIdx.x < 16) store_s_bytes(out_bytes + (size_t)set * 32, s, g.k);
+}
+
 // Accept-iff-identity (Verifier::verify, reference src/r1cs/verifier.rs:549): no encoding, hence no
 // inverse square root.  A ristretto255 element equals the identity iff X = 0 or Y = 0 (RFC 9496
 // §4.3.3: X1 Y2 == Y1 X2 or Y1 Y2 == X1 X2 against (0 : 1 : 1 : 0)).  out: 32 zero bytes (the
