@@ -49,10 +49,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lg-points", type=int, default=20, help="log2 of the points per GPU")
-    ap.add_argument("--cpu-sample-lg", type=int, default=18, help="log2 of the CPU-baseline sample size")
+    ap.add_argument("--cpu-sample-lg", type=int, default=20, help="log2 of the CPU-baseline sample size (default: the whole per-GPU workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-combine", action="store_true", help="N>1: NCCL all-gather + combine launch instead of the fused peer exchange")
     ap.add_argument("--no-r1cs", action="store_true", help="skip the R1CS prove/verify timing at 2^16 multipliers")
+    ap.add_argument("--no-varbase", action="store_true", help="skip the variable-base (ad-hoc points, no precomputed table) MSM timing")
     ap.add_argument("--r1cs-lg", type=int, default=16)
     return ap.parse_args()
 
@@ -129,6 +130,19 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+ACCUM_SOURCES = ["msm_accum_kernels.cuh", "msm_sort_kernels.cuh", "ge.cuh", "fe.cuh", "msm_accum.cu"]
+
+
+def kernel_source_hash() -> str:
+    import hashlib
+
+    h = hashlib.sha256()
+    for name in ACCUM_SOURCES:
+        with open(os.path.join(ROOT, "mpc_bulletproof_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def int32_peak():
     """wide multiply-add issue peak measured by tools/int32_peak (committed under profiles/)."""
     p = os.path.join(ROOT, "profiles", "int32_peak.json")
@@ -150,6 +164,32 @@ def ensure_oracle():
     return cbind
 
 
+def host_threads() -> int:
+    """every host core this process may run on -- NOT omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1 into its ranks, which would silently turn the CPU arm into a one-thread run"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+NSETS_ROT = 4  # scalar sets rotated through so that no step re-reads the previous step's scalars
+
+
+def workload_config(args, world: int) -> dict:
+    """identical in both arms: what one step computes"""
+    n = 1 << args.lg_points
+    return {
+        "workload": f"msm_2^{args.lg_points}_points_per_gpu",
+        "group": "ristretto255",
+        "points_per_gpu": n,
+        "points_total": world * n,
+        "scalars": "uniform in [0, 2^252), 32 bytes each",
+        "points": "k_i*B, k_i uniform",
+        "l2": f"{NSETS_ROT} scalar sets of {n * 32 >> 20} MiB rotated per GPU; scalars + table + sort/bucket workspace are far above the 126 MB L2",
+    }
+
+
 def host_uniform_scalars(n: int, seed: int) -> bytes:
     import numpy as np
 
@@ -160,23 +200,30 @@ def host_uniform_scalars(n: int, seed: int) -> bytes:
 
 
 def run_reference(args, rank, world):
+    """The reference's CPU path for the same workload on the box's host cores: oracle/c (the C restatement of
+    the reference algorithm; the Rust crate cannot be built here) with every host thread, one step = one
+    MSM over the same number of points per GPU as this framework's arm.  Rank 0 only."""
     if rank != 0:
         return
     cbind = ensure_oracle()
-    threads = cbind.max_threads()
-    n = 1 << args.cpu_sample_lg
+    threads = host_threads()
+    n = 1 << args.lg_points
     pts = cbind.basepoint_mul(host_uniform_scalars(n, 0xB2000003), threads)
     dec = cbind.DecodedPoints(pts, threads)
-    sc = [host_uniform_scalars(n, 0xB2000100 + i) for i in range(2)]
+    sc = [host_uniform_scalars(n, 0xB2000100 + i) for i in range(NSETS_ROT)]
     for i in range(args.warmup):
-        dec.msm(sc[i % 2], threads=threads)
+        dec.msm(sc[i % NSETS_ROT], threads=threads)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        dec.msm(sc[i % 2], threads=threads)
+        dec.msm(sc[i % NSETS_ROT], threads=threads)
     dt = time.perf_counter() - t0
     ms = dt / args.steps * 1e3
     val = n / ms / 1e3
-    sample = f"2^{args.cpu_sample_lg}-point MSM per step (same per-point algorithm as the 2^{args.lg_points} workload; dalek-style radix-2^8 Pippenger, digit columns over {threads} OpenMP threads; points pre-decoded)"
+    sample = (f"one 2^{args.lg_points}-point variable-base MSM per step, the whole per-GPU workload (dalek-style radix-2^8 "
+              f"Pippenger, digit columns over {threads} OpenMP threads; points pre-decoded, scalars in host memory)")
+    r1cs = None
+    if not args.no_r1cs:
+        r1cs = cpu_r1cs_baseline(cbind, threads, args.r1cs_lg)
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -191,12 +238,52 @@ def run_reference(args, rank, world):
         "vs_baseline": None,
         "dtype": "u64 limbs (radix 2^51)",
         "data": "synthetic",
-        "config": {"workload": f"msm_2^{args.lg_points}_points_per_gpu", "group": "ristretto255", "sample_points": n},
+        "config": workload_config(args, max(args.gpus, 1)),
+        "impl_config": {"algorithm": "variable-base Pippenger, radix 2^8 (32 bucket additions per point), no precomputed table",
+                        "host_threads": threads, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "r1cs": r1cs,
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def cpu_r1cs_baseline(cbind, threads: int, lg: int) -> dict:
+    """The first half of BASELINE.json's metric on the host cores: the group work of `Prover::prove` and
+    `Verifier::verify` at 2^lg multipliers as the reference performs it (src/r1cs/prover.rs:465-494, 627-631,
+    699-708; src/r1cs/verifier.rs:516-547), from oracle/c: the three phase-1 commitment MSMs (2n+1, n+1, 2n+1
+    terms), `InnerProductProof::create` at n = 2^lg with factors (2n sequential scalar multiplications, then
+    lg n rounds of two MSMs and a threaded two-term-MSM fold), and for verify the single 2n+13+2 lg n term MSM.
+    The O(n) scalar-field work around them (flattening, polynomials) is NOT included: this is a lower bound
+    of the CPU time, which makes the GPU/CPU ratio conservative."""
+    n = 1 << lg
+    G = cbind.basepoint_mul(host_uniform_scalars(n, 0xB2000011), threads)
+    H = cbind.basepoint_mul(host_uniform_scalars(n, 0xB2000012), threads)
+    Q = cbind.basepoint_mul(host_uniform_scalars(1, 0xB2000013), threads)
+    s = [host_uniform_scalars(2 * n + 16 + 2 * lg, 0xB2000020 + i) for i in range(4)]
+    dec = cbind.DecodedPoints(G + H, threads)
+    t0 = time.perf_counter()
+    dec.msm(s[0][: 64 * n], 0, 2 * n, threads=threads)  # A_I
+    dec.msm(s[1][: 32 * n], 0, n, threads=threads)      # A_O
+    dec.msm(s[2][: 64 * n], 0, 2 * n, threads=threads)  # S
+    t_commit = time.perf_counter() - t0
+    us = host_uniform_scalars(lg, 0xB2000030)
+    t0 = time.perf_counter()
+    cbind.ipp_create(Q, s[0][: 32 * n], s[1][: 32 * n], G, H, s[2][: 32 * n], s[3][: 32 * n], us, threads)
+    t_ipp = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    dec.msm(s[3][: 64 * n], 0, 2 * n, threads=threads)  # the verifier's mega-MSM (its 13 + 2 lg n ad-hoc terms are negligible)
+    t_verify = time.perf_counter() - t0
+    return {
+        "multipliers": n,
+        "prove_ms": (t_commit + t_ipp) * 1e3,
+        "verify_ms": t_verify * 1e3,
+        "prove_parts_ms": {"commitment_msms": t_commit * 1e3, "ipp_create": t_ipp * 1e3},
+        "cores": threads,
+        "kind": "port",
+        "what": "group work only (commitment MSMs + InnerProductProof::create; verify: the mega-MSM), points pre-decoded for the MSMs; a lower bound of the CPU prove/verify time",
+    }
 
 
 # ---------------------------------------------------------------------------------
@@ -217,7 +304,6 @@ def run_b200(args, rank, local_rank, world):
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
     n = 1 << args.lg_points
-    NSETS_ROT = 4  # scalar sets rotated through so that no step re-reads the previous step's scalars
 
     def uniform_scalars(count, seed):
         g = torch.Generator(device=dev)
@@ -297,6 +383,30 @@ def run_b200(args, rank, local_rank, world):
     value = world * n / ms_step / 1e3
     result_hex = bytes(result.cpu().tolist()).hex()
 
+    # ---- in-run parity of the timed computation, every N: the table's points are k_i*B, so the result of the
+    # last timed step must be (sum over all ranks of sum_i s_i k_i mod l) * B -- formed here from each rank's
+    # exact integer dot product (host big integers) and ONE fixed-base multiplication
+    L_ORDER = 2**252 + 27742317777372353535851937790883648493
+    last = scal[(args.steps - 1) % NSETS_ROT] if args.steps > 0 else scal[0]
+    if args.steps == 0:
+        with torch.cuda.stream(stream):
+            step(0)
+        barrier()
+        result_hex = bytes(result.cpu().tolist()).hex()
+
+    def ints(t):
+        raw = t.cpu().numpy().tobytes()
+        return [int.from_bytes(raw[i : i + 32], "little") for i in range(0, len(raw), 32)]
+
+    dot = sum(a * k for a, k in zip(ints(last), ints(gen_k))) % L_ORDER
+    dots = torch.tensor(list(dot.to_bytes(32, "little")), dtype=torch.uint8, device=dev)
+    if world > 1:
+        all_dots = [torch.empty_like(dots) for _ in range(world)]
+        dist.all_gather(all_dots, dots)
+        dot = sum(int.from_bytes(bytes(d.cpu().tolist()), "little") for d in all_dots) % L_ORDER
+    expected_hex = comb.mul(dot.to_bytes(32, "little")).hex()
+    result_ok = expected_hex == result_hex
+
     # ---- end to end through the host-buffer C ABI ("e2e") ----------------------
     # every step: scalars start in pinned HOST memory, go H2D, the MSM runs, the
     # 32-byte result comes back D2H.  N=1 uses bpg_msm_table itself; N>1 adds the
@@ -349,11 +459,16 @@ def run_b200(args, rank, local_rank, world):
         acc_ms = acc_ms / max(acc_n, 1)
         alg_bytes = 128.0 * n  # 32 B scalar + 96 B Niels entry per point
         achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else None
-        traffic = None
+        # DRAM bytes per launch of the dominant kernel come from an ncu capture (profiles/accum_traffic.json);
+        # the capture records a hash of the kernel's sources, and a capture of other code reads as null
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "accum_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            if tj.get("kernel_source_sha256") == kernel_source_hash():
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = tj.get("capture")
         roof = {
             "bound": "hbm",
             "kernel": "k_accum (bucket accumulation)",
@@ -363,6 +478,7 @@ def run_b200(args, rank, local_rank, world):
             "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"] if achieved else None,
             "traffic": traffic,
+            "traffic_capture": traffic_src,
             "kernel_ms": acc_ms,
             "kernel_share_of_step": acc_ms / ms_step if ms_step else None,
             "note": "the kernel is INT32-issue-bound, not HBM-bound; see int32",
@@ -387,6 +503,10 @@ def run_b200(args, rank, local_rank, world):
         r1cs = None
         if world == 1 and not args.no_r1cs:
             r1cs = r1cs_timing(ctx, comb, args.r1cs_lg, dev)
+        varbase = None
+        if world == 1 and not args.no_varbase:
+            varbase = variable_base_timing(ctx, pts_bytes, host_sc[0], n, min(args.steps, 5))
+        table_bytes = n * table.entry_bytes * table_windows
         line = {
             "metric": METRIC,
             "value": value,
@@ -400,14 +520,11 @@ def run_b200(args, rank, local_rank, world):
             "vs_baseline": None,
             "dtype": "u32 limbs (8x32-bit, GF(2^255-19))",
             "data": "synthetic",
-            "config": {
-                "workload": f"msm_2^{args.lg_points}_points_per_gpu",
-                "group": "ristretto255",
-                "points_total": world * n,
-                "scalars": "uniform in [0, 2^252)",
-                "points": "k_i*B, k_i uniform (device fixed-base comb)",
-                "table": f"windowed affine-Niels, c={table.window}, {(n * 96 * ((255 + table.window - 1) // table.window)) >> 20} MiB resident",
-                "l2": f"{NSETS_ROT} scalar sets of {n * 32 >> 20} MiB rotated + the table + sort/bucket workspace, all far above the 126 MB L2",
+            "config": workload_config(args, world),
+            "impl_config": {
+                "algorithm": f"fixed-base Pippenger over a resident windowed table (one gathered multiple per window, {table_windows} bucket additions per point, no doublings)",
+                "table": f"windowed affine-Niels, c={table.window}, {table_bytes >> 20} MiB resident",
+                "points_from": "device fixed-base comb",
                 "gpoint_ops_per_s_eq": 16 * world * n / (ms_step * 1e-3) / 1e9,
                 "combine": combine,
             },
@@ -424,8 +541,11 @@ def run_b200(args, rank, local_rank, world):
             "roofline": roof,
             "cpu_baseline": cpu,
             "r1cs": r1cs,
+            "variable_base": varbase,
             "clocks": clk,
             "result": result_hex,
+            "result_ok": result_ok,
+            "result_check": "encode((sum_ranks sum_i s_i k_i mod l) * B) from host big integers + one fixed-base multiplication",
         }
         emit(line)
     if peer is not None:
@@ -496,6 +616,35 @@ def r1cs_timing(ctx, comb, lg, dev):
     }
 
 
+def variable_base_timing(ctx, pts_bytes_dev, host_scalars, n, reps):
+    """BASELINE.json config 3 as the reference calls it for points it has never seen (src/r1cs/verifier.rs:516-547
+    for ad-hoc points): `bpg_msm` on n COMPRESSED points and n scalars, both in host memory -- upload, decode to
+    affine Niels, a plain (one multiple per point) table, Pippenger with per-window bucket arrays and Horner;
+    nothing precomputed, nothing resident.  Wall clock per call, best of `reps`."""
+    import ctypes
+
+    from mpc_bulletproof_b200._lib import check, lib
+
+    pts = pts_bytes_dev.cpu().pin_memory()
+    out = ctypes.create_string_buffer(32)
+    best, res = 1e9, None
+    for _ in range(max(reps, 2)):
+        t0 = time.perf_counter()
+        check(lib().bpg_msm(ctx._h, ctypes.c_void_p(host_scalars.data_ptr()), ctypes.c_void_p(pts.data_ptr()), n, out))
+        best = min(best, time.perf_counter() - t0)
+        res = out.raw.hex()
+    return {
+        "api": "bpg_msm (compressed points + scalars in host memory; decode + plain table + Pippenger with Horner per call)",
+        "points": n,
+        "ms": best * 1e3,
+        "value": n / best / 1e6,
+        "unit": UNIT,
+        "h2d_bytes": n * 64,
+        "result": res,
+        "note": "the headline `value` uses a table precomputed once (fixed-base, 13 additions per point); this is the no-precomputation form, the same algorithm class as the CPU arm",
+    }
+
+
 def cpu_baseline(args, pts_bytes_dev, scal_dev, n):
     """The C restatement of the reference CPU algorithm on a bounded sample, host cores."""
     try:
@@ -505,7 +654,7 @@ def cpu_baseline(args, pts_bytes_dev, scal_dev, n):
     m = min(n, 1 << args.cpu_sample_lg)
     pts = bytes(pts_bytes_dev[: m * 32].cpu().numpy().tobytes())
     sc = bytes(scal_dev[:m].cpu().numpy().tobytes())
-    threads = cbind.max_threads()
+    threads = host_threads()
     dec = cbind.DecodedPoints(pts, threads)
     dec.msm(sc, threads=threads)
     reps = 3
@@ -523,12 +672,14 @@ def cpu_baseline(args, pts_bytes_dev, scal_dev, n):
     gpu = Table(ctx2, pts).msm(sc)[0]
     ctx2.close()
     ipp = cpu_ipp_baseline(cbind, threads, pts, sc, 14)
+    r1cs_cpu = None if args.no_r1cs else cpu_r1cs_baseline(cbind, threads, args.r1cs_lg)
     return {
         "value": m / dt / 1e6,
         "unit": UNIT,
         "cores": threads,
         "kind": "port",
         "ipp_create": ipp,
+        "r1cs": r1cs_cpu,
         "sample": f"first 2^{m.bit_length() - 1} points+scalars of the workload, dalek-style radix-2^8 Pippenger, points pre-decoded, {reps} runs",
         "single_thread_value": (m // 4) / dt1 / 1e6,
         "bytes_equal_gpu": gpu == out,

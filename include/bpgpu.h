@@ -93,6 +93,7 @@ int bpg_table_upload_dev(bpg_ctx* ctx, const void* d_points_compressed, size_t n
 int bpg_table_set_windows(bpg_ctx* ctx, bpg_table* t, int c);
 int bpg_table_window(const bpg_table* t); /* 0 = plain */
 size_t bpg_table_len(const bpg_table* t);
+size_t bpg_table_entry_bytes(const bpg_table* t); /* bytes of HBM per resident multiple of a point */
 void bpg_table_free(bpg_table* t);
 
 /* ---- multiscalar multiplication ----------------------------------------------------

@@ -101,6 +101,7 @@ _SIGNATURES = {
     "bpg_table_upload": (_I, [_P, _P, _SZ, ctypes.POINTER(_P)]),
     "bpg_table_upload_dev": (_I, [_P, _P, _SZ, ctypes.POINTER(_P)]),
     "bpg_table_len": (_SZ, [_P]),
+    "bpg_table_entry_bytes": (_SZ, [_P]),
     "bpg_table_set_windows": (_I, [_P, _P, _I]),
     "bpg_table_window": (_I, [_P]),
     "bpg_table_free": (None, [_P]),

@@ -90,6 +90,10 @@ class Table:
         return self
 
     @property
+    def entry_bytes(self) -> int:
+        return int(lib().bpg_table_entry_bytes(self._h))
+
+    @property
     def window(self) -> int:
         return int(lib().bpg_table_window(self._h))
 

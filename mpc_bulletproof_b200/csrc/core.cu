@@ -363,6 +363,7 @@ extern "C" int bpg_table_upload(bpg_ctx* ctx, const uint8_t* comp, size_t n, bpg
 }
 
 extern "C" size_t bpg_table_len(const bpg_table* t) { return t ? t->n : 0; }
+extern "C" size_t bpg_table_entry_bytes(const bpg_table* t) { return t ? 96 : 0; }
 extern "C" void bpg_table_free(bpg_table* t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
