@@ -92,6 +92,13 @@ int bpg_table_upload_dev(bpg_ctx* ctx, const void* d_points_compressed, size_t n
  * always use its c. */
 int bpg_table_set_windows(bpg_ctx* ctx, bpg_table* t, int c);
 int bpg_table_window(const bpg_table* t); /* 0 = plain */
+/* Give every point of a resident table a COMB: the 64 x 8 affine-Niels multiples (d+1) 16^j P_i, 48 KB per
+ * point, so that k P_i is 64 additions with no doublings, no buckets and no sort.  One-time cost (like
+ * bpg_table_set_windows).  The inner-product rounds use the combs of a generator table for short vectors and
+ * to materialise the folded generators of long ones (csrc/comb_kernels.cuh); bpg_gens_new builds them when
+ * they fit BPG_COMB_MAX_GB (default 16) gigabytes. */
+int bpg_table_build_comb(bpg_ctx* ctx, bpg_table* t);
+int bpg_table_has_comb(const bpg_table* t);
 size_t bpg_table_len(const bpg_table* t);
 size_t bpg_table_entry_bytes(const bpg_table* t); /* bytes of HBM per resident multiple of a point */
 void bpg_table_free(bpg_table* t);

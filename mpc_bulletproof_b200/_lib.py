@@ -104,6 +104,8 @@ _SIGNATURES = {
     "bpg_table_entry_bytes": (_SZ, [_P]),
     "bpg_table_set_windows": (_I, [_P, _P, _I]),
     "bpg_table_window": (_I, [_P]),
+    "bpg_table_build_comb": (_I, [_P, _P]),
+    "bpg_table_has_comb": (_I, [_P]),
     "bpg_table_free": (None, [_P]),
     "bpg_msm": (_I, [_P, _P, _P, _SZ, _P]),
     "bpg_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),

@@ -89,6 +89,15 @@ class Table:
         check(lib().bpg_table_set_windows(self.ctx._h, self._h, c))
         return self
 
+    def build_comb(self):
+        """64 x 8 multiples per point (48 KB each): lets inner-product rounds over this table skip the bucket method."""
+        check(lib().bpg_table_build_comb(self.ctx._h, self._h))
+        return self
+
+    @property
+    def has_comb(self) -> bool:
+        return bool(lib().bpg_table_has_comb(self._h))
+
     @property
     def entry_bytes(self) -> int:
         return int(lib().bpg_table_entry_bytes(self._h))

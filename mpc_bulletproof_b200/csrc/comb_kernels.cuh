@@ -1,0 +1,469 @@
+// Comb (fixed-base, doubling-free) multiscalar multiplication for the inner-product argument, sm_100a.
+//
+// `InnerProductProof::create` (reference src/inner_product_proof.rs:49-193) works on vectors that halve every
+// round: its L/R MSMs have 2m + 1 terms in a round of length m, and it folds the generators with 2m
+// two-term MSMs (:226-227).  A bucket-method MSM costs a fixed dozen dependent launches whatever its size,
+// and the no-fold form of ipp_kernels.cuh costs 2n terms in every round.  This file removes both:
+//
+//  * A COMB of a point P holds (d+1) 16^j P for the 64 signed 4-bit windows j and d < 8, so that k P is 64
+//    additions, no doublings, no buckets, no sort.  Resident generator tables carry one (affine Niels, 96 B
+//    per entry, built once: k_table_comb_build).
+//  * Rounds over at most a few thousand generators run as ONE accumulation kernel over (term, window) pairs
+//    plus ONE finishing kernel (cross terms, the Q term, the tree over the blocks' partial sums, the two
+//    encodings): k_comb_round / k_comb_final.  Their scalars a_partner * w(i) are formed on the fly.
+//  * For long vectors the first rounds keep the bucket method over the original generators (no-fold form);
+//    when the vectors have shrunk to m0 entries the folded generators G'_p = sum_{i = p mod m0} w(i) G_i are
+//    MATERIALISED once from the generator combs (k_comb_materialize: the reference's accumulated folds,
+//    :125-146, as 2 m0 small MSMs), given combs of their own (k_comb_chain, k_comb_multiples: projective
+//    "cached" entries, no inversion) and the remaining rounds run on m0 points.
+// All of it computes the same group elements as the reference's round, hence the same encodings.
+#pragma once
+#include "ge.cuh"
+#include "ge4.cuh"
+#include "fe16.cuh"
+#include "sc.cuh"
+
+namespace bpg {
+
+constexpr int COMB_AFFINE_WORDS = 24;  // (y+x, y-x, 2dxy), Z = 1
+constexpr int COMB_CACHED_WORDS = 32;  // (Y-X, Y+X, 2Z, 2dT)
+
+// acc +- entry
+template <bool AFFINE>
+__device__ __forceinline__ ge_ext comb_add(const ge_ext& acc, const uint32_t* __restrict__ e, bool neg) {
+  if (AFFINE) {
+    ge_niels q;
+    ge_load_niels(q, e);
+    return ge_madd(acc, q, neg);
+  } else {
+    fe ymx, ypx, z2, t2d;
+    fe_load(ymx, e);
+    fe_load(ypx, e + 8);
+    fe_load(z2, e + 16);
+    fe_load(t2d, e + 24);
+    fe nt = fe_neg(t2d);
+    fe a = fe_sel(neg, ypx, ymx), b = fe_sel(neg, ymx, ypx), t = fe_sel(neg, nt, t2d);
+    return ge_add_cached(acc, a, b, z2, t);
+  }
+}
+// sum over windows [j0, j1) of digit_j * 16^j * P from P's comb
+template <bool AFFINE>
+__device__ __forceinline__ ge_ext comb_windows(const uint32_t* __restrict__ comb_of_point, const sc_recoded& r, int j0, int j1) {
+  constexpr int WORDS = AFFINE ? COMB_AFFINE_WORDS : COMB_CACHED_WORDS;
+  ge_ext acc = ge_identity();
+  for (int j = j0; j < j1; j++) {
+    int d = sc_digit(r, j, 4);
+    if (d != 0) {
+      int mag = d < 0 ? -d : d;
+      acc = comb_add<AFFINE>(acc, comb_of_point + (size_t)(j * 8 + mag - 1) * WORDS, d < 0);
+    }
+  }
+  return acc;
+}
+
+// every thread of the block holds one extended point; the block's sum lands in quad 0 of warp 0 (all threads call)
+constexpr int CB_THREADS = 128;
+__device__ __forceinline__ ge4 comb_block_sum(const ge_ext& mine, uint32_t (*pts)[32] /*[CB_THREADS][32]*/,
+                                              uint32_t (*sm)[32] /*[CB_THREADS/32][32]*/) {
+  ge_store_ext(pts[threadIdx.x], mine);
+  __syncthreads();
+  int g = threadIdx.x >> 2;
+  ge4 t = ge4_load(pts[4 * g]);
+#pragma unroll
+  for (int k = 1; k < 4; k++) t = ge4_add(t, ge4_load(pts[4 * g + k]));
+  return block_sum_quads(t, sm);
+}
+
+// ---------------------------------------------------------------------------
+// one-time: the comb of every point of a resident table.  Block = one point, thread j = window j:
+// 4 j doublings, the eight multiples, ONE inversion for the eight (Montgomery's trick), affine Niels out.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(COMB_WINDOWS) k_table_comb_build(const uint32_t* __restrict__ niels /*window 0 of the table*/,
+                                                                   uint32_t first, uint32_t* __restrict__ comb) {
+  const uint32_t i = first + blockIdx.x;
+  const int j = threadIdx.x;
+  ge_niels q;
+  ge_load_niels(q, niels + (size_t)i * 24);
+  ge_ext p = ge_from_niels(q, false);
+  for (int k = 0; k < 4 * j; k++) p = ge_dbl(p);
+  // forward: the eight multiples, parked projectively (X | Y | Z = 24 words) in the entries they will become,
+  // with the running product of their Z; backward: one inversion serves all eight (Montgomery's trick)
+  uint32_t* out = comb + ((size_t)i * COMB_WINDOWS + j) * 8 * COMB_AFFINE_WORDS;
+  ge_ext m = p;
+  fe zp[8];
+#pragma unroll
+  for (int d = 0; d < 8; d++) {
+    if (d) m = ge_add(m, p);
+    zp[d] = d ? fe_mul(zp[d - 1], m.Z) : m.Z;
+    fe_store(out + (size_t)d * COMB_AFFINE_WORDS, m.X);
+    fe_store(out + (size_t)d * COMB_AFFINE_WORDS + 8, m.Y);
+    fe_store(out + (size_t)d * COMB_AFFINE_WORDS + 16, m.Z);
+  }
+  fe inv = fe_invert(zp[7]);
+#pragma unroll
+  for (int d = 7; d >= 0; d--) {
+    fe X, Y, Z;
+    fe_load(X, out + (size_t)d * COMB_AFFINE_WORDS);
+    fe_load(Y, out + (size_t)d * COMB_AFFINE_WORDS + 8);
+    fe_load(Z, out + (size_t)d * COMB_AFFINE_WORDS + 16);
+    fe zi = d ? fe_mul(inv, zp[d - 1]) : inv;
+    inv = fe_mul(inv, Z);
+    ge_store_niels(out + (size_t)d * COMB_AFFINE_WORDS, ge_affine_to_niels(fe_mul(X, zi), fe_mul(Y, zi)));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// a round's accumulation.  grid.y = output set s = 2 lane + side (side 0: L, 1: R), grid.x covers the n terms
+// of that set -- the G_i with bit h of i set (L) / clear (R) and the H_i with bit h clear (L) / set (R), exactly
+// the pairing of inner_product_proof.rs:90-114, 159-172 -- times WSPLIT window slices.  A block is
+// set-homogeneous, so its 128 accumulators reduce to ONE partial sum: parts[s][blockIdx.x].
+// ---------------------------------------------------------------------------
+struct CombRound {
+  const uint32_t* comb;   // combs of the generators
+  uint32_t g_id, h_id;    // comb index of G_0 and of H_0
+  const uint32_t *a, *b;  // [lanes][stride] current vectors (normal form)
+  const uint32_t *wG, *wH;  // [n] weights, Montgomery form (null: all ones)
+  uint32_t stride;        // lane stride of a, b in scalars
+  uint32_t n;             // generators per vector (weights length)
+  uint32_t m;             // current vector length (power of two <= n)
+  uint32_t wsplit;        // threads per term: each takes 64 / wsplit windows (power of two <= 64)
+  sc_bias bias4;
+};
+template <bool AFFINE>
+__global__ void __launch_bounds__(CB_THREADS) k_comb_round(CombRound R, uint32_t* __restrict__ parts /*[sets][gridDim.x][32]*/) {
+  constexpr int WORDS = AFFINE ? COMB_AFFINE_WORDS : COMB_CACHED_WORDS;
+  __shared__ __align__(16) uint32_t pts[CB_THREADS][32];
+  __shared__ __align__(16) uint32_t sm[CB_THREADS / 32][32];
+  const uint32_t set = blockIdx.y, lane_id = set >> 1, side = set & 1;
+  const uint32_t u = blockIdx.x * CB_THREADS + threadIdx.x;
+  const uint32_t k = u / R.wsplit, slice = u % R.wsplit;
+  ge_ext acc = ge_identity();
+  if (k < R.n) {
+    const uint32_t half = R.n >> 1, h = R.m >> 1;
+    const bool is_h = k >= half;
+    const uint32_t kk = is_h ? k - half : k;
+    // the kk-th index whose bit h is set / clear
+    const bool want_bit = (side == 0) != is_h;  // L: G_hi, H_lo;  R: G_lo, H_hi
+    uint32_t i = ((kk / h) * 2 * h) + (kk % h) + (want_bit ? h : 0);
+    const uint32_t partner = (i & (R.m - 1)) ^ h;
+    sc v;
+    sc_load(v, (is_h ? R.b : R.a) + ((size_t)lane_id * R.stride + partner) * 8);
+    const uint32_t* w = is_h ? R.wH : R.wG;
+    if (w) {
+      sc ww;
+      sc_load(ww, w + (size_t)i * 8);
+      v = sc_montmul(v, ww);
+    }
+    const sc_recoded r = sc_recode(v.v, R.bias4);
+    const int per = COMB_WINDOWS / (int)R.wsplit;
+    const uint32_t id = (is_h ? R.h_id : R.g_id) + i;
+    acc = comb_windows<AFFINE>(R.comb + (size_t)id * COMB_ENTRIES * WORDS, r, (int)slice * per, (int)(slice + 1) * per);
+  }
+  ge4 tot = comb_block_sum(acc, pts, sm);
+  if (threadIdx.x < 4) ge4_store(parts + ((size_t)set * gridDim.x + blockIdx.x) * 32, tot);
+}
+
+// ---------------------------------------------------------------------------
+// a round's finish, one block per output set: the cross term c_side (sum of the fold kernel's partials, or
+// the caller's share of it), c * q_mul on Q's comb (one window per thread), the tree over the accumulation
+// partials, the encoding.
+// ---------------------------------------------------------------------------
+struct CombFinal {
+  const uint32_t* parts;       // [sets][nparts][32] ext
+  uint32_t nparts;
+  const uint32_t* cross;       // [ncross][16]: (c_L | c_R) partials, Montgomery-scaled by R^-1 (k_ipp_cross form); null if external
+  uint32_t ncross;
+  const uint32_t* c_ext;       // [lanes][2][8] canonical cross terms supplied by the caller (shares path); null otherwise
+  const uint32_t* q_mul;       // null or the scalar with Q = q_mul * (point of q_comb)
+  const uint32_t* q_comb;      // comb of Q's base point
+  sc_bias bias4;
+};
+template <bool Q_AFFINE>
+__global__ void __launch_bounds__(CB_THREADS) k_comb_final(CombFinal F, uint8_t* __restrict__ out_bytes /*[sets][32]*/,
+                                                           uint32_t* __restrict__ out_ext /*[sets][32] or null*/) {
+  __shared__ __align__(16) uint32_t pts[CB_THREADS][32];
+  __shared__ __align__(16) uint32_t sm[CB_THREADS / 32][32];
+  __shared__ __align__(16) uint32_t g16[G16_WORDS];
+  __shared__ uint32_t csum[CB_THREADS][8];
+  const uint32_t set = blockIdx.x, lane_id = set >> 1, side = set & 1;
+  // 1. the cross term of this side
+  sc c = sc_zero();
+  if (F.c_ext) {
+    sc_load(c, F.c_ext + ((size_t)lane_id * 2 + side) * 8);
+    if (F.q_mul) {
+      sc q;
+      sc_load(q, F.q_mul);
+      c = sc_montmul(c, sc_to_mont(q));
+    }
+  } else {
+    for (uint32_t i = threadIdx.x; i < F.ncross; i += CB_THREADS) {
+      sc x;
+      sc_load(x, F.cross + (size_t)i * 16 + 8 * side);
+      c = sc_add(c, x);
+    }
+#pragma unroll
+    for (int w = 0; w < 8; w++) csum[threadIdx.x][w] = c.v[w];
+    __syncthreads();
+    for (int half = CB_THREADS / 2; half >= 1; half >>= 1) {
+      if ((int)threadIdx.x < half) {
+        sc x, y;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+          x.v[w] = csum[threadIdx.x][w];
+          y.v[w] = csum[threadIdx.x + half][w];
+        }
+        x = sc_add(x, y);
+#pragma unroll
+        for (int w = 0; w < 8; w++) csum[threadIdx.x][w] = x.v[w];
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int w = 0; w < 8; w++) c.v[w] = csum[0][w];
+    sc f = sc_const(BPG_K(K_RR));  // the partial products carry R^-1
+    if (F.q_mul) {
+      sc q;
+      sc_load(q, F.q_mul);
+      f = sc_montmul(sc_to_mont(q), f);
+    }
+    c = sc_montmul(c, f);
+  }
+  // 2. c * Q: thread j < 64 contributes window j; every thread also folds in its share of the partial sums
+  constexpr int QW = Q_AFFINE ? COMB_AFFINE_WORDS : COMB_CACHED_WORDS;
+  (void)QW;
+  ge_ext acc = ge_identity();
+  if (threadIdx.x < COMB_WINDOWS) {
+    const sc_recoded r = sc_recode(c.v, F.bias4);
+    acc = comb_windows<Q_AFFINE>(F.q_comb, r, (int)threadIdx.x, (int)threadIdx.x + 1);
+  }
+  for (uint32_t i = threadIdx.x; i < F.nparts; i += CB_THREADS) {
+    ge_ext o;
+    ge_load_ext(o, F.parts + ((size_t)set * F.nparts + i) * 32);
+    acc = ge_add(acc, o);
+  }
+  ge4 tot4 = comb_block_sum(acc, pts, sm);
+  // 3. encode on warp 0 (whole-warp sixteen-lane form)
+  if (threadIdx.x < 4) ge4_store(pts[0], tot4);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    ge_ext tot;
+    ge_load_ext(tot, pts[0]);
+    if (out_ext && threadIdx.x == 0) ge_store_ext(out_ext + (size_t)set * 32, tot);
+    grp16 g;
+    g.sm = g16;
+    g.k = threadIdx.x & 15u;
+    g.half = (threadIdx.x >> 4) & 1u;
+    g.par = 0;
+    fe s = ge_encode16<true>(g, tot);
+    if (threadIdx.x < 16) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) w = (g.k >> 1) == (uint32_t)i ? s.v[i] : w;
+      w = (g.k & 1u) ? (w >> 16) : w;
+      out_bytes[(size_t)set * 32 + 2 * g.k] = (uint8_t)w;
+      out_bytes[(size_t)set * 32 + 2 * g.k + 1] = (uint8_t)(w >> 8);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fold_witness for a, b (inner_product_proof.rs:224-225, 239-240) fused with the NEXT round's cross terms
+// (:156-157): thread j < h' folds the four entries j, j + h' of both vectors (h' = half of the folded length)
+// and adds its two products to the block's partial sums; the weights pick up u^(+-1) as in k_ipp_fold.
+// grid.y = lane; cross terms only where `partials` is given (shares: they come from the fabric).
+// ---------------------------------------------------------------------------
+struct IppPair {
+  uint32_t v[16];  // u | u^-1, canonical words
+};
+constexpr int IFC_THREADS = 256;
+__global__ void __launch_bounds__(IFC_THREADS) k_ipp_fold_cross(uint32_t* __restrict__ a, uint32_t* __restrict__ b,
+                                                                uint32_t* __restrict__ wG, uint32_t* __restrict__ wH,
+                                                                uint32_t n /*weights*/, uint32_t m /*length before the fold*/,
+                                                                uint32_t stride, IppPair up,
+                                                                uint32_t* __restrict__ partials /*[gridDim.x][16] or null*/) {
+  __shared__ uint32_t sm[IFC_THREADS / 2][16];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane_id = blockIdx.y;
+  a += (size_t)lane_id * stride * 8;
+  b += (size_t)lane_id * stride * 8;
+  sc u, ui;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    u.v[w] = up.v[w];
+    ui.v[w] = up.v[8 + w];
+  }
+  u = sc_to_mont(u);
+  ui = sc_to_mont(ui);
+  const uint32_t mn = m >> 1, hn = mn >> 1;  // folded length and its half
+  if (lane_id == 0 && i < n && wG) {
+    const bool hi = (i & mn) != 0;
+    sc g, hh;
+    sc_load(g, wG + (size_t)i * 8);
+    sc_load(hh, wH + (size_t)i * 8);
+    sc_store(wG + (size_t)i * 8, sc_montmul(g, hi ? u : ui));
+    sc_store(wH + (size_t)i * 8, sc_montmul(hh, hi ? ui : u));
+  }
+  sc cl = sc_zero(), cr = sc_zero();
+  const uint32_t cnt = hn ? hn : 1;  // folded length 1: a single entry, no cross terms
+  if (i < cnt) {
+    sc x0, x1, y0, y1;
+    sc_load(x0, a + (size_t)i * 8);
+    sc_load(x1, a + (size_t)(i + mn) * 8);
+    sc_load(y0, b + (size_t)i * 8);
+    sc_load(y1, b + (size_t)(i + mn) * 8);
+    sc alo = sc_add(sc_montmul(x0, u), sc_montmul(x1, ui));
+    sc blo = sc_add(sc_montmul(y0, ui), sc_montmul(y1, u));
+    if (hn) {
+      sc x2, x3, y2, y3;
+      sc_load(x2, a + (size_t)(i + hn) * 8);
+      sc_load(x3, a + (size_t)(i + hn + mn) * 8);
+      sc_load(y2, b + (size_t)(i + hn) * 8);
+      sc_load(y3, b + (size_t)(i + hn + mn) * 8);
+      sc ahi = sc_add(sc_montmul(x2, u), sc_montmul(x3, ui));
+      sc bhi = sc_add(sc_montmul(y2, ui), sc_montmul(y3, u));
+      sc_store(a + (size_t)(i + hn) * 8, ahi);
+      sc_store(b + (size_t)(i + hn) * 8, bhi);
+      cl = sc_montmul(alo, bhi);
+      cr = sc_montmul(ahi, blo);
+    }
+    sc_store(a + (size_t)i * 8, alo);
+    sc_store(b + (size_t)i * 8, blo);
+  }
+  if (!partials) return;
+  // block sums (two accumulators at once)
+  for (int half = IFC_THREADS / 2; half >= 1; half >>= 1) {
+    if (threadIdx.x >= (uint32_t)half && threadIdx.x < (uint32_t)(2 * half)) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        sm[threadIdx.x - half][k] = cl.v[k];
+        sm[threadIdx.x - half][8 + k] = cr.v[k];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < (uint32_t)half) {
+      sc ox, oy;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        ox.v[k] = sm[threadIdx.x][k];
+        oy.v[k] = sm[threadIdx.x][8 + k];
+      }
+      cl = sc_add(cl, ox);
+      cr = sc_add(cr, oy);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && lane_id == 0) {
+    sc_store(partials + (size_t)blockIdx.x * 16, cl);
+    sc_store(partials + (size_t)blockIdx.x * 16 + 8, cr);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// folded generators, once: out[g] for g < 2 m0 is G'_p (g = p) or H'_p (g = m0 + p),
+//   G'_p = sum_{t < n/m0} wG(t m0 + p) * G_{t m0 + p}            (weights in Montgomery form)
+// and out[2 m0] = q_mul * (point q_id) when q_mul is given.  One WARP per output; its lanes share the
+// (term, window-slice) units, then a tree over the warp.
+// ---------------------------------------------------------------------------
+struct CombMat {
+  const uint32_t* comb;  // generator combs (affine)
+  uint32_t g_id, h_id, q_id;
+  const uint32_t *wG, *wH;
+  const uint32_t* q_mul;  // canonical scalar or null
+  uint32_t n, m0;
+  sc_bias bias4;
+};
+__global__ void __launch_bounds__(CB_THREADS) k_comb_materialize(CombMat M, uint32_t* __restrict__ out /*[2 m0 + 1][32] ext*/) {
+  __shared__ __align__(16) uint32_t pts[CB_THREADS][32];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ngroups = 2 * M.m0 + (M.q_mul ? 1u : 0u);
+  uint32_t g = blockIdx.x * (CB_THREADS / 32) + warp;
+  const bool live = g < ngroups;
+  if (!live) g = 0;  // idle warps shadow group 0 (the quad arithmetic shuffles warp-wide) and do not store
+  const bool is_q = g == 2 * M.m0;
+  const bool is_h = !is_q && g >= M.m0;
+  const uint32_t p = is_q ? 0 : (is_h ? g - M.m0 : g);
+  const uint32_t gterms = is_q ? 1u : M.n / M.m0;
+  const uint32_t ws = gterms >= 32 ? 1u : 32u / gterms;  // window slices per term: gterms * ws >= 32 units
+  const int per = COMB_WINDOWS / (int)ws;
+  ge_ext acc = ge_identity();
+  for (uint32_t unit = lane; unit < gterms * ws; unit += 32) {
+    const uint32_t t = unit / ws, slice = unit % ws;
+    sc v;
+    uint32_t id;
+    if (is_q) {
+      sc_load(v, M.q_mul);
+      id = M.q_id;
+    } else {
+      const uint32_t i = t * M.m0 + p;
+      sc_load(v, (is_h ? M.wH : M.wG) + (size_t)i * 8);
+      v = sc_from_mont(v);
+      id = (is_h ? M.h_id : M.g_id) + i;
+    }
+    const sc_recoded r = sc_recode(v.v, M.bias4);
+    ge_ext part = comb_windows<true>(M.comb + (size_t)id * COMB_ENTRIES * COMB_AFFINE_WORDS, r, (int)slice * per, (int)(slice + 1) * per);
+    acc = ge_add(acc, part);
+  }
+  ge_store_ext(pts[threadIdx.x], acc);
+  __syncwarp();
+  // quad q of the warp sums lanes 4q..4q+3, then a shuffle tree over the eight quads
+  const uint32_t quad = lane >> 2;
+  ge4 tq = ge4_load(pts[warp * 32 + 4 * quad]);
+#pragma unroll
+  for (int k = 1; k < 4; k++) tq = ge4_add(tq, ge4_load(pts[warp * 32 + 4 * quad + k]));
+#pragma unroll
+  for (int off = 16; off >= 4; off >>= 1) {
+    ge4 o;
+#pragma unroll
+    for (int w = 0; w < 8; w++) o.c.v[w] = __shfl_down_sync(BPG_FULL_MASK, tq.c.v[w], off);
+    tq = ge4_add(tq, o);
+  }
+  if (live && lane < 4) ge4_store(out + (size_t)g * 32, tq);
+}
+
+// ---------------------------------------------------------------------------
+// combs of the folded generators (per proof): the doubling chain 16^j P on a quad per point, then the eight
+// multiples of every (point, window) in the projective "cached" layout -- no inversion anywhere.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(CB_THREADS) k_comb_chain(const uint32_t* __restrict__ pts_in /*[npts][32] ext*/, uint32_t npts,
+                                                           uint32_t* __restrict__ chain /*[npts][64][32] ext*/) {
+  uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const bool live = q < npts;
+  if (!live) q = npts - 1;
+  ge4 cur = ge4_load(pts_in + (size_t)q * 32);
+  uint32_t* dst = chain + (size_t)q * COMB_WINDOWS * 32;
+  if (live) ge4_store(dst, cur);
+#pragma unroll 1
+  for (int j = 1; j < COMB_WINDOWS; j++) {
+    cur = ge4_dbl(cur);
+    cur = ge4_dbl(cur);
+    cur = ge4_dbl(cur);
+    cur = ge4_dbl(cur);
+    if (live) ge4_store(dst + (size_t)j * 32, cur);
+  }
+}
+__global__ void __launch_bounds__(CB_THREADS) k_comb_multiples(const uint32_t* __restrict__ chain, uint32_t nwin /*npts * 64*/,
+                                                               uint32_t* __restrict__ comb /*[npts][64][8][32] cached*/) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nwin) return;
+  ge_ext base;
+  ge_load_ext(base, chain + (size_t)t * 32);
+  const fe ymx = fe_sub(base.Y, base.X), ypx = fe_add_nc(base.Y, base.X), z2 = fe_add_nc(base.Z, base.Z);
+  const fe t2d = fe_mul(base.T, fe_const(BPG_K(K_D2)));
+  uint32_t* out = comb + (size_t)t * 8 * COMB_CACHED_WORDS;
+  fe_store(out, ymx);
+  fe_store(out + 8, ypx);
+  fe_store(out + 16, z2);
+  fe_store(out + 24, t2d);
+  ge_ext m = base;
+#pragma unroll 1
+  for (int d = 1; d < 8; d++) {
+    m = ge_add_cached(m, ymx, ypx, z2, t2d);
+    uint32_t* o = out + (size_t)d * COMB_CACHED_WORDS;
+    fe_store(o, fe_sub(m.Y, m.X));
+    fe_store(o + 8, fe_add_nc(m.Y, m.X));
+    fe_store(o + 16, fe_add_nc(m.Z, m.Z));
+    fe_store(o + 24, fe_mul(m.T, fe_const(BPG_K(K_D2))));
+  }
+}
+
+}  // namespace bpg

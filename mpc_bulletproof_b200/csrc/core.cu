@@ -368,6 +368,10 @@ extern "C" void bpg_table_free(bpg_table* t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
   dev_free(t->ctx, t->niels);  // stream-ordered: work already enqueued on the table finishes first
+  if (t->comb) {
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->comb);
+  }
   delete t;
 }
 extern "C" int bpg_dev_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t offset, size_t n,

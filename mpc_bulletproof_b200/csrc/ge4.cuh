@@ -117,4 +117,40 @@ __device__ __forceinline__ ge_ext ge4_gather(const ge4& p) {
   return r;
 }
 
+// sum of one point per quad over the whole block -> quad 0 of warp 0.
+// sm: [warps][32] words.  Every thread of the block must call it.
+__device__ __forceinline__ ge4 block_sum_quads(ge4 p, uint32_t (*sm)[32]) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int off = 16; off >= 4; off >>= 1) {
+    ge4 o;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o.c.v[i] = __shfl_down_sync(BPG_FULL_MASK, p.c.v[i], off);
+    p = ge4_add(p, o);
+  }
+  if (nw == 1) return p;
+  if (lane < 4) ge4_store(sm[wid], p);
+  __syncthreads();
+  if (wid == 0) {
+    int quad = lane >> 2;
+    ge4 t = ge4_identity();
+    // up to 32 warps: each quad folds warps quad, quad+8, ...
+    for (int k = 0; k < (nw + 7) / 8; k++) {
+      int w = quad + 8 * k;
+      ge4 o = w < nw ? ge4_load(sm[w]) : ge4_identity();
+      t = ge4_add(t, o);
+    }
+#pragma unroll
+    for (int off = 16; off >= 4; off >>= 1) {
+      ge4 o;
+#pragma unroll
+      for (int i = 0; i < 8; i++) o.c.v[i] = __shfl_down_sync(BPG_FULL_MASK, t.c.v[i], off);
+      t = ge4_add(t, o);
+    }
+    p = t;
+  }
+  __syncthreads();
+  return p;
+}
+
 }  // namespace bpg

@@ -155,6 +155,16 @@ extern "C" int bpg_gens_new(bpg_ctx* ctx, const uint8_t* G, const uint8_t* H, si
   memcpy(g->Bb.data(), B_blinding, 32);
   int rc = bpg_table_upload(ctx, all.data(), 2 * capacity + 2, &g->table);
   if (!rc) rc = bpg_table_set_windows(ctx, g->table, 0);
+  if (!rc) {
+    // combs for the inner-product rounds (48 KB per generator) when they fit the budget; without them the
+    // rounds keep the bucket method throughout
+    const char* e = getenv("BPG_COMB_MAX_GB");
+    double max_gb = e ? atof(e) : 16.0;
+    if ((double)(2 * capacity + 2) * 49152.0 <= max_gb * 1e9) {
+      int rc2 = bpg_table_build_comb(ctx, g->table);
+      if (rc2 && rc2 != BPG_ERR_NOMEM) rc = rc2;
+    }
+  }
   uint8_t bases[64];
   memcpy(bases, B, 32);
   memcpy(bases + 32, B_blinding, 32);

@@ -61,6 +61,7 @@ struct bpg_table {
   size_t n;
   int win_c = 0;    // 0: plain; otherwise the window width the multiples 2^(c w) P_i were built for
   int win_W = 1;
+  uint32_t* comb = nullptr;  // optional: 64 x 8 affine-Niels multiples (d+1) 16^j P_i per point (bpg_table_build_comb)
 };
 
 #define CK(call)                                  \

@@ -1,6 +1,7 @@
 // libbpgpu: inner-product argument, device-resident state, one MSM per round.
 #include "internal.cuh"
 #include "ipp_kernels.cuh"
+#include "comb_kernels.cuh"
 
 using namespace bpg;
 
@@ -23,7 +24,27 @@ struct bpg_ipp {
   bool lr_done;
   int lanes;        // (a, b) pairs folding together: 1, or a party's share + MAC vectors (r1cs_mpc)
   uint32_t* c_ext;  // [lanes][2] caller-supplied cross terms of the current round (shares path)
+  // comb rounds (comb_kernels.cuh)
+  int mode;               // 0: bucket MSM over the windowed table (no-fold form); 1: comb rounds
+  size_t m0;              // mode 0: materialise the folded generators when the vectors have shrunk to m0 (0 = never)
+  size_t n_eff;           // generators per vector in the current representation (n, or m0 once materialised)
+  bool comb_affine;       // comb rounds read the table's generator combs (true) or the proof's own combs of folded generators
+  const uint32_t* comb;   // the combs the rounds read
+  uint32_t cg_id, ch_id;  // comb index of G_0 / H_0
+  const uint32_t* cq_comb;  // comb of Q's base point (affine)
+  uint32_t* mat_buf;      // folded generators | doubling chains | their combs (per proof)
+  uint32_t* parts;        // partial sums of a comb round's blocks
+  size_t parts_cap;
+  bool cross_ready;       // the fold kernel already left this round's cross-term partials
+  uint32_t ncross;
 };
+
+// BPG_IPP_DIRECT_MAX: vectors up to this length run every round on the generators' own combs;
+// BPG_IPP_M0: longer ones switch to combs of the folded generators once they have shrunk to this length
+static size_t env_size(const char* name, size_t dflt) {
+  const char* e = getenv(name);
+  return e ? (size_t)strtoull(e, nullptr, 10) : dflt;
+}
 
 
 // d_* pointers are device pointers; factors may be null (all ones).
@@ -139,7 +160,131 @@ int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_tabl
     delete st;
     return rc;
   }
+  // Round strategy.  A table that carries combs (bpg_table_build_comb; bpg_gens_new builds them) lets short
+  // vectors run every round on the combs, and long ones switch to combs of the folded generators.
+  st->n_eff = n;
+  if (st->tab->comb && !st->own_tab && n > 1) {
+    const size_t direct_max = std::min<size_t>(env_size("BPG_IPP_DIRECT_MAX", 8192), 65536), m0 = env_size("BPG_IPP_M0", 2048);
+    st->cq_comb = st->q_sep ? st->q_comb : st->tab->comb + (size_t)q_id * COMB_ENTRIES * COMB_AFFINE_WORDS;
+    if (n <= direct_max || n <= m0) {
+      st->mode = 1;
+      st->comb_affine = true;
+      st->comb = st->tab->comb;
+      st->cg_id = (uint32_t)(shared ? g_base : g_off);
+      st->ch_id = (uint32_t)(shared ? h_base : h_off);
+    } else if (m0 >= 2 && (m0 & (m0 - 1)) == 0) {
+      st->m0 = m0;
+      st->cg_id = (uint32_t)(shared ? g_base : g_off);
+      st->ch_id = (uint32_t)(shared ? h_base : h_off);
+    }
+  }
   *out = st;
+  return BPG_OK;
+}
+
+// comb rounds ----------------------------------------------------------------------------------
+static int ipp_ensure_parts(bpg_ipp* st, size_t bytes) {
+  if (bytes <= st->parts_cap) return BPG_OK;
+  bpg_ctx* ctx = st->ctx;
+  if (st->parts) dev_free(ctx, st->parts);
+  st->parts = nullptr;
+  st->parts_cap = 0;
+  if (dev_alloc(ctx, &st->parts, bytes) != cudaSuccess) return BPG_ERR_NOMEM;
+  st->parts_cap = bytes;
+  return BPG_OK;
+}
+
+// The vectors have shrunk to m0: form the folded generators once (k_comb_materialize over the generator combs),
+// give them combs of their own, and restart the weights at one.  From here on a round touches 2 m0 points.
+static int ipp_materialize(bpg_ipp* st) {
+  bpg_ctx* ctx = st->ctx;
+  cudaStream_t s = ctx->stream;
+  const size_t m0 = st->m0, npts = 2 * m0;
+  const size_t w_pts = npts * 32, w_chain = npts * COMB_WINDOWS * 32, w_comb = npts * (size_t)COMB_ENTRIES * COMB_CACHED_WORDS;
+  if (dev_alloc(ctx, &st->mat_buf, (w_pts + w_chain + w_comb) * 4) != cudaSuccess) return BPG_ERR_NOMEM;
+  uint32_t *folded = st->mat_buf, *chain = folded + w_pts, *comb = chain + w_chain;
+  prof_mark(ctx, BPG_PROF_COMBINE);
+  CombMat M;
+  M.comb = st->tab->comb;
+  M.g_id = st->cg_id;
+  M.h_id = st->ch_id;
+  M.q_id = 0;
+  M.wG = st->wG;
+  M.wH = st->wH;
+  M.q_mul = nullptr;
+  M.n = (uint32_t)st->n;
+  M.m0 = (uint32_t)m0;
+  M.bias4 = bias_for(4);
+  k_comb_materialize<<<(unsigned)((npts + CB_THREADS / 32 - 1) / (CB_THREADS / 32)), CB_THREADS, 0, s>>>(M, folded);
+  LAUNCH_CHECK();
+  k_comb_chain<<<(unsigned)((npts * 4 + CB_THREADS - 1) / CB_THREADS), CB_THREADS, 0, s>>>(folded, (uint32_t)npts, chain);
+  LAUNCH_CHECK();
+  k_comb_multiples<<<(unsigned)((npts * COMB_WINDOWS + CB_THREADS - 1) / CB_THREADS), CB_THREADS, 0, s>>>(
+      chain, (uint32_t)(npts * COMB_WINDOWS), comb);
+  LAUNCH_CHECK();
+  k_ipp_init_weights<<<(unsigned)((m0 + 255) / 256), 256, 0, s>>>(nullptr, nullptr, (uint32_t)m0, st->wG, st->wH);
+  LAUNCH_CHECK();
+  prof_mark(ctx, -1);
+  st->mode = 1;
+  st->comb_affine = false;
+  st->comb = comb;
+  st->cg_id = 0;
+  st->ch_id = (uint32_t)m0;
+  st->n_eff = m0;
+  st->cross_ready = false;
+  return BPG_OK;
+}
+
+// one comb round: accumulation + finish; the encodings of the 2 x lanes sums land in st->out_bytes
+static int ipp_comb_round(bpg_ipp* st, bool external_cross) {
+  bpg_ctx* ctx = st->ctx;
+  cudaStream_t s = ctx->stream;
+  const size_t n = st->n_eff, m = st->m, h = m / 2;
+  const unsigned sets = 2u * (unsigned)st->lanes;
+  prof_mark(ctx, BPG_PROF_OTHER);
+  if (!external_cross && !st->cross_ready) {
+    unsigned gcross = (unsigned)std::min<size_t>(256, (h + IPP_THREADS - 1) / IPP_THREADS);
+    k_ipp_cross<<<gcross, IPP_THREADS, 0, s>>>(st->a, st->b, (uint32_t)h, st->partials);
+    LAUNCH_CHECK();
+    st->ncross = gcross;
+  }
+  // threads per term: enough (term, window-slice) units to fill the machine, at most one window per thread
+  uint32_t wsplit = 1;
+  while (wsplit < COMB_WINDOWS && n * wsplit < (size_t)ctx->sm_count * 256) wsplit <<= 1;
+  const unsigned bx = (unsigned)((n * wsplit + CB_THREADS - 1) / CB_THREADS);
+  int rc = ipp_ensure_parts(st, (size_t)sets * bx * 128);
+  if (rc) return rc;
+  CombRound R;
+  R.comb = st->comb;
+  R.g_id = st->cg_id;
+  R.h_id = st->ch_id;
+  R.a = st->a;
+  R.b = st->b;
+  R.wG = st->wG;
+  R.wH = st->wH;
+  R.stride = (uint32_t)st->n;
+  R.n = (uint32_t)n;
+  R.m = (uint32_t)m;
+  R.wsplit = wsplit;
+  R.bias4 = bias_for(4);
+  prof_mark(ctx, BPG_PROF_ACCUM);
+  if (st->comb_affine) k_comb_round<true><<<dim3(bx, sets), CB_THREADS, 0, s>>>(R, st->parts);
+  else k_comb_round<false><<<dim3(bx, sets), CB_THREADS, 0, s>>>(R, st->parts);
+  LAUNCH_CHECK();
+  CombFinal F;
+  F.parts = st->parts;
+  F.nparts = bx;
+  F.cross = external_cross ? nullptr : st->partials;
+  F.ncross = st->ncross;
+  F.c_ext = external_cross ? st->c_ext : nullptr;
+  F.q_mul = st->has_qmul ? st->q_mul : nullptr;
+  F.q_comb = st->cq_comb;
+  F.bias4 = bias_for(4);
+  prof_mark(ctx, BPG_PROF_ENCODE);
+  k_comb_final<true><<<sets, CB_THREADS, 0, s>>>(F, st->out_bytes, nullptr);
+  LAUNCH_CHECK();
+  prof_mark(ctx, -1);
+  st->cross_ready = false;
   return BPG_OK;
 }
 
@@ -204,6 +349,20 @@ extern "C" int bpg_ipp_round_LR(bpg_ipp* st, uint8_t L[32], uint8_t R[32]) {
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   size_t n = st->n, m = st->m, h = m / 2;
+  if (st->mode == 0 && st->m0 && m <= st->m0) {
+    int rc = ipp_materialize(st);
+    if (rc) return rc;
+  }
+  if (st->mode == 1) {
+    int rc = ipp_comb_round(st, false);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_pinned, st->out_bytes, 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(L, ctx->h_pinned, 32);
+    memcpy(R, ctx->h_pinned + 32, 32);
+    st->lr_done = true;
+    return BPG_OK;
+  }
   unsigned gcross = (unsigned)std::min<size_t>(256, (h + IPP_THREADS - 1) / IPP_THREADS);
   prof_mark(ctx, BPG_PROF_OTHER);
   k_ipp_cross<<<gcross, IPP_THREADS, 0, s>>>(st->a, st->b, (uint32_t)h, st->partials);
@@ -247,9 +406,24 @@ extern "C" int bpg_ipp_round_fold(bpg_ipp* st, const uint8_t u[32], const uint8_
   memcpy(up.v, u, 32);
   memcpy(up.v + 8, u_inv, 32);
   prof_mark(ctx, BPG_PROF_OTHER);
-  k_ipp_fold<<<dim3((unsigned)((st->n + 255) / 256), (unsigned)st->lanes), 256, 0, s>>>(st->a, st->b, st->wG, st->wH,
-                                                                                       (uint32_t)st->n, (uint32_t)st->m, up);
-  LAUNCH_CHECK();
+  if (st->mode == 1) {
+    // fold + the next round's cross-term partials in one kernel (the shares path gets them from the caller)
+    IppPair ip;
+    memcpy(ip.v, up.v, sizeof ip.v);
+    const size_t cover = std::max<size_t>(st->n_eff, 1);
+    const unsigned gx = (unsigned)((cover + IFC_THREADS - 1) / IFC_THREADS);
+    const bool want_cross = st->lanes == 1 && st->m >= 4;
+    k_ipp_fold_cross<<<dim3(gx, (unsigned)st->lanes), IFC_THREADS, 0, s>>>(st->a, st->b, st->wG, st->wH, (uint32_t)st->n_eff,
+                                                                            (uint32_t)st->m, (uint32_t)st->n, ip,
+                                                                            want_cross ? st->partials : nullptr);
+    LAUNCH_CHECK();
+    st->cross_ready = want_cross;
+    st->ncross = gx;
+  } else {
+    k_ipp_fold<<<dim3((unsigned)((st->n + 255) / 256), (unsigned)st->lanes), 256, 0, s>>>(st->a, st->b, st->wG, st->wH,
+                                                                                         (uint32_t)st->n, (uint32_t)st->m, up);
+    LAUNCH_CHECK();
+  }
   prof_mark(ctx, -1);
   st->m /= 2;
   st->lr_done = false;
@@ -317,18 +491,28 @@ extern "C" int bpg_ipp_round_LR_shares(bpg_ipp* st, const uint8_t* c_L, const ui
     memcpy(hp + 64 * l + 32, c_R + 32 * l, 32);
   }
   CK(cudaMemcpyAsync(st->c_ext, hp, 64 * (size_t)NL, cudaMemcpyHostToDevice, s));
-  prof_mark(ctx, BPG_PROF_OTHER);
-  k_ipp_round_scalars<<<dim3((unsigned)((n + 255) / 256), (unsigned)NL), 256, 0, s>>>(st->a, st->b, st->wG, st->wH, (uint32_t)n,
-                                                                                     (uint32_t)m, st->scalars, st->set_ids);
-  LAUNCH_CHECK();
-  k_ipp_q_terms_ext<<<1, 32, 0, s>>>(st->c_ext, st->has_qmul ? st->q_mul : nullptr, (uint32_t)n, (uint32_t)NL, st->scalars,
-                                     st->set_ids);
-  LAUNCH_CHECK();
-  int rc = msm_enqueue(ctx, st->tab->niels, st->tab->n, st->scalars, (size_t)NL * (2 * n + 2), st->set_ids, st->point_ids,
-                       2 * NL, st->out_ext, st->tab->win_c, st->tab->n);
-  if (rc) return rc;
-  rc = bpg_dev_sum_encode(ctx, st->out_ext, 1, 2 * NL, st->out_bytes, nullptr);
-  if (rc) return rc;
+  if (st->mode == 0 && st->m0 && m <= st->m0) {
+    int rc = ipp_materialize(st);
+    if (rc) return rc;
+  }
+  int rc;
+  if (st->mode == 1) {
+    rc = ipp_comb_round(st, true);
+    if (rc) return rc;
+  } else {
+    prof_mark(ctx, BPG_PROF_OTHER);
+    k_ipp_round_scalars<<<dim3((unsigned)((n + 255) / 256), (unsigned)NL), 256, 0, s>>>(st->a, st->b, st->wG, st->wH, (uint32_t)n,
+                                                                                       (uint32_t)m, st->scalars, st->set_ids);
+    LAUNCH_CHECK();
+    k_ipp_q_terms_ext<<<1, 32, 0, s>>>(st->c_ext, st->has_qmul ? st->q_mul : nullptr, (uint32_t)n, (uint32_t)NL, st->scalars,
+                                       st->set_ids);
+    LAUNCH_CHECK();
+    rc = msm_enqueue(ctx, st->tab->niels, st->tab->n, st->scalars, (size_t)NL * (2 * n + 2), st->set_ids, st->point_ids,
+                     2 * NL, st->out_ext, st->tab->win_c, st->tab->n);
+    if (rc) return rc;
+    rc = bpg_dev_sum_encode(ctx, st->out_ext, 1, 2 * NL, st->out_bytes, nullptr);
+    if (rc) return rc;
+  }
   CK(cudaMemcpyAsync(ctx->h_pinned, st->out_bytes, 64 * (size_t)NL, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   for (int l = 0; l < NL; l++) {
@@ -363,6 +547,39 @@ extern "C" void bpg_ipp_free(bpg_ipp* st) {
   cudaSetDevice(st->ctx->device);
   if (st->q_sep) cudaStreamSynchronize(st->ctx->aux_stream);
   if (st->own_tab) bpg_table_free(st->own_tab);
+  dev_free(st->ctx, st->mat_buf);
+  dev_free(st->ctx, st->parts);
   dev_free(st->ctx, st->buf);
   delete st;
 }
+
+// ---------------------------------------------------------------------------
+// combs of a resident table (one-time, like bpg_table_set_windows): 64 x 8 affine-Niels multiples per point
+// ---------------------------------------------------------------------------
+extern "C" int bpg_table_build_comb(bpg_ctx* ctx, bpg_table* t) {
+  if (!ctx || !t) return BPG_ERR_ARG;
+  if (t->comb || t->n == 0) return BPG_OK;
+  CK(cudaSetDevice(ctx->device));
+  uint32_t* comb = nullptr;
+  cudaError_t e = cudaMalloc(&comb, t->n * (size_t)COMB_ENTRIES * COMB_AFFINE_WORDS * 4);
+  if (e != cudaSuccess) {
+    ctx->last_cuda = (int)e;
+    cudaGetLastError();
+    return BPG_ERR_NOMEM;
+  }
+  const size_t CH = 1 << 15;
+  for (size_t first = 0; first < t->n; first += CH) {
+    size_t cnt = std::min(CH, t->n - first);
+    k_table_comb_build<<<(unsigned)cnt, COMB_WINDOWS, 0, ctx->stream>>>(t->niels, (uint32_t)first, comb);
+    ctx->launches++;
+  }
+  cudaError_t se = cudaStreamSynchronize(ctx->stream);
+  if (se != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+    ctx->last_cuda = (int)se;
+    cudaFree(comb);
+    return BPG_ERR_CUDA;
+  }
+  t->comb = comb;
+  return BPG_OK;
+}
+extern "C" int bpg_table_has_comb(const bpg_table* t) { return t && t->comb ? 1 : 0; }

@@ -18,41 +18,6 @@ __device__ __forceinline__ void ge_store_cached(uint32_t* p, const ge_ext& a) {
   fe_store(p + 24, fe_mul(a.T, fe_const(BPG_K(K_D2))));
 }
 
-// sum of one point per quad over the whole block -> quad 0 of warp 0.
-// sm: [warps][32] words.  Every thread of the block must call it.
-__device__ __forceinline__ ge4 block_sum_quads(ge4 p, uint32_t (*sm)[32]) {
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-  for (int off = 16; off >= 4; off >>= 1) {
-    ge4 o;
-#pragma unroll
-    for (int i = 0; i < 8; i++) o.c.v[i] = __shfl_down_sync(BPG_FULL_MASK, p.c.v[i], off);
-    p = ge4_add(p, o);
-  }
-  if (nw == 1) return p;
-  if (lane < 4) ge4_store(sm[wid], p);
-  __syncthreads();
-  if (wid == 0) {
-    int quad = lane >> 2;
-    ge4 t = ge4_identity();
-    // up to 32 warps: each quad folds warps quad, quad+8, ...
-    for (int k = 0; k < (nw + 7) / 8; k++) {
-      int w = quad + 8 * k;
-      ge4 o = w < nw ? ge4_load(sm[w]) : ge4_identity();
-      t = ge4_add(t, o);
-    }
-#pragma unroll
-    for (int off = 16; off >= 4; off >>= 1) {
-      ge4 o;
-#pragma unroll
-      for (int i = 0; i < 8; i++) o.c.v[i] = __shfl_down_sync(BPG_FULL_MASK, t.c.v[i], off);
-      t = ge4_add(t, o);
-    }
-    p = t;
-  }
-  __syncthreads();
-  return p;
-}
 
 // Software pipeline: the Niels entry of step k+1 (and the entry word of step k+2) are loaded
 // before step k multiplies.  Measured at 2^20 points (13.6 M additions): 0.899 ms, against 0.947 ms

@@ -97,21 +97,6 @@ __global__ void __launch_bounds__(RT_THREADS) k_reduce_leaf(const uint32_t* __re
 // (8 + 9 multiplications per bucket instead of five quad levels) and writes its pair; the
 // binary tree over the pairs is k_reduce_pairs.
 constexpr int RL_THREADS = 128;
-// p + q with q in the cached layout (Y-X, Y+X, 2Z, 2dT): 8 multiplications
-__device__ __forceinline__ ge_ext ge_add_cached(const ge_ext& p, const fe& ymx, const fe& ypx, const fe& z2,
-                                                const fe& t2d) {
-  fe A = fe_mul(fe_sub(p.Y, p.X), ymx);
-  fe B = fe_mul(fe_add_nc(p.Y, p.X), ypx);
-  fe C = fe_mul(p.T, t2d);
-  fe D = fe_mul(p.Z, z2);
-  fe E = fe_sub(B, A), H = fe_add_nc(B, A), F = fe_sub(D, C), G = fe_add(D, C);
-  ge_ext r;
-  r.X = fe_mul(E, F);
-  r.Y = fe_mul(G, H);
-  r.Z = fe_mul(F, G);
-  r.T = fe_mul(E, H);
-  return r;
-}
 template <int LC>
 __global__ void __launch_bounds__(RL_THREADS) k_reduce_leaf_thread(const uint32_t* __restrict__ in /*[narr][n] cached*/,
                                                                    uint32_t n, uint32_t chunks /*per array*/,
