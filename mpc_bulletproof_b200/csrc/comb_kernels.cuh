@@ -46,17 +46,57 @@ __device__ __forceinline__ ge_ext comb_add(const ge_ext& acc, const uint32_t* __
     return ge_add_cached(acc, a, b, z2, t);
   }
 }
-// sum over windows [j0, j1) of digit_j * 16^j * P from P's comb
+// sum over windows [j0, j1) of digit_j * 16^j * P from P's comb.  Software-pipelined: the entry of window j + 1 is
+// loaded before the addition of window j multiplies; a zero digit adds the neutral entry (the formulas are
+// complete), so the loop has no data-dependent branch.
+template <bool AFFINE>
+struct comb_entry {
+  fe c[AFFINE ? 3 : 4];
+  bool neg;
+};
+template <bool AFFINE>
+__device__ __forceinline__ comb_entry<AFFINE> comb_fetch(const uint32_t* __restrict__ comb_of_point, const sc_recoded& r, int j) {
+  constexpr int WORDS = AFFINE ? COMB_AFFINE_WORDS : COMB_CACHED_WORDS;
+  const int d = sc_digit(r, j, 4);
+  const int mag = d < 0 ? -d : d;
+  const uint32_t* e = comb_of_point + (size_t)(j * 8 + (mag ? mag - 1 : 0)) * WORDS;
+  comb_entry<AFFINE> o;
+  o.neg = d < 0;
+#pragma unroll
+  for (int k = 0; k < (AFFINE ? 3 : 4); k++) fe_load(o.c[k], e + 8 * k);
+  if (mag == 0) {  // neutral element: affine (y+x, y-x, 2dxy) = (1, 1, 0); cached (Y-X, Y+X, 2Z, 2dT) = (1, 1, 2, 0)
+    o.c[0] = fe_one();
+    o.c[1] = fe_one();
+    o.c[2] = fe_zero();
+    if (!AFFINE) {
+      o.c[2].v[0] = 2;
+      o.c[3] = fe_zero();
+    }
+  }
+  return o;
+}
+template <bool AFFINE>
+__device__ __forceinline__ ge_ext comb_apply(const ge_ext& acc, const comb_entry<AFFINE>& q) {
+  if (AFFINE) {
+    ge_niels n;
+    n.ypx = q.c[0];
+    n.ymx = q.c[1];
+    n.t2d = q.c[2];
+    return ge_madd(acc, n, q.neg);
+  } else {
+    fe nt = fe_neg(q.c[3]);
+    fe a = fe_sel(q.neg, q.c[1], q.c[0]), b = fe_sel(q.neg, q.c[0], q.c[1]), t = fe_sel(q.neg, nt, q.c[3]);
+    return ge_add_cached(acc, a, b, q.c[2], t);
+  }
+}
 template <bool AFFINE>
 __device__ __forceinline__ ge_ext comb_windows(const uint32_t* __restrict__ comb_of_point, const sc_recoded& r, int j0, int j1) {
-  constexpr int WORDS = AFFINE ? COMB_AFFINE_WORDS : COMB_CACHED_WORDS;
   ge_ext acc = ge_identity();
+  comb_entry<AFFINE> cur = comb_fetch<AFFINE>(comb_of_point, r, j0);
   for (int j = j0; j < j1; j++) {
-    int d = sc_digit(r, j, 4);
-    if (d != 0) {
-      int mag = d < 0 ? -d : d;
-      acc = comb_add<AFFINE>(acc, comb_of_point + (size_t)(j * 8 + mag - 1) * WORDS, d < 0);
-    }
+    comb_entry<AFFINE> nxt = comb_fetch<AFFINE>(comb_of_point, r, j + 1 < j1 ? j + 1 : j);
+    acc = comb_apply<AFFINE>(acc, cur);
+    cur = nxt;
   }
   return acc;
 }
@@ -72,44 +112,6 @@ __device__ __forceinline__ ge4 comb_block_sum(const ge_ext& mine, uint32_t (*pts
 #pragma unroll
   for (int k = 1; k < 4; k++) t = ge4_add(t, ge4_load(pts[4 * g + k]));
   return block_sum_quads(t, sm);
-}
-
-// ---------------------------------------------------------------------------
-// one-time: the comb of every point of a resident table.  Block = one point, thread j = window j:
-// 4 j doublings, the eight multiples, ONE inversion for the eight (Montgomery's trick), affine Niels out.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(COMB_WINDOWS) k_table_comb_build(const uint32_t* __restrict__ niels /*window 0 of the table*/,
-                                                                   uint32_t first, uint32_t* __restrict__ comb) {
-  const uint32_t i = first + blockIdx.x;
-  const int j = threadIdx.x;
-  ge_niels q;
-  ge_load_niels(q, niels + (size_t)i * 24);
-  ge_ext p = ge_from_niels(q, false);
-  for (int k = 0; k < 4 * j; k++) p = ge_dbl(p);
-  // forward: the eight multiples, parked projectively (X | Y | Z = 24 words) in the entries they will become,
-  // with the running product of their Z; backward: one inversion serves all eight (Montgomery's trick)
-  uint32_t* out = comb + ((size_t)i * COMB_WINDOWS + j) * 8 * COMB_AFFINE_WORDS;
-  ge_ext m = p;
-  fe zp[8];
-#pragma unroll
-  for (int d = 0; d < 8; d++) {
-    if (d) m = ge_add(m, p);
-    zp[d] = d ? fe_mul(zp[d - 1], m.Z) : m.Z;
-    fe_store(out + (size_t)d * COMB_AFFINE_WORDS, m.X);
-    fe_store(out + (size_t)d * COMB_AFFINE_WORDS + 8, m.Y);
-    fe_store(out + (size_t)d * COMB_AFFINE_WORDS + 16, m.Z);
-  }
-  fe inv = fe_invert(zp[7]);
-#pragma unroll
-  for (int d = 7; d >= 0; d--) {
-    fe X, Y, Z;
-    fe_load(X, out + (size_t)d * COMB_AFFINE_WORDS);
-    fe_load(Y, out + (size_t)d * COMB_AFFINE_WORDS + 8);
-    fe_load(Z, out + (size_t)d * COMB_AFFINE_WORDS + 16);
-    fe zi = d ? fe_mul(inv, zp[d - 1]) : inv;
-    inv = fe_mul(inv, Z);
-    ge_store_niels(out + (size_t)d * COMB_AFFINE_WORDS, ge_affine_to_niels(fe_mul(X, zi), fe_mul(Y, zi)));
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -276,7 +278,7 @@ struct IppPair {
   uint32_t v[16];  // u | u^-1, canonical words
 };
 constexpr int IFC_THREADS = 256;
-__global__ void __launch_bounds__(IFC_THREADS) k_ipp_fold_cross(uint32_t* __restrict__ a, uint32_t* __restrict__ b,
+static __global__ void __launch_bounds__(IFC_THREADS) k_ipp_fold_cross(uint32_t* __restrict__ a, uint32_t* __restrict__ b,
                                                                 uint32_t* __restrict__ wG, uint32_t* __restrict__ wH,
                                                                 uint32_t n /*weights*/, uint32_t m /*length before the fold*/,
                                                                 uint32_t stride, IppPair up,
@@ -355,114 +357,6 @@ __global__ void __launch_bounds__(IFC_THREADS) k_ipp_fold_cross(uint32_t* __rest
   if (threadIdx.x == 0 && lane_id == 0) {
     sc_store(partials + (size_t)blockIdx.x * 16, cl);
     sc_store(partials + (size_t)blockIdx.x * 16 + 8, cr);
-  }
-}
-
-// ---------------------------------------------------------------------------
-// folded generators, once: out[g] for g < 2 m0 is G'_p (g = p) or H'_p (g = m0 + p),
-//   G'_p = sum_{t < n/m0} wG(t m0 + p) * G_{t m0 + p}            (weights in Montgomery form)
-// and out[2 m0] = q_mul * (point q_id) when q_mul is given.  One WARP per output; its lanes share the
-// (term, window-slice) units, then a tree over the warp.
-// ---------------------------------------------------------------------------
-struct CombMat {
-  const uint32_t* comb;  // generator combs (affine)
-  uint32_t g_id, h_id, q_id;
-  const uint32_t *wG, *wH;
-  const uint32_t* q_mul;  // canonical scalar or null
-  uint32_t n, m0;
-  sc_bias bias4;
-};
-__global__ void __launch_bounds__(CB_THREADS) k_comb_materialize(CombMat M, uint32_t* __restrict__ out /*[2 m0 + 1][32] ext*/) {
-  __shared__ __align__(16) uint32_t pts[CB_THREADS][32];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t ngroups = 2 * M.m0 + (M.q_mul ? 1u : 0u);
-  uint32_t g = blockIdx.x * (CB_THREADS / 32) + warp;
-  const bool live = g < ngroups;
-  if (!live) g = 0;  // idle warps shadow group 0 (the quad arithmetic shuffles warp-wide) and do not store
-  const bool is_q = g == 2 * M.m0;
-  const bool is_h = !is_q && g >= M.m0;
-  const uint32_t p = is_q ? 0 : (is_h ? g - M.m0 : g);
-  const uint32_t gterms = is_q ? 1u : M.n / M.m0;
-  const uint32_t ws = gterms >= 32 ? 1u : 32u / gterms;  // window slices per term: gterms * ws >= 32 units
-  const int per = COMB_WINDOWS / (int)ws;
-  ge_ext acc = ge_identity();
-  for (uint32_t unit = lane; unit < gterms * ws; unit += 32) {
-    const uint32_t t = unit / ws, slice = unit % ws;
-    sc v;
-    uint32_t id;
-    if (is_q) {
-      sc_load(v, M.q_mul);
-      id = M.q_id;
-    } else {
-      const uint32_t i = t * M.m0 + p;
-      sc_load(v, (is_h ? M.wH : M.wG) + (size_t)i * 8);
-      v = sc_from_mont(v);
-      id = (is_h ? M.h_id : M.g_id) + i;
-    }
-    const sc_recoded r = sc_recode(v.v, M.bias4);
-    ge_ext part = comb_windows<true>(M.comb + (size_t)id * COMB_ENTRIES * COMB_AFFINE_WORDS, r, (int)slice * per, (int)(slice + 1) * per);
-    acc = ge_add(acc, part);
-  }
-  ge_store_ext(pts[threadIdx.x], acc);
-  __syncwarp();
-  // quad q of the warp sums lanes 4q..4q+3, then a shuffle tree over the eight quads
-  const uint32_t quad = lane >> 2;
-  ge4 tq = ge4_load(pts[warp * 32 + 4 * quad]);
-#pragma unroll
-  for (int k = 1; k < 4; k++) tq = ge4_add(tq, ge4_load(pts[warp * 32 + 4 * quad + k]));
-#pragma unroll
-  for (int off = 16; off >= 4; off >>= 1) {
-    ge4 o;
-#pragma unroll
-    for (int w = 0; w < 8; w++) o.c.v[w] = __shfl_down_sync(BPG_FULL_MASK, tq.c.v[w], off);
-    tq = ge4_add(tq, o);
-  }
-  if (live && lane < 4) ge4_store(out + (size_t)g * 32, tq);
-}
-
-// ---------------------------------------------------------------------------
-// combs of the folded generators (per proof): the doubling chain 16^j P on a quad per point, then the eight
-// multiples of every (point, window) in the projective "cached" layout -- no inversion anywhere.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(CB_THREADS) k_comb_chain(const uint32_t* __restrict__ pts_in /*[npts][32] ext*/, uint32_t npts,
-                                                           uint32_t* __restrict__ chain /*[npts][64][32] ext*/) {
-  uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-  const bool live = q < npts;
-  if (!live) q = npts - 1;
-  ge4 cur = ge4_load(pts_in + (size_t)q * 32);
-  uint32_t* dst = chain + (size_t)q * COMB_WINDOWS * 32;
-  if (live) ge4_store(dst, cur);
-#pragma unroll 1
-  for (int j = 1; j < COMB_WINDOWS; j++) {
-    cur = ge4_dbl(cur);
-    cur = ge4_dbl(cur);
-    cur = ge4_dbl(cur);
-    cur = ge4_dbl(cur);
-    if (live) ge4_store(dst + (size_t)j * 32, cur);
-  }
-}
-__global__ void __launch_bounds__(CB_THREADS) k_comb_multiples(const uint32_t* __restrict__ chain, uint32_t nwin /*npts * 64*/,
-                                                               uint32_t* __restrict__ comb /*[npts][64][8][32] cached*/) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nwin) return;
-  ge_ext base;
-  ge_load_ext(base, chain + (size_t)t * 32);
-  const fe ymx = fe_sub(base.Y, base.X), ypx = fe_add_nc(base.Y, base.X), z2 = fe_add_nc(base.Z, base.Z);
-  const fe t2d = fe_mul(base.T, fe_const(BPG_K(K_D2)));
-  uint32_t* out = comb + (size_t)t * 8 * COMB_CACHED_WORDS;
-  fe_store(out, ymx);
-  fe_store(out + 8, ypx);
-  fe_store(out + 16, z2);
-  fe_store(out + 24, t2d);
-  ge_ext m = base;
-#pragma unroll 1
-  for (int d = 1; d < 8; d++) {
-    m = ge_add_cached(m, ymx, ypx, z2, t2d);
-    uint32_t* o = out + (size_t)d * COMB_CACHED_WORDS;
-    fe_store(o, fe_sub(m.Y, m.X));
-    fe_store(o + 8, fe_add_nc(m.Y, m.X));
-    fe_store(o + 16, fe_add_nc(m.Z, m.Z));
-    fe_store(o + 24, fe_mul(m.T, fe_const(BPG_K(K_D2))));
   }
 }
 

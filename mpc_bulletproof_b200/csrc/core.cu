@@ -1,5 +1,6 @@
 // libbpgpu: context, memory, tables, fixed-base comb, peer exchange and the host-buffer MSM entry points
 // of the C ABI (include/bpgpu.h).  The Pippenger launch itself is msm.cu.
+#define BPG_FE_OUTLINE 1  // latency-bound kernels: products are calls, not 1.5 KB of inline code each
 #include "internal.cuh"
 #include "point_kernels.cuh"
 

@@ -166,7 +166,7 @@ BPG_DI fe fe_reduce512(uint32_t r[16]) {
 }
 
 // ---- multiplication -----------------------------------------------------------
-BPG_DI fe fe_mul(const fe& A, const fe& B) {
+BPG_DI fe fe_mul_inl(const fe& A, const fe& B) {
   const uint32_t* a = A.v;
   const uint32_t* b = B.v;
   uint32_t e[16];  // even-aligned columns: pair (e[2k], e[2k+1]) = columns 2k, 2k+1
@@ -228,7 +228,7 @@ BPG_DI fe fe_mul(const fe& A, const fe& B) {
 // doubled once as a 512-bit shift, plus the 8 squares: 36 + 8 wide multiply-adds instead of 64 + 8.
 // Measured on B200 (tools/fe_lat.cu): 207 ns against 262 ns for fe_mul(a, a) on a lone
 // warp, 119 against 165 ns per warp at full occupancy.
-BPG_DI fe fe_sq(const fe& A) {
+BPG_DI fe fe_sq_inl(const fe& A) {
   const uint32_t* a = A.v;
   uint32_t e[16], o[16];
   e[0] = e[1] = 0;
@@ -308,6 +308,21 @@ BPG_DI fe fe_sq(const fe& A) {
   }
   return fe_reduce512(r);
 }
+
+// Out-of-line products for the latency-bound kernels (tree reductions, encodings, comb rounds): a handful of
+// warps run hundreds of products each, and with every product inlined (about 1.5 KB of straight-line code)
+// such a kernel is bound by instruction FETCH, not by the multiplier -- the measured cold cost of a finishing
+// kernel was twice its arithmetic.  A translation unit defines BPG_FE_OUTLINE before including this header to
+// get calls (operands by value travel in registers: no local memory); the bucket accumulation keeps them inline.
+#if defined(BPG_FE_OUTLINE) && defined(__CUDA_ARCH__)
+static __device__ __noinline__ fe fe_mul_call(fe a, fe b) { return fe_mul_inl(a, b); }
+static __device__ __noinline__ fe fe_sq_call(fe a) { return fe_sq_inl(a); }
+__device__ __forceinline__ fe fe_mul(const fe& a, const fe& b) { return fe_mul_call(a, b); }
+__device__ __forceinline__ fe fe_sq(const fe& a) { return fe_sq_call(a); }
+#else
+BPG_DI fe fe_mul(const fe& a, const fe& b) { return fe_mul_inl(a, b); }
+BPG_DI fe fe_sq(const fe& a) { return fe_sq_inl(a); }
+#endif
 
 // ---- addition / subtraction -------------------------------------------------
 // loose + loose -> loose.  Carry out of 2^256 folds as +38; a second carry can

@@ -122,6 +122,11 @@ void launch_decode_to_niels(bpg_ctx* ctx, cudaStream_t s, const uint8_t* d_comp,
 void launch_comb_build(bpg_ctx* ctx, cudaStream_t s, const uint8_t* d_base32, uint32_t* table, uint32_t* bad);
 void launch_comb_mul(bpg_ctx* ctx, cudaStream_t s, const uint32_t* tables, int nbases, const uint32_t* d_scalars, size_t n,
                      uint8_t* d_out_bytes, uint32_t* d_out_ext);
+// folded generators of a long inner-product argument and their combs (comb_build.cu); `folded` holds
+// COMB_MAT_SPLIT partial sums per point
+constexpr uint32_t COMB_MAT_SPLIT = 2;
+int comb_materialize(bpg_ctx* ctx, cudaStream_t s, const uint32_t* gen_comb, uint32_t g_id, uint32_t h_id, const uint32_t* wG,
+                     const uint32_t* wH, size_t n, size_t m0, uint32_t* folded, uint32_t* chain, uint32_t* comb);
 // IPP state over device-resident vectors (ipp.cu)
 int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_table* H, size_t h_off, size_t n,
                   const uint8_t* Q_host, const bpg_table* shared, size_t g_base, size_t h_base, size_t q_id,

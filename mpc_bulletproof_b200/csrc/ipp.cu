@@ -1,4 +1,5 @@
 // libbpgpu: inner-product argument, device-resident state, one MSM per round.
+#define BPG_FE_OUTLINE 1  // latency-bound kernels: products are calls, not 1.5 KB of inline code each
 #include "internal.cuh"
 #include "ipp_kernels.cuh"
 #include "comb_kernels.cuh"
@@ -200,28 +201,12 @@ static int ipp_materialize(bpg_ipp* st) {
   bpg_ctx* ctx = st->ctx;
   cudaStream_t s = ctx->stream;
   const size_t m0 = st->m0, npts = 2 * m0;
-  const size_t w_pts = npts * 32, w_chain = npts * COMB_WINDOWS * 32, w_comb = npts * (size_t)COMB_ENTRIES * COMB_CACHED_WORDS;
+  const size_t w_pts = npts * 32 * COMB_MAT_SPLIT, w_chain = npts * COMB_WINDOWS * 32, w_comb = npts * (size_t)COMB_ENTRIES * COMB_CACHED_WORDS;
   if (dev_alloc(ctx, &st->mat_buf, (w_pts + w_chain + w_comb) * 4) != cudaSuccess) return BPG_ERR_NOMEM;
   uint32_t *folded = st->mat_buf, *chain = folded + w_pts, *comb = chain + w_chain;
   prof_mark(ctx, BPG_PROF_COMBINE);
-  CombMat M;
-  M.comb = st->tab->comb;
-  M.g_id = st->cg_id;
-  M.h_id = st->ch_id;
-  M.q_id = 0;
-  M.wG = st->wG;
-  M.wH = st->wH;
-  M.q_mul = nullptr;
-  M.n = (uint32_t)st->n;
-  M.m0 = (uint32_t)m0;
-  M.bias4 = bias_for(4);
-  k_comb_materialize<<<(unsigned)((npts + CB_THREADS / 32 - 1) / (CB_THREADS / 32)), CB_THREADS, 0, s>>>(M, folded);
-  LAUNCH_CHECK();
-  k_comb_chain<<<(unsigned)((npts * 4 + CB_THREADS - 1) / CB_THREADS), CB_THREADS, 0, s>>>(folded, (uint32_t)npts, chain);
-  LAUNCH_CHECK();
-  k_comb_multiples<<<(unsigned)((npts * COMB_WINDOWS + CB_THREADS - 1) / CB_THREADS), CB_THREADS, 0, s>>>(
-      chain, (uint32_t)(npts * COMB_WINDOWS), comb);
-  LAUNCH_CHECK();
+  int rc = comb_materialize(ctx, s, st->tab->comb, st->cg_id, st->ch_id, st->wG, st->wH, st->n, m0, folded, chain, comb);
+  if (rc) return rc;
   k_ipp_init_weights<<<(unsigned)((m0 + 255) / 256), 256, 0, s>>>(nullptr, nullptr, (uint32_t)m0, st->wG, st->wH);
   LAUNCH_CHECK();
   prof_mark(ctx, -1);
@@ -249,8 +234,11 @@ static int ipp_comb_round(bpg_ipp* st, bool external_cross) {
     st->ncross = gcross;
   }
   // threads per term: enough (term, window-slice) units to fill the machine, at most one window per thread
+  // (each thread's accumulator must then go through the block tree, which costs about three additions of its own:
+  // more slices than the machine needs only add tree work)
+  static const size_t target_mul = env_size("BPG_COMB_THREADS_PER_SM", 192);
   uint32_t wsplit = 1;
-  while (wsplit < COMB_WINDOWS && n * wsplit < (size_t)ctx->sm_count * 256) wsplit <<= 1;
+  while (wsplit < COMB_WINDOWS && n * wsplit * sets < (size_t)ctx->sm_count * target_mul) wsplit <<= 1;
   const unsigned bx = (unsigned)((n * wsplit + CB_THREADS - 1) / CB_THREADS);
   int rc = ipp_ensure_parts(st, (size_t)sets * bx * 128);
   if (rc) return rc;
@@ -553,33 +541,3 @@ extern "C" void bpg_ipp_free(bpg_ipp* st) {
   delete st;
 }
 
-// ---------------------------------------------------------------------------
-// combs of a resident table (one-time, like bpg_table_set_windows): 64 x 8 affine-Niels multiples per point
-// ---------------------------------------------------------------------------
-extern "C" int bpg_table_build_comb(bpg_ctx* ctx, bpg_table* t) {
-  if (!ctx || !t) return BPG_ERR_ARG;
-  if (t->comb || t->n == 0) return BPG_OK;
-  CK(cudaSetDevice(ctx->device));
-  uint32_t* comb = nullptr;
-  cudaError_t e = cudaMalloc(&comb, t->n * (size_t)COMB_ENTRIES * COMB_AFFINE_WORDS * 4);
-  if (e != cudaSuccess) {
-    ctx->last_cuda = (int)e;
-    cudaGetLastError();
-    return BPG_ERR_NOMEM;
-  }
-  const size_t CH = 1 << 15;
-  for (size_t first = 0; first < t->n; first += CH) {
-    size_t cnt = std::min(CH, t->n - first);
-    k_table_comb_build<<<(unsigned)cnt, COMB_WINDOWS, 0, ctx->stream>>>(t->niels, (uint32_t)first, comb);
-    ctx->launches++;
-  }
-  cudaError_t se = cudaStreamSynchronize(ctx->stream);
-  if (se != cudaSuccess || cudaGetLastError() != cudaSuccess) {
-    ctx->last_cuda = (int)se;
-    cudaFree(comb);
-    return BPG_ERR_CUDA;
-  }
-  t->comb = comb;
-  return BPG_OK;
-}
-extern "C" int bpg_table_has_comb(const bpg_table* t) { return t && t->comb ? 1 : 0; }

@@ -1,4 +1,5 @@
 // libbpgpu: one Pippenger launch, ristretto255 bucket reduction, Horner, and the few-term path.
+#define BPG_FE_OUTLINE 1  // latency-bound kernels: products are calls, not 1.5 KB of inline code each
 #include "msm_launch.cuh"
 #include "msm_reduce_kernels.cuh"
 
@@ -14,6 +15,8 @@ cudaError_t msm_kernels_init() {
 void msm_reduce_geometry(const MsmCfg& cfg, bool* thread_leaf, uint32_t* LC, uint32_t* tiles0) {
   *thread_leaf = cfg.nb >= (1u << 17);
   *LC = *thread_leaf ? 16 : (cfg.nb > (1u << 15) ? 8 : 4);
+  static const char* force = getenv("BPG_LEAF_LC");  // tuning: 4 or 8 (quad leaf)
+  if (force && !*thread_leaf) *LC = atoi(force) == 8 ? 8 : 4;
   *tiles0 = *thread_leaf ? (cfg.nb + *LC - 1) / *LC : (cfg.nb + RT_QUADS * *LC - 1) / (RT_QUADS * *LC);
 }
 

@@ -120,7 +120,7 @@ BPG_DI sc sc_cond_sub_l(const uint32_t* x) {
 }
 
 // Montgomery product a*b*R^-1 mod l; a, b < l.
-BPG_DI sc sc_montmul(const sc& a, const sc& b) {
+BPG_DI sc sc_montmul_inl(const sc& a, const sc& b) {
   uint32_t t[17];
   mul256_wide(t, a.v, b.v);
   t[16] = 0;
@@ -162,6 +162,13 @@ BPG_DI sc sc_montmul(const sc& a, const sc& b) {
   // result = t[8..16] < 2l
   return sc_cond_sub_l(t + 8);
 }
+// out of line in the latency-bound translation units (see fe.cuh, BPG_FE_OUTLINE)
+#if defined(BPG_FE_OUTLINE) && defined(__CUDA_ARCH__)
+static __device__ __noinline__ sc sc_montmul_call(sc a, sc b) { return sc_montmul_inl(a, b); }
+__device__ __forceinline__ sc sc_montmul(const sc& a, const sc& b) { return sc_montmul_call(a, b); }
+#else
+BPG_DI sc sc_montmul(const sc& a, const sc& b) { return sc_montmul_inl(a, b); }
+#endif
 
 BPG_DI sc sc_add(const sc& a, const sc& b) {
   uint32_t s[8];
