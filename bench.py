@@ -398,59 +398,108 @@ def run_b200(args, rank, local_rank, world):
         raw = t.cpu().numpy().tobytes()
         return [int.from_bytes(raw[i : i + 32], "little") for i in range(0, len(raw), 32)]
 
-    dot = sum(a * k for a, k in zip(ints(last), ints(gen_k))) % L_ORDER
-    dots = torch.tensor(list(dot.to_bytes(32, "little")), dtype=torch.uint8, device=dev)
-    if world > 1:
-        all_dots = [torch.empty_like(dots) for _ in range(world)]
-        dist.all_gather(all_dots, dots)
-        dot = sum(int.from_bytes(bytes(d.cpu().tolist()), "little") for d in all_dots) % L_ORDER
-    expected_hex = comb.mul(dot.to_bytes(32, "little")).hex()
+    gen_k_ints = ints(gen_k)
+
+    def expected_for(scalars_t):
+        dot = sum(a * k for a, k in zip(ints(scalars_t), gen_k_ints)) % L_ORDER
+        if world > 1:
+            mine = torch.tensor(list(dot.to_bytes(32, "little")), dtype=torch.uint8, device=dev)
+            all_dots = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(all_dots, mine)
+            dot = sum(int.from_bytes(bytes(d.cpu().tolist()), "little") for d in all_dots) % L_ORDER
+        return comb.mul(dot.to_bytes(32, "little")).hex()
+
+    expected_hex = expected_for(last)
     result_ok = expected_hex == result_hex
 
     # ---- end to end through the host-buffer C ABI ("e2e") ----------------------
-    # every step: scalars start in pinned HOST memory, go H2D, the MSM runs, the
-    # 32-byte result comes back D2H.  N=1 uses bpg_msm_table itself; N>1 adds the
-    # all-gather of partial sums between the device MSM and the encode.
+    # every step: its scalars start in page-locked HOST memory and go host -> device, the MSM runs, the 32-byte
+    # result comes back device -> host; all of it inside the timed region.  The steps are PIPELINED two deep, as
+    # a caller with a stream of MSMs would run them: N = 1 through bpg_msm_table_submit / bpg_msm_job_wait (the
+    # library's own double-buffered staging), N > 1 with the same two-slot scheme around bpg_dev_msm_table and
+    # the exchange.  `e2e_sync` is the one-call-at-a-time form (bpg_msm_table), `e2e_pageable` the pipelined
+    # form with ordinary (pageable) host memory, which is what a plain Vec<u8> caller passes.
+    import ctypes
+
+    from mpc_bulletproof_b200._lib import check, lib
+
     host_sc = [s.cpu().pin_memory() for s in scal[:2]]
-    d_in = torch.empty_like(scal[0])
-    host_out = torch.empty(32, dtype=torch.uint8).pin_memory()
+    host_out = [torch.empty(32, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    out_buf = ctypes.create_string_buffer(32)
 
-    def e2e_step(i):
-        if world == 1:
-            import ctypes
+    def e2e_sync_step(i):
+        check(lib().bpg_msm_table(ctx._h, table._h, 0, n, ctypes.c_void_p(host_sc[i % 2].data_ptr()), 1, out_buf))
 
-            from mpc_bulletproof_b200._lib import check, lib
+    if world == 1:
+        jobs = {}
 
-            check(
-                lib().bpg_msm_table(
-                    ctx._h, table._h, 0, n, ctypes.c_void_p(host_sc[i % 2].data_ptr()), 1, ctypes.c_void_p(host_out.data_ptr())
-                )
-            )
-        else:
+        def submit(i, src=None):
+            src = host_sc if src is None else src
+            j = ctypes.c_void_p()
+            check(lib().bpg_msm_table_submit(ctx._h, table._h, 0, n, ctypes.c_void_p(src[i % 2].data_ptr()), 1, ctypes.byref(j)))
+            jobs[i] = j
+
+        def wait(i):
+            check(lib().bpg_msm_job_wait(jobs.pop(i), out_buf))
+    else:
+        copy_stream = torch.cuda.Stream(device=dev)
+        d_in = [torch.empty_like(scal[0]) for _ in range(2)]
+        res2 = [torch.zeros(32, dtype=torch.uint8, device=dev) for _ in range(2)]
+        ev_up = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+
+        def submit(i, src=None):
+            src = host_sc if src is None else src
+            k = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_done[k])  # slot k was last read two submissions ago
+                d_in[k].copy_(src[k], non_blocking=True)
+                ev_up[k].record(copy_stream)
             with torch.cuda.stream(stream):
-                d_in.copy_(host_sc[i % 2], non_blocking=True)
-                table.dev_msm(d_in.data_ptr(), 1, part.data_ptr())
+                stream.wait_event(ev_up[k])
+                table.dev_msm(d_in[k].data_ptr(), 1, part.data_ptr())
                 if peer is not None:
-                    peer.exchange_sum_encode(part.data_ptr(), 1, result.data_ptr())
+                    peer.exchange_sum_encode(part.data_ptr(), 1, res2[k].data_ptr())
                 else:
                     dist.all_gather_into_tensor(parts, part)
-                    dev_sum_encode(ctx, parts.data_ptr(), world, 1, result.data_ptr())
-                host_out.copy_(result, non_blocking=True)
-            stream.synchronize()
+                    dev_sum_encode(ctx, parts.data_ptr(), world, 1, res2[k].data_ptr())
+                host_out[k].copy_(res2[k], non_blocking=True)
+                ev_done[k].record(stream)
 
-    for i in range(min(3, args.warmup)):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(i)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+        def wait(i):
+            ev_done[i % 2].synchronize()
+
+    def pipelined(steps, src=None):
+        submit(0, src)
+        for i in range(1, steps):
+            submit(i, src)
+            wait(i - 1)
+        wait(steps - 1)
+
+    def timed(fn, steps):
+        barrier()
+        t0 = time.perf_counter()
+        fn(steps)
+        barrier()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    pipelined(max(2, min(3, args.warmup)))
+    e2e_ms = timed(pipelined, max(args.steps, 2))
     e2e_val = world * n / e2e_ms / 1e3
+    e2e_expected_hex = expected_for(scal[(max(args.steps, 2) - 1) % 2])
+    e2e_last = bytes(out_buf.raw).hex() if world == 1 else bytes(host_out[(max(args.steps, 2) - 1) % 2].tolist()).hex()
+    e2e_sync_ms = e2e_page_ms = None
+    if world == 1:
+        for i in range(2):
+            e2e_sync_step(i)
+        e2e_sync_ms = timed(lambda k: [e2e_sync_step(i) for i in range(k)], max(args.steps, 2))
+        page_sc = [torch.from_numpy(s.numpy().copy()) for s in host_sc]  # ordinary pageable memory
+        pipelined(2, page_sc)
+        e2e_page_ms = timed(lambda k: pipelined(k, page_sc), max(args.steps, 2))
 
     # ---- rank 0: roofline, CPU baseline, JSON ----------------------------------
     if rank == 0:
@@ -534,7 +583,13 @@ def run_b200(args, rank, local_rank, world):
                 "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": n * 32,
                 "d2h_bytes_per_step": 32,
-                "api": "bpg_msm_table (host buffers)" if world == 1 else f"pinned H2D + bpg_dev_msm_table + {combine} + D2H",
+                "api": "bpg_msm_table_submit / bpg_msm_job_wait (page-locked host scalars, two jobs in flight)" if world == 1
+                else f"two-slot pipeline: pinned H2D on a copy stream + bpg_dev_msm_table + {combine} + D2H",
+                "result_ok": e2e_last == e2e_expected_hex,
+                "sync_ms_per_step": e2e_sync_ms,
+                "sync_value": (n / e2e_sync_ms / 1e3) if e2e_sync_ms else None,
+                "pageable_ms_per_step": e2e_page_ms,
+                "pageable_value": (n / e2e_page_ms / 1e3) if e2e_page_ms else None,
             },
             "gpu_launches": int(launches),
             "phases_ms": phases,
@@ -544,7 +599,7 @@ def run_b200(args, rank, local_rank, world):
             "variable_base": varbase,
             "clocks": clk,
             "result": result_hex,
-            "result_ok": result_ok,
+            "result_ok": result_ok and e2e_last == e2e_expected_hex,
             "result_check": "encode((sum_ranks sum_i s_i k_i mod l) * B) from host big integers + one fixed-base multiplication",
         }
         emit(line)
@@ -556,6 +611,9 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not (result_ok and e2e_last == e2e_expected_hex):
+        print(f"rank {rank}: RESULT MISMATCH: timed {result_hex} / e2e {e2e_last} vs expected {expected_hex} / {e2e_expected_hex}", file=sys.stderr)
+        sys.exit(3)
 
 
 def r1cs_timing(ctx, comb, lg, dev):

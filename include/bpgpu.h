@@ -118,6 +118,17 @@ int bpg_msm(bpg_ctx* ctx, const uint8_t* scalars_le, const uint8_t* points_compr
 int bpg_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t offset, size_t n,
                   const uint8_t* scalars_le, int n_sets, uint8_t* out /* n_sets*32 */);
 
+/* Pipelined form of bpg_msm_table for a STREAM of MSMs over a resident table (batch verification, a prover's
+ * successive commitments, the throughput benchmark): submit returns as soon as the upload and the kernels are
+ * enqueued, wait blocks for the 32-byte results.  At most two jobs are in flight per context; the scalars of
+ * the second travel host -> device (its own staging buffer, the copy engine) while the first computes.
+ * Page-locked scalars (bpg_host_alloc) make the upload asynchronous; pageable ones work but submit then
+ * blocks for the staging copy.  BPG_ERR_ARG if two jobs are already in flight. */
+typedef struct bpg_msm_job bpg_msm_job;
+int bpg_msm_table_submit(bpg_ctx* ctx, const bpg_table* table, size_t offset, size_t n, const uint8_t* scalars_le,
+                         int n_sets, bpg_msm_job** job);
+int bpg_msm_job_wait(bpg_msm_job* job, uint8_t* out /* n_sets*32 */);
+
 /* Indexed form: term t = scalars[t] * table[point_ids[t]], added into out[set_ids[t]]
  * (set_ids NULL = all set 0).  One launch forms A_I, A_O and S from (B_blinding, G, H)
  * (reference src/r1cs/prover.rs:465-494, 532-565). */

@@ -109,6 +109,8 @@ _SIGNATURES = {
     "bpg_table_free": (None, [_P]),
     "bpg_msm": (_I, [_P, _P, _P, _SZ, _P]),
     "bpg_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),
+    "bpg_msm_table_submit": (_I, [_P, _P, _SZ, _SZ, _P, _I, ctypes.POINTER(_P)]),
+    "bpg_msm_job_wait": (_I, [_P, _P]),
     "bpg_msm_table_indexed": (_I, [_P, _P, _P, _P, _P, _SZ, _I, _P]),
     "bpg_msm_mixed": (_I, [_P, _P, _SZ, _P, _P, _P, _I, _P, _P]),
     "bpg_dev_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),

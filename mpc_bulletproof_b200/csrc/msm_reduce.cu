@@ -1,5 +1,4 @@
 // libbpgpu: one Pippenger launch, ristretto255 bucket reduction, Horner, and the few-term path.
-#define BPG_FE_OUTLINE 1  // latency-bound kernels: products are calls, not 1.5 KB of inline code each
 #include "msm_launch.cuh"
 #include "msm_reduce_kernels.cuh"
 
