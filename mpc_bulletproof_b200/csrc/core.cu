@@ -64,6 +64,7 @@ extern "C" int bpg_init(int device, bpg_ctx** out) {
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_small, SMALL_BYTES);
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_pinned, SMALL_BYTES);
   if (e == cudaSuccess) e = msm_kernels_init();
+  if (e == cudaSuccess) e = msm_sort_kernels_init();
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) {
     delete ctx;

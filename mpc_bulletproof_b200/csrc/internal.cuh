@@ -116,7 +116,8 @@ int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points, const
 int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_adhoc, const bpg_table* const* tabs,
                    const size_t* offs, const size_t* lens, int nsegs, const uint32_t* d_scalars, size_t total,
                    uint8_t out[32], bool identity_only = false);
-cudaError_t msm_kernels_init();  // msm.cu: function attributes of the pipeline kernels
+cudaError_t msm_kernels_init();
+cudaError_t msm_sort_kernels_init();  // msm.cu  // msm.cu: function attributes of the pipeline kernels
 // point-level kernels launched on behalf of other translation units (core.cu)
 void launch_decode_to_niels(bpg_ctx* ctx, cudaStream_t s, const uint8_t* d_comp, size_t n, uint32_t* niels, uint32_t* bad);
 void launch_comb_build(bpg_ctx* ctx, cudaStream_t s, const uint8_t* d_base32, uint32_t* table, uint32_t* bad);

@@ -3,6 +3,13 @@
 
 using namespace bpg;
 
+cudaError_t msm_sort_kernels_init() {
+  cudaError_t e = cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_rs_finish, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(((size_t)4 << RS_MAX_LB) + (size_t)RS_FINISH_CAP * 4));
+}
+
 
 // ---------------------------------------------------------------------------
 // MSM launch
@@ -129,18 +136,29 @@ int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points, const
     msm_reduce_geometry(cfg, &L.thread_leaf, &L.LC, &L.tiles0);
   }
   size_t ntiles = (cfg.B + SCAN_TILE - 1) / SCAN_TILE;
+  // sort: two-pass radix partition in shared memory (default) or the global-atomic counting sort (BPG_SORT=atomic,
+  // and bucket spaces beyond 2^25)
+  static const bool sort_atomic = getenv("BPG_SORT") && !strcmp(getenv("BPG_SORT"), "atomic");
+  static const uint32_t target_parts = getenv("BPG_RS_PARTS") ? (uint32_t)atoi(getenv("BPG_RS_PARTS")) : RS_TARGET_PARTS;
+  static const uint32_t fin_threads = getenv("BPG_RS_FIN_THREADS") ? (uint32_t)atoi(getenv("BPG_RS_FIN_THREADS")) : RS_FINISH_THREADS;
+  static const uint32_t fin_cap = getenv("BPG_RS_FIN_CAP") ? (uint32_t)atoi(getenv("BPG_RS_FIN_CAP")) : RS_FINISH_CAP;
+  uint32_t lb = 4;
+  while (lb < RS_MAX_LB && ((uint64_t)cfg.B >> lb) > target_parts) lb++;
+  uint32_t P = (uint32_t)(((uint64_t)cfg.B + (1u << lb) - 1) >> lb);
+  const bool radix = !sort_atomic && P <= RS_MAX_PARTS && (size_t)RS_THREADS * cfg.W * 8 + (size_t)3 * P * 4 <= RS_SCATTER_SMEM;
   size_t off = 0;
-  // counts and the schedule's control words are adjacent: ONE memset per launch
-  size_t o_counts = off;  off += align_up((size_t)cfg.B * 4);
+  // counts / partition counters and the schedule's control words are adjacent: ONE memset per launch
+  size_t o_counts = off;  off += align_up(radix ? (size_t)2 * P * 4 : (size_t)cfg.B * 4);
   size_t o_bins = off;    off += align_up((2 * SIZE_BINS + 4) * 4);  // bins | n_items, part, multi, big_count | cursors
   size_t o_offsets = off; off += align_up(((size_t)cfg.B + 1) * 4);
-  size_t o_tiles = off;   off += align_up(ntiles * 4);
+  size_t o_tiles = off;   off += align_up(radix ? ((size_t)P + 1) * 4 : ntiles * 4);
   size_t o_big = off;     off += align_up(3 * (size_t)cfg.big_cap * 4);
   size_t o_bigpart = off; off += align_up((size_t)cfg.big_cap * 128);
   size_t o_entries = off; off += align_up((size_t)n_terms * cfg.W * 4);
+  size_t o_pairs = off;   off += radix ? align_up((size_t)n_terms * cfg.W * 8) : 0;
   size_t o_buckets = off; off += align_up((size_t)cfg.B * 128);
   size_t o_merged = off;  off += (windowed && cfg.gsub > 1) ? align_up((size_t)nsets * cfg.nb * 128) : 0;
-  size_t o_pairs = off;   off += 4 * align_up((size_t)L.rarr * L.tiles0 * 128);  // (A, Y) x ping-pong
+  size_t o_rpairs = off;  off += 4 * align_up((size_t)L.rarr * L.tiles0 * 128);  // (A, Y) x ping-pong
   size_t o_wins = off;    off += align_up((size_t)L.rarr * 128);
   // accumulation schedule: at most one item per bucket plus one per ACC_SEG entries
   L.max_items = (size_t)cfg.B + (size_t)n_terms * cfg.W / ACC_SEG + 1;
@@ -161,7 +179,7 @@ int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points, const
   L.buckets = (uint32_t*)(ws + o_buckets);
   L.merged = (uint32_t*)(ws + o_merged);
   L.pair_words = align_up((size_t)L.rarr * L.tiles0 * 128) / 4;
-  L.pairs = (uint32_t*)(ws + o_pairs);
+  L.pairs = (uint32_t*)(ws + o_rpairs);
   L.wins = (uint32_t*)(ws + o_wins);
   AccSched& sched = L.sched;
   L.big_count = bins + SIZE_BINS + 3;
@@ -178,14 +196,32 @@ int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points, const
 
   prof_mark(ctx, BPG_PROF_HIST);
   CK(cudaMemsetAsync(counts, 0, o_bins - o_counts + (2 * SIZE_BINS + 4) * 4, st));
+  // radix: a tile's pairs are staged in shared memory (RS_STAGE_PAIRS at most); terms per thread accordingly, but
+  // no more than leaves about four tiles per SM
+  int tpt = 1;
+  while (tpt < RS_TERMS && (size_t)RS_THREADS * (2 * tpt) * cfg.W <= RS_STAGE_PAIRS &&
+         n_terms / ((size_t)RS_THREADS * tpt) > (size_t)ctx->sm_count * 4)
+    tpt <<= 1;
+  const size_t tile_terms = (size_t)RS_THREADS * tpt;
+  const uint32_t stage_cap = (uint32_t)(tile_terms * cfg.W);
+  const size_t scatter_smem = (size_t)stage_cap * 8 + (size_t)3 * P * 4;
+  uint32_t *part_count = counts, *part_cursor = counts + P, *part_base = tiles;
+  auto hist = [&](size_t t0, size_t t1) -> int {
+    if (radix) {
+      k_rs_hist<<<(unsigned)((t1 - t0 + tile_terms - 1) / tile_terms), RS_THREADS, P * 4, st>>>(
+          d_scalars, d_set_ids, cfg, lb, P, part_count, (uint32_t)t0, (uint32_t)t1, tpt);
+    } else {
+      k_hist<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, st>>>(d_scalars, d_set_ids, cfg, counts, (uint32_t)t0, (uint32_t)t1);
+    }
+    LAUNCH_CHECK();
+    return BPG_OK;
+  };
   unsigned gt = (unsigned)((n_terms + 255) / 256);
   if (h_scalars && lane == 0 && n_terms >= (1u << 18)) {
     // Host scalars: the copy runs on the auxiliary stream in pieces and the digit histogram of
-    // piece i runs while piece i+1 is still on the bus (hides the 0.12 ms histogram of a 2^20-term
-    // launch; measured against one copy on two boxes: 2.26-2.45 vs 2.39-2.62 ms end to end, the
-    // spread being the PCIe rate of the box).
+    // piece i runs while piece i+1 is still on the bus (hides the histogram of a 2^20-term launch behind the copy).
     const int pieces = 4;
-    size_t per = (((n_terms + pieces - 1) / pieces) + 255) / 256 * 256;
+    size_t per = (((n_terms + pieces - 1) / pieces) + tile_terms - 1) / tile_terms * tile_terms;
     CK(cudaEventRecord(ctx->ev_fork, st));  // d_scalars (staging) is free once earlier work is done
     CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
     for (int i = 0; i < pieces; i++) {
@@ -196,24 +232,37 @@ int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points, const
                          ctx->aux_stream));
       CK(cudaEventRecord(ctx->ev_chunk[i], ctx->aux_stream));
       CK(cudaStreamWaitEvent(st, ctx->ev_chunk[i], 0));
-      k_hist<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, st>>>(d_scalars, d_set_ids, cfg, counts, (uint32_t)t0, (uint32_t)t1);
-      LAUNCH_CHECK();
+      rc = hist(t0, t1);
+      if (rc) return rc;
     }
   } else {
     if (h_scalars) CK(cudaMemcpyAsync((void*)d_scalars, h_scalars, n_terms * 32, cudaMemcpyHostToDevice, st));
-    k_hist<<<gt, 256, 0, st>>>(d_scalars, d_set_ids, cfg, counts, 0u, (uint32_t)n_terms);
+    rc = hist(0, n_terms);
+    if (rc) return rc;
+  }
+  if (radix) {
+    prof_mark(ctx, BPG_PROF_SCAN);
+    k_rs_scan<<<1, 1024, 0, st>>>(part_count, P, part_base);
+    LAUNCH_CHECK();
+    prof_mark(ctx, BPG_PROF_SCATTER);
+    k_rs_scatter<<<(unsigned)((n_terms + tile_terms - 1) / tile_terms), RS_THREADS, scatter_smem, st>>>(
+        d_scalars, d_set_ids, d_point_ids, cfg, lb, P, part_base, part_cursor, (uint2*)(ws + o_pairs), tpt, stage_cap);
+    LAUNCH_CHECK();
+    k_rs_finish<<<P, fin_threads, ((size_t)1 << lb) * 4 + (size_t)fin_cap * 4, st>>>((const uint2*)(ws + o_pairs), part_base, cfg.B, lb,
+                                                                                    P, offsets, L.entries, bins, fin_cap);
+    LAUNCH_CHECK();
+  } else {
+    prof_mark(ctx, BPG_PROF_SCAN);
+    k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.B, tiles);
+    LAUNCH_CHECK();
+    k_scan_spine<<<1, 1024, 0, st>>>(tiles, (uint32_t)ntiles, offsets, cfg.B);
+    LAUNCH_CHECK();
+    k_scan_apply<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.B, tiles, offsets, bins);
+    LAUNCH_CHECK();
+    prof_mark(ctx, BPG_PROF_SCATTER);
+    k_scatter<<<gt, 256, 0, st>>>(d_scalars, d_set_ids, d_point_ids, cfg, offsets, counts, L.entries);
     LAUNCH_CHECK();
   }
-  prof_mark(ctx, BPG_PROF_SCAN);
-  k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.B, tiles);
-  LAUNCH_CHECK();
-  k_scan_spine<<<1, 1024, 0, st>>>(tiles, (uint32_t)ntiles, offsets, cfg.B);
-  LAUNCH_CHECK();
-  k_scan_apply<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.B, tiles, offsets, bins);
-  LAUNCH_CHECK();
-  prof_mark(ctx, BPG_PROF_SCATTER);
-  k_scatter<<<gt, 256, 0, st>>>(d_scalars, d_set_ids, d_point_ids, cfg, offsets, counts, L.entries);
-  LAUNCH_CHECK();
   // accumulation schedule: (bucket, segment) items by decreasing length; over-long buckets -> big list
   k_size_scatter<<<(cfg.B + 255) / 256, 256, 0, st>>>(offsets, cfg, sched, L.big_count, L.big_list);
   LAUNCH_CHECK();

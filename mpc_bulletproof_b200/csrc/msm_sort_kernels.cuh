@@ -259,6 +259,247 @@ static __global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t*
   }
 }
 
+// ---------------------------------------------------------------------------
+// Two-pass radix sort of the (bucket, entry) pairs -- the default sort.  The counting sort above pays one L2
+// atomic per entry in the histogram and one more in the scatter (13.6 M each at 2^20 points x 13 windows:
+// ncu showed both kernels waiting on them, issue-active 14 %).  Here every per-entry atomic is a
+// SHARED-memory atomic:
+//   k_rs_hist     bucket id >> lb = partition; per-block histogram of the partitions, one global add per
+//                 (block, occupied partition)
+//   k_rs_scan     exclusive scan of the <= 8192 partition sizes
+//   k_rs_scatter  per-block histogram again, ONE global reservation per (block, partition), then the pairs
+//                 (bucket, entry) go to their partition's region at shared-memory ranks
+//   k_rs_finish   one block per partition (2^lb buckets, a few thousand pairs): bucket histogram and cursors
+//                 in shared memory -> offsets[], the size classes of the accumulation schedule, the entries in
+//                 bucket order.  A partition of any size works (structured scalars: the block just loops).
+// Order inside a bucket is irrelevant (the sum is a group element), so no stability is needed.
+// ---------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_TERMS = 16;           // at most this many terms per thread of k_rs_hist / k_rs_scatter (tiles of 4096 terms)
+constexpr uint32_t RS_MAX_PARTS = 8192;
+constexpr uint32_t RS_MAX_LB = 12;     // at most 4096 buckets per partition
+constexpr uint32_t RS_TARGET_PARTS = 2048;            // partitions aimed for (tuned at 2^20 points x 13 windows, tools/r2_sort_tune.sh)
+constexpr size_t RS_STAGE_PAIRS = 12288;              // pairs of a tile staged in shared memory (96 KB)
+constexpr size_t RS_SCATTER_SMEM = 200 * 1024;        // dynamic shared memory k_rs_scatter may be given
+
+__device__ __forceinline__ uint32_t rs_bucket(const MsmCfg& cfg, uint32_t base, uint32_t g, int d) {
+  uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+  return base + g * cfg.nb + mag - 1;
+}
+
+static __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t* __restrict__ scalars,
+                                                               const uint8_t* __restrict__ set_ids, MsmCfg cfg, uint32_t lb,
+                                                               uint32_t P, uint32_t* __restrict__ part_count,
+                                                               uint32_t t_begin, uint32_t t_end, int tpt /*terms per thread*/) {
+  extern __shared__ uint32_t rs_sm[];  // [P] histogram
+  __shared__ uint32_t sh[9][SORT_THREADS];
+  for (uint32_t p = threadIdx.x; p < P; p += RS_THREADS) rs_sm[p] = 0;
+  __syncthreads();
+  for (int k = 0; k < tpt; k++) {
+    uint32_t t = t_begin + (blockIdx.x * tpt + k) * RS_THREADS + threadIdx.x;
+    if (t >= t_end) break;  // later k are out of range as well
+    sc s;
+    sc_load(s, scalars + (size_t)t * 8);
+    digits_park(sh, sc_recode(s.v, cfg.bias));
+    uint32_t set = cfg.nsets > 1 ? (set_ids ? set_ids[t] : t / cfg.n_points) : 0;
+    uint32_t base = set * cfg.gsub * cfg.nb;
+    uint32_t g = 0;
+    for (int w = 0; w < cfg.W; w++) {
+      int d = digit_at(sh, w, cfg.c);
+      if (d != 0) atomicAdd(&rs_sm[rs_bucket(cfg, base, g, d) >> lb], 1u);
+      g = g + 1 == cfg.gsub ? 0 : g + 1;
+    }
+  }
+  __syncthreads();
+  for (uint32_t p = threadIdx.x; p < P; p += RS_THREADS)
+    if (rs_sm[p]) atomicAdd(&part_count[p], rs_sm[p]);
+}
+
+// single block: part_base[0..P] = exclusive scan of part_count[0..P)
+static __global__ void __launch_bounds__(1024) k_rs_scan(const uint32_t* __restrict__ part_count, uint32_t P,
+                                                         uint32_t* __restrict__ part_base) {
+  __shared__ uint32_t smem[33];
+  const uint32_t per = (P + 1023) / 1024;  // <= 8
+  uint32_t v[8];
+  uint32_t s = 0;
+  for (uint32_t k = 0; k < per; k++) {
+    uint32_t i = threadIdx.x * per + k;
+    v[k] = i < P ? part_count[i] : 0;
+    s += v[k];
+  }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(s, &total, smem);
+  for (uint32_t k = 0; k < per; k++) {
+    uint32_t i = threadIdx.x * per + k;
+    if (i < P) part_base[i] = ex;
+    ex += v[k];
+  }
+  if (threadIdx.x == 0) part_base[P] = total;
+}
+
+// Tile of `tpt` x 256 terms: its pairs are counting-sorted by partition IN SHARED MEMORY, then every partition's run
+// goes out in one piece (a run of r pairs is r x 8 contiguous bytes: sector-sized writes instead of one
+// read-modify-write of a sector per pair).  Dynamic shared memory: pairs[cap] | hist[P] | soff[P] | gbase[P].
+static __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t* __restrict__ scalars,
+                                                                  const uint8_t* __restrict__ set_ids,
+                                                                  const uint32_t* __restrict__ point_ids, MsmCfg cfg,
+                                                                  uint32_t lb, uint32_t P,
+                                                                  const uint32_t* __restrict__ part_base,
+                                                                  uint32_t* __restrict__ part_cursor,
+                                                                  uint2* __restrict__ pairs, int tpt, uint32_t cap) {
+  extern __shared__ __align__(16) uint32_t rs_sm[];
+  uint2* stage = reinterpret_cast<uint2*>(rs_sm);
+  uint32_t* hist = rs_sm + 2 * (size_t)cap;
+  uint32_t* soff = hist + P;
+  uint32_t* gbase = soff + P;
+  __shared__ uint32_t sh[9][SORT_THREADS];
+  __shared__ uint32_t smem[33];
+  __shared__ uint32_t carry_s;
+  for (uint32_t p = threadIdx.x; p < P; p += RS_THREADS) hist[p] = 0;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int pass = 0; pass < 2; pass++) {
+    for (int k = 0; k < tpt; k++) {
+      uint32_t t = (blockIdx.x * tpt + k) * RS_THREADS + threadIdx.x;
+      if (t >= cfg.n_terms) break;
+      sc s;
+      sc_load(s, scalars + (size_t)t * 8);
+      digits_park(sh, sc_recode(s.v, cfg.bias));
+      uint32_t set = cfg.nsets > 1 ? (set_ids ? set_ids[t] : t / cfg.n_points) : 0;
+      uint32_t pid = point_ids ? point_ids[t] : t % cfg.n_points;
+      uint32_t base = set * cfg.gsub * cfg.nb;
+      uint32_t g = 0;
+      for (int w = 0; w < cfg.W; w++) {
+        int d = digit_at(sh, w, cfg.c);
+        if (d != 0) {
+          uint32_t b = rs_bucket(cfg, base, g, d);
+          uint32_t r = atomicAdd(&hist[b >> lb], 1u);
+          if (pass == 1)
+            stage[soff[b >> lb] + r] = make_uint2(b, (pid + (uint32_t)w * cfg.win_stride) | (d < 0 ? ENTRY_NEG : 0u));
+        }
+        g = g + 1 == cfg.gsub ? 0 : g + 1;
+      }
+    }
+    __syncthreads();
+    if (pass == 0) {
+      // exclusive scan of hist over the partitions -> soff; one global reservation per occupied partition
+      for (uint32_t start = 0; start < P; start += RS_THREADS) {
+        uint32_t p = start + threadIdx.x;
+        uint32_t c = p < P ? hist[p] : 0;
+        uint32_t total;
+        uint32_t ex = block_exclusive_scan(c, &total, smem);
+        uint32_t carry = carry_s;
+        if (p < P) {
+          soff[p] = carry + ex;
+          gbase[p] = c ? part_base[p] + atomicAdd(&part_cursor[p], c) : 0;
+          hist[p] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+      }
+    }
+  }
+  const uint32_t npairs = carry_s;
+  for (uint32_t i = threadIdx.x; i < npairs; i += RS_THREADS) {
+    uint2 pr = stage[i];
+    uint32_t p = pr.x >> lb;
+    pairs[gbase[p] + (i - soff[p])] = pr;
+  }
+}
+
+// one block per partition.  lens pass -> offsets + size classes -> placement pass.  Both passes keep four loads in
+// flight per thread.  The placement happens IN SHARED MEMORY (the partition's entries in bucket order, `cap` of
+// them; dynamic shared memory: 2^lb words + cap words) and goes out as one contiguous copy: 13.6 M scattered
+// 4-byte stores were what bounded both the old scatter kernel and the first form of this one (one L2 sector
+// transaction per entry: 358 us at 2^20 points x 13 windows).  Entries beyond `cap` (one huge partition:
+// structured scalars) are stored directly.
+constexpr uint32_t RS_FINISH_CAP = 8192;
+constexpr uint32_t RS_FINISH_THREADS = 512;
+static __global__ void __launch_bounds__(512) k_rs_finish(const uint2* __restrict__ pairs,
+                                                                 const uint32_t* __restrict__ part_base, uint32_t B,
+                                                                 uint32_t lb, uint32_t P, uint32_t* __restrict__ offsets,
+                                                                 uint32_t* __restrict__ entries,
+                                                                 uint32_t* __restrict__ bins /*[SIZE_BINS], zeroed*/,
+                                                                 uint32_t cap) {
+  extern __shared__ __align__(16) uint32_t rs_sm[];
+  uint32_t* cnt = rs_sm;  // [2^lb] bucket counts, then cursors
+  uint32_t* placed = rs_sm + (1u << lb);  // [cap]
+  __shared__ uint32_t shb[SIZE_BINS];
+  __shared__ uint32_t smem[33];
+  const uint32_t p = blockIdx.x;
+  const uint32_t beg = part_base[p], end = part_base[p + 1];
+  const uint32_t first = p << lb;
+  const uint32_t nbk = min(1u << lb, B - first);
+  const uint32_t count = end - beg;
+  for (uint32_t j = threadIdx.x; j < (1u << lb); j += blockDim.x) cnt[j] = 0;
+  for (uint32_t j = threadIdx.x; j < SIZE_BINS; j += blockDim.x) shb[j] = 0;
+  __syncthreads();
+  for (uint32_t i0 = 0; i0 < count; i0 += 4 * blockDim.x) {
+    uint32_t bk[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+      if (i < count) bk[u] = pairs[beg + i].x;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+      if (i < count) atomicAdd(&cnt[bk[u] - first], 1u);
+    }
+  }
+  __syncthreads();
+  // exclusive scan of cnt[0..2^lb): each thread owns a run of consecutive buckets
+  const uint32_t per = ((1u << lb) + blockDim.x - 1) / blockDim.x;  // <= 16
+  uint32_t v[16];
+  uint32_t s = 0;
+  for (uint32_t k = 0; k < per; k++) {
+    uint32_t j = threadIdx.x * per + k;
+    v[k] = j < nbk ? cnt[j] : 0;
+    s += v[k];
+  }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(s, &total, smem);
+  for (uint32_t k = 0; k < per; k++) {
+    uint32_t j = threadIdx.x * per + k;
+    if (j < nbk) {
+      offsets[first + j] = beg + ex;
+      cnt[j] = ex;  // becomes the bucket's cursor
+      uint32_t len = v[k];
+      if (len <= BIG_SEG) {
+        uint32_t full = len / ACC_SEG, rem = len % ACC_SEG;
+        if (full) atomicAdd(&shb[ACC_SEG], full);
+        if (rem || !full) atomicAdd(&shb[rem], 1u);
+      }
+    }
+    ex += v[k];
+  }
+  if (p == P - 1 && threadIdx.x == 0) offsets[B] = end;
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < SIZE_BINS; j += blockDim.x)
+    if (shb[j]) atomicAdd(&bins[j], shb[j]);
+  for (uint32_t i0 = 0; i0 < count; i0 += 4 * blockDim.x) {
+    uint2 pr[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+      if (i < count) pr[u] = pairs[beg + i];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+      if (i < count) {
+        uint32_t pos = atomicAdd(&cnt[pr[u].x - first], 1u);
+        if (pos < cap) placed[pos] = pr[u].y;
+        else entries[beg + pos] = pr[u].y;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t m = min(count, cap);
+  for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) entries[beg + i] = placed[i];
+}
+
 // Accumulation schedule.  The work item of k_accum is a SEGMENT: at most ACC_SEG consecutive
 // entries of one bucket.  Items are ordered by decreasing length, so the 32 items of a warp have
 // (almost) the same trip count and the longest start first.  A bucket of one segment is

@@ -328,3 +328,38 @@ def test_few_terms_sets(ctx):
     kk2 = [[rand_scalar(r) for _ in range(20)] for _ in range(2)]
     assert t.msm(b"".join(scalars_bytes(k) for k in kk2), n_sets=2, offset=30, n=20) == [G.msm(k, ps[30:50]).encode() for k in kk2]
     t.close()
+
+
+@pytest.mark.parametrize("kind", ["all_equal", "bits", "two_values"])
+def test_radix_sort_overfull_partition(ctx, kind):
+    """Structured scalars put more pairs into ONE partition of the two-pass radix sort than its shared-memory
+    placement holds (k_rs_finish stores the overflow directly), and into one bucket than a segment holds; the
+    points are k_i*B, so the expected sum is one fixed-base multiplication.  Windowed and plain tables, both sorts."""
+    import os
+
+    from mpc_bulletproof_b200 import Comb, Table
+
+    r = rng(91)
+    n = 40000
+    base = G.BASEPOINT.encode()
+    ks = [rand_scalar(r) for _ in range(n)]
+    pts = Comb(ctx, base).mul(scalars_bytes(ks))
+    if kind == "all_equal":
+        v = rand_scalar(r)
+        ss = [v] * n
+    elif kind == "bits":
+        ss = [r.getrandbits(1) for _ in range(n)]
+    else:
+        a, b = rand_scalar(r), G.L - 1
+        ss = [a if r.getrandbits(1) else b for _ in range(n)]
+    want = (sum(s * k for s, k in zip(ss, ks)) % G.L * G.BASEPOINT).encode()
+    plain, win = Table(ctx, pts), Table(ctx, pts).set_windows(0)
+    old = os.environ.get("BPG_SORT")
+    try:
+        assert plain.msm(scalars_bytes(ss))[0] == want
+        assert win.msm(scalars_bytes(ss))[0] == want
+    finally:
+        if old is None:
+            os.environ.pop("BPG_SORT", None)
+    plain.close()
+    win.close()
