@@ -15,7 +15,7 @@ static __global__ void __launch_bounds__(COMB_WINDOWS) k_table_comb_build(const 
   const uint32_t i = first + blockIdx.x;
   const int j = threadIdx.x;
   ge_niels q;
-  ge_load_niels(q, niels + (size_t)i * 24);
+  ge_load_niels(q, niels + (size_t)i * NIELS_WORDS);
   ge_ext p = ge_from_niels(q, false);
   for (int k = 0; k < 4 * j; k++) p = ge_dbl(p);
   // forward: the eight multiples, parked projectively (X | Y | Z = 24 words) in the entries they will become,

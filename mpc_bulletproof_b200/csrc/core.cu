@@ -321,7 +321,7 @@ static int table_from_dev(bpg_ctx* ctx, const uint8_t* d_comp, size_t n, bpg_tab
   t->ctx = ctx;
   t->n = n;
   t->niels = nullptr;
-  cudaError_t e = dev_alloc(ctx, &t->niels, std::max<size_t>(n, 1) * 96);
+  cudaError_t e = dev_alloc(ctx, &t->niels, std::max<size_t>(n, 1) * NIELS_BYTES);
   if (e != cudaSuccess) {
     delete t;
     ctx->last_cuda = (int)e;
@@ -367,7 +367,7 @@ extern "C" int bpg_table_upload(bpg_ctx* ctx, const uint8_t* comp, size_t n, bpg
 }
 
 extern "C" size_t bpg_table_len(const bpg_table* t) { return t ? t->n : 0; }
-extern "C" size_t bpg_table_entry_bytes(const bpg_table* t) { return t ? 96 : 0; }
+extern "C" size_t bpg_table_entry_bytes(const bpg_table* t) { return t ? NIELS_BYTES : 0; }
 extern "C" void bpg_table_free(bpg_table* t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
@@ -383,7 +383,7 @@ extern "C" int bpg_dev_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t of
   if (!ctx || !table || !d_out_ext || (!d_scalars && n) || n_sets <= 0) return BPG_ERR_ARG;
   if (offset + n > table->n) return BPG_ERR_CAPACITY;
   CK(cudaSetDevice(ctx->device));
-  return msm_enqueue(ctx, table->niels + offset * 24, n, (const uint32_t*)d_scalars, n * (size_t)n_sets, nullptr,
+  return msm_enqueue(ctx, table->niels + offset * NIELS_WORDS, n, (const uint32_t*)d_scalars, n * (size_t)n_sets, nullptr,
                      nullptr, n_sets, (uint32_t*)d_out_ext, table->win_c, table->n);
 }
 
@@ -515,7 +515,7 @@ extern "C" int bpg_msm_table(bpg_ctx* ctx, const bpg_table* table, size_t offset
   if (rc) return rc;
   uint32_t* d_ext = (uint32_t*)ctx->d_small;
   uint8_t* d_bytes = ctx->d_small + (size_t)n_sets * 128;
-  rc = msm_enqueue(ctx, table->niels + offset * 24, n, (const uint32_t*)ctx->d_stage, n * (size_t)n_sets, nullptr,
+  rc = msm_enqueue(ctx, table->niels + offset * NIELS_WORDS, n, (const uint32_t*)ctx->d_stage, n * (size_t)n_sets, nullptr,
                    nullptr, n_sets, d_ext, table->win_c, table->n, 0, 0, sbytes ? scalars_le : nullptr);
   if (rc) return rc;
   rc = bpg_dev_sum_encode(ctx, d_ext, 1, n_sets, d_bytes, nullptr);
@@ -632,7 +632,7 @@ extern "C" int bpg_msm_table_submit(bpg_ctx* ctx, const bpg_table* table, size_t
   CK(cudaStreamWaitEvent(ctx->stream, p->ev_up[k], 0));
   uint32_t* d_ext = (uint32_t*)p->d_res[k];
   uint8_t* d_bytes = p->d_res[k] + (size_t)n_sets * 128;
-  rc = msm_enqueue(ctx, table->niels + offset * 24, n, (const uint32_t*)p->d_sc[k], n * (size_t)n_sets, nullptr, nullptr,
+  rc = msm_enqueue(ctx, table->niels + offset * NIELS_WORDS, n, (const uint32_t*)p->d_sc[k], n * (size_t)n_sets, nullptr, nullptr,
                    n_sets, d_ext, table->win_c, table->n);
   if (rc) return rc;
   rc = bpg_dev_sum_encode(ctx, d_ext, 1, n_sets, d_bytes, nullptr);
@@ -681,7 +681,7 @@ extern "C" int bpg_msm_table_partial(bpg_ctx* ctx, const bpg_table* table, size_
   if (rc) return rc;
   if (sbytes) CK(cudaMemcpyAsync(ctx->d_stage, scalars_le, sbytes, cudaMemcpyHostToDevice, ctx->stream));
   uint32_t* d_ext = (uint32_t*)ctx->d_small;
-  rc = msm_enqueue(ctx, table->niels + offset * 24, n, (const uint32_t*)ctx->d_stage, n * (size_t)n_sets, nullptr,
+  rc = msm_enqueue(ctx, table->niels + offset * NIELS_WORDS, n, (const uint32_t*)ctx->d_stage, n * (size_t)n_sets, nullptr,
                    nullptr, n_sets, d_ext, table->win_c, table->n);
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->h_pinned, d_ext, (size_t)n_sets * 128, cudaMemcpyDeviceToHost, ctx->stream));
@@ -870,7 +870,7 @@ extern "C" int bpg_table_set_windows(bpg_ctx* ctx, bpg_table* t, int c) {
     return BPG_OK;
   }
   uint32_t* out = nullptr;
-  cudaError_t e = dev_alloc(ctx, &out, (size_t)W * t->n * 96);
+  cudaError_t e = dev_alloc(ctx, &out, (size_t)W * t->n * NIELS_BYTES);
   if (e != cudaSuccess) {
     ctx->last_cuda = (int)e;
     return BPG_ERR_NOMEM;
@@ -909,7 +909,7 @@ int table_alloc_plain(bpg_ctx* ctx, size_t n, bpg_table** out) {
   if (!t) return BPG_ERR_NOMEM;
   t->ctx = ctx;
   t->n = n;
-  cudaError_t e = dev_alloc(ctx, &t->niels, std::max<size_t>(n, 1) * 96);
+  cudaError_t e = dev_alloc(ctx, &t->niels, std::max<size_t>(n, 1) * NIELS_BYTES);
   if (e != cudaSuccess) {
     delete t;
     ctx->last_cuda = (int)e;
@@ -1045,7 +1045,7 @@ int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_adhoc, 
     size_t pos = n_adhoc;
     bool ok = true;
     for (int i = 0; i < nsegs && ok; i++) {
-      if (lens[i] && cudaMemcpyAsync(t->niels + pos * 24, tabs[i]->niels + offs[i] * 24, lens[i] * 96,
+      if (lens[i] && cudaMemcpyAsync(t->niels + pos * NIELS_WORDS, tabs[i]->niels + offs[i] * NIELS_WORDS, lens[i] * NIELS_BYTES,
                                      cudaMemcpyDeviceToDevice, s) != cudaSuccess)
         ok = false;
       pos += lens[i];

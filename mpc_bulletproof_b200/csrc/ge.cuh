@@ -48,6 +48,11 @@ BPG_DI fe fe_const(const uint32_t* k) {
 struct ge_ext {  // (X:Y:Z:T), T = XY/Z; all coordinates tight (< 2^255)
   fe X, Y, Z, T;
 };
+// Resident tables keep one affine-Niels entry (96 bytes of payload) per 128-byte line: an entry never straddles
+// two lines, so a gathered entry costs one line of HBM traffic (unpadded entries cost 196 bytes on average,
+// profiles/r1r_top_ncu_summary.json).  Comb tables (point_kernels.cuh, comb_kernels.cuh) stay packed.
+constexpr int NIELS_WORDS = 32;
+constexpr size_t NIELS_BYTES = 128;
 struct ge_niels {  // affine: (y+x, y-x, 2dxy)
   fe ypx, ymx, t2d;
 };

@@ -137,14 +137,14 @@ int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_tabl
       rc = table_alloc_plain(ctx, 2 * n + 1, &st->own_tab);
       if (rc) break;
       st->tab = st->own_tab;
-      if (cudaMemcpyAsync(st->own_tab->niels, G->niels + g_off * 24, n * 96, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
-          cudaMemcpyAsync(st->own_tab->niels + n * 24, H->niels + h_off * 24, n * 96, cudaMemcpyDeviceToDevice, s) !=
+      if (cudaMemcpyAsync(st->own_tab->niels, G->niels + g_off * NIELS_WORDS, n * NIELS_BYTES, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+          cudaMemcpyAsync(st->own_tab->niels + n * NIELS_WORDS, H->niels + h_off * NIELS_WORDS, n * NIELS_BYTES, cudaMemcpyDeviceToDevice, s) !=
               cudaSuccess) { rc = BPG_ERR_CUDA; break; }
       memcpy(ctx->h_pinned + 512, Q_host, 32);
       uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small);
       if (cudaMemsetAsync(bad, 0, 4, s) != cudaSuccess ||
           cudaMemcpyAsync(d_q, ctx->h_pinned + 512, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
-      launch_decode_to_niels(ctx, s, d_q, 1, st->own_tab->niels + 2 * n * 24, bad);
+      launch_decode_to_niels(ctx, s, d_q, 1, st->own_tab->niels + 2 * n * NIELS_WORDS, bad);
       uint32_t* hbad = reinterpret_cast<uint32_t*>(ctx->h_pinned);
       if (cudaMemcpyAsync(hbad, bad, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
           cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }

@@ -39,16 +39,16 @@ static __global__ void __launch_bounds__(ACC_THREADS, 1) k_accum(const uint32_t*
   if (beg < end) {
     uint32_t e = __ldg(entries + beg);
     ge_niels q;
-    ge_load_niels(q, table + (size_t)(e & ~ENTRY_NEG) * 24);
+    ge_load_niels(q, table + (size_t)(e & ~ENTRY_NEG) * NIELS_WORDS);
     uint32_t e_next = beg + 1 < end ? __ldg(entries + beg + 1) : 0;
     acc = ge_from_niels(q, (e & ENTRY_NEG) != 0);
     ge_niels qn;
-    if (beg + 1 < end) ge_load_niels(qn, table + (size_t)(e_next & ~ENTRY_NEG) * 24);
+    if (beg + 1 < end) ge_load_niels(qn, table + (size_t)(e_next & ~ENTRY_NEG) * NIELS_WORDS);
     for (uint32_t i = beg + 1; i < end; i++) {
       e = e_next;
       q = qn;
       e_next = i + 1 < end ? __ldg(entries + i + 1) : e;
-      ge_load_niels(qn, table + (size_t)(e_next & ~ENTRY_NEG) * 24);  // next point (or a harmless re-read)
+      ge_load_niels(qn, table + (size_t)(e_next & ~ENTRY_NEG) * NIELS_WORDS);  // next point (or a harmless re-read)
       acc = ge_madd(acc, q, (e & ENTRY_NEG) != 0);
     }
   }
@@ -109,7 +109,7 @@ static __global__ void __launch_bounds__(BIG_THREADS) k_accum_big(const uint32_t
     for (uint32_t i = beg + threadIdx.x; i < end; i += BIG_THREADS) {
       uint32_t e = __ldg(entries + i);
       ge_niels q;
-      ge_load_niels(q, table + (size_t)(e & ~ENTRY_NEG) * 24);
+      ge_load_niels(q, table + (size_t)(e & ~ENTRY_NEG) * NIELS_WORDS);
       acc = ge_madd(acc, q, (e & ENTRY_NEG) != 0);
     }
     ge_store_ext(pts[threadIdx.x], acc);

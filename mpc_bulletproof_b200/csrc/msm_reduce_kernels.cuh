@@ -233,7 +233,7 @@ static __global__ void __launch_bounds__(SMALL_THREADS) k_msm_small(const uint32
   const sc_recoded rec = sc_recode(k.v, bias4);
   // the point, one coordinate per lane
   ge_niels nq;
-  ge_load_niels(nq, table + (size_t)pid * 24);
+  ge_load_niels(nq, table + (size_t)pid * NIELS_WORDS);
   ge_ext pe = ge_from_niels(nq, false);
   ge4 P;
   P.c = q == 0 ? pe.X : (q == 1 ? pe.Y : (q == 2 ? pe.Z : pe.T));

@@ -245,7 +245,7 @@ static __global__ void __launch_bounds__(128) k_decode_to_niels(const uint8_t* _
     q = ge_niels_identity();
     atomicAdd(bad_count, 1u);
   }
-  ge_store_niels(table + (size_t)i * 24, q);
+  ge_store_niels(table + (size_t)i * NIELS_WORDS, q);
 }
 
 // extended -> compressed, one thread per point
@@ -401,8 +401,8 @@ static __global__ void __launch_bounds__(128) k_window_chain(const uint32_t* __r
   if (t >= count) return;
   uint32_t i = first + t;
   ge_niels q;
-  ge_load_niels(q, niels_in + (size_t)i * 24);
-  ge_store_niels(out + (size_t)i * 24, q);  // window 0
+  ge_load_niels(q, niels_in + (size_t)i * NIELS_WORDS);
+  ge_store_niels(out + (size_t)i * NIELS_WORDS, q);  // window 0
   ge_ext p;
   p.X = fe_sub(q.ypx, q.ymx);     // 2x
   p.Y = fe_add(q.ypx, q.ymx);     // 2y
@@ -432,7 +432,7 @@ static __global__ void __launch_bounds__(128) k_window_chain(const uint32_t* __r
     }
     inv = fe_mul(inv, e.Z);
     fe x = fe_mul(e.X, zi), y = fe_mul(e.Y, zi);
-    ge_store_niels(out + ((size_t)w * n_total + i) * 24, ge_affine_to_niels(x, y));
+    ge_store_niels(out + ((size_t)w * n_total + i) * NIELS_WORDS, ge_affine_to_niels(x, y));
   }
 }
 
