@@ -224,6 +224,7 @@ def run_reference(args, rank, world):
     r1cs = None
     if not args.no_r1cs:
         r1cs = cpu_r1cs_baseline(cbind, threads, args.r1cs_lg)
+        r1cs["config1_shuffle_k64"] = cpu_shuffle_baseline(cbind, threads)
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -661,7 +662,9 @@ def r1cs_timing(ctx, comb, lg, dev):
         rejected = True
     gens.close()
     pm, vm = sorted(pm[1:]), sorted(vm[1:])  # first run warms the pools
+    shuffle = shuffle_timing(ctx, synth)
     return {
+        "config1_shuffle_k64": shuffle,
         "multipliers": n,
         "circuit": "chain of squarings (reference benches/r1cs.rs:24-32)",
         "prove_ms": pm[len(pm) // 2],
@@ -703,6 +706,62 @@ def variable_base_timing(ctx, pts_bytes_dev, host_scalars, n, reps):
     }
 
 
+def shuffle_timing(ctx, synth):
+    """BASELINE.json config 1: the reference's shuffle bench (benches/shuffle.rs:147-236) at k = 64 through the
+    product's gadget module -- 128 committed values, two phases (n1 = 0, n2 = 126 multipliers, padded to 128)."""
+    import random
+
+    from mpc_bulletproof_b200 import gadgets as PG
+    from mpc_bulletproof_b200 import protocol as P
+
+    k = 64
+    gens = P.Gens(ctx, synth(128, 21), synth(128, 22), BASEPOINT, synth(1, 23))
+    r = random.Random(64)
+    inp = [r.randrange(2**64) for _ in range(k)]
+    outp = inp[:]
+    r.shuffle(outp)
+    blinds = [r.randrange(P.L) for _ in range(2 * k)]
+    pm, vm = [], []
+    for it in range(6):
+        t0 = time.perf_counter()
+        proof, ic, oc = PG.shuffle_prove(gens, P.Transcript, b"ShuffleBenchmark", inp, outp, blinds, rng_seed=100 + it)
+        pm.append((time.perf_counter() - t0) * 1e3)
+        t0 = time.perf_counter()
+        PG.shuffle_verify(gens, P.Transcript, b"ShuffleBenchmark", proof, ic, oc)
+        vm.append((time.perf_counter() - t0) * 1e3)
+    gens.close()
+    pm, vm = sorted(pm[1:]), sorted(vm[1:])
+    return {"k": k, "prove_ms": pm[len(pm) // 2], "verify_ms": vm[len(vm) // 2], "proof_bytes": len(proof),
+            "timed": "constraint-system construction (128 commitments, gadget) + prove / verify through the Python face of the C ABI"}
+
+
+def cpu_shuffle_baseline(cbind, threads: int) -> dict:
+    """config 1 on the host cores, group work only (as cpu_r1cs_baseline): 128 Pedersen commitments, the phase-2
+    commitment MSMs (253, 127, 253 terms), five T commitments and InnerProductProof::create at n = 128; verify:
+    one MSM of 2 * 128 + 128 + 13 + 14 terms."""
+    n, k = 128, 64
+    G = cbind.basepoint_mul(host_uniform_scalars(n, 0xB2000041), threads)
+    H = cbind.basepoint_mul(host_uniform_scalars(n, 0xB2000042), threads)
+    Q = cbind.basepoint_mul(host_uniform_scalars(1, 0xB2000043), threads)
+    s = [host_uniform_scalars(512, 0xB2000050 + i) for i in range(4)]
+    t0 = time.perf_counter()
+    for i in range(2 * k + 5):  # V_j and T_i: two-term commitments
+        cbind.msm(s[0][64 * (i % 8) : 64 * (i % 8) + 64], G[:64], 1)
+    cbind.msm(s[0][: 32 * 253], (G + H)[: 32 * 253], threads)
+    cbind.msm(s[1][: 32 * 127], G[: 32 * 127], threads)
+    cbind.msm(s[2][: 32 * 253], (G + H)[: 32 * 253], threads)
+    t_commit = time.perf_counter() - t0
+    us = host_uniform_scalars(7, 0xB2000060)
+    t0 = time.perf_counter()
+    cbind.ipp_create(Q, s[0][: 32 * n], s[1][: 32 * n], G, H, s[2][: 32 * n], s[3][: 32 * n], us, threads)
+    t_ipp = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cbind.msm((s[0] + s[1])[: 32 * 411], ((G + H) * 2)[: 32 * 411], threads)
+    t_verify = time.perf_counter() - t0
+    return {"k": k, "prove_ms": (t_commit + t_ipp) * 1e3, "verify_ms": t_verify * 1e3, "cores": threads, "kind": "port",
+            "what": "group work only (points decoded inside the calls)"}
+
+
 def cpu_baseline(args, pts_bytes_dev, scal_dev, n):
     """The C restatement of the reference CPU algorithm on a bounded sample, host cores."""
     try:
@@ -731,6 +790,8 @@ def cpu_baseline(args, pts_bytes_dev, scal_dev, n):
     ctx2.close()
     ipp = cpu_ipp_baseline(cbind, threads, pts, sc, 14)
     r1cs_cpu = None if args.no_r1cs else cpu_r1cs_baseline(cbind, threads, args.r1cs_lg)
+    if r1cs_cpu is not None:
+        r1cs_cpu["config1_shuffle_k64"] = cpu_shuffle_baseline(cbind, threads)
     return {
         "value": m / dt / 1e6,
         "unit": UNIT,

@@ -458,6 +458,9 @@ int bpg_prover_new(bpg_ctx* ctx, const bpg_gens* gens, bpg_transcript* t, bpg_cs
 int bpg_verifier_new(bpg_ctx* ctx, const bpg_gens* gens, bpg_transcript* t, bpg_cs** out); /* Verifier::new */
 void bpg_cs_free(bpg_cs* cs);
 int bpg_prover_commit(bpg_cs* cs, const uint8_t v[32], const uint8_t v_blinding[32], uint8_t V_out[32], bpg_var* var);
+/* n calls of bpg_prover_commit in one (same transcript, same variables; one batched fixed-base launch) */
+int bpg_prover_commit_batch(bpg_cs* cs, const uint8_t* v /* n*32 */, const uint8_t* v_blinding /* n*32 */, size_t n,
+                            uint8_t* V_out /* n*32 */, bpg_var* vars /* n */);
 int bpg_verifier_commit(bpg_cs* cs, const uint8_t V[32], bpg_var* var);
 int bpg_cs_commit_public(bpg_cs* cs, const uint8_t value[32], bpg_var* var);
 int bpg_cs_multiply(bpg_cs* cs, const bpg_term* left, size_t nl, const bpg_term* right, size_t nr, bpg_var out[3]);

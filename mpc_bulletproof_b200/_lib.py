@@ -66,6 +66,7 @@ _SIGNATURES = {
     "bpg_verifier_new": (_I, [_P, _P, _P, ctypes.POINTER(_P)]),
     "bpg_cs_free": (None, [_P]),
     "bpg_prover_commit": (_I, [_P, _P, _P, _P, ctypes.POINTER(_U64)]),
+    "bpg_prover_commit_batch": (_I, [_P, _P, _P, _SZ, _P, _P]),
     "bpg_verifier_commit": (_I, [_P, _P, ctypes.POINTER(_U64)]),
     "bpg_cs_commit_public": (_I, [_P, _P, ctypes.POINTER(_U64)]),
     "bpg_cs_multiply": (_I, [_P, ctypes.POINTER(Term), _SZ, ctypes.POINTER(Term), _SZ, ctypes.POINTER(_U64)]),

@@ -713,6 +713,26 @@ extern "C" int bpg_prover_commit(bpg_cs* cs, const uint8_t v[32], const uint8_t 
   *var = mkvar(V_COMMITTED, i);
   return BPG_OK;
 }
+// n calls of Prover::commit in one: ONE batched fixed-base launch for the n commitments, then the transcript
+// appends in order -- the same transcript and variables as committing one by one (prover.rs:319-329), without a
+// launch and a synchronisation per value (a shuffle of 64 values commits 128 of them).
+extern "C" int bpg_prover_commit_batch(bpg_cs* cs, const uint8_t* v, const uint8_t* v_blinding, size_t n, uint8_t* V_out,
+                                       bpg_var* vars) {
+  if (!cs || !cs->is_prover || (n && (!v || !v_blinding || !V_out || !vars))) return BPG_ERR_ARG;
+  std::vector<Scalar> sv(n), sb(n);
+  for (size_t i = 0; i < n; i++)
+    if (!Scalar::from_bytes(v + 32 * i, &sv[i]) || !Scalar::from_bytes(v_blinding + 32 * i, &sb[i])) return BPG_ERR_DECODE;
+  int rc = bpg_pedersen_commit(cs->ctx, cs->gens, v, v_blinding, n, V_out);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; i++) {
+    size_t j = cs->v.size();
+    cs->v.push_back(sv[i]);
+    cs->v_blinding.push_back(sb[i]);
+    cs->tr->append_point("V", V_out + 32 * i);
+    vars[i] = mkvar(V_COMMITTED, j);
+  }
+  return BPG_OK;
+}
 // verifier.rs:298-308
 extern "C" int bpg_verifier_commit(bpg_cs* cs, const uint8_t V[32], bpg_var* var) {
   if (!cs || cs->is_prover || !V || !var) return BPG_ERR_ARG;

@@ -142,10 +142,17 @@ int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points, const
   static const uint32_t target_parts = getenv("BPG_RS_PARTS") ? (uint32_t)atoi(getenv("BPG_RS_PARTS")) : RS_TARGET_PARTS;
   static const uint32_t fin_threads = getenv("BPG_RS_FIN_THREADS") ? (uint32_t)atoi(getenv("BPG_RS_FIN_THREADS")) : RS_FINISH_THREADS;
   static const uint32_t fin_cap = getenv("BPG_RS_FIN_CAP") ? (uint32_t)atoi(getenv("BPG_RS_FIN_CAP")) : RS_FINISH_CAP;
+  // partitions: about target_parts, more (up to RS_MAX_PARTS) when a partition's pairs would not fit the shared-memory
+  // placement of k_rs_finish; launches whose partitions cannot be made small enough (2^24 points and beyond) keep
+  // the counting sort
+  const uint64_t n_pairs = (uint64_t)n_terms * cfg.W;
+  uint32_t want_parts = target_parts;
+  while (want_parts < RS_MAX_PARTS && n_pairs / want_parts > (fin_cap * 7) / 8) want_parts <<= 1;
   uint32_t lb = 4;
-  while (lb < RS_MAX_LB && ((uint64_t)cfg.B >> lb) > target_parts) lb++;
+  while (lb < RS_MAX_LB && ((uint64_t)cfg.B >> lb) > want_parts) lb++;
   uint32_t P = (uint32_t)(((uint64_t)cfg.B + (1u << lb) - 1) >> lb);
-  const bool radix = !sort_atomic && P <= RS_MAX_PARTS && (size_t)RS_THREADS * cfg.W * 8 + (size_t)3 * P * 4 <= RS_SCATTER_SMEM;
+  const bool radix = !sort_atomic && P <= RS_MAX_PARTS && n_pairs / P <= (uint64_t)fin_cap * 2 &&
+                     (size_t)RS_THREADS * cfg.W * 8 + (size_t)3 * P * 4 <= RS_SCATTER_SMEM;
   size_t off = 0;
   // counts / partition counters and the schedule's control words are adjacent: ONE memset per launch
   size_t o_counts = off;  off += align_up(radix ? (size_t)2 * P * 4 : (size_t)cfg.B * 4);

@@ -370,6 +370,14 @@ class Prover(_CS):
         _raise(lib().bpg_prover_commit(self._h, sc_bytes(v), sc_bytes(v_blinding), V, ctypes.byref(var)))
         return V.raw, _var(var.value)
 
+    def commit_batch(self, values, blindings):
+        """len(values) calls of `commit` in one library call (one batched fixed-base launch)"""
+        n = len(values)
+        V = ctypes.create_string_buffer(32 * max(n, 1))
+        vs = (ctypes.c_uint64 * max(n, 1))()
+        _raise(lib().bpg_prover_commit_batch(self._h, _scs(values), _scs(blindings), n, V, vs))
+        return [(V.raw[32 * i : 32 * i + 32], _var(vs[i])) for i in range(n)]
+
     def prove(self, rng_seed: int | None = None, rng_bytes: bytes | None = None) -> bytes:
         """Prover::prove(bp_gens) -> R1CSProof bytes (reference src/r1cs/proof.rs:82-108).
         No argument: blindings from the transcript-bound RNG finalized with operating-system randomness

@@ -533,3 +533,38 @@ def test_os_entropy_prove_and_hardened_verify(env):
     it = iter(coms)
     stmt(ov, lambda cs, x: cs.commit(G.decode(next(it))), 9)
     ov.verify(O.R1CSProof.from_bytes(proofs[0]), bp, rng_bytes=bytes(range(32)))
+
+
+def test_config1_shuffle_k64_product_gadget(ctx):
+    """BASELINE.json config 1 (benches/shuffle.rs, k = 64) through the product's own gadget module
+    (mpc_bulletproof_b200/gadgets.py): same proof bytes as the oracle's prover running the oracle's gadget,
+    the product verifier and the oracle verifier accept, a non-permutation is rejected."""
+    from mpc_bulletproof_b200 import gadgets as PG
+    from mpc_bulletproof_b200 import protocol as P
+
+    k = 64
+    pc = O.PedersenGens()
+    bp = O.BulletproofGens(128, 1)
+    gens = P.Gens(ctx, points_bytes(bp.G(128)), points_bytes(bp.H(128)), pc.B.encode(), pc.B_blinding.encode())
+    r = random.Random(64)
+    inp = [r.randrange(2**64) for _ in range(k)]
+    outp = inp[:]
+    r.shuffle(outp)
+    blinds = [r.randrange(L) for _ in range(2 * k)]
+    proof, ic, oc = PG.shuffle_prove(gens, P.Transcript, b"ShuffleBenchmark", inp, outp, blinds, rng_seed=640)
+    otr = O.Transcript(b"ShuffleBenchmark")
+    otr.append_message(b"dom-sep", b"ShuffleProof")
+    otr.append_u64(b"k", k)
+    op = O.Prover(pc, otr)
+    oic = [op.commit(v, blinds[i]) for i, v in enumerate(inp)]
+    ooc = [op.commit(v, blinds[k + i]) for i, v in enumerate(outp)]
+    gadgets.shuffle_gadget(op, [v for _, v in oic], [v for _, v in ooc])
+    want = op.prove(bp, O.Blindings(640)).to_bytes()
+    assert proof == want and ic == [c.encode() for c, _ in oic]
+    PG.shuffle_verify(gens, P.Transcript, b"ShuffleBenchmark", proof, ic, oc)
+    bad_out = outp[:]
+    bad_out[3] += 1
+    bad, bic, boc = PG.shuffle_prove(gens, P.Transcript, b"ShuffleBenchmark", inp, bad_out, blinds, rng_seed=641)
+    with pytest.raises(P.VerificationError):
+        PG.shuffle_verify(gens, P.Transcript, b"ShuffleBenchmark", bad, bic, boc)
+    gens.close()

@@ -7,4 +7,6 @@ timeout 300 $TR --master-port 29502 tools/multi_gpu_check.py > gpurun_out/${tag}
 if [ "$N" = "8" ]; then
   timeout 400 $TR --master-port 29503 tools/batch_verify_bench.py 1024 16 4 > gpurun_out/${tag}_batch_verify_1024_n$N.json 2> gpurun_out/${tag}_batch_verify_1024_n$N.err; echo "batch rc=$?"
 fi
+timeout 400 $TR --master-port 29504 tools/sweep_multi.py 24 > gpurun_out/${tag}_sweep_strong_n$N.json 2> gpurun_out/${tag}_sweep_strong_n$N.err; echo "strong rc=$?"
+timeout 200 $TR --master-port 29505 bench.py --impl reference --gpus $N --steps 3 --warmup 1 --no-r1cs > gpurun_out/${tag}_bench_ref_n$N.json 2>/dev/null; echo "ref rc=$?"
 tail -c 400 gpurun_out/${tag}_bench_n$N.json

@@ -100,6 +100,8 @@ def sweep_ipp(ctx, comb, lgs):
         n = 1 << lg
         # generators resident as ONE windowed table [G | H] (what a BulletproofGens holds); Q is per call
         tG = tH = Table(ctx, Gb[: 32 * n] + Hb[: 32 * n]).set_windows(0)
+        if 2 * n * 49152 <= 32e9:  # combs (48 KB per generator), as bpg_gens_new builds them
+            tG.build_comb()
         h_off = n
         a, b, Gf, Hf = (host_scalars(n, 10 * lg + k) for k in range(4))
         cr, proof = [], None
@@ -186,6 +188,27 @@ def random_circuit(ctx, comb, lg=16, m=16):
             "verify_ms": round(med(vm[1:]), 3), "proof_bytes": len(proof)}
 
 
+def sweep_varbase(ctx, comb, max_lg):
+    """config 3 as the reference calls it on points it has never seen: bpg_msm on COMPRESSED points + scalars in
+    host memory (upload, decode, plain table, Pippenger with Horner), nothing precomputed; wall clock per call."""
+    rows = []
+    for lg in range(12, max_lg + 1, 2):
+        n = 1 << lg
+        pts = dev_points(ctx, comb, n, 300 + lg).cpu().pin_memory()
+        sc = dev_scalars(n, 400 + lg).cpu().pin_memory()
+        res = ctypes.create_string_buffer(32)
+        ts = []
+        for it in range(5 if lg <= 20 else 3):
+            t0 = time.perf_counter()
+            check(lib().bpg_msm(ctx._h, ctypes.c_void_p(sc.data_ptr()), ctypes.c_void_p(pts.data_ptr()), n, res))
+            ts.append((time.perf_counter() - t0) * 1e3)
+        rows.append({"lg_n": lg, "ms": round(min(ts), 4), "mpoints_s": round(n / min(ts) / 1e3, 1)})
+        print(rows[-1], file=sys.stderr, flush=True)
+        del pts, sc
+        torch.cuda.empty_cache()
+    return rows
+
+
 def main():
     what = (sys.argv[1] if len(sys.argv) > 1 else "msm,ipp,r1cs").split(",")
     max_lg = int(sys.argv[2]) if len(sys.argv) > 2 else 24
@@ -194,6 +217,8 @@ def main():
     out = {"gpu": torch.cuda.get_device_name(0)}
     if "msm" in what:
         out["msm"] = sweep_msm(ctx, comb, max_lg)
+    if "varbase" in what:
+        out["variable_base_msm"] = sweep_varbase(ctx, comb, min(max_lg, 22))
     if "ipp" in what:
         out["ipp"] = sweep_ipp(ctx, comb, [10, 12, 14, 16, 18])
     if "r1cs" in what:
