@@ -377,6 +377,19 @@ int bpg_stark_ipp_round_fold(bpg_stark_ipp* st, const uint8_t u[32], const uint8
 int bpg_stark_ipp_finish(bpg_stark_ipp* st, uint8_t a[32], uint8_t b[32]);
 void bpg_stark_ipp_free(bpg_stark_ipp* st);
 
+/* The fork's Stark-curve conventions that ARE in /root/reference (src/util.rs:252-289, src/generators.rs:80-125):
+ * legacy Keccak-256 (`merlin::keccak256`), hash_to_scalar = (low || keccak256(low)) as a 512-bit little-endian
+ * integer mod the group order (out: 32 bytes little-endian), and the generator chain
+ *     state <- keccak256(state);  G_i = hash_to_scalar(state) * generator
+ * from its initial state state0 = keccak256(pad_label("GeneratorsChain" || label)), which the caller forms
+ * (`pad_label` belongs to the un-vendored merlin fork).  skip = GeneratorsChain::fast_forward.  The hash chain
+ * runs on the host, the wide reductions and fixed-base multiplications on the device; out_xy: n x 64 bytes. */
+void bpg_keccak256(const uint8_t* data, size_t len, uint8_t out[32]);
+void bpg_stark_hash_to_scalar(const uint8_t low[32], uint8_t out[32]);
+int bpg_stark_gens_chain(bpg_ctx* ctx, const uint8_t state0[32], size_t skip, size_t n, uint8_t* out_xy /* n*64 */);
+/* building block of the chain: out[i] = ((wide[i] as a 512-bit little-endian integer) mod order) * generator */
+int bpg_stark_wide_mul_generator(bpg_ctx* ctx, const uint8_t* wide64 /* n*64 */, size_t n, uint8_t* out_xy /* n*64 */);
+
 /* ==== host mirror of the reference's protocol layer ==================================
  * C bindings of the C++ host code in mpc_bulletproof_b200/csrc/host/: the transcript,
  * the generators as resident tables, InnerProductProof and the R1CS Prover/Verifier with

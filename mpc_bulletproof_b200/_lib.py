@@ -157,6 +157,10 @@ _SIGNATURES = {
     "bpg_stark_table_free": (None, [_P]),
     "bpg_stark_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),
     "bpg_stark_msm": (_I, [_P, _P, _P, _SZ, _P]),
+    "bpg_keccak256": (None, [_P, _SZ, _P]),
+    "bpg_stark_hash_to_scalar": (None, [_P, _P]),
+    "bpg_stark_gens_chain": (_I, [_P, _P, _SZ, _SZ, _P]),
+    "bpg_stark_wide_mul_generator": (_I, [_P, _P, _SZ, _P]),
     "bpg_stark_ipp_begin": (_I, [_P, _P, _SZ, _P, _SZ, _SZ, _P, _P, _P, _P, _P, ctypes.POINTER(_P)]),
     "bpg_stark_ipp_rounds_left": (_SZ, [_P]),
     "bpg_stark_ipp_round_LR": (_I, [_P, _P, _P]),

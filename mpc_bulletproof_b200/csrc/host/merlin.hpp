@@ -72,6 +72,12 @@ class KeccakSponge {
   bool squeezing_;
 };
 inline KeccakSponge shake256() { return KeccakSponge(136, 0x1f); }
+// legacy Keccak-256 (pad 0x01): `merlin::keccak256` of the fork (reference src/generators.rs:84-123, src/util.rs:252-267)
+inline void keccak256(const uint8_t* d, size_t n, uint8_t out[32]) {
+  KeccakSponge k(136, 0x01);
+  k.absorb(d, n);
+  k.squeeze(out, 32);
+}
 inline void sha3_512(const uint8_t* d, size_t n, uint8_t out[64]) {
   KeccakSponge k(72, 0x06);
   k.absorb(d, n);

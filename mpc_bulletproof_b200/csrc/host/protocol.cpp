@@ -1247,3 +1247,61 @@ extern "C" int bpg_batch_verify(bpg_cs* const* verifiers, const uint8_t* const* 
   }
   return BPG_OK;
 }
+
+// ---------------------------------------------------------------- Stark-curve conventions of the mounted fork
+// (the part of its transcript / generator layer that IS in /root/reference: src/util.rs:252-289,
+// src/generators.rs:80-125; `pad_label` and the HashChainTranscript construction live in the un-vendored merlin fork)
+extern "C" void bpg_keccak256(const uint8_t* data, size_t len, uint8_t out[32]) { keccak256(data, len, out); }
+
+// hash_to_scalar (src/util.rs:252-267): (low || keccak256(low)) as a 512-bit little-endian integer mod the Stark
+// group order; out = the scalar, 32 bytes little-endian
+extern "C" void bpg_stark_hash_to_scalar(const uint8_t low[32], uint8_t out[32]) {
+  static const uint64_t N[4] = {0x1e66a241adc64d2fULL, 0xb781126dcae7b232ULL, 0xffffffffffffffffULL, 0x0800000000000010ULL};
+  uint8_t wide[64];
+  memcpy(wide, low, 32);
+  keccak256(low, 32, wide + 32);
+  uint64_t r[4] = {0, 0, 0, 0};
+  for (int bit = 511; bit >= 0; bit--) {  // r = 2 r + bit, reduced: r < N < 2^252, so 2 r + 1 < 2^253 never overflows
+    uint64_t in = (wide[bit >> 3] >> (bit & 7)) & 1;
+    for (int i = 3; i > 0; i--) r[i] = (r[i] << 1) | (r[i - 1] >> 63);
+    r[0] = (r[0] << 1) | in;
+    bool ge = true;
+    for (int i = 3; i >= 0; i--)
+      if (r[i] != N[i]) {
+        ge = r[i] > N[i];
+        break;
+      }
+    if (ge) {
+      unsigned __int128 borrow = 0;
+      for (int i = 0; i < 4; i++) {
+        unsigned __int128 t = (unsigned __int128)r[i] - N[i] - (uint64_t)borrow;
+        r[i] = (uint64_t)t;
+        borrow = (t >> 64) & 1;
+      }
+    }
+  }
+  for (int i = 0; i < 4; i++)
+    for (int b = 0; b < 8; b++) out[8 * i + b] = (uint8_t)(r[i] >> (8 * b));
+}
+
+extern "C" int bpg_stark_wide_mul_generator(bpg_ctx* ctx, const uint8_t* wide64, size_t n, uint8_t* out_xy);
+// GeneratorsChain (src/generators.rs:80-125) from its initial state state0 = keccak256(pad_label("GeneratorsChain" ||
+// label)) -- the caller forms it (pad_label is the merlin fork's).  Points [skip, skip + n): per point
+// state <- keccak256(state), scalar = hash_to_scalar(state), point = scalar * G; out = n x 64 bytes affine x || y.
+extern "C" int bpg_stark_gens_chain(bpg_ctx* ctx, const uint8_t state0[32], size_t skip, size_t n, uint8_t* out_xy) {
+  if (!ctx || !state0 || (n && !out_xy)) return BPG_ERR_ARG;
+  uint8_t st[32], nx[32];
+  memcpy(st, state0, 32);
+  for (size_t i = 0; i < skip; i++) {  // fast_forward (:92-100)
+    keccak256(st, 32, nx);
+    memcpy(st, nx, 32);
+  }
+  std::vector<uint8_t> wide(n * 64);
+  for (size_t i = 0; i < n; i++) {
+    keccak256(st, 32, nx);
+    memcpy(st, nx, 32);
+    memcpy(wide.data() + 64 * i, st, 32);
+    keccak256(st, 32, wide.data() + 64 * i + 32);
+  }
+  return bpg_stark_wide_mul_generator(ctx, wide.data(), n, out_xy);
+}

@@ -3,6 +3,7 @@
 #pragma once
 #include "stark_pt.cuh"
 #include "stark_pt4.cuh"
+#include "stark_sc.cuh"
 
 namespace bpg {
 
@@ -90,6 +91,69 @@ static __global__ void __launch_bounds__(128) k_stark_window_chain(const uint32_
     a.y = fp_mul(e.Y, fp_mul(ti, e.ZZ));
     sp_aff_store(out + ((size_t)w * n_total + i) * 16, a);
   }
+}
+
+
+// ---------------------------------------------------------------------------
+// The fork's generator chain (reference src/generators.rs:80-125): point = hash_to_scalar(state) * G with
+// hash_to_scalar(low) = (low || keccak256(low)) read as a 512-bit little-endian integer mod the group order
+// (src/util.rs:252-267).  The hash chain is sequential and runs on the host; the wide reduction and the
+// fixed-base multiplication run here.  The comb of G holds (d+1) 16^j G, j < 64, d < 8, affine.
+// ---------------------------------------------------------------------------
+static __global__ void __launch_bounds__(COMB_WINDOWS) k_stark_comb_build(const uint32_t* __restrict__ g_xy /*16 canonical words*/,
+                                                                          uint32_t* __restrict__ comb /*[64][8][16]*/,
+                                                                          uint32_t* __restrict__ bad) {
+  const int j = threadIdx.x;
+  uint32_t w[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) w[i] = g_xy[i];
+  sp_aff g;
+  if (!sp_from_affine_words(g, w)) {
+    if (j == 0) atomicAdd(bad, 1u);
+    return;
+  }
+  sp_xyzz p = sp_from_aff(g);
+  for (int k = 0; k < 4 * j; k++) p = sp_dbl(p);
+  sp_xyzz m = p;
+  for (int d = 0; d < 8; d++) {
+    if (d) m = sp_add(m, p);
+    sp_to_affine_words(w, m);
+    sp_aff q;
+    sp_from_affine_words(q, w);
+    sp_aff_store(comb + (size_t)(j * 8 + d) * 16, q);
+  }
+}
+// in: n x 64 bytes (low || high, little-endian); out: n x 64 bytes affine x || y of ((low + 2^256 high) mod order) * G
+static __global__ void __launch_bounds__(128) k_stark_chain_points(const uint32_t* __restrict__ wide, uint32_t n,
+                                                                   const uint32_t* __restrict__ comb, sc_bias bias4,
+                                                                   uint8_t* __restrict__ out_xy) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  sc lo, hi;
+  sc_load(lo, wide + (size_t)i * 16);
+  sc_load(hi, wide + (size_t)i * 16 + 8);
+  const sc rr = sc_const(BPG_K(KSS_RR));
+  sc one = sc_zero();
+  one.v[0] = 1;
+  // Montgomery form of lo + hi 2^256, then back: the canonical scalar
+  sc km = scs_add(scs_montmul(lo, rr), scs_montmul(scs_montmul(hi, rr), rr));
+  sc k = scs_montmul(km, one);
+  const sc_recoded r = sc_recode(k.v, bias4);
+  sp_xyzz acc = sp_identity();
+  for (int j = 0; j < COMB_WINDOWS; j++) {
+    int d = sc_digit(r, j, 4);
+    if (d != 0) {
+      int mag = d < 0 ? -d : d;
+      sp_aff q;
+      sp_aff_load(q, comb + (size_t)(j * 8 + mag - 1) * 16);
+      acc = sp_madd(acc, q, d < 0);
+    }
+  }
+  uint32_t w[16];
+  sp_to_affine_words(w, acc);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(out_xy + (size_t)i * 64);
+#pragma unroll
+  for (int t = 0; t < 16; t++) dst[t] = w[t];
 }
 
 }  // namespace bpg

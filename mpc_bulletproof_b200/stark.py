@@ -108,3 +108,26 @@ class StarkIpp:
             self.close()
         except Exception:
             pass
+
+
+def keccak256(data: bytes) -> bytes:
+    """legacy Keccak-256, the fork's `merlin::keccak256`"""
+    out = ctypes.create_string_buffer(32)
+    lib().bpg_keccak256(data, len(data), out)
+    return out.raw
+
+
+def hash_to_scalar(low: bytes) -> int:
+    """reference src/util.rs:252-267"""
+    assert len(low) == 32
+    out = ctypes.create_string_buffer(32)
+    lib().bpg_stark_hash_to_scalar(low, out)
+    return int.from_bytes(out.raw, "little")
+
+
+def gens_chain(ctx, state0: bytes, skip: int, n: int) -> bytes:
+    """points [skip, skip + n) of the fork's generator chain (src/generators.rs:80-125) from its initial state"""
+    assert len(state0) == 32
+    out = ctypes.create_string_buffer(64 * max(n, 1))
+    check(lib().bpg_stark_gens_chain(ctx._h, state0, skip, n, out))
+    return out.raw[: 64 * n]

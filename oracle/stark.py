@@ -101,3 +101,28 @@ def msm(scalars, points) -> Point:
     for k, p in zip(scalars, points):
         acc = acc + (k % N) * p
     return acc
+
+
+# ---- the fork's hashing conventions that live in /root/reference (src/util.rs:252-267, src/generators.rs:80-125)
+def hash_to_scalar(low: bytes) -> int:
+    """(low || keccak256(low)) read as a 512-bit little-endian integer, mod the group order (src/util.rs:252-267:
+    the bytes are reversed and handed to from_be_bytes_mod_order)."""
+    from .merlin import keccak256
+
+    assert len(low) == 32
+    return int.from_bytes(low + keccak256(low), "little") % N
+
+
+def gens_chain(state0: bytes, skip: int, n: int):
+    """GeneratorsChain (src/generators.rs:80-125) from its initial state keccak256(pad_label("GeneratorsChain" || label));
+    `pad_label` is the un-vendored merlin fork's, so the state is an input here."""
+    from .merlin import keccak256
+
+    st = state0
+    for _ in range(skip):  # fast_forward (:92-100)
+        st = keccak256(st)
+    out = []
+    for _ in range(n):
+        st = keccak256(st)
+        out.append(hash_to_scalar(st) * GENERATOR)
+    return out

@@ -207,3 +207,17 @@ def test_ipp_rounds(ctx, n):
     st.close()
     tG.close()
     tH.close()
+
+
+def test_fork_generator_chain(ctx):
+    """the fork's GeneratorsChain (reference src/generators.rs:80-125): keccak hash chain -> hash_to_scalar -> k * G,
+    from a given initial state (the `pad_label`ed seed is the un-vendored merlin fork's); with fast_forward."""
+    from mpc_bulletproof_b200 import stark as PS
+    from oracle.merlin import keccak256
+
+    state0 = keccak256(b"GeneratorsChain" + b"G" + (0).to_bytes(4, "little"))  # stand-in for pad_label(...)
+    want = S.gens_chain(state0, 0, 24)
+    got = PS.gens_chain(ctx, state0, 0, 24)
+    assert [got[64 * i : 64 * i + 64] for i in range(24)] == [p.encode() for p in want]
+    assert PS.gens_chain(ctx, state0, 7, 9) == b"".join(p.encode() for p in want[7:16])
+    assert PS.gens_chain(ctx, state0, 3, 0) == b""

@@ -48,3 +48,22 @@ def test_transcript_rng_matches_oracle():
     assert base != o.build_rng().rekey_with_witness_bytes(b"v_blinding", w1).finalize(bytes(32)).fill_bytes(64)
     o2 = O.Transcript(b"rng")
     assert base != o2.build_rng().rekey_with_witness_bytes(b"v_blinding", w1).finalize(ext).fill_bytes(64)
+
+
+def test_fork_keccak_and_hash_to_scalar():
+    """legacy Keccak-256 (known answer: keccak256("") = c5d246...a470) and the fork's
+    hash_to_scalar (reference src/util.rs:252-267): host mirror against the oracle."""
+    import random
+
+    from mpc_bulletproof_b200 import stark as PS
+    from oracle import stark as S
+
+    assert PS.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    r = random.Random(12)
+    from oracle.merlin import keccak256
+
+    for n in (1, 31, 32, 135, 136, 137, 300):
+        data = bytes(r.getrandbits(8) for _ in range(n))
+        assert PS.keccak256(data) == keccak256(data)
+    for low in [bytes(32), bytes([255] * 32)] + [bytes(r.getrandbits(8) for _ in range(32)) for _ in range(20)]:
+        assert PS.hash_to_scalar(low) == S.hash_to_scalar(low) < S.N

@@ -68,11 +68,11 @@ def launches(src, dst, command):
     ends = [i for i, (n, _) in enumerate(ls) if n.startswith("k_sum_encode") or n.startswith("k_exchange_sum_encode")]
     step = []
     for e in reversed(ends):
-        starts = [i for i in range(e) if ls[i][0] == "k_hist"]
+        starts = [i for i in range(e) if ls[i][0] in ("k_hist", "k_rs_hist")]
         if starts:
             # all k_hist launches that belong to this step (a piecewise upload launches several)
             s = starts[-1]
-            while s > 0 and ls[s - 1][0] == "k_hist":
+            while s > 0 and ls[s - 1][0] in ("k_hist", "k_rs_hist"):
                 s -= 1
             step = ls[s : e + 1]
             break
