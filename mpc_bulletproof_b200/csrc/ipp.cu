@@ -1,5 +1,7 @@
 // libbpgpu: inner-product argument, device-resident state, one MSM per round.
+#ifndef BPG_NO_OUTLINE
 #define BPG_FE_OUTLINE 1  // latency-bound kernels: products are calls, not 1.5 KB of inline code each
+#endif
 #include "internal.cuh"
 #include "ipp_kernels.cuh"
 #include "comb_kernels.cuh"

@@ -7,7 +7,7 @@ use std::os::raw::{c_char, c_int, c_void};
 macro_rules! opaque {
     ($($name:ident),*) => { $( #[repr(C)] pub struct $name { _private: [u8; 0] } )* };
 }
-opaque!(bpg_ctx, bpg_table, bpg_ipp, bpg_comb, bpg_r1cs_dev, bpg_stark_table, bpg_stark_ipp, bpg_peer);
+opaque!(bpg_ctx, bpg_table, bpg_ipp, bpg_comb, bpg_r1cs_dev, bpg_stark_table, bpg_stark_ipp, bpg_peer, bpg_msm_job);
 
 pub const BPG_OK: c_int = 0;
 pub const BPG_ERR_ARG: c_int = -1;
@@ -194,6 +194,44 @@ extern "C" {
     pub fn bpg_stark_ipp_round_fold(st: *mut bpg_stark_ipp, u: *const u8, u_inv: *const u8) -> c_int;
     pub fn bpg_stark_ipp_finish(st: *mut bpg_stark_ipp, a: *mut u8, b: *mut u8) -> c_int;
     pub fn bpg_stark_ipp_free(st: *mut bpg_stark_ipp);
+
+    // ---- round 2 additions ----------------------------------------------------------------
+    /// combs of a resident table: inner-product rounds without the bucket method (csrc/comb_kernels.cuh)
+    pub fn bpg_table_build_comb(ctx: *mut bpg_ctx, t: *mut bpg_table) -> c_int;
+    pub fn bpg_table_has_comb(t: *const bpg_table) -> c_int;
+    pub fn bpg_table_entry_bytes(t: *const bpg_table) -> usize;
+    /// a stream of host-buffer MSMs, two in flight: uploads behind kernels
+    pub fn bpg_msm_table_submit(
+        ctx: *mut bpg_ctx, t: *const bpg_table, offset: usize, n: usize, scalars: *const u8, n_sets: c_int,
+        job: *mut *mut bpg_msm_job,
+    ) -> c_int;
+    pub fn bpg_msm_job_wait(job: *mut bpg_msm_job, out: *mut u8) -> c_int;
+    /// open of additively shared points (the parties' compressed shares): out[s] = sum_p points[p][s]
+    pub fn bpg_points_sum(ctx: *mut bpg_ctx, points: *const u8, n_parts: c_int, n_sets: c_int, out: *mut u8) -> c_int;
+    /// SharedInnerProductProof::create, one party's local work (src/r1cs_mpc/mpc_inner_product.rs:52-228):
+    /// `lanes` (a, b) pairs (value shares, MAC shares) over public generators; cross terms from the fabric
+    pub fn bpg_ipp_begin_shares(
+        ctx: *mut bpg_ctx, shared: *const bpg_table, g_base: usize, h_base: usize, q_id: usize, q_mul: *const u8,
+        n: usize, lanes: c_int, g_factors: *const u8, h_factors: *const u8, a: *const u8, b: *const u8,
+        out: *mut *mut bpg_ipp,
+    ) -> c_int;
+    pub fn bpg_ipp_lanes(st: *const bpg_ipp) -> c_int;
+    pub fn bpg_ipp_len(st: *const bpg_ipp) -> usize;
+    pub fn bpg_ipp_read_ab(st: *mut bpg_ipp, a_out: *mut u8, b_out: *mut u8) -> c_int;
+    pub fn bpg_ipp_round_LR_shares(
+        st: *mut bpg_ipp, c_l: *const u8, c_r: *const u8, l_out: *mut u8, r_out: *mut u8,
+    ) -> c_int;
+    pub fn bpg_ipp_finish_shares(st: *mut bpg_ipp, a: *mut u8, b: *mut u8) -> c_int;
+    /// (A_I, A_O, S) with s_L, s_R expanded from a 256-bit key (ChaCha20): the production form
+    pub fn bpg_r1cs_dev_commit_keyed(
+        st: *mut bpg_r1cs_dev, gens: *const bpg_table, g_base: usize, h_base: usize, bb_id: usize, first: usize,
+        cnt: usize, a_l: *const c_void, a_r: *const c_void, a_o: *const c_void, vec_key: *const u8, blind3: *const u8,
+        out: *mut u8,
+    ) -> c_int;
+    /// the fork's Stark-curve hashing conventions (src/util.rs:252-267, src/generators.rs:80-125)
+    pub fn bpg_keccak256(data: *const u8, len: usize, out: *mut u8);
+    pub fn bpg_stark_hash_to_scalar(low: *const u8, out: *mut u8);
+    pub fn bpg_stark_gens_chain(ctx: *mut bpg_ctx, state0: *const u8, skip: usize, n: usize, out_xy: *mut u8) -> c_int;
 
     // ---- page-locked staging ---------------------------------------------------------------
     pub fn bpg_host_alloc(bytes: usize) -> *mut c_void;

@@ -34,6 +34,17 @@ __global__ void __launch_bounds__(128) k_tput(uint32_t* out, const uint32_t* in,
   fe_store(out + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * 8, r);
 }
 
+// ONE dependent chain per thread: the latency regime of the tree / encoding / comb-round kernels
+template <int V>
+__global__ void __launch_bounds__(128) k_lat(uint32_t* out, const uint32_t* in, int iters) {
+  fe a, b;
+  fe_load(b, in + 8);
+  fe_load(a, in + (threadIdx.x & 31) * 8);
+  a.v[0] ^= threadIdx.x + blockIdx.x * 131;
+  for (int it = 0; it < iters; it++) a = mulv<V>(a, b);
+  fe_store(out + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * 8, a);
+}
+
 template <typename F>
 static double time_ms(F f) {
   cudaEvent_t e0, e1;
@@ -85,6 +96,17 @@ int main() {
     double t1 = time_ms([&] { k_tput<1><<<blocks, 128>>>(out, in, iters); });
     double t2 = time_ms([&] { k_tput<2><<<blocks, 128>>>(out, in, iters); });
     printf("\"%s_Gmul_per_s\": {\"v0\": %.1f, \"v1\": %.1f, \"v2\": %.1f}, ", c.name, muls / t0 / 1e6, muls / t1 / 1e6, muls / t2 / 1e6);
+  }
+  // latency: one warp per SM sub-partition (148 blocks x 128 threads), one chain per thread
+  {
+    const int it2 = 4096;
+    double t0 = time_ms([&] { k_lat<0><<<sms, 128>>>(out, in, it2); });
+    double t1 = time_ms([&] { k_lat<1><<<sms, 128>>>(out, in, it2); });
+    double t2 = time_ms([&] { k_lat<2><<<sms, 128>>>(out, in, it2); });
+    printf("\"lone_warp_ns_per_mul\": {\"v0\": %.1f, \"v1\": %.1f, \"v2\": %.1f}, ", t0 * 1e6 / it2, t1 * 1e6 / it2, t2 * 1e6 / it2);
+    double u0 = time_ms([&] { k_lat<0><<<sms * 2, 128>>>(out, in, it2); });
+    double u2 = time_ms([&] { k_lat<2><<<sms * 2, 128>>>(out, in, it2); });
+    printf("\"two_warps_ns_per_mul\": {\"v0\": %.1f, \"v2\": %.1f}, ", u0 * 1e6 / it2, u2 * 1e6 / it2);
   }
   printf("\"ok\": %d}\n", ok);
   return 0;

@@ -1,4 +1,3 @@
-python -m pytest tests/test_gpu_ipp_modes.py -m gpu -x -q 2>&1 | tail -3
-for lg in 12 14 16 18; do
-  python tools/prove_profile.py $lg 1 > gpurun_out/r2g_prove_$lg.json 2>gpurun_out/r2g_prove_$lg.err
+for lg in 10 16; do
+  python tools/prove_profile.py $lg 1 > gpurun_out/r2n_prove_$lg.json 2>gpurun_out/r2n_prove_$lg.err
 done
