@@ -96,7 +96,7 @@ int bpg_table_window(const bpg_table* t); /* 0 = plain */
  * point, so that k P_i is 64 additions with no doublings, no buckets and no sort.  One-time cost (like
  * bpg_table_set_windows).  The inner-product rounds use the combs of a generator table for short vectors and
  * to materialise the folded generators of long ones (csrc/comb_kernels.cuh); bpg_gens_new builds them when
- * they fit BPG_COMB_MAX_GB (default 16) gigabytes. */
+ * they fit BPG_COMB_MAX_GB (default 32) gigabytes. */
 int bpg_table_build_comb(bpg_ctx* ctx, bpg_table* t);
 int bpg_table_has_comb(const bpg_table* t);
 size_t bpg_table_len(const bpg_table* t);

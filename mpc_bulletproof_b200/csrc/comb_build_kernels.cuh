@@ -89,8 +89,7 @@ static __global__ void __launch_bounds__(CB_THREADS, 4) k_comb_materialize(CombM
       id = (is_h ? M.h_id : M.g_id) + i;
     }
     const sc_recoded r = sc_recode(v.v, M.bias4);
-    ge_ext term = comb_windows<true>(M.comb + (size_t)id * COMB_ENTRIES * COMB_AFFINE_WORDS, r, (int)slice * per, (int)(slice + 1) * per);
-    acc = ge_add(acc, term);
+    acc = comb_windows<true>(M.comb + (size_t)id * COMB_ENTRIES * COMB_AFFINE_WORDS, r, (int)slice * per, (int)(slice + 1) * per, acc);
   }
   ge_store_ext(pts[threadIdx.x], acc);
   __syncwarp();

@@ -90,8 +90,8 @@ __device__ __forceinline__ ge_ext comb_apply(const ge_ext& acc, const comb_entry
   }
 }
 template <bool AFFINE>
-__device__ __forceinline__ ge_ext comb_windows(const uint32_t* __restrict__ comb_of_point, const sc_recoded& r, int j0, int j1) {
-  ge_ext acc = ge_identity();
+__device__ __forceinline__ ge_ext comb_windows(const uint32_t* __restrict__ comb_of_point, const sc_recoded& r, int j0, int j1,
+                                               ge_ext acc = ge_identity()) {
   comb_entry<AFFINE> cur = comb_fetch<AFFINE>(comb_of_point, r, j0);
   for (int j = j0; j < j1; j++) {
     comb_entry<AFFINE> nxt = comb_fetch<AFFINE>(comb_of_point, r, j + 1 < j1 ? j + 1 : j);

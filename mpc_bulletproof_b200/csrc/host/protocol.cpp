@@ -159,7 +159,7 @@ extern "C" int bpg_gens_new(bpg_ctx* ctx, const uint8_t* G, const uint8_t* H, si
     // combs for the inner-product rounds (48 KB per generator) when they fit the budget; without them the
     // rounds keep the bucket method throughout
     const char* e = getenv("BPG_COMB_MAX_GB");
-    double max_gb = e ? atof(e) : 16.0;
+    double max_gb = e ? atof(e) : 32.0;
     if ((double)(2 * capacity + 2) * 49152.0 <= max_gb * 1e9) {
       int rc2 = bpg_table_build_comb(ctx, g->table);
       if (rc2 && rc2 != BPG_ERR_NOMEM) rc = rc2;
