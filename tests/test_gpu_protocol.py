@@ -568,3 +568,54 @@ def test_config1_shuffle_k64_product_gadget(ctx):
     with pytest.raises(P.VerificationError):
         PG.shuffle_verify(gens, P.Transcript, b"ShuffleBenchmark", bad, bic, boc)
     gens.close()
+
+
+def test_verification_scalars_directly(ctx):
+    """`InnerProductProof::verification_scalars` (reference src/inner_product_proof.rs:254-310): the n-vector s that the
+    device forms by its closed form, checked VALUE BY VALUE against the oracle's serial recurrence rather than
+    through accept/reject: with (a, b) = (1, 0) and no other term, bpg_ipp_verify_msm returns sum_i s_i g_i G_i, and
+    with (0, 1) it returns sum_i s_{N-1-i} h_i H_i (= 1/s_i); distinct random generators make the sums injective
+    in s for all practical purposes."""
+    import ctypes
+
+    from mpc_bulletproof_b200 import Table
+    from mpc_bulletproof_b200._lib import lib
+    from mpc_bulletproof_b200.protocol import _raise
+
+    class Params(ctypes.Structure):
+        _fields_ = [("u_sq", (ctypes.c_uint32 * 8) * 32), ("allinv", ctypes.c_uint32 * 8), ("a", ctypes.c_uint32 * 8),
+                    ("b", ctypes.c_uint32 * 8), ("lg_n", ctypes.c_uint32), ("N", ctypes.c_uint32)]
+
+    def mont(x):
+        v = x * (1 << 256) % L
+        return (ctypes.c_uint32 * 8)(*[(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+
+    for n in (1, 2, 16, 64):
+        r = random.Random(500 + n)
+        lg = n.bit_length() - 1
+        bp = O.BulletproofGens(n, 1)
+        Gs, Hs = bp.G(n), bp.H(n)
+        # a proof-shaped object whose L, R are arbitrary valid points: only the challenges matter here
+        Ls = [rand_pt(r) for _ in range(lg)]
+        Rs = [rand_pt(r) for _ in range(lg)]
+        proof = O.InnerProductProof(Ls, Rs, 1, 0)
+        u_sq, u_inv_sq, s = proof.verification_scalars(n, O.Transcript(b"vs"))
+        allinv = s[0] if n > 1 else 1
+        Gf = [r.randrange(1, L) for _ in range(n)]
+        Hf = [r.randrange(1, L) for _ in range(n)]
+        t = Table(ctx, points_bytes(Gs + Hs))
+        for a, b in ((1, 0), (0, 1), (r.randrange(L), r.randrange(L))):
+            p = Params()
+            for j in range(lg):
+                p.u_sq[j] = mont(u_sq[j])
+            p.allinv, p.a, p.b, p.lg_n, p.N = mont(allinv), mont(a), mont(b), lg, n
+            out = ctypes.create_string_buffer(32)
+            _raise(lib().bpg_ipp_verify_msm(ctx._h, t._h, 0, t._h, n, None, None, 0, scalars_bytes(Gf), scalars_bytes(Hf),
+                                            ctypes.byref(p), out))
+            want = G.msm([a * s[i] * Gf[i] % L for i in range(n)] + [b * s[n - 1 - i] * Hf[i] % L for i in range(n)], Gs + Hs)
+            assert out.raw == want.encode(), (n, a, b)
+        t.close()
+
+
+def rand_pt(r):
+    return r.randrange(1, L) * G.BASEPOINT
