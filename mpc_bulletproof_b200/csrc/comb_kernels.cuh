@@ -180,13 +180,56 @@ struct CombFinal {
   const uint32_t* q_comb;      // comb of Q's base point
   sc_bias bias4;
 };
+// ---------------------------------------------------------------------------
+// The finish in QUAD form: four adjacent lanes own one point, one coordinate each (ge4.cuh).  Adding a comb entry
+// is two multiplication levels, the partial sums are loaded straight into quads and the block tree needs no
+// regrouping through shared memory: the finish is one dependent chain on a single warp, and its length is what
+// it costs (tools/lat_bench.cu: 1620 cycles per quad addition of a cached entry, 2350 per full quad addition,
+// against 3530 / 4540 for a thread's mixed / full addition).  The ACCUMULATION stays thread-per-unit: at a few
+// thousand terms it is bound by issue slots, and a thread's mixed addition costs 1.75 quad additions of work
+// for 4 lanes' worth of registers (measured: the quad form of the accumulation was 20 % slower at every size).
+// ---------------------------------------------------------------------------
+// lane q of the quad gets its operand of the comb entry of window j in "cached" layout
+// (lane0 Y-X, lane1 Y+X, lane2 2Z, lane3 2dT), negated for a negative digit, neutral for a zero digit
+template <bool AFFINE>
+__device__ __forceinline__ ge4 comb_fetch4(const uint32_t* __restrict__ comb_of_point, const sc_recoded& r, int j) {
+  constexpr int WORDS = AFFINE ? COMB_AFFINE_WORDS : COMB_CACHED_WORDS;
+  const int q = threadIdx.x & 3;
+  const int d = sc_digit(r, j, 4);
+  const int mag = d < 0 ? -d : d;
+  const bool neg = d < 0;
+  const uint32_t* e = comb_of_point + (size_t)(j * 8 + (mag ? mag - 1 : 0)) * WORDS;
+  int comp;
+  if (AFFINE) comp = q == 0 ? (neg ? 0 : 1) : (q == 1 ? (neg ? 1 : 0) : 2);  // words: y+x | y-x | 2dxy
+  else comp = q == 0 ? (neg ? 1 : 0) : (q == 1 ? (neg ? 0 : 1) : q);         // words: Y-X | Y+X | 2Z | 2dT
+  ge4 o;
+  fe_load(o.c, e + 8 * comp);
+  if (q == 3 && neg) o.c = fe_neg(o.c);
+  fe two = fe_zero();
+  two.v[0] = 2;
+  if (AFFINE && q == 2) o.c = two;
+  if (mag == 0) o.c = q < 2 ? fe_one() : (q == 2 ? two : fe_zero());
+  return o;
+}
+template <bool AFFINE>
+__device__ __forceinline__ ge4 comb_windows4(const uint32_t* __restrict__ comb_of_point, const sc_recoded& r, int j0, int j1, ge4 acc) {
+  ge4 cur = comb_fetch4<AFFINE>(comb_of_point, r, j0);
+  for (int j = j0; j < j1; j++) {
+    ge4 nxt = comb_fetch4<AFFINE>(comb_of_point, r, j + 1 < j1 ? j + 1 : j);
+    acc = ge4_add_cached(acc, cur);
+    cur = nxt;
+  }
+  return acc;
+}
+
+constexpr int CBQ_THREADS = 256;  // 64 quads
 template <bool Q_AFFINE>
-__global__ void __launch_bounds__(CB_THREADS) k_comb_final(CombFinal F, uint8_t* __restrict__ out_bytes /*[sets][32]*/,
-                                                           uint32_t* __restrict__ out_ext /*[sets][32] or null*/) {
-  __shared__ __align__(16) uint32_t pts[CB_THREADS][32];
-  __shared__ __align__(16) uint32_t sm[CB_THREADS / 32][32];
+__global__ void __launch_bounds__(CBQ_THREADS) k_comb_final(CombFinal F, uint8_t* __restrict__ out_bytes /*[sets][32]*/,
+                                                             uint32_t* __restrict__ out_ext /*[sets][32] or null*/) {
+  __shared__ __align__(16) uint32_t sm[CBQ_THREADS / 32][32];
+  __shared__ __align__(16) uint32_t pt0[32];
   __shared__ __align__(16) uint32_t g16[G16_WORDS];
-  __shared__ uint32_t csum[CB_THREADS][8];
+  __shared__ uint32_t csum[CBQ_THREADS / 32][8];
   const uint32_t set = blockIdx.x, lane_id = set >> 1, side = set & 1;
   // 1. the cross term of this side
   sc c = sc_zero();
@@ -198,30 +241,32 @@ __global__ void __launch_bounds__(CB_THREADS) k_comb_final(CombFinal F, uint8_t*
       c = sc_montmul(c, sc_to_mont(q));
     }
   } else {
-    for (uint32_t i = threadIdx.x; i < F.ncross; i += CB_THREADS) {
+    for (uint32_t i = threadIdx.x; i < F.ncross; i += CBQ_THREADS) {
       sc x;
       sc_load(x, F.cross + (size_t)i * 16 + 8 * side);
       c = sc_add(c, x);
     }
+    // warp tree by shuffles, then the eight warp sums
 #pragma unroll
-    for (int w = 0; w < 8; w++) csum[threadIdx.x][w] = c.v[w];
-    __syncthreads();
-    for (int half = CB_THREADS / 2; half >= 1; half >>= 1) {
-      if ((int)threadIdx.x < half) {
-        sc x, y;
+    for (int off = 16; off >= 1; off >>= 1) {
+      sc o;
 #pragma unroll
-        for (int w = 0; w < 8; w++) {
-          x.v[w] = csum[threadIdx.x][w];
-          y.v[w] = csum[threadIdx.x + half][w];
-        }
-        x = sc_add(x, y);
-#pragma unroll
-        for (int w = 0; w < 8; w++) csum[threadIdx.x][w] = x.v[w];
-      }
-      __syncthreads();
+      for (int w = 0; w < 8; w++) o.v[w] = __shfl_down_sync(BPG_FULL_MASK, c.v[w], off);
+      c = sc_add(c, o);
     }
+    if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int w = 0; w < 8; w++) c.v[w] = csum[0][w];
+      for (int w = 0; w < 8; w++) csum[threadIdx.x >> 5][w] = c.v[w];
+    }
+    __syncthreads();
+    c = sc_zero();
+#pragma unroll
+    for (int k = 0; k < CBQ_THREADS / 32; k++) {
+      sc x;
+#pragma unroll
+      for (int w = 0; w < 8; w++) x.v[w] = csum[k][w];
+      c = sc_add(c, x);
+    }
     sc f = sc_const(BPG_K(K_RR));  // the partial products carry R^-1
     if (F.q_mul) {
       sc q;
@@ -230,40 +275,36 @@ __global__ void __launch_bounds__(CB_THREADS) k_comb_final(CombFinal F, uint8_t*
     }
     c = sc_montmul(c, f);
   }
-  // 2. c * Q: thread j < 64 contributes window j; every thread also folds in its share of the partial sums
-  constexpr int QW = Q_AFFINE ? COMB_AFFINE_WORDS : COMB_CACHED_WORDS;
-  (void)QW;
-  ge_ext acc = ge_identity();
-  if (threadIdx.x < COMB_WINDOWS) {
-    const sc_recoded r = sc_recode(c.v, F.bias4);
-    acc = comb_windows<Q_AFFINE>(F.q_comb, r, (int)threadIdx.x, (int)threadIdx.x + 1);
+  // 2. c * Q: quad g contributes window g; every quad also folds in its share of the partial sums
+  const uint32_t g = threadIdx.x >> 2;
+  const sc_recoded r = sc_recode(c.v, F.bias4);
+  ge4 acc = comb_windows4<Q_AFFINE>(F.q_comb, r, (int)g, (int)g + 1, ge4_identity());
+  for (uint32_t base = 0; base < F.nparts; base += CBQ_THREADS / 4) {  // warp-uniform trip count (whole-warp shuffles inside)
+    const uint32_t i = base + g;
+    ge4 o = i < F.nparts ? ge4_load(F.parts + ((size_t)set * F.nparts + i) * 32) : ge4_identity();
+    acc = ge4_add(acc, o);
   }
-  for (uint32_t i = threadIdx.x; i < F.nparts; i += CB_THREADS) {
-    ge_ext o;
-    ge_load_ext(o, F.parts + ((size_t)set * F.nparts + i) * 32);
-    acc = ge_add(acc, o);
-  }
-  ge4 tot4 = comb_block_sum(acc, pts, sm);
+  ge4 tot4 = block_sum_quads(acc, sm);
   // 3. encode on warp 0 (whole-warp sixteen-lane form)
-  if (threadIdx.x < 4) ge4_store(pts[0], tot4);
+  if (threadIdx.x < 4) ge4_store(pt0, tot4);
   __syncthreads();
   if (threadIdx.x < 32) {
     ge_ext tot;
-    ge_load_ext(tot, pts[0]);
+    ge_load_ext(tot, pt0);
     if (out_ext && threadIdx.x == 0) ge_store_ext(out_ext + (size_t)set * 32, tot);
-    grp16 g;
-    g.sm = g16;
-    g.k = threadIdx.x & 15u;
-    g.half = (threadIdx.x >> 4) & 1u;
-    g.par = 0;
-    fe s = ge_encode16<true>(g, tot);
+    grp16 gg;
+    gg.sm = g16;
+    gg.k = threadIdx.x & 15u;
+    gg.half = (threadIdx.x >> 4) & 1u;
+    gg.par = 0;
+    fe s = ge_encode16<true>(gg, tot);
     if (threadIdx.x < 16) {
       uint32_t w = 0;
 #pragma unroll
-      for (int i = 0; i < 8; i++) w = (g.k >> 1) == (uint32_t)i ? s.v[i] : w;
-      w = (g.k & 1u) ? (w >> 16) : w;
-      out_bytes[(size_t)set * 32 + 2 * g.k] = (uint8_t)w;
-      out_bytes[(size_t)set * 32 + 2 * g.k + 1] = (uint8_t)(w >> 8);
+      for (int i = 0; i < 8; i++) w = (gg.k >> 1) == (uint32_t)i ? s.v[i] : w;
+      w = (gg.k & 1u) ? (w >> 16) : w;
+      out_bytes[(size_t)set * 32 + 2 * gg.k] = (uint8_t)w;
+      out_bytes[(size_t)set * 32 + 2 * gg.k + 1] = (uint8_t)(w >> 8);
     }
   }
 }

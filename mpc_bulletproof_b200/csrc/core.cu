@@ -105,6 +105,8 @@ extern "C" void bpg_free(bpg_ctx* ctx) {
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->d_small) cudaFree(ctx->d_small);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
+  if (ctx->d_terms) cudaFree(ctx->d_terms);
+  if (ctx->ev_terms) cudaEventDestroy(ctx->ev_terms);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

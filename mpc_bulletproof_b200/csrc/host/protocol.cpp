@@ -271,10 +271,12 @@ struct InnerProductProof {
   // the round loop of inner_product_proof.rs:49-193 around a device-resident state
   static int run_rounds(bpg_ipp* st, Transcript& tr, InnerProductProof* out) {
     int rc = BPG_OK;
+    StageTimer tm("ipp");
     while (bpg_ipp_rounds_left(st)) {
       Bytes32 L, R;
       rc = bpg_ipp_round_LR(st, L.data(), R.data());
       if (rc) return rc;
+      tm.lap("round L,R");
       out->L_vec.push_back(L);
       out->R_vec.push_back(R);
       tr.append_point("L", L.data());  // :119-120
@@ -286,10 +288,12 @@ struct InnerProductProof {
       u_inv.to_bytes(uib);
       rc = bpg_ipp_round_fold(st, ub, uib);
       if (rc) return rc;
+      tm.lap("challenge + fold");
     }
     uint8_t ab[32], bb[32];
     rc = bpg_ipp_finish(st, ab, bb);
     if (rc) return rc;
+    tm.lap("finish");
     Scalar::from_bytes(ab, &out->a);
     Scalar::from_bytes(bb, &out->b);
     return BPG_OK;
@@ -619,6 +623,11 @@ struct bpg_cs {
 
   // prover.rs:342-379 / verifier.rs:323-362: sum_q z^(q+1) * row_q, evaluated on the device as a
   // sparse product over the flat terms; wL, wR, wO stay in HBM, wV and wc come back
+  // the terms known so far start their way to the device (they depend on no challenge); constraints added
+  // later (second phase) change the length and flattened_constraints uploads the whole list itself
+  int prefetch_terms(bool after_commit_uploads) const {
+    return bpg_r1cs_terms_prefetch(ctx, t_code.size(), t_code.data(), t_row.data(), t_coeff.data(), after_commit_uploads);
+  }
   int flattened_constraints(bpg_r1cs_dev* dv, const Scalar& z, std::vector<Scalar>& wV, Scalar& wc) const {
     size_t n = num_multipliers(), m = is_prover ? v.size() : V.size();
     uint32_t z_pow[32][8];
@@ -967,6 +976,8 @@ static int prover_prove(bpg_cs* cs, bool keyed, uint64_t rng_seed, const uint8_t
   int rc = bpg_r1cs_dev_new(cs->ctx, next_pow2(std::max<size_t>(n1, 1)), &dv.p);
   if (rc) return rc;
   uint8_t c3[96], blind3[96];
+  rc = cs->prefetch_terms(n1 != 0);  // behind the witness rows of the first commitment when there is one
+  if (rc) return rc;
   tm.lap("blindings s_L s_R");
   i_b1.to_bytes(blind3);
   o_b1.to_bytes(blind3 + 32);
@@ -1114,6 +1125,8 @@ static int verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_
   Transcript& tr = *cs->tr;
   const bpg_gens* g = cs->gens;
   StageTimer tm("verify");
+  rc = cs->prefetch_terms(false);
+  if (rc) return rc;
   tr.append_u64("m", cs->V.size());
   size_t n1 = cs->num_vars;
   if (!tr.validate_and_append_point("A_I1", proof.A_I1.data())) return BPG_ERR_VERIFY;
@@ -1139,12 +1152,14 @@ static int verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_
   Scalar w = tr.challenge_scalar("w");
   std::vector<Scalar> wV;
   Scalar wc;
+  tm.lap("replay");
   DevGuard dv;
   rc = bpg_r1cs_dev_new(cs->ctx, std::max<size_t>(n, 1), &dv.p);
   if (rc) return rc;
+  tm.lap("state");
   rc = cs->flattened_constraints(dv.p, z, wV, wc);
   if (rc) return rc;
-  tm.lap("replay + flatten");
+  tm.lap("flatten");
   std::vector<Scalar> u_sq, u_inv_sq;
   Scalar allinv;
   rc = proof.ipp.verification_challenges(padded_n, tr, u_sq, u_inv_sq, allinv);

@@ -53,6 +53,17 @@ struct bpg_ctx {
   // staging for host-buffer calls
   uint8_t* d_stage = nullptr;
   size_t d_stage_cap = 0;
+  // constraint terms uploaded ahead of their use (bpg_r1cs_terms_prefetch): consumed once by bpg_r1cs_dev_flatten
+  uint8_t* d_terms = nullptr;
+  size_t d_terms_cap = 0;
+  const void* terms_src = nullptr;  // host array the resident copy was taken from (identity check)
+  size_t terms_n = 0;
+  cudaEvent_t ev_terms = nullptr;
+  struct {
+    const uint32_t *code = nullptr, *row = nullptr;
+    const void* coeff = nullptr;
+    size_t n = 0;
+  } terms_pending;  // a prefetch waiting for the next commitment's own uploads to be queued first
 };
 
 struct bpg_table {
@@ -91,6 +102,7 @@ static inline cudaError_t dev_alloc(bpg_ctx* ctx, T** p, size_t bytes) {
 void dev_free(bpg_ctx* ctx, void* p);
 constexpr size_t SMALL_BYTES = 1 << 16;
 void prof_mark(bpg_ctx* ctx, int phase);
+int terms_issue_pending(bpg_ctx* ctx);  // r1cs_dev.inc
 int ensure_ws(bpg_ctx* ctx, size_t bytes, int lane = 0);
 int ensure_stage(bpg_ctx* ctx, size_t bytes);
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }

@@ -271,7 +271,7 @@ static int ipp_comb_round(bpg_ipp* st, bool external_cross) {
   F.q_comb = st->cq_comb;
   F.bias4 = bias_for(4);
   prof_mark(ctx, BPG_PROF_ENCODE);
-  k_comb_final<true><<<sets, CB_THREADS, 0, s>>>(F, st->out_bytes, nullptr);
+  k_comb_final<true><<<sets, CBQ_THREADS, 0, s>>>(F, st->out_bytes, nullptr);
   LAUNCH_CHECK();
   prof_mark(ctx, -1);
   st->cross_ready = false;

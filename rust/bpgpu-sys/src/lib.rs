@@ -154,6 +154,11 @@ extern "C" {
         st: *mut bpg_r1cs_dev, n: usize, m: usize, n_terms: usize, t_code: *const u32, t_row: *const u32,
         t_coeff: *const c_void, z_pow: *const c_void, wv_out: *mut c_void,
     ) -> c_int;
+    /// early upload of the constraint terms (they depend on no challenge); consumed by the next flatten
+    pub fn bpg_r1cs_terms_prefetch(
+        ctx: *mut bpg_ctx, n_terms: usize, t_code: *const u32, t_row: *const u32, t_coeff: *const c_void,
+        after_commit_uploads: c_int,
+    ) -> c_int;
     /// t_1..t_6, src/util.rs:152-170
     pub fn bpg_r1cs_dev_poly_t(
         st: *mut bpg_r1cs_dev, n: usize, y_pow: *const c_void, y_inv_pow: *const c_void, t_out: *mut u8,

@@ -35,7 +35,7 @@ def main():
         p = P.Prover(gens, P.Transcript(b"bench r1cs"))
         build(p, val)
         t0 = time.perf_counter()
-        p.prove(99 + it)
+        proof = p.prove(99 + it)
         walls.append((time.perf_counter() - t0) * 1e3)
     out["prove_ms_unprofiled"] = sorted(walls[1:])
     for it in range(reps):
