@@ -28,6 +28,20 @@ namespace bpg {
 constexpr int COMB_AFFINE_WORDS = 24;  // (y+x, y-x, 2dxy), Z = 1
 constexpr int COMB_CACHED_WORDS = 32;  // (Y-X, Y+X, 2Z, 2dT)
 
+// Point operations of the latency-bound comb kernels.  A translation unit that defines BPG_GE_OUTLINE gets ONE
+// out-of-line copy of each (products inline inside it): a lone warp runs hot looped code 1.3-1.7x faster than
+// straight-line code it meets once, and an addition with inline products 20 % faster than one that calls each
+// product (profiles/r2_lone_warp_latency.json), so the kernels below call these from every site.
+#if defined(BPG_GE_OUTLINE) && defined(__CUDA_ARCH__)
+#define BPG_CB_FN static __device__ __noinline__
+#else
+#define BPG_CB_FN __device__ __forceinline__
+#endif
+BPG_CB_FN ge_ext cb_madd(ge_ext p, ge_niels q, bool neg) { return ge_madd(p, q, neg); }
+BPG_CB_FN ge_ext cb_add_cached(ge_ext p, fe ymx, fe ypx, fe z2, fe t2d) { return ge_add_cached(p, ymx, ypx, z2, t2d); }
+BPG_CB_FN ge4 cb_add4(ge4 p, ge4 q) { return ge4_add(p, q); }
+BPG_CB_FN ge4 cb_add4_cached(ge4 p, ge4 qc) { return ge4_add_cached(p, qc); }
+
 // acc +- entry
 template <bool AFFINE>
 __device__ __forceinline__ ge_ext comb_add(const ge_ext& acc, const uint32_t* __restrict__ e, bool neg) {
@@ -82,11 +96,11 @@ __device__ __forceinline__ ge_ext comb_apply(const ge_ext& acc, const comb_entry
     n.ypx = q.c[0];
     n.ymx = q.c[1];
     n.t2d = q.c[2];
-    return ge_madd(acc, n, q.neg);
+    return cb_madd(acc, n, q.neg);
   } else {
     fe nt = fe_neg(q.c[3]);
     fe a = fe_sel(q.neg, q.c[1], q.c[0]), b = fe_sel(q.neg, q.c[0], q.c[1]), t = fe_sel(q.neg, nt, q.c[3]);
-    return ge_add_cached(acc, a, b, q.c[2], t);
+    return cb_add_cached(acc, a, b, q.c[2], t);
   }
 }
 template <bool AFFINE>
@@ -103,15 +117,49 @@ __device__ __forceinline__ ge_ext comb_windows(const uint32_t* __restrict__ comb
 
 // every thread of the block holds one extended point; the block's sum lands in quad 0 of warp 0 (all threads call)
 constexpr int CB_THREADS = 128;
+// sum of one point per quad over the whole block -> quad 0 of warp 0 (block_sum_quads of ge4.cuh through cb_add4,
+// as loops: every level runs the same code).  Every thread of the block must call it.
+__device__ __forceinline__ ge4 comb_tree_quads(ge4 p, uint32_t (*sm)[32]) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll 1
+  for (int off = 16; off >= 4; off >>= 1) {
+    ge4 o;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o.c.v[i] = __shfl_down_sync(BPG_FULL_MASK, p.c.v[i], off);
+    p = cb_add4(p, o);
+  }
+  if (nw == 1) return p;
+  if (lane < 4) ge4_store(sm[wid], p);
+  __syncthreads();
+  if (wid == 0) {
+    const int quad = lane >> 2;
+    ge4 t = quad < nw ? ge4_load(sm[quad]) : ge4_identity();
+#pragma unroll 1
+    for (int k = 1; k < (nw + 7) / 8; k++) {  // more than eight warps: quad q also folds warps q + 8, q + 16, ...
+      const int w = quad + 8 * k;
+      t = cb_add4(t, w < nw ? ge4_load(sm[w]) : ge4_identity());
+    }
+#pragma unroll 1
+    for (int off = 16; off >= 4; off >>= 1) {
+      ge4 o;
+#pragma unroll
+      for (int i = 0; i < 8; i++) o.c.v[i] = __shfl_down_sync(BPG_FULL_MASK, t.c.v[i], off);
+      t = cb_add4(t, o);
+    }
+    p = t;
+  }
+  __syncthreads();
+  return p;
+}
 __device__ __forceinline__ ge4 comb_block_sum(const ge_ext& mine, uint32_t (*pts)[32] /*[CB_THREADS][32]*/,
                                               uint32_t (*sm)[32] /*[CB_THREADS/32][32]*/) {
   ge_store_ext(pts[threadIdx.x], mine);
   __syncthreads();
   int g = threadIdx.x >> 2;
   ge4 t = ge4_load(pts[4 * g]);
-#pragma unroll
-  for (int k = 1; k < 4; k++) t = ge4_add(t, ge4_load(pts[4 * g + k]));
-  return block_sum_quads(t, sm);
+#pragma unroll 1
+  for (int k = 1; k < 4; k++) t = cb_add4(t, ge4_load(pts[4 * g + k]));
+  return comb_tree_quads(t, sm);
 }
 
 // ---------------------------------------------------------------------------
@@ -216,7 +264,7 @@ __device__ __forceinline__ ge4 comb_windows4(const uint32_t* __restrict__ comb_o
   ge4 cur = comb_fetch4<AFFINE>(comb_of_point, r, j0);
   for (int j = j0; j < j1; j++) {
     ge4 nxt = comb_fetch4<AFFINE>(comb_of_point, r, j + 1 < j1 ? j + 1 : j);
-    acc = ge4_add_cached(acc, cur);
+    acc = cb_add4_cached(acc, cur);
     cur = nxt;
   }
   return acc;
@@ -282,9 +330,9 @@ __global__ void __launch_bounds__(CBQ_THREADS) k_comb_final(CombFinal F, uint8_t
   for (uint32_t base = 0; base < F.nparts; base += CBQ_THREADS / 4) {  // warp-uniform trip count (whole-warp shuffles inside)
     const uint32_t i = base + g;
     ge4 o = i < F.nparts ? ge4_load(F.parts + ((size_t)set * F.nparts + i) * 32) : ge4_identity();
-    acc = ge4_add(acc, o);
+    acc = cb_add4(acc, o);
   }
-  ge4 tot4 = block_sum_quads(acc, sm);
+  ge4 tot4 = comb_tree_quads(acc, sm);
   // 3. encode on warp 0 (whole-warp sixteen-lane form)
   if (threadIdx.x < 4) ge4_store(pt0, tot4);
   __syncthreads();

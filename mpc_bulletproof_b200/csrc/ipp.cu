@@ -1,7 +1,5 @@
 // libbpgpu: inner-product argument, device-resident state, one MSM per round.
-#ifndef BPG_NO_OUTLINE
-#define BPG_FE_OUTLINE 1  // latency-bound kernels: products are calls, not 1.5 KB of inline code each
-#endif
+#define BPG_GE_OUTLINE 1  // latency-bound kernels: one out-of-line copy of each point operation (comb_kernels.cuh)
 #include "internal.cuh"
 #include "ipp_kernels.cuh"
 #include "comb_kernels.cuh"

@@ -163,7 +163,7 @@ BPG_DI sc sc_montmul_inl(const sc& a, const sc& b) {
   return sc_cond_sub_l(t + 8);
 }
 // out of line in the latency-bound translation units (see fe.cuh, BPG_FE_OUTLINE)
-#if defined(BPG_FE_OUTLINE) && defined(__CUDA_ARCH__)
+#if (defined(BPG_FE_OUTLINE) || defined(BPG_GE_OUTLINE)) && defined(__CUDA_ARCH__)
 static __device__ __noinline__ sc sc_montmul_call(sc a, sc b) { return sc_montmul_inl(a, b); }
 __device__ __forceinline__ sc sc_montmul(const sc& a, const sc& b) { return sc_montmul_call(a, b); }
 #else
