@@ -142,6 +142,13 @@ int bpg_msm_table_indexed(bpg_ctx* ctx, const bpg_table* table, const uint32_t* 
  * src/r1cs/verifier.rs:516-547) and `InnerProductProof::verify`'s MSM (:353-368). */
 int bpg_msm_mixed(bpg_ctx* ctx, const uint8_t* adhoc_points, size_t n_adhoc, const bpg_table* const* tabs,
                   const size_t* offs, const size_t* lens, int nsegs, const uint8_t* scalars_le, uint8_t out[32]);
+/* The ad-hoc points of a coming bpg_msm_mixed / bpg_r1cs_dev_verify_msm / bpg_ipp_verify_msm, handed over before
+ * their scalars exist.  A verifier holds every point of its final check as soon as it has the proof (reference
+ * src/r1cs/verifier.rs:516-547), and the 252 doublings of a variable-base multiplication do not depend on the
+ * scalar: decoding, doubling chains and digit multiples run on an auxiliary stream while the caller replays its
+ * transcript; the later call that names the same encodings in the same order adds comb entries instead.  At most 256
+ * points (more: no effect).  An invalid encoding is reported by that later call (BPG_ERR_DECODE), as without this. */
+int bpg_adhoc_prefetch(bpg_ctx* ctx, const uint8_t* points, size_t n);
 
 /* Device-resident form: d_scalars (n_sets*n*32 bytes, 16-byte aligned) already in
  * HBM; writes n_sets extended points (4x8 uint32 limbs X,Y,Z,T = 128 bytes each)

@@ -114,6 +114,7 @@ _SIGNATURES = {
     "bpg_msm_job_wait": (_I, [_P, _P]),
     "bpg_msm_table_indexed": (_I, [_P, _P, _P, _P, _P, _SZ, _I, _P]),
     "bpg_msm_mixed": (_I, [_P, _P, _SZ, _P, _P, _P, _I, _P, _P]),
+    "bpg_adhoc_prefetch": (_I, [_P, _P, _SZ]),
     "bpg_dev_msm_table": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),
     "bpg_dev_sum_encode": (_I, [_P, _P, _I, _I, _P, _P]),
     "bpg_msm_table_partial": (_I, [_P, _P, _SZ, _SZ, _P, _I, _P]),

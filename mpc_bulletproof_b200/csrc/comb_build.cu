@@ -32,6 +32,20 @@ int comb_materialize(bpg_ctx* ctx, cudaStream_t s, const uint32_t* gen_comb, uin
   return BPG_OK;
 }
 
+// combs of a few ad-hoc points (a proof's points before their scalars exist): the doubling chains do not depend
+// on the scalars, so a verifier starts them as soon as it has the proof and its final MSM finds combs.
+int comb_from_points(bpg_ctx* ctx, cudaStream_t s, const uint8_t* d_comp, size_t n, uint32_t* ext, uint32_t* chain,
+                     uint32_t* comb, uint32_t* bad) {
+  k_decode_ext<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_comp, (uint32_t)n, ext, bad);
+  LAUNCH_CHECK();
+  k_comb_chain<<<(unsigned)((n * 4 + CB_THREADS - 1) / CB_THREADS), CB_THREADS, 0, s>>>(ext, (uint32_t)n, 1, chain);
+  LAUNCH_CHECK();
+  k_comb_multiples<<<(unsigned)((n * COMB_WINDOWS + CB_THREADS - 1) / CB_THREADS), CB_THREADS, 0, s>>>(
+      chain, (uint32_t)(n * COMB_WINDOWS), comb);
+  LAUNCH_CHECK();
+  return BPG_OK;
+}
+
 // ---------------------------------------------------------------------------
 // combs of a resident table (one-time, like bpg_table_set_windows): 64 x 8 affine-Niels multiples per point
 // ---------------------------------------------------------------------------

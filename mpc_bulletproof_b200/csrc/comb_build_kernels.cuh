@@ -156,4 +156,19 @@ static __global__ void __launch_bounds__(CB_THREADS) k_comb_multiples(const uint
   }
 }
 
+// compressed -> extended (Z = 1), one thread per point; invalid encodings count in *bad and become the identity
+static __global__ void __launch_bounds__(128) k_decode_ext(const uint8_t* __restrict__ comp, uint32_t n, uint32_t* __restrict__ ext,
+                                                    uint32_t* __restrict__ bad) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t buf[32];
+  for (int k = 0; k < 32; k++) buf[k] = comp[(size_t)i * 32 + k];
+  ge_ext p;
+  if (!ge_decode(p, buf)) {
+    p = ge_identity();
+    atomicAdd(bad, 1u);
+  }
+  ge_store_ext(ext + (size_t)i * 32, p);
+}
+
 }  // namespace bpg

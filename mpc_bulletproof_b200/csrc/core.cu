@@ -106,6 +106,7 @@ extern "C" void bpg_free(bpg_ctx* ctx) {
   if (ctx->d_small) cudaFree(ctx->d_small);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->d_terms) cudaFree(ctx->d_terms);
+  if (ctx->d_adhoc) cudaFree(ctx->d_adhoc);
   if (ctx->ev_terms) cudaEventDestroy(ctx->ev_terms);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
@@ -961,14 +962,54 @@ extern "C" int bpg_msm_table_indexed(bpg_ctx* ctx, const bpg_table* table, const
 // one MSM over ad-hoc (compressed) points followed by ranges of resident tables
 // ---------------------------------------------------------------------------
 // core of the mixed MSM: scalars for all `total` terms are already in d_scalars (device)
+// ---------------------------------------------------------------------------
+// Ad-hoc points ahead of their scalars.  A verifier knows every point of its final check as soon as it holds the
+// proof (verifier.rs:516-547: A_*, S_*, V_*, T_*, L_*, R_*), and the doublings of a variable-base multiplication do
+// not depend on the scalar: decoding, the 252-step doubling chain and the digit multiples run on the auxiliary
+// stream while the transcript is replayed and the constraints are flattened.  The MSM that later names the same
+// points (same encodings, same order) adds comb entries instead of running its own double-and-add.
+// ---------------------------------------------------------------------------
+extern "C" int bpg_adhoc_prefetch(bpg_ctx* ctx, const uint8_t* points, size_t n) {
+  if (!ctx || (n && !points)) return BPG_ERR_ARG;
+  ctx->adhoc_n = 0;
+  if (n == 0 || n > ADHOC_MAX_POINTS) return BPG_OK;  // larger sets keep the plain path
+  CK(cudaSetDevice(ctx->device));
+  if (n > ctx->adhoc_cap) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->aux_stream));
+    if (ctx->d_adhoc) cudaFree(ctx->d_adhoc);
+    ctx->d_adhoc = nullptr;
+    ctx->adhoc_cap = 0;
+    const size_t cap = std::max<size_t>(64, std::min<size_t>(ADHOC_MAX_POINTS, 2 * n));
+    CK(cudaMalloc(&ctx->d_adhoc, AdhocLayout(cap).total));
+    ctx->adhoc_cap = cap;
+  }
+  const AdhocLayout L(ctx->adhoc_cap);
+  uint8_t* d = ctx->d_adhoc;
+  cudaStream_t a = ctx->aux_stream;
+  // the buffer's only reader is the auxiliary stream itself (in order)
+  CK(cudaMemcpyAsync(d + L.comp, points, n * 32, cudaMemcpyHostToDevice, a));
+  CK(cudaMemsetAsync(d + L.flags, 0, 8, a));
+  int rc = comb_from_points(ctx, a, d + L.comp, n, (uint32_t*)(d + L.ext), (uint32_t*)(d + L.chain), (uint32_t*)(d + L.comb),
+                            (uint32_t*)(d + L.flags));
+  if (rc) return rc;
+  ctx->adhoc_src.assign(points, points + n * 32);
+  ctx->adhoc_n = n;
+  return BPG_OK;
+}
+bool adhoc_matches(const bpg_ctx* ctx, const uint8_t* host_points, size_t n) {
+  return n && ctx->adhoc_n == n && ctx->adhoc_src.size() == n * 32 && memcmp(ctx->adhoc_src.data(), host_points, n * 32) == 0;
+}
+
 int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_adhoc, const bpg_table* const* tabs,
                           const size_t* offs, const size_t* lens, int nsegs, const uint32_t* d_scalars, size_t total,
-                          uint8_t out[32], bool identity_only /*out: zeros iff the sum is the identity*/) {
+                          uint8_t out[32], bool identity_only /*out: zeros iff the sum is the identity*/,
+                          bool adhoc_resident /*combs of exactly these points are in ctx->d_adhoc*/) {
   cudaStream_t s = ctx->stream;
   uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small + 1024);
   uint32_t* d_ext = (uint32_t*)ctx->d_small;  // up to two partial sums
   uint8_t* d_bytes = ctx->d_small + 256;
-  CK(cudaMemsetAsync(bad, 0, 4, s));
+  CK(cudaMemsetAsync(bad, 0, 8, s));  // [0] encodings rejected here, [1] encodings rejected by bpg_adhoc_prefetch
   // Fast path: every range lies in ONE windowed table (the R1CS verifier: B, B_blinding, G, H of the
   // generator table).  The table terms run as an indexed MSM over the window multiples (no doublings)
   // on the launch stream while the few ad-hoc points (proof points: decoded, no precomputation) run
@@ -984,7 +1025,20 @@ int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_adhoc, 
     int n_parts = 1;
     do {
       if (dev_alloc(ctx, &d_ids, n_tab * 4) != cudaSuccess) { rc = BPG_ERR_NOMEM; break; }
-      if (n_adhoc) {
+      if (n_adhoc && adhoc_resident) {
+        const AdhocLayout L(ctx->adhoc_cap);
+        uint8_t* da = ctx->d_adhoc;
+        rc = BPG_ERR_CUDA;
+        if (cudaEventRecord(ctx->ev_fork, s) != cudaSuccess) break;  // the scalars were uploaded on the launch stream
+        if (cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0) != cudaSuccess) break;
+        rc = launch_comb_msm(ctx, ctx->aux_stream, (const uint32_t*)(da + L.comb), d_scalars, n_adhoc, (uint32_t*)(da + L.parts),
+                             (uint32_t*)(da + L.flags) + 1, d_ext + 32);
+        if (rc) break;
+        rc = BPG_ERR_CUDA;
+        if (cudaMemcpyAsync(bad + 1, da + L.flags, 4, cudaMemcpyDeviceToDevice, ctx->aux_stream) != cudaSuccess) break;
+        if (cudaEventRecord(ctx->ev_join, ctx->aux_stream) != cudaSuccess) break;
+        n_parts = 2;
+      } else if (n_adhoc) {
         rc = table_alloc_plain(ctx, n_adhoc, &ta);
         if (rc) break;
         rc = BPG_ERR_CUDA;
@@ -1022,10 +1076,10 @@ int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_adhoc, 
       }
       rc = BPG_ERR_CUDA;
       if (cudaMemcpyAsync(ctx->h_pinned, d_bytes, 32, cudaMemcpyDeviceToHost, s) != cudaSuccess) break;
-      if (cudaMemcpyAsync(ctx->h_pinned + 64, bad, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) break;
+      if (cudaMemcpyAsync(ctx->h_pinned + 64, bad, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess) break;
       cudaError_t se = cudaStreamSynchronize(s);
       if (se != cudaSuccess) { ctx->last_cuda = (int)se; break; }
-      if (*reinterpret_cast<uint32_t*>(ctx->h_pinned + 64)) { rc = BPG_ERR_DECODE; break; }
+      if (reinterpret_cast<uint32_t*>(ctx->h_pinned + 64)[0] | reinterpret_cast<uint32_t*>(ctx->h_pinned + 64)[1]) { rc = BPG_ERR_DECODE; break; }
       memcpy(out, ctx->h_pinned, 32);
       rc = BPG_OK;
     } while (0);
@@ -1094,7 +1148,8 @@ extern "C" int bpg_msm_mixed(bpg_ctx* ctx, const uint8_t* adhoc_points, size_t n
   uint8_t* d_pts = ctx->d_stage + total * 32;
   if (total) CK(cudaMemcpyAsync(d_sc, scalars_le, total * 32, cudaMemcpyHostToDevice, ctx->stream));
   if (n_adhoc) CK(cudaMemcpyAsync(d_pts, adhoc_points, n_adhoc * 32, cudaMemcpyHostToDevice, ctx->stream));
-  return msm_mixed_core(ctx, d_pts, n_adhoc, tabs, offs, lens, nsegs, (const uint32_t*)d_sc, total, out);
+  return msm_mixed_core(ctx, d_pts, n_adhoc, tabs, offs, lens, nsegs, (const uint32_t*)d_sc, total, out, false,
+                        adhoc_matches(ctx, adhoc_points, n_adhoc));
 }
 
 // ---------------------------------------------------------------------------

@@ -1127,6 +1127,34 @@ static int verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_
   StageTimer tm("verify");
   rc = cs->prefetch_terms(false);
   if (rc) return rc;
+  // every point of the final check (:516-547) is known now: [A_I1 A_O1 S1 A_I2 A_O2 S2 | V_* | T_* | L_* | R_*];
+  // their doubling chains start beside the transcript replay (bpg_adhoc_prefetch)
+  const size_t lg_n = proof.ipp.L_vec.size(), m = cs->V.size();
+  const size_t n_adhoc = 6 + m + 5 + 2 * lg_n;
+  std::vector<uint8_t> pts(n_adhoc * 32);
+  {
+    uint8_t* pp = pts.data();
+    auto putp = [&](const uint8_t* p) {
+      memcpy(pp, p, 32);
+      pp += 32;
+    };
+    putp(proof.A_I1.data());
+    putp(proof.A_O1.data());
+    putp(proof.S1.data());
+    putp(proof.A_I2.data());
+    putp(proof.A_O2.data());
+    putp(proof.S2.data());
+    for (size_t j = 0; j < m; j++) putp(cs->V[j].data());
+    putp(proof.T_1.data());
+    putp(proof.T_3.data());
+    putp(proof.T_4.data());
+    putp(proof.T_5.data());
+    putp(proof.T_6.data());
+    for (size_t j = 0; j < lg_n; j++) putp(proof.ipp.L_vec[j].data());
+    for (size_t j = 0; j < lg_n; j++) putp(proof.ipp.R_vec[j].data());
+  }
+  rc = bpg_adhoc_prefetch(cs->ctx, pts.data(), n_adhoc);
+  if (rc) return rc;
   tr.append_u64("m", cs->V.size());
   size_t n1 = cs->num_vars;
   if (!tr.validate_and_append_point("A_I1", proof.A_I1.data())) return BPG_ERR_VERIFY;
@@ -1176,32 +1204,23 @@ static int verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_
     r = tr.challenge_scalar("r");  // :506
   }
   Scalar xx = x * x, rxx = r * xx, xxx = x * xx;
-  size_t lg_n = proof.ipp.L_vec.size(), m = cs->V.size();
-  // ad-hoc points: [A_I1 A_O1 S1 A_I2 A_O2 S2 | V_* | T_* | L_* | R_*]
-  size_t n_adhoc = 6 + m + 5 + 2 * lg_n;
-  std::vector<uint8_t> pts(n_adhoc * 32);
+  // scalars of the ad-hoc points, in the order of `pts` above
   std::vector<Scalar> sc;
   sc.reserve(n_adhoc);
-  uint8_t* pp = pts.data();
-  auto putp = [&](const uint8_t* p, const Scalar& k) {
-    memcpy(pp, p, 32);
-    pp += 32;
-    sc.push_back(k);
-  };
-  putp(proof.A_I1.data(), x);
-  putp(proof.A_O1.data(), xx);
-  putp(proof.S1.data(), xxx);
-  putp(proof.A_I2.data(), u * x);
-  putp(proof.A_O2.data(), u * xx);
-  putp(proof.S2.data(), u * xxx);
-  for (size_t j = 0; j < m; j++) putp(cs->V[j].data(), wV[j] * rxx);
-  putp(proof.T_1.data(), r * x);
-  putp(proof.T_3.data(), rxx * x);
-  putp(proof.T_4.data(), rxx * xx);
-  putp(proof.T_5.data(), rxx * xxx);
-  putp(proof.T_6.data(), rxx * xx * xx);
-  for (size_t j = 0; j < lg_n; j++) putp(proof.ipp.L_vec[j].data(), u_sq[j]);
-  for (size_t j = 0; j < lg_n; j++) putp(proof.ipp.R_vec[j].data(), u_inv_sq[j]);
+  sc.push_back(x);
+  sc.push_back(xx);
+  sc.push_back(xxx);
+  sc.push_back(u * x);
+  sc.push_back(u * xx);
+  sc.push_back(u * xxx);
+  for (size_t j = 0; j < m; j++) sc.push_back(wV[j] * rxx);
+  sc.push_back(r * x);
+  sc.push_back(rxx * x);
+  sc.push_back(rxx * xx);
+  sc.push_back(rxx * xxx);
+  sc.push_back(rxx * xx * xx);
+  for (size_t j = 0; j < lg_n; j++) sc.push_back(u_sq[j]);
+  for (size_t j = 0; j < lg_n; j++) sc.push_back(u_inv_sq[j]);
   // y^-i, s, delta = <y^-n o w_R, w_L> (:468-479), g_scalars (:487-491), h_scalars (:493-501) and the
   // scalar of B = w (t_x - a b) + r (x^2 (w_c + delta) - t_x) = c0 + c1 delta (:527-529): device
   bpg_verify_params vp;

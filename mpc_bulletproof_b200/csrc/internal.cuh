@@ -59,6 +59,11 @@ struct bpg_ctx {
   const void* terms_src = nullptr;  // host array the resident copy was taken from (identity check)
   size_t terms_n = 0;
   cudaEvent_t ev_terms = nullptr;
+  // combs of ad-hoc points built ahead of their MSM (bpg_adhoc_prefetch): [comp | bad, ticket | parts | ext | chain | comb]
+  uint8_t* d_adhoc = nullptr;
+  size_t adhoc_cap = 0;            // points the buffer holds
+  size_t adhoc_n = 0;              // points of the resident combs (0: none)
+  std::vector<uint8_t> adhoc_src;  // their encodings (identity check)
   struct {
     const uint32_t *code = nullptr, *row = nullptr;
     const void* coeff = nullptr;
@@ -127,7 +132,29 @@ int msm_enqueue(bpg_ctx* ctx, const uint32_t* table_base, size_t n_points, const
 // one sum over ad-hoc compressed points + ranges of resident tables, scalars already on the device (core.cu)
 int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_adhoc, const bpg_table* const* tabs,
                    const size_t* offs, const size_t* lens, int nsegs, const uint32_t* d_scalars, size_t total,
-                   uint8_t out[32], bool identity_only = false);
+                   uint8_t out[32], bool identity_only = false, bool adhoc_resident = false);
+// ad-hoc points with combs built ahead (bpg_adhoc_prefetch, core.cu): layout of ctx->d_adhoc for `cap` points
+constexpr size_t ADHOC_MAX_POINTS = 256;
+constexpr size_t ADHOC_PARTS = 64;
+struct AdhocLayout {
+  size_t comp, flags, parts, ext, chain, comb, total;
+  explicit AdhocLayout(size_t cap) {
+    comp = 0;
+    flags = align_up(cap * 32);                       // [0] bad encodings, [1] ticket of the comb MSM
+    parts = flags + 256;
+    ext = parts + ADHOC_PARTS * 128;
+    chain = ext + align_up(cap * 128);
+    comb = chain + align_up(cap * 64 * 128);
+    total = comb + cap * (size_t)512 * 128;
+  }
+};
+bool adhoc_matches(const bpg_ctx* ctx, const uint8_t* host_points, size_t n);
+// comb_build.cu: decode, doubling chains and cached combs of `n` compressed points
+int comb_from_points(bpg_ctx* ctx, cudaStream_t s, const uint8_t* d_comp, size_t n, uint32_t* ext, uint32_t* chain,
+                     uint32_t* comb, uint32_t* bad);
+// ipp.cu: sum_k scalars[k] * P_k from cached combs (canonical scalars on the device), one extended point
+int launch_comb_msm(bpg_ctx* ctx, cudaStream_t s, const uint32_t* comb_cached, const uint32_t* d_scalars, size_t n,
+                    uint32_t* parts /*ADHOC_PARTS x 32 words*/, uint32_t* ticket, uint32_t* out_ext);
 cudaError_t msm_kernels_init();
 cudaError_t msm_sort_kernels_init();  // msm.cu  // msm.cu: function attributes of the pipeline kernels
 // point-level kernels launched on behalf of other translation units (core.cu)

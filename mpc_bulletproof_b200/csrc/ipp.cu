@@ -3,8 +3,27 @@
 #include "internal.cuh"
 #include "ipp_kernels.cuh"
 #include "comb_kernels.cuh"
+#include "comb_msm_kernels.cuh"
 
 using namespace bpg;
+
+int launch_comb_msm(bpg_ctx* ctx, cudaStream_t s, const uint32_t* comb_cached, const uint32_t* d_scalars, size_t n,
+                    uint32_t* parts, uint32_t* ticket, uint32_t* out_ext) {
+  CombMsm M;
+  M.comb = comb_cached;
+  M.scalars = d_scalars;
+  M.n = (uint32_t)n;
+  M.wsplit = 16;  // four windows per thread: a few hundred threads per term set, a handful of blocks
+  while (M.wsplit > 1 && (n * M.wsplit + CB_THREADS - 1) / CB_THREADS > ADHOC_PARTS) M.wsplit >>= 1;
+  M.bias4 = bias_for(4);
+  M.parts = parts;
+  M.ticket = ticket;
+  const unsigned grid = (unsigned)((n * M.wsplit + CB_THREADS - 1) / CB_THREADS);
+  if (grid > ADHOC_PARTS) return BPG_ERR_ARG;
+  k_comb_msm<<<grid, CB_THREADS, 0, s>>>(M, out_ext);
+  LAUNCH_CHECK();
+  return BPG_OK;
+}
 
 // ---------------------------------------------------------------------------
 // inner-product argument: device-resident state, one MSM per round

@@ -89,6 +89,8 @@ extern "C" {
         ctx: *mut bpg_ctx, adhoc_points: *const u8, n_adhoc: usize, tabs: *const *const bpg_table, offs: *const usize,
         lens: *const usize, nsegs: c_int, scalars: *const u8, out: *mut u8,
     ) -> c_int;
+    /// the same ad-hoc points ahead of their scalars: doubling chains beside the transcript replay
+    pub fn bpg_adhoc_prefetch(ctx: *mut bpg_ctx, points: *const u8, n: usize) -> c_int;
     /// one rank's / one MPC party's partial sums: n_sets x 128 bytes (X|Y|Z|T)
     pub fn bpg_msm_table_partial(
         ctx: *mut bpg_ctx, t: *const bpg_table, offset: usize, n: usize, scalars: *const u8, n_sets: c_int,
