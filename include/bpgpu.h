@@ -330,14 +330,27 @@ void bpg_host_free(void* p);
  * receives wV[0..m) and w_c, (m + 1) x 32 bytes of Montgomery limbs. */
 int bpg_r1cs_dev_flatten(bpg_r1cs_dev* st, size_t n, size_t m, size_t n_terms, const uint32_t* t_code,
                          const uint32_t* t_row, const void* t_coeff, const void* z_pow, void* wv_out);
+/* The same with the terms in two lists.  Most coefficients of an R1CS are +1 or -1 (copies, differences, booleans):
+ * such a term carries no coefficient -- bit 31 of its code says -1 -- and costs 8 bytes on the bus instead of 40
+ * and no multiplication in the kernel.  `t_*` are the general terms as above, `u_*` the unit ones. */
+typedef struct {
+  size_t n_terms;
+  const uint32_t* t_code;
+  const uint32_t* t_row;
+  const void* t_coeff;
+  size_t n_unit;
+  const uint32_t* u_code;
+  const uint32_t* u_row;
+} bpg_terms;
+int bpg_r1cs_dev_flatten_terms(bpg_r1cs_dev* st, size_t n, size_t m, const bpg_terms* terms, const void* z_pow,
+                               void* wv_out);
 /* The terms depend on no challenge: handing them over when the circuit is built lets their upload run on an
  * auxiliary stream beside the commitments (prover.rs:465-494) or the transcript replay (verifier.rs:400-440).
- * The next bpg_r1cs_dev_flatten on this context whose arrays are these (same pointer and length, unchanged
- * contents) uses the resident copy; any other uploads its own.  Arrays from bpg_host_alloc copy at bus rate.
- * after_commit_uploads != 0 queues the copy behind the witness rows of the next bpg_r1cs_dev_commit* (they are
- * on the prover's critical path and share the bus). */
-int bpg_r1cs_terms_prefetch(bpg_ctx* ctx, size_t n_terms, const uint32_t* t_code, const uint32_t* t_row,
-                            const void* t_coeff, int after_commit_uploads);
+ * The next bpg_r1cs_dev_flatten_terms on this context that names the same arrays (same pointers and lengths,
+ * unchanged contents) uses the resident copy; any other uploads its own.  Arrays from bpg_host_alloc copy at bus
+ * rate.  after_commit_uploads != 0 queues the copy behind the witness rows of the next bpg_r1cs_dev_commit* (they
+ * are on the prover's critical path and share the bus). */
+int bpg_r1cs_terms_prefetch(bpg_ctx* ctx, const bpg_terms* terms, int after_commit_uploads);
 /* t_1..t_6 (util.rs:152-170) from the resident vectors.  t_out: six canonical scalars. */
 int bpg_r1cs_dev_poly_t(bpg_r1cs_dev* st, size_t n, const void* y_pow, const void* y_inv_pow, uint8_t t_out[192]);
 /* The verifier's mega-MSM (verifier.rs:516-547) with g_scalars, h_scalars and delta computed on

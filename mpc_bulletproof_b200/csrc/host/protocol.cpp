@@ -510,6 +510,7 @@ struct bpg_cs {
   // code = kind << 28 | index, Montgomery coefficient -- uploaded as is for the device flattening
   PinnedVec<uint32_t> t_code, t_row;
   PinnedVec<Scalar> t_coeff;
+  PinnedVec<uint32_t> u_code, u_row;  // terms with coefficient +1 / -1 (bit 31 of the code): no coefficient stored
   size_t n_rows = 0;
   // prover
   PinnedVec<Scalar> a_L, a_R, a_O;
@@ -541,10 +542,17 @@ struct bpg_cs {
     return tot;
   }
   void add_constraint(const LinComb& lc) {
+    static const Scalar one = Scalar::one(), minus_one = -Scalar::one();
     for (auto& t : lc) {
-      t_code.push_back(((uint32_t)var_kind(t.var) << 28) | (uint32_t)var_idx(t.var));
-      t_row.push_back((uint32_t)n_rows);
-      t_coeff.push_back(t.coeff);
+      const uint32_t code = ((uint32_t)var_kind(t.var) << 28) | (uint32_t)var_idx(t.var);
+      if (t.coeff == one || t.coeff == minus_one) {
+        u_code.push_back(t.coeff == one ? code : code | 0x80000000u);
+        u_row.push_back((uint32_t)n_rows);
+      } else {
+        t_code.push_back(code);
+        t_row.push_back((uint32_t)n_rows);
+        t_coeff.push_back(t.coeff);
+      }
     }
     n_rows++;
   }
@@ -625,8 +633,20 @@ struct bpg_cs {
   // sparse product over the flat terms; wL, wR, wO stay in HBM, wV and wc come back
   // the terms known so far start their way to the device (they depend on no challenge); constraints added
   // later (second phase) change the length and flattened_constraints uploads the whole list itself
+  bpg_terms terms() const {
+    bpg_terms T;
+    T.n_terms = t_code.size();
+    T.t_code = t_code.data();
+    T.t_row = t_row.data();
+    T.t_coeff = t_coeff.data();
+    T.n_unit = u_code.size();
+    T.u_code = u_code.data();
+    T.u_row = u_row.data();
+    return T;
+  }
   int prefetch_terms(bool after_commit_uploads) const {
-    return bpg_r1cs_terms_prefetch(ctx, t_code.size(), t_code.data(), t_row.data(), t_coeff.data(), after_commit_uploads);
+    bpg_terms T = terms();
+    return bpg_r1cs_terms_prefetch(ctx, &T, after_commit_uploads);
   }
   int flattened_constraints(bpg_r1cs_dev* dv, const Scalar& z, std::vector<Scalar>& wV, Scalar& wc) const {
     size_t n = num_multipliers(), m = is_prover ? v.size() : V.size();
@@ -637,7 +657,8 @@ struct bpg_cs {
       b = b * b;
     }
     std::vector<Scalar> out(m + 1);
-    int rc = bpg_r1cs_dev_flatten(dv, n, m, t_code.size(), t_code.data(), t_row.data(), t_coeff.data(), z_pow, out.data());
+    bpg_terms T = terms();
+    int rc = bpg_r1cs_dev_flatten_terms(dv, n, m, &T, z_pow, out.data());
     if (rc) return rc;
     wV.assign(out.begin(), out.begin() + m);
     wc = out[m];  // the prover ignores it (prover.rs:370-372)

@@ -56,19 +56,16 @@ struct bpg_ctx {
   // constraint terms uploaded ahead of their use (bpg_r1cs_terms_prefetch): consumed once by bpg_r1cs_dev_flatten
   uint8_t* d_terms = nullptr;
   size_t d_terms_cap = 0;
-  const void* terms_src = nullptr;  // host array the resident copy was taken from (identity check)
-  size_t terms_n = 0;
+  bpg_terms terms_res = {};      // host arrays the resident copy was taken from (identity check)
+  bool terms_resident = false;
+  bpg_terms terms_pending = {};  // a prefetch waiting for the next commitment's own uploads to be queued first
+  bool terms_is_pending = false;
   cudaEvent_t ev_terms = nullptr;
   // combs of ad-hoc points built ahead of their MSM (bpg_adhoc_prefetch): [comp | bad, ticket | parts | ext | chain | comb]
   uint8_t* d_adhoc = nullptr;
   size_t adhoc_cap = 0;            // points the buffer holds
   size_t adhoc_n = 0;              // points of the resident combs (0: none)
   std::vector<uint8_t> adhoc_src;  // their encodings (identity check)
-  struct {
-    const uint32_t *code = nullptr, *row = nullptr;
-    const void* coeff = nullptr;
-    size_t n = 0;
-  } terms_pending;  // a prefetch waiting for the next commitment's own uploads to be queued first
 };
 
 struct bpg_table {

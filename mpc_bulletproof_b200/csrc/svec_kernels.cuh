@@ -348,21 +348,28 @@ static __global__ void __launch_bounds__(256) k_ipp_verify_scalars(const uint32_
 // by a large share of the rows of some circuits, so its terms are summed per block first.
 // k_flat_finish carries the counters, reduces mod l and applies the signs.
 constexpr uint32_t FLAT_KIND_SHIFT = 28;  // term code: kind << 28 | index; kinds as in the host mirror
+constexpr uint32_t FLAT_IDX_MASK = (1u << 27) - 1, FLAT_NEG = 1u << 31;
 enum : uint32_t { FK_LEFT = 1, FK_RIGHT = 2, FK_OUT = 3, FK_COMMITTED = 4, FK_ONE = 5, FK_ZERO = 6 };
 
 static __global__ void __launch_bounds__(SV_THREADS) k_flat_terms(const uint32_t* __restrict__ t_code,
                                                             const uint32_t* __restrict__ t_row,
-                                                            const uint32_t* __restrict__ t_coeff /*Montgomery*/,
-                                                            uint32_t n_terms, uint32_t n, uint32_t m, PowTable z,
+                                                            const uint32_t* __restrict__ t_coeff /*[n_general] Montgomery*/,
+                                                            uint32_t n_general, uint32_t n_terms /*general, then unit*/,
+                                                            uint32_t n, uint32_t m, PowTable z,
                                                             unsigned long long* __restrict__ acc /*[3n+m+1][8]*/) {
   __shared__ uint32_t sm[SV_THREADS / 2][8];
   sc one_sum[1] = {sc_zero()};
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n_terms) {
-    uint32_t code = t_code[t], kind = code >> FLAT_KIND_SHIFT, idx = code & ((1u << FLAT_KIND_SHIFT) - 1);
-    sc c;
-    sc_load(c, t_coeff + (size_t)t * 8);
-    sc v = sc_montmul(c, sc_pow(z, t_row[t] + 1));
+    const uint32_t code = t_code[t], kind = (code >> FLAT_KIND_SHIFT) & 7u, idx = code & FLAT_IDX_MASK;
+    sc v = sc_pow(z, t_row[t] + 1);
+    if (t < n_general) {
+      sc c;
+      sc_load(c, t_coeff + (size_t)t * 8);
+      v = sc_montmul(c, v);
+    } else if (code & FLAT_NEG) {  // unit terms carry no coefficient: +1, or -1 with the top bit of the code
+      v = sc_sub(sc_zero(), v);
+    }
     if (kind == FK_ONE) {
       one_sum[0] = v;
     } else if (kind >= FK_LEFT && kind <= FK_COMMITTED) {

@@ -59,6 +59,18 @@ pub struct bpg_ipp_verify_params {
     pub padded_n: u32,
 }
 
+/// The flat constraint terms, general ones (with a coefficient) and unit ones (+1, or -1 with bit 31 of the code).
+#[repr(C)]
+pub struct bpg_terms {
+    pub n_terms: usize,
+    pub t_code: *const u32,
+    pub t_row: *const u32,
+    pub t_coeff: *const c_void,
+    pub n_unit: usize,
+    pub u_code: *const u32,
+    pub u_row: *const u32,
+}
+
 extern "C" {
     // ---- context -----------------------------------------------------------------------
     pub fn bpg_init(device: c_int, out: *mut *mut bpg_ctx) -> c_int;
@@ -156,11 +168,12 @@ extern "C" {
         st: *mut bpg_r1cs_dev, n: usize, m: usize, n_terms: usize, t_code: *const u32, t_row: *const u32,
         t_coeff: *const c_void, z_pow: *const c_void, wv_out: *mut c_void,
     ) -> c_int;
-    /// early upload of the constraint terms (they depend on no challenge); consumed by the next flatten
-    pub fn bpg_r1cs_terms_prefetch(
-        ctx: *mut bpg_ctx, n_terms: usize, t_code: *const u32, t_row: *const u32, t_coeff: *const c_void,
-        after_commit_uploads: c_int,
+    /// flattened_constraints with the +1 / -1 terms in a list of their own (no coefficient stored)
+    pub fn bpg_r1cs_dev_flatten_terms(
+        st: *mut bpg_r1cs_dev, n: usize, m: usize, terms: *const bpg_terms, z_pow: *const c_void, wv_out: *mut c_void,
     ) -> c_int;
+    /// early upload of the constraint terms (they depend on no challenge); consumed by the next flatten
+    pub fn bpg_r1cs_terms_prefetch(ctx: *mut bpg_ctx, terms: *const bpg_terms, after_commit_uploads: c_int) -> c_int;
     /// t_1..t_6, src/util.rs:152-170
     pub fn bpg_r1cs_dev_poly_t(
         st: *mut bpg_r1cs_dev, n: usize, y_pow: *const c_void, y_inv_pow: *const c_void, t_out: *mut u8,
