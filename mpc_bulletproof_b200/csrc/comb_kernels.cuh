@@ -271,6 +271,35 @@ __device__ __forceinline__ ge4 comb_windows4(const uint32_t* __restrict__ comb_o
 }
 
 constexpr int CBQ_THREADS = 256;  // 64 quads
+// one point per quad over the block -> their sum, encoded by warp 0 (whole-warp sixteen-lane form) into
+// out_bytes[set] (and, extended, into out_ext[set] when given).  Every thread of the block must call it.
+__device__ __forceinline__ void comb_tree_encode(ge4 acc, uint32_t (*sm)[32], uint32_t* pt0 /*[32] shared*/,
+                                                 uint32_t* g16 /*[G16_WORDS] shared*/, uint32_t set,
+                                                 uint8_t* __restrict__ out_bytes, uint32_t* __restrict__ out_ext) {
+  ge4 tot4 = comb_tree_quads(acc, sm);
+  if (threadIdx.x < 4) ge4_store(pt0, tot4);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    ge_ext tot;
+    ge_load_ext(tot, pt0);
+    if (out_ext && threadIdx.x == 0) ge_store_ext(out_ext + (size_t)set * 32, tot);
+    grp16 gg;
+    gg.sm = g16;
+    gg.k = threadIdx.x & 15u;
+    gg.half = (threadIdx.x >> 4) & 1u;
+    gg.par = 0;
+    fe s = ge_encode16<true>(gg, tot);
+    if (threadIdx.x < 16) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) w = (gg.k >> 1) == (uint32_t)i ? s.v[i] : w;
+      w = (gg.k & 1u) ? (w >> 16) : w;
+      out_bytes[(size_t)set * 32 + 2 * gg.k] = (uint8_t)w;
+      out_bytes[(size_t)set * 32 + 2 * gg.k + 1] = (uint8_t)(w >> 8);
+    }
+  }
+}
+
 template <bool Q_AFFINE>
 __global__ void __launch_bounds__(CBQ_THREADS) k_comb_final(CombFinal F, uint8_t* __restrict__ out_bytes /*[sets][32]*/,
                                                              uint32_t* __restrict__ out_ext /*[sets][32] or null*/) {
@@ -332,29 +361,7 @@ __global__ void __launch_bounds__(CBQ_THREADS) k_comb_final(CombFinal F, uint8_t
     ge4 o = i < F.nparts ? ge4_load(F.parts + ((size_t)set * F.nparts + i) * 32) : ge4_identity();
     acc = cb_add4(acc, o);
   }
-  ge4 tot4 = comb_tree_quads(acc, sm);
-  // 3. encode on warp 0 (whole-warp sixteen-lane form)
-  if (threadIdx.x < 4) ge4_store(pt0, tot4);
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    ge_ext tot;
-    ge_load_ext(tot, pt0);
-    if (out_ext && threadIdx.x == 0) ge_store_ext(out_ext + (size_t)set * 32, tot);
-    grp16 gg;
-    gg.sm = g16;
-    gg.k = threadIdx.x & 15u;
-    gg.half = (threadIdx.x >> 4) & 1u;
-    gg.par = 0;
-    fe s = ge_encode16<true>(gg, tot);
-    if (threadIdx.x < 16) {
-      uint32_t w = 0;
-#pragma unroll
-      for (int i = 0; i < 8; i++) w = (gg.k >> 1) == (uint32_t)i ? s.v[i] : w;
-      w = (gg.k & 1u) ? (w >> 16) : w;
-      out_bytes[(size_t)set * 32 + 2 * gg.k] = (uint8_t)w;
-      out_bytes[(size_t)set * 32 + 2 * gg.k + 1] = (uint8_t)(w >> 8);
-    }
-  }
+  comb_tree_encode(acc, sm, pt0, g16, set, out_bytes, out_ext);
 }
 
 // ---------------------------------------------------------------------------

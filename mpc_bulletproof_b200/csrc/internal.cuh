@@ -108,6 +108,11 @@ int terms_issue_pending(bpg_ctx* ctx);  // r1cs_dev.inc
 int ensure_ws(bpg_ctx* ctx, size_t bytes, int lane = 0);
 int ensure_stage(bpg_ctx* ctx, size_t bytes);
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+// tuning knobs read from the environment (documented where they are used)
+static inline size_t env_size(const char* name, size_t dflt) {
+  const char* e = getenv(name);
+  return e ? (size_t)strtoull(e, nullptr, 10) : dflt;
+}
 int pick_window(size_t n_per_set, int forced);
 int pick_window_table(size_t n, int forced);
 int table_alloc_plain(bpg_ctx* ctx, size_t n, bpg_table** out);
@@ -149,6 +154,10 @@ bool adhoc_matches(const bpg_ctx* ctx, const uint8_t* host_points, size_t n);
 // comb_build.cu: decode, doubling chains and cached combs of `n` compressed points
 int comb_from_points(bpg_ctx* ctx, cudaStream_t s, const uint8_t* d_comp, size_t n, uint32_t* ext, uint32_t* chain,
                      uint32_t* comb, uint32_t* bad);
+// ipp.cu: up to four sets of indexed terms over the affine combs of a table, encoded (set s: term single[s] and terms [lo[s], hi[s]))
+int launch_comb_terms(bpg_ctx* ctx, cudaStream_t s, const uint32_t* comb_affine, const uint32_t* d_scalars,
+                      const uint32_t* d_point_ids, const uint32_t single[4], const uint32_t lo[4], const uint32_t hi[4],
+                      int nsets, uint8_t* d_out_bytes);
 // ipp.cu: sum_k scalars[k] * P_k from cached combs (canonical scalars on the device), one extended point
 int launch_comb_msm(bpg_ctx* ctx, cudaStream_t s, const uint32_t* comb_cached, const uint32_t* d_scalars, size_t n,
                     uint32_t* parts /*ADHOC_PARTS x 32 words*/, uint32_t* ticket, uint32_t* out_ext);

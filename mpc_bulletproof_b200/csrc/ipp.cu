@@ -25,6 +25,42 @@ int launch_comb_msm(bpg_ctx* ctx, cudaStream_t s, const uint32_t* comb_cached, c
   return BPG_OK;
 }
 
+// sets of indexed terms over the affine combs of a table, encoded: `single`, `lo`, `hi` per set (k_comb_terms)
+int launch_comb_terms(bpg_ctx* ctx, cudaStream_t s, const uint32_t* comb_affine, const uint32_t* d_scalars,
+                      const uint32_t* d_point_ids, const uint32_t single[4], const uint32_t lo[4], const uint32_t hi[4],
+                      int nsets, uint8_t* d_out_bytes) {
+  if (nsets < 1 || nsets > 4) return BPG_ERR_ARG;
+  CombTerms M;
+  memset(&M, 0, sizeof M);
+  M.comb = comb_affine;
+  M.scalars = d_scalars;
+  M.point_ids = d_point_ids;
+  size_t max_units = 0, total = 0;
+  for (int i = 0; i < nsets; i++) {
+    M.single[i] = single[i];
+    M.lo[i] = lo[i];
+    M.hi[i] = hi[i];
+    max_units = std::max<size_t>(max_units, 1 + hi[i] - lo[i]);
+    total += 1 + hi[i] - lo[i];
+  }
+  static const size_t target_mul = env_size("BPG_COMB_THREADS_PER_SM", 192);
+  M.wsplit = 1;
+  while (M.wsplit < COMB_WINDOWS && total * M.wsplit < (size_t)ctx->sm_count * target_mul) M.wsplit <<= 1;
+  M.bias4 = bias_for(4);
+  const unsigned bx = (unsigned)((max_units * M.wsplit + CB_THREADS - 1) / CB_THREADS);
+  int rc = ensure_ws(ctx, (size_t)nsets * bx * 128);
+  if (rc) return rc;
+  uint32_t* parts = (uint32_t*)ctx->ws;
+  prof_mark(ctx, BPG_PROF_ACCUM);
+  k_comb_terms<<<dim3(bx, nsets), CB_THREADS, 0, s>>>(M, parts);
+  LAUNCH_CHECK();
+  prof_mark(ctx, BPG_PROF_ENCODE);
+  k_parts_encode<<<nsets, CBQ_THREADS, 0, s>>>(parts, bx, d_out_bytes);
+  LAUNCH_CHECK();
+  prof_mark(ctx, -1);
+  return BPG_OK;
+}
+
 // ---------------------------------------------------------------------------
 // inner-product argument: device-resident state, one MSM per round
 // ---------------------------------------------------------------------------
@@ -61,10 +97,6 @@ struct bpg_ipp {
 
 // BPG_IPP_DIRECT_MAX: vectors up to this length run every round on the generators' own combs;
 // BPG_IPP_M0: longer ones switch to combs of the folded generators once they have shrunk to this length
-static size_t env_size(const char* name, size_t dflt) {
-  const char* e = getenv(name);
-  return e ? (size_t)strtoull(e, nullptr, 10) : dflt;
-}
 
 
 // d_* pointers are device pointers; factors may be null (all ones).
@@ -184,7 +216,11 @@ int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_tabl
   // vectors run every round on the combs, and long ones switch to combs of the folded generators.
   st->n_eff = n;
   if (st->tab->comb && !st->own_tab && n > 1) {
-    const size_t direct_max = std::min<size_t>(env_size("BPG_IPP_DIRECT_MAX", 8192), 65536), m0 = env_size("BPG_IPP_M0", 2048);
+    // measured on a B200 (profiles/r2_ipp_strategy_tuning.json): every round on the generators' combs up to 4096
+    // entries; beyond, the folded generators are formed at 1024 entries (2048 from 2^16 on, where the bucket
+    // rounds before it are the larger share)
+    const size_t direct_max = std::min<size_t>(env_size("BPG_IPP_DIRECT_MAX", 4096), 65536);
+    const size_t m0 = env_size("BPG_IPP_M0", n >= 65536 ? 2048 : 1024);
     st->cq_comb = st->q_sep ? st->q_comb : st->tab->comb + (size_t)q_id * COMB_ENTRIES * COMB_AFFINE_WORDS;
     if (n <= direct_max || n <= m0) {
       st->mode = 1;
