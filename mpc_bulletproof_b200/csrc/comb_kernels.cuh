@@ -272,7 +272,7 @@ __device__ __forceinline__ ge4 comb_windows4(const uint32_t* __restrict__ comb_o
 
 constexpr int CBQ_THREADS = 256;  // 64 quads
 // one point per quad over the block -> their sum, encoded by warp 0 (whole-warp sixteen-lane form) into
-// out_bytes[set] (and, extended, into out_ext[set] when given).  Every thread of the block must call it.
+// out_bytes[set] when given (and, extended, into out_ext[set] when given).  Every thread of the block must call it.
 __device__ __forceinline__ void comb_tree_encode(ge4 acc, uint32_t (*sm)[32], uint32_t* pt0 /*[32] shared*/,
                                                  uint32_t* g16 /*[G16_WORDS] shared*/, uint32_t set,
                                                  uint8_t* __restrict__ out_bytes, uint32_t* __restrict__ out_ext) {
@@ -283,6 +283,7 @@ __device__ __forceinline__ void comb_tree_encode(ge4 acc, uint32_t (*sm)[32], ui
     ge_ext tot;
     ge_load_ext(tot, pt0);
     if (out_ext && threadIdx.x == 0) ge_store_ext(out_ext + (size_t)set * 32, tot);
+    if (!out_bytes) return;  // block-uniform: the caller wants the extended sum only
     grp16 gg;
     gg.sm = g16;
     gg.k = threadIdx.x & 15u;

@@ -102,7 +102,8 @@ static __global__ void __launch_bounds__(CB_THREADS) k_comb_terms(CombTerms M, u
 }
 // the blocks' partial sums of every set -> the set's encoding (one block per set)
 static __global__ void __launch_bounds__(CBQ_THREADS) k_parts_encode(const uint32_t* __restrict__ parts /*[sets][nparts][32]*/,
-                                                              uint32_t nparts, uint8_t* __restrict__ out_bytes) {
+                                                              uint32_t nparts, uint8_t* __restrict__ out_bytes /*or null*/,
+                                                              uint32_t* __restrict__ out_ext /*or null*/) {
   __shared__ __align__(16) uint32_t sm[CBQ_THREADS / 32][32];
   __shared__ __align__(16) uint32_t pt0[32];
   __shared__ __align__(16) uint32_t g16[G16_WORDS];
@@ -113,7 +114,7 @@ static __global__ void __launch_bounds__(CBQ_THREADS) k_parts_encode(const uint3
     ge4 o = i < nparts ? ge4_load(parts + ((size_t)set * nparts + i) * 32) : ge4_identity();
     acc = cb_add4(acc, o);
   }
-  comb_tree_encode(acc, sm, pt0, g16, set, out_bytes, nullptr);
+  comb_tree_encode(acc, sm, pt0, g16, set, out_bytes, out_ext);
 }
 
 }  // namespace bpg

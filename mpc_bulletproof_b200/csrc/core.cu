@@ -1061,7 +1061,14 @@ int msm_mixed_core(bpg_ctx* ctx, const uint8_t* d_adhoc_points, size_t n_adhoc, 
       }
       k_seg_point_ids<<<(unsigned)((n_tab + 255) / 256), 256, 0, s>>>(sg, (uint32_t)n_tab, d_ids);
       ctx->launches++;
-      rc = msm_enqueue(ctx, T->niels, T->n, d_scalars + n_adhoc * 8, n_tab, nullptr, d_ids, 1, d_ext, T->win_c, T->n);
+      // a few thousand table terms: 64 comb additions each in two launches instead of the bucket pipeline's dozen
+      static const size_t comb_max = env_size("BPG_MIXED_COMB_MAX", 4100);
+      if (T->comb && n_tab <= comb_max) {
+        const uint32_t single[4] = {0, 0, 0, 0}, lo[4] = {1, 0, 0, 0}, hi[4] = {(uint32_t)n_tab, 0, 0, 0};
+        rc = launch_comb_terms(ctx, s, T->comb, d_scalars + n_adhoc * 8, d_ids, single, lo, hi, 1, nullptr, d_ext);
+      } else {
+        rc = msm_enqueue(ctx, T->niels, T->n, d_scalars + n_adhoc * 8, n_tab, nullptr, d_ids, 1, d_ext, T->win_c, T->n);
+      }
       if (rc) break;
       rc = BPG_ERR_CUDA;
       if (n_adhoc && cudaStreamWaitEvent(s, ctx->ev_join, 0) != cudaSuccess) break;

@@ -157,7 +157,7 @@ int comb_from_points(bpg_ctx* ctx, cudaStream_t s, const uint8_t* d_comp, size_t
 // ipp.cu: up to four sets of indexed terms over the affine combs of a table, encoded (set s: term single[s] and terms [lo[s], hi[s]))
 int launch_comb_terms(bpg_ctx* ctx, cudaStream_t s, const uint32_t* comb_affine, const uint32_t* d_scalars,
                       const uint32_t* d_point_ids, const uint32_t single[4], const uint32_t lo[4], const uint32_t hi[4],
-                      int nsets, uint8_t* d_out_bytes);
+                      int nsets, uint8_t* d_out_bytes /*encodings, or null*/, uint32_t* d_out_ext /*extended sums, or null*/);
 // ipp.cu: sum_k scalars[k] * P_k from cached combs (canonical scalars on the device), one extended point
 int launch_comb_msm(bpg_ctx* ctx, cudaStream_t s, const uint32_t* comb_cached, const uint32_t* d_scalars, size_t n,
                     uint32_t* parts /*ADHOC_PARTS x 32 words*/, uint32_t* ticket, uint32_t* out_ext);

@@ -28,8 +28,8 @@ int launch_comb_msm(bpg_ctx* ctx, cudaStream_t s, const uint32_t* comb_cached, c
 // sets of indexed terms over the affine combs of a table, encoded: `single`, `lo`, `hi` per set (k_comb_terms)
 int launch_comb_terms(bpg_ctx* ctx, cudaStream_t s, const uint32_t* comb_affine, const uint32_t* d_scalars,
                       const uint32_t* d_point_ids, const uint32_t single[4], const uint32_t lo[4], const uint32_t hi[4],
-                      int nsets, uint8_t* d_out_bytes) {
-  if (nsets < 1 || nsets > 4) return BPG_ERR_ARG;
+                      int nsets, uint8_t* d_out_bytes, uint32_t* d_out_ext) {
+  if (nsets < 1 || nsets > 4 || (!d_out_bytes && !d_out_ext)) return BPG_ERR_ARG;
   CombTerms M;
   memset(&M, 0, sizeof M);
   M.comb = comb_affine;
@@ -55,7 +55,7 @@ int launch_comb_terms(bpg_ctx* ctx, cudaStream_t s, const uint32_t* comb_affine,
   k_comb_terms<<<dim3(bx, nsets), CB_THREADS, 0, s>>>(M, parts);
   LAUNCH_CHECK();
   prof_mark(ctx, BPG_PROF_ENCODE);
-  k_parts_encode<<<nsets, CBQ_THREADS, 0, s>>>(parts, bx, d_out_bytes);
+  k_parts_encode<<<nsets, CBQ_THREADS, 0, s>>>(parts, bx, d_out_bytes, d_out_ext);
   LAUNCH_CHECK();
   prof_mark(ctx, -1);
   return BPG_OK;
