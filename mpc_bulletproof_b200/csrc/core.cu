@@ -107,6 +107,7 @@ extern "C" void bpg_free(bpg_ctx* ctx) {
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->d_terms) cudaFree(ctx->d_terms);
   if (ctx->d_adhoc) cudaFree(ctx->d_adhoc);
+  if (ctx->q_cache_comb) cudaFree(ctx->q_cache_comb);
   if (ctx->ev_terms) cudaEventDestroy(ctx->ev_terms);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);

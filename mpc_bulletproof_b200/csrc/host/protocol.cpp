@@ -367,6 +367,17 @@ extern "C" int bpg_ipp_verify(bpg_ctx* ctx, bpg_transcript* t, size_t n, const u
   InnerProductProof p;
   int rc = InnerProductProof::from_bytes(proof, proof_len, &p);
   if (rc) return rc;
+  // the ad-hoc points [Q | L | R] of the check (:352-366) are known before their scalars: their doubling chains
+  // start now, beside the transcript replay (bpg_adhoc_prefetch)
+  size_t lg_n = p.L_vec.size();
+  std::vector<uint8_t> pts((1 + 2 * lg_n) * 32);
+  memcpy(pts.data(), Q, 32);
+  for (size_t i = 0; i < lg_n; i++) {
+    memcpy(pts.data() + 32 * (1 + i), p.L_vec[i].data(), 32);
+    memcpy(pts.data() + 32 * (1 + lg_n + i), p.R_vec[i].data(), 32);
+  }
+  rc = bpg_adhoc_prefetch(ctx, pts.data(), 1 + 2 * lg_n);
+  if (rc) return rc;
   std::vector<Scalar> u_sq, u_inv_sq;
   Scalar allinv;
   rc = p.verification_challenges(n, t->t, u_sq, u_inv_sq, allinv);
@@ -376,7 +387,6 @@ extern "C" int bpg_ipp_verify(bpg_ctx* ctx, bpg_transcript* t, size_t n, const u
       if (G_factors && !Scalar::is_canonical(G_factors + 32 * i)) return BPG_ERR_DECODE;
       if (H_factors && !Scalar::is_canonical(H_factors + 32 * i)) return BPG_ERR_DECODE;
     }
-  size_t lg_n = p.L_vec.size();
   // ad-hoc terms [Q | L | R] with scalars [a*b | -u_sq | -u_inv_sq]; the 2n generator scalars
   // a s_i g_i, b s_i^-1 h_i (:335-351) are produced on the device
   std::vector<Scalar> sc;
@@ -384,12 +394,6 @@ extern "C" int bpg_ipp_verify(bpg_ctx* ctx, bpg_transcript* t, size_t n, const u
   sc.push_back(p.a * p.b);
   for (auto& x : u_sq) sc.push_back(-x);
   for (auto& x : u_inv_sq) sc.push_back(-x);
-  std::vector<uint8_t> pts((1 + 2 * lg_n) * 32);
-  memcpy(pts.data(), Q, 32);
-  for (size_t i = 0; i < lg_n; i++) {
-    memcpy(pts.data() + 32 * (1 + i), p.L_vec[i].data(), 32);
-    memcpy(pts.data() + 32 * (1 + lg_n + i), p.R_vec[i].data(), 32);
-  }
   bpg_ipp_verify_params vp;
   memset(&vp, 0, sizeof vp);
   for (size_t j = 0; j < lg_n; j++) memcpy(vp.u_sq[j], u_sq[j].v, 32);

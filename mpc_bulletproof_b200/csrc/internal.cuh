@@ -61,6 +61,11 @@ struct bpg_ctx {
   bpg_terms terms_pending = {};  // a prefetch waiting for the next commitment's own uploads to be queued first
   bool terms_is_pending = false;
   cudaEvent_t ev_terms = nullptr;
+  // comb of the last Q given to a standalone InnerProductProof::create (callers tend to reuse one Q: building its
+  // affine comb is a 1.2 ms chain of doublings and an inversion, a copy of 48 KB is not)
+  uint32_t* q_cache_comb = nullptr;
+  uint8_t q_cache_key[32] = {0};
+  bool q_cache_valid = false;
   // combs of ad-hoc points built ahead of their MSM (bpg_adhoc_prefetch): [comp | bad, ticket | parts | ext | chain | comb]
   uint8_t* d_adhoc = nullptr;
   size_t adhoc_cap = 0;            // points the buffer holds

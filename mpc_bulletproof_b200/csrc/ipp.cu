@@ -172,15 +172,31 @@ int ipp_begin_dev(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg_tabl
       st->q_sep = true;
       k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, (uint32_t)g_off, (uint32_t)h_off, (uint32_t)g_off);
       ctx->launches++;
-      memcpy(ctx->h_pinned + 512, Q_host, 32);
-      uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small);
-      if (cudaMemsetAsync(bad, 0, 4, s) != cudaSuccess ||
-          cudaMemcpyAsync(d_q, ctx->h_pinned + 512, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
-      launch_comb_build(ctx, s, d_q, st->q_comb, bad);
-      uint32_t* hbad = reinterpret_cast<uint32_t*>(ctx->h_pinned);
-      if (cudaMemcpyAsync(hbad, bad, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-          cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
-      if (*hbad) { rc = BPG_ERR_DECODE; break; }
+      const size_t qc_bytes = (size_t)COMB_ENTRIES * COMB_AFFINE_WORDS * 4;
+      if (ctx->q_cache_valid && memcmp(ctx->q_cache_key, Q_host, 32) == 0) {
+        // the same Q as the last call: its comb is resident
+        if (cudaMemcpyAsync(st->q_comb, ctx->q_cache_comb, qc_bytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+      } else {
+        memcpy(ctx->h_pinned + 512, Q_host, 32);
+        uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->d_small);
+        if (cudaMemsetAsync(bad, 0, 4, s) != cudaSuccess ||
+            cudaMemcpyAsync(d_q, ctx->h_pinned + 512, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+        launch_comb_build(ctx, s, d_q, st->q_comb, bad);
+        uint32_t* hbad = reinterpret_cast<uint32_t*>(ctx->h_pinned);
+        if (cudaMemcpyAsync(hbad, bad, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess) { rc = BPG_ERR_CUDA; break; }
+        if (*hbad) { rc = BPG_ERR_DECODE; break; }
+        ctx->q_cache_valid = false;
+        if (!ctx->q_cache_comb && cudaMalloc(&ctx->q_cache_comb, qc_bytes) != cudaSuccess) {
+          ctx->q_cache_comb = nullptr;
+          cudaGetLastError();  // no cache: not an error
+        }
+        if (ctx->q_cache_comb &&
+            cudaMemcpyAsync(ctx->q_cache_comb, st->q_comb, qc_bytes, cudaMemcpyDeviceToDevice, s) == cudaSuccess) {
+          memcpy(ctx->q_cache_key, Q_host, 32);
+          ctx->q_cache_valid = true;
+        }
+      }
     } else {
       k_ipp_point_ids<<<gn, 256, 0, s>>>(st->point_ids, (uint32_t)n, 0u, (uint32_t)n, (uint32_t)(2 * n));
       ctx->launches++;
