@@ -168,6 +168,9 @@ __device__ __forceinline__ ge4 comb_block_sum(const ge_ext& mine, uint32_t (*pts
 // the pairing of inner_product_proof.rs:90-114, 159-172 -- times WSPLIT window slices.  A block is
 // set-homogeneous, so its 128 accumulators reduce to ONE partial sum: parts[s][blockIdx.x].
 // ---------------------------------------------------------------------------
+struct IppPair {
+  uint32_t v[16];  // u | u^-1, canonical words
+};
 struct CombRound {
   const uint32_t* comb;   // combs of the generators
   uint32_t g_id, h_id;    // comb index of G_0 and of H_0
@@ -178,6 +181,14 @@ struct CombRound {
   uint32_t m;             // current vector length (power of two <= n)
   uint32_t wsplit;        // threads per term: each takes 64 / wsplit windows (power of two <= 64)
   sc_bias bias4;
+  // The previous round's fold, taken on the fly (single-prover path): with `fold` set, a, b, wG, wH are the vectors
+  // BEFORE the fold by the challenge `up` (a, b of length 2 m), every term forms its folded entries itself
+  // (fold_witness, inner_product_proof.rs:224-227, 239-242, for the two entries it needs), and the folded state is
+  // left in a2, b2, wG2, wH2 -- each entry by the one unit that computed it anyway.  The round is then ONE
+  // accumulation kernel that folds a, b and the generator weights and forms L and R, plus the finish.
+  uint32_t fold;
+  IppPair up;
+  uint32_t *a2, *b2, *wG2, *wH2;
 };
 template <bool AFFINE>
 __global__ void __launch_bounds__(CB_THREADS) k_comb_round(CombRound R, uint32_t* __restrict__ parts /*[sets][gridDim.x][32]*/) {
@@ -196,13 +207,40 @@ __global__ void __launch_bounds__(CB_THREADS) k_comb_round(CombRound R, uint32_t
     const bool want_bit = (side == 0) != is_h;  // L: G_hi, H_lo;  R: G_lo, H_hi
     uint32_t i = ((kk / h) * 2 * h) + (kk % h) + (want_bit ? h : 0);
     const uint32_t partner = (i & (R.m - 1)) ^ h;
-    sc v;
-    sc_load(v, (is_h ? R.b : R.a) + ((size_t)lane_id * R.stride + partner) * 8);
+    const uint32_t* vec = (is_h ? R.b : R.a) + (size_t)lane_id * R.stride * 8;
     const uint32_t* w = is_h ? R.wH : R.wG;
-    if (w) {
+    sc v;
+    if (R.fold) {
+      sc u, ui;
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        u.v[t] = R.up.v[t];
+        ui.v[t] = R.up.v[8 + t];
+      }
+      u = sc_to_mont(u);
+      ui = sc_to_mont(ui);
+      // a' = u a_lo + u^-1 a_hi,  b' = u^-1 b_lo + u b_hi  (entry `partner` of the folded vector)
+      sc x0, x1;
+      sc_load(x0, vec + (size_t)partner * 8);
+      sc_load(x1, vec + (size_t)(partner + R.m) * 8);
+      v = sc_add(sc_montmul(x0, is_h ? ui : u), sc_montmul(x1, is_h ? u : ui));
+      // weight of generator i: times u for the half that is folded onto (G: upper, H: lower), u^-1 for the other
+      const bool hi = (i & R.m) != 0;
       sc ww;
       sc_load(ww, w + (size_t)i * 8);
+      ww = sc_montmul(ww, (hi != is_h) ? u : ui);
+      if (slice == 0) {
+        if (i < R.m) sc_store((is_h ? R.b2 : R.a2) + ((size_t)lane_id * R.stride + partner) * 8, v);
+        if (lane_id == 0) sc_store((is_h ? R.wH2 : R.wG2) + (size_t)i * 8, ww);
+      }
       v = sc_montmul(v, ww);
+    } else {
+      sc_load(v, vec + (size_t)partner * 8);
+      if (w) {
+        sc ww;
+        sc_load(ww, w + (size_t)i * 8);
+        v = sc_montmul(v, ww);
+      }
     }
     const sc_recoded r = sc_recode(v.v, R.bias4);
     const int per = COMB_WINDOWS / (int)R.wsplit;
@@ -224,6 +262,8 @@ struct CombFinal {
   const uint32_t* cross;       // [ncross][16]: (c_L | c_R) partials, Montgomery-scaled by R^-1 (k_ipp_cross form); null if external
   uint32_t ncross;
   const uint32_t* c_ext;       // [lanes][2][8] canonical cross terms supplied by the caller (shares path); null otherwise
+  const uint32_t *va, *vb;     // cross == null and c_ext == null: the current vectors (normal form), c_L = <a_lo, b_hi>,
+  uint32_t vh;                 //   c_R = <a_hi, b_lo> over halves of length vh are formed here (inner_product_proof.rs:156-157)
   const uint32_t* q_mul;       // null or the scalar with Q = q_mul * (point of q_comb)
   const uint32_t* q_comb;      // comb of Q's base point
   sc_bias bias4;
@@ -319,10 +359,20 @@ __global__ void __launch_bounds__(CBQ_THREADS) k_comb_final(CombFinal F, uint8_t
       c = sc_montmul(c, sc_to_mont(q));
     }
   } else {
-    for (uint32_t i = threadIdx.x; i < F.ncross; i += CBQ_THREADS) {
-      sc x;
-      sc_load(x, F.cross + (size_t)i * 16 + 8 * side);
-      c = sc_add(c, x);
+    if (F.cross) {
+      for (uint32_t i = threadIdx.x; i < F.ncross; i += CBQ_THREADS) {
+        sc x;
+        sc_load(x, F.cross + (size_t)i * 16 + 8 * side);
+        c = sc_add(c, x);
+      }
+    } else {
+      // side 0: sum_p a[p] b[p + h];  side 1: sum_p a[p + h] b[p]   (each product carries R^-1, like the partials)
+      for (uint32_t p = threadIdx.x; p < F.vh; p += CBQ_THREADS) {
+        sc x, y;
+        sc_load(x, F.va + (size_t)(p + (side ? F.vh : 0)) * 8);
+        sc_load(y, F.vb + (size_t)(p + (side ? 0 : F.vh)) * 8);
+        c = sc_add(c, sc_montmul(x, y));
+      }
     }
     // warp tree by shuffles, then the eight warp sums
 #pragma unroll
@@ -371,9 +421,6 @@ __global__ void __launch_bounds__(CBQ_THREADS) k_comb_final(CombFinal F, uint8_t
 // and adds its two products to the block's partial sums; the weights pick up u^(+-1) as in k_ipp_fold.
 // grid.y = lane; cross terms only where `partials` is given (shares: they come from the fabric).
 // ---------------------------------------------------------------------------
-struct IppPair {
-  uint32_t v[16];  // u | u^-1, canonical words
-};
 constexpr int IFC_THREADS = 256;
 static __global__ void __launch_bounds__(IFC_THREADS) k_ipp_fold_cross(uint32_t* __restrict__ a, uint32_t* __restrict__ b,
                                                                 uint32_t* __restrict__ wG, uint32_t* __restrict__ wH,

@@ -93,6 +93,14 @@ struct bpg_ipp {
   size_t parts_cap;
   bool cross_ready;       // the fold kernel already left this round's cross-term partials
   uint32_t ncross;
+  // single-prover comb rounds take the previous fold on the fly (CombRound::fold): the challenge waits here and the
+  // folded vectors land in the alternate buffers, which then become the current ones
+  bool shares;            // created by bpg_ipp_begin_shares: the caller reads the folded vectors between rounds
+  bool fold_pending;
+  IppPair fold_up;
+  uint32_t* alt;          // a2 | b2 | wG2 | wH2, n_eff scalars each
+  size_t alt_n;
+  uint32_t* oth[4];       // the vectors (a, b, wG, wH) that are not current: targets of the next fused fold
 };
 
 // BPG_IPP_DIRECT_MAX: vectors up to this length run every round on the generators' own combs;
@@ -298,12 +306,20 @@ static int ipp_comb_round(bpg_ipp* st, bool external_cross) {
   const size_t n = st->n_eff, m = st->m, h = m / 2;
   const unsigned sets = 2u * (unsigned)st->lanes;
   prof_mark(ctx, BPG_PROF_OTHER);
-  if (!external_cross && !st->cross_ready) {
+  // cross terms: the caller's shares, the fold kernel's partials, or (single prover) formed by the finish itself
+  const bool cross_in_finish = !external_cross && !st->cross_ready && st->lanes == 1;
+  if (!external_cross && !st->cross_ready && !cross_in_finish) {
     unsigned gcross = (unsigned)std::min<size_t>(256, (h + IPP_THREADS - 1) / IPP_THREADS);
     k_ipp_cross<<<gcross, IPP_THREADS, 0, s>>>(st->a, st->b, (uint32_t)h, st->partials);
     LAUNCH_CHECK();
     st->ncross = gcross;
   }
+  if (st->fold_pending && !st->alt) {
+    if (dev_alloc(ctx, &st->alt, 4 * n * 32) != cudaSuccess) return BPG_ERR_NOMEM;
+    st->alt_n = n;
+    for (int k = 0; k < 4; k++) st->oth[k] = st->alt + (size_t)k * n * 8;
+  }
+  if (st->fold_pending && st->alt_n < n) return BPG_ERR_ARG;  // n_eff only shrinks after the first comb round
   // threads per term: enough (term, window-slice) units to fill the machine, at most one window per thread
   // (each thread's accumulator must then go through the block tree, which costs about three additions of its own:
   // more slices than the machine needs only add tree work)
@@ -326,14 +342,33 @@ static int ipp_comb_round(bpg_ipp* st, bool external_cross) {
   R.m = (uint32_t)m;
   R.wsplit = wsplit;
   R.bias4 = bias_for(4);
+  R.fold = st->fold_pending ? 1u : 0u;
+  R.up = st->fold_up;
+  R.a2 = R.b2 = R.wG2 = R.wH2 = nullptr;
+  if (st->fold_pending) {  // lanes == 1 here
+    R.a2 = st->oth[0];
+    R.b2 = st->oth[1];
+    R.wG2 = st->oth[2];
+    R.wH2 = st->oth[3];
+  }
   prof_mark(ctx, BPG_PROF_ACCUM);
   if (st->comb_affine) k_comb_round<true><<<dim3(bx, sets), CB_THREADS, 0, s>>>(R, st->parts);
   else k_comb_round<false><<<dim3(bx, sets), CB_THREADS, 0, s>>>(R, st->parts);
   LAUNCH_CHECK();
+  if (st->fold_pending) {
+    // the folded state is the current one from here on; the old vectors become the next round's alternates
+    st->fold_pending = false;
+    uint32_t* cur[4] = {st->a, st->b, st->wG, st->wH};
+    st->a = st->oth[0], st->b = st->oth[1], st->wG = st->oth[2], st->wH = st->oth[3];
+    for (int k = 0; k < 4; k++) st->oth[k] = cur[k];
+  }
   CombFinal F;
   F.parts = st->parts;
   F.nparts = bx;
-  F.cross = external_cross ? nullptr : st->partials;
+  F.va = cross_in_finish ? st->a : nullptr;
+  F.vb = cross_in_finish ? st->b : nullptr;
+  F.vh = (uint32_t)h;
+  F.cross = (external_cross || cross_in_finish) ? nullptr : st->partials;
   F.ncross = st->ncross;
   F.c_ext = external_cross ? st->c_ext : nullptr;
   F.q_mul = st->has_qmul ? st->q_mul : nullptr;
@@ -465,7 +500,12 @@ extern "C" int bpg_ipp_round_fold(bpg_ipp* st, const uint8_t u[32], const uint8_
   memcpy(up.v, u, 32);
   memcpy(up.v + 8, u_inv, 32);
   prof_mark(ctx, BPG_PROF_OTHER);
-  if (st->mode == 1) {
+  if (st->mode == 1 && st->lanes == 1 && !st->shares && st->m > 2 && !st->fold_pending) {
+    // single prover, another round follows: that round's accumulation takes this fold on the fly (CombRound::fold)
+    memcpy(st->fold_up.v, up.v, sizeof st->fold_up.v);
+    st->fold_pending = true;
+    st->cross_ready = false;
+  } else if (st->mode == 1) {
     // fold + the next round's cross-term partials in one kernel (the shares path gets them from the caller)
     IppPair ip;
     memcpy(ip.v, up.v, sizeof ip.v);
@@ -513,9 +553,11 @@ extern "C" int bpg_ipp_begin_shares(bpg_ctx* ctx, const bpg_table* shared, size_
   CK(cudaMemcpyAsync(d_b, b, NL * n * 32, cudaMemcpyHostToDevice, ctx->stream));
   if (G_factors) CK(cudaMemcpyAsync(d_gf, G_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
   if (H_factors) CK(cudaMemcpyAsync(d_hf, H_factors, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  return ipp_begin_dev(ctx, nullptr, 0, nullptr, 0, n, nullptr, shared, g_base, h_base, q_id, q_mul,
-                       G_factors ? (const uint32_t*)d_gf : nullptr, H_factors ? (const uint32_t*)d_hf : nullptr,
-                       (const uint32_t*)d_a, (const uint32_t*)d_b, out, lanes);
+  rc = ipp_begin_dev(ctx, nullptr, 0, nullptr, 0, n, nullptr, shared, g_base, h_base, q_id, q_mul,
+                     G_factors ? (const uint32_t*)d_gf : nullptr, H_factors ? (const uint32_t*)d_hf : nullptr,
+                     (const uint32_t*)d_a, (const uint32_t*)d_b, out, lanes);
+  if (rc == BPG_OK) (*out)->shares = true;  // the caller reads the folded vectors between rounds: folds stay eager
+  return rc;
 }
 extern "C" int bpg_ipp_lanes(const bpg_ipp* st) { return st ? st->lanes : 0; }
 extern "C" size_t bpg_ipp_len(const bpg_ipp* st) { return st ? st->m : 0; }
@@ -608,6 +650,7 @@ extern "C" void bpg_ipp_free(bpg_ipp* st) {
   if (st->own_tab) bpg_table_free(st->own_tab);
   dev_free(st->ctx, st->mat_buf);
   dev_free(st->ctx, st->parts);
+  dev_free(st->ctx, st->alt);
   dev_free(st->ctx, st->buf);
   delete st;
 }
