@@ -305,6 +305,19 @@ int bpg_ipp_verify_msm(bpg_ctx* ctx, const bpg_table* G, size_t g_off, const bpg
 typedef struct bpg_r1cs_dev bpg_r1cs_dev;
 int bpg_r1cs_dev_new(bpg_ctx* ctx, size_t capacity, bpg_r1cs_dev** out);
 void bpg_r1cs_dev_free(bpg_r1cs_dev* st);
+/* Batch verification (BASELINE config 4; the reference verifies proof by proof, verifier.rs:393): the 2 + 2N generator
+ * scalars of several proofs' final checks kept side by side on the device (bpg_vbatch_put: what
+ * bpg_r1cs_dev_verify_msm computes before its MSM), then sum_j rho_j * check_j as ONE multiscalar multiplication over
+ * [adhoc points | B | B_blinding | G | H] (bpg_vbatch_check; the caller weights the adhoc scalars by rho itself).
+ * out = 32 zero bytes iff the combination is the identity.  A single slot with rho = 1 is that proof's own check. */
+typedef struct bpg_vbatch bpg_vbatch;
+int bpg_vbatch_new(bpg_ctx* ctx, size_t N, size_t capacity, bpg_vbatch** out);
+void bpg_vbatch_free(bpg_vbatch* b);
+int bpg_vbatch_put(bpg_vbatch* b, size_t k, bpg_r1cs_dev* st, const uint8_t bb_scalar[32], const bpg_verify_params* params);
+int bpg_vbatch_check(bpg_vbatch* b, const bpg_table* gens, size_t g_base, size_t h_base, size_t b_id, const uint32_t* idx,
+                     size_t cnt, const uint8_t* rho, const uint8_t* adhoc_points, const uint8_t* adhoc_scalars,
+                     size_t n_adhoc, uint8_t out[32]);
+
 /* grow to `capacity` rows keeping a_L, a_R, a_O, s_L, s_R (second-phase multipliers, prover.rs:501-530) */
 int bpg_r1cs_dev_reserve(bpg_r1cs_dev** st, size_t capacity);
 /* (A_I, A_O, S) of one phase over gens[first .. first+cnt) (prover.rs:465-494, 532-565):

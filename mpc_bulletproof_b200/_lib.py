@@ -148,6 +148,10 @@ _SIGNATURES = {
     "bpg_host_alloc": (_P, [_SZ]),
     "bpg_host_free": (None, [_P]),
     "bpg_r1cs_dev_flatten": (_I, [_P, _SZ, _SZ, _SZ, _P, _P, _P, _P, _P]),
+    "bpg_vbatch_new": (_I, [_P, _SZ, _SZ, _P]),
+    "bpg_vbatch_free": (None, [_P]),
+    "bpg_vbatch_put": (_I, [_P, _SZ, _P, _P, _P]),
+    "bpg_vbatch_check": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _SZ, _P, _P, _P, _SZ, _P]),
     "bpg_r1cs_dev_flatten_terms": (_I, [_P, _SZ, _SZ, _P, _P, _P]),
     "bpg_r1cs_terms_prefetch": (_I, [_P, _P, _I]),
     "bpg_r1cs_dev_poly_t": (_I, [_P, _SZ, _P, _P, _P]),

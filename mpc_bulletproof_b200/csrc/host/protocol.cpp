@@ -1142,7 +1142,18 @@ extern "C" int bpg_prover_prove_deterministic(bpg_cs* cs, uint64_t rng_seed, uin
 // r_bytes == nullptr: r = challenge_scalar("r") as the mounted fork does (verifier.rs:506).  Otherwise r is
 // drawn from a TranscriptRng finalized with r_bytes (upstream's build_rng().finalize(&mut thread_rng())),
 // so that a prover cannot predict the scalar that batches the two checks.
-static int verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_len, const uint8_t* r_bytes) {
+// Everything of Verifier::verify (verifier.rs:393-549) up to the final multiscalar multiplication: the ad-hoc points
+// and their scalars, the parameters of the device scalar preparation, the scalar of B_blinding; the flattened
+// weights are resident in `dv`.  Shared by the single verification and the batch.
+struct VerifyPrep {
+  std::vector<uint8_t> pts;  // n_adhoc x 32: [A_I1 A_O1 S1 A_I2 A_O2 S2 | V_* | T_* | L_* | R_*]
+  std::vector<Scalar> sc;    // their scalars
+  bpg_verify_params vp;
+  Scalar bb;                 // scalar of B_blinding
+  size_t n_adhoc = 0, padded_n = 0;
+};
+static int verifier_prepare(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_len, const uint8_t* r_bytes,
+                            bool prefetch_points, DevGuard& dv, VerifyPrep& out) {
   if (!cs || cs->is_prover || !proof_bytes) return BPG_ERR_ARG;
   R1CSProof proof;
   int rc = R1CSProof::from_bytes(proof_bytes, proof_len, &proof);
@@ -1156,7 +1167,8 @@ static int verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_
   // their doubling chains start beside the transcript replay (bpg_adhoc_prefetch)
   const size_t lg_n = proof.ipp.L_vec.size(), m = cs->V.size();
   const size_t n_adhoc = 6 + m + 5 + 2 * lg_n;
-  std::vector<uint8_t> pts(n_adhoc * 32);
+  std::vector<uint8_t>& pts = out.pts;
+  pts.assign(n_adhoc * 32, 0);
   {
     uint8_t* pp = pts.data();
     auto putp = [&](const uint8_t* p) {
@@ -1178,8 +1190,10 @@ static int verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_
     for (size_t j = 0; j < lg_n; j++) putp(proof.ipp.L_vec[j].data());
     for (size_t j = 0; j < lg_n; j++) putp(proof.ipp.R_vec[j].data());
   }
-  rc = bpg_adhoc_prefetch(cs->ctx, pts.data(), n_adhoc);
-  if (rc) return rc;
+  if (prefetch_points) {
+    rc = bpg_adhoc_prefetch(cs->ctx, pts.data(), n_adhoc);
+    if (rc) return rc;
+  }
   tr.append_u64("m", cs->V.size());
   size_t n1 = cs->num_vars;
   if (!tr.validate_and_append_point("A_I1", proof.A_I1.data())) return BPG_ERR_VERIFY;
@@ -1206,7 +1220,6 @@ static int verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_
   std::vector<Scalar> wV;
   Scalar wc;
   tm.lap("replay");
-  DevGuard dv;
   rc = bpg_r1cs_dev_new(cs->ctx, std::max<size_t>(n, 1), &dv.p);
   if (rc) return rc;
   tm.lap("state");
@@ -1230,7 +1243,8 @@ static int verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_
   }
   Scalar xx = x * x, rxx = r * xx, xxx = x * xx;
   // scalars of the ad-hoc points, in the order of `pts` above
-  std::vector<Scalar> sc;
+  std::vector<Scalar>& sc = out.sc;
+  sc.clear();
   sc.reserve(n_adhoc);
   sc.push_back(x);
   sc.push_back(xx);
@@ -1248,7 +1262,7 @@ static int verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_
   for (size_t j = 0; j < lg_n; j++) sc.push_back(u_inv_sq[j]);
   // y^-i, s, delta = <y^-n o w_R, w_L> (:468-479), g_scalars (:487-491), h_scalars (:493-501) and the
   // scalar of B = w (t_x - a b) + r (x^2 (w_c + delta) - t_x) = c0 + c1 delta (:527-529): device
-  bpg_verify_params vp;
+  bpg_verify_params& vp = out.vp;
   memset(&vp, 0, sizeof vp);
   pow_table(y_inv, vp.y_inv_pow);
   for (size_t j = 0; j < lg_n; j++) memcpy(vp.u_sq[j], u_sq[j].v, 32);
@@ -1264,12 +1278,24 @@ static int verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_
   vp.n = (uint32_t)n;
   vp.n1 = (uint32_t)n1;
   vp.N = (uint32_t)padded_n;
-  uint8_t bb_scalar[32], mega[32];
-  (-proof.e_blinding - r * proof.t_x_blinding).to_bytes(bb_scalar);  // B_blinding
-  std::vector<uint8_t> scb = sc_vec_bytes(sc);
+  out.bb = -proof.e_blinding - r * proof.t_x_blinding;  // B_blinding
+  out.n_adhoc = n_adhoc;
+  out.padded_n = padded_n;
   tm.lap("adhoc scalars");
-  rc = bpg_r1cs_dev_verify_msm(dv.p, g->table, g->g_base(), g->h_base(), g->b_id(), pts.data(), scb.data(), n_adhoc,
-                               bb_scalar, &vp, mega);
+  return BPG_OK;
+}
+static int verifier_verify(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof_len, const uint8_t* r_bytes) {
+  DevGuard dv;
+  VerifyPrep P;
+  int rc = verifier_prepare(cs, proof_bytes, proof_len, r_bytes, true, dv, P);
+  if (rc) return rc;
+  const bpg_gens* g = cs->gens;
+  StageTimer tm("verify");
+  uint8_t bb_scalar[32], mega[32];
+  P.bb.to_bytes(bb_scalar);
+  std::vector<uint8_t> scb = sc_vec_bytes(P.sc);
+  rc = bpg_r1cs_dev_verify_msm(dv.p, g->table, g->g_base(), g->h_base(), g->b_id(), P.pts.data(), scb.data(), P.n_adhoc,
+                               bb_scalar, &P.vp, mega);
   tm.lap("g/h scalars + mega msm");
   if (rc == BPG_ERR_DECODE) return BPG_ERR_DECODE;  // a proof point that is not a valid encoding: FormatError
   if (rc) return rc;
@@ -1295,14 +1321,129 @@ extern "C" int bpg_verifier_verify_with_rng_bytes(bpg_cs* cs, const uint8_t* pro
 // (`Verifier::verify`, verifier.rs:393), so per-proof accept/reject is the parity surface.  Every
 // verifier is consumed.  ok[i] = 1 iff proof i verifies; a malformed proof is a reject, not an
 // error.  Returns non-zero only for failures of the machinery (bad handle, CUDA, memory).
+// One context, one generator set, equal padded sizes: the proofs' final checks are combined.  Every proof k leaves
+// its 2 + 2N generator scalars in a slot on the device; sum_k rho_k * (check_k) with rho_0 = 1 and 128-bit rho_k from
+// the operating system is ONE multiscalar multiplication over [all proof points | B | B_blinding | G | H] instead of
+// one per proof, and it is the identity iff every check is (error 2^-128).  If it is not -- or a point does not
+// decode -- each proof is checked from its own slot, so the per-proof answers are the reference's in every case.
+static int batch_verify_chunk(bpg_cs* const* verifiers, const uint8_t* const* proofs, const size_t* proof_lens, size_t n,
+                              uint8_t* ok) {
+  bpg_ctx* ctx = verifiers[0]->ctx;
+  const bpg_gens* g = verifiers[0]->gens;
+  struct VBGuard {
+    bpg_vbatch* p = nullptr;
+    ~VBGuard() { bpg_vbatch_free(p); }
+  } vb;
+  std::vector<VerifyPrep> preps(n);
+  std::vector<size_t> slot_of;  // proofs that made it into the batch, in slot order
+  size_t N0 = 0;
+  for (size_t i = 0; i < n; i++) {
+    ok[i] = 0;
+    DevGuard dv;
+    int rc = verifier_prepare(verifiers[i], proofs[i], proof_lens[i], nullptr, false, dv, preps[i]);
+    if (rc == BPG_ERR_VERIFY || rc == BPG_ERR_DECODE || rc == BPG_ERR_CAPACITY) continue;  // rejected before the check
+    if (rc) return rc;
+    if (!vb.p) {
+      N0 = preps[i].padded_n;
+      rc = bpg_vbatch_new(ctx, N0, n, &vb.p);
+      if (rc) return rc;
+    }
+    uint8_t bb[32];
+    preps[i].bb.to_bytes(bb);
+    if (preps[i].padded_n != N0) {  // another size: on its own
+      uint8_t mega[32];
+      std::vector<uint8_t> scb = sc_vec_bytes(preps[i].sc);
+      rc = bpg_r1cs_dev_verify_msm(dv.p, g->table, g->g_base(), g->h_base(), g->b_id(), preps[i].pts.data(), scb.data(),
+                                   preps[i].n_adhoc, bb, &preps[i].vp, mega);
+      if (rc == BPG_OK) ok[i] = is_identity_enc(mega) ? 1 : 0;
+      else if (rc != BPG_ERR_DECODE) return rc;
+      continue;
+    }
+    rc = bpg_vbatch_put(vb.p, slot_of.size(), dv.p, bb, &preps[i].vp);
+    if (rc) return rc;
+    slot_of.push_back(i);
+  }
+  if (slot_of.empty()) return BPG_OK;
+  StageTimer tmb("batch");
+  auto check = [&](const std::vector<uint32_t>& slots, const std::vector<Scalar>& rho, uint8_t mega[32]) {
+    std::vector<uint8_t> pts, scb, rb(slots.size() * 32);
+    for (size_t j = 0; j < slots.size(); j++) {
+      const VerifyPrep& P = preps[slot_of[slots[j]]];
+      pts.insert(pts.end(), P.pts.begin(), P.pts.end());
+      for (const Scalar& x : P.sc) {
+        uint8_t b32[32];
+        (x * rho[j]).to_bytes(b32);
+        scb.insert(scb.end(), b32, b32 + 32);
+      }
+      rho[j].to_bytes(rb.data() + 32 * j);
+    }
+    return bpg_vbatch_check(vb.p, g->table, g->g_base(), g->h_base(), g->b_id(), slots.data(), slots.size(), rb.data(),
+                            pts.data(), scb.data(), pts.size() / 32, mega);
+  };
+  // does the random combination of these slots pass?  (a point that does not decode counts as a failure)
+  int err = BPG_OK;
+  auto passes = [&](const std::vector<uint32_t>& slots) {
+    std::vector<Scalar> rho(slots.size());
+    for (size_t j = 0; j < slots.size(); j++) {
+      if (j == 0) {
+        rho[j] = Scalar::one();
+      } else {
+        uint8_t rb[32], lo[32] = {0};
+        if (!os_random(rb)) {
+          err = BPG_ERR_ARG;
+          return false;
+        }
+        memcpy(lo, rb, 16);  // 128 bits
+        rho[j] = Scalar::from_bytes_mod_order(lo);
+      }
+    }
+    uint8_t mega[32];
+    int rc = check(slots, rho, mega);
+    tmb.lap("combined check");
+    if (rc != BPG_OK && rc != BPG_ERR_DECODE) err = rc;
+    return rc == BPG_OK && is_identity_enc(mega);
+  };
+  // `failed`: the combination of exactly these slots is known not to pass.  Halves are tested and the failing ones
+  // split again: one bad proof among n costs about 2 lg n checks instead of n.
+  std::function<void(const std::vector<uint32_t>&, bool)> solve = [&](const std::vector<uint32_t>& slots, bool failed) {
+    if (err) return;
+    if (!failed && passes(slots)) {
+      for (uint32_t j : slots) ok[slot_of[j]] = 1;
+      return;
+    }
+    if (err || slots.size() == 1) return;  // a single slot that does not pass: rejected (ok stays 0)
+    const size_t half = slots.size() / 2;
+    std::vector<uint32_t> lo(slots.begin(), slots.begin() + half), hi(slots.begin() + half, slots.end());
+    const bool lo_ok = passes(lo);
+    if (err) return;
+    if (lo_ok) {
+      for (uint32_t j : lo) ok[slot_of[j]] = 1;
+      solve(hi, true);  // the failure is in the other half
+    } else {
+      solve(lo, true);
+      solve(hi, false);
+    }
+  };
+  std::vector<uint32_t> all(slot_of.size());
+  for (size_t j = 0; j < all.size(); j++) all[j] = (uint32_t)j;
+  solve(all, false);
+  return err;
+}
 extern "C" int bpg_batch_verify(bpg_cs* const* verifiers, const uint8_t* const* proofs, const size_t* proof_lens,
                                 size_t n, uint8_t* ok) {
   if (n && (!verifiers || !proofs || !proof_lens || !ok)) return BPG_ERR_ARG;
-  for (size_t i = 0; i < n; i++) {
-    int rc = bpg_verifier_verify(verifiers[i], proofs[i], proof_lens[i]);
-    if (rc == BPG_OK) ok[i] = 1;
-    else if (rc == BPG_ERR_VERIFY || rc == BPG_ERR_DECODE || rc == BPG_ERR_CAPACITY) ok[i] = 0;
-    else return rc;
+  for (size_t i = 0; i < n; i++)
+    if (!verifiers[i] || verifiers[i]->is_prover || !proofs[i]) return BPG_ERR_ARG;
+  // chunks of proofs that share a context and a generator set; the slots of a chunk stay within ~512 MB
+  size_t i = 0;
+  while (i < n) {
+    const size_t cap = verifiers[i]->gens ? verifiers[i]->gens->cap : 0;
+    const size_t per = std::max<size_t>(1, std::min<size_t>(256, ((size_t)512 << 20) / ((2 * std::max<size_t>(cap, 1) + 2) * 32)));
+    size_t j = i + 1;
+    while (j < n && j - i < per && verifiers[j]->ctx == verifiers[i]->ctx && verifiers[j]->gens == verifiers[i]->gens) j++;
+    int rc = batch_verify_chunk(verifiers + i, proofs + i, proof_lens + i, j - i, ok + i);
+    if (rc) return rc;
+    i = j;
   }
   return BPG_OK;
 }

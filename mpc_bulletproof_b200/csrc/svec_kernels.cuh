@@ -301,6 +301,23 @@ static __global__ void __launch_bounds__(SV_THREADS) k_verify_finish(const uint3
   }
 }
 
+// batch verification: out[i] = sum_j rho_j * slots[idx_j][i] over the (2 + 2N) generator scalars of the chosen proofs
+static __global__ void __launch_bounds__(256) k_vbatch_combine(const uint32_t* __restrict__ slots, size_t stride_words,
+                                                         const uint32_t* __restrict__ idx, uint32_t cnt,
+                                                         const uint32_t* __restrict__ rho /*[cnt][8] canonical*/,
+                                                         uint32_t total, uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  sc acc = sc_zero();
+  for (uint32_t j = 0; j < cnt; j++) {
+    sc x, r;
+    sc_load(x, slots + (size_t)idx[j] * stride_words + (size_t)i * 8);
+    sc_load(r, rho + (size_t)j * 8);
+    acc = sc_add(acc, sc_montmul(x, sc_to_mont(r)));  // canonical * Montgomery -> canonical
+  }
+  sc_store(out + (size_t)i * 8, acc);
+}
+
 // ---- InnerProductProof::verify scalars (inner_product_proof.rs:283-307, 335-351) -----------
 //   g_i = a * s_i * G_factors[i],  h_i = b * s_{N-1-i} * H_factors[i]   (1/s_i = s_{N-1-i})
 struct IppVerifyParams {

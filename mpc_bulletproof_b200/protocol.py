@@ -424,9 +424,11 @@ class Verifier(_CS):
 
 
 def batch_verify(jobs) -> list[bool]:
-    """jobs: [(Verifier with its constraint system built, proof bytes), ...] -> per-proof accept.
-    The reference verifies proof by proof (verifier.rs:393); so does this, in one library call.
-    Across GPUs shard the jobs with `multi.batch_verify_sharded`."""
+    """jobs: [(Verifier with its constraint system built, proof bytes), ...] -> per-proof accept, the answers of
+    the reference's proof-by-proof `Verifier::verify` (verifier.rs:393).  Proofs of equal padded size on one
+    context share ONE multiscalar multiplication (random combination of their checks); a combination that does
+    not pass is split until the failing proofs are isolated.  Across GPUs shard the jobs with
+    `multi.batch_verify_sharded`."""
     n = len(jobs)
     if n == 0:
         return []

@@ -7,7 +7,7 @@ use std::os::raw::{c_char, c_int, c_void};
 macro_rules! opaque {
     ($($name:ident),*) => { $( #[repr(C)] pub struct $name { _private: [u8; 0] } )* };
 }
-opaque!(bpg_ctx, bpg_table, bpg_ipp, bpg_comb, bpg_r1cs_dev, bpg_stark_table, bpg_stark_ipp, bpg_peer, bpg_msm_job);
+opaque!(bpg_ctx, bpg_table, bpg_ipp, bpg_comb, bpg_r1cs_dev, bpg_vbatch, bpg_stark_table, bpg_stark_ipp, bpg_peer, bpg_msm_job);
 
 pub const BPG_OK: c_int = 0;
 pub const BPG_ERR_ARG: c_int = -1;
@@ -167,6 +167,16 @@ extern "C" {
     pub fn bpg_r1cs_dev_flatten(
         st: *mut bpg_r1cs_dev, n: usize, m: usize, n_terms: usize, t_code: *const u32, t_row: *const u32,
         t_coeff: *const c_void, z_pow: *const c_void, wv_out: *mut c_void,
+    ) -> c_int;
+    /// batch verification: the generator scalars of several proofs side by side, combined into one MSM
+    pub fn bpg_vbatch_new(ctx: *mut bpg_ctx, n: usize, capacity: usize, out: *mut *mut bpg_vbatch) -> c_int;
+    pub fn bpg_vbatch_free(b: *mut bpg_vbatch);
+    pub fn bpg_vbatch_put(
+        b: *mut bpg_vbatch, k: usize, st: *mut bpg_r1cs_dev, bb_scalar: *const u8, params: *const bpg_verify_params,
+    ) -> c_int;
+    pub fn bpg_vbatch_check(
+        b: *mut bpg_vbatch, gens: *const bpg_table, g_base: usize, h_base: usize, b_id: usize, idx: *const u32, cnt: usize,
+        rho: *const u8, adhoc_points: *const u8, adhoc_scalars: *const u8, n_adhoc: usize, out: *mut u8,
     ) -> c_int;
     /// flattened_constraints with the +1 / -1 terms in a list of their own (no coefficient stored)
     pub fn bpg_r1cs_dev_flatten_terms(

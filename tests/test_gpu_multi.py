@@ -109,6 +109,67 @@ def test_batch_verify(ctx):
     gens.close()
 
 
+def test_batch_verify_combined(ctx):
+    """Proofs of equal padded size share ONE multiscalar multiplication (sum_k rho_k * check_k); a batch that does not
+    pass -- or holds a point that does not decode -- falls back to each proof's own check, so the per-proof answers
+    are `Verifier::verify`'s (reference src/r1cs/verifier.rs:393-549) in every case.  The oracle decides the truth."""
+    from mpc_bulletproof_b200 import protocol as P
+    from mpc_bulletproof_b200.protocol import Gens
+
+    pc = O.PedersenGens()
+    bp = O.BulletproofGens(16, 1)
+    gens = Gens(ctx, points_bytes(bp.G(16)), points_bytes(bp.H(16)), pc.B.encode(), pc.B_blinding.encode())
+    n = 13  # padded to 16 for every proof
+
+    def circuit(cs, val):
+        cs.square_chain(cs.commit_public(val), n)
+
+    def oracle_accepts(val, proof):
+        ov = O.Verifier(pc, O.Transcript(b"batch2"))
+        var = ov.commit_public(val)
+        for _ in range(n):
+            _, _, var = ov.multiply(var, var)
+        try:
+            ov.verify(O.R1CSProof.from_bytes(proof), bp)
+            return True
+        except (O.VerificationError, O.FormatError, ValueError):
+            return False
+
+    vals = [100 + 7 * k for k in range(10)]
+    proofs = []
+    for k, val in enumerate(vals):
+        p = P.Prover(gens, P.Transcript(b"batch2"))
+        circuit(p, val)
+        proofs.append(p.prove(4000 + k))
+
+    def run(ps):
+        jobs = []
+        for val, pr in zip(vals, ps):
+            v = P.Verifier(gens, P.Transcript(b"batch2"))
+            circuit(v, val)
+            jobs.append((v, pr))
+        return P.batch_verify(jobs)
+
+    # every proof valid: one combined check accepts them all
+    l0 = ctx.launches
+    assert run(proofs) == [True] * len(vals)
+    combined_launches = ctx.launches - l0
+    # a tampered scalar (t_x) in one proof, a point that is not a valid encoding in another
+    bad = list(proofs)
+    b = bytearray(bad[3])
+    b[11 * 32 + 5] ^= 2  # inside t_x (the 12th 32-byte field of R1CSProof::to_bytes)
+    bad[3] = bytes(b)
+    b = bytearray(bad[7])
+    b[0:32] = b"\xff" * 32  # A_I1
+    bad[7] = bytes(b)
+    want = [oracle_accepts(val, pr) for val, pr in zip(vals, bad)]
+    assert want == [k not in (3, 7) for k in range(len(vals))]
+    l0 = ctx.launches
+    assert run(bad) == want
+    assert ctx.launches - l0 > combined_launches  # the fallback ran
+    gens.close()
+
+
 def test_mpc_share_commitments_equal_the_provers(ctx):
     """Config 5 in miniature (reference integration/mpc_prover.rs): two parties hold additive shares
     of the witness rows and of the blinding factors; each commits to its shares over the shared
