@@ -364,6 +364,10 @@ int bpg_r1cs_dev_flatten_terms(bpg_r1cs_dev* st, size_t n, size_t m, const bpg_t
  * rate.  after_commit_uploads != 0 queues the copy behind the witness rows of the next bpg_r1cs_dev_commit* (they
  * are on the prover's critical path and share the bus). */
 int bpg_r1cs_terms_prefetch(bpg_ctx* ctx, const bpg_terms* terms, int after_commit_uploads);
+/* Blocks until a prefetched copy has left the host arrays (and drops a request still waiting for its commitment): call
+ * it before the arrays change or are freed while a prefetch may be in flight -- e.g. before second-phase constraints
+ * are appended (prover.rs:383-402).  The next flatten then names longer arrays and uploads them itself. */
+int bpg_r1cs_terms_wait(bpg_ctx* ctx);
 /* t_1..t_6 (util.rs:152-170) from the resident vectors.  t_out: six canonical scalars. */
 int bpg_r1cs_dev_poly_t(bpg_r1cs_dev* st, size_t n, const void* y_pow, const void* y_inv_pow, uint8_t t_out[192]);
 /* The verifier's mega-MSM (verifier.rs:516-547) with g_scalars, h_scalars and delta computed on

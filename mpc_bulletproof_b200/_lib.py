@@ -154,6 +154,7 @@ _SIGNATURES = {
     "bpg_vbatch_check": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _SZ, _P, _P, _P, _SZ, _P]),
     "bpg_r1cs_dev_flatten_terms": (_I, [_P, _SZ, _SZ, _P, _P, _P]),
     "bpg_r1cs_terms_prefetch": (_I, [_P, _P, _I]),
+    "bpg_r1cs_terms_wait": (_I, [_P]),
     "bpg_r1cs_dev_poly_t": (_I, [_P, _SZ, _P, _P, _P]),
     "bpg_r1cs_dev_verify_msm": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _P, _SZ, _P, _P, _P]),
     "bpg_r1cs_dev_ipp_begin": (_I, [_P, _P, _SZ, _SZ, _SZ, _P, _SZ, _SZ, _SZ, _P, _P, _P, _P, ctypes.POINTER(_P)]),

@@ -676,6 +676,9 @@ struct bpg_cs {
       tr->r1cs_1phase_domain_sep();
       return BPG_OK;
     }
+    // the callbacks append constraints: a prefetch of the first-phase terms must have left the arrays (they may move)
+    int wrc = bpg_r1cs_terms_wait(ctx);
+    if (wrc) return wrc;
     tr->r1cs_2phase_domain_sep();
     randomizing = true;
     auto cbs = std::move(deferred);
@@ -971,6 +974,13 @@ struct DevGuard {  // frees the resident prover state on every exit path
   ~DevGuard() { bpg_r1cs_dev_free(p); }
 };
 
+// a prefetch of the term arrays must not outlive the call that issued it (the arrays belong to the constraint
+// system, which the caller may free right after an early return); after a flatten there is nothing to wait for
+struct TermsGuard {
+  bpg_ctx* ctx;
+  ~TermsGuard() { bpg_r1cs_terms_wait(ctx); }
+};
+
 static int prover_prove(bpg_cs* cs, bool keyed, uint64_t rng_seed, const uint8_t* random_bytes, uint8_t* proof_out,
                         size_t proof_cap, size_t* proof_len) {
   if (!cs || !cs->is_prover || !proof_out || !proof_len) return BPG_ERR_ARG;
@@ -1001,6 +1011,7 @@ static int prover_prove(bpg_cs* cs, bool keyed, uint64_t rng_seed, const uint8_t
   int rc = bpg_r1cs_dev_new(cs->ctx, next_pow2(std::max<size_t>(n1, 1)), &dv.p);
   if (rc) return rc;
   uint8_t c3[96], blind3[96];
+  TermsGuard terms_guard{cs->ctx};
   rc = cs->prefetch_terms(n1 != 0);  // behind the witness rows of the first commitment when there is one
   if (rc) return rc;
   tm.lap("blindings s_L s_R");
@@ -1161,6 +1172,7 @@ static int verifier_prepare(bpg_cs* cs, const uint8_t* proof_bytes, size_t proof
   Transcript& tr = *cs->tr;
   const bpg_gens* g = cs->gens;
   StageTimer tm("verify");
+  TermsGuard terms_guard{cs->ctx};
   rc = cs->prefetch_terms(false);
   if (rc) return rc;
   // every point of the final check (:516-547) is known now: [A_I1 A_O1 S1 A_I2 A_O2 S2 | V_* | T_* | L_* | R_*];

@@ -184,6 +184,8 @@ extern "C" {
     ) -> c_int;
     /// early upload of the constraint terms (they depend on no challenge); consumed by the next flatten
     pub fn bpg_r1cs_terms_prefetch(ctx: *mut bpg_ctx, terms: *const bpg_terms, after_commit_uploads: c_int) -> c_int;
+    /// the prefetched copy has left the host arrays: they may change (second-phase constraints) or be freed
+    pub fn bpg_r1cs_terms_wait(ctx: *mut bpg_ctx) -> c_int;
     /// t_1..t_6, src/util.rs:152-170
     pub fn bpg_r1cs_dev_poly_t(
         st: *mut bpg_r1cs_dev, n: usize, y_pow: *const c_void, y_inv_pow: *const c_void, t_out: *mut u8,
