@@ -531,6 +531,10 @@ int bpg_cs_eval(bpg_cs* cs, const bpg_term* lc, size_t n, uint8_t out[32]);
 /* The reference's benchmark circuit (benches/r1cs.rs:24-32): n chained squarings starting from `var`;
  * equivalent to n calls of bpg_cs_multiply(var, var).  out (may be NULL) = the last output variable. */
 int bpg_gadget_square_chain(bpg_cs* cs, bpg_var var, size_t n, bpg_var* out);
+/* The shuffle gadget of the reference's bench and tests (benches/shuffle.rs:30-69, tests/r1cs.rs:22-63): y[0..k) is a
+ * permutation of x[0..k), by the randomized product check (one deferred callback, 2 (k - 1) multipliers; k = 1: the
+ * constraint y_0 - x_0).  The same constraint system as the callback form built through bpg_cs_*. */
+int bpg_gadget_shuffle(bpg_cs* cs, const bpg_var* x, const bpg_var* y, size_t k);
 /* BASELINE.json config 4: n_mult multipliers with uniform a_L, a_R and n_cons random
  * linear constraints over (a_L, a_R, a_O, v) with constants c0 fixed from the witness; everything from
  * xoshiro256**(seed).  c0: n_cons x 32 bytes, written by the prover, read by the verifier. */

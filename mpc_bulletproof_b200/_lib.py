@@ -79,6 +79,7 @@ _SIGNATURES = {
     "bpg_cs_num_multipliers": (_SZ, [_P]),
     "bpg_gadget_random_circuit": (_I, [_P, ctypes.c_uint64, _SZ, _SZ, _P]),
     "bpg_gadget_square_chain": (_I, [_P, ctypes.c_uint64, _SZ, ctypes.POINTER(ctypes.c_uint64)]),
+    "bpg_gadget_shuffle": (_I, [_P, _P, _P, _SZ]),
     "bpg_cs_num_constraints": (_SZ, [_P]),
     "bpg_prover_prove": (_I, [_P, _P, _SZ, ctypes.POINTER(_SZ)]),
     "bpg_prover_prove_with_rng_bytes": (_I, [_P, _P, _P, _SZ, ctypes.POINTER(_SZ)]),

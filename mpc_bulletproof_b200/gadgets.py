@@ -35,7 +35,14 @@ class LC:
 
 def shuffle_gadget(cs, x, y):
     """reference benches/shuffle.rs:30-69 (tests/r1cs.rs:22-63): y is a permutation of x, through the
-    randomized product check prod (x_i - z) = prod (y_i - z)."""
+    randomized product check prod (x_i - z) = prod (y_i - z).  The library's native form of the gadget
+    (bpg_gadget_shuffle); `shuffle_gadget_callbacks` builds the same system through the callback interface."""
+    cs.shuffle(x, y)
+
+
+def shuffle_gadget_callbacks(cs, x, y):
+    """the same gadget through `specify_randomized_constraints` and per-multiplier calls (what a caller's own
+    gadget code does)"""
     assert len(x) == len(y)
     k = len(x)
     if k == 1:

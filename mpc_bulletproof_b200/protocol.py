@@ -301,6 +301,17 @@ class _CS:
         _raise(lib().bpg_gadget_square_chain(self._h, (_KIND[var[0]] << 56) | idx, n, ctypes.byref(out)))
         return _var(out.value)
 
+    def shuffle(self, x, y):
+        """The shuffle gadget of the reference's bench and tests (benches/shuffle.rs:30-69): y is a permutation
+        of x.  Native (bpg_gadget_shuffle): one library call instead of 2 (k - 1) multiplier calls in a callback."""
+        assert len(x) == len(y) and len(x) >= 1
+        k = len(x)
+
+        def pack(vs):
+            return (ctypes.c_uint64 * k)(*[(_KIND[v[0]] << 56) | (v[1] if len(v) > 1 else 0) for v in vs])
+
+        _raise(lib().bpg_gadget_shuffle(self._h, pack(x), pack(y), k))
+
     def random_circuit(self, seed: int, n_mult: int, n_cons: int, c0: bytes | None = None) -> bytes:
         """BASELINE.json config 4: the synthetic random circuit over the variables committed so far.
         Prover: returns the public constants c0 (n_cons x 32 bytes); verifier: pass them in."""

@@ -567,6 +567,30 @@ def test_config1_shuffle_k64_product_gadget(ctx):
     bad, bic, boc = PG.shuffle_prove(gens, P.Transcript, b"ShuffleBenchmark", inp, bad_out, blinds, rng_seed=641)
     with pytest.raises(P.VerificationError):
         PG.shuffle_verify(gens, P.Transcript, b"ShuffleBenchmark", bad, bic, boc)
+    # the native gadget (bpg_gadget_shuffle) at the small sizes with their own code paths (k = 1: one constraint,
+    # k = 2: no chain), and against the callback form of the same gadget: identical proof bytes
+    for ks in (1, 2, 3, 5):
+        inp = [r.randrange(2**64) for _ in range(ks)]
+        outp = inp[:]
+        r.shuffle(outp)
+        bl = [r.randrange(L) for _ in range(2 * ks)]
+        proof, ic, oc = PG.shuffle_prove(gens, P.Transcript, b"ShuffleBenchmark", inp, outp, bl, rng_seed=700 + ks)
+        otr = O.Transcript(b"ShuffleBenchmark")
+        otr.append_message(b"dom-sep", b"ShuffleProof")
+        otr.append_u64(b"k", ks)
+        op = O.Prover(pc, otr)
+        oic = [op.commit(v, bl[i]) for i, v in enumerate(inp)]
+        ooc = [op.commit(v, bl[ks + i]) for i, v in enumerate(outp)]
+        gadgets.shuffle_gadget(op, [v for _, v in oic], [v for _, v in ooc])
+        assert proof == op.prove(bp, O.Blindings(700 + ks)).to_bytes(), ks
+        PG.shuffle_verify(gens, P.Transcript, b"ShuffleBenchmark", proof, ic, oc)
+        tr = P.Transcript(b"ShuffleBenchmark")
+        tr.append_message(b"dom-sep", b"ShuffleProof")
+        tr.append_u64(b"k", ks)
+        p2 = P.Prover(gens, tr)
+        cv = p2.commit_batch(list(inp) + list(outp), bl)
+        PG.shuffle_gadget_callbacks(p2, [v for _, v in cv[:ks]], [v for _, v in cv[ks:]])
+        assert p2.prove(700 + ks) == proof, ks
     gens.close()
 
 
