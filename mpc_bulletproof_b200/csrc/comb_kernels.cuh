@@ -10,7 +10,9 @@
 //    per entry, built once: k_table_comb_build).
 //  * Rounds over at most a few thousand generators run as ONE accumulation kernel over (term, window) pairs
 //    plus ONE finishing kernel (cross terms, the Q term, the tree over the blocks' partial sums, the two
-//    encodings): k_comb_round / k_comb_final.  Their scalars a_partner * w(i) are formed on the fly.
+//    encodings): k_comb_round / k_comb_final.  Their scalars a_partner * w(i) are formed on the fly, and so is
+//    the fold of a, b and the generator weights that precedes the round (CombRound::fold: the reference's
+//    fold_witness, :224-227, inside the kernel that forms L and R).
 //  * For long vectors the first rounds keep the bucket method over the original generators (no-fold form);
 //    when the vectors have shrunk to m0 entries the folded generators G'_p = sum_{i = p mod m0} w(i) G_i are
 //    MATERIALISED once from the generator combs (k_comb_materialize: the reference's accumulated folds,

@@ -389,7 +389,7 @@ def test_adhoc_prefetch_msm_mixed(ctx):
         rc = lib().bpg_msm_mixed(ctx._h, adhoc, len(adhoc) // 32, tabs, offs, lens, 1, scalars_bytes(ks), out)
         return rc, out.raw
 
-    for n_adhoc in (1, 7, 44, 130):
+    for n_adhoc in (1, 7, 44, 130, 300):  # 300: more than a prefetch holds (256), the plain path
         pts = [rand_point(r) for _ in range(n_adhoc)]
         # edge scalars among the ad-hoc terms: 0, 1, l - 1
         ks = [rand_scalar(r) for _ in range(n_adhoc + n_tab - 8)]
