@@ -162,6 +162,12 @@ BPG_DI sc sc_montmul_inl(const sc& a, const sc& b) {
   // result = t[8..16] < 2l
   return sc_cond_sub_l(t + 8);
 }
+BPG_DI sc sc_sel(bool p, const sc& a, const sc& b) {
+  sc o;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o.v[i] = p ? a.v[i] : b.v[i];
+  return o;
+}
 // out of line in the latency-bound translation units (see fe.cuh, BPG_FE_OUTLINE)
 #if (defined(BPG_FE_OUTLINE) || defined(BPG_GE_OUTLINE)) && defined(__CUDA_ARCH__)
 static __device__ __noinline__ sc sc_montmul_call(sc a, sc b) { return sc_montmul_inl(a, b); }

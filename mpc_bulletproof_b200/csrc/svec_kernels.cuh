@@ -261,9 +261,13 @@ static __global__ void __launch_bounds__(SV_THREADS) k_verify_scalars(const uint
     // s_i = allinv * prod_{bits of i} u^2, s_{N-1-i} the same over the clear bits (inner_product_proof.rs:300-307)
     sc s = sc_param(vp.allinv), srev = s;
     for (uint32_t bit = 0; bit < vp.lg_n; bit++) {
-      sc usq = sc_param(vp.u_sq[(vp.lg_n - 1) - bit]);
-      if ((i >> bit) & 1u) s = sc_montmul(s, usq);
-      else srev = sc_montmul(srev, usq);
+      // every bit multiplies exactly one of the two: ONE product per bit for the whole warp, operand by select
+      // (a branch would make a warp with mixed bits run both sides)
+      const sc usq = sc_param(vp.u_sq[(vp.lg_n - 1) - bit]);
+      const bool set = (i >> bit) & 1u;
+      sc t = sc_montmul(sc_sel(set, s, srev), usq);
+      s = sc_sel(set, t, s);
+      srev = sc_sel(set, srev, t);
     }
     sc yni = sc_pow(vp.y_inv, i);
     sc wl = sc_zero(), wr = sc_zero(), wo = sc_zero();
@@ -331,10 +335,12 @@ static __global__ void __launch_bounds__(256) k_ipp_verify_scalars(const uint32_
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= vp.N) return;
   sc s = sc_param(vp.allinv), srev = s;
-  for (uint32_t bit = 0; bit < vp.lg_n; bit++) {
-    sc usq = sc_param(vp.u_sq[(vp.lg_n - 1) - bit]);
-    if ((i >> bit) & 1u) s = sc_montmul(s, usq);
-    else srev = sc_montmul(srev, usq);
+  for (uint32_t bit = 0; bit < vp.lg_n; bit++) {  // one product per bit, operand by select (see k_verify_scalars)
+    const sc usq = sc_param(vp.u_sq[(vp.lg_n - 1) - bit]);
+    const bool set = (i >> bit) & 1u;
+    sc t = sc_montmul(sc_sel(set, s, srev), usq);
+    s = sc_sel(set, t, s);
+    srev = sc_sel(set, srev, t);
   }
   sc g = sc_montmul(sc_param(vp.a), s), h = sc_montmul(sc_param(vp.b), srev);
   // a canonical factor f times a Montgomery value x R: montmul(xR, f) = x f, already canonical
