@@ -36,7 +36,7 @@ int comb_materialize(bpg_ctx* ctx, cudaStream_t s, const uint32_t* gen_comb, uin
 // on the scalars, so a verifier starts them as soon as it has the proof and its final MSM finds combs.
 int comb_from_points(bpg_ctx* ctx, cudaStream_t s, const uint8_t* d_comp, size_t n, uint32_t* ext, uint32_t* chain,
                      uint32_t* comb, uint32_t* bad) {
-  k_decode_ext<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_comp, (uint32_t)n, ext, bad);
+  k_decode_ext<<<(unsigned)n, 32, 0, s>>>(d_comp, (uint32_t)n, ext, bad);
   LAUNCH_CHECK();
   k_comb_chain<<<(unsigned)((n * 4 + CB_THREADS - 1) / CB_THREADS), CB_THREADS, 0, s>>>(ext, (uint32_t)n, 1, chain);
   LAUNCH_CHECK();

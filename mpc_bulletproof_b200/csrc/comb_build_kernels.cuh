@@ -156,19 +156,30 @@ static __global__ void __launch_bounds__(CB_THREADS) k_comb_multiples(const uint
   }
 }
 
-// compressed -> extended (Z = 1), one thread per point; invalid encodings count in *bad and become the identity
-static __global__ void __launch_bounds__(128) k_decode_ext(const uint8_t* __restrict__ comp, uint32_t n, uint32_t* __restrict__ ext,
-                                                    uint32_t* __restrict__ bad) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// compressed -> extended (Z = 1), one WARP per point on the sixteen-lane field layer (fe16.cuh, whole-warp form): the
+// decoding is an inverse square root, 254 dependent squarings, and it heads the chain a small verification waits for
+// (75 us with a thread per point).  Invalid encodings count in *bad and become the identity.
+static __global__ void __launch_bounds__(32) k_decode_ext(const uint8_t* __restrict__ comp, uint32_t n, uint32_t* __restrict__ ext,
+                                                   uint32_t* __restrict__ bad) {
+  __shared__ __align__(16) uint32_t sm[G16_WORDS];
+  const uint32_t i = blockIdx.x;  // grid = n
   if (i >= n) return;
   uint8_t buf[32];
   for (int k = 0; k < 32; k++) buf[k] = comp[(size_t)i * 32 + k];
+  grp16 g;
+  g.sm = sm;
+  g.k = threadIdx.x & 15u;
+  g.half = (threadIdx.x >> 4) & 1u;
+  g.par = 0;
   ge_ext p;
-  if (!ge_decode(p, buf)) {
-    p = ge_identity();
-    atomicAdd(bad, 1u);
+  const bool ok = ge_decode16<true>(g, buf, p);
+  if (threadIdx.x == 0) {
+    if (!ok) {
+      p = ge_identity();
+      atomicAdd(bad, 1u);
+    }
+    ge_store_ext(ext + (size_t)i * 32, p);
   }
-  ge_store_ext(ext + (size_t)i * 32, p);
 }
 
 }  // namespace bpg

@@ -285,4 +285,67 @@ BPG_DI fe ge_encode16(grp16& g, const ge_ext& p) {
   return fe_canon(fe_cneg(sc, sc.v[0] & 1u));
 }
 
+// RFC 9496 §4.3.1 on a half-warp (or a warp, WIDE): the same steps as ge_decode (ge.cuh), hence the same point and
+// the same verdict.  `in` is replicated in the group's lanes; the extended point (Z = 1) comes back replicated.
+template <bool WIDE>
+BPG_DI bool ge_decode16(grp16& g, const uint8_t in[32], ge_ext& out) {
+  fe s;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    s.v[i] = (uint32_t)in[4 * i] | ((uint32_t)in[4 * i + 1] << 8) | ((uint32_t)in[4 * i + 2] << 16) |
+             ((uint32_t)in[4 * i + 3] << 24);
+  // canonical (s < p) and non-negative
+  fe c = fe_canon(s);
+  uint32_t diff = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) diff |= c.v[i] ^ s.v[i];
+  bool ok = (diff == 0) & ((s.v[0] & 1u) == 0);
+  s = c;  // the arithmetic below wants a reduced operand; a non-canonical input is rejected anyway
+  fe16 zero;
+  zero.l = 0;
+  const fe16 one = fe16_from_fe(g, fe_one());
+  const fe16 I = fe16_from_fe(g, fe_const(BPG_K(K_SQRT_M1)));
+  const fe16 s16 = fe16_from_fe(g, s);
+  fe16 ss = fe16_sq<WIDE>(g, s16);
+  fe16 u1 = fe16_sub(g, one, ss);
+  fe16 u2 = fe16_add(g, one, ss);
+  fe16 u2_sqr = fe16_sq<WIDE>(g, u2);
+  fe16 du1 = fe16_mul<WIDE>(g, fe16_from_fe(g, fe_const(BPG_K(K_D))), fe16_sq<WIDE>(g, u1));
+  fe16 v = fe16_sub(g, fe16_sub(g, zero, du1), u2_sqr);
+  // (was_square, invsqrt) = sqrt_ratio_m1(1, w), w = v u2^2
+  fe16 w = fe16_mul<WIDE>(g, v, u2_sqr);
+  fe16 w3 = fe16_mul<WIDE>(g, fe16_sq<WIDE>(g, w), w);
+  fe16 w7 = fe16_mul<WIDE>(g, fe16_sq<WIDE>(g, w3), w);
+  fe16 r = fe16_mul<WIDE>(g, w3, fe16_pow22523<WIDE>(g, w7));
+  fe check = fe16_to_fe(g, fe16_mul<WIDE>(g, w, fe16_sq<WIDE>(g, r)));
+  const fe p1 = fe_one(), m1 = fe_canon(fe_neg(fe_one())), mi = fe_canon(fe_neg(fe_const(BPG_K(K_SQRT_M1))));
+  uint32_t d0 = 0, d1 = 0, di = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    d0 |= check.v[i] ^ p1.v[i];
+    d1 |= check.v[i] ^ m1.v[i];
+    di |= check.v[i] ^ mi.v[i];
+  }
+  const bool correct = d0 == 0, flipped = d1 == 0, flipped_i = di == 0;
+  r = fe16_sel(flipped | flipped_i, fe16_mul<WIDE>(g, r, I), r);
+  const bool rneg = fe16_to_fe(g, r).v[0] & 1u;
+  fe16 invsqrt = fe16_sel(rneg, fe16_sub(g, zero, r), r);
+  const bool was_square = correct | flipped;
+  fe16 den_x = fe16_mul<WIDE>(g, invsqrt, u2);
+  fe16 den_y = fe16_mul<WIDE>(g, fe16_mul<WIDE>(g, invsqrt, den_x), v);
+  fe16 x = fe16_mul<WIDE>(g, fe16_add(g, s16, s16), den_x);
+  const bool xneg = fe16_to_fe(g, x).v[0] & 1u;
+  x = fe16_sel(xneg, fe16_sub(g, zero, x), x);  // abs
+  fe16 y = fe16_mul<WIDE>(g, u1, den_y);
+  fe16 t = fe16_mul<WIDE>(g, x, y);
+  out.X = fe16_to_fe(g, x);
+  out.Y = fe16_to_fe(g, y);
+  out.Z = fe_one();
+  out.T = fe16_to_fe(g, t);
+  uint32_t ynz = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) ynz |= out.Y.v[i];
+  return ok & was_square & ((out.T.v[0] & 1u) == 0) & (ynz != 0);
+}
+
 }  // namespace bpg

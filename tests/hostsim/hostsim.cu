@@ -193,6 +193,18 @@ void hs_from_uniform(const uint8_t* in64, uint8_t* out32) {
   ge_ext p = ge_add(ge_elligator_map(fe_from_bytes_255(in64)), ge_elligator_map(fe_from_bytes_255(in64 + 32)));
   ge_encode(out32, p);
 }
+int hs_decode16(const uint8_t* b, int wide, uint32_t* ext) {
+  int ok = 0;
+  run_lanes(wide ? 32 : 16, [&](grp16& g) {
+    ge_ext e;
+    bool o = wide ? ge_decode16<true>(g, b, e) : ge_decode16<false>(g, b, e);
+    if (g.k == 7 && g.half == 0) {
+      ste(ext, e);
+      ok = o;
+    }
+  });
+  return ok;
+}
 void hs_encode16(const uint32_t* ext, uint8_t* b) {
   ge_ext e = lde(ext);
   run16([&](grp16& g) {

@@ -209,6 +209,34 @@ def test_encode_on_sixteen_lanes(hs):
                 assert bytes(o2) == want
 
 
+def test_decode_on_sixteen_lanes(hs):
+    """ge_decode16 (fe16.cuh; the verifier's proof points are decoded one per warp before their doubling chains
+    start): the same point and the same verdict as ge_decode on RFC 9496 A.1 multiples, its 28 invalid encodings,
+    random points and random strings; whole-warp form on a few of them."""
+    from tests.test_oracle_group import BAD, MULTIPLES
+
+    r = random.Random(16)
+    cases = [bytes.fromhex(h) for h in MULTIPLES] + [bytes.fromhex(h) for h in BAD]
+    cases += [(r.randrange(G.L) * G.BASEPOINT).encode() for _ in range(12)]
+    cases += [bytes(r.randrange(256) for _ in range(31)) + bytes([r.randrange(128)]) for _ in range(24)]
+    cases += [b"\xff" * 32, b"\x00" * 32, (G.P - 1).to_bytes(32, "little"), (G.P + 2).to_bytes(32, "little")]
+    for i, enc in enumerate(cases):
+        e0, e1 = E32(), E32()
+        ok0 = hs.hs_decode(B32(*enc), e0)
+        ok1 = hs.hs_decode16(B32(*enc), 0, e1)
+        assert ok0 == ok1, enc.hex()
+        def coords(e):  # the same field elements (ge_decode leaves loose representatives, ge_decode16 canonical ones)
+            return [sum(int(e[8 * j + k]) << (32 * k) for k in range(8)) % G.P for j in range(4)]
+
+        if ok0:
+            assert coords(e0) == coords(e1) and _pt(e1).encode() == enc, enc.hex()
+        if i % 9 == 0:  # 32 host threads per run: keep the CPU suite short
+            e2 = E32()
+            assert hs.hs_decode16(B32(*enc), 1, e2) == ok0
+            if ok0:
+                assert coords(e0) == coords(e2)
+
+
 def test_element_derivation(hs):
     """ge_elligator_map / from_uniform_bytes (generator chains, reference src/generators.rs:107-125)
     against the oracle, which RFC 9496 A.3's hash-to-group vectors pin (tests/test_oracle_group.py)."""
