@@ -300,7 +300,7 @@ static int ipp_materialize(bpg_ipp* st) {
 }
 
 // one comb round: accumulation + finish; the encodings of the 2 x lanes sums land in st->out_bytes
-static int ipp_comb_round(bpg_ipp* st, bool external_cross) {
+static int ipp_comb_round(bpg_ipp* st, bool external_cross, uint8_t* out_bytes /*device-visible: where the encodings go*/) {
   bpg_ctx* ctx = st->ctx;
   cudaStream_t s = ctx->stream;
   const size_t n = st->n_eff, m = st->m, h = m / 2;
@@ -375,7 +375,7 @@ static int ipp_comb_round(bpg_ipp* st, bool external_cross) {
   F.q_comb = st->cq_comb;
   F.bias4 = bias_for(4);
   prof_mark(ctx, BPG_PROF_ENCODE);
-  k_comb_final<true><<<sets, CBQ_THREADS, 0, s>>>(F, st->out_bytes, nullptr);
+  k_comb_final<true><<<sets, CBQ_THREADS, 0, s>>>(F, out_bytes, nullptr);
   LAUNCH_CHECK();
   prof_mark(ctx, -1);
   st->cross_ready = false;
@@ -447,13 +447,15 @@ extern "C" int bpg_ipp_round_LR(bpg_ipp* st, uint8_t L[32], uint8_t R[32]) {
     int rc = ipp_materialize(st);
     if (rc) return rc;
   }
+  // The two encodings are written by the finishing kernel straight into page-locked host memory (it is mapped into
+  // the device's address space): the round trip is the kernel and one stream wait, no copy-engine hop in between.
+  uint8_t* host_lr = ctx->h_pinned + 1024;
   if (st->mode == 1) {
-    int rc = ipp_comb_round(st, false);
+    int rc = ipp_comb_round(st, false, host_lr);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->h_pinned, st->out_bytes, 64, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    memcpy(L, ctx->h_pinned, 32);
-    memcpy(R, ctx->h_pinned + 32, 32);
+    memcpy(L, host_lr, 32);
+    memcpy(R, host_lr + 32, 32);
     st->lr_done = true;
     return BPG_OK;
   }
@@ -478,12 +480,11 @@ extern "C" int bpg_ipp_round_LR(bpg_ipp* st, uint8_t L[32], uint8_t R[32]) {
                        st->out_ext, st->tab->win_c, st->tab->n);
   if (rc) return rc;
   if (st->q_sep) CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-  rc = bpg_dev_sum_encode(ctx, st->out_ext, st->q_sep ? 2 : 1, 2, st->out_bytes, nullptr);
+  rc = bpg_dev_sum_encode(ctx, st->out_ext, st->q_sep ? 2 : 1, 2, host_lr, nullptr);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(ctx->h_pinned, st->out_bytes, 64, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  memcpy(L, ctx->h_pinned, 32);
-  memcpy(R, ctx->h_pinned + 32, 32);
+  memcpy(L, host_lr, 32);
+  memcpy(R, host_lr + 32, 32);
   st->lr_done = true;
   return BPG_OK;
 }
@@ -598,7 +599,7 @@ extern "C" int bpg_ipp_round_LR_shares(bpg_ipp* st, const uint8_t* c_L, const ui
   }
   int rc;
   if (st->mode == 1) {
-    rc = ipp_comb_round(st, true);
+    rc = ipp_comb_round(st, true, st->out_bytes);
     if (rc) return rc;
   } else {
     prof_mark(ctx, BPG_PROF_OTHER);
