@@ -319,6 +319,20 @@ impl<'g> R1csDevice<'g> {
         let wc = wv.pop().unwrap();
         Ok((wv, wc))
     }
+    /// The same with the terms in two lists: `unit` terms have coefficient +1, or -1 with bit 31 of the code, and
+    /// carry no coefficient (8 bytes on the bus instead of 40).  Finds the lists resident when `prefetch_terms`
+    /// named the same slices and they have not changed since.
+    pub fn flatten_terms(
+        &mut self, n: usize, m: usize, general: (&[u32], &[u32], &[sys::Mont]), unit: (&[u32], &[u32]), z_pow: &sys::PowTable,
+    ) -> Result<(Vec<sys::Mont>, sys::Mont), Error> {
+        let t = terms_of(general, unit)?;
+        let mut wv = vec![[0u32; 8]; m + 1];
+        check(unsafe {
+            sys::bpg_r1cs_dev_flatten_terms(self.raw, n, m, &t, z_pow.as_ptr() as *const _, wv.as_mut_ptr() as *mut _)
+        })?;
+        let wc = wv.pop().unwrap();
+        Ok((wv, wc))
+    }
     /// t_1..t_6 as canonical scalars (src/util.rs:152-170)
     pub fn poly_t(&mut self, n: usize, y_pow: &sys::PowTable, y_inv_pow: &sys::PowTable) -> Result<[[u8; 32]; 6], Error> {
         let mut t = [[0u8; 32]; 6];
@@ -366,4 +380,44 @@ impl Drop for R1csDevice<'_> {
     fn drop(&mut self) {
         unsafe { sys::bpg_r1cs_dev_free(self.raw) }
     }
+}
+
+fn terms_of(general: (&[u32], &[u32], &[sys::Mont]), unit: (&[u32], &[u32])) -> Result<sys::bpg_terms, Error> {
+    let (t_code, t_row, t_coeff) = general;
+    let (u_code, u_row) = unit;
+    if t_row.len() != t_code.len() || t_coeff.len() != t_code.len() || u_row.len() != u_code.len() {
+        return Err(Error::InvalidInput("vector lengths differ"));
+    }
+    Ok(sys::bpg_terms {
+        n_terms: t_code.len(),
+        t_code: t_code.as_ptr(),
+        t_row: t_row.as_ptr(),
+        t_coeff: t_coeff.as_ptr() as *const _,
+        n_unit: u_code.len(),
+        u_code: u_code.as_ptr(),
+        u_row: u_row.as_ptr(),
+    })
+}
+
+/// Work that depends on no challenge, started before the transcript is replayed.
+/// `ctx` is the context the later calls run on.
+///
+/// # Safety
+/// The slices of `prefetch_terms` must stay alive and unchanged until the matching `flatten_terms`
+/// (or `terms_wait`); page-locked memory (`bpg_host_alloc`) lets the copy run beside other work.
+pub unsafe fn prefetch_terms(
+    ctx: *mut sys::bpg_ctx, general: (&[u32], &[u32], &[sys::Mont]), unit: (&[u32], &[u32]), after_commit_uploads: bool,
+) -> Result<(), Error> {
+    let t = terms_of(general, unit)?;
+    check(sys::bpg_r1cs_terms_prefetch(ctx, &t, after_commit_uploads as std::os::raw::c_int))
+}
+/// The prefetched copy has left the host arrays (call before second-phase constraints are appended).
+pub unsafe fn terms_wait(ctx: *mut sys::bpg_ctx) -> Result<(), Error> {
+    check(sys::bpg_r1cs_terms_wait(ctx))
+}
+/// The points of the verifier's final check (src/r1cs/verifier.rs:516-547), handed over as soon as the proof is
+/// parsed: their doubling chains run beside the transcript replay, and the MSM that later names the same
+/// encodings in the same order adds comb entries instead of running its own double-and-add.
+pub unsafe fn prefetch_points(ctx: *mut sys::bpg_ctx, points: &[[u8; 32]]) -> Result<(), Error> {
+    check(sys::bpg_adhoc_prefetch(ctx, points.as_ptr() as *const u8, points.len()))
 }
